@@ -1,0 +1,379 @@
+"""ctypes harness over the C ABI (include/hg_b200.h). It plays the role of the Rust caller in this container
+(no Rust toolchain here): same object names and call order as the reference
+
+    LassoPreprocessing::preprocess      /root/reference/lasso/src/lasso.rs:527-627
+    LassoNode::new / prove_claim_reduction   /root/reference/lasso/src/lasso.rs:143-154, :57-114
+    Keccak256Transcript                 /root/reference/bfv-gkr/src/transcript.rs:117-203
+
+There is NO CPU fallback: if the CUDA library is missing or no GPU is present every compute call raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+GOLDILOCKS, BN254 = 0, 1
+MODE_PREFETCH, MODE_INTERACTIVE = 0, 1
+OPT_A3_WIRE, OPT_A3_H1, OPT_A5_ASCENDING = 3, 31, 5
+LIMBS = {GOLDILOCKS: 1, BN254: 4}
+DEGREE = {GOLDILOCKS: 2, BN254: 1}
+
+# every symbol include/hg_b200.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "hg_last_error", "hg_version", "hg_ctx_create", "hg_ctx_destroy", "hg_ctx_set_option", "hg_ctx_synchronize", "hg_ctx_launch_count",
+    "hg_ctx_stream", "hg_buf_alloc", "hg_buf_upload", "hg_buf_download", "hg_buf_device_ptr", "hg_buf_size", "hg_buf_free",
+    "hg_transcript_new", "hg_transcript_from_proof", "hg_transcript_free", "hg_transcript_squeeze_challenge", "hg_transcript_write_felt_ext",
+    "hg_transcript_read_felt_ext", "hg_transcript_proof_len", "hg_transcript_proof_copy", "hg_transcript_num_squeezed",
+    "hg_lasso_preprocess", "hg_lasso_pp_free", "hg_lasso_pp_num_lookups", "hg_lasso_pp_num_subtables", "hg_lasso_pp_num_memories",
+    "hg_lasso_pp_lookup_index", "hg_lasso_pp_memory_maps", "hg_lasso_pp_subtable_id", "hg_lasso_node_new", "hg_lasso_node_free",
+    "hg_lasso_node_log2_input_size", "hg_lasso_node_device_bytes", "hg_lasso_node_prove", "hg_lasso_node_download_polys",
+    "hg_lasso_node_num_chunks", "hg_sumcheck_prove", "hg_mle_eval_batch", "hg_field_selftest",
+]
+
+_lib = None
+
+
+class HgError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads hyper-greco_b200/lib/libhg_b200.so (built by build.py). Raises if it is missing: no fallback."""
+    global _lib
+    if _lib is None:
+        path = _build.LIB
+        if not os.path.exists(path):
+            raise HgError(f"{path} is missing: run __graft_entry__.build() (nvcc, sm_100a). There is no CPU fallback.")
+        L = C.CDLL(path)
+        vp, sz, i32, u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64
+        L.hg_last_error.restype = C.c_char_p
+        L.hg_ctx_create.argtypes = [i32, i32, C.POINTER(vp)]
+        L.hg_ctx_destroy.argtypes = [vp]
+        L.hg_ctx_set_option.argtypes = [vp, i32, i32]
+        L.hg_ctx_synchronize.argtypes = [vp]
+        L.hg_ctx_launch_count.argtypes = [vp]
+        L.hg_ctx_launch_count.restype = u64
+        L.hg_ctx_stream.argtypes = [vp]
+        L.hg_ctx_stream.restype = vp
+        L.hg_buf_alloc.argtypes = [vp, sz, C.POINTER(vp)]
+        L.hg_buf_upload.argtypes = [vp, vp, sz, vp, sz]
+        L.hg_buf_download.argtypes = [vp, vp, sz, vp, sz]
+        L.hg_buf_device_ptr.argtypes = [vp]
+        L.hg_buf_device_ptr.restype = vp
+        L.hg_buf_size.argtypes = [vp]
+        L.hg_buf_size.restype = sz
+        L.hg_buf_free.argtypes = [vp]
+        L.hg_transcript_new.argtypes = [i32, C.POINTER(vp)]
+        L.hg_transcript_from_proof.argtypes = [i32, vp, sz, C.POINTER(vp)]
+        L.hg_transcript_free.argtypes = [vp]
+        L.hg_transcript_squeeze_challenge.argtypes = [vp, vp]
+        L.hg_transcript_write_felt_ext.argtypes = [vp, vp]
+        L.hg_transcript_read_felt_ext.argtypes = [vp, vp]
+        L.hg_transcript_proof_len.argtypes = [vp]
+        L.hg_transcript_proof_len.restype = sz
+        L.hg_transcript_proof_copy.argtypes = [vp, vp, sz]
+        L.hg_transcript_num_squeezed.argtypes = [vp]
+        L.hg_transcript_num_squeezed.restype = sz
+        L.hg_lasso_preprocess.argtypes = [vp, sz, sz, sz, C.POINTER(vp)]
+        L.hg_lasso_pp_free.argtypes = [vp]
+        for f in ("hg_lasso_pp_num_lookups", "hg_lasso_pp_num_subtables", "hg_lasso_pp_num_memories"):
+            getattr(L, f).argtypes = [vp]
+            getattr(L, f).restype = sz
+        L.hg_lasso_pp_lookup_index.argtypes = [vp, u64]
+        L.hg_lasso_pp_memory_maps.argtypes = [vp, vp, vp]
+        L.hg_lasso_pp_subtable_id.argtypes = [vp, sz, vp, sz]
+        L.hg_lasso_node_new.argtypes = [vp, vp, sz, vp, vp, sz, C.POINTER(vp)]
+        L.hg_lasso_node_free.argtypes = [vp]
+        for f in ("hg_lasso_node_log2_input_size", "hg_lasso_node_device_bytes", "hg_lasso_node_num_chunks"):
+            getattr(L, f).argtypes = [vp]
+            getattr(L, f).restype = sz
+        L.hg_lasso_node_prove.argtypes = [vp, vp, sz, i32, vp, i32, vp, vp]
+        L.hg_lasso_node_download_polys.argtypes = [vp, vp, vp, vp, vp]
+        L.hg_sumcheck_prove.argtypes = [vp, i32, sz, sz, vp, vp, vp, vp, i32, vp, vp]
+        L.hg_mle_eval_batch.argtypes = [vp, vp, sz, sz, sz, vp, vp]
+        L.hg_field_selftest.argtypes = [vp, i32, vp, vp, sz, vp]
+        _lib = L
+    return _lib
+
+
+def _chk(rc):
+    if rc != 0:
+        raise HgError(lib().hg_last_error().decode())
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Context:
+    """One device + one stream (hg_ctx)."""
+
+    def __init__(self, device=0, field=GOLDILOCKS):
+        self.field = field
+        self.h = C.c_void_p()
+        _chk(lib().hg_ctx_create(device, field, C.byref(self.h)))
+
+    def set_option(self, option, value):
+        _chk(lib().hg_ctx_set_option(self.h, option, value))
+
+    def synchronize(self):
+        _chk(lib().hg_ctx_synchronize(self.h))
+
+    @property
+    def launch_count(self):
+        return int(lib().hg_ctx_launch_count(self.h))
+
+    @property
+    def stream(self):
+        return lib().hg_ctx_stream(self.h)
+
+    def close(self):
+        if self.h:
+            lib().hg_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceBuffer:
+    """hg_buf: device memory owned by the caller through a handle."""
+
+    def __init__(self, ctx: Context, nbytes: int):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        _chk(lib().hg_buf_alloc(ctx.h, nbytes, C.byref(self.h)))
+        self.nbytes = nbytes
+
+    @classmethod
+    def from_numpy(cls, ctx, arr):
+        arr = np.ascontiguousarray(arr)
+        b = cls(ctx, arr.nbytes)
+        b.upload(arr)
+        return b
+
+    def upload(self, arr, offset=0):
+        arr = np.ascontiguousarray(arr)
+        _chk(lib().hg_buf_upload(self.ctx.h, self.h, offset, _p(arr), arr.nbytes))
+
+    def download(self, dtype, count, offset=0):
+        out = np.zeros(count, dtype)
+        _chk(lib().hg_buf_download(self.ctx.h, self.h, offset, _p(out), out.nbytes))
+        return out
+
+    @property
+    def ptr(self):
+        return lib().hg_buf_device_ptr(self.h)
+
+    def free(self):
+        if self.h:
+            lib().hg_buf_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Keccak256Transcript:
+    """transcript.rs:117-203."""
+
+    def __init__(self, field=GOLDILOCKS, proof: bytes = None):
+        self.field = field
+        self.h = C.c_void_p()
+        self._el = LIMBS[field] * DEGREE[field]
+        if proof is None:
+            _chk(lib().hg_transcript_new(field, C.byref(self.h)))
+        else:
+            buf = np.frombuffer(proof, np.uint8)
+            _chk(lib().hg_transcript_from_proof(field, _p(np.ascontiguousarray(buf)), buf.size, C.byref(self.h)))
+
+    @classmethod
+    def from_proof(cls, proof: bytes, field=GOLDILOCKS):
+        return cls(field, proof)
+
+    def squeeze_challenge(self):
+        out = np.zeros(self._el, np.uint64)
+        _chk(lib().hg_transcript_squeeze_challenge(self.h, _p(out)))
+        return out
+
+    def squeeze_challenges(self, n):
+        return np.stack([self.squeeze_challenge() for _ in range(n)]) if n else np.zeros((0, self._el), np.uint64)
+
+    def write_felt_ext(self, e):
+        _chk(lib().hg_transcript_write_felt_ext(self.h, _p(np.ascontiguousarray(e, np.uint64))))
+
+    def read_felt_ext(self):
+        out = np.zeros(self._el, np.uint64)
+        _chk(lib().hg_transcript_read_felt_ext(self.h, _p(out)))
+        return out
+
+    def into_proof(self) -> bytes:
+        n = lib().hg_transcript_proof_len(self.h)
+        out = np.zeros(max(n, 1), np.uint8)
+        _chk(lib().hg_transcript_proof_copy(self.h, _p(out), n))
+        return out[:n].tobytes()
+
+    @property
+    def num_squeezed(self):
+        return int(lib().hg_transcript_num_squeezed(self.h))
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().hg_transcript_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class LassoPreprocessing:
+    """lasso.rs:513-651 for RangeLookup types given by their bounds."""
+
+    def __init__(self, bounds, C_=4, M=1 << 16):
+        b = np.array([int(x) for x in bounds], np.uint64)
+        self.h = C.c_void_p()
+        _chk(lib().hg_lasso_preprocess(_p(b), b.size, C_, M, C.byref(self.h)))
+        self.C, self.M = C_, M
+
+    @classmethod
+    def preprocess(cls, bounds, C_=4, M=1 << 16):
+        return cls(bounds, C_, M)
+
+    @property
+    def num_lookups(self):
+        return int(lib().hg_lasso_pp_num_lookups(self.h))
+
+    @property
+    def num_subtables(self):
+        return int(lib().hg_lasso_pp_num_subtables(self.h))
+
+    @property
+    def num_memories(self):
+        return int(lib().hg_lasso_pp_num_memories(self.h))
+
+    def lookup_index(self, bound):
+        return int(lib().hg_lasso_pp_lookup_index(self.h, int(bound)))
+
+    def memory_maps(self):
+        m = self.num_memories
+        a, b = np.zeros(m, np.uint32), np.zeros(m, np.uint32)
+        _chk(lib().hg_lasso_pp_memory_maps(self.h, _p(a), _p(b)))
+        return [int(x) for x in a], [int(x) for x in b]
+
+    def subtable_id(self, idx):
+        buf = C.create_string_buffer(64)
+        _chk(lib().hg_lasso_pp_subtable_id(self.h, idx, buf, 64))
+        return buf.value.decode()
+
+    def memory_names(self):
+        sub, dim = self.memory_maps()
+        return [f"{self.subtable_id(s)}@{d}" for s, d in zip(sub, dim)]
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().hg_lasso_pp_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class LassoNode:
+    """LassoNode<F, E, C, M> (lasso.rs:32-154) on one device."""
+
+    def __init__(self, ctx: Context, preprocessing: LassoPreprocessing, num_vars: int, lookup_segments):
+        """lookup_segments: [(bound, run_length), ...] = the node's `lookups: Vec<LookupId>` run-length encoded."""
+        self.ctx, self.pp, self.num_vars = ctx, preprocessing, num_vars
+        sb = np.array([int(b) for b, _ in lookup_segments], np.uint64)
+        sl = np.array([int(l) for _, l in lookup_segments], np.uint64)
+        self.h = C.c_void_p()
+        _chk(lib().hg_lasso_node_new(ctx.h, preprocessing.h, num_vars, _p(sb), _p(sl), sb.size, C.byref(self.h)))
+        self._el = LIMBS[ctx.field] * DEGREE[ctx.field]
+
+    def is_input(self):
+        return False  # lasso.rs:41-43
+
+    def log2_input_size(self):
+        return int(lib().hg_lasso_node_log2_input_size(self.h))  # lasso.rs:45-47
+
+    def log2_output_size(self):
+        return 0  # lasso.rs:49-51
+
+    @property
+    def device_bytes(self):
+        return int(lib().hg_lasso_node_device_bytes(self.h))
+
+    @property
+    def num_chunks(self):
+        return int(lib().hg_lasso_node_num_chunks(self.h))
+
+    def prove_claim_reduction(self, inputs, transcript: Keccak256Transcript, mode=MODE_PREFETCH, n_inputs=None):
+        """inputs: numpy uint64 array of canonical limbs (host; copied inside the call) or a DeviceBuffer.
+        Returns the node's single EvalClaim (point limbs [num_vars, el], value limbs [el])."""
+        pt = np.zeros((self.num_vars, self._el), np.uint64)
+        val = np.zeros(self._el, np.uint64)
+        if isinstance(inputs, DeviceBuffer):
+            n = n_inputs if n_inputs is not None else inputs.nbytes // (8 * LIMBS[self.ctx.field])
+            _chk(lib().hg_lasso_node_prove(self.h, inputs.ptr, n, 1, transcript.h, mode, _p(pt), _p(val)))
+        else:
+            arr = np.ascontiguousarray(inputs, np.uint64)
+            n = arr.size // LIMBS[self.ctx.field]
+            _chk(lib().hg_lasso_node_prove(self.h, _p(arr), n, 0, transcript.h, mode, _p(pt), _p(val)))
+        return pt, val
+
+    def download_polys(self):
+        R, M, m, nc = 1 << self.num_vars, self.pp.M, self.pp.num_memories, self.num_chunks
+        dims = np.zeros((self.pp.C, R), np.uint16)
+        rd = np.zeros((nc, R), np.uint32)
+        fc = np.zeros((nc, M), np.uint32)
+        e = np.zeros((m, R, LIMBS[self.ctx.field]), np.uint64)
+        _chk(lib().hg_lasso_node_download_polys(self.h, _p(dims), _p(rd), _p(fc), _p(e)))
+        return dims, rd, fc, e
+
+    def free(self):
+        if self.h:
+            lib().hg_lasso_node_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def sumcheck_prove(ctx: Context, arity, coeffs_ext, d_tables: DeviceBuffer, num_vars, claim_ext, transcript, mode=MODE_PREFETCH):
+    """gkr::sum_check::prove_sum_check for g = poly(0) * sum_i coeffs[i] * prod_{k<arity} poly(arity*i+k)."""
+    el = LIMBS[ctx.field] * DEGREE[ctx.field]
+    coeffs_ext = np.ascontiguousarray(coeffs_ext, np.uint64)
+    nterms = coeffs_ext.size // el
+    pt = np.zeros((num_vars, el), np.uint64)
+    ev = np.zeros((nterms * arity, el), np.uint64)
+    _chk(lib().hg_sumcheck_prove(ctx.h, arity, nterms, num_vars, _p(coeffs_ext), d_tables.ptr, _p(np.ascontiguousarray(claim_ext, np.uint64)),
+                                 transcript.h, mode, _p(pt), _p(ev)))
+    return pt, ev
+
+
+def mle_eval_batch(ctx: Context, d_tables: DeviceBuffer, n_tables, num_vars, point_ext, stride=None):
+    el = LIMBS[ctx.field] * DEGREE[ctx.field]
+    out = np.zeros((n_tables, el), np.uint64)
+    stride = (1 << num_vars) if stride is None else stride
+    _chk(lib().hg_mle_eval_batch(ctx.h, d_tables.ptr, n_tables, stride, num_vars, _p(np.ascontiguousarray(point_ext, np.uint64)), _p(out)))
+    return out
+
+
+def field_selftest(ctx: Context, op, a_ext, b_ext):
+    a = np.ascontiguousarray(a_ext, np.uint64)
+    b = np.ascontiguousarray(b_ext, np.uint64)
+    el = LIMBS[ctx.field] * DEGREE[ctx.field]
+    out = np.zeros_like(a)
+    _chk(lib().hg_field_selftest(ctx.h, op, _p(a), _p(b), a.size // el, _p(out)))
+    return out

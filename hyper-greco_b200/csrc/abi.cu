@@ -1,0 +1,345 @@
+// extern "C" boundary (include/hg_b200.h). Translates handles + limb arrays to the templated C++/CUDA implementation
+// and turns every exception into an error code + message.
+#include "../../include/hg_b200.h"
+
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "prover.cuh"
+
+using namespace hg;
+
+namespace {
+thread_local std::string g_err;
+int fail(const std::string& m) { g_err = m; return 1; }
+#define HG_TRY(...)                                                             \
+    try { __VA_ARGS__; return 0; }                                              \
+    catch (const std::exception& e) { cudaGetLastError(); return fail(e.what()); } \
+    catch (...) { cudaGetLastError(); return fail("unknown error"); }
+
+template <class FP> __global__ void k_selftest(int op, const typename FP::X* a, const typename FP::X* b, size_t n, typename FP::X* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    typename FP::X x = a[i], y = b[i], z;
+    if (op == 0) z = FP::x_add(x, y);
+    else if (op == 1) z = FP::x_sub(x, y);
+    else z = FP::x_mul(x, y);
+    out[i] = z;
+}
+}  // namespace
+
+struct hg_ctx {
+    DeviceCtx dev;
+    int field_id;
+    WireOptions wire;
+};
+struct hg_buf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int device = 0;
+};
+struct hg_transcript {
+    int field_id;
+    std::unique_ptr<Keccak256Transcript<GlField>> gl;
+};
+struct hg_lasso_pp {
+    LassoPreprocessing pp;
+    std::vector<uint64_t> lookup_bounds;  // in preprocessing order
+};
+struct hg_lasso_node {
+    hg_ctx* ctx;
+    std::unique_ptr<LassoNodeDev<GlField>> gl;
+    DevBuf<u64> staging;  // device copy of host inputs
+    size_t log2_input_size = 0;
+};
+
+static void need_gl(int field_id) {
+    if (field_id != HG_FIELD_GOLDILOCKS) throw std::runtime_error("field not supported by this build (only HG_FIELD_GOLDILOCKS)");
+}
+
+extern "C" {
+
+const char* hg_last_error(void) { return g_err.c_str(); }
+int hg_version(void) { return 1; }
+
+int hg_ctx_create(int device, int field_id, hg_ctx** out) {
+    HG_TRY({
+        need_gl(field_id);
+        int n = 0;
+        HG_CUDA(cudaGetDeviceCount(&n));
+        if (device < 0 || device >= n) throw std::runtime_error("no such CUDA device");
+        HG_CUDA(cudaSetDevice(device));
+        std::unique_ptr<hg_ctx> c(new hg_ctx());
+        c->dev.device = device;
+        c->field_id = field_id;
+        HG_CUDA(cudaStreamCreateWithFlags(&c->dev.stream, cudaStreamNonBlocking));
+        HG_CUDA(cudaDeviceGetAttribute(&c->dev.sm_count, cudaDevAttrMultiProcessorCount, device));
+        *out = c.release();
+    })
+}
+void hg_ctx_destroy(hg_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->dev.device);
+    if (ctx->dev.stream) cudaStreamDestroy(ctx->dev.stream);
+    delete ctx;
+}
+int hg_ctx_set_option(hg_ctx* ctx, int option, int value) {
+    HG_TRY({
+        if (option == HG_OPT_A3_WIRE) ctx->wire.a3_wire = value;
+        else if (option == HG_OPT_A3_H1) ctx->wire.a3_h1 = value;
+        else if (option == HG_OPT_A5_ASCENDING) ctx->wire.a5_ascending = value;
+        else throw std::runtime_error("unknown option");
+    })
+}
+int hg_ctx_synchronize(hg_ctx* ctx) { HG_TRY({ HG_CUDA(cudaSetDevice(ctx->dev.device)); HG_CUDA(cudaStreamSynchronize(ctx->dev.stream)); }) }
+uint64_t hg_ctx_launch_count(hg_ctx* ctx) { return ctx->dev.launches; }
+void* hg_ctx_stream(hg_ctx* ctx) { return (void*)ctx->dev.stream; }
+
+int hg_buf_alloc(hg_ctx* ctx, size_t bytes, hg_buf** out) {
+    HG_TRY({
+        HG_CUDA(cudaSetDevice(ctx->dev.device));
+        std::unique_ptr<hg_buf> b(new hg_buf());
+        HG_CUDA(cudaMalloc(&b->p, bytes ? bytes : 1));
+        b->bytes = bytes;
+        b->device = ctx->dev.device;
+        *out = b.release();
+    })
+}
+int hg_buf_upload(hg_ctx* ctx, hg_buf* buf, size_t offset, const void* host, size_t bytes) {
+    HG_TRY({
+        if (offset + bytes > buf->bytes) throw std::runtime_error("hg_buf_upload: out of range");
+        HG_CUDA(cudaSetDevice(ctx->dev.device));
+        HG_CUDA(cudaMemcpyAsync((char*)buf->p + offset, host, bytes, cudaMemcpyHostToDevice, ctx->dev.stream));
+        HG_CUDA(cudaStreamSynchronize(ctx->dev.stream));
+    })
+}
+int hg_buf_download(hg_ctx* ctx, const hg_buf* buf, size_t offset, void* host, size_t bytes) {
+    HG_TRY({
+        if (offset + bytes > buf->bytes) throw std::runtime_error("hg_buf_download: out of range");
+        HG_CUDA(cudaSetDevice(ctx->dev.device));
+        HG_CUDA(cudaMemcpyAsync(host, (const char*)buf->p + offset, bytes, cudaMemcpyDeviceToHost, ctx->dev.stream));
+        HG_CUDA(cudaStreamSynchronize(ctx->dev.stream));
+    })
+}
+void* hg_buf_device_ptr(hg_buf* buf) { return buf->p; }
+size_t hg_buf_size(const hg_buf* buf) { return buf->bytes; }
+void hg_buf_free(hg_buf* buf) {
+    if (!buf) return;
+    cudaSetDevice(buf->device);
+    cudaFree(buf->p);
+    delete buf;
+}
+
+// ---- transcript
+int hg_transcript_new(int field_id, hg_transcript** out) {
+    HG_TRY({
+        need_gl(field_id);
+        std::unique_ptr<hg_transcript> t(new hg_transcript());
+        t->field_id = field_id;
+        t->gl.reset(new Keccak256Transcript<GlField>());
+        *out = t.release();
+    })
+}
+int hg_transcript_from_proof(int field_id, const uint8_t* proof, size_t len, hg_transcript** out) {
+    HG_TRY({
+        need_gl(field_id);
+        std::unique_ptr<hg_transcript> t(new hg_transcript());
+        t->field_id = field_id;
+        t->gl.reset(new Keccak256Transcript<GlField>(proof, len));
+        *out = t.release();
+    })
+}
+void hg_transcript_free(hg_transcript* t) { delete t; }
+int hg_transcript_squeeze_challenge(hg_transcript* t, uint64_t* out_ext) { HG_TRY({ GlField::x_to_limbs(t->gl->squeeze_challenge(), out_ext); }) }
+int hg_transcript_write_felt_ext(hg_transcript* t, const uint64_t* ext) { HG_TRY({ t->gl->write_felt_ext(GlField::x_from_limbs(ext)); }) }
+int hg_transcript_read_felt_ext(hg_transcript* t, uint64_t* out_ext) { HG_TRY({ GlField::x_to_limbs(t->gl->read_felt_ext(), out_ext); }) }
+size_t hg_transcript_proof_len(const hg_transcript* t) { return t->gl->proof().size(); }
+int hg_transcript_proof_copy(const hg_transcript* t, uint8_t* out, size_t cap) {
+    HG_TRY({
+        auto& p = t->gl->proof();
+        if (p.size() > cap) throw std::runtime_error("hg_transcript_proof_copy: buffer too small");
+        memcpy(out, p.data(), p.size());
+    })
+}
+size_t hg_transcript_num_squeezed(const hg_transcript* t) { return t->gl->num_base_squeezed(); }
+
+// ---- preprocessing
+int hg_lasso_preprocess(const uint64_t* bounds, size_t n_bounds, size_t C, size_t M, hg_lasso_pp** out) {
+    HG_TRY({
+        if (M < 2 || (M & (M - 1))) throw std::runtime_error("M must be a power of two >= 2");
+        std::vector<std::shared_ptr<LookupType>> lk;
+        for (size_t i = 0; i < n_bounds; i++) lk.push_back(std::make_shared<RangeLookup>(bounds[i]));
+        std::unique_ptr<hg_lasso_pp> h(new hg_lasso_pp());
+        h->pp = LassoPreprocessing::preprocess(lk, C, M);
+        for (auto& l : h->pp.lookups) h->lookup_bounds.push_back(static_cast<RangeLookup*>(l.get())->bound());
+        *out = h.release();
+    })
+}
+void hg_lasso_pp_free(hg_lasso_pp* pp) { delete pp; }
+size_t hg_lasso_pp_num_lookups(const hg_lasso_pp* pp) { return pp->pp.lookups.size(); }
+size_t hg_lasso_pp_num_subtables(const hg_lasso_pp* pp) { return pp->pp.subtables_by_idx.size(); }
+size_t hg_lasso_pp_num_memories(const hg_lasso_pp* pp) { return pp->pp.num_memories; }
+int hg_lasso_pp_lookup_index(const hg_lasso_pp* pp, uint64_t bound) {
+    auto it = pp->pp.lookup_id_to_index.find(RangeLookup::id_for(bound));
+    return it == pp->pp.lookup_id_to_index.end() ? -1 : (int)it->second;
+}
+int hg_lasso_pp_memory_maps(const hg_lasso_pp* pp, uint32_t* mem_to_subtable, uint32_t* mem_to_dimension) {
+    HG_TRY({
+        for (size_t i = 0; i < pp->pp.num_memories; i++) {
+            if (mem_to_subtable) mem_to_subtable[i] = (uint32_t)pp->pp.memory_to_subtable_index[i];
+            if (mem_to_dimension) mem_to_dimension[i] = (uint32_t)pp->pp.memory_to_dimension_index[i];
+        }
+    })
+}
+int hg_lasso_pp_subtable_id(const hg_lasso_pp* pp, size_t idx, char* out, size_t cap) {
+    HG_TRY({
+        if (idx >= pp->pp.subtables_by_idx.size()) throw std::runtime_error("subtable index out of range");
+        std::string id = pp->pp.subtables_by_idx[idx]->subtable_id();
+        if (id.size() + 1 > cap) throw std::runtime_error("buffer too small");
+        memcpy(out, id.c_str(), id.size() + 1);
+    })
+}
+
+// ---- node
+int hg_lasso_node_new(hg_ctx* ctx, const hg_lasso_pp* pp, size_t num_vars, const uint64_t* seg_bounds, const uint64_t* seg_lens, size_t n_segs,
+                      hg_lasso_node** out) {
+    HG_TRY({
+        HG_CUDA(cudaSetDevice(ctx->dev.device));
+        if (num_vars < 1 || num_vars > 30) throw std::runtime_error("num_vars out of range");
+        std::vector<uint8_t> rows;
+        for (size_t s = 0; s < n_segs; s++) {
+            int li = hg_lasso_pp_lookup_index(pp, seg_bounds[s]);
+            if (li < 0) throw std::runtime_error("lookup id " + RangeLookup::id_for(seg_bounds[s]) + " not in preprocessing");
+            rows.insert(rows.end(), seg_lens[s], (uint8_t)li);
+        }
+        std::unique_ptr<hg_lasso_node> n(new hg_lasso_node());
+        n->ctx = ctx;
+        n->gl.reset(new LassoNodeDev<GlField>(&ctx->dev, pp->pp, (int)num_vars, rows));
+        n->log2_input_size = std::max<size_t>(num_vars, ilog2u(pp->pp.M));  // lasso.rs:45-47
+        *out = n.release();
+    })
+}
+void hg_lasso_node_free(hg_lasso_node* node) {
+    if (!node) return;
+    cudaSetDevice(node->ctx->dev.device);
+    delete node;
+}
+size_t hg_lasso_node_log2_input_size(const hg_lasso_node* node) { return node->log2_input_size; }
+size_t hg_lasso_node_device_bytes(const hg_lasso_node* node) { return node->gl->device_bytes(); }
+size_t hg_lasso_node_num_chunks(const hg_lasso_node* node) { return node->gl->chunk_dims().size(); }
+
+int hg_lasso_node_prove(hg_lasso_node* node, const void* inputs, size_t n_inputs, int inputs_on_device, hg_transcript* t, int mode,
+                        uint64_t* out_point, uint64_t* out_value) {
+    HG_TRY({
+        hg_ctx* ctx = node->ctx;
+        HG_CUDA(cudaSetDevice(ctx->dev.device));
+        const u64* d_in = (const u64*)inputs;
+        if (!inputs_on_device) {
+            if (node->staging.n < n_inputs) node->staging.alloc(n_inputs);
+            HG_CUDA(cudaMemcpyAsync(node->staging.p, inputs, n_inputs * sizeof(u64), cudaMemcpyHostToDevice, ctx->dev.stream));
+            d_in = node->staging.p;
+        }
+        std::vector<gl2> pt;
+        gl2 val;
+        node->gl->prove(d_in, n_inputs, *t->gl, mode == HG_MODE_INTERACTIVE ? kModeInteractive : kModePrefetch, ctx->wire, &pt, &val);
+        if (out_point) for (size_t i = 0; i < pt.size(); i++) GlField::x_to_limbs(pt[i], out_point + 2 * i);
+        if (out_value) GlField::x_to_limbs(val, out_value);
+    })
+}
+int hg_lasso_node_download_polys(hg_lasso_node* node, uint16_t* dims, uint32_t* read_cts, uint32_t* final_cts, uint64_t* e_polys) {
+    HG_TRY({
+        HG_CUDA(cudaSetDevice(node->ctx->dev.device));
+        std::vector<u16> d; std::vector<u32> r, f; std::vector<u64> e;
+        node->gl->download_polys(dims ? &d : nullptr, read_cts ? &r : nullptr, final_cts ? &f : nullptr, e_polys ? &e : nullptr);
+        if (dims) memcpy(dims, d.data(), d.size() * sizeof(u16));
+        if (read_cts) memcpy(read_cts, r.data(), r.size() * sizeof(u32));
+        if (final_cts) memcpy(final_cts, f.data(), f.size() * sizeof(u32));
+        if (e_polys) memcpy(e_polys, e.data(), e.size() * sizeof(u64));
+    })
+}
+
+// ---- generic sumcheck
+int hg_sumcheck_prove(hg_ctx* ctx, int arity, size_t n_terms, size_t num_vars, const uint64_t* coeffs_ext, const void* d_tables,
+                      const uint64_t* claim_ext, hg_transcript* t, int mode, uint64_t* out_point, uint64_t* out_evals) {
+    HG_TRY({
+        typedef GlField FP;
+        HG_CUDA(cudaSetDevice(ctx->dev.device));
+        if (arity != 1 && arity != 2) throw std::runtime_error("arity must be 1 or 2");
+        if (num_vars < 1 || num_vars > 30) throw std::runtime_error("num_vars out of range");
+        const size_t n = (size_t)1 << num_vars, ntab = n_terms * arity;
+        DevBuf<gl2> coeffs, bufA, bufB, partials;
+        DevBuf<unsigned> counters;
+        coeffs.alloc(n_terms);
+        std::vector<gl2> hc(n_terms);
+        for (size_t i = 0; i < n_terms; i++) hc[i] = FP::x_from_limbs(coeffs_ext + 2 * i);
+        HG_CUDA(cudaMemcpy(coeffs.p, hc.data(), n_terms * sizeof(gl2), cudaMemcpyHostToDevice));
+        bufA.alloc(std::max<size_t>(ntab * (n / 2), ntab));
+        bufB.alloc(std::max<size_t>(ntab * (n / 4), ntab));
+        ScScratch sc;
+        sc.max_blocks = ctx->dev.sm_count * 8;
+        partials.alloc((size_t)sc.max_blocks * 4);
+        counters.alloc(4);
+        HG_CUDA(cudaMemset(counters.p, 0, counters.bytes()));
+        sc.partials = partials.p; sc.counters = counters.p;
+        Channel<FP> ch(&ctx->dev, num_vars + 1, 4 * num_vars + ntab + 4);
+        ch.begin(t->gl.get(), mode == HG_MODE_INTERACTIVE ? kModeInteractive : kModePrefetch, num_vars);
+        auto st = std::make_shared<ScHostState<FP>>();
+        st->claim = FP::x_from_limbs(claim_ext);
+        size_t first = 0, eo = 0;
+        if (arity == 1) sumcheck_dev<FP, 1>(&ctx->dev, ch, ctx->wire, (const u64*)d_tables, n, (int)n_terms, coeffs.p, bufA.p, bufB.p, sc, st, &first, &eo);
+        else sumcheck_dev<FP, 2>(&ctx->dev, ch, ctx->wire, (const u64*)d_tables, n, (int)n_terms, coeffs.p, bufA.p, bufB.p, sc, st, &first, &eo);
+        ch.flush();
+        if (out_point) for (size_t i = 0; i < num_vars; i++) FP::x_to_limbs(ch.chal(first + i), out_point + 2 * i);
+        if (out_evals) for (size_t i = 0; i < ntab; i++) FP::x_to_limbs(ch.msg(eo + i), out_evals + 2 * i);
+    })
+}
+
+int hg_mle_eval_batch(hg_ctx* ctx, const void* d_tables, size_t n_tables, size_t stride, size_t num_vars, const uint64_t* point_ext,
+                      uint64_t* out_ext) {
+    HG_TRY({
+        typedef GlField FP;
+        HG_CUDA(cudaSetDevice(ctx->dev.device));
+        const size_t n = (size_t)1 << num_vars;
+        cudaStream_t s = ctx->dev.stream;
+        DevBuf<gl2> pt, eq, partials, out;
+        DevBuf<unsigned> counters;
+        std::vector<gl2> hp(num_vars);
+        for (size_t i = 0; i < num_vars; i++) hp[i] = FP::x_from_limbs(point_ext + 2 * i);
+        pt.alloc(std::max<size_t>(num_vars, 1));
+        HG_CUDA(cudaMemcpy(pt.p, hp.data(), num_vars * sizeof(gl2), cudaMemcpyHostToDevice));
+        eq.alloc(n);
+        out.alloc(n_tables);
+        int blocks = (int)std::min<size_t>((n + HG_BLOCK - 1) / HG_BLOCK, (size_t)ctx->dev.sm_count * 2);
+        partials.alloc((size_t)blocks * n_tables);
+        counters.alloc(n_tables);
+        HG_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), s));
+        k_eq_build<FP><<<(unsigned)((n + HG_BLOCK - 1) / HG_BLOCK), HG_BLOCK, 0, s>>>(pt.p, (int)num_vars, eq.p);
+        HG_LAUNCH_CHECK();
+        k_dot_eq<FP, u64><<<dim3(blocks, (unsigned)n_tables), HG_BLOCK, 0, s>>>((const u64*)d_tables, stride, n, eq.p, partials.p, counters.p, out.p);
+        HG_LAUNCH_CHECK();
+        ctx->dev.launches += 2;
+        std::vector<gl2> ho(n_tables);
+        HG_CUDA(cudaMemcpyAsync(ho.data(), out.p, n_tables * sizeof(gl2), cudaMemcpyDeviceToHost, s));
+        HG_CUDA(cudaStreamSynchronize(s));
+        for (size_t i = 0; i < n_tables; i++) FP::x_to_limbs(ho[i], out_ext + 2 * i);
+    })
+}
+
+int hg_field_selftest(hg_ctx* ctx, int op, const uint64_t* a_ext, const uint64_t* b_ext, size_t n, uint64_t* out_ext) {
+    HG_TRY({
+        typedef GlField FP;
+        HG_CUDA(cudaSetDevice(ctx->dev.device));
+        DevBuf<gl2> a, b, o;
+        a.alloc(n); b.alloc(n); o.alloc(n);
+        HG_CUDA(cudaMemcpy(a.p, a_ext, n * sizeof(gl2), cudaMemcpyHostToDevice));
+        HG_CUDA(cudaMemcpy(b.p, b_ext, n * sizeof(gl2), cudaMemcpyHostToDevice));
+        k_selftest<FP><<<(unsigned)((n + 255) / 256), 256, 0, ctx->dev.stream>>>(op, a.p, b.p, n, o.p);
+        HG_LAUNCH_CHECK();
+        HG_CUDA(cudaStreamSynchronize(ctx->dev.stream));
+        HG_CUDA(cudaMemcpy(out_ext, o.p, n * sizeof(gl2), cudaMemcpyDeviceToHost));
+    })
+}
+
+}  // extern "C"

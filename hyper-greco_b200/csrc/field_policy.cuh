@@ -1,0 +1,82 @@
+// Field policies the kernels are templated on: base element B (tables as witnessed), extension element X
+// (tables after the first fold, challenges, round messages).
+//   GlField : B = Goldilocks u64, X = GoldilocksExt2 (16 B, one 128-bit load)
+//   (BN254 Fr policy lives in bn254.cuh: B = X = 4x64 Montgomery)
+#pragma once
+#include <cstddef>
+
+#include "gl.cuh"
+
+namespace hg {
+
+struct GlField {
+    typedef u64 B;
+    typedef gl2 X;
+    static constexpr int FIELD_ID = 0;
+    static constexpr int B_LIMBS = 1, X_LIMBS = 2;
+    HG_HD static B b_zero() { return 0; }
+    HG_HD static B b_one() { return 1; }
+    HG_HD static B b_from_u64(u64 x) { return gl_from_u64(x); }
+    HG_HD static B b_add(B a, B b) { return gl_add(a, b); }
+    HG_HD static B b_sub(B a, B b) { return gl_sub(a, b); }
+    HG_HD static B b_mul(B a, B b) { return gl_mul(a, b); }
+    HG_HD static X x_zero() { return gl2_zero(); }
+    HG_HD static X x_one() { return gl2_one(); }
+    HG_HD static X lift(B a) { return gl2_lift(a); }
+    HG_HD static X x_add(X a, X b) { return gl2_add(a, b); }
+    HG_HD static X x_sub(X a, X b) { return gl2_sub(a, b); }
+    HG_HD static X x_mul(X a, X b) { return gl2_mul(a, b); }
+    HG_HD static X x_mul_b(X a, B b) { return gl2_mul_base(a, b); }
+    HG_HD static X x_add_b(X a, B b) { return gl2_make(gl_add(a.c0, b), a.c1); }
+    HG_HD static bool x_eq(X a, X b) { return gl2_eq(a, b); }
+    HG_HD static X x_inv(X a) { return gl2_inv(a); }
+    HG_HD static B x_base0(X a) { return a.c0; }  // E::as_bases()[0], prover.rs:38-39
+    // overloads so kernels can be written once for base or extension inputs
+    HG_HD static X as_x(B a) { return gl2_lift(a); }
+    HG_HD static X as_x(X a) { return a; }
+    HG_HD static B sub(B a, B b) { return gl_sub(a, b); }
+    HG_HD static X sub(X a, X b) { return gl2_sub(a, b); }
+    HG_HD static B add(B a, B b) { return gl_add(a, b); }
+    HG_HD static X add(X a, X b) { return gl2_add(a, b); }
+    HG_HD static B mul(B a, B b) { return gl_mul(a, b); }
+    HG_HD static X mul(X a, X b) { return gl2_mul(a, b); }
+    HG_HD static X mul(X a, B b) { return gl2_mul_base(a, b); }
+    HG_HD static X mul(B a, X b) { return gl2_mul_base(b, a); }
+    HG_HD static u64 b_low_u64(B a) { return a; }  // low 64 bits of the canonical repr (fe_to_bits_le, lasso.rs:654-669)
+    HG_HD static bool b_fits_u64(B) { return true; }
+    // ---- host-side representation (transcript.rs:183-203)
+    typedef B Base;
+    typedef X Ext;
+    static constexpr int DEGREE = 2, REPR_BYTES = 8;
+    static B base_from_le_bytes_mod(const unsigned char* h, size_t n) {  // fe_mod_from_le_bytes
+        B acc = 0;
+        for (size_t i = n; i-- > 0;) acc = gl_add(gl_mul(acc, 256), h[i]);
+        return acc;
+    }
+    static void base_to_repr_le(B f, unsigned char* out) { for (int i = 0; i < 8; i++) out[i] = (unsigned char)(f >> (8 * i)); }
+    static bool base_from_repr_le(const unsigned char* in, B* out) {
+        u64 x = 0;
+        for (int i = 0; i < 8; i++) x |= (u64)in[i] << (8 * i);
+        if (x >= GL_P) return false;
+        *out = x;
+        return true;
+    }
+    static X ext_from_bases(const B* b) { return gl2_make(b[0], b[1]); }
+    static void ext_as_bases(X e, B* b) { b[0] = e.c0; b[1] = e.c1; }
+    // canonical u64 limbs at the C ABI
+    static void b_to_limbs(B a, u64* out) { out[0] = a; }
+    static B b_from_limbs(const u64* in) { return gl_from_u64(in[0]); }
+    static void x_to_limbs(X a, u64* out) { out[0] = a.c0; out[1] = a.c1; }
+    static X x_from_limbs(const u64* in) { return gl2_make(gl_from_u64(in[0]), gl_from_u64(in[1])); }
+#if defined(__CUDACC__)
+    __device__ __forceinline__ static X x_shfl_down(X v, int off) {
+        return gl2_make(__shfl_down_sync(0xffffffffu, v.c0, off), __shfl_down_sync(0xffffffffu, v.c1, off));
+    }
+    __device__ __forceinline__ static X x_ldcg(const X* p) {
+        ulonglong2 t = __ldcg(reinterpret_cast<const ulonglong2*>(p));
+        return gl2_make(t.x, t.y);
+    }
+#endif
+};
+
+}  // namespace hg

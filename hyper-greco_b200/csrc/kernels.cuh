@@ -1,0 +1,362 @@
+// sm_100a kernels for the Lasso node hot path. Templated on a field policy FP
+// (field_policy.cuh). All are HBM-streaming integer kernels: coalesced 64/128-bit loads, 64x64->128 IMAD
+// reduction, warp-shuffle + block-tree reduction of round-polynomial evaluations, no tensor cores.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "field_policy.cuh"
+
+namespace hg {
+
+typedef unsigned short u16;
+typedef unsigned char u8;
+
+constexpr int HG_MAX_LOOKUPS = 64;
+constexpr int HG_MAX_MEMORIES = 128;
+constexpr int HG_MAX_C = 8;
+constexpr int HG_BLOCK = 256;
+
+// Flattened LassoPreprocessing maps (lasso.rs:513-523) for device use.
+struct NodeMeta {
+    int C, log2M, num_lookups, num_memories;
+    u8 total_bits[HG_MAX_LOOKUPS];            // sum(chunk_bits) per lookup type (lasso.rs:389, range.rs:234-250)
+    u8 lookup_nmem[HG_MAX_LOOKUPS];
+    u8 lookup_mem[HG_MAX_LOOKUPS][HG_MAX_C];  // lookup_to_memory_indices (lasso.rs:590-602)
+    u8 mem_sub[HG_MAX_MEMORIES];              // memory_to_subtable_index
+    u8 mem_dim[HG_MAX_MEMORIES];              // memory_to_dimension_index
+    u64 mem_used[HG_MAX_MEMORIES];            // bit l = lookup type l touches this memory (lasso.rs:182-183)
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// block reduction of NP extension values + cross-block finalisation by the last block to arrive.
+// partials: [gridDim.y][gridDim.x][NP]; counter: [gridDim.y]; out: [gridDim.y][NP]
+template <class FP, int NP>
+__device__ __forceinline__ void block_reduce_finalize(typename FP::X (&acc)[NP], typename FP::X* partials, unsigned* counter,
+                                                      typename FP::X* out) {
+    typedef typename FP::X X;
+    __shared__ X sm[32][NP];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        X v = acc[p];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v = FP::x_add(v, FP::x_shfl_down(v, off));
+        if (lane == 0) sm[warp][p] = v;
+    }
+    __syncthreads();
+    X* my_part = partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * NP;
+    if (warp == 0) {
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            X v = lane < nwarps ? sm[lane][p] : FP::x_zero();
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v = FP::x_add(v, FP::x_shfl_down(v, off));
+            if (lane == 0) my_part[p] = v;
+        }
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned t = atomicAdd(counter + blockIdx.y, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const X* all = partials + (size_t)blockIdx.y * gridDim.x * NP;
+    X s[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) s[p] = FP::x_zero();
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+#pragma unroll
+        for (int p = 0; p < NP; p++) s[p] = FP::x_add(s[p], FP::x_ldcg(all + (size_t)b * NP + p));
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        X v = s[p];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v = FP::x_add(v, FP::x_shfl_down(v, off));
+        if (lane == 0) sm[warp][p] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            X v = lane < nwarps ? sm[lane][p] : FP::x_zero();
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v = FP::x_add(v, FP::x_shfl_down(v, off));
+            if (lane == 0) out[(size_t)blockIdx.y * NP + p] = v;
+        }
+        if (lane == 0) counter[blockIdx.y] = 0;  // re-arm for the next launch that uses this slot
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1 + K2(E) + collation pre-combination.  One thread per lookup row (lasso.rs:157-250, :381-414).
+//   dims[c][j]   16-bit limbs of the (truncated) input        -> u16 [C][R]
+//   E[mi][j]     T_sub(mi)[dims[dim(mi)][j]] or 0              -> B   [m][R]
+//   S[j]         sum_i coeff[i] * E[i][j]   (collation inner sum, lasso.rs:457-475, is multilinear in the E tables)
+//   out[j]       combine_lookups of the row's lookup type      (lasso.rs:438-449, range.rs:184-195)
+template <class FP>
+__global__ void k_polynomialize(const typename FP::B* __restrict__ inputs, size_t n_rows, const u8* __restrict__ row_lookup,
+                                const NodeMeta* __restrict__ meta, const typename FP::B* __restrict__ subtables,
+                                const typename FP::B* __restrict__ coll_coeff, const typename FP::B* __restrict__ wpow, size_t R,
+                                u16* __restrict__ dims, typename FP::B* __restrict__ E, typename FP::B* __restrict__ S,
+                                typename FP::B* __restrict__ out) {
+    typedef typename FP::B B;
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= R) return;
+    const int C = meta->C, log2M = meta->log2M, m = meta->num_memories;
+    const size_t M = (size_t)1 << log2M;
+    int l = 0xFF;
+    u64 x = 0;
+    if (j < n_rows) {
+        l = row_lookup[j];
+        B in = inputs[j];
+        x = FP::b_low_u64(in);
+        int tb = meta->total_bits[l];
+        if (tb < 64) x &= (((u64)1) << tb) - 1;
+    }
+    u16 d[HG_MAX_C];
+    for (int c = 0; c < C; c++) {
+        u64 v = (c * log2M < 64) ? ((x >> (c * log2M)) & (M - 1)) : 0;
+        d[c] = (l == 0xFF) ? 0 : (u16)v;
+        dims[(size_t)c * R + j] = d[c];
+    }
+    B s = FP::b_zero();
+    for (int mi = 0; mi < m; mi++) {
+        B e = FP::b_zero();
+        if (l != 0xFF && ((meta->mem_used[mi] >> l) & 1)) e = subtables[(size_t)meta->mem_sub[mi] * M + d[meta->mem_dim[mi]]];
+        E[(size_t)mi * R + j] = e;
+        s = FP::b_add(s, FP::b_mul(coll_coeff[mi], e));
+    }
+    S[j] = s;
+    B o = FP::b_zero();
+    if (l != 0xFF) {
+        int nm = meta->lookup_nmem[l];
+        for (int t = 0; t < nm; t++) {
+            int mi = meta->lookup_mem[l][t];
+            B e = subtables[(size_t)meta->mem_sub[mi] * M + d[meta->mem_dim[mi]]];
+            o = FP::b_add(o, FP::b_mul(wpow[t], e));
+        }
+    }
+    out[j] = o;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2 counters (lasso.rs:177-196): read_cts[j] = number of earlier rows that touch the same address of memory `mem`,
+// final_cts[a] = total. Order-dependent, so: per-block histogram -> per-address scan over blocks -> ordered rank.
+// rows_per_block <= 65535 so that 16-bit packed shared counters cannot overflow.
+__global__ void k_cnt_hist(const u16* __restrict__ addr, const u8* __restrict__ row_lookup, u64 used_mask, size_t n_rows,
+                           int rows_per_block, u16* __restrict__ blk_hist /*[nblk][M]*/, int log2M);
+__global__ void k_cnt_scan(const u16* __restrict__ blk_hist, int nblk, int log2M, u32* __restrict__ blk_base, u32* __restrict__ final_cts);
+__global__ void k_cnt_rank(const u16* __restrict__ addr, const u8* __restrict__ row_lookup, u64 used_mask, size_t n_rows, size_t R,
+                           int rows_per_block, const u32* __restrict__ blk_base, int log2M, u32* __restrict__ read_cts);
+
+// ---------------------------------------------------------------------------------------------------------
+// eq(point, k) table, k_0 = LSB (plonkish MultilinearPolynomial::eq_xy, lasso.rs:432)
+template <class FP>
+__global__ void k_eq_build(const typename FP::X* __restrict__ point, int nv, typename FP::X* __restrict__ eq) {
+    typedef typename FP::X X;
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ((size_t)1 << nv)) return;
+    X acc = FP::x_one();
+    for (int i = 0; i < nv; i++) {
+        X r = point[i];
+        X f = ((k >> i) & 1) ? r : FP::x_sub(FP::x_one(), r);
+        acc = FP::x_mul(acc, f);
+    }
+    eq[k] = acc;
+}
+
+template <class FP, class T> struct ToBase;
+template <class FP> struct ToBase<FP, u16> { __device__ __forceinline__ static typename FP::B f(u16 v) { return FP::b_from_u64(v); } };
+template <class FP> struct ToBase<FP, u32> { __device__ __forceinline__ static typename FP::B f(u32 v) { return FP::b_from_u64(v); } };
+template <class FP> struct ToBase<FP, u64> { __device__ __forceinline__ static typename FP::B f(u64 v) { return v; } };
+
+// Batched MLE evaluation as dot products with a shared eq table (mod.rs:80-93, lasso.rs:422-454):
+// out[y] = sum_k eq[k] * tables[y][k];  grid = (blocks, ntables)
+template <class FP, class T>
+__global__ void k_dot_eq(const T* __restrict__ tables, size_t stride, size_t n, const typename FP::X* __restrict__ eq,
+                         typename FP::X* partials, unsigned* counter, typename FP::X* out) {
+    typedef typename FP::X X;
+    const T* t = tables + (size_t)blockIdx.y * stride;
+    X acc[1] = {FP::x_zero()};
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+        acc[0] = FP::x_add(acc[0], FP::x_mul_b(eq[k], ToBase<FP, T>::f(t[k])));
+    block_reduce_finalize<FP, 1>(acc, partials, counter, out);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K6 multiset hashes (prover.rs:35-89): h(a,v,t) = a + v*gamma + t*gamma^2 - tau, gamma/tau truncated to the base
+// field (prover.rs:38-39). V = [reads (m, chunk-major) | writes (m)] x R.
+template <class FP>
+__global__ void k_hash_rw(const u16* __restrict__ dims, const u32* __restrict__ read_cts, const typename FP::B* __restrict__ E,
+                          const int* __restrict__ pos_mem, const int* __restrict__ pos_dim, const int* __restrict__ pos_slot,
+                          const typename FP::X* __restrict__ gamma_tau, size_t R, int m, typename FP::B* __restrict__ V) {
+    typedef typename FP::B B;
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int pos = blockIdx.y;
+    if (j >= R) return;
+    const B gamma = FP::x_base0(gamma_tau[0]), tau = FP::x_base0(gamma_tau[1]), gamma2 = FP::b_mul(gamma, gamma);
+    B a = FP::b_from_u64(dims[(size_t)pos_dim[pos] * R + j]);
+    B t = FP::b_from_u64(read_cts[(size_t)pos_slot[pos] * R + j]);
+    B e = E[(size_t)pos_mem[pos] * R + j];
+    B rd = FP::b_sub(FP::b_add(FP::b_add(a, FP::b_mul(e, gamma)), FP::b_mul(t, gamma2)), tau);
+    V[(size_t)pos * R + j] = rd;
+    V[(size_t)(m + pos) * R + j] = FP::b_add(rd, gamma2);
+}
+// V2 = [inits (m) | final_reads (m)] x M
+template <class FP>
+__global__ void k_hash_if(const typename FP::B* __restrict__ subtables, const u32* __restrict__ final_cts, const int* __restrict__ pos_sub,
+                          const int* __restrict__ pos_slot, const typename FP::X* __restrict__ gamma_tau, size_t M, int m,
+                          typename FP::B* __restrict__ V) {
+    typedef typename FP::B B;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int pos = blockIdx.y;
+    if (i >= M) return;
+    const B gamma = FP::x_base0(gamma_tau[0]), tau = FP::x_base0(gamma_tau[1]), gamma2 = FP::b_mul(gamma, gamma);
+    B v = subtables[(size_t)pos_sub[pos] * M + i];
+    B in = FP::b_sub(FP::b_add(FP::b_from_u64(i), FP::b_mul(v, gamma)), tau);
+    B fc = FP::b_from_u64(final_cts[(size_t)pos_slot[pos] * M + i]);
+    V[(size_t)pos * M + i] = in;
+    V[(size_t)(m + pos) * M + i] = FP::b_add(in, FP::b_mul(fc, gamma2));
+}
+
+// K7 product-tree layer (prover.rs:332-354): out[i][k] = in[i][k] * in[i][k + h]; halves = top index bit
+template <class FP>
+__global__ void k_tree_up(const typename FP::B* __restrict__ in, typename FP::B* __restrict__ out, size_t h) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= h) return;
+    const typename FP::B* v = in + (size_t)blockIdx.y * 2 * h;
+    out[(size_t)blockIdx.y * h + k] = FP::b_mul(v[k], v[k + h]);
+}
+// roots (prover.rs:197-203) and the nv = 0 layer's evaluations (prover.rs:232-236) from the top layer [nvec][2]
+template <class FP>
+__global__ void k_tree_top(const typename FP::B* __restrict__ top, int nvec, typename FP::X* __restrict__ roots, typename FP::X* __restrict__ evals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvec) return;
+    typename FP::B l = top[2 * i], r = top[2 * i + 1];
+    roots[i] = FP::lift(FP::b_mul(l, r));
+    evals[2 * i] = FP::lift(l);
+    evals[2 * i + 1] = FP::lift(r);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K5/K8: one sumcheck round of g = t_0 * sum_i coeff[i] * prod_{k<ARITY} t_{ARITY*i+k}  (lasso.rs:457-475,
+// prover.rs:268-279), evaluation FUSED with the fold by the previous round's challenge, so every table is read once
+// and its folded image written once per round.
+//   in : ntab tables of n_in elements (TIN = B in rounds 0/1, X later), table t at in + t*n_in
+//   FOLD: out[t][q] = in[t][2q] + r_prev*(in[t][2q+1] - in[t][2q]) is written (n_in/2 per table) and the round
+//         polynomial is evaluated on the folded values; !FOLD: evaluated on `in` directly (round 0).
+//   msg: h(0), h(2), .., h(d) [, h(1) when WITH_H1]  with d = ARITY + 1, X = lowest remaining variable (LSB first)
+template <class FP, class TIN, int ARITY, bool FOLD, bool WITH_H1>
+__global__ void __launch_bounds__(HG_BLOCK)
+k_sc_round(const TIN* __restrict__ in, typename FP::X* __restrict__ out, size_t n_in, int nterm,
+           const typename FP::X* __restrict__ coeffs, const typename FP::X* __restrict__ r_prev, typename FP::X* partials,
+           unsigned* counter, typename FP::X* msg) {
+    typedef typename FP::X X;
+    constexpr int D = ARITY + 1;
+    constexpr int NP = WITH_H1 ? D + 1 : D;  // slots: 0 -> X=0, 1..D-1 -> X=2..D, D -> X=1
+    const size_t npairs = FOLD ? n_in / 4 : n_in / 2;
+    const size_t n_out = n_in / 2;
+    X acc[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) acc[p] = FP::x_zero();
+    X r = FP::x_zero();
+    if (FOLD) r = *r_prev;
+    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < npairs; b += (size_t)gridDim.x * blockDim.x) {
+        if constexpr (FOLD) {
+            X inner[NP], t0[NP];
+#pragma unroll
+            for (int p = 0; p < NP; p++) inner[p] = FP::x_zero();
+            for (int i = 0; i < nterm; i++) {
+                X prod[NP];
+#pragma unroll
+                for (int k = 0; k < ARITY; k++) {
+                    const int t = ARITY * i + k;
+                    const TIN* src = in + (size_t)t * n_in + 4 * b;
+                    TIN a0 = src[0], a1 = src[1], a2 = src[2], a3 = src[3];
+                    X lo = FP::x_add(FP::as_x(a0), FP::mul(r, FP::sub(a1, a0)));
+                    X hi = FP::x_add(FP::as_x(a2), FP::mul(r, FP::sub(a3, a2)));
+                    X* dst = out + (size_t)t * n_out + 2 * b;
+                    dst[0] = lo;
+                    dst[1] = hi;
+                    X df = FP::x_sub(hi, lo);
+                    X v[NP];
+                    v[0] = lo;
+                    X cur = FP::x_add(hi, df);
+#pragma unroll
+                    for (int p = 1; p < D; p++) { v[p] = cur; cur = FP::x_add(cur, df); }
+                    if constexpr (WITH_H1) v[NP - 1] = hi;
+#pragma unroll
+                    for (int p = 0; p < NP; p++) {
+                        if (k == 0) prod[p] = v[p]; else prod[p] = FP::x_mul(prod[p], v[p]);
+                        if (i == 0 && k == 0) t0[p] = v[p];
+                    }
+                }
+                X c = coeffs[i];
+#pragma unroll
+                for (int p = 0; p < NP; p++) inner[p] = FP::x_add(inner[p], FP::x_mul(c, prod[p]));
+            }
+#pragma unroll
+            for (int p = 0; p < NP; p++) acc[p] = FP::x_add(acc[p], FP::x_mul(t0[p], inner[p]));
+        } else {
+            X inner[NP];
+            TIN t0[NP];
+#pragma unroll
+            for (int p = 0; p < NP; p++) inner[p] = FP::x_zero();
+            for (int i = 0; i < nterm; i++) {
+                TIN prod[NP];
+#pragma unroll
+                for (int k = 0; k < ARITY; k++) {
+                    const int t = ARITY * i + k;
+                    const TIN* src = in + (size_t)t * n_in + 2 * b;
+                    TIN lo = src[0], hi = src[1];
+                    TIN df = FP::sub(hi, lo);
+                    TIN v[NP];
+                    v[0] = lo;
+                    TIN cur = FP::add(hi, df);
+#pragma unroll
+                    for (int p = 1; p < D; p++) { v[p] = cur; cur = FP::add(cur, df); }
+                    if constexpr (WITH_H1) v[NP - 1] = hi;
+#pragma unroll
+                    for (int p = 0; p < NP; p++) {
+                        if (k == 0) prod[p] = v[p]; else prod[p] = FP::mul(prod[p], v[p]);
+                        if (i == 0 && k == 0) t0[p] = v[p];
+                    }
+                }
+                X c = coeffs[i];
+#pragma unroll
+                for (int p = 0; p < NP; p++) inner[p] = FP::x_add(inner[p], FP::mul(c, prod[p]));
+            }
+#pragma unroll
+            for (int p = 0; p < NP; p++) acc[p] = FP::x_add(acc[p], FP::mul(inner[p], t0[p]));
+        }
+    }
+    block_reduce_finalize<FP, NP>(acc, partials, counter, msg);
+}
+
+// final fold of 2-element tables: evals[t] = in[t][0] + r*(in[t][1] - in[t][0])   (prove_sum_check's returned evals)
+template <class FP, class TIN>
+__global__ void k_fold_final(const TIN* __restrict__ in, int ntab, const typename FP::X* __restrict__ r, typename FP::X* __restrict__ evals) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntab) return;
+    TIN a0 = in[2 * t], a1 = in[2 * t + 1];
+    evals[t] = FP::x_add(FP::as_x(a0), FP::mul(*r, FP::sub(a1, a0)));
+}
+// plain fold (used by standalone MLE evaluation / tests): out[q] = in[2q] + r*(in[2q+1]-in[2q])
+template <class FP, class TIN>
+__global__ void k_fold(const TIN* __restrict__ in, size_t n_out_total, const typename FP::X* __restrict__ r, typename FP::X* __restrict__ out) {
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_out_total) return;
+    TIN a0 = in[2 * q], a1 = in[2 * q + 1];
+    out[q] = FP::x_add(FP::as_x(a0), FP::mul(*r, FP::sub(a1, a0)));
+}
+
+template <class T> __global__ void k_fill(T* p, size_t n, T v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+}  // namespace hg

@@ -1,0 +1,638 @@
+// Device-resident Lasso node prover: orchestration of the kernels in kernels.cuh in the reference's protocol order
+//   LassoNode::prove_claim_reduction            /root/reference/lasso/src/lasso.rs:57-114
+//   prove_collation_sum_check                   /root/reference/lasso/src/lasso.rs:254-288
+//   prove_memory_checking                       /root/reference/lasso/src/lasso.rs:292-339
+//   MemoryCheckingProver::{new,prove}           /root/reference/lasso/src/memory_checking/prover.rs:35-89,158-181
+//   prove_grand_product                         /root/reference/lasso/src/memory_checking/prover.rs:183-266
+// The transcript stays on the host. Two modes:
+//   PREFETCH     all challenges are squeezed up front and uploaded once (legal because the reference transcript never
+//                absorbs prover messages, transcript.rs:156,183-203); kernels run back to back, messages come back in
+//                one copy at the end and are serialised in protocol order.
+//   INTERACTIVE  one device->host->device round trip per squeeze; works with any transcript.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "lasso_host.hpp"
+#include "transcript.hpp"
+
+namespace hg {
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+#define HG_CUDA(expr)                                                                                            \
+    do {                                                                                                         \
+        cudaError_t _e = (expr);                                                                                 \
+        if (_e != cudaSuccess) throw ::hg::CudaError(std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+    } while (0)
+#define HG_LAUNCH_CHECK() HG_CUDA(cudaGetLastError())
+
+struct DeviceCtx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    size_t launches = 0;  // kernels enqueued (bench.py "gpu_launches")
+};
+
+template <class T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) HG_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    size_t bytes() const { return n * sizeof(T); }
+};
+template <class T> struct PinnedBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    PinnedBuf() {}
+    PinnedBuf(const PinnedBuf&) = delete;
+    PinnedBuf& operator=(const PinnedBuf&) = delete;
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+    void alloc(size_t count) {
+        if (p) cudaFreeHost(p);
+        p = nullptr; n = count;
+        if (count) HG_CUDA(cudaMallocHost((void**)&p, count * sizeof(T)));
+    }
+};
+
+// Upstream-format switches. Host-only: the kernels always return values of the TRUE round
+// polynomial; how they are put on the wire is decided here.
+struct WireOptions {
+    int a3_wire = 0;       // 0: coefficients c0,c2..cd   1: evaluations h(0),h(2)..h(d)
+    int a3_h1 = 0;         // 0: h(1) := claim - h(0)     1: h(1) from the tables
+    int a5_ascending = 1;  // distribute_powers: 1: sum_i b^i e_i   0: first expression gets the highest power
+};
+enum ProveMode { kModePrefetch = 0, kModeInteractive = 1 };
+
+// ---------------------------------------------------------------------------------------------------------
+// Challenge / message plumbing between the host transcript and the device pipeline.
+template <class FP> class Channel {
+  public:
+    typedef typename FP::X X;
+    Channel(DeviceCtx* ctx, size_t chal_cap, size_t msg_cap) : ctx_(ctx) {
+        d_chal_.alloc(chal_cap); h_chal_.alloc(chal_cap);
+        d_msg_.alloc(msg_cap); h_msg_.alloc(msg_cap);
+    }
+    void begin(Keccak256Transcript<FP>* tr, ProveMode mode, size_t total_chal) {
+        tr_ = tr; mode_ = mode;
+        chal_cursor_ = chal_ready_ = msg_cursor_ = msg_ready_ = 0;
+        deferred_.clear(); deferred_done_ = 0;
+        if (total_chal > d_chal_.n) throw std::runtime_error("Channel: challenge capacity exceeded");
+        if (mode_ == kModePrefetch) {
+            for (size_t i = 0; i < total_chal; i++) h_chal_.p[i] = tr_->squeeze_challenge();
+            chal_ready_ = total_chal;
+            HG_CUDA(cudaMemcpyAsync(d_chal_.p, h_chal_.p, total_chal * sizeof(X), cudaMemcpyHostToDevice, ctx_->stream));
+        }
+    }
+    // index of the first of n consecutive challenges, squeezed at this point of the protocol
+    size_t squeeze(size_t n = 1) {
+        size_t first = chal_cursor_;
+        chal_cursor_ += n;
+        if (chal_cursor_ > d_chal_.n) throw std::runtime_error("Channel: challenge capacity exceeded");
+        if (mode_ == kModeInteractive) {
+            flush();
+            for (size_t i = first; i < chal_cursor_; i++) h_chal_.p[i] = tr_->squeeze_challenge();
+            chal_ready_ = chal_cursor_;
+            HG_CUDA(cudaMemcpyAsync(d_chal_.p + first, h_chal_.p + first, n * sizeof(X), cudaMemcpyHostToDevice, ctx_->stream));
+        } else if (chal_cursor_ > chal_ready_) {
+            throw std::runtime_error("Channel: prefetch count too small");
+        }
+        return first;
+    }
+    size_t alloc_msg(size_t n) {
+        size_t off = msg_cursor_;
+        msg_cursor_ += n;
+        if (msg_cursor_ > d_msg_.n) throw std::runtime_error("Channel: message capacity exceeded");
+        return off;
+    }
+    void emit(std::function<void()> fn) { deferred_.push_back(std::move(fn)); }
+    // bring finished messages to the host and serialise everything emitted so far, in order
+    void flush() {
+        if (msg_cursor_ > msg_ready_) {
+            HG_CUDA(cudaMemcpyAsync(h_msg_.p + msg_ready_, d_msg_.p + msg_ready_, (msg_cursor_ - msg_ready_) * sizeof(X),
+                                    cudaMemcpyDeviceToHost, ctx_->stream));
+            msg_ready_ = msg_cursor_;
+        }
+        HG_CUDA(cudaStreamSynchronize(ctx_->stream));
+        for (; deferred_done_ < deferred_.size(); deferred_done_++) deferred_[deferred_done_]();
+    }
+    const X* d_chal(size_t i) const { return d_chal_.p + i; }
+    X* d_msg(size_t i) { return d_msg_.p + i; }
+    X chal(size_t i) const { if (i >= chal_ready_) throw std::runtime_error("Channel: challenge not squeezed yet"); return h_chal_.p[i]; }
+    X msg(size_t i) const { if (i >= msg_ready_) throw std::runtime_error("Channel: message not downloaded yet"); return h_msg_.p[i]; }
+    Keccak256Transcript<FP>& transcript() { return *tr_; }
+    size_t chal_used() const { return chal_cursor_; }
+    size_t next_index() const { return chal_cursor_; }
+
+  private:
+    DeviceCtx* ctx_;
+    Keccak256Transcript<FP>* tr_ = nullptr;
+    ProveMode mode_ = kModePrefetch;
+    DevBuf<X> d_chal_, d_msg_;
+    PinnedBuf<X> h_chal_, h_msg_;
+    size_t chal_cursor_ = 0, chal_ready_ = 0, msg_cursor_ = 0, msg_ready_ = 0;
+    std::vector<std::function<void()>> deferred_;
+    size_t deferred_done_ = 0;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// host arithmetic on round messages [UPSTREAM gkr::sum_check, assumptions A3]
+template <class FP> struct RoundPoly {
+    typedef typename FP::X X;
+    static X small(u64 v) { return FP::lift(FP::b_from_u64(v)); }
+    // coefficients of the degree-d polynomial through (0,y0)..(d,yd), d in {1,2,3}, by forward differences
+    static std::vector<X> interpolate(const std::vector<X>& y) {
+        const int d = (int)y.size() - 1;
+        if (d < 1 || d > 3) throw std::runtime_error("RoundPoly: unsupported degree");
+        X d1 = FP::x_sub(y[1], y[0]);
+        if (d == 1) return {y[0], d1};
+        X d2 = FP::x_add(FP::x_sub(y[2], FP::x_add(y[1], y[1])), y[0]);
+        X inv2 = FP::x_inv(small(2));
+        if (d == 2) {
+            X c2 = FP::x_mul(d2, inv2);
+            return {y[0], FP::x_sub(d1, c2), c2};
+        }
+        // d3 = y3 - 3y2 + 3y1 - y0
+        X three = small(3);
+        X d3 = FP::x_sub(FP::x_add(FP::x_sub(y[3], FP::x_mul(three, y[2])), FP::x_mul(three, y[1])), y[0]);
+        X inv3 = FP::x_inv(three), inv6 = FP::x_mul(inv2, inv3);
+        X c3 = FP::x_mul(d3, inv6);
+        X h2 = FP::x_mul(d2, inv2), h3 = FP::x_mul(d3, inv2);
+        X c2 = FP::x_sub(h2, h3);
+        X c1 = FP::x_add(FP::x_sub(d1, h2), FP::x_mul(d3, inv3));
+        return {y[0], c1, c2, c3};
+    }
+    static X horner(const std::vector<X>& c, X x) {
+        X r = FP::x_zero();
+        for (size_t i = c.size(); i-- > 0;) r = FP::x_add(FP::x_mul(r, x), c[i]);
+        return r;
+    }
+};
+
+// host-side state of one sumcheck instance (claim bookkeeping happens while messages are serialised)
+template <class FP> struct ScHostState {
+    typedef typename FP::X X;
+    X claim;
+    bool has_pending = false;
+    std::vector<X> pending_coeffs;
+    size_t pending_chal = 0;
+};
+
+struct ScScratch {
+    void* partials = nullptr;  // X [max_blocks * max_batch * 4]
+    unsigned* counters = nullptr;
+    int max_blocks = 0;
+};
+
+// one launch of k_sc_round with the right instantiation
+template <class FP, int ARITY>
+void launch_sc_round(DeviceCtx* ctx, bool in_base, bool fold, bool with_h1, const void* in, typename FP::X* out, size_t n_in, int nterm,
+                     const typename FP::X* coeffs, const typename FP::X* r_prev, const ScScratch& sc, typename FP::X* msg) {
+    typedef typename FP::B B;
+    typedef typename FP::X X;
+    size_t npairs = fold ? n_in / 4 : n_in / 2;
+    int blocks = (int)std::min<size_t>((npairs + HG_BLOCK - 1) / HG_BLOCK, (size_t)sc.max_blocks);
+    if (blocks < 1) blocks = 1;
+    X* part = (X*)sc.partials;
+#define HG_SC(TIN, FOLD, H1) \
+    k_sc_round<FP, TIN, ARITY, FOLD, H1><<<blocks, HG_BLOCK, 0, ctx->stream>>>((const TIN*)in, out, n_in, nterm, coeffs, r_prev, part, sc.counters, msg)
+    if (in_base) {
+        if (fold) { if (with_h1) HG_SC(B, true, true); else HG_SC(B, true, false); }
+        else { if (with_h1) HG_SC(B, false, true); else HG_SC(B, false, false); }
+    } else {
+        if (!fold) throw std::runtime_error("launch_sc_round: extension input is always folded");
+        if (with_h1) HG_SC(X, true, true); else HG_SC(X, true, false);
+    }
+#undef HG_SC
+    HG_LAUNCH_CHECK();
+    ctx->launches++;
+}
+
+// prove_sum_check for g = t_0 * sum_i coeffs[i] * prod_{k<ARITY} t_{ARITY*i+k} over base tables of length n = 2^nv laid
+// out back to back. Returns the message offset of the final evaluations and the index of the first round challenge.
+template <class FP, int ARITY>
+void sumcheck_dev(DeviceCtx* ctx, Channel<FP>& ch, const WireOptions& wo, const typename FP::B* d_tables, size_t n, int nterm,
+                  const typename FP::X* d_coeffs, typename FP::X* bufA, typename FP::X* bufB, const ScScratch& sc,
+                  std::shared_ptr<ScHostState<FP>> st, size_t* first_chal, size_t* evals_off) {
+    typedef typename FP::B B;
+    typedef typename FP::X X;
+    constexpr int D = ARITY + 1;
+    const int ntab = nterm * ARITY;
+    int nv = 0;
+    while (((size_t)1 << nv) < n) nv++;
+    if (nv < 1) throw std::runtime_error("sumcheck_dev: num_vars must be positive");
+    const bool h1 = wo.a3_h1 != 0;
+    const int NP = h1 ? D + 1 : D;
+    const void* cur_in = d_tables;
+    bool in_base = true;
+    size_t n_in = n;
+    size_t prev_chal = 0;
+    for (int j = 0; j < nv; j++) {
+        size_t off = ch.alloc_msg(NP);
+        if (j == 0) {
+            launch_sc_round<FP, ARITY>(ctx, true, false, h1, d_tables, nullptr, n, nterm, d_coeffs, nullptr, sc, ch.d_msg(off));
+        } else {
+            X* out = (j & 1) ? bufA : bufB;
+            launch_sc_round<FP, ARITY>(ctx, in_base, true, h1, cur_in, out, n_in, nterm, d_coeffs, ch.d_chal(prev_chal), sc, ch.d_msg(off));
+            cur_in = out; in_base = false; n_in >>= 1;
+        }
+        Channel<FP>* chp = &ch;
+        WireOptions w = wo;
+        const size_t next_idx = ch.next_index();  // the challenge squeezed right after this message
+        ch.emit([chp, st, off, w, h1, next_idx]() {
+            typedef RoundPoly<FP> RP;
+            if (st->has_pending) st->claim = RP::horner(st->pending_coeffs, chp->chal(st->pending_chal));
+            std::vector<X> ev(D + 1);
+            ev[0] = chp->msg(off);
+            for (int p = 2; p <= D; p++) ev[p] = chp->msg(off + p - 1);
+            ev[1] = h1 ? chp->msg(off + D) : FP::x_sub(st->claim, ev[0]);
+            std::vector<X> co = RP::interpolate(ev);
+            auto& tr = chp->transcript();
+            if (w.a3_wire == 0) { tr.write_felt_ext(co[0]); for (int p = 2; p <= D; p++) tr.write_felt_ext(co[p]); }
+            else { tr.write_felt_ext(ev[0]); for (int p = 2; p <= D; p++) tr.write_felt_ext(ev[p]); }
+            st->pending_coeffs = co;
+            st->pending_chal = next_idx;
+            st->has_pending = true;
+        });
+        prev_chal = ch.squeeze(1);
+        if (prev_chal != next_idx) throw std::runtime_error("sumcheck_dev: challenge index drift");
+        if (j == 0 && first_chal) *first_chal = prev_chal;
+    }
+    // final evaluations: the tables now have 2 elements each
+    size_t eo = ch.alloc_msg(ntab);
+    int blocks = (ntab + HG_BLOCK - 1) / HG_BLOCK;
+    if (in_base) k_fold_final<FP, B><<<blocks, HG_BLOCK, 0, ctx->stream>>>((const B*)cur_in, ntab, ch.d_chal(prev_chal), ch.d_msg(eo));
+    else k_fold_final<FP, X><<<blocks, HG_BLOCK, 0, ctx->stream>>>((const X*)cur_in, ntab, ch.d_chal(prev_chal), ch.d_msg(eo));
+    HG_LAUNCH_CHECK();
+    ctx->launches++;
+    if (evals_off) *evals_off = eo;
+}
+
+template <class FP> __global__ void k_powers(const typename FP::X* __restrict__ base, int n, int ascending, typename FP::X* __restrict__ out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    typename FP::X p = FP::x_one(), b = *base;
+    for (int i = 0; i < n; i++) { out[ascending ? i : n - 1 - i] = p; p = FP::x_mul(p, b); }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+template <class FP> class LassoNodeDev {
+  public:
+    typedef typename FP::B B;
+    typedef typename FP::X X;
+
+    // LassoNode::new (lasso.rs:143-154). row_lookup[j] = index of row j's lookup type in preprocessing order.
+    LassoNodeDev(DeviceCtx* ctx, const LassoPreprocessing& pp, int num_vars, const std::vector<uint8_t>& row_lookup)
+        : ctx_(ctx), pp_(pp), num_vars_(num_vars), n_rows_(row_lookup.size()) {
+        if (pp.lookups.size() > (size_t)HG_MAX_LOOKUPS - 1 || pp.num_memories > (size_t)HG_MAX_MEMORIES || pp.C > (size_t)HG_MAX_C)
+            throw std::runtime_error("LassoNode: preprocessing exceeds device limits");
+        log2M_ = (int)ilog2u(pp.M);
+        if (log2M_ > 16 || log2M_ < 1) throw std::runtime_error("LassoNode: M must be in 2..=65536");
+        R_ = (size_t)1 << num_vars;
+        M_ = pp.M;
+        if (n_rows_ > R_) throw std::runtime_error("LassoNode: more lookups than 2^num_vars");
+        m_ = (int)pp.num_memories;
+        // chunks: memories grouped by dimension, ascending (lasso.rs:303-336); chunk-major memory order (Q10)
+        std::map<size_t, std::vector<size_t>> by_dim;
+        for (size_t mi = 0; mi < pp.num_memories; mi++) by_dim[pp.memory_to_dimension_index[mi]].push_back(mi);
+        std::vector<int> pos_mem, pos_dim, pos_slot, pos_sub;
+        for (auto& kv : by_dim) {
+            // F6: chunk `d` reads read_cts[d] / final_cts[d], i.e. the counters of MEMORY index d (lasso.rs:318-319)
+            if (kv.first >= pp.num_memories) throw std::runtime_error("LassoNode: chunk index exceeds memory count (the reference panics here)");
+            int slot = (int)chunk_dims_.size();
+            chunk_dims_.push_back((int)kv.first);
+            chunk_mems_.push_back(std::vector<int>(kv.second.begin(), kv.second.end()));
+            for (size_t mi : kv.second) {
+                pos_mem.push_back((int)mi); pos_dim.push_back((int)kv.first); pos_slot.push_back(slot);
+                pos_sub.push_back((int)pp.memory_to_subtable_index[mi]);
+            }
+        }
+        nslots_ = (int)chunk_dims_.size();
+
+        NodeMeta meta;
+        memset(&meta, 0, sizeof meta);
+        meta.C = (int)pp.C; meta.log2M = log2M_; meta.num_lookups = (int)pp.lookups.size(); meta.num_memories = m_;
+        for (size_t l = 0; l < pp.lookups.size(); l++) {
+            unsigned tb = 0;
+            for (unsigned b : pp.lookups[l]->chunk_bits(pp.M)) tb += b;
+            meta.total_bits[l] = (u8)std::min(tb, 64u);
+            auto& mem = pp.lookup_to_memory_indices[l];
+            if (mem.size() > (size_t)HG_MAX_C) throw std::runtime_error("LassoNode: lookup uses too many memories");
+            meta.lookup_nmem[l] = (u8)mem.size();
+            for (size_t t = 0; t < mem.size(); t++) { meta.lookup_mem[l][t] = (u8)mem[t]; meta.mem_used[mem[t]] |= 1ULL << l; }
+        }
+        for (int mi = 0; mi < m_; mi++) { meta.mem_sub[mi] = (u8)pp.memory_to_subtable_index[mi]; meta.mem_dim[mi] = (u8)pp.memory_to_dimension_index[mi]; }
+        for (int s = 0; s < nslots_; s++) slot_used_.push_back(meta.mem_used[chunk_dims_[s]]);
+        for (int s = 0; s < nslots_; s++) slot_addr_dim_.push_back(meta.mem_dim[chunk_dims_[s]]);
+        meta_host_ = meta;
+
+        d_meta_.alloc(1);
+        HG_CUDA(cudaMemcpy(d_meta_.p, &meta, sizeof meta, cudaMemcpyHostToDevice));
+        d_row_lookup_.alloc(R_);
+        {
+            std::vector<uint8_t> rl(R_, 0xFF);
+            std::copy(row_lookup.begin(), row_lookup.end(), rl.begin());
+            for (auto v : row_lookup) if (v >= pp.lookups.size()) throw std::runtime_error("LassoNode: lookup index out of range");
+            HG_CUDA(cudaMemcpy(d_row_lookup_.p, rl.data(), R_, cudaMemcpyHostToDevice));
+        }
+        // materialised subtables (lasso.rs:604-609), lifted with F::from(u64)
+        {
+            auto mats = pp.materialize_subtables();
+            std::vector<B> flat(mats.size() * M_);
+            for (size_t s = 0; s < mats.size(); s++) for (size_t i = 0; i < M_; i++) flat[s * M_ + i] = FP::b_from_u64(mats[s][i]);
+            d_subtables_.alloc(flat.size());
+            HG_CUDA(cudaMemcpy(d_subtables_.p, flat.data(), flat.size() * sizeof(B), cudaMemcpyHostToDevice));
+        }
+        auto up_int = [](DevBuf<int>& b, const std::vector<int>& v) { b.alloc(v.size()); HG_CUDA(cudaMemcpy(b.p, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice)); };
+        up_int(d_pos_mem_, pos_mem); up_int(d_pos_dim_, pos_dim); up_int(d_pos_slot_, pos_slot); up_int(d_pos_sub_, pos_sub);
+
+        // work buffers
+        d_dims_.alloc(pp.C * R_);
+        d_E_.alloc((size_t)m_ * R_);
+        d_coll_.alloc(2 * R_);  // [E_0 copy is not needed: table 0 of the collation is E_0 itself] -> coll = [E_0 | S]
+        d_out_.alloc(R_);
+        d_read_cts_.alloc((size_t)nslots_ * R_);
+        d_final_cts_.alloc((size_t)nslots_ * M_);
+        rows_per_block_ = 4096;
+        nblk_cnt_ = (int)((std::max<size_t>(n_rows_, 1) + rows_per_block_ - 1) / rows_per_block_);
+        d_blk_hist_.alloc((size_t)nblk_cnt_ * M_);
+        d_blk_base_.alloc((size_t)nblk_cnt_ * M_);
+        d_eq_.alloc(std::max(R_, M_));
+        d_coeff_coll_.alloc(m_);
+        d_wpow_.alloc(HG_MAX_C);
+        d_gp_coeffs_.alloc(2 * (size_t)m_);
+        // product trees: sum_k 2m * (N >> k) < 2m * 2N
+        d_tree1_.alloc(2 * (size_t)m_ * 2 * R_);
+        d_tree2_.alloc(2 * (size_t)m_ * 2 * M_);
+        size_t nmax = std::max(R_, M_) / 2;  // longest sumcheck table
+        d_bufA_.alloc(std::max<size_t>(4 * (size_t)m_ * (nmax / 2), 4 * (size_t)m_));
+        d_bufB_.alloc(std::max<size_t>(4 * (size_t)m_ * (nmax / 4), 4 * (size_t)m_));
+        max_blocks_ = ctx->sm_count * 8;
+        size_t batch = std::max<size_t>((size_t)m_, pp.C);
+        d_partials_.alloc((size_t)max_blocks_ * 4 * batch);
+        d_counters_.alloc(batch + 8);
+        HG_CUDA(cudaMemset(d_counters_.p, 0, d_counters_.bytes()));
+        sc_.partials = d_partials_.p; sc_.counters = d_counters_.p; sc_.max_blocks = max_blocks_;
+
+        // challenge / message budget
+        size_t v = num_vars_, lm = log2M_;
+        total_chal_ = v + v + 2 + gp_chal_count(v) + gp_chal_count(lm);
+        size_t msg = 1 + 4 * v + gp_msg_count(v) + gp_msg_count(lm) + pp.C + 2 * nslots_ + m_ + 16;
+        ch_.reset(new Channel<FP>(ctx, total_chal_ + 4, msg));
+
+        // constant coefficient vectors
+        {
+            std::vector<B> cc(m_), wp(HG_MAX_C);
+            B w = FP::b_from_u64(pp.lookups.empty() ? M_ : pp.lookups[0]->combine_weight_base(pp.M));  // mock lookup = first in map order (lasso.rs:65)
+            B p = FP::b_one();
+            for (int i = 0; i < m_; i++) { cc[i] = p; p = FP::b_mul(p, w); }
+            coll_coeff_host_ = cc;
+            p = FP::b_one();
+            for (int t = 0; t < HG_MAX_C; t++) { wp[t] = p; p = FP::b_mul(p, FP::b_from_u64(M_)); }
+            HG_CUDA(cudaMemcpy(d_wpow_.p, wp.data(), wp.size() * sizeof(B), cudaMemcpyHostToDevice));
+        }
+        HG_CUDA(cudaFuncSetAttribute(k_cnt_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(M_ * 2)));
+        HG_CUDA(cudaFuncSetAttribute(k_cnt_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(M_ * 2)));
+    }
+
+    size_t device_bytes() const {
+        return d_dims_.bytes() + d_E_.bytes() + d_coll_.bytes() + d_out_.bytes() + d_read_cts_.bytes() + d_final_cts_.bytes() + d_blk_hist_.bytes() +
+               d_blk_base_.bytes() + d_eq_.bytes() + d_tree1_.bytes() + d_tree2_.bytes() + d_bufA_.bytes() + d_bufB_.bytes() + d_subtables_.bytes();
+    }
+    size_t num_rows() const { return n_rows_; }
+    int num_vars() const { return num_vars_; }
+    size_t total_challenges() const { return total_chal_; }
+
+    // lasso.rs:57-114. d_inputs: device pointer, n_inputs base elements (the node's single input poly, lasso.rs:64).
+    // Output: the claim (r, claimed_sum) for input 0 (lasso.rs:97,113).
+    void prove(const B* d_inputs, size_t n_inputs, Keccak256Transcript<FP>& tr, ProveMode mode, const WireOptions& wo, std::vector<X>* out_point,
+               X* out_value) {
+        Channel<FP>& ch = *ch_;
+        cudaStream_t s = ctx_->stream;
+        const size_t R = R_, M = M_;
+        const int m = m_, v = num_vars_;
+        const size_t rows = std::min(n_inputs, n_rows_);  // izip! stops at the shorter (Q9)
+        ch.begin(&tr, mode, total_chal_);
+
+        // collation coefficients (A5)
+        {
+            std::vector<B> cc = coll_coeff_host_;
+            if (!wo.a5_ascending) std::reverse(cc.begin(), cc.end());
+            HG_CUDA(cudaMemcpyAsync(d_coeff_coll_.p, cc.data(), cc.size() * sizeof(B), cudaMemcpyHostToDevice, s));
+            HG_CUDA(cudaStreamSynchronize(s));  // cc is a stack temporary
+        }
+        // ---- polynomialize (lasso.rs:157-250)
+        B* d_S = d_coll_.p + R;
+        k_polynomialize<FP><<<(unsigned)((R + HG_BLOCK - 1) / HG_BLOCK), HG_BLOCK, 0, s>>>(d_inputs, rows, d_row_lookup_.p, d_meta_.p, d_subtables_.p,
+                                                                                          d_coeff_coll_.p, d_wpow_.p, R, d_dims_.p, d_E_.p, d_S, d_out_.p);
+        HG_LAUNCH_CHECK(); ctx_->launches++;
+        HG_CUDA(cudaMemcpyAsync(d_coll_.p, d_E_.p, R * sizeof(B), cudaMemcpyDeviceToDevice, s));
+        HG_CUDA(cudaMemsetAsync(d_read_cts_.p, 0, d_read_cts_.bytes(), s));
+        for (int sl = 0; sl < nslots_; sl++) {
+            const u16* addr = d_dims_.p + (size_t)slot_addr_dim_[sl] * R;
+            k_cnt_hist<<<nblk_cnt_, 1024, M * 2, s>>>(addr, d_row_lookup_.p, slot_used_[sl], rows, rows_per_block_, d_blk_hist_.p, log2M_);
+            HG_LAUNCH_CHECK();
+            k_cnt_scan<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(d_blk_hist_.p, nblk_cnt_, log2M_, d_blk_base_.p, d_final_cts_.p + (size_t)sl * M);
+            HG_LAUNCH_CHECK();
+            k_cnt_rank<<<nblk_cnt_, 32, M * 2, s>>>(addr, d_row_lookup_.p, slot_used_[sl], rows, R, rows_per_block_, d_blk_base_.p, log2M_,
+                                                    d_read_cts_.p + (size_t)sl * R);
+            HG_LAUNCH_CHECK();
+            ctx_->launches += 3;
+        }
+
+        // ---- r, claimed sum (lasso.rs:85, :264, :269)
+        const size_t r_idx = ch.squeeze(v);
+        const size_t sum_off = ch.alloc_msg(1);
+        eval_tables<B>(ch, d_out_.p, R, 1, R, r_idx, v, sum_off);
+        auto coll_state = std::make_shared<ScHostState<FP>>();
+        {
+            Channel<FP>* chp = &ch;
+            ch.emit([chp, coll_state, sum_off]() {
+                X cs = chp->msg(sum_off);
+                chp->transcript().write_felt_ext(cs);
+                coll_state->claim = cs;
+            });
+        }
+        // ---- collation sumcheck (lasso.rs:271-279): t_0 * sum_i c_i t_i == E_0 * S with S = sum_i c_i E_i
+        {
+            X one_one[2] = {FP::x_zero(), FP::x_one()};
+            // g(E_0, S) = E_0 * (0 * E_0 + 1 * S): nterm = 2, arity 1, tables [E_0 | S]
+            HG_CUDA(cudaMemcpyAsync(d_gp_coeffs_.p, one_one, sizeof one_one, cudaMemcpyHostToDevice, s));
+            HG_CUDA(cudaStreamSynchronize(s));
+            sumcheck_dev<FP, 1>(ctx_, ch, wo, d_coll_.p, R, 2, d_gp_coeffs_.p, d_bufA_.p, d_bufB_.p, sc_, coll_state, nullptr, nullptr);
+        }
+        // ---- gamma, tau (lasso.rs:99)
+        const size_t gt_idx = ch.squeeze(2);
+        // ---- memory checking (lasso.rs:292-339, prover.rs:35-181)
+        k_hash_rw<FP><<<dim3((unsigned)((R + HG_BLOCK - 1) / HG_BLOCK), m), HG_BLOCK, 0, s>>>(d_dims_.p, d_read_cts_.p, d_E_.p, d_pos_mem_.p, d_pos_dim_.p,
+                                                                                               d_pos_slot_.p, ch.d_chal(gt_idx), R, m, d_tree1_.p);
+        HG_LAUNCH_CHECK(); ctx_->launches++;
+        k_hash_if<FP><<<dim3((unsigned)((M + HG_BLOCK - 1) / HG_BLOCK), m), HG_BLOCK, 0, s>>>(d_subtables_.p, d_final_cts_.p, d_pos_sub_.p, d_pos_slot_.p,
+                                                                                               ch.d_chal(gt_idx), M, m, d_tree2_.p);
+        HG_LAUNCH_CHECK(); ctx_->launches++;
+        size_t x_idx = 0, y_idx = 0;
+        grand_product(ch, wo, d_tree1_.p, R, &x_idx);
+        grand_product(ch, wo, d_tree2_.p, M, &y_idx);
+        // ---- openings (prover.rs:173-178, mod.rs:80-93)
+        const size_t o_dims = ch.alloc_msg(pp_.C), o_rts = ch.alloc_msg(nslots_), o_fcs = ch.alloc_msg(nslots_), o_e = ch.alloc_msg(m);
+        build_eq(ch, x_idx, v);
+        dot_tables<u16>(ch, d_dims_.p, R, (int)pp_.C, R, o_dims);
+        dot_tables<u32>(ch, d_read_cts_.p, R, nslots_, R, o_rts);
+        dot_tables<B>(ch, d_E_.p, R, m, R, o_e);
+        build_eq(ch, y_idx, log2M_);
+        dot_tables<u32>(ch, d_final_cts_.p, M, nslots_, M, o_fcs);
+        {
+            Channel<FP>* chp = &ch;
+            auto dims = chunk_dims_; auto mems = chunk_mems_;
+            ch.emit([chp, dims, mems, o_dims, o_rts, o_fcs, o_e]() {
+                auto& t = chp->transcript();
+                for (size_t c = 0; c < dims.size(); c++) {
+                    t.write_felt_ext(chp->msg(o_dims + dims[c]));
+                    t.write_felt_ext(chp->msg(o_rts + c));
+                    t.write_felt_ext(chp->msg(o_fcs + c));
+                    for (int mi : mems[c]) t.write_felt_ext(chp->msg(o_e + mi));
+                }
+            });
+        }
+        ch.flush();
+        if (ch.chal_used() != total_chal_) throw std::runtime_error("LassoNode: challenge count mismatch");
+        if (out_point) { out_point->resize(v); for (int i = 0; i < v; i++) (*out_point)[i] = ch.chal(r_idx + i); }
+        if (out_value) *out_value = ch.msg(sum_off);
+    }
+
+    // test hooks: copies of the polynomialised witness
+    void download_polys(std::vector<u16>* dims, std::vector<u32>* read_cts, std::vector<u32>* final_cts, std::vector<B>* E) {
+        HG_CUDA(cudaStreamSynchronize(ctx_->stream));
+        auto dl = [](auto* vec, auto& buf) { vec->resize(buf.n); HG_CUDA(cudaMemcpy(vec->data(), buf.p, buf.bytes(), cudaMemcpyDeviceToHost)); };
+        if (dims) dl(dims, d_dims_);
+        if (read_cts) dl(read_cts, d_read_cts_);
+        if (final_cts) dl(final_cts, d_final_cts_);
+        if (E) dl(E, d_E_);
+    }
+    const std::vector<int>& chunk_dims() const { return chunk_dims_; }
+
+  private:
+    static size_t gp_chal_count(size_t nvars) {  // layers nv = 0..nvars-1: mu each; gamma + nv round challenges for nv >= 1
+        size_t c = 0;
+        for (size_t nv = 0; nv < nvars; nv++) c += 1 + (nv ? 1 + nv : 0);
+        return c;
+    }
+    size_t gp_msg_count(size_t nvars) const {
+        size_t c = 2 * (size_t)m_;  // roots
+        for (size_t nv = 0; nv < nvars; nv++) c += 4 * (size_t)m_ + 4 * nv;
+        return c;
+    }
+    void build_eq(Channel<FP>& ch, size_t point_idx, int nv) {
+        size_t n = (size_t)1 << nv;
+        k_eq_build<FP><<<(unsigned)((n + HG_BLOCK - 1) / HG_BLOCK), HG_BLOCK, 0, ctx_->stream>>>(ch.d_chal(point_idx), nv, d_eq_.p);
+        HG_LAUNCH_CHECK(); ctx_->launches++;
+    }
+    template <class T> void dot_tables(Channel<FP>& ch, const T* tables, size_t stride, int ntab, size_t n, size_t msg_off) {
+        int blocks = (int)std::min<size_t>((n + HG_BLOCK - 1) / HG_BLOCK, (size_t)ctx_->sm_count * 2);
+        k_dot_eq<FP, T><<<dim3(blocks, ntab), HG_BLOCK, 0, ctx_->stream>>>(tables, stride, n, d_eq_.p, d_partials_.p, d_counters_.p, ch.d_msg(msg_off));
+        HG_LAUNCH_CHECK(); ctx_->launches++;
+    }
+    template <class T> void eval_tables(Channel<FP>& ch, const T* tables, size_t stride, int ntab, size_t n, size_t point_idx, int nv, size_t msg_off) {
+        build_eq(ch, point_idx, nv);
+        dot_tables<T>(ch, tables, stride, ntab, n, msg_off);
+    }
+
+    // prove_grand_product (prover.rs:183-266) over nvec = 2m vectors of length N stored at tree (layer 0), upper layers appended
+    void grand_product(Channel<FP>& ch, const WireOptions& wo, B* tree, size_t N, size_t* point_idx) {
+        cudaStream_t s = ctx_->stream;
+        const int nvec = 2 * m_;
+        int nvars = 0;
+        while (((size_t)1 << nvars) < N) nvars++;
+        // layer k has vectors of length N >> k, k = 0..nvars-1 (prover.rs:191-195)
+        std::vector<B*> layer(nvars);
+        layer[0] = tree;
+        for (int k = 1; k < nvars; k++) {
+            layer[k] = layer[k - 1] + (size_t)nvec * (N >> (k - 1));
+            size_t h = N >> k;
+            k_tree_up<FP><<<dim3((unsigned)((h + HG_BLOCK - 1) / HG_BLOCK), nvec), HG_BLOCK, 0, s>>>(layer[k - 1], layer[k], h);
+            HG_LAUNCH_CHECK(); ctx_->launches++;
+        }
+        const size_t roots_off = ch.alloc_msg(nvec), ev0_off = ch.alloc_msg(2 * nvec);
+        k_tree_top<FP><<<(nvec + HG_BLOCK - 1) / HG_BLOCK, HG_BLOCK, 0, s>>>(layer[nvars - 1], nvec, ch.d_msg(roots_off), ch.d_msg(ev0_off));
+        HG_LAUNCH_CHECK(); ctx_->launches++;
+        struct GpHost { std::vector<X> claimed; std::vector<X> evals; size_t mu_idx = 0; bool pending = false; };
+        auto gp = std::make_shared<GpHost>();
+        Channel<FP>* chp = &ch;
+        ch.emit([chp, gp, roots_off, ev0_off, nvec]() {
+            auto& t = chp->transcript();
+            gp->claimed.resize(nvec);
+            for (int i = 0; i < nvec; i++) { gp->claimed[i] = chp->msg(roots_off + i); t.write_felt_ext(gp->claimed[i]); }  // prover.rs:197-221
+            gp->evals.resize(2 * nvec);
+            for (int i = 0; i < 2 * nvec; i++) { gp->evals[i] = chp->msg(ev0_off + i); t.write_felt_ext(gp->evals[i]); }   // prover.rs:257
+        });
+        size_t mu_idx = ch.squeeze(1);  // prover.rs:259
+        size_t first_chal = mu_idx;
+        for (int nv = 1; nv < nvars; nv++) {
+            const size_t prev_mu = mu_idx;
+            const size_t gamma_idx = ch.squeeze(1);  // prover.rs:238
+            k_powers<FP><<<1, 32, 0, s>>>(ch.d_chal(gamma_idx), nvec, wo.a5_ascending, d_gp_coeffs_.p);
+            HG_LAUNCH_CHECK(); ctx_->launches++;
+            auto st = std::make_shared<ScHostState<FP>>();
+            const int asc = wo.a5_ascending;
+            ch.emit([chp, gp, st, prev_mu, gamma_idx, nvec, asc]() {
+                // layer_down_claim (prover.rs:288-294) then sum_check_claim (prover.rs:281-286)
+                X mu = chp->chal(prev_mu), g = chp->chal(gamma_idx);
+                X claim = FP::x_zero(), p = FP::x_one();
+                for (int i = 0; i < nvec; i++) {
+                    X l = gp->evals[2 * i], r = gp->evals[2 * i + 1];
+                    gp->claimed[i] = FP::x_add(l, FP::x_mul(mu, FP::x_sub(r, l)));
+                    claim = FP::x_add(claim, FP::x_mul(gp->claimed[i], p));
+                    p = FP::x_mul(p, g);
+                }
+                (void)asc;  // the claim always uses ascending powers (prover.rs:281-286); only the expression order is an assumption
+                st->claim = claim;
+            });
+            size_t sc_first = 0, ev_off = 0;
+            const B* tables = layer[nvars - 1 - nv];
+            sumcheck_dev<FP, 2>(ctx_, ch, wo, tables, (size_t)1 << nv, nvec, d_gp_coeffs_.p, d_bufA_.p, d_bufB_.p, sc_, st, &sc_first, &ev_off);
+            ch.emit([chp, gp, ev_off, nvec]() {
+                auto& t = chp->transcript();
+                for (int i = 0; i < 2 * nvec; i++) { gp->evals[i] = chp->msg(ev_off + i); t.write_felt_ext(gp->evals[i]); }  // prover.rs:257
+            });
+            mu_idx = ch.squeeze(1);
+            first_chal = sc_first;
+        }
+        // x = round challenges of the bottom layer ++ [mu]  (prover.rs:261-264): contiguous in squeeze order
+        if (nvars > 1 && mu_idx != first_chal + (size_t)(nvars - 1)) throw std::runtime_error("grand_product: challenge layout broken");
+        *point_idx = first_chal;
+    }
+
+    DeviceCtx* ctx_;
+    LassoPreprocessing pp_;
+    int num_vars_, log2M_ = 16, m_ = 0, nslots_ = 0, rows_per_block_ = 4096, nblk_cnt_ = 1, max_blocks_ = 0;
+    size_t n_rows_, R_ = 0, M_ = 0, total_chal_ = 0;
+    NodeMeta meta_host_;
+    std::vector<int> chunk_dims_;
+    std::vector<std::vector<int>> chunk_mems_;
+    std::vector<u64> slot_used_;
+    std::vector<int> slot_addr_dim_;
+    std::vector<B> coll_coeff_host_;
+    DevBuf<NodeMeta> d_meta_;
+    DevBuf<u8> d_row_lookup_;
+    DevBuf<B> d_subtables_, d_E_, d_coll_, d_out_, d_coeff_coll_, d_wpow_, d_tree1_, d_tree2_;
+    DevBuf<u16> d_dims_, d_blk_hist_;
+    DevBuf<u32> d_read_cts_, d_final_cts_, d_blk_base_;
+    DevBuf<int> d_pos_mem_, d_pos_dim_, d_pos_slot_, d_pos_sub_;
+    DevBuf<X> d_eq_, d_gp_coeffs_, d_bufA_, d_bufB_, d_partials_;
+    DevBuf<unsigned> d_counters_;
+    ScScratch sc_;
+    std::unique_ptr<Channel<FP>> ch_;
+};
+
+}  // namespace hg

@@ -1,0 +1,127 @@
+/* hg_b200.h — C ABI of the B200-native hyper-greco GKR/Lasso proving path.
+ *
+ * This is the boundary a Rust `extern "C"` FFI crate binds (INTEGRATION.md shows the binding). Plain pointers and
+ * sizes only; no C++ / torch types. Every entry point cites the reference interface it replaces, paths relative to
+ * /root/reference.
+ *
+ * Conventions
+ *   field ids        HG_FIELD_GOLDILOCKS: F = Goldilocks, E = GoldilocksExt2 (bfv-gkr/src/sk_encryption_circuit.rs:554-612)
+ *                    HG_FIELD_BN254     : F = E = bn256::Fr                  (bfv-gkr/src/sk_encryption_circuit.rs:616-626)
+ *   element encoding canonical integer in little-endian u64 limbs: base element = HG limbs(field) u64,
+ *                    extension element = degree(field) base elements in `as_bases()` order.
+ *   return value     0 = ok, non-zero = error; hg_last_error() returns the message (thread-local). No C++ exception
+ *                    and no sticky CUDA error crosses this boundary.
+ *   threading        one hg_ctx = one device + one stream, driven by one host thread at a time.
+ *   ownership        handles are created/destroyed only through this API; the library never frees caller memory and
+ *                    never keeps a host pointer after a call returns.
+ */
+#ifndef HG_B200_H
+#define HG_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HG_FIELD_GOLDILOCKS 0
+#define HG_FIELD_BN254 1
+
+#define HG_MODE_PREFETCH 0    /* challenges squeezed up front; legal for Keccak256Transcript (transcript.rs:156,183-203) */
+#define HG_MODE_INTERACTIVE 1 /* one host round trip per squeeze; legal for any transcript */
+
+/* Upstream-format switches: ids for hg_ctx_set_option */
+#define HG_OPT_A3_WIRE 3       /* 0 coefficients c0,c2..cd (default) / 1 evaluations h(0),h(2)..h(d) */
+#define HG_OPT_A3_H1 31        /* 0 h(1) := claim - h(0) (default) / 1 h(1) from the tables */
+#define HG_OPT_A5_ASCENDING 5  /* distribute_powers: 1 ascending (default) / 0 first expression highest power */
+
+typedef struct hg_ctx hg_ctx;
+typedef struct hg_transcript hg_transcript;
+typedef struct hg_lasso_pp hg_lasso_pp;
+typedef struct hg_lasso_node hg_lasso_node;
+typedef struct hg_buf hg_buf;
+
+const char* hg_last_error(void);
+int hg_version(void);
+
+/* ---- context ------------------------------------------------------------------------------------------------ */
+int hg_ctx_create(int device, int field_id, hg_ctx** out);
+void hg_ctx_destroy(hg_ctx* ctx);
+int hg_ctx_set_option(hg_ctx* ctx, int option, int value);
+int hg_ctx_synchronize(hg_ctx* ctx);
+/* kernels enqueued by this context so far */
+uint64_t hg_ctx_launch_count(hg_ctx* ctx);
+/* the CUDA stream kernels are launched on (cudaStream_t), for event timing by the caller */
+void* hg_ctx_stream(hg_ctx* ctx);
+
+/* ---- device buffers (owned by the caller through the handle; Rust frees them in Drop) --------------------------- */
+int hg_buf_alloc(hg_ctx* ctx, size_t bytes, hg_buf** out);
+int hg_buf_upload(hg_ctx* ctx, hg_buf* buf, size_t offset, const void* host, size_t bytes);
+int hg_buf_download(hg_ctx* ctx, const hg_buf* buf, size_t offset, void* host, size_t bytes);
+void* hg_buf_device_ptr(hg_buf* buf);
+size_t hg_buf_size(const hg_buf* buf);
+void hg_buf_free(hg_buf* buf);
+
+/* ---- transcript: replaces Keccak256Transcript (bfv-gkr/src/transcript.rs:117-203) ----------------------------- */
+int hg_transcript_new(int field_id, hg_transcript** out);                                      /* ::default()      :431 of sk_encryption_circuit.rs */
+int hg_transcript_from_proof(int field_id, const uint8_t* proof, size_t len, hg_transcript** out); /* ::from_proof  transcript.rs:131-135 */
+void hg_transcript_free(hg_transcript* t);
+int hg_transcript_squeeze_challenge(hg_transcript* t, uint64_t* out_ext);   /* transcript.rs:149-154 */
+int hg_transcript_write_felt_ext(hg_transcript* t, const uint64_t* ext);    /* transcript.rs:191-195 */
+int hg_transcript_read_felt_ext(hg_transcript* t, uint64_t* out_ext);       /* transcript.rs:172-177 */
+size_t hg_transcript_proof_len(const hg_transcript* t);                     /* into_proof, transcript.rs:126-128 */
+int hg_transcript_proof_copy(const hg_transcript* t, uint8_t* out, size_t cap);
+size_t hg_transcript_num_squeezed(const hg_transcript* t);                  /* base-field squeezes so far */
+
+/* ---- Lasso preprocessing: LassoPreprocessing::preprocess::<C, M> over RangeLookup types (lasso/src/lasso.rs:527-627,
+ *      lasso/src/table/range.rs:177-274). `bounds[i]` is the argument of RangeLookup::new_boxed. ---------------- */
+int hg_lasso_preprocess(const uint64_t* bounds, size_t n_bounds, size_t C, size_t M, hg_lasso_pp** out);
+void hg_lasso_pp_free(hg_lasso_pp* pp);
+size_t hg_lasso_pp_num_lookups(const hg_lasso_pp* pp);
+size_t hg_lasso_pp_num_subtables(const hg_lasso_pp* pp);
+size_t hg_lasso_pp_num_memories(const hg_lasso_pp* pp);
+/* index of RangeLookup::id_for(bound) in preprocessing (BTreeMap) order, or -1 */
+int hg_lasso_pp_lookup_index(const hg_lasso_pp* pp, uint64_t bound);
+/* memory_to_subtable_index / memory_to_dimension_index (lasso.rs:575-585); arrays of num_memories */
+int hg_lasso_pp_memory_maps(const hg_lasso_pp* pp, uint32_t* mem_to_subtable, uint32_t* mem_to_dimension);
+/* subtable id string ("full", "bound_<b>") of subtable `idx`, NUL-terminated into out[cap] */
+int hg_lasso_pp_subtable_id(const hg_lasso_pp* pp, size_t idx, char* out, size_t cap);
+
+/* ---- Lasso node: LassoNode::<F, E, C, M>::new + Node::prove_claim_reduction (lasso/src/lasso.rs:143-154, :57-114) -- */
+/* lookups: Vec<LookupId> given as run-length segments (bound of the RangeLookup, run length), in row order. */
+int hg_lasso_node_new(hg_ctx* ctx, const hg_lasso_pp* pp, size_t num_vars, const uint64_t* seg_bounds, const uint64_t* seg_lens, size_t n_segs,
+                      hg_lasso_node** out);
+void hg_lasso_node_free(hg_lasso_node* node);
+size_t hg_lasso_node_log2_input_size(const hg_lasso_node* node);  /* Node::log2_input_size, lasso.rs:45-47 */
+size_t hg_lasso_node_device_bytes(const hg_lasso_node* node);
+/* prove_claim_reduction. `inputs` is inputs[0] of the node (n_inputs base elements): a HOST pointer when
+ * inputs_on_device == 0 (copied to the device inside the call), else a device pointer (e.g. hg_buf_device_ptr).
+ * Messages are appended to `t` exactly as the reference writes them. On return
+ * out_point[num_vars] / out_value hold the single EvalClaim the node returns for its input (lasso.rs:97,113). */
+int hg_lasso_node_prove(hg_lasso_node* node, const void* inputs, size_t n_inputs, int inputs_on_device, hg_transcript* t, int mode,
+                        uint64_t* out_point, uint64_t* out_value);
+/* test hook: polynomialised witness of the last prove (lasso.rs:157-250). dims: C x R u16, read_cts: chunks x R u32,
+ * final_cts: chunks x M u32, e_polys: num_memories x R base elements. Any pointer may be NULL. */
+int hg_lasso_node_download_polys(hg_lasso_node* node, uint16_t* dims, uint32_t* read_cts, uint32_t* final_cts, uint64_t* e_polys);
+size_t hg_lasso_node_num_chunks(const hg_lasso_node* node);
+
+/* ---- generic sumcheck: gkr::sum_check::prove_sum_check with a Generic function of the shape the lasso crate builds
+ *      (lasso/src/lasso.rs:457-475, lasso/src/memory_checking/prover.rs:268-279):
+ *          g = poly(0) * sum_{i<n_terms} coeffs[i] * prod_{k<arity} poly(arity*i + k)
+ *      tables: device pointer to n_terms*arity base tables of 2^num_vars elements, back to back.
+ *      Writes the round messages to `t`, squeezes one challenge per round; out_point[num_vars], out_evals[n_terms*arity]. */
+int hg_sumcheck_prove(hg_ctx* ctx, int arity, size_t n_terms, size_t num_vars, const uint64_t* coeffs_ext, const void* d_tables,
+                      const uint64_t* claim_ext, hg_transcript* t, int mode, uint64_t* out_point, uint64_t* out_evals);
+
+/* ---- batched multilinear evaluation: MultilinearPoly::evaluate (lasso/src/memory_checking/mod.rs:80-93) ---------
+ *      d_tables: n_tables base tables of 2^num_vars elements (stride elements apart); point: num_vars ext elements (host). */
+int hg_mle_eval_batch(hg_ctx* ctx, const void* d_tables, size_t n_tables, size_t stride, size_t num_vars, const uint64_t* point_ext,
+                      uint64_t* out_ext);
+
+/* field self-test kernel: out[i] = a[i] (op) b[i] on extension elements, op 0 add 1 sub 2 mul (device arithmetic check) */
+int hg_field_selftest(hg_ctx* ctx, int op, const uint64_t* a_ext, const uint64_t* b_ext, size_t n, uint64_t* out_ext);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HG_B200_H */
