@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native hyper-greco proving path (contract: see the task statement / DESIGN.md "Measurement").
+
+    python bench.py --gpus 1 --steps K --warmup W                 # our arm
+    python bench.py --impl reference --gpus 1 --steps K --warmup W   # CPU arm: the oracle port on the host cores
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # one rank per GPU, weak scaling
+
+A step = one proof: LassoNode::prove_claim_reduction (lasso/src/lasso.rs:57-114) on a synthetic BFV SK-encryption witness
+of the n=32768, k=16, Goldilocks parameter set (BASELINE.json metric config). Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "gkr_prove_proofs_per_sec"
+UNIT = "proofs/s"
+DEFAULT_CONFIG = "32768_16x59_65537"
+
+
+def workload_desc(name, P, nv, m):
+    return {
+        "workload": f"lasso_node.prove_claim_reduction n={P.N} k={P.K} goldilocks/ext2 (num_vars={nv}, memories={m}, C=4, M=65536), one proof per step per GPU",
+        "scope": "Lasso range-check node = collation sumcheck + 2 grand-product memory-checking trees + openings (README: 76% of the reference's GKR prove); "
+                 "Vanilla/FFT layers not in the timed region yet",
+        "params": name,
+        "parallelism": "one independent proof instance per GPU, no data-path collective",
+        "cache": "working set ~3.5 GB per proof >> 126 MB L2, no explicit flush between steps",
+    }
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons DURING the timed region (pynvml, 20 ms period)."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop, self._t = index, [], set(), None, threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "hw_power_brake": 0x80,
+                 "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def make_case(name, seed):
+    import numpy as np
+    import hyper_greco_b200  # noqa: F401
+    from hyper_greco_b200 import params, witness
+    P = params.PARAMS[name]
+    args = witness.synth_witness(P, seed)
+    inp = np.array(witness.lasso_inputs(P, args), dtype=np.uint64)
+    return P, inp, witness.lasso_lookup_bounds(P), witness.lasso_lookup_segments(P), witness.lasso_num_vars(P)
+
+
+def oracle_case(hgo, bounds, segs):
+    import numpy as np
+    opp = hgo.Preprocessing(bounds)
+    rows = np.concatenate([np.full(l, opp.lookup_index(b), np.int32) for b, l in segs])
+    return opp, rows
+
+
+def run_reference(args):
+    """CPU arm: the reference's own implementation cannot be built here (Rust nightly + un-vendored git deps),
+    so this times the oracle port (oracle/protocol.hpp, OpenMP over all host cores) on the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import hgo
+    hgo.build()
+    P, inp, bounds, segs, nv = make_case(args.config, 0)
+    opp, rows = oracle_case(hgo, bounds, segs)
+    cores = hgo.num_threads()
+    t0 = time.perf_counter()
+    hgo.lasso_prove(0, opp, nv, rows, inp)
+    t1 = time.perf_counter() - t0
+    budget = 240.0
+    steps = max(1, min(args.steps, int(budget / max(t1, 1e-3)) - 1))
+    warm = 0 if steps < args.steps else max(0, min(args.warmup - 1, 1))
+    for _ in range(warm):
+        hgo.lasso_prove(0, opp, nv, rows, inp)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        hgo.lasso_prove(0, opp, nv, rows, inp)
+    dt = time.perf_counter() - t0
+    v = steps / dt
+    sample = f"{steps} full proofs of the same workload (first call {t1:.1f}s used as warm-up" + (f"; --steps {args.steps} capped to fit ~4 min" if steps < args.steps else "") + ")"
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm + 1,
+            "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": workload_desc(args.config, P, nv, opp.num_memories),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import hyper_greco_b200  # noqa: F401
+    from hyper_greco_b200 import api
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    api.lib()
+
+    P, inp, bounds, segs, nv = make_case(args.config, seed=rank)
+    ctx = api.Context(local)
+    pp = api.LassoPreprocessing.preprocess(bounds)
+    node = api.LassoNode(ctx, pp, nv, segs)
+    d_inp = api.DeviceBuffer.from_numpy(ctx, inp)
+    pinned = torch.empty(inp.size, dtype=torch.int64).pin_memory()
+    h_inp = pinned.numpy().view(np.uint64)
+    h_inp[:] = inp
+    ext = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        tr = api.Keccak256Transcript()
+        node.prove_claim_reduction(d_inp, tr, api.MODE_PREFETCH, n_inputs=inp.size)
+        return tr
+
+    def step_e2e():
+        tr = api.Keccak256Transcript()
+        node.prove_claim_reduction(h_inp, tr, api.MODE_PREFETCH)
+        return tr.into_proof()
+
+    for _ in range(max(args.warmup, 3)):
+        tr = step_resident()
+    proof_len = len(tr.into_proof())
+    l0 = ctx.launch_count
+    step_resident()
+    launches_per_step = ctx.launch_count - l0
+
+    # ---- timed region: exactly K steps, CUDA events on the launching stream, max over ranks
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record(ext)
+    barrier()
+    wall = time.perf_counter() - w0
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms, wall * 1000.0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, wall_ms = float(t[0]), float(t[1])
+    value = world * args.steps / (ms_total / 1000.0)
+
+    # ---- end to end through the C ABI with HOST buffers (H2D of the inputs and D2H of the proof messages inside)
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_wall = time.perf_counter() - w0
+    t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps / float(t[0])
+    n_chal = None
+
+    line = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel class: CUDA events around every launch, separate pass right after the timed one
+        ctx.profile(True)
+        prof_steps = 3
+        for _ in range(prof_steps):
+            step_resident()
+        prof = ctx.profile_read()
+        ctx.profile(False)
+        dom = max(prof.items(), key=lambda kv: kv[1][1])
+        dn, (dl, dms, dby) = dom
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
+        achieved = (dby / 1e9) / (dms / 1e3) if dms > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dn)
+        except Exception:
+            pass
+        total_ms = sum(v[1] for v in prof.values())
+        roofline = {"bound": "hbm", "kernel": dn, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                    "traffic": traffic, "peak_source": peak_src, "launches_per_step": dl / prof_steps, "avg_launch_us": 1000.0 * dms / max(dl, 1),
+                    "share_of_step_kernel_time": dms / total_ms if total_ms else None,
+                    "per_class": {k: {"launches": v[0] / prof_steps, "ms": v[1] / prof_steps, "alg_GB": v[2] / prof_steps / 1e9,
+                                      "GBps": (v[2] / 1e9) / (v[1] / 1e3) if v[1] > 0 else None} for k, v in prof.items()},
+                    "whole_step_alg_GB": sum(v[2] for v in prof.values()) / prof_steps / 1e9,
+                    "whole_step_frac": (sum(v[2] for v in prof.values()) / prof_steps / 1e9) / ((ms_total / args.steps) / 1e3) / peak}
+        # ---- CPU baseline: the oracle port on this box's host cores, one full proof (N=1 only)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import hgo
+            hgo.build()
+            opp, rows = oracle_case(hgo, bounds, segs)
+            t0 = time.perf_counter()
+            oproof, *_ = hgo.lasso_prove(0, opp, nv, rows, inp)
+            dt = time.perf_counter() - t0
+            same = oproof == step_e2e()
+            cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": hgo.num_threads(), "kind": "port",
+                   "sample": f"1 full proof of the same witness ({dt:.1f}s); GPU proof bytes == CPU proof bytes: {same}"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+                "data": "synthetic", "config": workload_desc(args.config, P, nv, pp.num_memories), "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(inp.nbytes + node_chal_bytes(nv)),
+                        "d2h_bytes_per_step": int(proof_len + 64 * nv)},
+                "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
+                "wall_ms_per_step": wall_ms / args.steps, "proof_bytes": proof_len, "roofline": roofline, "cpu_baseline": cpu}
+    barrier()
+    node.free()
+    d_inp.free()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+def node_chal_bytes(nv, lm=16):
+    gp = lambda k: sum(1 + ((1 + j) if j else 0) for j in range(k))
+    return 16 * (2 * nv + 2 + gp(nv) + gp(lm))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=DEFAULT_CONFIG)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -23,7 +23,7 @@ DEGREE = {GOLDILOCKS: 2, BN254: 1}
 # every symbol include/hg_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "hg_last_error", "hg_version", "hg_ctx_create", "hg_ctx_destroy", "hg_ctx_set_option", "hg_ctx_synchronize", "hg_ctx_launch_count",
-    "hg_ctx_stream", "hg_buf_alloc", "hg_buf_upload", "hg_buf_download", "hg_buf_device_ptr", "hg_buf_size", "hg_buf_free",
+    "hg_ctx_stream", "hg_ctx_profile", "hg_ctx_profile_read", "hg_kernel_class_count", "hg_kernel_class_name", "hg_buf_alloc", "hg_buf_upload", "hg_buf_download", "hg_buf_device_ptr", "hg_buf_size", "hg_buf_free",
     "hg_transcript_new", "hg_transcript_from_proof", "hg_transcript_free", "hg_transcript_squeeze_challenge", "hg_transcript_write_felt_ext",
     "hg_transcript_read_felt_ext", "hg_transcript_proof_len", "hg_transcript_proof_copy", "hg_transcript_num_squeezed",
     "hg_lasso_preprocess", "hg_lasso_pp_free", "hg_lasso_pp_num_lookups", "hg_lasso_pp_num_subtables", "hg_lasso_pp_num_memories",
@@ -55,6 +55,10 @@ def lib():
         L.hg_ctx_synchronize.argtypes = [vp]
         L.hg_ctx_launch_count.argtypes = [vp]
         L.hg_ctx_launch_count.restype = u64
+        L.hg_ctx_profile.argtypes = [vp, i32]
+        L.hg_ctx_profile_read.argtypes = [vp, i32, vp, vp, vp]
+        L.hg_kernel_class_name.argtypes = [i32]
+        L.hg_kernel_class_name.restype = C.c_char_p
         L.hg_ctx_stream.argtypes = [vp]
         L.hg_ctx_stream.restype = vp
         L.hg_buf_alloc.argtypes = [vp, sz, C.POINTER(vp)]
@@ -128,6 +132,18 @@ class Context:
     @property
     def stream(self):
         return lib().hg_ctx_stream(self.h)
+
+    def profile(self, enable: bool):
+        _chk(lib().hg_ctx_profile(self.h, 1 if enable else 0))
+
+    def profile_read(self):
+        """{class name: (launches, device ms, algorithmic bytes)} accumulated since profile(True)."""
+        out = {}
+        for k in range(lib().hg_kernel_class_count()):
+            n, ms, by = C.c_uint64(0), C.c_double(0), C.c_uint64(0)
+            _chk(lib().hg_ctx_profile_read(self.h, k, C.byref(n), C.byref(ms), C.byref(by)))
+            out[lib().hg_kernel_class_name(k).decode()] = (n.value, ms.value, by.value)
+        return out
 
     def close(self):
         if self.h:

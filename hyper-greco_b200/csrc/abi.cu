@@ -95,6 +95,26 @@ int hg_ctx_set_option(hg_ctx* ctx, int option, int value) {
 }
 int hg_ctx_synchronize(hg_ctx* ctx) { HG_TRY({ HG_CUDA(cudaSetDevice(ctx->dev.device)); HG_CUDA(cudaStreamSynchronize(ctx->dev.stream)); }) }
 uint64_t hg_ctx_launch_count(hg_ctx* ctx) { return ctx->dev.launches; }
+int hg_ctx_profile(hg_ctx* ctx, int enable) {
+    HG_TRY({
+        HG_CUDA(cudaSetDevice(ctx->dev.device));
+        ctx->dev.profile_collect();
+        if (enable) ctx->dev.profile_reset();
+        ctx->dev.profile = enable != 0;
+    })
+}
+int hg_ctx_profile_read(hg_ctx* ctx, int kernel_class, uint64_t* launches, double* ms, uint64_t* algorithmic_bytes) {
+    HG_TRY({
+        if (kernel_class < 0 || kernel_class >= KC_COUNT) throw std::runtime_error("no such kernel class");
+        HG_CUDA(cudaSetDevice(ctx->dev.device));
+        ctx->dev.profile_collect();
+        *launches = ctx->dev.cls_launches[kernel_class];
+        *ms = ctx->dev.cls_ms[kernel_class];
+        *algorithmic_bytes = ctx->dev.cls_bytes[kernel_class];
+    })
+}
+int hg_kernel_class_count(void) { return KC_COUNT; }
+const char* hg_kernel_class_name(int kernel_class) { return kernel_class_name(kernel_class); }
 void* hg_ctx_stream(hg_ctx* ctx) { return (void*)ctx->dev.stream; }
 
 int hg_buf_alloc(hg_ctx* ctx, size_t bytes, hg_buf** out) {
@@ -288,8 +308,8 @@ int hg_sumcheck_prove(hg_ctx* ctx, int arity, size_t n_terms, size_t num_vars, c
         auto st = std::make_shared<ScHostState<FP>>();
         st->claim = FP::x_from_limbs(claim_ext);
         size_t first = 0, eo = 0;
-        if (arity == 1) sumcheck_dev<FP, 1>(&ctx->dev, ch, ctx->wire, (const u64*)d_tables, n, (int)n_terms, coeffs.p, bufA.p, bufB.p, sc, st, &first, &eo);
-        else sumcheck_dev<FP, 2>(&ctx->dev, ch, ctx->wire, (const u64*)d_tables, n, (int)n_terms, coeffs.p, bufA.p, bufB.p, sc, st, &first, &eo);
+        if (arity == 1) sumcheck_dev<FP, 1>(&ctx->dev, KC_SC_COLL, ch, ctx->wire, (const u64*)d_tables, n, (int)n_terms, coeffs.p, bufA.p, bufB.p, sc, st, &first, &eo);
+        else sumcheck_dev<FP, 2>(&ctx->dev, KC_SC_GP, ch, ctx->wire, (const u64*)d_tables, n, (int)n_terms, coeffs.p, bufA.p, bufB.p, sc, st, &first, &eo);
         ch.flush();
         if (out_point) for (size_t i = 0; i < num_vars; i++) FP::x_to_limbs(ch.chal(first + i), out_point + 2 * i);
         if (out_evals) for (size_t i = 0; i < ntab; i++) FP::x_to_limbs(ch.msg(eo + i), out_evals + 2 * i);
@@ -315,11 +335,9 @@ int hg_mle_eval_batch(hg_ctx* ctx, const void* d_tables, size_t n_tables, size_t
         partials.alloc((size_t)blocks * n_tables);
         counters.alloc(n_tables);
         HG_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), s));
-        k_eq_build<FP><<<(unsigned)((n + HG_BLOCK - 1) / HG_BLOCK), HG_BLOCK, 0, s>>>(pt.p, (int)num_vars, eq.p);
-        HG_LAUNCH_CHECK();
-        k_dot_eq<FP, u64><<<dim3(blocks, (unsigned)n_tables), HG_BLOCK, 0, s>>>((const u64*)d_tables, stride, n, eq.p, partials.p, counters.p, out.p);
-        HG_LAUNCH_CHECK();
-        ctx->dev.launches += 2;
+        HG_K(&ctx->dev, KC_EQ, n * sizeof(gl2), k_eq_build<FP><<<(unsigned)((n + HG_BLOCK - 1) / HG_BLOCK), HG_BLOCK, 0, s>>>(pt.p, (int)num_vars, eq.p));
+        HG_K(&ctx->dev, KC_DOT, n_tables * n * 8 + n * sizeof(gl2),
+             k_dot_eq<FP, u64><<<dim3(blocks, (unsigned)n_tables), HG_BLOCK, 0, s>>>((const u64*)d_tables, stride, n, eq.p, partials.p, counters.p, out.p));
         std::vector<gl2> ho(n_tables);
         HG_CUDA(cudaMemcpyAsync(ho.data(), out.p, n_tables * sizeof(gl2), cudaMemcpyDeviceToHost, s));
         HG_CUDA(cudaStreamSynchronize(s));

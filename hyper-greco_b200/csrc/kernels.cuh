@@ -30,13 +30,17 @@ struct NodeMeta {
 // ---------------------------------------------------------------------------------------------------------
 // block reduction of NP extension values + cross-block finalisation by the last block to arrive.
 // partials: [gridDim.y][gridDim.x][NP]; counter: [gridDim.y]; out: [gridDim.y][NP]
-template <class FP, int NP>
+// FLAT: a single output summed over the whole (x, y) grid (partials: [gridDim.x*gridDim.y][NP], one counter).
+template <class FP, int NP, bool FLAT = false>
 __device__ __forceinline__ void block_reduce_finalize(typename FP::X (&acc)[NP], typename FP::X* partials, unsigned* counter,
                                                       typename FP::X* out) {
     typedef typename FP::X X;
     __shared__ X sm[32][NP];
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    const unsigned nblk = FLAT ? gridDim.x * gridDim.y : gridDim.x;
+    const unsigned bid = FLAT ? blockIdx.y * gridDim.x + blockIdx.x : blockIdx.x;
+    const unsigned slot = FLAT ? 0 : blockIdx.y;
 #pragma unroll
     for (int p = 0; p < NP; p++) {
         X v = acc[p];
@@ -45,7 +49,7 @@ __device__ __forceinline__ void block_reduce_finalize(typename FP::X (&acc)[NP],
         if (lane == 0) sm[warp][p] = v;
     }
     __syncthreads();
-    X* my_part = partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * NP;
+    X* my_part = partials + ((size_t)slot * nblk + bid) * NP;
     if (warp == 0) {
 #pragma unroll
         for (int p = 0; p < NP; p++) {
@@ -57,17 +61,17 @@ __device__ __forceinline__ void block_reduce_finalize(typename FP::X (&acc)[NP],
     }
     if (threadIdx.x == 0) {
         __threadfence();
-        unsigned t = atomicAdd(counter + blockIdx.y, 1u);
-        is_last = (t == gridDim.x - 1);
+        unsigned t = atomicAdd(counter + slot, 1u);
+        is_last = (t == nblk - 1);
     }
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    const X* all = partials + (size_t)blockIdx.y * gridDim.x * NP;
+    const X* all = partials + (size_t)slot * nblk * NP;
     X s[NP];
 #pragma unroll
     for (int p = 0; p < NP; p++) s[p] = FP::x_zero();
-    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+    for (unsigned b = threadIdx.x; b < nblk; b += blockDim.x)
 #pragma unroll
         for (int p = 0; p < NP; p++) s[p] = FP::x_add(s[p], FP::x_ldcg(all + (size_t)b * NP + p));
     __syncthreads();
@@ -85,9 +89,9 @@ __device__ __forceinline__ void block_reduce_finalize(typename FP::X (&acc)[NP],
             X v = lane < nwarps ? sm[lane][p] : FP::x_zero();
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) v = FP::x_add(v, FP::x_shfl_down(v, off));
-            if (lane == 0) out[(size_t)blockIdx.y * NP + p] = v;
+            if (lane == 0) out[(size_t)slot * NP + p] = v;
         }
-        if (lane == 0) counter[blockIdx.y] = 0;  // re-arm for the next launch that uses this slot
+        if (lane == 0) counter[slot] = 0;  // re-arm for the next launch that uses this slot
     }
 }
 

@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 
+#include "gp_kernels.cuh"
 #include "kernels.cuh"
 #include "lasso_host.hpp"
 #include "transcript.hpp"
@@ -31,12 +32,58 @@ struct CudaError : std::runtime_error { using std::runtime_error::runtime_error;
     } while (0)
 #define HG_LAUNCH_CHECK() HG_CUDA(cudaGetLastError())
 
+// kernel classes for the per-class event timing bench.py reports (roofline of the dominant kernel)
+enum KernelClass { KC_POLY = 0, KC_COUNTERS, KC_EQ, KC_DOT, KC_HASH, KC_TREE, KC_SC_COLL, KC_SC_GP, KC_MISC, KC_COUNT };
+inline const char* kernel_class_name(int c) {
+    static const char* n[] = {"polynomialize", "counters", "eq_build", "mle_dot", "hash_build", "product_tree", "sumcheck_collation",
+                              "sumcheck_grand_product", "misc"};
+    return (c >= 0 && c < KC_COUNT) ? n[c] : "?";
+}
 struct DeviceCtx {
     int device = 0;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     size_t launches = 0;  // kernels enqueued (bench.py "gpu_launches")
+    // optional per-launch CUDA-event timing on the launching stream
+    bool profile = false;
+    struct Rec { int cls; cudaEvent_t a, b; size_t bytes; };
+    std::vector<Rec> recs;
+    size_t cls_launches[KC_COUNT] = {0};
+    double cls_ms[KC_COUNT] = {0};
+    size_t cls_bytes[KC_COUNT] = {0};
+    void profile_reset() {
+        for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        recs.clear();
+        for (int i = 0; i < KC_COUNT; i++) { cls_launches[i] = 0; cls_ms[i] = 0; cls_bytes[i] = 0; }
+    }
+    void profile_collect() {
+        cudaStreamSynchronize(stream);
+        for (auto& r : recs) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, r.a, r.b);
+            cls_launches[r.cls]++; cls_ms[r.cls] += ms; cls_bytes[r.cls] += r.bytes;
+            cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+        }
+        recs.clear();
+    }
 };
+// brackets one kernel launch: counts it and, when profiling, times it with events on the launching stream
+struct KernelScope {
+    DeviceCtx* c; int cls; size_t bytes; cudaEvent_t a = nullptr, b = nullptr;
+    KernelScope(DeviceCtx* ctx, int k, size_t algorithmic_bytes) : c(ctx), cls(k), bytes(algorithmic_bytes) {
+        if (c->profile) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, c->stream); }
+    }
+    ~KernelScope() {
+        c->launches++;
+        if (c->profile) { cudaEventRecord(b, c->stream); c->recs.push_back({cls, a, b, bytes}); }
+    }
+};
+#define HG_K(ctx, cls, bytes, ...)               \
+    do {                                         \
+        ::hg::KernelScope _ks(ctx, cls, bytes);  \
+        __VA_ARGS__;                             \
+        HG_LAUNCH_CHECK();                       \
+    } while (0)
 
 template <class T> struct DevBuf {
     T* p = nullptr;
@@ -196,9 +243,32 @@ struct ScScratch {
     int max_blocks = 0;
 };
 
+// serialisation of one round message + claim bookkeeping (runs on the host when the message has been downloaded)
+template <class FP, int D>
+void emit_round(Channel<FP>& ch, std::shared_ptr<ScHostState<FP>> st, size_t off, const WireOptions& wo, bool h1, size_t next_idx) {
+    typedef typename FP::X X;
+    Channel<FP>* chp = &ch;
+    WireOptions w = wo;
+    ch.emit([chp, st, off, w, h1, next_idx]() {
+        typedef RoundPoly<FP> RP;
+        if (st->has_pending) st->claim = RP::horner(st->pending_coeffs, chp->chal(st->pending_chal));
+        std::vector<X> ev(D + 1);
+        ev[0] = chp->msg(off);
+        for (int p = 2; p <= D; p++) ev[p] = chp->msg(off + p - 1);
+        ev[1] = h1 ? chp->msg(off + D) : FP::x_sub(st->claim, ev[0]);
+        std::vector<X> co = RP::interpolate(ev);
+        auto& tr = chp->transcript();
+        if (w.a3_wire == 0) { tr.write_felt_ext(co[0]); for (int p = 2; p <= D; p++) tr.write_felt_ext(co[p]); }
+        else { tr.write_felt_ext(ev[0]); for (int p = 2; p <= D; p++) tr.write_felt_ext(ev[p]); }
+        st->pending_coeffs = co;
+        st->pending_chal = next_idx;
+        st->has_pending = true;
+    });
+}
+
 // one launch of k_sc_round with the right instantiation
 template <class FP, int ARITY>
-void launch_sc_round(DeviceCtx* ctx, bool in_base, bool fold, bool with_h1, const void* in, typename FP::X* out, size_t n_in, int nterm,
+void launch_sc_round(DeviceCtx* ctx, int kclass, bool in_base, bool fold, bool with_h1, const void* in, typename FP::X* out, size_t n_in, int nterm,
                      const typename FP::X* coeffs, const typename FP::X* r_prev, const ScScratch& sc, typename FP::X* msg) {
     typedef typename FP::B B;
     typedef typename FP::X X;
@@ -206,6 +276,10 @@ void launch_sc_round(DeviceCtx* ctx, bool in_base, bool fold, bool with_h1, cons
     int blocks = (int)std::min<size_t>((npairs + HG_BLOCK - 1) / HG_BLOCK, (size_t)sc.max_blocks);
     if (blocks < 1) blocks = 1;
     X* part = (X*)sc.partials;
+    // algorithmic bytes of this launch: every input table read once, every folded table written once
+    const size_t ntab = (size_t)nterm * ARITY;
+    const size_t bytes = ntab * n_in * (in_base ? sizeof(B) : sizeof(X)) + (fold ? ntab * (n_in / 2) * sizeof(X) : 0);
+    KernelScope _ks(ctx, kclass, bytes);
 #define HG_SC(TIN, FOLD, H1) \
     k_sc_round<FP, TIN, ARITY, FOLD, H1><<<blocks, HG_BLOCK, 0, ctx->stream>>>((const TIN*)in, out, n_in, nterm, coeffs, r_prev, part, sc.counters, msg)
     if (in_base) {
@@ -217,13 +291,12 @@ void launch_sc_round(DeviceCtx* ctx, bool in_base, bool fold, bool with_h1, cons
     }
 #undef HG_SC
     HG_LAUNCH_CHECK();
-    ctx->launches++;
 }
 
 // prove_sum_check for g = t_0 * sum_i coeffs[i] * prod_{k<ARITY} t_{ARITY*i+k} over base tables of length n = 2^nv laid
 // out back to back. Returns the message offset of the final evaluations and the index of the first round challenge.
 template <class FP, int ARITY>
-void sumcheck_dev(DeviceCtx* ctx, Channel<FP>& ch, const WireOptions& wo, const typename FP::B* d_tables, size_t n, int nterm,
+void sumcheck_dev(DeviceCtx* ctx, int kclass, Channel<FP>& ch, const WireOptions& wo, const typename FP::B* d_tables, size_t n, int nterm,
                   const typename FP::X* d_coeffs, typename FP::X* bufA, typename FP::X* bufB, const ScScratch& sc,
                   std::shared_ptr<ScHostState<FP>> st, size_t* first_chal, size_t* evals_off) {
     typedef typename FP::B B;
@@ -242,30 +315,14 @@ void sumcheck_dev(DeviceCtx* ctx, Channel<FP>& ch, const WireOptions& wo, const 
     for (int j = 0; j < nv; j++) {
         size_t off = ch.alloc_msg(NP);
         if (j == 0) {
-            launch_sc_round<FP, ARITY>(ctx, true, false, h1, d_tables, nullptr, n, nterm, d_coeffs, nullptr, sc, ch.d_msg(off));
+            launch_sc_round<FP, ARITY>(ctx, kclass, true, false, h1, d_tables, nullptr, n, nterm, d_coeffs, nullptr, sc, ch.d_msg(off));
         } else {
             X* out = (j & 1) ? bufA : bufB;
-            launch_sc_round<FP, ARITY>(ctx, in_base, true, h1, cur_in, out, n_in, nterm, d_coeffs, ch.d_chal(prev_chal), sc, ch.d_msg(off));
+            launch_sc_round<FP, ARITY>(ctx, kclass, in_base, true, h1, cur_in, out, n_in, nterm, d_coeffs, ch.d_chal(prev_chal), sc, ch.d_msg(off));
             cur_in = out; in_base = false; n_in >>= 1;
         }
-        Channel<FP>* chp = &ch;
-        WireOptions w = wo;
         const size_t next_idx = ch.next_index();  // the challenge squeezed right after this message
-        ch.emit([chp, st, off, w, h1, next_idx]() {
-            typedef RoundPoly<FP> RP;
-            if (st->has_pending) st->claim = RP::horner(st->pending_coeffs, chp->chal(st->pending_chal));
-            std::vector<X> ev(D + 1);
-            ev[0] = chp->msg(off);
-            for (int p = 2; p <= D; p++) ev[p] = chp->msg(off + p - 1);
-            ev[1] = h1 ? chp->msg(off + D) : FP::x_sub(st->claim, ev[0]);
-            std::vector<X> co = RP::interpolate(ev);
-            auto& tr = chp->transcript();
-            if (w.a3_wire == 0) { tr.write_felt_ext(co[0]); for (int p = 2; p <= D; p++) tr.write_felt_ext(co[p]); }
-            else { tr.write_felt_ext(ev[0]); for (int p = 2; p <= D; p++) tr.write_felt_ext(ev[p]); }
-            st->pending_coeffs = co;
-            st->pending_chal = next_idx;
-            st->has_pending = true;
-        });
+        emit_round<FP, D>(ch, st, off, wo, h1, next_idx);
         prev_chal = ch.squeeze(1);
         if (prev_chal != next_idx) throw std::runtime_error("sumcheck_dev: challenge index drift");
         if (j == 0 && first_chal) *first_chal = prev_chal;
@@ -273,11 +330,74 @@ void sumcheck_dev(DeviceCtx* ctx, Channel<FP>& ch, const WireOptions& wo, const 
     // final evaluations: the tables now have 2 elements each
     size_t eo = ch.alloc_msg(ntab);
     int blocks = (ntab + HG_BLOCK - 1) / HG_BLOCK;
-    if (in_base) k_fold_final<FP, B><<<blocks, HG_BLOCK, 0, ctx->stream>>>((const B*)cur_in, ntab, ch.d_chal(prev_chal), ch.d_msg(eo));
-    else k_fold_final<FP, X><<<blocks, HG_BLOCK, 0, ctx->stream>>>((const X*)cur_in, ntab, ch.d_chal(prev_chal), ch.d_msg(eo));
-    HG_LAUNCH_CHECK();
-    ctx->launches++;
+    if (in_base) HG_K(ctx, kclass, 2 * ntab * sizeof(B), k_fold_final<FP, B><<<blocks, HG_BLOCK, 0, ctx->stream>>>((const B*)cur_in, ntab, ch.d_chal(prev_chal), ch.d_msg(eo)));
+    else HG_K(ctx, kclass, 2 * ntab * sizeof(X), k_fold_final<FP, X><<<blocks, HG_BLOCK, 0, ctx->stream>>>((const X*)cur_in, ntab, ch.d_chal(prev_chal), ch.d_msg(eo)));
     if (evals_off) *evals_off = eo;
+}
+
+// Grand-product layer sumcheck with the specialised kernels of gp_kernels.cuh. tables: [nvec][2n] base elements.
+// *scaled = whether the final evaluations of l_i (i > 0) carry the factor c_i (true iff a round >= 1 ran).
+template <class FP>
+void gp_sumcheck_dev(DeviceCtx* ctx, Channel<FP>& ch, const WireOptions& wo, const typename FP::B* d_tables, size_t n, int nvec,
+                     const typename FP::X* d_coeffs, typename FP::X* bufA, typename FP::X* bufB, const ScScratch& sc,
+                     std::shared_ptr<ScHostState<FP>> st, size_t* first_chal, size_t* evals_off, bool* scaled) {
+    typedef typename FP::B B;
+    typedef typename FP::X X;
+    constexpr int D = 3;
+    const int ntab = 2 * nvec;
+    int nv = 0;
+    while (((size_t)1 << nv) < n) nv++;
+    const bool h1 = wo.a3_h1 != 0;
+    const int NP = h1 ? D + 1 : D;
+    X* part = (X*)sc.partials;
+    const int target_blocks = ctx->sm_count * 4;
+    auto plan = [&](size_t threads_x, int* bx, int* groups, int* tpg) {
+        size_t b = (threads_x + HG_BLOCK - 1) / HG_BLOCK;
+        if (b < 1) b = 1;
+        if (b > (size_t)sc.max_blocks) b = sc.max_blocks;
+        int g = (int)std::min<size_t>((size_t)nvec, std::max<size_t>(1, ((size_t)target_blocks + b - 1) / b));
+        *tpg = (nvec + g - 1) / g;
+        *groups = (nvec + *tpg - 1) / *tpg;
+        *bx = (int)b;
+    };
+    const void* cur_in = d_tables;
+    bool in_base = true;
+    size_t n_in = n, prev_chal = 0;
+    for (int j = 0; j < nv; j++) {
+        size_t off = ch.alloc_msg(NP);
+        int bx, groups, tpg;
+        if (j == 0) {
+            constexpr int U = 4;
+            plan((n / 2 + U - 1) / U, &bx, &groups, &tpg);
+            KernelScope ks(ctx, KC_SC_GP, (size_t)ntab * n * sizeof(B));
+            if (h1) k_gp_r0<FP, U, true><<<dim3(bx, groups), HG_BLOCK, 0, ctx->stream>>>(d_tables, n, nvec, tpg, d_coeffs, part, sc.counters, ch.d_msg(off));
+            else k_gp_r0<FP, U, false><<<dim3(bx, groups), HG_BLOCK, 0, ctx->stream>>>(d_tables, n, nvec, tpg, d_coeffs, part, sc.counters, ch.d_msg(off));
+            HG_LAUNCH_CHECK();
+        } else {
+            X* out = (j & 1) ? bufA : bufB;
+            plan(n_in / 4, &bx, &groups, &tpg);
+            KernelScope ks(ctx, KC_SC_GP, (size_t)ntab * n_in * (in_base ? sizeof(B) : sizeof(X)) + (size_t)ntab * (n_in / 2) * sizeof(X));
+            const X* rp = ch.d_chal(prev_chal);
+            dim3 grid(bx, groups);
+#define HG_GP(TIN, SC, H1) k_gp_fold<FP, TIN, SC, H1><<<grid, HG_BLOCK, 0, ctx->stream>>>((const TIN*)cur_in, out, n_in, nvec, tpg, d_coeffs, rp, part, sc.counters, ch.d_msg(off))
+            if (in_base) { if (h1) HG_GP(B, true, true); else HG_GP(B, true, false); }
+            else { if (h1) HG_GP(X, false, true); else HG_GP(X, false, false); }
+#undef HG_GP
+            HG_LAUNCH_CHECK();
+            cur_in = out; in_base = false; n_in >>= 1;
+        }
+        const size_t next_idx = ch.next_index();
+        emit_round<FP, D>(ch, st, off, wo, h1, next_idx);
+        prev_chal = ch.squeeze(1);
+        if (prev_chal != next_idx) throw std::runtime_error("gp_sumcheck_dev: challenge index drift");
+        if (j == 0 && first_chal) *first_chal = prev_chal;
+    }
+    size_t eo = ch.alloc_msg(ntab);
+    int blocks = (ntab + HG_BLOCK - 1) / HG_BLOCK;
+    if (in_base) HG_K(ctx, KC_SC_GP, 2 * ntab * sizeof(B), k_fold_final<FP, B><<<blocks, HG_BLOCK, 0, ctx->stream>>>((const B*)cur_in, ntab, ch.d_chal(prev_chal), ch.d_msg(eo)));
+    else HG_K(ctx, KC_SC_GP, 2 * ntab * sizeof(X), k_fold_final<FP, X><<<blocks, HG_BLOCK, 0, ctx->stream>>>((const X*)cur_in, ntab, ch.d_chal(prev_chal), ch.d_msg(eo)));
+    if (evals_off) *evals_off = eo;
+    if (scaled) *scaled = !in_base;
 }
 
 template <class FP> __global__ void k_powers(const typename FP::X* __restrict__ base, int n, int ascending, typename FP::X* __restrict__ out) {
@@ -423,6 +543,11 @@ template <class FP> class LassoNodeDev {
         const size_t R = R_, M = M_;
         const int m = m_, v = num_vars_;
         const size_t rows = std::min(n_inputs, n_rows_);  // izip! stops at the shorter (Q9)
+        {
+            size_t np2 = 1;  // lasso.rs:161 num_reads = inputs.len().next_power_of_two(); lasso.rs:79-80 assert_eq!(num_vars, self.num_vars)
+            while (np2 < n_inputs) np2 <<= 1;
+            if (np2 != R_) throw std::runtime_error("assertion `left == right` failed: num_vars of the input does not match the node (lasso.rs:80)");
+        }
         ch.begin(&tr, mode, total_chal_);
 
         // collation coefficients (A5)
@@ -434,21 +559,17 @@ template <class FP> class LassoNodeDev {
         }
         // ---- polynomialize (lasso.rs:157-250)
         B* d_S = d_coll_.p + R;
-        k_polynomialize<FP><<<(unsigned)((R + HG_BLOCK - 1) / HG_BLOCK), HG_BLOCK, 0, s>>>(d_inputs, rows, d_row_lookup_.p, d_meta_.p, d_subtables_.p,
-                                                                                          d_coeff_coll_.p, d_wpow_.p, R, d_dims_.p, d_E_.p, d_S, d_out_.p);
-        HG_LAUNCH_CHECK(); ctx_->launches++;
+        HG_K(ctx_, KC_POLY, R * (sizeof(B) + 1 + pp_.C * 2 + ((size_t)m + 2) * sizeof(B)),
+             k_polynomialize<FP><<<(unsigned)((R + HG_BLOCK - 1) / HG_BLOCK), HG_BLOCK, 0, s>>>(d_inputs, rows, d_row_lookup_.p, d_meta_.p, d_subtables_.p,
+                                                                                                d_coeff_coll_.p, d_wpow_.p, R, d_dims_.p, d_E_.p, d_S, d_out_.p));
         HG_CUDA(cudaMemcpyAsync(d_coll_.p, d_E_.p, R * sizeof(B), cudaMemcpyDeviceToDevice, s));
         HG_CUDA(cudaMemsetAsync(d_read_cts_.p, 0, d_read_cts_.bytes(), s));
         for (int sl = 0; sl < nslots_; sl++) {
             const u16* addr = d_dims_.p + (size_t)slot_addr_dim_[sl] * R;
-            k_cnt_hist<<<nblk_cnt_, 1024, M * 2, s>>>(addr, d_row_lookup_.p, slot_used_[sl], rows, rows_per_block_, d_blk_hist_.p, log2M_);
-            HG_LAUNCH_CHECK();
-            k_cnt_scan<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(d_blk_hist_.p, nblk_cnt_, log2M_, d_blk_base_.p, d_final_cts_.p + (size_t)sl * M);
-            HG_LAUNCH_CHECK();
-            k_cnt_rank<<<nblk_cnt_, 32, M * 2, s>>>(addr, d_row_lookup_.p, slot_used_[sl], rows, R, rows_per_block_, d_blk_base_.p, log2M_,
-                                                    d_read_cts_.p + (size_t)sl * R);
-            HG_LAUNCH_CHECK();
-            ctx_->launches += 3;
+            HG_K(ctx_, KC_COUNTERS, rows * 3, k_cnt_hist<<<nblk_cnt_, 1024, M * 2, s>>>(addr, d_row_lookup_.p, slot_used_[sl], rows, rows_per_block_, d_blk_hist_.p, log2M_));
+            HG_K(ctx_, KC_COUNTERS, M * 4, k_cnt_scan<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(d_blk_hist_.p, nblk_cnt_, log2M_, d_blk_base_.p, d_final_cts_.p + (size_t)sl * M));
+            HG_K(ctx_, KC_COUNTERS, rows * 7, k_cnt_rank<<<nblk_cnt_, 32, M * 2, s>>>(addr, d_row_lookup_.p, slot_used_[sl], rows, R, rows_per_block_, d_blk_base_.p, log2M_,
+                                                                                  d_read_cts_.p + (size_t)sl * R));
         }
 
         // ---- r, claimed sum (lasso.rs:85, :264, :269)
@@ -470,17 +591,17 @@ template <class FP> class LassoNodeDev {
             // g(E_0, S) = E_0 * (0 * E_0 + 1 * S): nterm = 2, arity 1, tables [E_0 | S]
             HG_CUDA(cudaMemcpyAsync(d_gp_coeffs_.p, one_one, sizeof one_one, cudaMemcpyHostToDevice, s));
             HG_CUDA(cudaStreamSynchronize(s));
-            sumcheck_dev<FP, 1>(ctx_, ch, wo, d_coll_.p, R, 2, d_gp_coeffs_.p, d_bufA_.p, d_bufB_.p, sc_, coll_state, nullptr, nullptr);
+            sumcheck_dev<FP, 1>(ctx_, KC_SC_COLL, ch, wo, d_coll_.p, R, 2, d_gp_coeffs_.p, d_bufA_.p, d_bufB_.p, sc_, coll_state, nullptr, nullptr);
         }
         // ---- gamma, tau (lasso.rs:99)
         const size_t gt_idx = ch.squeeze(2);
         // ---- memory checking (lasso.rs:292-339, prover.rs:35-181)
-        k_hash_rw<FP><<<dim3((unsigned)((R + HG_BLOCK - 1) / HG_BLOCK), m), HG_BLOCK, 0, s>>>(d_dims_.p, d_read_cts_.p, d_E_.p, d_pos_mem_.p, d_pos_dim_.p,
-                                                                                               d_pos_slot_.p, ch.d_chal(gt_idx), R, m, d_tree1_.p);
-        HG_LAUNCH_CHECK(); ctx_->launches++;
-        k_hash_if<FP><<<dim3((unsigned)((M + HG_BLOCK - 1) / HG_BLOCK), m), HG_BLOCK, 0, s>>>(d_subtables_.p, d_final_cts_.p, d_pos_sub_.p, d_pos_slot_.p,
-                                                                                               ch.d_chal(gt_idx), M, m, d_tree2_.p);
-        HG_LAUNCH_CHECK(); ctx_->launches++;
+        HG_K(ctx_, KC_HASH, (size_t)m * R * (2 + 4 + 3 * sizeof(B)),
+             k_hash_rw<FP><<<dim3((unsigned)((R + HG_BLOCK - 1) / HG_BLOCK), m), HG_BLOCK, 0, s>>>(d_dims_.p, d_read_cts_.p, d_E_.p, d_pos_mem_.p, d_pos_dim_.p,
+                                                                                                   d_pos_slot_.p, ch.d_chal(gt_idx), R, m, d_tree1_.p));
+        HG_K(ctx_, KC_HASH, (size_t)m * M * (4 + 3 * sizeof(B)),
+             k_hash_if<FP><<<dim3((unsigned)((M + HG_BLOCK - 1) / HG_BLOCK), m), HG_BLOCK, 0, s>>>(d_subtables_.p, d_final_cts_.p, d_pos_sub_.p, d_pos_slot_.p,
+                                                                                                   ch.d_chal(gt_idx), M, m, d_tree2_.p));
         size_t x_idx = 0, y_idx = 0;
         grand_product(ch, wo, d_tree1_.p, R, &x_idx);
         grand_product(ch, wo, d_tree2_.p, M, &y_idx);
@@ -535,13 +656,12 @@ template <class FP> class LassoNodeDev {
     }
     void build_eq(Channel<FP>& ch, size_t point_idx, int nv) {
         size_t n = (size_t)1 << nv;
-        k_eq_build<FP><<<(unsigned)((n + HG_BLOCK - 1) / HG_BLOCK), HG_BLOCK, 0, ctx_->stream>>>(ch.d_chal(point_idx), nv, d_eq_.p);
-        HG_LAUNCH_CHECK(); ctx_->launches++;
+        HG_K(ctx_, KC_EQ, n * sizeof(X), k_eq_build<FP><<<(unsigned)((n + HG_BLOCK - 1) / HG_BLOCK), HG_BLOCK, 0, ctx_->stream>>>(ch.d_chal(point_idx), nv, d_eq_.p));
     }
     template <class T> void dot_tables(Channel<FP>& ch, const T* tables, size_t stride, int ntab, size_t n, size_t msg_off) {
         int blocks = (int)std::min<size_t>((n + HG_BLOCK - 1) / HG_BLOCK, (size_t)ctx_->sm_count * 2);
-        k_dot_eq<FP, T><<<dim3(blocks, ntab), HG_BLOCK, 0, ctx_->stream>>>(tables, stride, n, d_eq_.p, d_partials_.p, d_counters_.p, ch.d_msg(msg_off));
-        HG_LAUNCH_CHECK(); ctx_->launches++;
+        HG_K(ctx_, KC_DOT, (size_t)ntab * n * sizeof(T) + n * sizeof(X),
+             k_dot_eq<FP, T><<<dim3(blocks, ntab), HG_BLOCK, 0, ctx_->stream>>>(tables, stride, n, d_eq_.p, d_partials_.p, d_counters_.p, ch.d_msg(msg_off)));
     }
     template <class T> void eval_tables(Channel<FP>& ch, const T* tables, size_t stride, int ntab, size_t n, size_t point_idx, int nv, size_t msg_off) {
         build_eq(ch, point_idx, nv);
@@ -560,12 +680,10 @@ template <class FP> class LassoNodeDev {
         for (int k = 1; k < nvars; k++) {
             layer[k] = layer[k - 1] + (size_t)nvec * (N >> (k - 1));
             size_t h = N >> k;
-            k_tree_up<FP><<<dim3((unsigned)((h + HG_BLOCK - 1) / HG_BLOCK), nvec), HG_BLOCK, 0, s>>>(layer[k - 1], layer[k], h);
-            HG_LAUNCH_CHECK(); ctx_->launches++;
+            HG_K(ctx_, KC_TREE, (size_t)nvec * h * 3 * sizeof(B), k_tree_up<FP><<<dim3((unsigned)((h + HG_BLOCK - 1) / HG_BLOCK), nvec), HG_BLOCK, 0, s>>>(layer[k - 1], layer[k], h));
         }
         const size_t roots_off = ch.alloc_msg(nvec), ev0_off = ch.alloc_msg(2 * nvec);
-        k_tree_top<FP><<<(nvec + HG_BLOCK - 1) / HG_BLOCK, HG_BLOCK, 0, s>>>(layer[nvars - 1], nvec, ch.d_msg(roots_off), ch.d_msg(ev0_off));
-        HG_LAUNCH_CHECK(); ctx_->launches++;
+        HG_K(ctx_, KC_TREE, (size_t)nvec * 2 * sizeof(B), k_tree_top<FP><<<(nvec + HG_BLOCK - 1) / HG_BLOCK, HG_BLOCK, 0, s>>>(layer[nvars - 1], nvec, ch.d_msg(roots_off), ch.d_msg(ev0_off)));
         struct GpHost { std::vector<X> claimed; std::vector<X> evals; size_t mu_idx = 0; bool pending = false; };
         auto gp = std::make_shared<GpHost>();
         Channel<FP>* chp = &ch;
@@ -581,8 +699,7 @@ template <class FP> class LassoNodeDev {
         for (int nv = 1; nv < nvars; nv++) {
             const size_t prev_mu = mu_idx;
             const size_t gamma_idx = ch.squeeze(1);  // prover.rs:238
-            k_powers<FP><<<1, 32, 0, s>>>(ch.d_chal(gamma_idx), nvec, wo.a5_ascending, d_gp_coeffs_.p);
-            HG_LAUNCH_CHECK(); ctx_->launches++;
+            HG_K(ctx_, KC_MISC, 0, k_powers<FP><<<1, 32, 0, s>>>(ch.d_chal(gamma_idx), nvec, wo.a5_ascending, d_gp_coeffs_.p));
             auto st = std::make_shared<ScHostState<FP>>();
             const int asc = wo.a5_ascending;
             ch.emit([chp, gp, st, prev_mu, gamma_idx, nvec, asc]() {
@@ -599,11 +716,21 @@ template <class FP> class LassoNodeDev {
                 st->claim = claim;
             });
             size_t sc_first = 0, ev_off = 0;
+            bool scaled = false;
             const B* tables = layer[nvars - 1 - nv];
-            sumcheck_dev<FP, 2>(ctx_, ch, wo, tables, (size_t)1 << nv, nvec, d_gp_coeffs_.p, d_bufA_.p, d_bufB_.p, sc_, st, &sc_first, &ev_off);
-            ch.emit([chp, gp, ev_off, nvec]() {
+            gp_sumcheck_dev<FP>(ctx_, ch, wo, tables, (size_t)1 << nv, nvec, d_gp_coeffs_.p, d_bufA_.p, d_bufB_.p, sc_, st, &sc_first, &ev_off, &scaled);
+            ch.emit([chp, gp, ev_off, nvec, scaled, gamma_idx, asc]() {
                 auto& t = chp->transcript();
-                for (int i = 0; i < 2 * nvec; i++) { gp->evals[i] = chp->msg(ev_off + i); t.write_felt_ext(gp->evals[i]); }  // prover.rs:257
+                // the device keeps l_i (i > 0) pre-multiplied by c_i (gp_kernels.cuh); undo it exactly with c_i^{-1}
+                X ginv = FP::x_inv(chp->chal(gamma_idx)), p = FP::x_one();
+                std::vector<X> cinv(nvec);
+                for (int i = 0; i < nvec; i++) { cinv[asc ? i : nvec - 1 - i] = p; p = FP::x_mul(p, ginv); }
+                for (int i = 0; i < 2 * nvec; i++) {
+                    X e = chp->msg(ev_off + i);
+                    if (scaled && (i & 1) == 0 && i > 0) e = FP::x_mul(e, cinv[i / 2]);
+                    gp->evals[i] = e;
+                    t.write_felt_ext(e);  // prover.rs:257
+                }
             });
             mu_idx = ch.squeeze(1);
             first_chal = sc_first;

@@ -51,6 +51,13 @@ int hg_ctx_set_option(hg_ctx* ctx, int option, int value);
 int hg_ctx_synchronize(hg_ctx* ctx);
 /* kernels enqueued by this context so far */
 uint64_t hg_ctx_launch_count(hg_ctx* ctx);
+/* per-kernel-class CUDA-event timing on the launching stream (bench.py's roofline leg). hg_ctx_profile(ctx,1) resets and
+ * starts recording, hg_ctx_profile(ctx,0) stops; hg_ctx_profile_read returns the launches, summed device milliseconds and
+ * summed ALGORITHMIC bytes (per-kernel table) of one class. */
+int hg_ctx_profile(hg_ctx* ctx, int enable);
+int hg_ctx_profile_read(hg_ctx* ctx, int kernel_class, uint64_t* launches, double* ms, uint64_t* algorithmic_bytes);
+int hg_kernel_class_count(void);
+const char* hg_kernel_class_name(int kernel_class);
 /* the CUDA stream kernels are launched on (cudaStream_t), for event timing by the caller */
 void* hg_ctx_stream(hg_ctx* ctx);
 

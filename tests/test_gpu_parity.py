@@ -1,0 +1,231 @@
+"""GPU parity tests (run with -m gpu on the B200 box). Everything goes through the C ABI (hyper_greco_b200.api ->
+libhg_b200.so) and is compared bit-for-bit with the CPU oracle on the same inputs; at the BASELINE.json sizes the checks are
+size-independent properties (oracle VERIFIER acceptance, claim == input MLE, prefetch == interactive, determinism)."""
+import numpy as np
+import pytest
+
+from conftest import load_case
+
+pytestmark = pytest.mark.gpu
+GL_P = 2**64 - 2**32 + 1
+
+
+@pytest.fixture(scope="module")
+def api():
+    import hyper_greco_b200  # noqa: F401
+    from hyper_greco_b200 import api
+    api.lib()  # raises if the CUDA library is missing: no fallback
+    return api
+
+
+@pytest.fixture(scope="module")
+def ctx(api):
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+def rand_ext(rng, n):
+    return rng.integers(0, GL_P, size=(n, 2), dtype=np.uint64)
+
+
+def test_device_field_arithmetic(api, ctx, oracle):
+    rng = np.random.default_rng(0)
+    edge = np.array([0, 1, GL_P - 1, GL_P - 2, 2**32, 2**32 - 1, 2**63, 0xFFFFFFFF00000000, 0xFFFFFFFF], np.uint64)
+    a = np.concatenate([rand_ext(rng, 4096), np.stack(np.meshgrid(edge, edge), -1).reshape(-1, 2)])
+    b = np.concatenate([rand_ext(rng, 4096), np.stack(np.meshgrid(edge, edge), -1).reshape(-1, 2)[::-1]])
+    for op in (0, 1, 2):
+        got = api.field_selftest(ctx, op, a, b)
+        ai, bi = a.astype(object), b.astype(object)
+        if op == 0:
+            want = (ai + bi) % GL_P
+        elif op == 1:
+            want = (ai - bi) % GL_P
+        else:
+            want = np.stack([(ai[:, 0] * bi[:, 0] + 7 * ai[:, 1] * bi[:, 1]) % GL_P, (ai[:, 0] * bi[:, 1] + ai[:, 1] * bi[:, 0]) % GL_P], -1)
+        assert (got.astype(object) == want).all(), op
+    # and against the oracle's own arithmetic
+    for i in range(0, 64):
+        assert (api.field_selftest(ctx, 2, a[i:i + 1], b[i:i + 1])[0] == oracle.field_op(0, 2, a[i], b[i])).all()
+
+
+@pytest.mark.parametrize("arity,nterms,nv", [(1, 2, 1), (1, 7, 4), (2, 1, 1), (2, 3, 2), (2, 5, 3), (2, 12, 11), (1, 25, 12), (2, 50, 9)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_sumcheck_matches_oracle(api, ctx, oracle, arity, nterms, nv, mode):
+    rng = np.random.default_rng(nv * 100 + nterms)
+    tables = rng.integers(0, GL_P, size=(nterms * arity, 1 << nv), dtype=np.uint64)
+    coeffs = rand_ext(rng, nterms)
+    claim = rand_ext(rng, 1)[0]
+    oproof, te, orr, ofe = oracle.sumcheck_prove(0, arity, coeffs, tables, nv, claim)
+    d = api.DeviceBuffer.from_numpy(ctx, tables)
+    t = api.Keccak256Transcript()
+    pt, ev = api.sumcheck_prove(ctx, arity, coeffs, d, nv, claim, t, mode)
+    assert t.into_proof() == oproof
+    assert (pt == orr).all() and (ev == ofe).all()
+    d.free()
+
+
+@pytest.mark.parametrize("opts", [((3, 1),), ((31, 1),), ((3, 1), (31, 1))])
+def test_sumcheck_wire_variants(api, oracle, opts):
+    """Appendix-B switches A3 / A3': both implementations must agree under every setting."""
+    rng = np.random.default_rng(5)
+    arity, nterms, nv = 2, 4, 6
+    tables = rng.integers(0, GL_P, size=(nterms * arity, 1 << nv), dtype=np.uint64)
+    coeffs, claim = rand_ext(rng, nterms), rand_ext(rng, 1)[0]
+    c = api.Context(0)
+    try:
+        for w, v in opts:
+            oracle.set_assumption(w, v)
+            c.set_option(w, v)
+        oproof, *_ = oracle.sumcheck_prove(0, arity, coeffs, tables, nv, claim)
+        d = api.DeviceBuffer.from_numpy(c, tables)
+        t = api.Keccak256Transcript()
+        api.sumcheck_prove(c, arity, coeffs, d, nv, claim, t)
+        assert t.into_proof() == oproof
+        d.free()
+    finally:
+        for w, v in ((3, 0), (31, 0), (5, 1)):
+            oracle.set_assumption(w, v)
+        c.close()
+
+
+def test_mle_eval_batch_matches_oracle(api, ctx, oracle):
+    rng = np.random.default_rng(9)
+    for nv in (1, 5, 13):
+        tables = rng.integers(0, GL_P, size=(3, 1 << nv), dtype=np.uint64)
+        pt = rand_ext(rng, nv)
+        d = api.DeviceBuffer.from_numpy(ctx, tables)
+        got = api.mle_eval_batch(ctx, d, 3, nv, pt)
+        for i in range(3):
+            assert (got[i] == oracle.mle_eval(0, tables[i], nv, pt)).all()
+        d.free()
+
+
+def _prove_gpu(api, ctx, bounds, segs, nv, inp, mode=0, device_resident=False):
+    pp = api.LassoPreprocessing.preprocess(bounds)
+    node = api.LassoNode(ctx, pp, nv, segs)
+    tr = api.Keccak256Transcript()
+    if device_resident:
+        buf = api.DeviceBuffer.from_numpy(ctx, inp)
+        pt, val = node.prove_claim_reduction(buf, tr, mode, n_inputs=inp.size)
+        buf.free()
+    else:
+        pt, val = node.prove_claim_reduction(inp, tr, mode)
+    return node, pp, tr, pt, val
+
+
+@pytest.mark.parametrize("name", ["1024_1x27_65537", "2048_1x52_65537", "4096_2x55_65537"])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_lasso_node_proof_bytes_match_oracle_on_reference_fixtures(api, ctx, oracle, golden_dir, name, mode):
+    P, inp, bounds, segs, nv, opp, rows = load_case(name, oracle, golden_dir)
+    oproof, orr, osum, nsq = oracle.lasso_prove(0, opp, nv, rows, inp)
+    node, pp, tr, pt, val = _prove_gpu(api, ctx, bounds, segs, nv, inp, mode, device_resident=(mode == 0))
+    assert tr.into_proof() == oproof
+    assert tr.num_squeezed == nsq
+    assert (pt.reshape(-1) == orr).all() and (val == osum).all()
+    # polynomialised witness (lasso.rs:157-250)
+    dims, rd, fc, e = node.download_polys()
+    od, ord_, ofc, oe = oracle.lasso_polynomialize(0, opp, nv, rows, inp)
+    assert (dims == od).all() and (e == oe).all()
+    for slot, d in enumerate(sorted(set(opp.memory_to_dimension_index))):
+        assert (rd[slot] == ord_[d]).all() and (fc[slot] == ofc[d]).all()
+    # the reference's own acceptance test, on the GPU proof
+    oracle.lasso_verify(0, opp, nv, tr.into_proof())
+    assert node.log2_input_size() == max(nv, 16)
+    node.free()
+
+
+@pytest.mark.parametrize("opts", [((3, 1), (31, 1)), ((5, 0),)])
+def test_lasso_node_under_assumption_switches(api, oracle, golden_dir, opts):
+    P, inp, bounds, segs, nv, opp, rows = load_case("1024_1x27_65537", oracle, golden_dir)
+    c = api.Context(0)
+    try:
+        for w, v in opts:
+            oracle.set_assumption(w, v)
+            c.set_option(w, v)
+        oproof, *_ = oracle.lasso_prove(0, opp, nv, rows, inp)
+        node, pp, tr, pt, val = _prove_gpu(api, c, bounds, segs, nv, inp)
+        assert tr.into_proof() == oproof
+        node.free()
+    finally:
+        for w, v in ((3, 0), (31, 0), (5, 1)):
+            oracle.set_assumption(w, v)
+        c.close()
+
+
+def test_lasso_node_ragged_and_edge_inputs(api, ctx, oracle, golden_dir):
+    """Edge cases the reference's structure implies: fewer inputs than lookups (izip stops early, Q9), values at the
+    range boundaries, an out-of-range value (bits silently truncated, Q8), transcript offset (node not first in the proof)."""
+    P, inp, bounds, segs, nv, opp, rows = load_case("1024_1x27_65537", oracle, golden_dir)
+    cases = {"short": inp[: inp.size - 777].copy()}
+    # an input whose padded length is not 2^num_vars trips assert_eq!(num_vars, self.num_vars) (lasso.rs:80) in both
+    with pytest.raises(oracle.OracleError):
+        oracle.lasso_prove(0, opp, nv, rows, inp[:1].copy())
+    pp0 = api.LassoPreprocessing.preprocess(bounds)
+    node0 = api.LassoNode(ctx, pp0, nv, segs)
+    with pytest.raises(api.HgError):
+        node0.prove_claim_reduction(inp[:1].copy(), api.Keccak256Transcript())
+    node0.free()
+    edge = inp.copy()
+    edge[-1] = 65536          # k1 + K1_BOUND maximum
+    edge[-2] = 0              # minimum
+    edge[0] = 200000          # out of range for R1: truncated
+    edge[5] = GL_P - 1        # a "negative" value that was not shifted into range
+    cases["edge"] = edge
+    for label, x in cases.items():
+        oproof, orr, osum, _ = oracle.lasso_prove(0, opp, nv, rows, x)
+        node, pp, tr, pt, val = _prove_gpu(api, ctx, bounds, segs, nv, x)
+        assert tr.into_proof() == oproof, label
+        assert (val == osum).all(), label
+        node.free()
+    # transcript already advanced by other nodes: skip 37 base squeezes = 18.5 -> use 38 (19 ext challenges)
+    oproof, *_ = oracle.lasso_prove(0, opp, nv, rows, inp, skip=38)
+    pp = api.LassoPreprocessing.preprocess(bounds)
+    node = api.LassoNode(ctx, pp, nv, segs)
+    tr = api.Keccak256Transcript()
+    tr.squeeze_challenges(19)
+    node.prove_claim_reduction(inp, tr)
+    assert tr.into_proof() == oproof
+    # a node can be reused for a second proof
+    tr2 = api.Keccak256Transcript()
+    tr2.squeeze_challenges(19)
+    node.prove_claim_reduction(inp, tr2, 1)
+    assert tr2.into_proof() == oproof
+    node.free()
+
+
+@pytest.mark.parametrize("name,seed", [("4096_2x55_65537", 11), ("8192_4x55_65537", 12)])
+def test_lasso_node_synthetic_witness_matches_oracle(api, ctx, oracle, name, seed):
+    P, inp, bounds, segs, nv, opp, rows = load_case(name, oracle, seed=seed)
+    oproof, orr, osum, _ = oracle.lasso_prove(0, opp, nv, rows, inp)
+    node, pp, tr, pt, val = _prove_gpu(api, ctx, bounds, segs, nv, inp)
+    assert tr.into_proof() == oproof
+    node.free()
+
+
+def test_lasso_node_full_size_properties(api, ctx, oracle):
+    """BASELINE.json metric config: n=32768, k=16, Goldilocks (num_vars 21, 25 memories). The oracle prover needs minutes
+    here, so parity is checked through size-independent properties: the oracle VERIFIER (restated from
+    lasso/src/memory_checking/verifier.rs:130-235, lasso/src/lasso.rs:116-139) accepts the GPU proof; the returned claim is
+    the MLE of the input at the squeezed point; prefetch and interactive modes give identical bytes; proving twice is
+    deterministic; a flipped proof byte is rejected."""
+    P, inp, bounds, segs, nv, opp, rows = load_case("32768_16x59_65537", oracle, seed=0)
+    assert nv == 21 and opp.num_memories == 25
+    node, pp, tr, pt, val = _prove_gpu(api, ctx, bounds, segs, nv, inp)
+    proof = tr.into_proof()
+    r, s, used = oracle.lasso_verify(0, opp, nv, proof)
+    assert used == len(proof) and (r == pt.reshape(-1)).all() and (s == val).all()
+    padded = np.zeros(1 << nv, np.uint64)
+    padded[: inp.size] = inp
+    assert (oracle.mle_eval(0, padded, nv, pt.reshape(-1)) == val).all()
+    tr2 = api.Keccak256Transcript()
+    node.prove_claim_reduction(inp, tr2, 0)
+    assert tr2.into_proof() == proof
+    tr3 = api.Keccak256Transcript()
+    node.prove_claim_reduction(inp, tr3, 1)
+    assert tr3.into_proof() == proof
+    bad = bytearray(proof)
+    bad[-3] ^= 4
+    with pytest.raises(oracle.OracleError):
+        oracle.lasso_verify(0, opp, nv, bytes(bad))
+    node.free()
