@@ -72,6 +72,38 @@ struct GlField {
     __device__ __forceinline__ static X x_shfl_down(X v, int off) {
         return gl2_make(__shfl_down_sync(0xffffffffu, v.c0, off), __shfl_down_sync(0xffffffffu, v.c1, off));
     }
+    // ---- fast device path (gl.cuh): lazy accumulators, canonical memory
+    typedef acc192 BAcc;
+    typedef xacc XAcc;
+    struct FoldAux { u64 r7; };  // 7 * r.c1
+    __device__ __forceinline__ static FoldAux fold_aux(X r) { FoldAux a; a.r7 = gl_mul7(r.c1); return a; }
+    __device__ __forceinline__ static BAcc bacc_zero() { return acc_zero(); }
+    __device__ __forceinline__ static void bacc_mad(BAcc& a, B x, B y) { acc_mad(a, x, y); }
+    __device__ __forceinline__ static B bacc_reduce(const BAcc& a) { return acc_reduce(a); }
+    __device__ __forceinline__ static XAcc xacc_zero_() { return xacc_zero(); }
+    __device__ __forceinline__ static void xacc_mad_(XAcc& a, X x, X y) { xacc_mad(a, x, y); }
+    __device__ __forceinline__ static void xacc_mad_b(XAcc& a, X x, B y) { xacc_mad_base(a, x, y); }
+    __device__ __forceinline__ static X xacc_reduce_(const XAcc& a) { return xacc_reduce(a); }
+    __device__ __forceinline__ static B fmul(B x, B y) { return gl_mul_fast(x, y); }
+    __device__ __forceinline__ static X fmul(X x, X y) { return gl2_mul_fast(x, y); }
+    // a0 + r (a1 - a0): canonical in, canonical out
+    __device__ __forceinline__ static X fold(X a0, X a1, X r, FoldAux aux) { return gl2_fold(a0, a1, r, aux.r7); }
+    __device__ __forceinline__ static X fold(B a0, B a1, X r, FoldAux aux) { return gl2_fold(a0, a1, r, aux.r7); }
+    // c * (a0 + r (a1 - a0)) = c a0 + (c r)(a1 - a0) for base a0, a1 (round 1 of the grand product: fold + pre-scale)
+    __device__ __forceinline__ static X fold_scaled(B a0, B a1, X c, X cr) {
+        const u64 d = gl_sub_cs(a1, a0);
+        acc192 c0 = acc_zero(), c1 = acc_zero();
+        acc_mad(c0, c.c0, a0); acc_mad(c0, cr.c0, d);
+        acc_mad(c1, c.c1, a0); acc_mad(c1, cr.c1, d);
+        return gl2_make(acc_reduce(c0), acc_reduce(c1));
+    }
+    // line through (0, lo), (1, hi) at X = infinity (slope) and X = -1; canonical inputs, lazy outputs
+    __device__ __forceinline__ static B slope(B lo, B hi) { return gl_sub_cs(hi, lo); }
+    __device__ __forceinline__ static B at_m1(B lo, B hi) { return gl_add_cs(lo, gl_sub_cs(lo, hi)); }
+    __device__ __forceinline__ static X slope(X lo, X hi) { return gl2_make(gl_sub_cs(hi.c0, lo.c0), gl_sub_cs(hi.c1, lo.c1)); }
+    __device__ __forceinline__ static X at_m1(X lo, X hi) {
+        return gl2_make(gl_add_cs(lo.c0, gl_sub_cs(lo.c0, hi.c0)), gl_add_cs(lo.c1, gl_sub_cs(lo.c1, hi.c1)));
+    }
     __device__ __forceinline__ static X x_ldcg(const X* p) {
         ulonglong2 t = __ldcg(reinterpret_cast<const ulonglong2*>(p));
         return gl2_make(t.x, t.y);

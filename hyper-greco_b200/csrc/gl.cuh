@@ -99,4 +99,114 @@ HG_HD gl2 gl2_inv(gl2 a) {
     return gl2_make(gl_mul(a.c0, ni), gl_mul(gl_neg(a.c1), ni));
 }
 
+
+// ------------------------------------------------------------------ device fast path: carry chains + lazy accumulation
+// The generic functions above compile to long compare/select sequences that saturate the ALU pipe (profiles/ round 1).
+// The hot kernels use these instead:
+//   * table elements in memory are always CANONICAL (< p);
+//   * products are accumulated UNREDUCED in a 160-bit accumulator (lo, hi, carry word) and reduced once;
+//   * subtraction needs only its subtrahend canonical; results are "lazy" (any representative in [0, 2^64)).
+#if defined(__CUDACC__)
+struct acc192 {
+    u64 lo, hi;
+    u32 c;
+};
+__device__ __forceinline__ acc192 acc_zero() { acc192 a; a.lo = 0; a.hi = 0; a.c = 0; return a; }
+// a += x * y   (x, y any 64-bit values)
+__device__ __forceinline__ void acc_mad(acc192& a, u64 x, u64 y) {
+    u64 lo = x * y, hi = __umul64hi(x, y);
+    asm("add.cc.u64 %0, %0, %3; addc.cc.u64 %1, %1, %4; addc.u32 %2, %2, 0;" : "+l"(a.lo), "+l"(a.hi), "+r"(a.c) : "l"(lo), "l"(hi));
+}
+__device__ __forceinline__ void acc_add(acc192& a, u64 x) {
+    asm("add.cc.u64 %0, %0, %3; addc.cc.u64 %1, %1, 0; addc.u32 %2, %2, 0;" : "+l"(a.lo), "+l"(a.hi), "+r"(a.c) : "l"(x));
+}
+__device__ __forceinline__ void acc_merge(acc192& a, const acc192& b) {
+    asm("add.cc.u64 %0, %0, %3; addc.cc.u64 %1, %1, %4; addc.u32 %2, %2, %5;" : "+l"(a.lo), "+l"(a.hi), "+r"(a.c) : "l"(b.lo), "l"(b.hi), "r"(b.c));
+}
+// a - b mod p for CANONICAL b (a may be lazy); result lazy, canonical when a is canonical
+__device__ __forceinline__ u64 gl_sub_cs(u64 a, u64 b) {
+    u64 d;
+    u32 m;
+    asm("sub.cc.u64 %0, %2, %3; subc.u32 %1, 0, 0;" : "=l"(d), "=r"(m) : "l"(a), "l"(b));
+    return d - (u64)m;  // m = 0xFFFFFFFF = EPS on borrow
+}
+// a + b mod p for CANONICAL a (b may be lazy); result lazy
+__device__ __forceinline__ u64 gl_add_cs(u64 a, u64 b) {
+    u64 s;
+    u32 c;
+    asm("add.cc.u64 %0, %2, %3; addc.u32 %1, 0, 0;" : "=l"(s), "=r"(c) : "l"(a), "l"(b));
+    return s + (u64)(0u - c);  // + EPS on carry; cannot wrap twice because a < p
+}
+// lazy -> canonical
+__device__ __forceinline__ u64 gl_canon(u64 r) {
+    u64 t;
+    u32 c;
+    asm("add.cc.u64 %0, %2, %3; addc.u32 %1, 0, 0;" : "=l"(t), "=r"(c) : "l"(r), "l"(GL_EPS));  // t = r - p (mod 2^64), carry iff r >= p
+    return c ? t : r;
+}
+// (lo + 2^64 hi + 2^128 c) mod p, canonical.  2^64 = 2^32 - 1, 2^96 = -1, 2^128 = -2^32 (mod p); c < 2^31
+__device__ __forceinline__ u64 acc_reduce(const acc192& a) {
+    const u64 s1 = (a.hi >> 32) | ((u64)a.c << 32);  // hi_hi + c * 2^32, canonical (< 2^63)
+    u64 t0 = gl_sub_cs(a.lo, s1);
+    const u64 hl = a.hi & GL_EPS;
+    const u64 t1 = (hl << 32) - hl;  // hi_lo * (2^32 - 1) < 2^64 - 2^33 + 2
+    u64 r;
+    u32 c;
+    asm("add.cc.u64 %0, %2, %3; addc.u32 %1, 0, 0;" : "=l"(r), "=r"(c) : "l"(t0), "l"(t1));
+    r += (u64)(0u - c);  // cannot wrap twice
+    return gl_canon(r);
+}
+// extension-field accumulator: sum of products x*y kept as three unreduced base accumulators
+struct xacc {
+    acc192 a00, a11, ax;
+};
+__device__ __forceinline__ xacc xacc_zero() { xacc a; a.a00 = acc_zero(); a.a11 = acc_zero(); a.ax = acc_zero(); return a; }
+__device__ __forceinline__ void xacc_mad(xacc& a, gl2 x, gl2 y) {
+    acc_mad(a.a00, x.c0, y.c0);
+    acc_mad(a.a11, x.c1, y.c1);
+    acc_mad(a.ax, x.c0, y.c1);
+    acc_mad(a.ax, x.c1, y.c0);
+}
+__device__ __forceinline__ void xacc_mad_base(xacc& a, gl2 x, u64 y) {
+    acc_mad(a.a00, x.c0, y);
+    acc_mad(a.ax, x.c1, y);
+}
+__device__ __forceinline__ gl2 xacc_reduce(const xacc& a) {
+    acc192 t = a.a00;
+    acc_mad(t, acc_reduce(a.a11), 7);  // X^2 = 7
+    return gl2_make(acc_reduce(t), acc_reduce(a.ax));
+}
+// fold: a0 + r * (a1 - a0), canonical inputs, canonical output; r7 = 7 * r.c1 mod p
+__device__ __forceinline__ gl2 gl2_fold(gl2 a0, gl2 a1, gl2 r, u64 r7) {
+    const u64 d0 = gl_sub_cs(a1.c0, a0.c0), d1 = gl_sub_cs(a1.c1, a0.c1);
+    acc192 c0 = acc_zero(), c1 = acc_zero();
+    c0.lo = a0.c0;
+    c1.lo = a0.c1;
+    acc_mad(c0, r.c0, d0);
+    acc_mad(c0, r7, d1);
+    acc_mad(c1, r.c0, d1);
+    acc_mad(c1, r.c1, d0);
+    return gl2_make(acc_reduce(c0), acc_reduce(c1));
+}
+__device__ __forceinline__ gl2 gl2_fold(u64 a0, u64 a1, gl2 r, u64) {
+    const u64 d = gl_sub_cs(a1, a0);
+    acc192 c0 = acc_zero(), c1 = acc_zero();
+    c0.lo = a0;
+    acc_mad(c0, r.c0, d);
+    acc_mad(c1, r.c1, d);
+    return gl2_make(acc_reduce(c0), acc_reduce(c1));
+}
+// canonical product of two canonical/lazy extension elements
+__device__ __forceinline__ gl2 gl2_mul_fast(gl2 x, gl2 y) {
+    xacc a = xacc_zero();
+    xacc_mad(a, x, y);
+    return xacc_reduce(a);
+}
+__device__ __forceinline__ u64 gl_mul_fast(u64 x, u64 y) {
+    acc192 a = acc_zero();
+    acc_mad(a, x, y);
+    return acc_reduce(a);
+}
+#endif
+
 }  // namespace hg

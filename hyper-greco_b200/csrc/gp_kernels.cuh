@@ -1,13 +1,18 @@
 // Grand-product layer sumcheck kernels (K8; /root/reference/lasso/src/memory_checking/prover.rs:223-279), the dominant
 // cost of the Lasso node. One round of
 //        g = t_0 * sum_i c_i * l_i * r_i          (t_0 = l_0, F4/Q2; c_i = gamma^i under A5)
-// per launch, evaluation fused with the fold by the previous challenge. Differences from the generic k_sc_round:
+// per launch, evaluation fused with the fold by the previous challenge.
 //   * work is split over (pair-index tiles) x (term groups) so that small rounds still fill the GPU and every thread has
 //     several independent 256-bit loads in flight;
-//   * because h(X) = sum_i c_i sum_b t_0 l_i r_i is linear in the terms, the c_i are folded into the TABLES once
-//     (round 1 writes l'_i = c_i * l_i; folding is linear, so later rounds never multiply by c_i again) and the final
-//     evaluations are unscaled on the host with c_i^{-1}. Field arithmetic is exact, so the messages are bit-identical;
-//   * round 0 runs entirely in the base field and multiplies by c_i once per (thread, term).
+//   * h(X) = sum_i c_i sum_b t_0 l_i r_i is linear in the terms, so the c_i are folded into the TABLES once (round 1
+//     writes l'_i = c_i * l_i; folding is linear, later rounds never multiply by c_i again) and the final evaluations are
+//     unscaled on the host with c_i^{-1}. Field arithmetic is exact, so the messages are bit-identical;
+//   * the round polynomial is sampled at X = 0, infinity (leading coefficient) and -1: those line values cost one
+//     subtraction each. Together with the running TRUE sum h(0) + h(1) (tracked on the host, h(1) is sampled only in
+//     round 0) they determine the cubic exactly; the host derives whatever the wire format needs (A3);
+//   * products are accumulated unreduced (gl.cuh acc192 / xacc) and reduced once per accumulator: the kernels are bound by
+//     the integer ALU pipe, not by HBM, so instruction count is what matters (profiles/).
+// Message slots: [h(0), h(inf), h(-1)] and, in round 0 only, [.., h(1)].
 #pragma once
 #include "kernels.cuh"
 
@@ -32,28 +37,20 @@ __device__ __forceinline__ void load4(const gl2* p, gl2 (&v)[4]) {
 __device__ __forceinline__ void load2(const u64* p, u64 (&v)[2]) { ldg128(p, v[0], v[1]); }
 __device__ __forceinline__ void store2(gl2* p, gl2 a, gl2 b) { stg256(p, a.c0, a.c1, b.c0, b.c1); }
 
-// values of the line through (0, lo), (1, hi) at the message points: slot 0 -> X=0, 1 -> X=2, 2 -> X=3 [, 3 -> X=1]
-template <class FP, class T, int NP> __device__ __forceinline__ void line_points(T lo, T hi, T (&v)[NP]) {
-    T df = FP::sub(hi, lo);
-    v[0] = lo;
-    v[1] = FP::add(hi, df);
-    v[2] = FP::add(v[1], df);
-    if constexpr (NP == 4) v[3] = hi;
-}
-
 // ---- round 0: base-field tables [nvec][2n] (l_i = first half, r_i = second half of vector i), n = 2^nv
-template <class FP, int U, bool WITH_H1>
+//      msg: h(0), h(inf), h(-1), h(1)
+template <class FP, int U>
 __global__ void __launch_bounds__(HG_BLOCK)
 k_gp_r0(const typename FP::B* __restrict__ tables, size_t n, int nvec, int tpg, const typename FP::X* __restrict__ coeffs,
         typename FP::X* partials, unsigned* counter, typename FP::X* msg) {
     typedef typename FP::B B;
     typedef typename FP::X X;
-    constexpr int NP = WITH_H1 ? 4 : 3;
+    constexpr int NP = 4;
     const size_t npairs = n / 2, stride = (size_t)gridDim.x * blockDim.x;
     const int i0 = blockIdx.y * tpg, i1 = min(nvec, i0 + tpg);
-    X acc[NP];
+    typename FP::XAcc accx[NP];
 #pragma unroll
-    for (int p = 0; p < NP; p++) acc[p] = FP::x_zero();
+    for (int p = 0; p < NP; p++) accx[p] = FP::xacc_zero_();
     for (size_t b0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b0 < npairs; b0 += stride * U) {
         B t0[U][NP];
 #pragma unroll
@@ -61,7 +58,7 @@ k_gp_r0(const typename FP::B* __restrict__ tables, size_t n, int nvec, int tpg, 
             const size_t b = b0 + u * stride;
             B p[2] = {FP::b_zero(), FP::b_zero()};
             if (b < npairs) load2(tables + 2 * b, p);
-            line_points<FP, B, NP>(p[0], p[1], t0[u]);
+            t0[u][0] = p[0]; t0[u][1] = FP::slope(p[0], p[1]); t0[u][2] = FP::at_m1(p[0], p[1]); t0[u][3] = p[1];
         }
         for (int i = i0; i < i1; i++) {
             const B* li = tables + (size_t)i * 2 * n;
@@ -73,39 +70,42 @@ k_gp_r0(const typename FP::B* __restrict__ tables, size_t n, int nvec, int tpg, 
                 l[u][0] = l[u][1] = r[u][0] = r[u][1] = FP::b_zero();
                 if (b < npairs) { load2(li + 2 * b, l[u]); load2(ri + 2 * b, r[u]); }
             }
-            B s[NP];
+            typename FP::BAcc s[NP];
 #pragma unroll
-            for (int p = 0; p < NP; p++) s[p] = FP::b_zero();
+            for (int p = 0; p < NP; p++) s[p] = FP::bacc_zero();
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                B vl[NP], vr[NP];
-                line_points<FP, B, NP>(l[u][0], l[u][1], vl);
-                line_points<FP, B, NP>(r[u][0], r[u][1], vr);
-#pragma unroll
-                for (int p = 0; p < NP; p++) s[p] = FP::b_add(s[p], FP::b_mul(t0[u][p], FP::b_mul(vl[p], vr[p])));
+                FP::bacc_mad(s[0], t0[u][0], FP::fmul(l[u][0], r[u][0]));
+                FP::bacc_mad(s[1], t0[u][1], FP::fmul(FP::slope(l[u][0], l[u][1]), FP::slope(r[u][0], r[u][1])));
+                FP::bacc_mad(s[2], t0[u][2], FP::fmul(FP::at_m1(l[u][0], l[u][1]), FP::at_m1(r[u][0], r[u][1])));
+                FP::bacc_mad(s[3], t0[u][3], FP::fmul(l[u][1], r[u][1]));
             }
             const X c = coeffs[i];
 #pragma unroll
-            for (int p = 0; p < NP; p++) acc[p] = FP::x_add(acc[p], FP::x_mul_b(c, s[p]));
+            for (int p = 0; p < NP; p++) FP::xacc_mad_b(accx[p], c, FP::bacc_reduce(s[p]));
         }
     }
+    X acc[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) acc[p] = FP::xacc_reduce_(accx[p]);
     block_reduce_finalize<FP, NP, true>(acc, partials, counter, msg);
 }
 
 // ---- rounds >= 1: fold by r_prev, write the folded tables, evaluate the next round polynomial on them
 //   in : [2*nvec][n_in] (TIN = B in round 1, X later);  out: [2*nvec][n_in/2]
-//   SCALE (round 1): l_i (i > 0) is multiplied by c_i when it is written; later rounds see pre-scaled tables
-template <class FP, class TIN, bool SCALE, bool WITH_H1>
+//   SCALE (round 1, TIN = B): l_i (i > 0) is written as c_i * l_i; cr[i] = c_i * r_prev is precomputed (k_gp_coeffs)
+//   msg: h(0), h(inf), h(-1)
+template <class FP, class TIN, bool SCALE>
 __global__ void __launch_bounds__(HG_BLOCK)
 k_gp_fold(const TIN* __restrict__ in, typename FP::X* __restrict__ out, size_t n_in, int nvec, int tpg,
-          const typename FP::X* __restrict__ coeffs, const typename FP::X* __restrict__ r_prev, typename FP::X* partials, unsigned* counter,
-          typename FP::X* msg) {
+          const typename FP::X* __restrict__ coeffs, const typename FP::X* __restrict__ cr, const typename FP::X* __restrict__ r_prev,
+          typename FP::X* partials, unsigned* counter, typename FP::X* msg) {
     typedef typename FP::X X;
-    constexpr int NP = WITH_H1 ? 4 : 3;
+    constexpr int NP = 3;
     const size_t npairs = n_in / 4, n_out = n_in / 2;
     const int i0 = blockIdx.y * tpg, i1 = min(nvec, i0 + tpg);
     const X r = *r_prev;
-    const X c0 = coeffs[0];
+    const typename FP::FoldAux aux = FP::fold_aux(r);
     X acc[NP];
 #pragma unroll
     for (int p = 0; p < NP; p++) acc[p] = FP::x_zero();
@@ -114,43 +114,63 @@ k_gp_fold(const TIN* __restrict__ in, typename FP::X* __restrict__ out, size_t n
         {
             TIN a[4];
             load4(in + 4 * b, a);
-            X lo = FP::x_add(FP::as_x(a[0]), FP::mul(r, FP::sub(a[1], a[0])));
-            X hi = FP::x_add(FP::as_x(a[2]), FP::mul(r, FP::sub(a[3], a[2])));
-            line_points<FP, X, NP>(lo, hi, t0);
+            X lo = FP::fold(a[0], a[1], r, aux), hi = FP::fold(a[2], a[3], r, aux);
+            t0[0] = lo; t0[1] = FP::slope(lo, hi); t0[2] = FP::at_m1(lo, hi);
         }
-        X P[NP];
+        typename FP::XAcc P[NP];
 #pragma unroll
-        for (int p = 0; p < NP; p++) P[p] = FP::x_zero();
-#pragma unroll 2
+        for (int p = 0; p < NP; p++) P[p] = FP::xacc_zero_();
         for (int i = i0; i < i1; i++) {
             TIN a[4], c[4];
             load4(in + (size_t)(2 * i) * n_in + 4 * b, a);
             load4(in + (size_t)(2 * i + 1) * n_in + 4 * b, c);
-            X l_lo = FP::x_add(FP::as_x(a[0]), FP::mul(r, FP::sub(a[1], a[0])));
-            X l_hi = FP::x_add(FP::as_x(a[2]), FP::mul(r, FP::sub(a[3], a[2])));
-            X r_lo = FP::x_add(FP::as_x(c[0]), FP::mul(r, FP::sub(c[1], c[0])));
-            X r_hi = FP::x_add(FP::as_x(c[2]), FP::mul(r, FP::sub(c[3], c[2])));
-            if (SCALE && i > 0) {
-                const X ci = coeffs[i];
-                l_lo = FP::x_mul(l_lo, ci);
-                l_hi = FP::x_mul(l_hi, ci);
+            X l_lo, l_hi;
+            if constexpr (SCALE) {
+                if (i > 0) {
+                    const X ci = coeffs[i], cri = cr[i];
+                    l_lo = FP::fold_scaled(a[0], a[1], ci, cri);
+                    l_hi = FP::fold_scaled(a[2], a[3], ci, cri);
+                } else {
+                    l_lo = FP::fold(a[0], a[1], r, aux);
+                    l_hi = FP::fold(a[2], a[3], r, aux);
+                }
+            } else {
+                l_lo = FP::fold(a[0], a[1], r, aux);
+                l_hi = FP::fold(a[2], a[3], r, aux);
             }
+            const X r_lo = FP::fold(c[0], c[1], r, aux), r_hi = FP::fold(c[2], c[3], r, aux);
             store2(out + (size_t)(2 * i) * n_out + 2 * b, l_lo, l_hi);
             store2(out + (size_t)(2 * i + 1) * n_out + 2 * b, r_lo, r_hi);
-            X vl[NP], vr[NP];
-            line_points<FP, X, NP>(l_lo, l_hi, vl);
-            line_points<FP, X, NP>(r_lo, r_hi, vr);
-#pragma unroll
-            for (int p = 0; p < NP; p++) {
-                X pr = FP::x_mul(vl[p], vr[p]);
-                if (i == 0) pr = FP::x_mul(pr, c0);
-                P[p] = FP::x_add(P[p], pr);
+            if (i == 0) {
+                // term 0 keeps l_0 unscaled (it is also t_0), so its products take c_0 explicitly
+                const X c0 = coeffs[0];
+                FP::xacc_mad_(P[0], FP::fmul(c0, l_lo), r_lo);
+                FP::xacc_mad_(P[1], FP::fmul(c0, FP::slope(l_lo, l_hi)), FP::slope(r_lo, r_hi));
+                FP::xacc_mad_(P[2], FP::fmul(c0, FP::at_m1(l_lo, l_hi)), FP::at_m1(r_lo, r_hi));
+            } else {
+                FP::xacc_mad_(P[0], l_lo, r_lo);
+                FP::xacc_mad_(P[1], FP::slope(l_lo, l_hi), FP::slope(r_lo, r_hi));
+                FP::xacc_mad_(P[2], FP::at_m1(l_lo, l_hi), FP::at_m1(r_lo, r_hi));
             }
         }
 #pragma unroll
-        for (int p = 0; p < NP; p++) acc[p] = FP::x_add(acc[p], FP::x_mul(t0[p], P[p]));
+        for (int p = 0; p < NP; p++) acc[p] = FP::x_add(acc[p], FP::fmul(t0[p], FP::xacc_reduce_(P[p])));
     }
     block_reduce_finalize<FP, NP, true>(acc, partials, counter, msg);
+}
+
+// per-layer coefficient tables: c[i] = gamma^i (A5: or reversed), cr[i] = c[i] * r_0 when r0 != nullptr
+template <class FP>
+__global__ void k_gp_coeffs(const typename FP::X* __restrict__ gamma, const typename FP::X* __restrict__ r0, int n, int ascending,
+                            typename FP::X* __restrict__ c, typename FP::X* __restrict__ cr) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    typename FP::X p = FP::x_one(), g = *gamma;
+    for (int i = 0; i < n; i++) {
+        const int k = ascending ? i : n - 1 - i;
+        c[k] = p;
+        if (r0) cr[k] = FP::x_mul(p, *r0);
+        p = FP::x_mul(p, g);
+    }
 }
 
 }  // namespace hg

@@ -4,6 +4,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "field_policy.cuh"
 
 namespace hg {
@@ -247,21 +249,23 @@ __global__ void k_tree_top(const typename FP::B* __restrict__ top, int nvec, typ
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K5/K8: one sumcheck round of g = t_0 * sum_i coeff[i] * prod_{k<ARITY} t_{ARITY*i+k}  (lasso.rs:457-475,
-// prover.rs:268-279), evaluation FUSED with the fold by the previous round's challenge, so every table is read once
-// and its folded image written once per round.
+// K5 (and the generic hg_sumcheck_prove): one sumcheck round of g = t_0 * sum_i coeff[i] * prod_{k<ARITY} t_{ARITY*i+k}
+// (lasso.rs:457-475, prover.rs:268-279), evaluation FUSED with the fold by the previous round's challenge, so every table
+// is read once and its folded image written once per round.
 //   in : ntab tables of n_in elements (TIN = B in rounds 0/1, X later), table t at in + t*n_in
 //   FOLD: out[t][q] = in[t][2q] + r_prev*(in[t][2q+1] - in[t][2q]) is written (n_in/2 per table) and the round
-//         polynomial is evaluated on the folded values; !FOLD: evaluated on `in` directly (round 0).
-//   msg: h(0), h(2), .., h(d) [, h(1) when WITH_H1]  with d = ARITY + 1, X = lowest remaining variable (LSB first)
-template <class FP, class TIN, int ARITY, bool FOLD, bool WITH_H1>
+//         polynomial is sampled on the folded values; !FOLD (= round 0): sampled on `in` directly.
+//   msg: h(0), h(inf) [, h(-1) when ARITY == 2] and, in round 0 only, h(1) last. X = lowest remaining variable (A4).
+//   The host tracks the true running sum h(0) + h(1) and reconstructs the polynomial (prover.cuh emit_round).
+template <class FP, class TIN, int ARITY, bool FOLD>
 __global__ void __launch_bounds__(HG_BLOCK)
 k_sc_round(const TIN* __restrict__ in, typename FP::X* __restrict__ out, size_t n_in, int nterm,
            const typename FP::X* __restrict__ coeffs, const typename FP::X* __restrict__ r_prev, typename FP::X* partials,
            unsigned* counter, typename FP::X* msg) {
     typedef typename FP::X X;
     constexpr int D = ARITY + 1;
-    constexpr int NP = WITH_H1 ? D + 1 : D;  // slots: 0 -> X=0, 1..D-1 -> X=2..D, D -> X=1
+    constexpr int NP = FOLD ? D : D + 1;
+    typedef typename std::conditional<FOLD, X, TIN>::type EL;  // element type the round polynomial is sampled on
     const size_t npairs = FOLD ? n_in / 4 : n_in / 2;
     const size_t n_out = n_in / 2;
     X acc[NP];
@@ -270,73 +274,47 @@ k_sc_round(const TIN* __restrict__ in, typename FP::X* __restrict__ out, size_t 
     X r = FP::x_zero();
     if (FOLD) r = *r_prev;
     for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < npairs; b += (size_t)gridDim.x * blockDim.x) {
-        if constexpr (FOLD) {
-            X inner[NP], t0[NP];
+        X inner[NP];
+        EL t0[NP];
 #pragma unroll
-            for (int p = 0; p < NP; p++) inner[p] = FP::x_zero();
-            for (int i = 0; i < nterm; i++) {
-                X prod[NP];
+        for (int p = 0; p < NP; p++) inner[p] = FP::x_zero();
+        for (int i = 0; i < nterm; i++) {
+            EL prod[NP];
 #pragma unroll
-                for (int k = 0; k < ARITY; k++) {
-                    const int t = ARITY * i + k;
+            for (int k = 0; k < ARITY; k++) {
+                const int t = ARITY * i + k;
+                EL lo, hi;
+                if constexpr (FOLD) {
                     const TIN* src = in + (size_t)t * n_in + 4 * b;
                     TIN a0 = src[0], a1 = src[1], a2 = src[2], a3 = src[3];
-                    X lo = FP::x_add(FP::as_x(a0), FP::mul(r, FP::sub(a1, a0)));
-                    X hi = FP::x_add(FP::as_x(a2), FP::mul(r, FP::sub(a3, a2)));
+                    lo = FP::x_add(FP::as_x(a0), FP::mul(r, FP::sub(a1, a0)));
+                    hi = FP::x_add(FP::as_x(a2), FP::mul(r, FP::sub(a3, a2)));
                     X* dst = out + (size_t)t * n_out + 2 * b;
                     dst[0] = lo;
                     dst[1] = hi;
-                    X df = FP::x_sub(hi, lo);
-                    X v[NP];
-                    v[0] = lo;
-                    X cur = FP::x_add(hi, df);
-#pragma unroll
-                    for (int p = 1; p < D; p++) { v[p] = cur; cur = FP::x_add(cur, df); }
-                    if constexpr (WITH_H1) v[NP - 1] = hi;
-#pragma unroll
-                    for (int p = 0; p < NP; p++) {
-                        if (k == 0) prod[p] = v[p]; else prod[p] = FP::x_mul(prod[p], v[p]);
-                        if (i == 0 && k == 0) t0[p] = v[p];
-                    }
-                }
-                X c = coeffs[i];
-#pragma unroll
-                for (int p = 0; p < NP; p++) inner[p] = FP::x_add(inner[p], FP::x_mul(c, prod[p]));
-            }
-#pragma unroll
-            for (int p = 0; p < NP; p++) acc[p] = FP::x_add(acc[p], FP::x_mul(t0[p], inner[p]));
-        } else {
-            X inner[NP];
-            TIN t0[NP];
-#pragma unroll
-            for (int p = 0; p < NP; p++) inner[p] = FP::x_zero();
-            for (int i = 0; i < nterm; i++) {
-                TIN prod[NP];
-#pragma unroll
-                for (int k = 0; k < ARITY; k++) {
-                    const int t = ARITY * i + k;
+                } else {
                     const TIN* src = in + (size_t)t * n_in + 2 * b;
-                    TIN lo = src[0], hi = src[1];
-                    TIN df = FP::sub(hi, lo);
-                    TIN v[NP];
-                    v[0] = lo;
-                    TIN cur = FP::add(hi, df);
-#pragma unroll
-                    for (int p = 1; p < D; p++) { v[p] = cur; cur = FP::add(cur, df); }
-                    if constexpr (WITH_H1) v[NP - 1] = hi;
-#pragma unroll
-                    for (int p = 0; p < NP; p++) {
-                        if (k == 0) prod[p] = v[p]; else prod[p] = FP::mul(prod[p], v[p]);
-                        if (i == 0 && k == 0) t0[p] = v[p];
-                    }
+                    lo = src[0];
+                    hi = src[1];
                 }
-                X c = coeffs[i];
+                EL v[NP];
+                EL df = FP::sub(hi, lo);
+                v[0] = lo;
+                v[1] = df;
+                if constexpr (D == 3) v[2] = FP::sub(lo, df);
+                if constexpr (!FOLD) v[D] = hi;
 #pragma unroll
-                for (int p = 0; p < NP; p++) inner[p] = FP::x_add(inner[p], FP::mul(c, prod[p]));
+                for (int p = 0; p < NP; p++) {
+                    if (k == 0) prod[p] = v[p]; else prod[p] = FP::mul(prod[p], v[p]);
+                    if (i == 0 && k == 0) t0[p] = v[p];
+                }
             }
+            X c = coeffs[i];
 #pragma unroll
-            for (int p = 0; p < NP; p++) acc[p] = FP::x_add(acc[p], FP::mul(inner[p], t0[p]));
+            for (int p = 0; p < NP; p++) inner[p] = FP::x_add(inner[p], FP::mul(c, prod[p]));
         }
+#pragma unroll
+        for (int p = 0; p < NP; p++) acc[p] = FP::x_add(acc[p], FP::mul(inner[p], t0[p]));
     }
     block_reduce_finalize<FP, NP>(acc, partials, counter, msg);
 }

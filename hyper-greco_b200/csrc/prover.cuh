@@ -231,9 +231,10 @@ template <class FP> struct RoundPoly {
 // host-side state of one sumcheck instance (claim bookkeeping happens while messages are serialised)
 template <class FP> struct ScHostState {
     typedef typename FP::X X;
-    X claim;
+    X claim;                         // the claim the WIRE polynomial is checked against (prove_sum_check's running claim)
     bool has_pending = false;
-    std::vector<X> pending_coeffs;
+    std::vector<X> pending_wire;     // coefficients of the polynomial that went on the wire last round
+    std::vector<X> pending_true;     // coefficients of the TRUE round polynomial of the last round
     size_t pending_chal = 0;
 };
 
@@ -243,24 +244,50 @@ struct ScScratch {
     int max_blocks = 0;
 };
 
-// serialisation of one round message + claim bookkeeping (runs on the host when the message has been downloaded)
+// serialisation of one round message + claim bookkeeping (runs on the host when the message has been downloaded).
+// The device sends samples of the TRUE round polynomial h: h(0), h(inf), [h(-1)], and h(1) in round 0. With the running
+// true sum s = h(0) + h(1) (= previous true polynomial at the previous challenge) they determine h; the wire message then
+// follows the upstream format under assumptions A3 / A3'.
 template <class FP, int D>
-void emit_round(Channel<FP>& ch, std::shared_ptr<ScHostState<FP>> st, size_t off, const WireOptions& wo, bool h1, size_t next_idx) {
+void emit_round(Channel<FP>& ch, std::shared_ptr<ScHostState<FP>> st, size_t off, const WireOptions& wo, bool round0, size_t next_idx) {
     typedef typename FP::X X;
     Channel<FP>* chp = &ch;
     WireOptions w = wo;
-    ch.emit([chp, st, off, w, h1, next_idx]() {
+    ch.emit([chp, st, off, w, round0, next_idx]() {
         typedef RoundPoly<FP> RP;
-        if (st->has_pending) st->claim = RP::horner(st->pending_coeffs, chp->chal(st->pending_chal));
+        X s;
+        if (round0) {
+            s = FP::x_add(chp->msg(off), chp->msg(off + D));
+        } else {
+            X rprev = chp->chal(st->pending_chal);
+            s = RP::horner(st->pending_true, rprev);
+            st->claim = RP::horner(st->pending_wire, rprev);
+        }
+        const X h0 = chp->msg(off), hinf = chp->msg(off + 1);
+        std::vector<X> tc(D + 1);
+        tc[0] = h0;
+        tc[D] = hinf;
+        X a = FP::x_sub(FP::x_sub(s, FP::x_add(h0, h0)), hinf);  // sum of the middle coefficients
+        if (D == 2) {
+            tc[1] = a;
+        } else {
+            X bv = FP::x_add(FP::x_sub(chp->msg(off + 2), h0), hinf);  // c2 - c1
+            X inv2 = FP::x_inv(RP::small(2));
+            tc[2] = FP::x_mul(FP::x_add(a, bv), inv2);
+            tc[1] = FP::x_mul(FP::x_sub(a, bv), inv2);
+        }
         std::vector<X> ev(D + 1);
-        ev[0] = chp->msg(off);
-        for (int p = 2; p <= D; p++) ev[p] = chp->msg(off + p - 1);
-        ev[1] = h1 ? chp->msg(off + D) : FP::x_sub(st->claim, ev[0]);
-        std::vector<X> co = RP::interpolate(ev);
+        for (int k = 0; k <= D; k++) ev[k] = RP::horner(tc, RP::small(k));
+        std::vector<X> co = tc;
+        if (w.a3_h1 == 0) {
+            ev[1] = FP::x_sub(st->claim, ev[0]);
+            co = RP::interpolate(ev);
+        }
         auto& tr = chp->transcript();
         if (w.a3_wire == 0) { tr.write_felt_ext(co[0]); for (int p = 2; p <= D; p++) tr.write_felt_ext(co[p]); }
         else { tr.write_felt_ext(ev[0]); for (int p = 2; p <= D; p++) tr.write_felt_ext(ev[p]); }
-        st->pending_coeffs = co;
+        st->pending_wire = co;
+        st->pending_true = tc;
         st->pending_chal = next_idx;
         st->has_pending = true;
     });
@@ -268,7 +295,7 @@ void emit_round(Channel<FP>& ch, std::shared_ptr<ScHostState<FP>> st, size_t off
 
 // one launch of k_sc_round with the right instantiation
 template <class FP, int ARITY>
-void launch_sc_round(DeviceCtx* ctx, int kclass, bool in_base, bool fold, bool with_h1, const void* in, typename FP::X* out, size_t n_in, int nterm,
+void launch_sc_round(DeviceCtx* ctx, int kclass, bool in_base, bool fold, const void* in, typename FP::X* out, size_t n_in, int nterm,
                      const typename FP::X* coeffs, const typename FP::X* r_prev, const ScScratch& sc, typename FP::X* msg) {
     typedef typename FP::B B;
     typedef typename FP::X X;
@@ -280,15 +307,10 @@ void launch_sc_round(DeviceCtx* ctx, int kclass, bool in_base, bool fold, bool w
     const size_t ntab = (size_t)nterm * ARITY;
     const size_t bytes = ntab * n_in * (in_base ? sizeof(B) : sizeof(X)) + (fold ? ntab * (n_in / 2) * sizeof(X) : 0);
     KernelScope _ks(ctx, kclass, bytes);
-#define HG_SC(TIN, FOLD, H1) \
-    k_sc_round<FP, TIN, ARITY, FOLD, H1><<<blocks, HG_BLOCK, 0, ctx->stream>>>((const TIN*)in, out, n_in, nterm, coeffs, r_prev, part, sc.counters, msg)
-    if (in_base) {
-        if (fold) { if (with_h1) HG_SC(B, true, true); else HG_SC(B, true, false); }
-        else { if (with_h1) HG_SC(B, false, true); else HG_SC(B, false, false); }
-    } else {
-        if (!fold) throw std::runtime_error("launch_sc_round: extension input is always folded");
-        if (with_h1) HG_SC(X, true, true); else HG_SC(X, true, false);
-    }
+#define HG_SC(TIN, FOLD) \
+    k_sc_round<FP, TIN, ARITY, FOLD><<<blocks, HG_BLOCK, 0, ctx->stream>>>((const TIN*)in, out, n_in, nterm, coeffs, r_prev, part, sc.counters, msg)
+    if (in_base) { if (fold) HG_SC(B, true); else HG_SC(B, false); }
+    else { if (!fold) throw std::runtime_error("launch_sc_round: extension input is always folded"); HG_SC(X, true); }
 #undef HG_SC
     HG_LAUNCH_CHECK();
 }
@@ -306,23 +328,21 @@ void sumcheck_dev(DeviceCtx* ctx, int kclass, Channel<FP>& ch, const WireOptions
     int nv = 0;
     while (((size_t)1 << nv) < n) nv++;
     if (nv < 1) throw std::runtime_error("sumcheck_dev: num_vars must be positive");
-    const bool h1 = wo.a3_h1 != 0;
-    const int NP = h1 ? D + 1 : D;
     const void* cur_in = d_tables;
     bool in_base = true;
     size_t n_in = n;
     size_t prev_chal = 0;
     for (int j = 0; j < nv; j++) {
-        size_t off = ch.alloc_msg(NP);
+        size_t off = ch.alloc_msg(j == 0 ? D + 1 : D);
         if (j == 0) {
-            launch_sc_round<FP, ARITY>(ctx, kclass, true, false, h1, d_tables, nullptr, n, nterm, d_coeffs, nullptr, sc, ch.d_msg(off));
+            launch_sc_round<FP, ARITY>(ctx, kclass, true, false, d_tables, nullptr, n, nterm, d_coeffs, nullptr, sc, ch.d_msg(off));
         } else {
             X* out = (j & 1) ? bufA : bufB;
-            launch_sc_round<FP, ARITY>(ctx, kclass, in_base, true, h1, cur_in, out, n_in, nterm, d_coeffs, ch.d_chal(prev_chal), sc, ch.d_msg(off));
+            launch_sc_round<FP, ARITY>(ctx, kclass, in_base, true, cur_in, out, n_in, nterm, d_coeffs, ch.d_chal(prev_chal), sc, ch.d_msg(off));
             cur_in = out; in_base = false; n_in >>= 1;
         }
         const size_t next_idx = ch.next_index();  // the challenge squeezed right after this message
-        emit_round<FP, D>(ch, st, off, wo, h1, next_idx);
+        emit_round<FP, D>(ch, st, off, wo, j == 0, next_idx);
         prev_chal = ch.squeeze(1);
         if (prev_chal != next_idx) throw std::runtime_error("sumcheck_dev: challenge index drift");
         if (j == 0 && first_chal) *first_chal = prev_chal;
@@ -336,10 +356,11 @@ void sumcheck_dev(DeviceCtx* ctx, int kclass, Channel<FP>& ch, const WireOptions
 }
 
 // Grand-product layer sumcheck with the specialised kernels of gp_kernels.cuh. tables: [nvec][2n] base elements.
+// d_gamma: the layer's batching challenge (device); d_coeffs: scratch for [c_i | c_i * r_0] (2*nvec).
 // *scaled = whether the final evaluations of l_i (i > 0) carry the factor c_i (true iff a round >= 1 ran).
 template <class FP>
 void gp_sumcheck_dev(DeviceCtx* ctx, Channel<FP>& ch, const WireOptions& wo, const typename FP::B* d_tables, size_t n, int nvec,
-                     const typename FP::X* d_coeffs, typename FP::X* bufA, typename FP::X* bufB, const ScScratch& sc,
+                     const typename FP::X* d_gamma, typename FP::X* d_coeffs, typename FP::X* bufA, typename FP::X* bufB, const ScScratch& sc,
                      std::shared_ptr<ScHostState<FP>> st, size_t* first_chal, size_t* evals_off, bool* scaled) {
     typedef typename FP::B B;
     typedef typename FP::X X;
@@ -347,9 +368,9 @@ void gp_sumcheck_dev(DeviceCtx* ctx, Channel<FP>& ch, const WireOptions& wo, con
     const int ntab = 2 * nvec;
     int nv = 0;
     while (((size_t)1 << nv) < n) nv++;
-    const bool h1 = wo.a3_h1 != 0;
-    const int NP = h1 ? D + 1 : D;
     X* part = (X*)sc.partials;
+    X* d_c = d_coeffs;
+    X* d_cr = d_coeffs + nvec;
     const int target_blocks = ctx->sm_count * 4;
     auto plan = [&](size_t threads_x, int* bx, int* groups, int* tpg) {
         size_t b = (threads_x + HG_BLOCK - 1) / HG_BLOCK;
@@ -360,34 +381,33 @@ void gp_sumcheck_dev(DeviceCtx* ctx, Channel<FP>& ch, const WireOptions& wo, con
         *groups = (nvec + *tpg - 1) / *tpg;
         *bx = (int)b;
     };
+    HG_K(ctx, KC_MISC, 0, k_gp_coeffs<FP><<<1, 32, 0, ctx->stream>>>(d_gamma, nullptr, nvec, wo.a5_ascending, d_c, d_cr));
     const void* cur_in = d_tables;
     bool in_base = true;
     size_t n_in = n, prev_chal = 0;
     for (int j = 0; j < nv; j++) {
-        size_t off = ch.alloc_msg(NP);
+        size_t off = ch.alloc_msg(j == 0 ? D + 1 : D);
         int bx, groups, tpg;
         if (j == 0) {
             constexpr int U = 4;
             plan((n / 2 + U - 1) / U, &bx, &groups, &tpg);
             KernelScope ks(ctx, KC_SC_GP, (size_t)ntab * n * sizeof(B));
-            if (h1) k_gp_r0<FP, U, true><<<dim3(bx, groups), HG_BLOCK, 0, ctx->stream>>>(d_tables, n, nvec, tpg, d_coeffs, part, sc.counters, ch.d_msg(off));
-            else k_gp_r0<FP, U, false><<<dim3(bx, groups), HG_BLOCK, 0, ctx->stream>>>(d_tables, n, nvec, tpg, d_coeffs, part, sc.counters, ch.d_msg(off));
+            k_gp_r0<FP, U><<<dim3(bx, groups), HG_BLOCK, 0, ctx->stream>>>(d_tables, n, nvec, tpg, d_c, part, sc.counters, ch.d_msg(off));
             HG_LAUNCH_CHECK();
         } else {
             X* out = (j & 1) ? bufA : bufB;
+            const X* rp = ch.d_chal(prev_chal);
+            if (j == 1) HG_K(ctx, KC_MISC, 0, k_gp_coeffs<FP><<<1, 32, 0, ctx->stream>>>(d_gamma, rp, nvec, wo.a5_ascending, d_c, d_cr));
             plan(n_in / 4, &bx, &groups, &tpg);
             KernelScope ks(ctx, KC_SC_GP, (size_t)ntab * n_in * (in_base ? sizeof(B) : sizeof(X)) + (size_t)ntab * (n_in / 2) * sizeof(X));
-            const X* rp = ch.d_chal(prev_chal);
             dim3 grid(bx, groups);
-#define HG_GP(TIN, SC, H1) k_gp_fold<FP, TIN, SC, H1><<<grid, HG_BLOCK, 0, ctx->stream>>>((const TIN*)cur_in, out, n_in, nvec, tpg, d_coeffs, rp, part, sc.counters, ch.d_msg(off))
-            if (in_base) { if (h1) HG_GP(B, true, true); else HG_GP(B, true, false); }
-            else { if (h1) HG_GP(X, false, true); else HG_GP(X, false, false); }
-#undef HG_GP
+            if (in_base) k_gp_fold<FP, B, true><<<grid, HG_BLOCK, 0, ctx->stream>>>((const B*)cur_in, out, n_in, nvec, tpg, d_c, d_cr, rp, part, sc.counters, ch.d_msg(off));
+            else k_gp_fold<FP, X, false><<<grid, HG_BLOCK, 0, ctx->stream>>>((const X*)cur_in, out, n_in, nvec, tpg, d_c, d_cr, rp, part, sc.counters, ch.d_msg(off));
             HG_LAUNCH_CHECK();
             cur_in = out; in_base = false; n_in >>= 1;
         }
         const size_t next_idx = ch.next_index();
-        emit_round<FP, D>(ch, st, off, wo, h1, next_idx);
+        emit_round<FP, D>(ch, st, off, wo, j == 0, next_idx);
         prev_chal = ch.squeeze(1);
         if (prev_chal != next_idx) throw std::runtime_error("gp_sumcheck_dev: challenge index drift");
         if (j == 0 && first_chal) *first_chal = prev_chal;
@@ -491,7 +511,7 @@ template <class FP> class LassoNodeDev {
         d_eq_.alloc(std::max(R_, M_));
         d_coeff_coll_.alloc(m_);
         d_wpow_.alloc(HG_MAX_C);
-        d_gp_coeffs_.alloc(2 * (size_t)m_);
+        d_gp_coeffs_.alloc(4 * (size_t)m_ + 4);
         // product trees: sum_k 2m * (N >> k) < 2m * 2N
         d_tree1_.alloc(2 * (size_t)m_ * 2 * R_);
         d_tree2_.alloc(2 * (size_t)m_ * 2 * M_);
@@ -699,7 +719,6 @@ template <class FP> class LassoNodeDev {
         for (int nv = 1; nv < nvars; nv++) {
             const size_t prev_mu = mu_idx;
             const size_t gamma_idx = ch.squeeze(1);  // prover.rs:238
-            HG_K(ctx_, KC_MISC, 0, k_powers<FP><<<1, 32, 0, s>>>(ch.d_chal(gamma_idx), nvec, wo.a5_ascending, d_gp_coeffs_.p));
             auto st = std::make_shared<ScHostState<FP>>();
             const int asc = wo.a5_ascending;
             ch.emit([chp, gp, st, prev_mu, gamma_idx, nvec, asc]() {
@@ -718,7 +737,7 @@ template <class FP> class LassoNodeDev {
             size_t sc_first = 0, ev_off = 0;
             bool scaled = false;
             const B* tables = layer[nvars - 1 - nv];
-            gp_sumcheck_dev<FP>(ctx_, ch, wo, tables, (size_t)1 << nv, nvec, d_gp_coeffs_.p, d_bufA_.p, d_bufB_.p, sc_, st, &sc_first, &ev_off, &scaled);
+            gp_sumcheck_dev<FP>(ctx_, ch, wo, tables, (size_t)1 << nv, nvec, ch.d_chal(gamma_idx), d_gp_coeffs_.p, d_bufA_.p, d_bufB_.p, sc_, st, &sc_first, &ev_off, &scaled);
             ch.emit([chp, gp, ev_off, nvec, scaled, gamma_idx, asc]() {
                 auto& t = chp->transcript();
                 // the device keeps l_i (i > 0) pre-multiplied by c_i (gp_kernels.cuh); undo it exactly with c_i^{-1}
