@@ -174,3 +174,346 @@ __global__ void k_gp_coeffs(const typename FP::X* __restrict__ gamma, const type
 }
 
 }  // namespace hg
+
+// =========================================================================================================
+// Batched (prefetch-mode) variants. With the challenges known up front every layer of both grand products is an
+// independent sumcheck, so round j of ALL layers runs in ONE launch (a grid partitioned by a descriptor table), and the
+// last rounds of every layer (tables of <= HG_GP_TAIL elements) run in ONE launch with one CTA per layer, tables in
+// shared memory. ~430 launches per proof become ~20.
+namespace hg {
+
+constexpr int HG_GP_TAIL_LOG = 6;
+constexpr int HG_GP_TAIL = 1 << HG_GP_TAIL_LOG;  // table length at which a layer moves to the shared-memory tail kernel
+constexpr int HG_TAIL_THREADS = 512;
+
+template <class FP> struct GpItem {
+    const void* in;                  // tables read this round (base in rounds 0/1, extension later): [2*nvec][n_in]
+    typename FP::X* out;             // folded tables written this round: [2*nvec][n_in/2]
+    unsigned long long n_in;
+    const typename FP::X* c;         // c_i
+    const typename FP::X* cr;        // c_i * r_0 (round 1)
+    const typename FP::X* r_prev;    // challenge folded in this round
+    typename FP::X* msg;
+    typename FP::X* partials;
+    unsigned* counter;
+    int nvec, tpg, bx, groups;
+    int blk_start, nblk;
+};
+
+template <class FP, int NP>
+__device__ __forceinline__ void block_reduce_finalize_ex(typename FP::X (&acc)[NP], typename FP::X* partials, unsigned* counter,
+                                                         typename FP::X* out, unsigned nblk, unsigned bid) {
+    typedef typename FP::X X;
+    __shared__ X sm[32][NP];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        X v = acc[p];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v = FP::x_add(v, FP::x_shfl_down(v, off));
+        if (lane == 0) sm[warp][p] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            X v = lane < nwarps ? sm[lane][p] : FP::x_zero();
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v = FP::x_add(v, FP::x_shfl_down(v, off));
+            if (lane == 0) partials[(size_t)bid * NP + p] = v;
+        }
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned t = atomicAdd(counter, 1u);
+        is_last = (t == nblk - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    X s[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) s[p] = FP::x_zero();
+    for (unsigned b = threadIdx.x; b < nblk; b += blockDim.x)
+#pragma unroll
+        for (int p = 0; p < NP; p++) s[p] = FP::x_add(s[p], FP::x_ldcg(partials + (size_t)b * NP + p));
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        X v = s[p];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v = FP::x_add(v, FP::x_shfl_down(v, off));
+        if (lane == 0) sm[warp][p] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            X v = lane < nwarps ? sm[lane][p] : FP::x_zero();
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v = FP::x_add(v, FP::x_shfl_down(v, off));
+            if (lane == 0) out[p] = v;
+        }
+        if (lane == 0) *counter = 0;
+    }
+}
+
+template <class FP> __device__ __forceinline__ int gp_find_item(const GpItem<FP>* items, int nitems) {
+    int k = 0;
+    while (k + 1 < nitems && (int)blockIdx.x >= items[k + 1].blk_start) k++;
+    return k;
+}
+
+template <class FP, int U>
+__global__ void __launch_bounds__(HG_BLOCK, 2) k_gp_r0_multi(const GpItem<FP>* __restrict__ items, int nitems) {
+    typedef typename FP::B B;
+    typedef typename FP::X X;
+    constexpr int NP = 4;
+    const GpItem<FP> it = items[gp_find_item<FP>(items, nitems)];
+    const unsigned lb = blockIdx.x - it.blk_start;
+    const unsigned bxi = lb % it.bx, grp = lb / it.bx;
+    const B* tables = (const B*)it.in;
+    const size_t n = it.n_in, npairs = n / 2, stride = (size_t)it.bx * blockDim.x;
+    const int i0 = grp * it.tpg, i1 = min(it.nvec, i0 + it.tpg);
+    typename FP::XAcc accx[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) accx[p] = FP::xacc_zero_();
+    for (size_t b0 = (size_t)bxi * blockDim.x + threadIdx.x; b0 < npairs; b0 += stride * U) {
+        B t0[U][NP];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const size_t b = b0 + u * stride;
+            B p[2] = {FP::b_zero(), FP::b_zero()};
+            if (b < npairs) load2(tables + 2 * b, p);
+            t0[u][0] = p[0]; t0[u][1] = FP::slope(p[0], p[1]); t0[u][2] = FP::at_m1(p[0], p[1]); t0[u][3] = p[1];
+        }
+        for (int i = i0; i < i1; i++) {
+            const B* li = tables + (size_t)i * 2 * n;
+            const B* ri = li + n;
+            B l[U][2], r[U][2];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const size_t b = b0 + u * stride;
+                l[u][0] = l[u][1] = r[u][0] = r[u][1] = FP::b_zero();
+                if (b < npairs) { load2(li + 2 * b, l[u]); load2(ri + 2 * b, r[u]); }
+            }
+            typename FP::BAcc s[NP];
+#pragma unroll
+            for (int p = 0; p < NP; p++) s[p] = FP::bacc_zero();
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                FP::bacc_mad(s[0], t0[u][0], FP::fmul(l[u][0], r[u][0]));
+                FP::bacc_mad(s[1], t0[u][1], FP::fmul(FP::slope(l[u][0], l[u][1]), FP::slope(r[u][0], r[u][1])));
+                FP::bacc_mad(s[2], t0[u][2], FP::fmul(FP::at_m1(l[u][0], l[u][1]), FP::at_m1(r[u][0], r[u][1])));
+                FP::bacc_mad(s[3], t0[u][3], FP::fmul(l[u][1], r[u][1]));
+            }
+            const X c = it.c[i];
+#pragma unroll
+            for (int p = 0; p < NP; p++) FP::xacc_mad_b(accx[p], c, FP::bacc_reduce(s[p]));
+        }
+    }
+    X acc[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) acc[p] = FP::xacc_reduce_(accx[p]);
+    block_reduce_finalize_ex<FP, NP>(acc, it.partials, it.counter, it.msg, it.nblk, lb);
+}
+
+template <class FP, class TIN, bool SCALE>
+__global__ void __launch_bounds__(HG_BLOCK, 2) k_gp_fold_multi(const GpItem<FP>* __restrict__ items, int nitems) {
+    typedef typename FP::X X;
+    constexpr int NP = 3;
+    const GpItem<FP> it = items[gp_find_item<FP>(items, nitems)];
+    const unsigned lb = blockIdx.x - it.blk_start;
+    const unsigned bxi = lb % it.bx, grp = lb / it.bx;
+    const TIN* in = (const TIN*)it.in;
+    X* out = it.out;
+    const size_t n_in = it.n_in, npairs = n_in / 4, n_out = n_in / 2;
+    const int i0 = grp * it.tpg, i1 = min(it.nvec, i0 + it.tpg);
+    const X r = *it.r_prev;
+    const typename FP::FoldAux aux = FP::fold_aux(r);
+    X acc[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) acc[p] = FP::x_zero();
+    for (size_t b = (size_t)bxi * blockDim.x + threadIdx.x; b < npairs; b += (size_t)it.bx * blockDim.x) {
+        X t0[NP];
+        {
+            TIN a[4];
+            load4(in + 4 * b, a);
+            X lo = FP::fold(a[0], a[1], r, aux), hi = FP::fold(a[2], a[3], r, aux);
+            t0[0] = lo; t0[1] = FP::slope(lo, hi); t0[2] = FP::at_m1(lo, hi);
+        }
+        typename FP::XAcc P[NP];
+#pragma unroll
+        for (int p = 0; p < NP; p++) P[p] = FP::xacc_zero_();
+        for (int i = i0; i < i1; i++) {
+            TIN a[4], c[4];
+            load4(in + (size_t)(2 * i) * n_in + 4 * b, a);
+            load4(in + (size_t)(2 * i + 1) * n_in + 4 * b, c);
+            X l_lo, l_hi;
+            if constexpr (SCALE) {
+                if (i > 0) {
+                    const X ci = it.c[i], cri = it.cr[i];
+                    l_lo = FP::fold_scaled(a[0], a[1], ci, cri);
+                    l_hi = FP::fold_scaled(a[2], a[3], ci, cri);
+                } else {
+                    l_lo = FP::fold(a[0], a[1], r, aux);
+                    l_hi = FP::fold(a[2], a[3], r, aux);
+                }
+            } else {
+                l_lo = FP::fold(a[0], a[1], r, aux);
+                l_hi = FP::fold(a[2], a[3], r, aux);
+            }
+            const X r_lo = FP::fold(c[0], c[1], r, aux), r_hi = FP::fold(c[2], c[3], r, aux);
+            store2(out + (size_t)(2 * i) * n_out + 2 * b, l_lo, l_hi);
+            store2(out + (size_t)(2 * i + 1) * n_out + 2 * b, r_lo, r_hi);
+            if (i == 0) {
+                const X c0 = it.c[0];
+                FP::xacc_mad_(P[0], FP::fmul(c0, l_lo), r_lo);
+                FP::xacc_mad_(P[1], FP::fmul(c0, FP::slope(l_lo, l_hi)), FP::slope(r_lo, r_hi));
+                FP::xacc_mad_(P[2], FP::fmul(c0, FP::at_m1(l_lo, l_hi)), FP::at_m1(r_lo, r_hi));
+            } else {
+                FP::xacc_mad_(P[0], l_lo, r_lo);
+                FP::xacc_mad_(P[1], FP::slope(l_lo, l_hi), FP::slope(r_lo, r_hi));
+                FP::xacc_mad_(P[2], FP::at_m1(l_lo, l_hi), FP::at_m1(r_lo, r_hi));
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < NP; p++) acc[p] = FP::x_add(acc[p], FP::fmul(t0[p], FP::xacc_reduce_(P[p])));
+    }
+    block_reduce_finalize_ex<FP, NP>(acc, it.partials, it.counter, it.msg, it.nblk, lb);
+}
+
+// coefficient tables of all layers in one launch: block = layer
+template <class FP> struct GpCoeffItem {
+    const typename FP::X* gamma;
+    const typename FP::X* r0;  // may be nullptr (layers with a single round)
+    typename FP::X* c;
+    typename FP::X* cr;
+    int n;
+};
+template <class FP> __global__ void k_gp_coeffs_multi(const GpCoeffItem<FP>* __restrict__ items, int ascending) {
+    if (threadIdx.x != 0) return;
+    const GpCoeffItem<FP> it = items[blockIdx.x];
+    typename FP::X p = FP::x_one(), g = *it.gamma;
+    for (int i = 0; i < it.n; i++) {
+        const int k = ascending ? i : it.n - 1 - i;
+        it.c[k] = p;
+        if (it.r0) it.cr[k] = FP::x_mul(p, *it.r0);
+        p = FP::x_mul(p, g);
+    }
+}
+
+// ---- tail: one CTA per layer, tables in shared memory, all remaining rounds + the final evaluations
+template <class FP> struct GpTailItem {
+    const void* in;                 // from_base: base tables [nvec][2n]; else extension tables [2*nvec][n] (already scaled)
+    const typename FP::X* c;
+    const typename FP::X* chal;     // chal[k] = challenge folded in the k-th tail round; chal[rounds] = last challenge (final fold)
+    typename FP::X* msg0;           // from_base: 4 slots for round 0
+    typename FP::X* msg;            // 3 slots per tail round
+    typename FP::X* evals;          // 2*nvec final evaluations (l_i for i > 0 scaled by c_i)
+    int from_base, n, nvec, rounds;
+};
+
+template <class FP, int NP>
+__device__ __forceinline__ void tail_block_sum(typename FP::X (&acc)[NP], typename FP::X* red /*[32][NP]*/, typename FP::X* out) {
+    typedef typename FP::X X;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        X v = acc[p];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v = FP::x_add(v, FP::x_shfl_down(v, off));
+        if (lane == 0) red[warp * NP + p] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            X v = lane < nwarps ? red[lane * NP + p] : FP::x_zero();
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v = FP::x_add(v, FP::x_shfl_down(v, off));
+            if (lane == 0) out[p] = v;
+        }
+    }
+    __syncthreads();
+}
+
+template <class FP> __global__ void __launch_bounds__(HG_TAIL_THREADS) k_gp_tail(const GpTailItem<FP>* __restrict__ items) {
+    typedef typename FP::B B;
+    typedef typename FP::X X;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const GpTailItem<FP> it = items[blockIdx.x];
+    const int ntab = 2 * it.nvec;
+    X* A = reinterpret_cast<X*>(smem_raw);                 // [ntab][HG_GP_TAIL]
+    X* Bf = A + (size_t)ntab * HG_GP_TAIL;                 // [ntab][HG_GP_TAIL/2]
+    X* red = Bf + (size_t)ntab * (HG_GP_TAIL / 2);         // [32][4]
+    int len = it.n;
+    if (it.from_base) {
+        const B* base = (const B*)it.in;  // vector i = [l_i (n) | r_i (n)] -> tables 2i, 2i+1 are consecutive runs of n
+        for (int e = threadIdx.x; e < ntab * len; e += blockDim.x) A[e] = FP::lift(base[e]);
+        __syncthreads();
+        // round 0 on the unscaled tables: h(0), h(inf), h(-1), h(1)
+        X acc[4] = {FP::x_zero(), FP::x_zero(), FP::x_zero(), FP::x_zero()};
+        const int npairs = len / 2;
+        for (int e = threadIdx.x; e < it.nvec * npairs; e += blockDim.x) {
+            const int i = e / npairs, b = e % npairs;
+            const X t_lo = A[2 * b], t_hi = A[2 * b + 1];
+            const X l_lo = A[(2 * i) * len + 2 * b], l_hi = A[(2 * i) * len + 2 * b + 1];
+            const X r_lo = A[(2 * i + 1) * len + 2 * b], r_hi = A[(2 * i + 1) * len + 2 * b + 1];
+            const X ci = it.c[i];
+            acc[0] = FP::x_add(acc[0], FP::fmul(FP::fmul(ci, t_lo), FP::fmul(l_lo, r_lo)));
+            acc[1] = FP::x_add(acc[1], FP::fmul(FP::fmul(ci, FP::slope(t_lo, t_hi)), FP::fmul(FP::slope(l_lo, l_hi), FP::slope(r_lo, r_hi))));
+            acc[2] = FP::x_add(acc[2], FP::fmul(FP::fmul(ci, FP::at_m1(t_lo, t_hi)), FP::fmul(FP::at_m1(l_lo, l_hi), FP::at_m1(r_lo, r_hi))));
+            acc[3] = FP::x_add(acc[3], FP::fmul(FP::fmul(ci, t_hi), FP::fmul(l_hi, r_hi)));
+        }
+        tail_block_sum<FP, 4>(acc, red, it.msg0);
+        // pre-scale l_i by c_i (i > 0), as round 1 of the streaming kernels does
+        for (int e = threadIdx.x; e < (it.nvec - 1) * len; e += blockDim.x) {
+            const int i = 1 + e / len, k = e % len;
+            A[(2 * i) * len + k] = FP::fmul(A[(2 * i) * len + k], it.c[i]);
+        }
+        __syncthreads();
+    } else {
+        const X* src = (const X*)it.in;
+        for (int e = threadIdx.x; e < ntab * len; e += blockDim.x) A[e] = src[e];
+        __syncthreads();
+    }
+    X* cur = A;
+    X* nxt = Bf;
+    const X c0 = it.c[0];
+    for (int rd = 0; rd < it.rounds; rd++) {
+        const X r = it.chal[rd];
+        const typename FP::FoldAux aux = FP::fold_aux(r);
+        const int npairs = len / 4, half = len / 2;
+        X acc[3] = {FP::x_zero(), FP::x_zero(), FP::x_zero()};
+        for (int e = threadIdx.x; e < it.nvec * npairs; e += blockDim.x) {
+            const int i = e / npairs, b = e % npairs;
+            const X* t = cur + 4 * b;
+            const X* l = cur + (2 * i) * len + 4 * b;
+            const X* q = cur + (2 * i + 1) * len + 4 * b;
+            const X t_lo = FP::fold(t[0], t[1], r, aux), t_hi = FP::fold(t[2], t[3], r, aux);
+            const X l_lo = FP::fold(l[0], l[1], r, aux), l_hi = FP::fold(l[2], l[3], r, aux);
+            const X r_lo = FP::fold(q[0], q[1], r, aux), r_hi = FP::fold(q[2], q[3], r, aux);
+            nxt[(2 * i) * half + 2 * b] = l_lo;
+            nxt[(2 * i) * half + 2 * b + 1] = l_hi;
+            nxt[(2 * i + 1) * half + 2 * b] = r_lo;
+            nxt[(2 * i + 1) * half + 2 * b + 1] = r_hi;
+            X p0 = FP::fmul(l_lo, r_lo), p1 = FP::fmul(FP::slope(l_lo, l_hi), FP::slope(r_lo, r_hi)),
+              p2 = FP::fmul(FP::at_m1(l_lo, l_hi), FP::at_m1(r_lo, r_hi));
+            if (i == 0) { p0 = FP::fmul(p0, c0); p1 = FP::fmul(p1, c0); p2 = FP::fmul(p2, c0); }
+            acc[0] = FP::x_add(acc[0], FP::fmul(t_lo, p0));
+            acc[1] = FP::x_add(acc[1], FP::fmul(FP::slope(t_lo, t_hi), p1));
+            acc[2] = FP::x_add(acc[2], FP::fmul(FP::at_m1(t_lo, t_hi), p2));
+        }
+        tail_block_sum<FP, 3>(acc, red, it.msg + 3 * rd);  // ends with __syncthreads: nxt is complete
+        X* tmp = cur; cur = nxt; nxt = tmp;
+        len = half;
+    }
+    // len == 2: final evaluations
+    const X r = it.chal[it.rounds];
+    const typename FP::FoldAux aux = FP::fold_aux(r);
+    for (int t = threadIdx.x; t < ntab; t += blockDim.x) it.evals[t] = FP::fold(cur[2 * t], cur[2 * t + 1], r, aux);
+}
+
+}  // namespace hg

@@ -355,19 +355,46 @@ void sumcheck_dev(DeviceCtx* ctx, int kclass, Channel<FP>& ch, const WireOptions
     if (evals_off) *evals_off = eo;
 }
 
+// one layer sumcheck recorded for batched execution (prefetch mode): everything the device needs is static
+template <class FP> struct GpLayerJob {
+    const typename FP::B* tables;  // [nvec][2n]
+    size_t n;
+    int nvec, nv;
+    size_t gamma_idx, r0_idx, msg_off, evals_off;
+};
+
 // Grand-product layer sumcheck with the specialised kernels of gp_kernels.cuh. tables: [nvec][2n] base elements.
 // d_gamma: the layer's batching challenge (device); d_coeffs: scratch for [c_i | c_i * r_0] (2*nvec).
 // *scaled = whether the final evaluations of l_i (i > 0) carry the factor c_i (true iff a round >= 1 ran).
 template <class FP>
 void gp_sumcheck_dev(DeviceCtx* ctx, Channel<FP>& ch, const WireOptions& wo, const typename FP::B* d_tables, size_t n, int nvec,
                      const typename FP::X* d_gamma, typename FP::X* d_coeffs, typename FP::X* bufA, typename FP::X* bufB, const ScScratch& sc,
-                     std::shared_ptr<ScHostState<FP>> st, size_t* first_chal, size_t* evals_off, bool* scaled) {
+                     std::shared_ptr<ScHostState<FP>> st, size_t* first_chal, size_t* evals_off, bool* scaled,
+                     std::vector<GpLayerJob<FP>>* batch = nullptr, size_t gamma_idx = 0) {
     typedef typename FP::B B;
     typedef typename FP::X X;
     constexpr int D = 3;
     const int ntab = 2 * nvec;
     int nv = 0;
     while (((size_t)1 << nv) < n) nv++;
+    if (batch) {
+        // prefetch mode: only the protocol bookkeeping happens here; LassoNodeDev::run_gp_batch launches the work
+        GpLayerJob<FP> job;
+        job.tables = d_tables; job.n = n; job.nvec = nvec; job.nv = nv; job.gamma_idx = gamma_idx;
+        for (int j = 0; j < nv; j++) {
+            size_t off = ch.alloc_msg(j == 0 ? D + 1 : D);
+            if (j == 0) job.msg_off = off;
+            const size_t next_idx = ch.next_index();
+            emit_round<FP, D>(ch, st, off, wo, j == 0, next_idx);
+            size_t idx = ch.squeeze(1);
+            if (j == 0) { job.r0_idx = idx; if (first_chal) *first_chal = idx; }
+        }
+        job.evals_off = ch.alloc_msg(ntab);
+        if (evals_off) *evals_off = job.evals_off;
+        if (scaled) *scaled = true;  // the batched kernels always pre-scale l_i (i > 0)
+        batch->push_back(job);
+        return;
+    }
     X* part = (X*)sc.partials;
     X* d_c = d_coeffs;
     X* d_cr = d_coeffs + nvec;
@@ -511,13 +538,22 @@ template <class FP> class LassoNodeDev {
         d_eq_.alloc(std::max(R_, M_));
         d_coeff_coll_.alloc(m_);
         d_wpow_.alloc(HG_MAX_C);
-        d_gp_coeffs_.alloc(4 * (size_t)m_ + 4);
+        d_gp_coeffs_.alloc(4 * (size_t)m_ * (num_vars_ + log2M_ + 2) + 4);  // [c | c*r_0] per layer of both grand products
         // product trees: sum_k 2m * (N >> k) < 2m * 2N
         d_tree1_.alloc(2 * (size_t)m_ * 2 * R_);
         d_tree2_.alloc(2 * (size_t)m_ * 2 * M_);
         size_t nmax = std::max(R_, M_) / 2;  // longest sumcheck table
         d_bufA_.alloc(std::max<size_t>(4 * (size_t)m_ * (nmax / 2), 4 * (size_t)m_));
         d_bufB_.alloc(std::max<size_t>(4 * (size_t)m_ * (nmax / 4), 4 * (size_t)m_));
+        // prefetch mode runs all layers concurrently: every layer needs its own fold buffers, sum < 3/4 * 4m * (R + M) elements
+        d_pool_.alloc(3 * (size_t)m_ * (R_ + M_) + 64);
+        d_gp_partials_.alloc((size_t)ctx->sm_count * 64 * 4 + 4096);
+        d_gp_counters_.alloc(128);
+        HG_CUDA(cudaMemset(d_gp_counters_.p, 0, d_gp_counters_.bytes()));
+        h_desc_.alloc(1 << 16);
+        d_desc_.alloc(1 << 16);
+        HG_CUDA(cudaFuncSetAttribute(k_gp_tail<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)((size_t)2 * (2 * m_) * (HG_GP_TAIL + HG_GP_TAIL / 2) * sizeof(X) + 32 * 4 * sizeof(X))));
         max_blocks_ = ctx->sm_count * 8;
         size_t batch = std::max<size_t>((size_t)m_, pp.C);
         d_partials_.alloc((size_t)max_blocks_ * 4 * batch);
@@ -548,7 +584,7 @@ template <class FP> class LassoNodeDev {
 
     size_t device_bytes() const {
         return d_dims_.bytes() + d_E_.bytes() + d_coll_.bytes() + d_out_.bytes() + d_read_cts_.bytes() + d_final_cts_.bytes() + d_blk_hist_.bytes() +
-               d_blk_base_.bytes() + d_eq_.bytes() + d_tree1_.bytes() + d_tree2_.bytes() + d_bufA_.bytes() + d_bufB_.bytes() + d_subtables_.bytes();
+               d_blk_base_.bytes() + d_eq_.bytes() + d_tree1_.bytes() + d_tree2_.bytes() + d_bufA_.bytes() + d_bufB_.bytes() + d_pool_.bytes() + d_subtables_.bytes();
     }
     size_t num_rows() const { return n_rows_; }
     int num_vars() const { return num_vars_; }
@@ -623,8 +659,11 @@ template <class FP> class LassoNodeDev {
              k_hash_if<FP><<<dim3((unsigned)((M + HG_BLOCK - 1) / HG_BLOCK), m), HG_BLOCK, 0, s>>>(d_subtables_.p, d_final_cts_.p, d_pos_sub_.p, d_pos_slot_.p,
                                                                                                    ch.d_chal(gt_idx), M, m, d_tree2_.p));
         size_t x_idx = 0, y_idx = 0;
-        grand_product(ch, wo, d_tree1_.p, R, &x_idx);
-        grand_product(ch, wo, d_tree2_.p, M, &y_idx);
+        std::vector<GpLayerJob<FP>> jobs;
+        std::vector<GpLayerJob<FP>>* batch = (mode == kModePrefetch) ? &jobs : nullptr;
+        grand_product(ch, wo, d_tree1_.p, R, &x_idx, batch);
+        grand_product(ch, wo, d_tree2_.p, M, &y_idx, batch);
+        if (batch) run_gp_batch(ch, wo, jobs);
         // ---- openings (prover.rs:173-178, mod.rs:80-93)
         const size_t o_dims = ch.alloc_msg(pp_.C), o_rts = ch.alloc_msg(nslots_), o_fcs = ch.alloc_msg(nslots_), o_e = ch.alloc_msg(m);
         build_eq(ch, x_idx, v);
@@ -689,7 +728,7 @@ template <class FP> class LassoNodeDev {
     }
 
     // prove_grand_product (prover.rs:183-266) over nvec = 2m vectors of length N stored at tree (layer 0), upper layers appended
-    void grand_product(Channel<FP>& ch, const WireOptions& wo, B* tree, size_t N, size_t* point_idx) {
+    void grand_product(Channel<FP>& ch, const WireOptions& wo, B* tree, size_t N, size_t* point_idx, std::vector<GpLayerJob<FP>>* batch) {
         cudaStream_t s = ctx_->stream;
         const int nvec = 2 * m_;
         int nvars = 0;
@@ -737,7 +776,7 @@ template <class FP> class LassoNodeDev {
             size_t sc_first = 0, ev_off = 0;
             bool scaled = false;
             const B* tables = layer[nvars - 1 - nv];
-            gp_sumcheck_dev<FP>(ctx_, ch, wo, tables, (size_t)1 << nv, nvec, ch.d_chal(gamma_idx), d_gp_coeffs_.p, d_bufA_.p, d_bufB_.p, sc_, st, &sc_first, &ev_off, &scaled);
+            gp_sumcheck_dev<FP>(ctx_, ch, wo, tables, (size_t)1 << nv, nvec, ch.d_chal(gamma_idx), d_gp_coeffs_.p, d_bufA_.p, d_bufB_.p, sc_, st, &sc_first, &ev_off, &scaled, batch, gamma_idx);
             ch.emit([chp, gp, ev_off, nvec, scaled, gamma_idx, asc]() {
                 auto& t = chp->transcript();
                 // the device keeps l_i (i > 0) pre-multiplied by c_i (gp_kernels.cuh); undo it exactly with c_i^{-1}
@@ -759,6 +798,135 @@ template <class FP> class LassoNodeDev {
         *point_idx = first_chal;
     }
 
+    // all layer sumchecks of both grand products, batched: round j of every layer in one launch, then one tail launch
+    void run_gp_batch(Channel<FP>& ch, const WireOptions& wo, const std::vector<GpLayerJob<FP>>& jobs) {
+        cudaStream_t s = ctx_->stream;
+        const int nl = (int)jobs.size();
+        if (!nl) return;
+        // carve per-layer regions out of the pools
+        std::vector<X*> bufA(nl, nullptr), bufB(nl, nullptr), coef(nl, nullptr);
+        size_t pool_off = 0, coef_off = 0;
+        for (int k = 0; k < nl; k++) {
+            const auto& j = jobs[k];
+            coef[k] = d_gp_coeffs_.p + coef_off;
+            coef_off += 2 * (size_t)j.nvec;
+            if (j.n > (size_t)HG_GP_TAIL) {
+                size_t a = 2 * (size_t)j.nvec * (j.n / 2), b = 2 * (size_t)j.nvec * (j.n / 4);
+                bufA[k] = d_pool_.p + pool_off; pool_off += a;
+                bufB[k] = d_pool_.p + pool_off; pool_off += b;
+            }
+        }
+        if (pool_off > d_pool_.n || coef_off > d_gp_coeffs_.n) throw std::runtime_error("run_gp_batch: pool too small");
+        // host staging of every descriptor table, one upload
+        std::vector<GpCoeffItem<FP>> citems(nl);
+        for (int k = 0; k < nl; k++) {
+            const auto& j = jobs[k];
+            citems[k].gamma = ch.d_chal(j.gamma_idx);
+            citems[k].r0 = j.nv >= 2 ? ch.d_chal(j.r0_idx) : nullptr;
+            citems[k].c = coef[k]; citems[k].cr = coef[k] + j.nvec; citems[k].n = j.nvec;
+        }
+        int maxJ = -1;
+        for (auto& j : jobs) if (j.n > (size_t)HG_GP_TAIL) maxJ = std::max(maxJ, j.nv - HG_GP_TAIL_LOG);
+        std::vector<std::vector<GpItem<FP>>> rounds(maxJ + 1);
+        std::vector<size_t> round_bytes(maxJ + 1, 0);
+        size_t part_need = 0;
+        const int target_blocks = ctx_->sm_count * 4;
+        for (int r = 0; r <= maxJ; r++) {
+            int blk = 0;
+            size_t part_off = 0;
+            for (int k = 0; k < nl; k++) {
+                const auto& j = jobs[k];
+                if (j.n <= (size_t)HG_GP_TAIL || r > j.nv - HG_GP_TAIL_LOG) continue;
+                GpItem<FP> it;
+                const int ntab = 2 * j.nvec;
+                it.nvec = j.nvec;
+                it.c = coef[k]; it.cr = coef[k] + j.nvec;
+                size_t threads_x;
+                if (r == 0) {
+                    it.in = j.tables; it.out = nullptr; it.n_in = j.n; it.r_prev = nullptr;
+                    it.msg = ch.d_msg(j.msg_off);
+                    threads_x = (j.n / 2 + 1) / 2;  // U = 2
+                    round_bytes[r] += (size_t)ntab * j.n * sizeof(B);
+                } else {
+                    it.n_in = j.n >> (r - 1);
+                    it.in = (r == 1) ? (const void*)j.tables : (const void*)(((r - 1) & 1) ? bufA[k] : bufB[k]);
+                    it.out = (r & 1) ? bufA[k] : bufB[k];
+                    it.r_prev = ch.d_chal(j.r0_idx + r - 1);
+                    it.msg = ch.d_msg(j.msg_off + 4 + 3 * (size_t)(r - 1));
+                    threads_x = it.n_in / 4;
+                    round_bytes[r] += (size_t)ntab * it.n_in * (r == 1 ? sizeof(B) : sizeof(X)) + (size_t)ntab * (it.n_in / 2) * sizeof(X);
+                }
+                size_t b = (threads_x + HG_BLOCK - 1) / HG_BLOCK;
+                if (b < 1) b = 1;
+                if (b > (size_t)max_blocks_) b = max_blocks_;
+                int g = (int)std::min<size_t>((size_t)j.nvec, std::max<size_t>(1, ((size_t)target_blocks + b - 1) / b));
+                it.tpg = (j.nvec + g - 1) / g;
+                it.groups = (j.nvec + it.tpg - 1) / it.tpg;
+                it.bx = (int)b;
+                it.nblk = it.bx * it.groups;
+                it.blk_start = blk;
+                blk += it.nblk;
+                it.partials = d_gp_partials_.p + part_off;
+                part_off += (size_t)it.nblk * 4;
+                it.counter = d_gp_counters_.p + rounds[r].size();
+                rounds[r].push_back(it);
+            }
+            part_need = std::max(part_need, part_off);
+            if (rounds[r].size() > d_gp_counters_.n) throw std::runtime_error("run_gp_batch: too many layers");
+        }
+        if (part_need > d_gp_partials_.n) { d_gp_partials_.alloc(part_need * 2); /* re-point */
+            for (auto& rv : rounds) { size_t off = 0; for (auto& it : rv) { it.partials = d_gp_partials_.p + off; off += (size_t)it.nblk * 4; } } }
+        std::vector<GpTailItem<FP>> titems(nl);
+        size_t tail_bytes = 0;
+        for (int k = 0; k < nl; k++) {
+            const auto& j = jobs[k];
+            GpTailItem<FP>& t = titems[k];
+            t.c = coef[k]; t.nvec = j.nvec; t.evals = ch.d_msg(j.evals_off);
+            if (j.n <= (size_t)HG_GP_TAIL) {
+                t.from_base = 1; t.in = j.tables; t.n = (int)j.n; t.rounds = j.nv - 1;
+                t.chal = ch.d_chal(j.r0_idx); t.msg0 = ch.d_msg(j.msg_off); t.msg = ch.d_msg(j.msg_off + 4);
+                tail_bytes += 2 * (size_t)j.nvec * j.n * sizeof(B);
+            } else {
+                const int J = j.nv - HG_GP_TAIL_LOG;
+                t.from_base = 0; t.in = (J & 1) ? bufA[k] : bufB[k]; t.n = HG_GP_TAIL; t.rounds = HG_GP_TAIL_LOG - 1;
+                t.chal = ch.d_chal(j.r0_idx + J); t.msg0 = nullptr; t.msg = ch.d_msg(j.msg_off + 4 + 3 * (size_t)J);
+                tail_bytes += 2 * (size_t)j.nvec * HG_GP_TAIL * sizeof(X);
+            }
+        }
+        // upload descriptors
+        size_t bytes = citems.size() * sizeof(GpCoeffItem<FP>) + titems.size() * sizeof(GpTailItem<FP>);
+        for (auto& rv : rounds) bytes += rv.size() * sizeof(GpItem<FP>);
+        if (h_desc_.n < bytes) { h_desc_.alloc(bytes * 2); d_desc_.alloc(bytes * 2); }
+        unsigned char* hp = h_desc_.p;
+        size_t off = 0;
+        auto put = [&](const void* src, size_t n) { size_t o = off; memcpy(hp + off, src, n); off += (n + 15) & ~(size_t)15; return o; };
+        size_t c_off = put(citems.data(), citems.size() * sizeof(GpCoeffItem<FP>));
+        std::vector<size_t> r_off(rounds.size());
+        for (size_t r = 0; r < rounds.size(); r++) r_off[r] = put(rounds[r].data(), rounds[r].size() * sizeof(GpItem<FP>));
+        size_t t_off = put(titems.data(), titems.size() * sizeof(GpTailItem<FP>));
+        if (off > h_desc_.n) throw std::runtime_error("run_gp_batch: descriptor staging overflow");
+        HG_CUDA(cudaMemcpyAsync(d_desc_.p, h_desc_.p, off, cudaMemcpyHostToDevice, s));
+        // launches
+        HG_K(ctx_, KC_MISC, 0, k_gp_coeffs_multi<FP><<<nl, 32, 0, s>>>((const GpCoeffItem<FP>*)(d_desc_.p + c_off), wo.a5_ascending));
+        for (size_t r = 0; r < rounds.size(); r++) {
+            if (rounds[r].empty()) continue;
+            const auto& last = rounds[r].back();
+            const int grid = last.blk_start + last.nblk, ni = (int)rounds[r].size();
+            const GpItem<FP>* di = (const GpItem<FP>*)(d_desc_.p + r_off[r]);
+            KernelScope ks(ctx_, KC_SC_GP, round_bytes[r]);
+            if (r == 0) k_gp_r0_multi<FP, 2><<<grid, HG_BLOCK, 0, s>>>(di, ni);
+            else if (r == 1) k_gp_fold_multi<FP, B, true><<<grid, HG_BLOCK, 0, s>>>(di, ni);
+            else k_gp_fold_multi<FP, X, false><<<grid, HG_BLOCK, 0, s>>>(di, ni);
+            HG_LAUNCH_CHECK();
+        }
+        {
+            const size_t smem = (size_t)2 * (2 * m_) * (HG_GP_TAIL + HG_GP_TAIL / 2) * sizeof(X) + 32 * 4 * sizeof(X);
+            KernelScope ks(ctx_, KC_SC_GP, tail_bytes);
+            k_gp_tail<FP><<<nl, HG_TAIL_THREADS, smem, s>>>((const GpTailItem<FP>*)(d_desc_.p + t_off));
+            HG_LAUNCH_CHECK();
+        }
+    }
+
     DeviceCtx* ctx_;
     LassoPreprocessing pp_;
     int num_vars_, log2M_ = 16, m_ = 0, nslots_ = 0, rows_per_block_ = 4096, nblk_cnt_ = 1, max_blocks_ = 0;
@@ -776,7 +944,10 @@ template <class FP> class LassoNodeDev {
     DevBuf<u32> d_read_cts_, d_final_cts_, d_blk_base_;
     DevBuf<int> d_pos_mem_, d_pos_dim_, d_pos_slot_, d_pos_sub_;
     DevBuf<X> d_eq_, d_gp_coeffs_, d_bufA_, d_bufB_, d_partials_;
-    DevBuf<unsigned> d_counters_;
+    DevBuf<unsigned> d_counters_, d_gp_counters_;
+    DevBuf<X> d_pool_, d_gp_partials_;
+    DevBuf<unsigned char> d_desc_;
+    PinnedBuf<unsigned char> h_desc_;
     ScScratch sc_;
     std::unique_ptr<Channel<FP>> ch_;
 };
