@@ -175,6 +175,7 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         tr = step_resident()
     proof_len = len(tr.into_proof())
+    host_phases = node.timing()
     l0 = ctx.launch_count
     step_resident()
     launches_per_step = ctx.launch_count - l0
@@ -264,7 +265,7 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(inp.nbytes + node_chal_bytes(nv)),
                         "d2h_bytes_per_step": int(proof_len + 64 * nv)},
                 "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
-                "wall_ms_per_step": wall_ms / args.steps, "proof_bytes": proof_len, "roofline": roofline, "cpu_baseline": cpu}
+                "wall_ms_per_step": wall_ms / args.steps, "proof_bytes": proof_len, "host_phases_us": host_phases, "roofline": roofline, "cpu_baseline": cpu}
     barrier()
     node.free()
     d_inp.free()

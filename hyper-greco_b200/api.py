@@ -29,7 +29,7 @@ SYMBOLS = [
     "hg_lasso_preprocess", "hg_lasso_pp_free", "hg_lasso_pp_num_lookups", "hg_lasso_pp_num_subtables", "hg_lasso_pp_num_memories",
     "hg_lasso_pp_lookup_index", "hg_lasso_pp_memory_maps", "hg_lasso_pp_subtable_id", "hg_lasso_node_new", "hg_lasso_node_free",
     "hg_lasso_node_log2_input_size", "hg_lasso_node_device_bytes", "hg_lasso_node_prove", "hg_lasso_node_download_polys",
-    "hg_lasso_node_num_chunks", "hg_sumcheck_prove", "hg_mle_eval_batch", "hg_field_selftest",
+    "hg_lasso_node_num_chunks", "hg_lasso_node_timing", "hg_sumcheck_prove", "hg_mle_eval_batch", "hg_field_selftest",
 ]
 
 _lib = None
@@ -93,6 +93,8 @@ def lib():
         for f in ("hg_lasso_node_log2_input_size", "hg_lasso_node_device_bytes", "hg_lasso_node_num_chunks"):
             getattr(L, f).argtypes = [vp]
             getattr(L, f).restype = sz
+        L.hg_lasso_node_timing.argtypes = [vp, vp]
+        L.hg_lasso_node_timing.restype = None
         L.hg_lasso_node_prove.argtypes = [vp, vp, sz, i32, vp, i32, vp, vp]
         L.hg_lasso_node_download_polys.argtypes = [vp, vp, vp, vp, vp]
         L.hg_sumcheck_prove.argtypes = [vp, i32, sz, sz, vp, vp, vp, vp, i32, vp, vp]
@@ -344,6 +346,12 @@ class LassoNode:
             n = arr.size // LIMBS[self.ctx.field]
             _chk(lib().hg_lasso_node_prove(self.h, _p(arr), n, 0, transcript.h, mode, _p(pt), _p(val)))
         return pt, val
+
+    def timing(self):
+        """Host phases of the last prove in microseconds: squeeze+upload challenges, enqueue, wait for GPU, serialise."""
+        out = np.zeros(4, np.float64)
+        lib().hg_lasso_node_timing(self.h, _p(out))
+        return dict(zip(("challenges_us", "enqueue_us", "gpu_wait_us", "serialise_us"), (float(x) for x in out)))
 
     def download_polys(self):
         R, M, m, nc = 1 << self.num_vars, self.pp.M, self.pp.num_memories, self.num_chunks

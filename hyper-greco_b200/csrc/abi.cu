@@ -249,6 +249,7 @@ void hg_lasso_node_free(hg_lasso_node* node) {
 size_t hg_lasso_node_log2_input_size(const hg_lasso_node* node) { return node->log2_input_size; }
 size_t hg_lasso_node_device_bytes(const hg_lasso_node* node) { return node->gl->device_bytes(); }
 size_t hg_lasso_node_num_chunks(const hg_lasso_node* node) { return node->gl->chunk_dims().size(); }
+void hg_lasso_node_timing(const hg_lasso_node* node, double* out_us4) { for (int i = 0; i < 4; i++) out_us4[i] = node->gl->timing()[i]; }
 
 int hg_lasso_node_prove(hg_lasso_node* node, const void* inputs, size_t n_inputs, int inputs_on_device, hg_transcript* t, int mode,
                         uint64_t* out_point, uint64_t* out_value) {
@@ -329,15 +330,17 @@ int hg_mle_eval_batch(hg_ctx* ctx, const void* d_tables, size_t n_tables, size_t
         for (size_t i = 0; i < num_vars; i++) hp[i] = FP::x_from_limbs(point_ext + 2 * i);
         pt.alloc(std::max<size_t>(num_vars, 1));
         HG_CUDA(cudaMemcpy(pt.p, hp.data(), num_vars * sizeof(gl2), cudaMemcpyHostToDevice));
-        eq.alloc(n);
+        const int lo = num_vars < 12 ? (int)num_vars : 12;
+        const size_t nlo = (size_t)1 << lo, nhi = n >> lo;
+        eq.alloc(nlo + nhi);
         out.alloc(n_tables);
-        int blocks = (int)std::min<size_t>((n + HG_BLOCK - 1) / HG_BLOCK, (size_t)ctx->dev.sm_count * 2);
+        int blocks = (int)std::min<size_t>(nhi, (size_t)ctx->dev.sm_count * 2);
         partials.alloc((size_t)blocks * n_tables);
         counters.alloc(n_tables);
         HG_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), s));
-        HG_K(&ctx->dev, KC_EQ, n * sizeof(gl2), k_eq_build<FP><<<(unsigned)((n + HG_BLOCK - 1) / HG_BLOCK), HG_BLOCK, 0, s>>>(pt.p, (int)num_vars, eq.p));
-        HG_K(&ctx->dev, KC_DOT, n_tables * n * 8 + n * sizeof(gl2),
-             k_dot_eq<FP, u64><<<dim3(blocks, (unsigned)n_tables), HG_BLOCK, 0, s>>>((const u64*)d_tables, stride, n, eq.p, partials.p, counters.p, out.p));
+        HG_K(&ctx->dev, KC_EQ, (nlo + nhi) * sizeof(gl2), k_eq_split<FP><<<(unsigned)((nlo + nhi + HG_BLOCK - 1) / HG_BLOCK), HG_BLOCK, 0, s>>>(pt.p, (int)num_vars, lo, eq.p, eq.p + nlo));
+        HG_K(&ctx->dev, KC_DOT, n_tables * n * 8,
+             k_dot_eq<FP, u64><<<dim3(blocks, (unsigned)n_tables), HG_BLOCK, 0, s>>>((const u64*)d_tables, stride, n, lo, eq.p, eq.p + nlo, partials.p, counters.p, out.p));
         std::vector<gl2> ho(n_tables);
         HG_CUDA(cudaMemcpyAsync(ho.data(), out.p, n_tables * sizeof(gl2), cudaMemcpyDeviceToHost, s));
         HG_CUDA(cudaStreamSynchronize(s));

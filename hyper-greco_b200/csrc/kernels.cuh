@@ -160,19 +160,25 @@ __global__ void k_cnt_rank(const u16* __restrict__ addr, const u8* __restrict__ 
                            int rows_per_block, const u32* __restrict__ blk_base, int log2M, u32* __restrict__ read_cts);
 
 // ---------------------------------------------------------------------------------------------------------
-// eq(point, k) table, k_0 = LSB (plonkish MultilinearPolynomial::eq_xy, lasso.rs:432)
+// eq(point, k) = prod_i (k_i ? r_i : 1 - r_i), k_0 = LSB (plonkish MultilinearPolynomial::eq_xy, lasso.rs:432), kept as
+// two small factor tables: eq(point, k) = eq_lo[k mod 2^lo_bits] * eq_hi[k >> lo_bits]
 template <class FP>
-__global__ void k_eq_build(const typename FP::X* __restrict__ point, int nv, typename FP::X* __restrict__ eq) {
+__global__ void k_eq_split(const typename FP::X* __restrict__ point, int nv, int lo_bits, typename FP::X* __restrict__ eq_lo,
+                           typename FP::X* __restrict__ eq_hi) {
     typedef typename FP::X X;
-    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= ((size_t)1 << nv)) return;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nlo = (size_t)1 << lo_bits, nhi = (size_t)1 << (nv - lo_bits);
+    if (t >= nlo + nhi) return;
+    const bool hi = t >= nlo;
+    const size_t k = hi ? t - nlo : t;
+    const int first = hi ? lo_bits : 0, last = hi ? nv : lo_bits;
     X acc = FP::x_one();
-    for (int i = 0; i < nv; i++) {
+    for (int i = first; i < last; i++) {
         X r = point[i];
-        X f = ((k >> i) & 1) ? r : FP::x_sub(FP::x_one(), r);
+        X f = ((k >> (i - first)) & 1) ? r : FP::x_sub(FP::x_one(), r);
         acc = FP::x_mul(acc, f);
     }
-    eq[k] = acc;
+    (hi ? eq_hi : eq_lo)[k] = acc;
 }
 
 template <class FP, class T> struct ToBase;
@@ -180,16 +186,22 @@ template <class FP> struct ToBase<FP, u16> { __device__ __forceinline__ static t
 template <class FP> struct ToBase<FP, u32> { __device__ __forceinline__ static typename FP::B f(u32 v) { return FP::b_from_u64(v); } };
 template <class FP> struct ToBase<FP, u64> { __device__ __forceinline__ static typename FP::B f(u64 v) { return v; } };
 
-// Batched MLE evaluation as dot products with a shared eq table (mod.rs:80-93, lasso.rs:422-454):
-// out[y] = sum_k eq[k] * tables[y][k];  grid = (blocks, ntables)
+// Batched MLE evaluation (mod.rs:80-93, lasso.rs:422-454): out[y] = sum_k eq(point, k) * tables[y][k], one streaming pass
+// per table. Row kh of 2^lo_bits elements is reduced against eq_lo with unreduced accumulation, then scaled by eq_hi[kh].
+// grid = (blocks, ntables)
 template <class FP, class T>
-__global__ void k_dot_eq(const T* __restrict__ tables, size_t stride, size_t n, const typename FP::X* __restrict__ eq,
-                         typename FP::X* partials, unsigned* counter, typename FP::X* out) {
+__global__ void k_dot_eq(const T* __restrict__ tables, size_t stride, size_t n, int lo_bits, const typename FP::X* __restrict__ eq_lo,
+                         const typename FP::X* __restrict__ eq_hi, typename FP::X* partials, unsigned* counter, typename FP::X* out) {
     typedef typename FP::X X;
     const T* t = tables + (size_t)blockIdx.y * stride;
+    const size_t nlo = (size_t)1 << lo_bits, nhi = n >> lo_bits;
     X acc[1] = {FP::x_zero()};
-    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
-        acc[0] = FP::x_add(acc[0], FP::x_mul_b(eq[k], ToBase<FP, T>::f(t[k])));
+    for (size_t kh = blockIdx.x; kh < nhi; kh += gridDim.x) {
+        typename FP::XAcc a = FP::xacc_zero_();
+        const T* row = t + kh * nlo;
+        for (size_t kl = threadIdx.x; kl < nlo; kl += blockDim.x) FP::xacc_mad_b(a, eq_lo[kl], ToBase<FP, T>::f(row[kl]));
+        acc[0] = FP::x_add(acc[0], FP::fmul(FP::xacc_reduce_(a), eq_hi[kh]));
+    }
     block_reduce_finalize<FP, 1>(acc, partials, counter, out);
 }
 

@@ -12,6 +12,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <functional>
 #include <memory>
 #include <string>
@@ -166,14 +167,19 @@ template <class FP> class Channel {
     }
     void emit(std::function<void()> fn) { deferred_.push_back(std::move(fn)); }
     // bring finished messages to the host and serialise everything emitted so far, in order
-    void flush() {
+    void flush(double* wait_us = nullptr, double* emit_us = nullptr) {
+        auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double t0 = now();
         if (msg_cursor_ > msg_ready_) {
             HG_CUDA(cudaMemcpyAsync(h_msg_.p + msg_ready_, d_msg_.p + msg_ready_, (msg_cursor_ - msg_ready_) * sizeof(X),
                                     cudaMemcpyDeviceToHost, ctx_->stream));
             msg_ready_ = msg_cursor_;
         }
         HG_CUDA(cudaStreamSynchronize(ctx_->stream));
+        const double t1 = now();
         for (; deferred_done_ < deferred_.size(); deferred_done_++) deferred_[deferred_done_]();
+        if (wait_us) *wait_us = t1 - t0;
+        if (emit_us) *emit_us = now() - t1;
     }
     const X* d_chal(size_t i) const { return d_chal_.p + i; }
     X* d_msg(size_t i) { return d_msg_.p + i; }
@@ -199,6 +205,10 @@ template <class FP> class Channel {
 template <class FP> struct RoundPoly {
     typedef typename FP::X X;
     static X small(u64 v) { return FP::lift(FP::b_from_u64(v)); }
+    static X inv_small(int v) {  // 1/2, 1/3, 1/6 are needed every round: invert once
+        static const X i2 = FP::x_inv(small(2)), i3 = FP::x_inv(small(3)), i6 = FP::x_mul(i2, i3);
+        return v == 2 ? i2 : v == 3 ? i3 : i6;
+    }
     // coefficients of the degree-d polynomial through (0,y0)..(d,yd), d in {1,2,3}, by forward differences
     static std::vector<X> interpolate(const std::vector<X>& y) {
         const int d = (int)y.size() - 1;
@@ -206,7 +216,7 @@ template <class FP> struct RoundPoly {
         X d1 = FP::x_sub(y[1], y[0]);
         if (d == 1) return {y[0], d1};
         X d2 = FP::x_add(FP::x_sub(y[2], FP::x_add(y[1], y[1])), y[0]);
-        X inv2 = FP::x_inv(small(2));
+        X inv2 = inv_small(2);
         if (d == 2) {
             X c2 = FP::x_mul(d2, inv2);
             return {y[0], FP::x_sub(d1, c2), c2};
@@ -214,7 +224,7 @@ template <class FP> struct RoundPoly {
         // d3 = y3 - 3y2 + 3y1 - y0
         X three = small(3);
         X d3 = FP::x_sub(FP::x_add(FP::x_sub(y[3], FP::x_mul(three, y[2])), FP::x_mul(three, y[1])), y[0]);
-        X inv3 = FP::x_inv(three), inv6 = FP::x_mul(inv2, inv3);
+        X inv3 = inv_small(3), inv6 = inv_small(6);
         X c3 = FP::x_mul(d3, inv6);
         X h2 = FP::x_mul(d2, inv2), h3 = FP::x_mul(d3, inv2);
         X c2 = FP::x_sub(h2, h3);
@@ -272,7 +282,7 @@ void emit_round(Channel<FP>& ch, std::shared_ptr<ScHostState<FP>> st, size_t off
             tc[1] = a;
         } else {
             X bv = FP::x_add(FP::x_sub(chp->msg(off + 2), h0), hinf);  // c2 - c1
-            X inv2 = FP::x_inv(RP::small(2));
+            X inv2 = RP::inv_small(2);
             tc[2] = FP::x_mul(FP::x_add(a, bv), inv2);
             tc[1] = FP::x_mul(FP::x_sub(a, bv), inv2);
         }
@@ -579,7 +589,7 @@ template <class FP> class LassoNodeDev {
             HG_CUDA(cudaMemcpy(d_wpow_.p, wp.data(), wp.size() * sizeof(B), cudaMemcpyHostToDevice));
         }
         HG_CUDA(cudaFuncSetAttribute(k_cnt_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(M_ * 2)));
-        HG_CUDA(cudaFuncSetAttribute(k_cnt_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(M_ * 2)));
+        HG_CUDA(cudaFuncSetAttribute(k_cnt_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(M_ * 2 + (size_t)rows_per_block_ * 6)));
     }
 
     size_t device_bytes() const {
@@ -596,6 +606,8 @@ template <class FP> class LassoNodeDev {
                X* out_value) {
         Channel<FP>& ch = *ch_;
         cudaStream_t s = ctx_->stream;
+        auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double t_start = now();
         const size_t R = R_, M = M_;
         const int m = m_, v = num_vars_;
         const size_t rows = std::min(n_inputs, n_rows_);  // izip! stops at the shorter (Q9)
@@ -604,7 +616,7 @@ template <class FP> class LassoNodeDev {
             while (np2 < n_inputs) np2 <<= 1;
             if (np2 != R_) throw std::runtime_error("assertion `left == right` failed: num_vars of the input does not match the node (lasso.rs:80)");
         }
-        ch.begin(&tr, mode, total_chal_);
+        double t_begin = t_start;
 
         // collation coefficients (A5)
         {
@@ -624,10 +636,13 @@ template <class FP> class LassoNodeDev {
             const u16* addr = d_dims_.p + (size_t)slot_addr_dim_[sl] * R;
             HG_K(ctx_, KC_COUNTERS, rows * 3, k_cnt_hist<<<nblk_cnt_, 1024, M * 2, s>>>(addr, d_row_lookup_.p, slot_used_[sl], rows, rows_per_block_, d_blk_hist_.p, log2M_));
             HG_K(ctx_, KC_COUNTERS, M * 4, k_cnt_scan<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(d_blk_hist_.p, nblk_cnt_, log2M_, d_blk_base_.p, d_final_cts_.p + (size_t)sl * M));
-            HG_K(ctx_, KC_COUNTERS, rows * 7, k_cnt_rank<<<nblk_cnt_, 32, M * 2, s>>>(addr, d_row_lookup_.p, slot_used_[sl], rows, R, rows_per_block_, d_blk_base_.p, log2M_,
+            HG_K(ctx_, KC_COUNTERS, rows * 7, k_cnt_rank<<<nblk_cnt_, 128, M * 2 + (size_t)rows_per_block_ * 6, s>>>(addr, d_row_lookup_.p, slot_used_[sl], rows, R, rows_per_block_, d_blk_base_.p, log2M_,
                                                                                   d_read_cts_.p + (size_t)sl * R));
         }
 
+        // the kernels above need no challenges: squeezing (Keccak on the host) overlaps them
+        ch.begin(&tr, mode, total_chal_);
+        t_begin = now();
         // ---- r, claimed sum (lasso.rs:85, :264, :269)
         const size_t r_idx = ch.squeeze(v);
         const size_t sum_off = ch.alloc_msg(1);
@@ -685,7 +700,10 @@ template <class FP> class LassoNodeDev {
                 }
             });
         }
-        ch.flush();
+        const double t_enq = now();
+        ch.flush(&timing_[2], &timing_[3]);
+        timing_[0] = t_begin - t_start;
+        timing_[1] = t_enq - t_begin;
         if (ch.chal_used() != total_chal_) throw std::runtime_error("LassoNode: challenge count mismatch");
         if (out_point) { out_point->resize(v); for (int i = 0; i < v; i++) (*out_point)[i] = ch.chal(r_idx + i); }
         if (out_value) *out_value = ch.msg(sum_off);
@@ -701,6 +719,8 @@ template <class FP> class LassoNodeDev {
         if (E) dl(E, d_E_);
     }
     const std::vector<int>& chunk_dims() const { return chunk_dims_; }
+    // host-side phases of the last prove in microseconds: squeeze+upload challenges, enqueue kernels, wait for the GPU, serialise
+    const double* timing() const { return timing_; }
 
   private:
     static size_t gp_chal_count(size_t nvars) {  // layers nv = 0..nvars-1: mu each; gamma + nv round challenges for nv >= 1
@@ -713,14 +733,20 @@ template <class FP> class LassoNodeDev {
         for (size_t nv = 0; nv < nvars; nv++) c += 4 * (size_t)m_ + 4 * nv;
         return c;
     }
+    static int eq_lo_bits(int nv) { return nv < 12 ? nv : 12; }
     void build_eq(Channel<FP>& ch, size_t point_idx, int nv) {
-        size_t n = (size_t)1 << nv;
-        HG_K(ctx_, KC_EQ, n * sizeof(X), k_eq_build<FP><<<(unsigned)((n + HG_BLOCK - 1) / HG_BLOCK), HG_BLOCK, 0, ctx_->stream>>>(ch.d_chal(point_idx), nv, d_eq_.p));
+        const int lo = eq_lo_bits(nv);
+        eq_nv_ = nv;
+        size_t n = ((size_t)1 << lo) + ((size_t)1 << (nv - lo));
+        HG_K(ctx_, KC_EQ, n * sizeof(X), k_eq_split<FP><<<(unsigned)((n + HG_BLOCK - 1) / HG_BLOCK), HG_BLOCK, 0, ctx_->stream>>>(ch.d_chal(point_idx), nv, lo, d_eq_.p, d_eq_.p + ((size_t)1 << lo)));
     }
     template <class T> void dot_tables(Channel<FP>& ch, const T* tables, size_t stride, int ntab, size_t n, size_t msg_off) {
-        int blocks = (int)std::min<size_t>((n + HG_BLOCK - 1) / HG_BLOCK, (size_t)ctx_->sm_count * 2);
-        HG_K(ctx_, KC_DOT, (size_t)ntab * n * sizeof(T) + n * sizeof(X),
-             k_dot_eq<FP, T><<<dim3(blocks, ntab), HG_BLOCK, 0, ctx_->stream>>>(tables, stride, n, d_eq_.p, d_partials_.p, d_counters_.p, ch.d_msg(msg_off)));
+        const int lo = eq_lo_bits(eq_nv_);
+        if (n != (size_t)1 << eq_nv_) throw std::runtime_error("dot_tables: eq tables were built for another size");
+        int blocks = (int)std::min<size_t>(n >> lo, (size_t)ctx_->sm_count * 2);
+        if (blocks < 1) blocks = 1;
+        HG_K(ctx_, KC_DOT, (size_t)ntab * n * sizeof(T),
+             k_dot_eq<FP, T><<<dim3(blocks, ntab), HG_BLOCK, 0, ctx_->stream>>>(tables, stride, n, lo, d_eq_.p, d_eq_.p + ((size_t)1 << lo), d_partials_.p, d_counters_.p, ch.d_msg(msg_off)));
     }
     template <class T> void eval_tables(Channel<FP>& ch, const T* tables, size_t stride, int ntab, size_t n, size_t point_idx, int nv, size_t msg_off) {
         build_eq(ch, point_idx, nv);
@@ -927,6 +953,8 @@ template <class FP> class LassoNodeDev {
         }
     }
 
+    double timing_[4] = {0, 0, 0, 0};
+    int eq_nv_ = 0;
     DeviceCtx* ctx_;
     LassoPreprocessing pp_;
     int num_vars_, log2M_ = 16, m_ = 0, nslots_ = 0, rows_per_block_ = 4096, nblk_cnt_ = 1, max_blocks_ = 0;

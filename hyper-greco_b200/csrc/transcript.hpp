@@ -22,8 +22,11 @@ class Keccak256 {
     Keccak256() { reset(); }
     void reset() { memset(a_, 0, sizeof a_); fill_ = 0; }
     void update(const uint8_t* p, size_t n) {
-        while (n--) {
-            reinterpret_cast<uint8_t*>(a_)[fill_++] ^= *p++;
+        uint8_t* s = reinterpret_cast<uint8_t*>(a_);
+        while (n) {
+            size_t take = kRate - fill_ < n ? kRate - fill_ : n;
+            for (size_t i = 0; i < take; i++) s[fill_ + i] ^= p[i];
+            fill_ += take; p += take; n -= take;
             if (fill_ == kRate) { permute(); fill_ = 0; }
         }
     }
@@ -41,39 +44,52 @@ class Keccak256 {
     static constexpr size_t kRate = 136;
     uint64_t a_[25];
     size_t fill_;
-    static uint64_t rol(uint64_t v, unsigned s) { return (v << s) | (v >> ((64 - s) & 63)); }
-    void permute() {
-        uint64_t rc = 1;  // round constants from the degree-8 LFSR x^8+x^6+x^5+x^4+1
-        uint8_t lfsr = 1;
-        for (int round = 0; round < 24; round++) {
-            uint64_t c[5];
-            for (int x = 0; x < 5; x++) c[x] = a_[x] ^ a_[x + 5] ^ a_[x + 10] ^ a_[x + 15] ^ a_[x + 20];
-            for (int x = 0; x < 5; x++) {
-                uint64_t d = c[(x + 4) % 5] ^ rol(c[(x + 1) % 5], 1);
-                for (int y = 0; y < 25; y += 5) a_[y + x] ^= d;
+    static inline uint64_t rol(uint64_t v, unsigned s) { return (v << s) | (v >> (64 - s)); }
+    // round constants from the degree-8 LFSR x^8+x^6+x^5+x^4+1, rho offsets from the (x,y) -> (y, 2x+3y) orbit; computed once
+    struct Tables {
+        uint64_t rc[24];
+        unsigned rot[24];
+        int lane[24];
+        Tables() {
+            uint8_t lfsr = 1;
+            for (int round = 0; round < 24; round++) {
+                uint64_t c = 0;
+                for (int j = 0; j < 7; j++) {
+                    if (lfsr & 1) c ^= 1ULL << ((1 << j) - 1);
+                    lfsr = (lfsr & 0x80) ? (uint8_t)((lfsr << 1) ^ 0x71) : (uint8_t)(lfsr << 1);
+                }
+                rc[round] = c;
             }
-            // rho + pi, walking the (x,y) -> (y, 2x+3y) orbit
             int x = 1, y = 0;
-            uint64_t cur = a_[1];
             for (int t = 0; t < 24; t++) {
-                unsigned r = ((t + 1) * (t + 2) / 2) % 64;
+                rot[t] = ((t + 1) * (t + 2) / 2) % 64;
                 int ny = (2 * x + 3 * y) % 5;
                 x = y; y = ny;
-                uint64_t nxt = a_[x + 5 * y];
-                a_[x + 5 * y] = r ? rol(cur, r) : cur;
+                lane[t] = x + 5 * y;
+            }
+        }
+    };
+    static const Tables& tables() { static const Tables t; return t; }
+    void permute() {
+        const Tables& T = tables();
+        uint64_t* a = a_;
+        for (int round = 0; round < 24; round++) {
+            uint64_t c0 = a[0] ^ a[5] ^ a[10] ^ a[15] ^ a[20], c1 = a[1] ^ a[6] ^ a[11] ^ a[16] ^ a[21],
+                     c2 = a[2] ^ a[7] ^ a[12] ^ a[17] ^ a[22], c3 = a[3] ^ a[8] ^ a[13] ^ a[18] ^ a[23],
+                     c4 = a[4] ^ a[9] ^ a[14] ^ a[19] ^ a[24];
+            uint64_t d0 = c4 ^ rol(c1, 1), d1 = c0 ^ rol(c2, 1), d2 = c1 ^ rol(c3, 1), d3 = c2 ^ rol(c4, 1), d4 = c3 ^ rol(c0, 1);
+            for (int y = 0; y < 25; y += 5) { a[y] ^= d0; a[y + 1] ^= d1; a[y + 2] ^= d2; a[y + 3] ^= d3; a[y + 4] ^= d4; }
+            uint64_t cur = a[1];
+            for (int t = 0; t < 24; t++) {
+                uint64_t nxt = a[T.lane[t]];
+                a[T.lane[t]] = rol(cur, T.rot[t]);
                 cur = nxt;
             }
-            for (int yy = 0; yy < 25; yy += 5) {
-                uint64_t row[5];
-                for (int xx = 0; xx < 5; xx++) row[xx] = a_[yy + xx];
-                for (int xx = 0; xx < 5; xx++) a_[yy + xx] = row[xx] ^ (~row[(xx + 1) % 5] & row[(xx + 2) % 5]);
+            for (int y = 0; y < 25; y += 5) {
+                uint64_t r0 = a[y], r1 = a[y + 1], r2 = a[y + 2], r3 = a[y + 3], r4 = a[y + 4];
+                a[y] = r0 ^ (~r1 & r2); a[y + 1] = r1 ^ (~r2 & r3); a[y + 2] = r2 ^ (~r3 & r4); a[y + 3] = r3 ^ (~r4 & r0); a[y + 4] = r4 ^ (~r0 & r1);
             }
-            rc = 0;
-            for (int j = 0; j < 7; j++) {
-                if (lfsr & 1) rc ^= 1ULL << ((1 << j) - 1);
-                lfsr = (lfsr & 0x80) ? (uint8_t)((lfsr << 1) ^ 0x71) : (uint8_t)(lfsr << 1);
-            }
-            a_[0] ^= rc;
+            a[0] ^= T.rc[round];
         }
     }
 };

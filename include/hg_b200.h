@@ -111,6 +111,8 @@ int hg_lasso_node_prove(hg_lasso_node* node, const void* inputs, size_t n_inputs
  * final_cts: chunks x M u32, e_polys: num_memories x R base elements. Any pointer may be NULL. */
 int hg_lasso_node_download_polys(hg_lasso_node* node, uint16_t* dims, uint32_t* read_cts, uint32_t* final_cts, uint64_t* e_polys);
 size_t hg_lasso_node_num_chunks(const hg_lasso_node* node);
+/* host-side phases of the last prove, microseconds: [squeeze+upload challenges, enqueue kernels, wait for the GPU, serialise proof] */
+void hg_lasso_node_timing(const hg_lasso_node* node, double* out_us4);
 
 /* ---- generic sumcheck: gkr::sum_check::prove_sum_check with a Generic function of the shape the lasso crate builds
  *      (lasso/src/lasso.rs:457-475, lasso/src/memory_checking/prover.rs:268-279):
