@@ -36,6 +36,8 @@ __device__ __forceinline__ void load4(const gl2* p, gl2 (&v)[4]) {
 }
 __device__ __forceinline__ void load2(const u64* p, u64 (&v)[2]) { ldg128(p, v[0], v[1]); }
 __device__ __forceinline__ void store2(gl2* p, gl2 a, gl2 b) { stg256(p, a.c0, a.c1, b.c0, b.c1); }
+// pull the bytes a later iteration will load into L2 (costs no registers; the loop is otherwise latency-bound, profiles/)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- round 0: base-field tables [nvec][2n] (l_i = first half, r_i = second half of vector i), n = 2^nv
 //      msg: h(0), h(inf), h(-1), h(1)
@@ -185,6 +187,9 @@ namespace hg {
 constexpr int HG_GP_TAIL_LOG = 6;
 constexpr int HG_GP_TAIL = 1 << HG_GP_TAIL_LOG;  // table length at which a layer moves to the shared-memory tail kernel
 constexpr int HG_TAIL_THREADS = 512;
+#ifndef HG_GP_PREFETCH
+#define HG_GP_PREFETCH 2
+#endif
 
 template <class FP> struct GpItem {
     const void* in;                  // tables read this round (base in rounds 0/1, extension later): [2*nvec][n_in]
@@ -296,7 +301,10 @@ __global__ void __launch_bounds__(HG_BLOCK, 2) k_gp_r0_multi(const GpItem<FP>* _
             for (int u = 0; u < U; u++) {
                 const size_t b = b0 + u * stride;
                 l[u][0] = l[u][1] = r[u][0] = r[u][1] = FP::b_zero();
-                if (b < npairs) { load2(li + 2 * b, l[u]); load2(ri + 2 * b, r[u]); }
+                if (b < npairs) {
+                    load2(li + 2 * b, l[u]); load2(ri + 2 * b, r[u]);
+                    if (i + HG_GP_PREFETCH < i1) { prefetch_l2(li + (size_t)HG_GP_PREFETCH * 2 * n + 2 * b); prefetch_l2(ri + (size_t)HG_GP_PREFETCH * 2 * n + 2 * b); }
+                }
             }
             typename FP::BAcc s[NP];
 #pragma unroll
@@ -350,6 +358,10 @@ __global__ void __launch_bounds__(HG_BLOCK, 2) k_gp_fold_multi(const GpItem<FP>*
             TIN a[4], c[4];
             load4(in + (size_t)(2 * i) * n_in + 4 * b, a);
             load4(in + (size_t)(2 * i + 1) * n_in + 4 * b, c);
+            if (i + HG_GP_PREFETCH < i1) {
+                prefetch_l2(in + (size_t)(2 * (i + HG_GP_PREFETCH)) * n_in + 4 * b);
+                prefetch_l2(in + (size_t)(2 * (i + HG_GP_PREFETCH) + 1) * n_in + 4 * b);
+            }
             X l_lo, l_hi;
             if constexpr (SCALE) {
                 if (i > 0) {

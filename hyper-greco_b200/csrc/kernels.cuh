@@ -224,6 +224,35 @@ __global__ void k_hash_rw(const u16* __restrict__ dims, const u32* __restrict__ 
     V[(size_t)pos * R + j] = rd;
     V[(size_t)(m + pos) * R + j] = FP::b_add(rd, gamma2);
 }
+// Same, fused with the first product-tree level (prover.rs:332-354): each thread hashes rows j and j + R/2, so the bottom
+// layer is written once and never re-read to build layer 1.  V = layer 0 ([2m][R]), up = layer 1 ([2m][R/2]).
+template <class FP>
+__global__ void k_hash_rw_up(const u16* __restrict__ dims, const u32* __restrict__ read_cts, const typename FP::B* __restrict__ E,
+                             const int* __restrict__ pos_mem, const int* __restrict__ pos_dim, const int* __restrict__ pos_slot,
+                             const typename FP::X* __restrict__ gamma_tau, size_t R, int m, typename FP::B* __restrict__ V,
+                             typename FP::B* __restrict__ up) {
+    typedef typename FP::B B;
+    const size_t h = R / 2;
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int pos = blockIdx.y;
+    if (j >= h) return;
+    const B gamma = FP::x_base0(gamma_tau[0]), tau = FP::x_base0(gamma_tau[1]), gamma2 = FP::b_mul(gamma, gamma);
+    const u16* dm = dims + (size_t)pos_dim[pos] * R;
+    const u32* ts = read_cts + (size_t)pos_slot[pos] * R;
+    const B* e = E + (size_t)pos_mem[pos] * R;
+    B rd[2], wr[2];
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const size_t q = j + s * h;
+        B a = FP::b_from_u64(dm[q]), t = FP::b_from_u64(ts[q]);
+        rd[s] = FP::b_sub(FP::b_add(FP::b_add(a, FP::b_mul(e[q], gamma)), FP::b_mul(t, gamma2)), tau);
+        wr[s] = FP::b_add(rd[s], gamma2);
+        V[(size_t)pos * R + q] = rd[s];
+        V[(size_t)(m + pos) * R + q] = wr[s];
+    }
+    up[(size_t)pos * h + j] = FP::b_mul(rd[0], rd[1]);
+    up[(size_t)(m + pos) * h + j] = FP::b_mul(wr[0], wr[1]);
+}
 // V2 = [inits (m) | final_reads (m)] x M
 template <class FP>
 __global__ void k_hash_if(const typename FP::B* __restrict__ subtables, const u32* __restrict__ final_cts, const int* __restrict__ pos_sub,

@@ -589,7 +589,6 @@ template <class FP> class LassoNodeDev {
             HG_CUDA(cudaMemcpy(d_wpow_.p, wp.data(), wp.size() * sizeof(B), cudaMemcpyHostToDevice));
         }
         HG_CUDA(cudaFuncSetAttribute(k_cnt_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(M_ * 2)));
-        HG_CUDA(cudaFuncSetAttribute(k_cnt_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(M_ * 2 + (size_t)rows_per_block_ * 6)));
     }
 
     size_t device_bytes() const {
@@ -636,7 +635,7 @@ template <class FP> class LassoNodeDev {
             const u16* addr = d_dims_.p + (size_t)slot_addr_dim_[sl] * R;
             HG_K(ctx_, KC_COUNTERS, rows * 3, k_cnt_hist<<<nblk_cnt_, 1024, M * 2, s>>>(addr, d_row_lookup_.p, slot_used_[sl], rows, rows_per_block_, d_blk_hist_.p, log2M_));
             HG_K(ctx_, KC_COUNTERS, M * 4, k_cnt_scan<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(d_blk_hist_.p, nblk_cnt_, log2M_, d_blk_base_.p, d_final_cts_.p + (size_t)sl * M));
-            HG_K(ctx_, KC_COUNTERS, rows * 7, k_cnt_rank<<<nblk_cnt_, 128, M * 2 + (size_t)rows_per_block_ * 6, s>>>(addr, d_row_lookup_.p, slot_used_[sl], rows, R, rows_per_block_, d_blk_base_.p, log2M_,
+            HG_K(ctx_, KC_COUNTERS, rows * 7, k_cnt_rank<<<nblk_cnt_, 1024, 0, s>>>(addr, d_row_lookup_.p, slot_used_[sl], rows, R, rows_per_block_, d_blk_base_.p, log2M_,
                                                                                   d_read_cts_.p + (size_t)sl * R));
         }
 
@@ -667,17 +666,24 @@ template <class FP> class LassoNodeDev {
         // ---- gamma, tau (lasso.rs:99)
         const size_t gt_idx = ch.squeeze(2);
         // ---- memory checking (lasso.rs:292-339, prover.rs:35-181)
-        HG_K(ctx_, KC_HASH, (size_t)m * R * (2 + 4 + 3 * sizeof(B)),
-             k_hash_rw<FP><<<dim3((unsigned)((R + HG_BLOCK - 1) / HG_BLOCK), m), HG_BLOCK, 0, s>>>(d_dims_.p, d_read_cts_.p, d_E_.p, d_pos_mem_.p, d_pos_dim_.p,
-                                                                                                   d_pos_slot_.p, ch.d_chal(gt_idx), R, m, d_tree1_.p));
+        const bool fused_up = R >= 4;  // hash build fused with the first tree level
+        if (fused_up)
+            HG_K(ctx_, KC_HASH, (size_t)m * R * (2 + 4 + 4 * sizeof(B)),
+                 k_hash_rw_up<FP><<<dim3((unsigned)((R / 2 + HG_BLOCK - 1) / HG_BLOCK), m), HG_BLOCK, 0, s>>>(
+                     d_dims_.p, d_read_cts_.p, d_E_.p, d_pos_mem_.p, d_pos_dim_.p, d_pos_slot_.p, ch.d_chal(gt_idx), R, m, d_tree1_.p,
+                     d_tree1_.p + (size_t)2 * m * R));
+        else
+            HG_K(ctx_, KC_HASH, (size_t)m * R * (2 + 4 + 3 * sizeof(B)),
+                 k_hash_rw<FP><<<dim3((unsigned)((R + HG_BLOCK - 1) / HG_BLOCK), m), HG_BLOCK, 0, s>>>(d_dims_.p, d_read_cts_.p, d_E_.p, d_pos_mem_.p, d_pos_dim_.p,
+                                                                                                       d_pos_slot_.p, ch.d_chal(gt_idx), R, m, d_tree1_.p));
         HG_K(ctx_, KC_HASH, (size_t)m * M * (4 + 3 * sizeof(B)),
              k_hash_if<FP><<<dim3((unsigned)((M + HG_BLOCK - 1) / HG_BLOCK), m), HG_BLOCK, 0, s>>>(d_subtables_.p, d_final_cts_.p, d_pos_sub_.p, d_pos_slot_.p,
                                                                                                    ch.d_chal(gt_idx), M, m, d_tree2_.p));
         size_t x_idx = 0, y_idx = 0;
         std::vector<GpLayerJob<FP>> jobs;
         std::vector<GpLayerJob<FP>>* batch = (mode == kModePrefetch) ? &jobs : nullptr;
-        grand_product(ch, wo, d_tree1_.p, R, &x_idx, batch);
-        grand_product(ch, wo, d_tree2_.p, M, &y_idx, batch);
+        grand_product(ch, wo, d_tree1_.p, R, &x_idx, batch, fused_up);
+        grand_product(ch, wo, d_tree2_.p, M, &y_idx, batch, false);
         if (batch) run_gp_batch(ch, wo, jobs);
         // ---- openings (prover.rs:173-178, mod.rs:80-93)
         const size_t o_dims = ch.alloc_msg(pp_.C), o_rts = ch.alloc_msg(nslots_), o_fcs = ch.alloc_msg(nslots_), o_e = ch.alloc_msg(m);
@@ -754,7 +760,8 @@ template <class FP> class LassoNodeDev {
     }
 
     // prove_grand_product (prover.rs:183-266) over nvec = 2m vectors of length N stored at tree (layer 0), upper layers appended
-    void grand_product(Channel<FP>& ch, const WireOptions& wo, B* tree, size_t N, size_t* point_idx, std::vector<GpLayerJob<FP>>* batch) {
+    void grand_product(Channel<FP>& ch, const WireOptions& wo, B* tree, size_t N, size_t* point_idx, std::vector<GpLayerJob<FP>>* batch,
+                       bool level1_done) {
         cudaStream_t s = ctx_->stream;
         const int nvec = 2 * m_;
         int nvars = 0;
@@ -765,6 +772,7 @@ template <class FP> class LassoNodeDev {
         for (int k = 1; k < nvars; k++) {
             layer[k] = layer[k - 1] + (size_t)nvec * (N >> (k - 1));
             size_t h = N >> k;
+            if (k == 1 && level1_done) continue;
             HG_K(ctx_, KC_TREE, (size_t)nvec * h * 3 * sizeof(B), k_tree_up<FP><<<dim3((unsigned)((h + HG_BLOCK - 1) / HG_BLOCK), nvec), HG_BLOCK, 0, s>>>(layer[k - 1], layer[k], h));
         }
         const size_t roots_off = ch.alloc_msg(nvec), ev0_off = ch.alloc_msg(2 * nvec);
