@@ -107,6 +107,7 @@ def run_reference(args):
     hgo.build()
     P, inp, bounds, segs, nv = make_case(args.config, 0)
     opp, rows = oracle_case(hgo, bounds, segs)
+    hgo.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
     cores = hgo.num_threads()
     t0 = time.perf_counter()
     hgo.lasso_prove(0, opp, nv, rows, inp)
@@ -252,6 +253,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             from oracle import hgo
             hgo.build()
+            hgo.set_num_threads(os.cpu_count() or 1)
             opp, rows = oracle_case(hgo, bounds, segs)
             t0 = time.perf_counter()
             oproof, *_ = hgo.lasso_prove(0, opp, nv, rows, inp)

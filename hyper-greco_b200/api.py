@@ -29,7 +29,7 @@ SYMBOLS = [
     "hg_lasso_preprocess", "hg_lasso_pp_free", "hg_lasso_pp_num_lookups", "hg_lasso_pp_num_subtables", "hg_lasso_pp_num_memories",
     "hg_lasso_pp_lookup_index", "hg_lasso_pp_memory_maps", "hg_lasso_pp_subtable_id", "hg_lasso_node_new", "hg_lasso_node_free",
     "hg_lasso_node_log2_input_size", "hg_lasso_node_device_bytes", "hg_lasso_node_prove", "hg_lasso_node_download_polys",
-    "hg_lasso_node_num_chunks", "hg_lasso_node_timing", "hg_sumcheck_prove", "hg_mle_eval_batch", "hg_field_selftest",
+    "hg_lasso_node_num_chunks", "hg_lasso_node_timing", "hg_sumcheck_prove", "hg_mle_eval_batch", "hg_ntt", "hg_bfv_evaluate", "hg_field_selftest",
 ]
 
 _lib = None
@@ -100,6 +100,8 @@ def lib():
         L.hg_sumcheck_prove.argtypes = [vp, i32, sz, sz, vp, vp, vp, vp, i32, vp, vp]
         L.hg_mle_eval_batch.argtypes = [vp, vp, sz, sz, sz, vp, vp]
         L.hg_field_selftest.argtypes = [vp, i32, vp, vp, sz, vp]
+        L.hg_ntt.argtypes = [vp, vp, sz, i32, sz]
+        L.hg_bfv_evaluate.argtypes = [vp, sz, sz, vp, vp, vp, vp, u64, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -401,3 +403,40 @@ def field_selftest(ctx: Context, op, a_ext, b_ext):
     out = np.zeros_like(a)
     _chk(lib().hg_field_selftest(ctx.h, op, _p(a), _p(b), a.size // el, _p(out)))
     return out
+
+
+def ntt(ctx: Context, d_data: DeviceBuffer, log_n, inverse=False, batch=1):
+    """FftNode::forward / ::inverse evaluation, in place on the device (sk_encryption_circuit.rs:224,249,251)."""
+    _chk(lib().hg_ntt(ctx.h, d_data.ptr, log_n, 1 if inverse else 0, batch))
+
+
+class BfvEncrypt:
+    """Driver-level mirror of `BfvEncrypt` (sk_encryption_circuit.rs:300-523) for the part that runs on the device:
+    forward evaluation of the circuit and the Lasso node."""
+
+    def __init__(self, ctx: Context, params):
+        from . import witness
+        self.ctx, self.P = ctx, params
+        self.pp = LassoPreprocessing.preprocess(witness.lasso_lookup_bounds(params))  # setup(), :319-349
+        self.num_vars = witness.lasso_num_vars(params)
+        self.node = LassoNode(ctx, self.pp, self.num_vars, witness.lasso_lookup_segments(params))  # configure(), :205-209
+        self.n_lasso = sum(l for _, l in witness.lasso_lookup_segments(params))
+
+    def upload_inputs(self, ins):
+        """get_inputs() vectors (python ints or uint64 arrays) -> device buffers."""
+        u = lambda v: DeviceBuffer.from_numpy(self.ctx, np.asarray(v, dtype=np.uint64).reshape(-1))
+        return dict(s=u(ins["s"]), e=u(ins["e"]), k1=u(ins["k1"]), ais=u(np.concatenate([np.asarray(a, dtype=np.uint64) for a in ins["ais"]])),
+                    r1is=u(np.concatenate([np.asarray(a, dtype=np.uint64) for a in ins["r1is"]])), r2is=u(ins["r2is"]))
+
+    def evaluate(self, dev_ins):
+        """circuit.evaluate (:442): returns (lasso inputs DeviceBuffer, sum DeviceBuffer)."""
+        P = self.P
+        N2 = 1 << P.log2_size
+        lasso = DeviceBuffer(self.ctx, self.n_lasso * 8)
+        summ = DeviceBuffer(self.ctx, P.K * N2 * 8)
+        a = lambda v: np.array([int(x) for x in v], np.uint64)
+        q, k0, r1b, r2b = a(P.QIS), a(P.K0IS), a(P.R1_BOUNDS), a(P.R2_BOUNDS)
+        _chk(lib().hg_bfv_evaluate(self.ctx.h, P.log2_size, P.K, _p(q), _p(k0), _p(r1b), _p(r2b), P.S_BOUND, P.E_BOUND, P.K1_BOUND,
+                                   dev_ins["s"].ptr, dev_ins["e"].ptr, dev_ins["k1"].ptr, dev_ins["ais"].ptr, dev_ins["r1is"].ptr, dev_ins["r2is"].ptr,
+                                   lasso.ptr, summ.ptr))
+        return lasso, summ

@@ -7,6 +7,9 @@
 #include <string>
 #include <vector>
 
+#include <map>
+
+#include "bfv.cuh"
 #include "prover.cuh"
 
 using namespace hg;
@@ -34,7 +37,39 @@ struct hg_ctx {
     DeviceCtx dev;
     int field_id;
     WireOptions wire;
+    std::map<int, std::unique_ptr<DevBuf<u64>>> twiddles;  // key = log_n * 2 + inverse
+    DevBuf<u64> ntt_scratch;
 };
+
+namespace {
+// batched in-place NTT of `batch` transforms of 2^log_n base elements at d_data (device)
+void ntt_run(hg_ctx* ctx, u64* d_data, int log_n, bool inverse, size_t batch) {
+    typedef GlField FP;
+    if (log_n < 1 || log_n > 24) throw std::runtime_error("hg_ntt: log_n out of range (1..24)");
+    cudaStream_t s = ctx->dev.stream;
+    const size_t N = (size_t)1 << log_n;
+    const int key = log_n * 2 + (inverse ? 1 : 0);
+    auto& tw = ctx->twiddles[key];
+    if (!tw) {
+        tw.reset(new DevBuf<u64>());
+        tw->alloc(N);
+        HG_K(&ctx->dev, KC_MISC, N * 8, k_ntt_twiddles<FP><<<(unsigned)((N + 255) / 256), 256, 0, s>>>(log_n, inverse ? 1 : 0, FP::root_of_unity_2_32(), tw->p));
+    }
+    if (ctx->ntt_scratch.n < N * batch) ctx->ntt_scratch.alloc(N * batch);
+    const int log_n1 = (log_n + 1) / 2, log_n2 = log_n - log_n1;
+    const int n1 = 1 << log_n1, n2 = 1 << log_n2;
+    const int tile_c = std::min(HG_NTT_TILE, n2), tile_r = std::min(HG_NTT_TILE, n1);
+    const size_t smem_c = (size_t)n1 * (tile_c | 1) * sizeof(u64), smem_r = (size_t)n2 * (tile_r | 1) * sizeof(u64);
+    if (smem_c > 200 * 1024 || smem_r > 200 * 1024) throw std::runtime_error("hg_ntt: transform too large for the shared-memory tiles");
+    HG_CUDA(cudaFuncSetAttribute(k_ntt_cols<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+    HG_CUDA(cudaFuncSetAttribute(k_ntt_rows<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+    HG_K(&ctx->dev, KC_MISC, 2 * N * batch * 8,
+         k_ntt_cols<FP><<<dim3(n2 / tile_c, (unsigned)batch), HG_NTT_THREADS, smem_c, s>>>(d_data, ctx->ntt_scratch.p, log_n1, log_n2, tile_c, tw->p));
+    const u64 scale = inverse ? gl_inv(gl_from_u64(N)) : 1;
+    HG_K(&ctx->dev, KC_MISC, 2 * N * batch * 8,
+         k_ntt_rows<FP><<<dim3(n1 / tile_r, (unsigned)batch), HG_NTT_THREADS, smem_r, s>>>(ctx->ntt_scratch.p, d_data, log_n1, log_n2, tile_r, tw->p, scale, inverse ? 1 : 0));
+}
+}  // namespace
 struct hg_buf {
     void* p = nullptr;
     size_t bytes = 0;
@@ -345,6 +380,50 @@ int hg_mle_eval_batch(hg_ctx* ctx, const void* d_tables, size_t n_tables, size_t
         HG_CUDA(cudaMemcpyAsync(ho.data(), out.p, n_tables * sizeof(gl2), cudaMemcpyDeviceToHost, s));
         HG_CUDA(cudaStreamSynchronize(s));
         for (size_t i = 0; i < n_tables; i++) FP::x_to_limbs(ho[i], out_ext + 2 * i);
+    })
+}
+
+int hg_ntt(hg_ctx* ctx, void* d_data, size_t log_n, int inverse, size_t batch) {
+    HG_TRY({
+        HG_CUDA(cudaSetDevice(ctx->dev.device));
+        ntt_run(ctx, (u64*)d_data, (int)log_n, inverse != 0, batch);
+    })
+}
+
+int hg_bfv_evaluate(hg_ctx* ctx, size_t log2_size, size_t K, const uint64_t* qis, const uint64_t* k0is, const uint64_t* r1_bounds,
+                    const uint64_t* r2_bounds, uint64_t s_bound, uint64_t e_bound, uint64_t k1_bound, const void* d_s, const void* d_e,
+                    const void* d_k1, const void* d_ais, const void* d_r1is, const void* d_r2is, void* d_lasso_inputs, void* d_sum) {
+    HG_TRY({
+        typedef GlField FP;
+        HG_CUDA(cudaSetDevice(ctx->dev.device));
+        cudaStream_t s = ctx->dev.stream;
+        const size_t N2 = (size_t)1 << log2_size, r2_len = K * (N2 / 2);
+        BfvShape sh;
+        sh.log2_size = (int)log2_size; sh.K = (int)K; sh.n_chunks = (int)std::max<size_t>(1, (r2_len + N2 - 1) / N2);
+        // per-modulus constants as field elements (F::from_str_vartime(QIS/K0IS), sk_encryption_circuit.rs:109,135)
+        std::vector<u64> consts(3 * K);
+        for (size_t i = 0; i < K; i++) { consts[i] = gl_from_u64(qis[i]); consts[K + i] = gl_from_u64(k0is[i]); consts[2 * K + i] = gl_from_u64(r1_bounds[i]); }
+        DevBuf<u64> d_consts, d_sai, d_seval;
+        d_consts.alloc(3 * K);
+        HG_CUDA(cudaMemcpyAsync(d_consts.p, consts.data(), consts.size() * 8, cudaMemcpyHostToDevice, s));
+        const size_t total = (K + sh.n_chunks + 3) * N2;
+        HG_K(&ctx->dev, KC_MISC, total * 16,
+             k_bfv_lasso_inputs<FP><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(sh, (const u64*)d_s, (const u64*)d_e, (const u64*)d_k1, (const u64*)d_r1is,
+                                                                                  (const u64*)d_r2is, r2_len, d_consts.p + 2 * K, gl_from_u64(r2_bounds[0]),
+                                                                                  gl_from_u64(s_bound), gl_from_u64(e_bound), gl_from_u64(k1_bound), (u64*)d_lasso_inputs));
+        // s_eval = FFT(s); ai_eval = FFT(ai); sai = IFFT(s_eval . ai_eval)   (sk_encryption_circuit.rs:224-260)
+        d_seval.alloc(N2);
+        d_sai.alloc(K * N2);
+        HG_CUDA(cudaMemcpyAsync(d_seval.p, d_s, N2 * 8, cudaMemcpyDeviceToDevice, s));
+        HG_CUDA(cudaMemcpyAsync(d_sai.p, d_ais, K * N2 * 8, cudaMemcpyDeviceToDevice, s));
+        ntt_run(ctx, d_seval.p, (int)log2_size, false, 1);
+        ntt_run(ctx, d_sai.p, (int)log2_size, false, K);
+        HG_K(&ctx->dev, KC_MISC, 3 * K * N2 * 8, k_pointwise_mul_bcast<FP><<<dim3((unsigned)((N2 + 255) / 256), (unsigned)K), 256, 0, s>>>(d_sai.p, d_seval.p, N2));
+        ntt_run(ctx, d_sai.p, (int)log2_size, true, K);
+        HG_K(&ctx->dev, KC_MISC, 4 * K * N2 * 8,
+             k_bfv_sum<FP><<<dim3((unsigned)((N2 + 255) / 256), (unsigned)K), 256, 0, s>>>(sh, d_sai.p, (const u64*)d_e, (const u64*)d_k1, (const u64*)d_r1is,
+                                                                                         (const u64*)d_r2is, d_consts.p, d_consts.p + K, (u64*)d_sum));
+        HG_CUDA(cudaStreamSynchronize(s));  // temporaries are freed on return
     })
 }
 

@@ -20,6 +20,9 @@ struct GlField {
     HG_HD static B b_add(B a, B b) { return gl_add(a, b); }
     HG_HD static B b_sub(B a, B b) { return gl_sub(a, b); }
     HG_HD static B b_mul(B a, B b) { return gl_mul(a, b); }
+    HG_HD static B b_inv(B a) { return gl_inv(a); }
+    HG_HD static B root_of_unity_2_32() { return 0x185629dcda58878cULL; }  // 7^((p-1)/2^32), goldilocks ROOT_OF_UNITY (A9)
+    static constexpr int TWO_ADICITY = 32;
     HG_HD static X x_zero() { return gl2_zero(); }
     HG_HD static X x_one() { return gl2_one(); }
     HG_HD static X lift(B a) { return gl2_lift(a); }

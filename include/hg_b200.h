@@ -127,6 +127,21 @@ int hg_sumcheck_prove(hg_ctx* ctx, int arity, size_t n_terms, size_t num_vars, c
 int hg_mle_eval_batch(hg_ctx* ctx, const void* d_tables, size_t n_tables, size_t stride, size_t num_vars, const uint64_t* point_ext,
                       uint64_t* out_ext);
 
+/* ---- FFT layers: FftNode::forward / ::inverse evaluation (call sites bfv-gkr/src/sk_encryption_circuit.rs:224,249,251; the
+ *      transform lives in the un-vendored gkr crate: radix-2 over ROOT_OF_UNITY^(2^(S-log_n)), natural order, inverse scaled
+ *      by 1/n). In place on `batch` consecutive transforms of 2^log_n base elements at the DEVICE pointer d_data. */
+int hg_ntt(hg_ctx* ctx, void* d_data, size_t log_n, int inverse, size_t batch);
+
+/* ---- forward evaluation of the BFV SK-encryption circuit (circuit.evaluate, sk_encryption_circuit.rs:442, topology :86-293)
+ *      on the get_inputs() vectors (:365-415), all DEVICE pointers of base elements:
+ *        d_s, d_e, d_k1: 2^log2_size; d_ais, d_r1is: K x 2^log2_size; d_r2is: K x 2^(log2_size-1)
+ *      outputs: d_lasso_inputs = `lasso_inputs_batched` layer ((K + chunks + 3) x 2^log2_size, the Lasso node's input),
+ *               d_sum = `sum` layer (K x 2^log2_size, equals ct0is for a valid witness).
+ *      qis/k0is/bounds are the BfvSkEncryptConstans of the parameter set (constants/mod.rs:16-35), host arrays of K. */
+int hg_bfv_evaluate(hg_ctx* ctx, size_t log2_size, size_t K, const uint64_t* qis, const uint64_t* k0is, const uint64_t* r1_bounds,
+                    const uint64_t* r2_bounds, uint64_t s_bound, uint64_t e_bound, uint64_t k1_bound, const void* d_s, const void* d_e,
+                    const void* d_k1, const void* d_ais, const void* d_r1is, const void* d_r2is, void* d_lasso_inputs, void* d_sum);
+
 /* field self-test kernel: out[i] = a[i] (op) b[i] on extension elements, op 0 add 1 sub 2 mul (device arithmetic check) */
 int hg_field_selftest(hg_ctx* ctx, int op, const uint64_t* a_ext, const uint64_t* b_ext, size_t n, uint64_t* out_ext);
 

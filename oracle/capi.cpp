@@ -119,6 +119,32 @@ template <class F> int subtable_t(int full, uint64_t bound, int log2M, const uin
     }
     return 0;
 }
+template <class F> int ntt_t(uint64_t* data, int log_n, int inverse, size_t batch) {
+    size_t n = (size_t)1 << log_n;
+    for (size_t b = 0; b < batch; b++) {
+        std::vector<F> a = load_base<F>(data + b * n * F::LIMBS, n);
+        ntt_naive_order(a, inverse != 0);
+        for (size_t i = 0; i < n; i++) a[i].to_limbs(data + (b * n + i) * F::LIMBS);
+    }
+    return 0;
+}
+template <class F>
+int bfv_eval_t(int log2_size, int K, const uint64_t* qis, const uint64_t* k0is, const uint64_t* r1b, const uint64_t* r2b, uint64_t sb, uint64_t eb,
+               uint64_t k1b, const uint64_t* s, const uint64_t* e, const uint64_t* k1, const uint64_t* ais, const uint64_t* r1is, const uint64_t* r2is,
+               uint64_t* lasso_out, size_t* n_lasso, uint64_t* sum_out) {
+    BfvParams<F> P; P.log2_size = log2_size; P.K = K; P.s_bound = sb; P.e_bound = eb; P.k1_bound = k1b;
+    P.qis = load_base<F>(qis, K); P.k0is = load_base<F>(k0is, K);
+    P.r1_bounds.assign(r1b, r1b + K); P.r2_bounds.assign(r2b, r2b + K);
+    size_t N2 = (size_t)1 << log2_size;
+    std::vector<std::vector<F>> A(K), R1(K);
+    for (int i = 0; i < K; i++) { A[i] = load_base<F>(ais + i * N2 * F::LIMBS, N2); R1[i] = load_base<F>(r1is + i * N2 * F::LIMBS, N2); }
+    std::vector<F> li, sum;
+    bfv_evaluate<F>(P, load_base<F>(s, N2), load_base<F>(e, N2), load_base<F>(k1, N2), A, R1, load_base<F>(r2is, (size_t)K * N2 / 2), &li, &sum);
+    *n_lasso = li.size();
+    for (size_t i = 0; i < li.size(); i++) li[i].to_limbs(lasso_out + i * F::LIMBS);
+    for (size_t i = 0; i < sum.size(); i++) sum[i].to_limbs(sum_out + i * F::LIMBS);
+    return 0;
+}
 template <class F> int field_op_t(int op, const uint64_t* a, const uint64_t* b, uint64_t* out) {
     typedef typename ExtOf<F>::type E;
     E x = load_ext<F, E>(a), y = load_ext<F, E>(b), z;
@@ -200,6 +226,16 @@ int hgo_sumcheck_prove(int field, int arity, size_t nterms, int num_vars, const 
 }
 int hgo_mle_eval(int field, const uint64_t* table, int num_vars, const uint64_t* point, uint64_t* out) {
     GUARD(return field == 0 ? mle_eval_t<Gl>(table, num_vars, point, out) : mle_eval_t<Fr>(table, num_vars, point, out);)
+}
+int hgo_ntt(int field, uint64_t* data, int log_n, int inverse, size_t batch) {
+    GUARD(return field == 0 ? ntt_t<Gl>(data, log_n, inverse, batch) : ntt_t<Fr>(data, log_n, inverse, batch);)
+}
+// forward evaluation of the BFV circuit: lasso_inputs_batched output and `sum` output (sk_encryption_circuit.rs:163-181,280-285)
+int hgo_bfv_eval(int field, int log2_size, int K, const uint64_t* qis, const uint64_t* k0is, const uint64_t* r1b, const uint64_t* r2b, uint64_t sb,
+                 uint64_t eb, uint64_t k1b, const uint64_t* s, const uint64_t* e, const uint64_t* k1, const uint64_t* ais, const uint64_t* r1is,
+                 const uint64_t* r2is, uint64_t* lasso_out, size_t* n_lasso, uint64_t* sum_out) {
+    GUARD(return field == 0 ? bfv_eval_t<Gl>(log2_size, K, qis, k0is, r1b, r2b, sb, eb, k1b, s, e, k1, ais, r1is, r2is, lasso_out, n_lasso, sum_out)
+                            : bfv_eval_t<Fr>(log2_size, K, qis, k0is, r1b, r2b, sb, eb, k1b, s, e, k1, ais, r1is, r2is, lasso_out, n_lasso, sum_out);)
 }
 int hgo_subtable(int field, int full, uint64_t bound, int log2M, const uint64_t* point, uint64_t* table_out, uint64_t* mle_out) {
     GUARD(return field == 0 ? subtable_t<Gl>(full, bound, log2M, point, table_out, mle_out) : subtable_t<Fr>(full, bound, log2M, point, table_out, mle_out);)

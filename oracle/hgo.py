@@ -60,6 +60,8 @@ def lib():
                                          C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hgo_mle_eval.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.hgo_subtable.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hgo_ntt.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t]
+        L.hgo_bfv_eval.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_uint64] * 3 + [C.c_void_p] * 9
         L.hgo_field_op.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
@@ -253,3 +255,30 @@ def field_op(field, op, a, b):
     out = np.zeros(el, np.uint64)
     _chk(lib().hgo_field_op(field, op, _p(np.ascontiguousarray(a, np.uint64)), _p(np.ascontiguousarray(b, np.uint64)), _p(out)))
     return out
+
+
+def ntt(field, data_limbs, log_n, inverse=False):
+    """Batched radix-2 NTT in natural order (assumption A9); data: [batch, 2^log_n(, limbs)]."""
+    a = np.ascontiguousarray(data_limbs, np.uint64).copy()
+    batch = a.size // ((1 << log_n) * LIMBS[field])
+    _chk(lib().hgo_ntt(field, _p(a), log_n, 1 if inverse else 0, batch))
+    return a
+
+
+def bfv_eval(field, P, ins):
+    """Forward evaluation of the BFV circuit on get_inputs() vectors -> (lasso inputs, `sum` node output), limb arrays."""
+    k = LIMBS[field]
+    K, L = P.K, P.log2_size
+    N2 = 1 << L
+    tl = lambda v: ints_to_limbs(v, field)
+    s, e, k1 = tl(ins["s"]), tl(ins["e"]), tl(ins["k1"])
+    ais = np.concatenate([tl(v) for v in ins["ais"]])
+    r1is = np.concatenate([tl(v) for v in ins["r1is"]])
+    r2is = tl(ins["r2is"])
+    nch = max(1, (len(ins["r2is"]) + N2 - 1) // N2)
+    lasso = np.zeros((K + nch + 3) * N2 * k, np.uint64)
+    n_l = C.c_size_t(0)
+    summ = np.zeros(K * N2 * k, np.uint64)
+    _chk(lib().hgo_bfv_eval(field, L, K, _p(tl(P.QIS)), _p(tl(P.K0IS)), _p(np.array(P.R1_BOUNDS, np.uint64)), _p(np.array(P.R2_BOUNDS, np.uint64)),
+                            P.S_BOUND, P.E_BOUND, P.K1_BOUND, _p(s), _p(e), _p(k1), _p(ais), _p(r1is), _p(r2is), _p(lasso), C.byref(n_l), _p(summ)))
+    return lasso[: n_l.value * k], summ

@@ -677,3 +677,76 @@ template <class F> struct LassoNode {
 };
 
 }  // namespace hgo
+
+// ---------------------------------------------------------------- NTT + forward circuit evaluation
+// [UPSTREAM gkr FftNode / VanillaNode::evaluate, assumption A9]: radix-2 NTT over w = ROOT_OF_UNITY^(2^(S - log2 n)),
+// natural order in and out, inverse scaled by n^{-1}. Call sites: sk_encryption_circuit.rs:224,249,251.
+namespace hgo {
+template <class F> void ntt_naive_order(std::vector<F>& a, bool inverse) {
+    size_t n = a.size();
+    int lg = 0; while (((size_t)1 << lg) < n) lg++;
+    F w = F::root_of_unity();
+    for (int i = lg; i < F::TWO_ADICITY; i++) w = w.square();
+    if (inverse) w = w.inv();
+    // bit reversal + iterative Cooley-Tukey
+    for (size_t i = 1, j = 0; i < n; i++) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(a[i], a[j]);
+    }
+    for (size_t len = 2; len <= n; len <<= 1) {
+        F wl = w;
+        for (size_t k = len; k < n; k <<= 1) wl = wl.square();
+        for (size_t i = 0; i < n; i += len) {
+            F x = F::one();
+            for (size_t j = 0; j < len / 2; j++) {
+                F u = a[i + j], v = a[i + j + len / 2] * x;
+                a[i + j] = u + v; a[i + j + len / 2] = u - v;
+                x *= wl;
+            }
+        }
+    }
+    if (inverse) { F ni = F::from_u64(n).inv(); for (auto& x : a) x *= ni; }
+}
+
+// Values of the circuit's layers that matter downstream (sk_encryption_circuit.rs:86-293 evaluated on get_inputs :365-415):
+//   lasso_inputs = output of `lasso_inputs_batched` (:163-181), sum = output of `sum` (:280-285) which must equal ct0is.
+template <class F> struct BfvParams { int log2_size, K; std::vector<F> qis, k0is; std::vector<uint64_t> r1_bounds, r2_bounds; uint64_t s_bound, e_bound, k1_bound; };
+template <class F>
+void bfv_evaluate(const BfvParams<F>& P, const std::vector<F>& s, const std::vector<F>& e, const std::vector<F>& k1,
+                  const std::vector<std::vector<F>>& ais, const std::vector<std::vector<F>>& r1is, const std::vector<F>& r2is,
+                  std::vector<F>* lasso_inputs, std::vector<F>* sum) {
+    const size_t N2 = (size_t)1 << P.log2_size, n = N2 / 2;
+    const int K = P.K;
+    lasso_inputs->clear();
+    for (int i = 0; i < K; i++) for (size_t j = 0; j < N2; j++) lasso_inputs->push_back(r1is[i][j] + F::from_u64(P.r1_bounds[i]));
+    for (size_t c = 0; c * N2 < r2is.size() || c == 0; c++) {  // r2is_chunks (:150-161); Q7: every chunk shifted by R2_BOUNDS[0]
+        for (size_t j = 0; j < N2; j++) {
+            size_t q = c * N2 + j;
+            F v = q < r2is.size() ? r2is[q] : F::zero();
+            lasso_inputs->push_back(v + F::from_u64(P.r2_bounds[0]));
+        }
+        if ((c + 1) * N2 >= r2is.size()) break;
+    }
+    for (size_t j = 0; j < N2; j++) lasso_inputs->push_back(s[j] + F::from_u64(P.s_bound));
+    for (size_t j = 0; j < N2; j++) lasso_inputs->push_back(e[j] + F::from_u64(P.e_bound));
+    for (size_t j = 0; j < N2; j++) lasso_inputs->push_back(k1[j] + F::from_u64(P.k1_bound));
+    std::vector<F> s_eval = s;
+    ntt_naive_order(s_eval, false);
+    sum->assign((size_t)K * N2, F::zero());
+    for (int i = 0; i < K; i++) {
+        std::vector<F> a = ais[i];
+        ntt_naive_order(a, false);
+        for (size_t j = 0; j < N2; j++) a[j] *= s_eval[j];
+        ntt_naive_order(a, true);
+        for (size_t j = 0; j < N2; j++) {
+            F v = a[j] + e[j] + k1[j] * P.k0is[i] + r1is[i][j] * P.qis[i];
+            // r2i_cyclo (:262-278): [r2i[0..n-2], 0, r2i[0..n-2], 0]
+            size_t jj = j % n;
+            if (jj < n - 1) v += r2is[(size_t)i * n + jj];
+            (*sum)[(size_t)i * N2 + j] = v;
+        }
+    }
+}
+}  // namespace hgo

@@ -29,6 +29,12 @@ for name in ["1024_1x27_65537", "2048_1x52_65537", "4096_2x55_65537"]:
     inp = np.array(witness.lasso_inputs(P, args), dtype=np.uint64)
     np.savez_compressed(os.path.join(OUT, f"lasso_inputs_{name}.npz"), inputs=inp)
     print(name, inp.size, "rows")
+    if name in ("1024_1x27_65537", "4096_2x55_65537"):
+        # the circuit's input vectors (get_inputs, sk_encryption_circuit.rs:365-415) and its expected output ct0is
+        ins, ct0is = witness.get_inputs(P, args)
+        u = lambda v: np.array(v, dtype=np.uint64)
+        np.savez_compressed(os.path.join(OUT, f"circuit_io_{name}.npz"), s=u(ins["s"]), e=u(ins["e"]), k1=u(ins["k1"]), ais=u(ins["ais"]),
+                            r1is=u(ins["r1is"]), r2is=u(ins["r2is"]), ct0is=u(ct0is))
 
 kat = {
     "keccak256_empty": "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470",

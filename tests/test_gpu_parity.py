@@ -229,3 +229,64 @@ def test_lasso_node_full_size_properties(api, ctx, oracle):
     with pytest.raises(oracle.OracleError):
         oracle.lasso_verify(0, opp, nv, bytes(bad))
     node.free()
+
+
+@pytest.mark.parametrize("log_n,batch", [(1, 3), (2, 1), (5, 4), (8, 2), (11, 3), (13, 2), (16, 3), (17, 1)])
+def test_ntt_matches_oracle(api, ctx, oracle, log_n, batch):
+    """FftNode forward / inverse evaluation (assumption A9: natural order, inverse scaled by 1/n)."""
+    rng = np.random.default_rng(log_n)
+    x = rng.integers(0, GL_P, size=(batch, 1 << log_n), dtype=np.uint64)
+    for inverse in (False, True):
+        d = api.DeviceBuffer.from_numpy(ctx, x)
+        api.ntt(ctx, d, log_n, inverse, batch)
+        got = d.download(np.uint64, x.size).reshape(x.shape)
+        assert (got == oracle.ntt(0, x, log_n, inverse)).all(), (log_n, inverse)
+        d.free()
+    # size-independent properties: inverse(forward(x)) = x, and the transform of a delta at 1 is the root powers
+    d = api.DeviceBuffer.from_numpy(ctx, x)
+    api.ntt(ctx, d, log_n, False, batch)
+    api.ntt(ctx, d, log_n, True, batch)
+    assert (d.download(np.uint64, x.size).reshape(x.shape) == x).all()
+    d.free()
+
+
+@pytest.mark.parametrize("name", ["1024_1x27_65537", "4096_2x55_65537"])
+def test_bfv_forward_evaluation_on_reference_fixture(api, ctx, oracle, golden_dir, name):
+    """circuit.evaluate on the reference's own witness: the `sum` layer equals ct0is (the circuit identity the reference's
+    verify() relies on, sk_encryption_circuit.rs:512-516) and the `lasso_inputs_batched` layer equals the golden vector; the
+    Lasso node then proves straight from the device-resident layer."""
+    import os
+    from hyper_greco_b200 import params
+    P = params.PARAMS[name]
+    io = np.load(os.path.join(golden_dir, f"circuit_io_{name}.npz"))
+    want_lasso = np.load(os.path.join(golden_dir, f"lasso_inputs_{name}.npz"))["inputs"]
+    bfv = api.BfvEncrypt(ctx, P)
+    dev = bfv.upload_inputs({k: io[k] for k in ("s", "e", "k1", "ais", "r1is", "r2is")})
+    lasso, summ = bfv.evaluate(dev)
+    assert (lasso.download(np.uint64, want_lasso.size) == want_lasso).all()
+    assert (summ.download(np.uint64, io["ct0is"].size) == io["ct0is"]).all()
+    # oracle agrees on the same layers
+    ins = {k: [int(v) for v in io[k]] for k in ("s", "e", "k1", "r2is")}
+    ins["ais"] = [[int(v) for v in row] for row in io["ais"]]
+    ins["r1is"] = [[int(v) for v in row] for row in io["r1is"]]
+    ol, osum = oracle.bfv_eval(0, P, ins)
+    assert (ol == want_lasso).all() and (osum == io["ct0is"]).all()
+    # prove from the device-resident layer
+    _, inp, bounds, segs, nv, opp, rows = load_case(name, oracle, golden_dir)
+    oproof, *_ = oracle.lasso_prove(0, opp, nv, rows, inp)
+    tr = api.Keccak256Transcript()
+    bfv.node.prove_claim_reduction(lasso, tr, n_inputs=want_lasso.size)
+    assert tr.into_proof() == oproof
+
+
+def test_bfv_forward_evaluation_full_size(api, ctx):
+    """n=32768, k=16: 33 transforms of 2^16; the sum layer must equal ct0is of the synthetic witness."""
+    from hyper_greco_b200 import params, witness
+    P = params.by_n(32768)
+    args = witness.synth_witness(P, 3)
+    ins, ct0is = witness.get_inputs(P, args)
+    bfv = api.BfvEncrypt(ctx, P)
+    lasso, summ = bfv.evaluate(bfv.upload_inputs(ins))
+    assert (summ.download(np.uint64, len(ct0is)) == np.array(ct0is, dtype=np.uint64)).all()
+    want = np.array(witness.lasso_inputs(P, args), dtype=np.uint64)
+    assert (lasso.download(np.uint64, want.size) == want).all()

@@ -223,3 +223,32 @@ def test_synthetic_witness_follows_reference_shape():
             seg = inp[pos:pos + l]
             pos += l
             assert max(seg) < b or b != shift_b
+
+
+def test_forward_evaluation_matches_reference_fixtures(oracle, golden_dir):
+    """The reference's witnesses satisfy ct0i = s*ai + e + k1*k0i + r1i*qi + r2i*(x^n+1) under the get_inputs layout; the
+    oracle's circuit evaluation (NTT -> dot product -> INTT, relay/scale/sum layers) must reproduce ct0is exactly."""
+    import hyper_greco_b200  # noqa: F401
+    from hyper_greco_b200 import params
+    for name in ("1024_1x27_65537", "4096_2x55_65537"):
+        P = params.PARAMS[name]
+        io = np.load(os.path.join(golden_dir, f"circuit_io_{name}.npz"))
+        ins = {k: [int(v) for v in io[k]] for k in ("s", "e", "k1", "r2is")}
+        ins["ais"] = [[int(v) for v in row] for row in io["ais"]]
+        ins["r1is"] = [[int(v) for v in row] for row in io["r1is"]]
+        lasso, summ = oracle.bfv_eval(0, P, ins)
+        assert (summ == io["ct0is"]).all()
+        assert (lasso == np.load(os.path.join(golden_dir, f"lasso_inputs_{name}.npz"))["inputs"]).all()
+
+
+def test_ntt_is_the_dft_over_the_2_adic_root(oracle):
+    """NTT KAT from the field definition: root = 7^((p-1)/2^32) (goldilocks crate ROOT_OF_UNITY), out[k] = sum_j in[j] w^(jk)."""
+    log_n, n = 4, 16
+    w = pow(pow(7, (GL_P - 1) >> 32, GL_P), 1 << (32 - log_n), GL_P)
+    rnd = random.Random(4)
+    x = [rnd.randrange(GL_P) for _ in range(n)]
+    want = [sum(x[j] * pow(w, j * k, GL_P) for j in range(n)) % GL_P for k in range(n)]
+    got = oracle.ntt(0, np.array([x], dtype=np.uint64), log_n)[0]
+    assert [int(v) for v in got] == want
+    back = oracle.ntt(0, got.reshape(1, -1), log_n, True)[0]
+    assert [int(v) for v in back] == x
