@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cstdio>
 
+#include "gkr.hpp"
 #include "protocol.hpp"
 
 using namespace hgo;
@@ -145,6 +146,40 @@ int bfv_eval_t(int log2_size, int K, const uint64_t* qis, const uint64_t* k0is, 
     for (size_t i = 0; i < sum.size(); i++) sum[i].to_limbs(sum_out + i * F::LIMBS);
     return 0;
 }
+template <class F>
+BfvParams<F> make_params(int log2_size, int K, const uint64_t* qis, const uint64_t* k0is, const uint64_t* r1b, const uint64_t* r2b, uint64_t sb,
+                         uint64_t eb, uint64_t k1b) {
+    BfvParams<F> P; P.log2_size = log2_size; P.K = K; P.s_bound = sb; P.e_bound = eb; P.k1_bound = k1b;
+    P.qis = load_base<F>(qis, K); P.k0is = load_base<F>(k0is, K);
+    P.r1_bounds.assign(r1b, r1b + K); P.r2_bounds.assign(r2b, r2b + K);
+    return P;
+}
+template <class F>
+std::vector<std::vector<F>> load_inputs(int log2_size, int K, const uint64_t* s, const uint64_t* e, const uint64_t* k1, const uint64_t* ais,
+                                        const uint64_t* r1is, const uint64_t* r2is) {
+    size_t N2 = (size_t)1 << log2_size;
+    std::vector<std::vector<F>> in;
+    in.push_back(load_base<F>(s, N2)); in.push_back(load_base<F>(e, N2)); in.push_back(load_base<F>(k1, N2));
+    for (int i = 0; i < K; i++) in.push_back(load_base<F>(ais + i * N2 * F::LIMBS, N2));
+    for (int i = 0; i < K; i++) in.push_back(load_base<F>(r1is + i * N2 * F::LIMBS, N2));
+    in.push_back(load_base<F>(r2is, (size_t)K * N2 / 2));
+    return in;
+}
+// full BfvEncrypt::prove / ::verify (sk_encryption_circuit.rs:417-517) with the restated engine of gkr.hpp
+template <class F>
+int bfv_prove_t(int log2_size, int K, const uint64_t* qis, const uint64_t* k0is, const uint64_t* r1b, const uint64_t* r2b, uint64_t sb, uint64_t eb,
+                uint64_t k1b, const uint64_t* s, const uint64_t* e, const uint64_t* k1, const uint64_t* ais, const uint64_t* r1is, const uint64_t* r2is,
+                const uint64_t* ct0is, uint8_t* proof, size_t cap, size_t* len, int verify_only) {
+    BfvEncrypt<F> bfv(make_params<F>(log2_size, K, qis, k0is, r1b, r2b, sb, eb, k1b));
+    auto in = load_inputs<F>(log2_size, K, s, e, k1, ais, r1is, r2is);
+    auto ct = load_base<F>(ct0is, (size_t)K << log2_size);
+    if (verify_only) { bfv.verify(in, ct, proof, *len); return 0; }
+    auto pr = bfv.prove(in, ct);
+    *len = pr.size();
+    if (pr.size() > cap) { g_err = "proof buffer too small"; return 2; }
+    memcpy(proof, pr.data(), pr.size());
+    return 0;
+}
 template <class F> int field_op_t(int op, const uint64_t* a, const uint64_t* b, uint64_t* out) {
     typedef typename ExtOf<F>::type E;
     E x = load_ext<F, E>(a), y = load_ext<F, E>(b), z;
@@ -236,6 +271,12 @@ int hgo_bfv_eval(int field, int log2_size, int K, const uint64_t* qis, const uin
                  const uint64_t* r2is, uint64_t* lasso_out, size_t* n_lasso, uint64_t* sum_out) {
     GUARD(return field == 0 ? bfv_eval_t<Gl>(log2_size, K, qis, k0is, r1b, r2b, sb, eb, k1b, s, e, k1, ais, r1is, r2is, lasso_out, n_lasso, sum_out)
                             : bfv_eval_t<Fr>(log2_size, K, qis, k0is, r1b, r2b, sb, eb, k1b, s, e, k1, ais, r1is, r2is, lasso_out, n_lasso, sum_out);)
+}
+int hgo_bfv_prove(int field, int log2_size, int K, const uint64_t* qis, const uint64_t* k0is, const uint64_t* r1b, const uint64_t* r2b, uint64_t sb,
+                  uint64_t eb, uint64_t k1b, const uint64_t* s, const uint64_t* e, const uint64_t* k1, const uint64_t* ais, const uint64_t* r1is,
+                  const uint64_t* r2is, const uint64_t* ct0is, uint8_t* proof, size_t cap, size_t* len, int verify_only) {
+    GUARD(return field == 0 ? bfv_prove_t<Gl>(log2_size, K, qis, k0is, r1b, r2b, sb, eb, k1b, s, e, k1, ais, r1is, r2is, ct0is, proof, cap, len, verify_only)
+                            : bfv_prove_t<Fr>(log2_size, K, qis, k0is, r1b, r2b, sb, eb, k1b, s, e, k1, ais, r1is, r2is, ct0is, proof, cap, len, verify_only);)
 }
 int hgo_subtable(int field, int full, uint64_t bound, int log2M, const uint64_t* point, uint64_t* table_out, uint64_t* mle_out) {
     GUARD(return field == 0 ? subtable_t<Gl>(full, bound, log2M, point, table_out, mle_out) : subtable_t<Fr>(full, bound, log2M, point, table_out, mle_out);)

@@ -62,6 +62,7 @@ def lib():
         L.hgo_subtable.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hgo_ntt.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t]
         L.hgo_bfv_eval.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_uint64] * 3 + [C.c_void_p] * 9
+        L.hgo_bfv_prove.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_uint64] * 3 + [C.c_void_p] * 8 + [C.c_size_t, C.c_void_p, C.c_int]
         L.hgo_field_op.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
@@ -282,3 +283,30 @@ def bfv_eval(field, P, ins):
     _chk(lib().hgo_bfv_eval(field, L, K, _p(tl(P.QIS)), _p(tl(P.K0IS)), _p(np.array(P.R1_BOUNDS, np.uint64)), _p(np.array(P.R2_BOUNDS, np.uint64)),
                             P.S_BOUND, P.E_BOUND, P.K1_BOUND, _p(s), _p(e), _p(k1), _p(ais), _p(r1is), _p(r2is), _p(lasso), C.byref(n_l), _p(summ)))
     return lasso[: n_l.value * k], summ
+
+
+def _bfv_args(field, P, ins, ct0is):
+    tl = lambda v: ints_to_limbs(v, field)
+    return [_p(x) for x in ()], dict(
+        q=tl(P.QIS), k0=tl(P.K0IS), r1b=np.array(P.R1_BOUNDS, np.uint64), r2b=np.array(P.R2_BOUNDS, np.uint64),
+        s=tl(ins["s"]), e=tl(ins["e"]), k1=tl(ins["k1"]), ais=np.concatenate([tl(v) for v in ins["ais"]]),
+        r1is=np.concatenate([tl(v) for v in ins["r1is"]]), r2is=tl(ins["r2is"]), ct=tl(ct0is))
+
+
+def bfv_prove(field, P, ins, ct0is, cap=1 << 24):
+    """BfvEncrypt::prove (sk_encryption_circuit.rs:417-460) with the restated GKR engine (oracle/gkr.hpp). Returns proof bytes."""
+    _, a = _bfv_args(field, P, ins, ct0is)
+    proof = np.zeros(cap, np.uint8)
+    ln = C.c_size_t(0)
+    _chk(lib().hgo_bfv_prove(field, P.log2_size, P.K, _p(a["q"]), _p(a["k0"]), _p(a["r1b"]), _p(a["r2b"]), P.S_BOUND, P.E_BOUND, P.K1_BOUND,
+                             _p(a["s"]), _p(a["e"]), _p(a["k1"]), _p(a["ais"]), _p(a["r1is"]), _p(a["r2is"]), _p(a["ct"]), _p(proof), cap, C.byref(ln), 0))
+    return proof[: ln.value].tobytes()
+
+
+def bfv_verify(field, P, ins, ct0is, proof: bytes):
+    """BfvEncrypt::verify (sk_encryption_circuit.rs:462-517). Raises OracleError where the reference would panic / Err."""
+    _, a = _bfv_args(field, P, ins, ct0is)
+    buf = np.frombuffer(proof, np.uint8).copy()
+    ln = C.c_size_t(buf.size)
+    _chk(lib().hgo_bfv_prove(field, P.log2_size, P.K, _p(a["q"]), _p(a["k0"]), _p(a["r1b"]), _p(a["r2b"]), P.S_BOUND, P.E_BOUND, P.K1_BOUND,
+                             _p(a["s"]), _p(a["e"]), _p(a["k1"]), _p(a["ais"]), _p(a["r1is"]), _p(a["r2is"]), _p(a["ct"]), _p(buf), buf.size, C.byref(ln), 1))
