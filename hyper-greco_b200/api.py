@@ -30,6 +30,9 @@ SYMBOLS = [
     "hg_lasso_pp_lookup_index", "hg_lasso_pp_memory_maps", "hg_lasso_pp_subtable_id", "hg_lasso_node_new", "hg_lasso_node_free",
     "hg_lasso_node_log2_input_size", "hg_lasso_node_device_bytes", "hg_lasso_node_prove", "hg_lasso_node_download_polys",
     "hg_lasso_node_num_chunks", "hg_lasso_node_timing", "hg_sumcheck_prove", "hg_mle_eval_batch", "hg_ntt", "hg_bfv_evaluate", "hg_field_selftest",
+    "hg_circuit_new", "hg_circuit_free", "hg_circuit_insert_input", "hg_circuit_insert_fft", "hg_circuit_insert_lasso", "hg_circuit_insert_vanilla",
+    "hg_circuit_connect", "hg_circuit_evaluate", "hg_circuit_node_value", "hg_gkr_prove", "hg_gkr_num_inputs", "hg_gkr_num_input_claims",
+    "hg_gkr_input_claim_num_vars", "hg_gkr_input_claim",
 ]
 
 _lib = None
@@ -101,6 +104,24 @@ def lib():
         L.hg_mle_eval_batch.argtypes = [vp, vp, sz, sz, sz, vp, vp]
         L.hg_field_selftest.argtypes = [vp, i32, vp, vp, sz, vp]
         L.hg_ntt.argtypes = [vp, vp, sz, i32, sz]
+        L.hg_circuit_new.argtypes = [vp, C.POINTER(vp)]
+        L.hg_circuit_free.argtypes = [vp]
+        L.hg_circuit_insert_input.argtypes = [vp, sz, sz, C.POINTER(i32)]
+        L.hg_circuit_insert_fft.argtypes = [vp, sz, i32, C.POINTER(i32)]
+        L.hg_circuit_insert_lasso.argtypes = [vp, vp, C.POINTER(i32)]
+        L.hg_circuit_insert_vanilla.argtypes = [vp, sz, sz, sz, sz] + [vp] * 12 + [C.POINTER(i32)]
+        L.hg_circuit_connect.argtypes = [vp, i32, i32]
+        L.hg_circuit_evaluate.argtypes = [vp, vp, sz]
+        L.hg_circuit_node_value.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(sz)]
+        L.hg_gkr_prove.argtypes = [vp, sz, vp, vp, vp, vp, i32]
+        for f in ("hg_gkr_num_inputs",):
+            getattr(L, f).argtypes = [vp]
+            getattr(L, f).restype = sz
+        L.hg_gkr_num_input_claims.argtypes = [vp, sz]
+        L.hg_gkr_num_input_claims.restype = sz
+        L.hg_gkr_input_claim_num_vars.argtypes = [vp, sz, sz]
+        L.hg_gkr_input_claim_num_vars.restype = sz
+        L.hg_gkr_input_claim.argtypes = [vp, sz, sz, vp, vp]
         L.hg_bfv_evaluate.argtypes = [vp, sz, sz, vp, vp, vp, vp, u64, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
@@ -440,3 +461,193 @@ class BfvEncrypt:
                                    dev_ins["s"].ptr, dev_ins["e"].ptr, dev_ins["k1"].ptr, dev_ins["ais"].ptr, dev_ins["r1is"].ptr, dev_ins["r2is"].ptr,
                                    lasso.ptr, summ.ptr))
         return lasso, summ
+
+
+class VanillaGate:
+    """VanillaGate::new(Option<F>, Vec<(Option<F>, (input, wire))>, Vec<(Option<F>, (input, wire), (input, wire))>) as plain data."""
+
+    def __init__(self, const=None, adds=(), muls=()):
+        self.const, self.adds, self.muls = const, list(adds), list(muls)
+
+
+class Circuit:
+    """gkr::circuit::Circuit on the device (sk_encryption_circuit.rs:434-437): insert / connect / evaluate / prove_gkr."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        _chk(lib().hg_circuit_new(ctx.h, C.byref(self.h)))
+        self._keep = []
+
+    def insert_input(self, log2_size, num_reps=1):
+        i = C.c_int(-1)
+        _chk(lib().hg_circuit_insert_input(self.h, log2_size, num_reps, C.byref(i)))
+        return i.value
+
+    def insert_fft(self, log2_size, inverse=False):
+        i = C.c_int(-1)
+        _chk(lib().hg_circuit_insert_fft(self.h, log2_size, 1 if inverse else 0, C.byref(i)))
+        return i.value
+
+    def insert_lasso(self, node: "LassoNode"):
+        i = C.c_int(-1)
+        _chk(lib().hg_circuit_insert_lasso(self.h, node.h, C.byref(i)))
+        self._keep.append(node)
+        return i.value
+
+    def insert_vanilla_arrays(self, arity, log2_sub, num_reps, has_const, consts, add_ptr, add_coef, add_in, add_wire,
+                              mul_ptr=None, mul_coef=None, mul_in0=None, mul_w0=None, mul_in1=None, mul_w1=None):
+        """VanillaNode::new with the gates already in CSR arrays (numpy); see include/hg_b200.h."""
+        ng = len(has_const)
+        z64, z32 = np.zeros(0, np.uint64), np.zeros(0, np.uint32)
+        a = lambda v, t: np.ascontiguousarray(v if v is not None else (z64 if t == np.uint64 else z32), t)
+        hc = np.ascontiguousarray(has_const, np.uint8)
+        mp = a(mul_ptr if mul_ptr is not None else np.zeros(ng + 1, np.uint64), np.uint64)
+        arrs = [hc, a(consts, np.uint64), a(add_ptr, np.uint64), a(add_coef, np.uint64), a(add_in, np.uint32), a(add_wire, np.uint64), mp,
+                a(mul_coef, np.uint64), a(mul_in0, np.uint32), a(mul_w0, np.uint64), a(mul_in1, np.uint32), a(mul_w1, np.uint64)]
+        i = C.c_int(-1)
+        _chk(lib().hg_circuit_insert_vanilla(self.h, arity, log2_sub, num_reps, ng, *[_p(x) for x in arrs], C.byref(i)))
+        return i.value
+
+    def connect(self, frm, to):
+        _chk(lib().hg_circuit_connect(self.h, frm, to))
+
+    def evaluate(self, dev_inputs):
+        ptrs = (C.c_void_p * len(dev_inputs))(*[b.ptr for b in dev_inputs])
+        _chk(lib().hg_circuit_evaluate(self.h, ptrs, len(dev_inputs)))
+
+    def node_value(self, node_id):
+        p, n = C.c_void_p(), C.c_size_t(0)
+        _chk(lib().hg_circuit_node_value(self.h, node_id, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def prove_gkr(self, output_claims, transcript: Keccak256Transcript, mode=MODE_PREFETCH):
+        """output_claims: [(point [nv, el] uint64, value [el] uint64), ...]. Returns per input node a list of (point, value)."""
+        el = self.ctx and LIMBS[self.ctx.field] * DEGREE[self.ctx.field]
+        lens = np.array([len(p) for p, _ in output_claims], dtype=np.uint64)
+        pts = np.concatenate([np.asarray(p, np.uint64).reshape(-1) for p, _ in output_claims] + [np.zeros(0, np.uint64)])
+        vals = np.concatenate([np.asarray(v, np.uint64).reshape(-1) for _, v in output_claims])
+        _chk(lib().hg_gkr_prove(self.h, len(output_claims), _p(lens), _p(np.ascontiguousarray(pts)), _p(np.ascontiguousarray(vals)), transcript.h, mode))
+        out = []
+        for i in range(lib().hg_gkr_num_inputs(self.h)):
+            cl = []
+            for k in range(lib().hg_gkr_num_input_claims(self.h, i)):
+                nv = lib().hg_gkr_input_claim_num_vars(self.h, i, k)
+                pt, v = np.zeros((nv, el), np.uint64), np.zeros(el, np.uint64)
+                _chk(lib().hg_gkr_input_claim(self.h, i, k, _p(pt), _p(v)))
+                cl.append((pt, v))
+            out.append(cl)
+        return out
+
+    def free(self):
+        if self.h:
+            lib().hg_circuit_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class BfvSkEncryptProver:
+    """BfvEncrypt::{setup, configure, prove} (sk_encryption_circuit.rs:300-460) with every table on the device."""
+
+    def __init__(self, ctx: Context, params):
+        from . import witness
+        P = self.P = params
+        self.ctx = ctx
+        L, K = P.log2_size, P.K
+        N2 = 1 << L
+        self.pp = LassoPreprocessing.preprocess(witness.lasso_lookup_bounds(P))                 # setup(): :327-341
+        self.lasso = LassoNode(ctx, self.pp, witness.lasso_num_vars(P), witness.lasso_lookup_segments(P))
+        c = self.circuit = Circuit(ctx)                                                         # configure(): :351-363, :86-293
+        idx = np.arange(N2, dtype=np.uint64)
+        ones = lambda n: np.ones(n, np.uint64)
+
+        def linear(arity, log2_sub, reps, in_idx, wires, coefs, consts=None):
+            ng = len(wires)
+            hc = np.zeros(ng, np.uint8) if consts is None else np.ones(ng, np.uint8)
+            cs = np.zeros(ng, np.uint64) if consts is None else np.asarray(consts, np.uint64)
+            return c.insert_vanilla_arrays(arity, log2_sub, reps, hc, cs, np.arange(ng + 1, dtype=np.uint64), coefs, in_idx, wires)
+
+        s, e, k1 = c.insert_input(L), c.insert_input(L), c.insert_input(L)
+        tile = np.tile(idx, K)
+        es = linear(1, L, 1, np.zeros(K * N2, np.uint32), tile, ones(K * N2))                    # :97-103
+        k1kis = linear(1, L, 1, np.zeros(K * N2, np.uint32), tile, np.repeat(np.array(P.K0IS, np.uint64), N2))   # :105-115
+        c.connect(e, es)
+        c.connect(k1, k1kis)
+        ais = [c.insert_input(L) for _ in range(K)]
+        r1is = [c.insert_input(L) for _ in range(K)]
+        r1iqis = linear(K, L, 1, np.repeat(np.arange(K, dtype=np.uint32), N2), tile, np.repeat(np.array(P.QIS, np.uint64), N2))  # :130-141
+        for r in r1is:
+            c.connect(r, r1iqis)
+        r2is = c.insert_input(P.N_LOG2, K)                                                       # :147
+        r2_log2 = P.N_LOG2 + (K.bit_length() - 1)
+        chunks = []
+        for start in range(0, 1 << r2_log2, N2):                                                 # :150-161
+            cnt = min(N2, (1 << r2_log2) - start)
+            ng = N2
+            add_ptr = np.minimum(np.arange(ng + 1, dtype=np.uint64), cnt)
+            hc = np.zeros(ng, np.uint8)
+            hc[cnt:] = 1
+            nd = c.insert_vanilla_arrays(1, r2_log2, 1, hc, np.zeros(ng, np.uint64), add_ptr, ones(cnt), np.zeros(cnt, np.uint32),
+                                         np.arange(start, start + cnt, dtype=np.uint64))
+            c.connect(r2is, nd)
+            chunks.append(nd)
+        shifts = list(P.R1_BOUNDS[:K]) + [P.R2_BOUNDS[0]] * len(chunks) + [P.S_BOUND, P.E_BOUND, P.K1_BOUND]   # :163-181 (Q7)
+        na = len(shifts)
+        lasso_in = linear(na, L, 1, np.repeat(np.arange(na, dtype=np.uint32), N2), np.tile(idx, na), ones(na * N2),
+                          consts=np.repeat(np.array(shifts, np.uint64), N2))
+        lasso = c.insert_lasso(self.lasso)                                                       # :205-209
+        for r in r1is:
+            c.connect(r, lasso_in)
+        for ch in chunks:
+            c.connect(ch, lasso_in)
+        for x in (s, e, k1):
+            c.connect(x, lasso_in)
+        c.connect(lasso_in, lasso)
+        s_eval = c.insert_fft(L, False)                                                          # :224
+        c.connect(s, s_eval)
+        s_copy = linear(1, L, 1, np.zeros(N2, np.uint32), idx, ones(N2))                         # :227-235
+        c.connect(s_eval, s_copy)
+        sai_par = linear(K, L, 1, np.repeat(np.arange(K, dtype=np.uint32), N2), tile, ones(K * N2))   # :237-243
+        for ai in ais:                                                                           # :245-260
+            ai_eval = c.insert_fft(L, False)
+            sai_eval = c.insert_vanilla_arrays(2, L, 1, np.zeros(N2, np.uint8), np.zeros(N2, np.uint64), np.zeros(N2 + 1, np.uint64), None, None, None,
+                                               np.arange(N2 + 1, dtype=np.uint64), ones(N2), np.zeros(N2, np.uint32), idx, np.ones(N2, np.uint32), idx)
+            sai = c.insert_fft(L, True)
+            c.connect(ai, ai_eval)
+            c.connect(s_copy, sai_eval)
+            c.connect(ai_eval, sai_eval)
+            c.connect(sai_eval, sai)
+            c.connect(sai, sai_par)
+        n = 1 << P.N_LOG2                                                                        # :262-278
+        w = np.arange(n - 1, dtype=np.uint64)
+        add_ptr = np.concatenate([np.arange(n, dtype=np.uint64), [n - 1], n - 1 + np.arange(1, n, dtype=np.uint64), [2 * n - 2]]).astype(np.uint64)
+        hc = np.zeros(2 * n, np.uint8)
+        hc[n - 1] = hc[2 * n - 1] = 1
+        cyclo = c.insert_vanilla_arrays(1, P.N_LOG2, K, hc, np.zeros(2 * n, np.uint64), add_ptr, ones(2 * n - 2), np.zeros(2 * n - 2, np.uint32),
+                                        np.concatenate([w, w]))
+        summ = c.insert_vanilla_arrays(5, L, K, np.zeros(N2, np.uint8), np.zeros(N2, np.uint64), np.arange(0, 5 * N2 + 1, 5, dtype=np.uint64), ones(5 * N2),
+                                       np.tile(np.arange(5, dtype=np.uint32), N2), np.repeat(idx, 5))   # :280-285
+        c.connect(r2is, cyclo)
+        for x in (sai_par, es, k1kis, r1iqis, cyclo):
+            c.connect(x, summ)
+        self.ids = dict(s=s, e=e, k1=k1, lasso_in=lasso_in, sum=summ)
+        self.ct0is_log2_size = L + (K.bit_length() - 1)                                          # :519-522
+
+    def upload_inputs(self, ins):
+        u = lambda v: DeviceBuffer.from_numpy(self.ctx, np.asarray(v, dtype=np.uint64).reshape(-1))
+        return [u(ins["s"]), u(ins["e"]), u(ins["k1"])] + [u(a) for a in ins["ais"]] + [u(a) for a in ins["r1is"]] + [u(ins["r2is"])]
+
+    def prove(self, dev_inputs, d_ct0is: DeviceBuffer, mode=MODE_PREFETCH):
+        """BfvEncrypt::prove (:417-460). Returns (proof bytes, input claims)."""
+        tr = Keccak256Transcript(self.ctx.field)                                                 # :431
+        self.circuit.evaluate(dev_inputs)                                                        # :442
+        point = tr.squeeze_challenges(self.ct0is_log2_size)                                      # :445
+        value = mle_eval_batch(self.ctx, d_ct0is, 1, self.ct0is_log2_size, point)[0]             # :446
+        el = point.shape[1]
+        claims = self.circuit.prove_gkr([(np.zeros((0, el), np.uint64), np.zeros(el, np.uint64)), (point, value)], tr, mode)   # :450-457
+        return tr.into_proof(), claims                                                           # :459

@@ -10,6 +10,7 @@
 #include <map>
 
 #include "bfv.cuh"
+#include "gkr_dev.cuh"
 #include "prover.cuh"
 
 using namespace hg;
@@ -37,37 +38,18 @@ struct hg_ctx {
     DeviceCtx dev;
     int field_id;
     WireOptions wire;
-    std::map<int, std::unique_ptr<DevBuf<u64>>> twiddles;  // key = log_n * 2 + inverse
-    DevBuf<u64> ntt_scratch;
+    std::unique_ptr<NttEngine<GlField>> ntt;
+};
+struct hg_circuit {
+    hg_ctx* ctx;
+    std::unique_ptr<GkrCircuitDev<GlField>> gl;
+    std::vector<std::vector<GkrCircuitDev<GlField>::InputClaim>> input_claims;
 };
 
 namespace {
-// batched in-place NTT of `batch` transforms of 2^log_n base elements at d_data (device)
 void ntt_run(hg_ctx* ctx, u64* d_data, int log_n, bool inverse, size_t batch) {
-    typedef GlField FP;
-    if (log_n < 1 || log_n > 24) throw std::runtime_error("hg_ntt: log_n out of range (1..24)");
-    cudaStream_t s = ctx->dev.stream;
-    const size_t N = (size_t)1 << log_n;
-    const int key = log_n * 2 + (inverse ? 1 : 0);
-    auto& tw = ctx->twiddles[key];
-    if (!tw) {
-        tw.reset(new DevBuf<u64>());
-        tw->alloc(N);
-        HG_K(&ctx->dev, KC_MISC, N * 8, k_ntt_twiddles<FP><<<(unsigned)((N + 255) / 256), 256, 0, s>>>(log_n, inverse ? 1 : 0, FP::root_of_unity_2_32(), tw->p));
-    }
-    if (ctx->ntt_scratch.n < N * batch) ctx->ntt_scratch.alloc(N * batch);
-    const int log_n1 = (log_n + 1) / 2, log_n2 = log_n - log_n1;
-    const int n1 = 1 << log_n1, n2 = 1 << log_n2;
-    const int tile_c = std::min(HG_NTT_TILE, n2), tile_r = std::min(HG_NTT_TILE, n1);
-    const size_t smem_c = (size_t)n1 * (tile_c | 1) * sizeof(u64), smem_r = (size_t)n2 * (tile_r | 1) * sizeof(u64);
-    if (smem_c > 200 * 1024 || smem_r > 200 * 1024) throw std::runtime_error("hg_ntt: transform too large for the shared-memory tiles");
-    HG_CUDA(cudaFuncSetAttribute(k_ntt_cols<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-    HG_CUDA(cudaFuncSetAttribute(k_ntt_rows<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
-    HG_K(&ctx->dev, KC_MISC, 2 * N * batch * 8,
-         k_ntt_cols<FP><<<dim3(n2 / tile_c, (unsigned)batch), HG_NTT_THREADS, smem_c, s>>>(d_data, ctx->ntt_scratch.p, log_n1, log_n2, tile_c, tw->p));
-    const u64 scale = inverse ? gl_inv(gl_from_u64(N)) : 1;
-    HG_K(&ctx->dev, KC_MISC, 2 * N * batch * 8,
-         k_ntt_rows<FP><<<dim3(n1 / tile_r, (unsigned)batch), HG_NTT_THREADS, smem_r, s>>>(ctx->ntt_scratch.p, d_data, log_n1, log_n2, tile_r, tw->p, scale, inverse ? 1 : 0));
+    if (!ctx->ntt) ctx->ntt.reset(new NttEngine<GlField>(&ctx->dev));
+    ctx->ntt->run(d_data, log_n, inverse, batch);
 }
 }  // namespace
 struct hg_buf {
@@ -424,6 +406,89 @@ int hg_bfv_evaluate(hg_ctx* ctx, size_t log2_size, size_t K, const uint64_t* qis
              k_bfv_sum<FP><<<dim3((unsigned)((N2 + 255) / 256), (unsigned)K), 256, 0, s>>>(sh, d_sai.p, (const u64*)d_e, (const u64*)d_k1, (const u64*)d_r1is,
                                                                                          (const u64*)d_r2is, d_consts.p, d_consts.p + K, (u64*)d_sum));
         HG_CUDA(cudaStreamSynchronize(s));  // temporaries are freed on return
+    })
+}
+
+// ---- circuit-level API: Circuit::{insert, connect, evaluate} + prove_gkr
+int hg_circuit_new(hg_ctx* ctx, hg_circuit** out) {
+    HG_TRY({
+        HG_CUDA(cudaSetDevice(ctx->dev.device));
+        if (!ctx->ntt) ctx->ntt.reset(new NttEngine<GlField>(&ctx->dev));
+        std::unique_ptr<hg_circuit> c(new hg_circuit());
+        c->ctx = ctx;
+        c->gl.reset(new GkrCircuitDev<GlField>(&ctx->dev, ctx->ntt.get()));
+        *out = c.release();
+    })
+}
+void hg_circuit_free(hg_circuit* c) {
+    if (!c) return;
+    cudaSetDevice(c->ctx->dev.device);
+    delete c;
+}
+int hg_circuit_insert_input(hg_circuit* c, size_t log2_size, size_t num_reps, int* out_id) { HG_TRY({ *out_id = c->gl->insert_input(log2_size, num_reps); }) }
+int hg_circuit_insert_fft(hg_circuit* c, size_t log2_size, int inverse, int* out_id) {
+    HG_TRY({ HG_CUDA(cudaSetDevice(c->ctx->dev.device)); *out_id = c->gl->insert_fft(log2_size, inverse != 0); })
+}
+int hg_circuit_insert_lasso(hg_circuit* c, hg_lasso_node* node, int* out_id) { HG_TRY({ *out_id = c->gl->insert_lasso(node->gl.get()); }) }
+int hg_circuit_insert_vanilla(hg_circuit* c, size_t input_arity, size_t log2_sub_input_size, size_t num_reps, size_t n_gates, const uint8_t* has_const,
+                              const uint64_t* consts, const uint64_t* add_ptr, const uint64_t* add_coef, const uint32_t* add_input,
+                              const uint64_t* add_wire, const uint64_t* mul_ptr, const uint64_t* mul_coef, const uint32_t* mul_in0, const uint64_t* mul_w0,
+                              const uint32_t* mul_in1, const uint64_t* mul_w1, int* out_id) {
+    HG_TRY({
+        HG_CUDA(cudaSetDevice(c->ctx->dev.device));
+        VanillaDesc d;
+        d.arity = input_arity; d.log2_sub = log2_sub_input_size; d.num_reps = num_reps; d.n_gates = n_gates;
+        d.has_const.assign(has_const, has_const + n_gates);
+        d.consts.assign(consts, consts + n_gates);
+        d.add_ptr.assign(add_ptr, add_ptr + n_gates + 1);
+        const size_t na = d.add_ptr[n_gates];
+        d.add_coef.assign(add_coef, add_coef + na); d.add_in.assign(add_input, add_input + na); d.add_wire.assign(add_wire, add_wire + na);
+        d.mul_ptr.assign(mul_ptr, mul_ptr + n_gates + 1);
+        const size_t nm = d.mul_ptr[n_gates];
+        d.mul_coef.assign(mul_coef, mul_coef + nm); d.mul_in0.assign(mul_in0, mul_in0 + nm); d.mul_w0.assign(mul_w0, mul_w0 + nm);
+        d.mul_in1.assign(mul_in1, mul_in1 + nm); d.mul_w1.assign(mul_w1, mul_w1 + nm);
+        *out_id = c->gl->insert_vanilla(d);
+    })
+}
+int hg_circuit_connect(hg_circuit* c, int from, int to) { HG_TRY({ c->gl->connect(from, to); }) }
+int hg_circuit_evaluate(hg_circuit* c, const void* const* d_inputs, size_t n_inputs) {
+    HG_TRY({
+        HG_CUDA(cudaSetDevice(c->ctx->dev.device));
+        std::vector<const u64*> in;
+        for (size_t i = 0; i < n_inputs; i++) in.push_back((const u64*)d_inputs[i]);
+        c->gl->evaluate(in);
+    })
+}
+int hg_circuit_node_value(hg_circuit* c, int id, const void** d_ptr, size_t* len) {
+    HG_TRY({
+        if (id < 0 || (size_t)id >= c->gl->num_nodes()) throw std::runtime_error("no such node");
+        *d_ptr = c->gl->node_value(id);
+        *len = c->gl->node_out_len(id);
+    })
+}
+int hg_gkr_prove(hg_circuit* c, size_t n_output_claims, const size_t* point_lens, const uint64_t* points_ext, const uint64_t* values_ext,
+                 hg_transcript* t, int mode) {
+    HG_TRY({
+        typedef GlField FP;
+        HG_CUDA(cudaSetDevice(c->ctx->dev.device));
+        std::vector<GkrCircuitDev<FP>::InputClaim> oc(n_output_claims);
+        size_t off = 0;
+        for (size_t i = 0; i < n_output_claims; i++) {
+            for (size_t k = 0; k < point_lens[i]; k++) oc[i].point.push_back(FP::x_from_limbs(points_ext + 2 * (off + k)));
+            off += point_lens[i];
+            oc[i].value = FP::x_from_limbs(values_ext + 2 * i);
+        }
+        c->input_claims = c->gl->prove(*t->gl, mode == HG_MODE_INTERACTIVE ? kModeInteractive : kModePrefetch, c->ctx->wire, oc);
+    })
+}
+size_t hg_gkr_num_inputs(const hg_circuit* c) { return c->input_claims.size(); }
+size_t hg_gkr_num_input_claims(const hg_circuit* c, size_t input) { return input < c->input_claims.size() ? c->input_claims[input].size() : 0; }
+size_t hg_gkr_input_claim_num_vars(const hg_circuit* c, size_t input, size_t k) { return c->input_claims.at(input).at(k).point.size(); }
+int hg_gkr_input_claim(const hg_circuit* c, size_t input, size_t k, uint64_t* point_ext, uint64_t* value_ext) {
+    HG_TRY({
+        const auto& ic = c->input_claims.at(input).at(k);
+        for (size_t q = 0; q < ic.point.size(); q++) GlField::x_to_limbs(ic.point[q], point_ext + 2 * q);
+        GlField::x_to_limbs(ic.value, value_ext);
     })
 }
 

@@ -1,0 +1,564 @@
+// Device GKR prover for the circuits bfv-gkr builds: Circuit::{insert, connect, evaluate} and gkr::prove_gkr
+// (call sites /root/reference/bfv-gkr/src/sk_encryption_circuit.rs:102-290, :442, :455-457). The engine is the un-vendored `gkr`
+// crate (PARITY UNPINNED); the protocol restated here is specified in DESIGN.md section 3 (the parity tests check it against an independent CPU restatement):
+//     per node, in reverse topological order: [T > 1 claims: squeeze alpha] -> product sumcheck rounds -> write input evaluations
+// Node shapes: Input, Vanilla with linear gates (relay / scale / add-const / sum), the element-wise product layer, FFT
+// forward / inverse, Lasso. In PREFETCH mode every node's sumcheck is independent (claim POINTS are transcript challenges,
+// only claim VALUES flow between nodes, and those are needed on the host only), so round j of all nodes is one launch.
+#pragma once
+#include <algorithm>
+#include <map>
+
+#include "gkr_kernels.cuh"
+#include "ntt_engine.cuh"
+
+namespace hg {
+
+enum GkrNodeKind { GKR_INPUT = 0, GKR_VANILLA = 1, GKR_FFT = 2, GKR_LASSO = 3 };
+
+// host description of one Vanilla layer (VanillaNode::new(input_arity, log2_sub_input_size, gates, num_reps)), CSR over gates
+struct VanillaDesc {
+    size_t arity = 0, log2_sub = 0, num_reps = 1, n_gates = 0;
+    std::vector<uint8_t> has_const;
+    std::vector<uint64_t> consts;                       // limbs per gate
+    std::vector<uint64_t> add_ptr, add_coef, add_wire;  // add_coef: limbs
+    std::vector<uint32_t> add_in;
+    std::vector<uint64_t> mul_ptr, mul_coef, mul_w0, mul_w1;
+    std::vector<uint32_t> mul_in0, mul_in1;
+};
+
+template <class FP> class GkrCircuitDev {
+  public:
+    typedef typename FP::B B;
+    typedef typename FP::X X;
+
+    struct InputClaim { std::vector<X> point; X value; };
+
+    GkrCircuitDev(DeviceCtx* ctx, NttEngine<FP>* ntt) : ctx_(ctx), ntt_(ntt) {}
+
+    int insert_input(size_t log2_size, size_t num_reps) {
+        auto n = std::make_unique<Node>();
+        n->kind = GKR_INPUT; n->out_len = num_reps << log2_size;
+        nodes_.push_back(std::move(n));
+        return (int)nodes_.size() - 1;
+    }
+    int insert_fft(size_t log2_size, bool inverse) {
+        auto n = std::make_unique<Node>();
+        n->kind = GKR_FFT; n->out_len = (size_t)1 << log2_size; n->fft_inverse = inverse; n->log2_size = (int)log2_size;
+        n->value.alloc(n->out_len);
+        nodes_.push_back(std::move(n));
+        return (int)nodes_.size() - 1;
+    }
+    int insert_lasso(LassoNodeDev<FP>* lasso) {
+        auto n = std::make_unique<Node>();
+        n->kind = GKR_LASSO; n->out_len = 1; n->lasso = lasso;
+        nodes_.push_back(std::move(n));
+        return (int)nodes_.size() - 1;
+    }
+    int insert_vanilla(const VanillaDesc& d) {
+        auto np = std::make_unique<Node>();
+        Node& n = *np;
+        n.kind = GKR_VANILLA; n.arity = (int)d.arity; n.log2_sub = (int)d.log2_sub; n.num_reps = (int)d.num_reps; n.ng = d.n_gates;
+        n.out_len = pad2(d.n_gates * d.num_reps);
+        n.n_in = d.num_reps << d.log2_sub;
+        n.a_pad = pad2(d.arity);
+        const size_t ng = d.n_gates, sub = (size_t)1 << d.log2_sub;
+        const size_t n_add = d.add_ptr.at(ng), n_mul = d.mul_ptr.at(ng);
+        // classify
+        n.is_linear = n_mul == 0;
+        n.is_elemmul = false;
+        if (!n.is_linear) {
+            bool ok = d.arity == 2 && n_add == 0 && n_mul == ng && d.num_reps == 1;
+            for (size_t g = 0; ok && g < ng; g++) {
+                ok = !d.has_const[g] && d.mul_ptr[g] == g && d.mul_in0[g] == 0 && d.mul_in1[g] == 1 && d.mul_w0[g] == g && d.mul_w1[g] == g &&
+                     FP::b_from_limbs(&d.mul_coef[g * FP::B_LIMBS]) == FP::b_one();
+            }
+            if (!ok) throw std::runtime_error("VanillaNode: only linear gates and the element-wise product layer are supported on the device");
+            n.is_elemmul = true;
+        }
+        auto up = [](auto& buf, const auto& v) { buf.alloc(std::max<size_t>(v.size(), 1)); if (!v.empty()) HG_CUDA(cudaMemcpy(buf.p, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice)); };
+        std::vector<B> addc(n_add), mulc(n_mul), cg(ng);
+        for (size_t e = 0; e < n_add; e++) addc[e] = FP::b_from_limbs(&d.add_coef[e * FP::B_LIMBS]);
+        for (size_t e = 0; e < n_mul; e++) mulc[e] = FP::b_from_limbs(&d.mul_coef[e * FP::B_LIMBS]);
+        n.has_consts = false;
+        for (size_t g = 0; g < ng; g++) { cg[g] = d.has_const[g] ? FP::b_from_limbs(&d.consts[g * FP::B_LIMBS]) : FP::b_zero(); if (d.has_const[g]) n.has_consts = true; }
+        up(n.add_ptr, d.add_ptr); up(n.add_in, d.add_in); up(n.add_wire, d.add_wire); up(n.add_coef, addc);
+        up(n.mul_ptr, d.mul_ptr); up(n.mul_in0, d.mul_in0); up(n.mul_w0, d.mul_w0); up(n.mul_in1, d.mul_in1); up(n.mul_w1, d.mul_w1); up(n.mul_coef, mulc);
+        up(n.consts, cg);
+        if (n.is_linear) {
+            // reverse wiring: for every element x of the concatenated inputs, the (output, coefficient) pairs that read it
+            const size_t S = n.a_pad * n.n_in;
+            std::vector<uint64_t> rp(S + 1, 0);
+            for (size_t r = 0; r < d.num_reps; r++)
+                for (size_t g = 0; g < ng; g++)
+                    for (uint64_t e = d.add_ptr[g]; e < d.add_ptr[g + 1]; e++) rp[(size_t)d.add_in[e] * n.n_in + r * sub + d.add_wire[e] + 1]++;
+            for (size_t x = 0; x < S; x++) rp[x + 1] += rp[x];
+            std::vector<uint32_t> ro(rp[S]);
+            std::vector<B> rc(rp[S]);
+            std::vector<uint64_t> fill(rp.begin(), rp.end() - 1);
+            for (size_t r = 0; r < d.num_reps; r++)
+                for (size_t g = 0; g < ng; g++)
+                    for (uint64_t e = d.add_ptr[g]; e < d.add_ptr[g + 1]; e++) {
+                        size_t x = (size_t)d.add_in[e] * n.n_in + r * sub + d.add_wire[e];
+                        ro[fill[x]] = (uint32_t)(r * ng + g); rc[fill[x]] = addc[e]; fill[x]++;
+                    }
+            up(n.rev_ptr, rp); up(n.rev_out, ro); up(n.rev_coef, rc);
+            if (n.has_consts) {
+                std::vector<B> cf(n.out_len, FP::b_zero());
+                for (size_t r = 0; r < d.num_reps; r++) for (size_t g = 0; g < ng; g++) cf[r * ng + g] = cg[g];
+                up(n.consts_full, cf);
+            }
+        }
+        n.value.alloc(n.out_len);
+        nodes_.push_back(std::move(np));
+        return (int)nodes_.size() - 1;
+    }
+    void connect(int from, int to) {
+        if (from < 0 || to < 0 || from >= (int)nodes_.size() || to >= (int)nodes_.size()) throw std::runtime_error("connect: no such node");
+        nodes_[to]->preds.push_back(from);
+        nodes_[from]->succs.push_back(to);
+        topo_.clear();
+    }
+    size_t num_nodes() const { return nodes_.size(); }
+    size_t node_out_len(int id) const { return nodes_.at(id)->out_len; }
+    const B* node_value(int id) const { return nodes_.at(id)->value_ptr; }
+
+    // Circuit::evaluate (sk_encryption_circuit.rs:442): inputs = device pointers for the input nodes in insertion order
+    void evaluate(const std::vector<const B*>& inputs) {
+        cudaStream_t s = ctx_->stream;
+        size_t next = 0;
+        for (auto& n : nodes_) if (n->kind == GKR_INPUT) { if (next >= inputs.size()) throw std::runtime_error("evaluate: too few inputs"); n->value_ptr = inputs[next++]; }
+        if (next != inputs.size()) throw std::runtime_error("evaluate: too many inputs");
+        for (int id : topo()) {
+            Node& n = *nodes_[id];
+            if (n.kind == GKR_INPUT) continue;
+            if (n.kind == GKR_LASSO) { n.value_ptr = nullptr; continue; }
+            if (n.kind == GKR_FFT) {
+                const Node& p = *nodes_[n.preds.at(0)];
+                if (p.out_len != n.out_len) throw std::runtime_error("evaluate: FFT input size mismatch");
+                HG_CUDA(cudaMemcpyAsync(n.value.p, p.value_ptr, n.out_len * sizeof(B), cudaMemcpyDeviceToDevice, s));
+                ntt_->run(n.value.p, n.log2_size, n.fft_inverse, 1);
+                n.value_ptr = n.value.p;
+                continue;
+            }
+            if ((int)n.preds.size() != n.arity) throw std::runtime_error("evaluate: Vanilla node arity does not match its connections");
+            std::vector<const B*> ptrs;
+            for (int pid : n.preds) { if (nodes_[pid]->out_len != n.n_in) throw std::runtime_error("evaluate: Vanilla input size mismatch"); ptrs.push_back(nodes_[pid]->value_ptr); }
+            n.in_ptrs.alloc(ptrs.size());
+            HG_CUDA(cudaMemcpyAsync(n.in_ptrs.p, ptrs.data(), ptrs.size() * sizeof(B*), cudaMemcpyHostToDevice, s));
+            HG_CUDA(cudaStreamSynchronize(s));
+            VanillaFwd w{n.add_ptr.p, n.add_in.p, n.add_wire.p, n.mul_ptr.p, n.mul_in0.p, n.mul_w0.p, n.mul_in1.p, n.mul_w1.p};
+            HG_K(ctx_, KC_MISC, n.out_len * sizeof(B) * 2,
+                 k_vanilla_eval<FP><<<(unsigned)((n.out_len + 255) / 256), 256, 0, s>>>(w, n.add_coef.p, n.mul_coef.p, n.consts.p, (const B* const*)n.in_ptrs.p, n.ng,
+                                                                                      (size_t)1 << n.log2_sub, n.num_reps, n.out_len, n.value.p));
+            n.value_ptr = n.value.p;
+        }
+        evaluated_ = true;
+    }
+
+    // gkr::prove_gkr (sk_encryption_circuit.rs:455-457). output_claims: one per output node (nodes without successors, insertion
+    // order), point given by value (the caller squeezed it from the same transcript). Returns the claims on the input nodes.
+    std::vector<std::vector<InputClaim>> prove(Keccak256Transcript<FP>& tr, ProveMode mode, const WireOptions& wo,
+                                               const std::vector<InputClaim>& output_claims) {
+        if (!evaluated_) throw std::runtime_error("prove_gkr: evaluate the circuit first");
+        cudaStream_t s = ctx_->stream;
+        plan();
+        Channel<FP>& ch = *ch_;
+        // Lasso witness kernels need no challenge: enqueue them first so that Keccak squeezing overlaps them
+        for (auto& n : nodes_) if (n->kind == GKR_LASSO) {
+            const Node& p = *nodes_[n->preds.at(0)];
+            n->lasso->enqueue_witness(p.value_ptr, n->lasso->num_rows(), wo);
+        }
+        ch.begin(&tr, mode, total_chal_);
+        struct Claim { bool by_index; size_t idx; std::vector<X> point_host; int nvars; std::shared_ptr<X> value; };
+        std::vector<std::vector<Claim>> claims(nodes_.size());
+        // output claims: their points live in extra device slots after the challenges
+        std::vector<int> outs;
+        for (size_t i = 0; i < nodes_.size(); i++) if (nodes_[i]->succs.empty() && nodes_[i]->kind != GKR_INPUT) outs.push_back((int)i);
+        if (outs.size() != output_claims.size()) throw std::runtime_error("prove_gkr: one output claim per output node is required");
+        {
+            size_t slot = 0;
+            std::vector<X> stage;
+            for (size_t i = 0; i < outs.size(); i++) {
+                Claim c; c.by_index = false; c.idx = slot; c.point_host = output_claims[i].point; c.nvars = (int)output_claims[i].point.size();
+                c.value = std::make_shared<X>(output_claims[i].value);
+                slot += c.point_host.size();
+                stage.insert(stage.end(), c.point_host.begin(), c.point_host.end());
+                claims[outs[i]].push_back(c);
+            }
+            if (slot > d_outpts_.n) d_outpts_.alloc(slot + 16);
+            if (!stage.empty()) { HG_CUDA(cudaMemcpyAsync(d_outpts_.p, stage.data(), stage.size() * sizeof(X), cudaMemcpyHostToDevice, s)); HG_CUDA(cudaStreamSynchronize(s)); }
+        }
+        auto point_ptr = [&](const Claim& c) -> const X* { return c.by_index ? ch.d_chal(c.idx) : d_outpts_.p + c.idx; };
+        std::vector<Job> jobs;
+        auto ord = topo();
+        Channel<FP>* chp = &ch;
+        for (size_t oi = ord.size(); oi-- > 0;) {
+            const int id = ord[oi];
+            Node& n = *nodes_[id];
+            if (n.kind == GKR_INPUT) continue;
+            if (n.kind == GKR_LASSO) {
+                size_t r_idx = 0, sum_off = 0;
+                n.lasso->enqueue_protocol(ch, mode, wo, &r_idx, &sum_off);
+                Claim c; c.by_index = true; c.idx = r_idx; c.nvars = n.lasso->num_vars(); c.value = std::make_shared<X>(FP::x_zero());
+                auto vp = c.value;
+                ch.emit([chp, vp, sum_off]() { *vp = chp->msg(sum_off); });
+                claims[n.preds.at(0)].push_back(c);
+                continue;
+            }
+            auto& cl = claims[id];
+            if (cl.empty()) throw std::runtime_error("prove_gkr: node without claims");
+            Job job;
+            job.node = id;
+            job.nt = n.is_elemmul ? 2 : 1;
+            job.S = n.kind == GKR_FFT || n.is_elemmul ? n.out_len : n.a_pad * n.n_in;
+            job.nv = log2sz(job.S);
+            job.alpha_idx = cl.size() > 1 ? ch.squeeze(1) : (size_t)-1;
+            for (auto& c : cl) { if (((size_t)1 << c.nvars) != n.out_len) throw std::runtime_error("prove_gkr: claim point does not match the node's output size"); job.points.push_back(point_ptr(c)); }
+            job.const_off = ch.alloc_msg(1);
+            auto st = std::make_shared<ScHostState<FP>>();
+            {
+                std::vector<std::shared_ptr<X>> vals;
+                for (auto& c : cl) vals.push_back(c.value);
+                const size_t aidx = job.alpha_idx, coff = job.const_off;
+                const bool has_c = n.kind == GKR_VANILLA && n.is_linear && n.has_consts;
+                ch.emit([chp, st, vals, aidx, coff, has_c]() {
+                    X a = aidx == (size_t)-1 ? FP::x_one() : chp->chal(aidx), p = FP::x_one(), comb = FP::x_zero();
+                    for (auto& v : vals) { comb = FP::x_add(comb, FP::x_mul(p, *v)); p = FP::x_mul(p, a); }
+                    if (has_c) comb = FP::x_sub(comb, chp->msg(coff));
+                    st->claim = comb;
+                });
+            }
+            const int n_ev = n.kind == GKR_FFT ? 1 : (n.is_elemmul ? 2 : n.arity);
+            if (mode == kModeInteractive) prepare_jobs(ch, {job}, wo);
+            for (int j = 0; j < job.nv; j++) {
+                size_t off = ch.alloc_msg(4);
+                if (j == 0) job.msg_off = off;
+                if (mode == kModeInteractive) launch_round(ch, {job}, j);
+                const size_t next_idx = ch.next_index();
+                if (job.nt == 1) emit_round_slots<FP, 2>(ch, st, off, wo, j == 0, next_idx);
+                else emit_round_slots<FP, 3>(ch, st, off, wo, j == 0, next_idx);
+                size_t idx = ch.squeeze(1);
+                if (j == 0) job.r0_idx = idx;
+            }
+            job.evals_off = ch.alloc_msg(n_ev);  // after the rounds: in interactive mode earlier slots have already been downloaded
+            if (mode == kModeInteractive) launch_finals(ch, {job});
+            // new claims on the predecessors: (point = the round challenges restricted to the input's variables, value = its evaluation)
+            const int in_vars = n.kind == GKR_VANILLA && n.is_linear ? log2sz(n.n_in) : job.nv;
+            std::vector<std::shared_ptr<X>> outv;
+            for (int k = 0; k < n_ev; k++) {
+                Claim c; c.by_index = true; c.idx = job.r0_idx; c.nvars = in_vars; c.value = std::make_shared<X>(FP::x_zero());
+                outv.push_back(c.value);
+                claims[n.preds.at(k)].push_back(c);
+            }
+            {
+                const size_t eo = job.evals_off;
+                ch.emit([chp, outv, eo]() {
+                    for (size_t k = 0; k < outv.size(); k++) { *outv[k] = chp->msg(eo + k); chp->transcript().write_felt_ext(*outv[k]); }
+                });
+            }
+            jobs.push_back(job);
+        }
+        if (mode == kModePrefetch) {
+            prepare_jobs(ch, jobs, wo);
+            int maxv = 0;
+            for (auto& j : jobs) maxv = std::max(maxv, j.nv);
+            for (int r = 0; r < maxv; r++) launch_round(ch, jobs, r);
+            launch_finals(ch, jobs);
+        }
+        ch.flush();
+        if (ch.chal_used() != total_chal_) throw std::runtime_error("prove_gkr: challenge count mismatch");
+        std::vector<std::vector<InputClaim>> res;
+        for (size_t i = 0; i < nodes_.size(); i++) {
+            if (nodes_[i]->kind != GKR_INPUT) continue;
+            std::vector<InputClaim> v;
+            for (auto& c : claims[i]) {
+                InputClaim ic;
+                if (c.by_index) { ic.point.resize(c.nvars); for (int q = 0; q < c.nvars; q++) ic.point[q] = ch.chal(c.idx + q); }
+                else ic.point = c.point_host;
+                ic.value = *c.value;
+                v.push_back(ic);
+            }
+            res.push_back(v);
+        }
+        return res;
+    }
+
+  private:
+    struct Node {
+        int kind = GKR_INPUT, log2_size = 0, num_reps = 1, arity = 0, log2_sub = 0;
+        bool fft_inverse = false, is_linear = false, is_elemmul = false, has_consts = false;
+        size_t ng = 0, out_len = 0, n_in = 0, a_pad = 1;
+        std::vector<int> preds, succs;
+        DevBuf<u64> add_ptr, add_wire, mul_ptr, mul_w0, mul_w1, rev_ptr;
+        DevBuf<u32> add_in, mul_in0, mul_in1, rev_out;
+        DevBuf<B> add_coef, mul_coef, consts, consts_full, rev_coef, value;
+        DevBuf<const B*> in_ptrs;
+        const B* value_ptr = nullptr;
+        LassoNodeDev<FP>* lasso = nullptr;
+        // per-node work buffers of the layer sumcheck
+        DevBuf<X> W, A, wbuf0, wbuf1, tbuf0, tbuf1, capture;
+        DevBuf<B> Xcat;
+    };
+    struct Job {
+        int node = 0, nt = 1, nv = 0;
+        size_t S = 0, alpha_idx = (size_t)-1, const_off = 0, msg_off = 0, r0_idx = 0, evals_off = 0;
+        std::vector<const X*> points;
+    };
+
+    static size_t pad2(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }
+    static int log2sz(size_t n) { int l = 0; while (((size_t)1 << l) < n) l++; return l; }
+    static int eq_lo_bits(int nv) { return nv < 12 ? nv : 12; }
+
+    const std::vector<int>& topo() {
+        if (!topo_.empty() || nodes_.empty()) return topo_;
+        std::vector<int> indeg(nodes_.size());
+        std::vector<char> done(nodes_.size(), 0);
+        for (size_t i = 0; i < nodes_.size(); i++) indeg[i] = (int)nodes_[i]->preds.size();
+        for (size_t step = 0; step < nodes_.size(); step++) {
+            int pick = -1;
+            for (size_t i = 0; i < nodes_.size(); i++) if (!done[i] && indeg[i] == 0) { pick = (int)i; break; }
+            if (pick < 0) throw std::runtime_error("circuit has a cycle");
+            done[pick] = 1; topo_.push_back(pick);
+            for (int sx : nodes_[pick]->succs) indeg[sx]--;
+        }
+        return topo_;
+    }
+
+    // challenge / message budget and per-node buffers (static per circuit)
+    void plan() {
+        if (planned_) return;
+        size_t chal = 0, msg = 0, eq_elems = 0, items = 0;
+        for (int id : topo()) {
+            Node& n = *nodes_[id];
+            if (n.kind == GKR_INPUT) continue;
+            if (n.kind == GKR_LASSO) { chal += n.lasso->total_challenges(); msg += n.lasso->message_budget(); continue; }
+            const size_t S = n.kind == GKR_FFT || n.is_elemmul ? n.out_len : n.a_pad * n.n_in;
+            const int nv = log2sz(S), nt = n.is_elemmul ? 2 : 1;
+            size_t n_claims = std::max<size_t>(1, n.succs.size());  // one claim per successor edge (upper bound: every successor pushes one)
+            // a successor may push several claims only through distinct input slots; count edges
+            size_t edges = 0;
+            for (int sx : n.succs) for (int p : nodes_[sx]->preds) if (p == id) edges++;
+            n_claims = std::max<size_t>(1, edges);
+            chal += (n_claims > 1 ? 1 : 0) + nv;
+            msg += 1 + 4 * (size_t)nv + 8 + n.a_pad;
+            eq_elems += n_claims * (((size_t)1 << eq_lo_bits(log2sz(n.out_len))) + (n.out_len >> eq_lo_bits(log2sz(n.out_len))) + 2);
+            items += n_claims + 4;
+            n.W.alloc(n.out_len);
+            if (!(n.kind == GKR_VANILLA && n.is_elemmul)) n.A.alloc(S);
+            n.wbuf0.alloc(std::max<size_t>(S / 2, 1)); n.wbuf1.alloc(std::max<size_t>(S / 4, 1));
+            n.tbuf0.alloc(std::max<size_t>(nt * (S / 2), 1)); n.tbuf1.alloc(std::max<size_t>(nt * (S / 4), 1));
+            if (n.kind == GKR_VANILLA) n.Xcat.alloc(n.is_elemmul ? 2 * S : S);
+            n.capture.alloc(n.a_pad + 2);
+        }
+        total_chal_ = chal;
+        ch_.reset(new Channel<FP>(ctx_, chal + 8, msg + 64));
+        d_eq_.alloc(eq_elems + 64);
+        d_partials_.alloc(((size_t)ctx_->sm_count * 4 + 8) * 4 * (items + 4));
+        d_counters_.alloc(items + 64);
+        HG_CUDA(cudaMemset(d_counters_.p, 0, d_counters_.bytes()));
+        h_desc_.alloc(1 << 20);
+        d_desc_.alloc(1 << 20);
+        planned_ = true;
+    }
+
+    // descriptor staging: per call, a fresh region of the pinned/device descriptor buffers
+    template <class T> const T* stage(const std::vector<T>& v) {
+        size_t bytes = (v.size() * sizeof(T) + 15) & ~(size_t)15;
+        if (desc_off_ + bytes > h_desc_.n) throw std::runtime_error("gkr: descriptor staging overflow");
+        memcpy(h_desc_.p + desc_off_, v.data(), v.size() * sizeof(T));
+        HG_CUDA(cudaMemcpyAsync(d_desc_.p + desc_off_, h_desc_.p + desc_off_, bytes, cudaMemcpyHostToDevice, ctx_->stream));
+        const T* r = (const T*)(d_desc_.p + desc_off_);
+        desc_off_ += bytes;
+        return r;
+    }
+
+    // weights W, A and concatenated inputs for the given jobs
+    void prepare_jobs(Channel<FP>& ch, const std::vector<Job>& jobs, const WireOptions& wo) {
+        cudaStream_t s = ctx_->stream;
+        if (jobs.size() > 1) { desc_off_ = 0; eq_off_ = 0; }
+        if (desc_off_ > h_desc_.n / 2) { HG_CUDA(cudaStreamSynchronize(s)); desc_off_ = 0; eq_off_ = 0; }
+        // eq factor tables of every (node, claim), then accumulation claim by claim (t = 0 initialises W)
+        size_t max_claims = 0;
+        struct EqRef { X* lo; X* hi; int lo_bits; };
+        std::vector<std::vector<EqRef>> eqs(jobs.size());
+        for (size_t q = 0; q < jobs.size(); q++) {
+            const Job& j = jobs[q];
+            Node& n = *nodes_[j.node];
+            const int nvw = log2sz(n.out_len), lo = eq_lo_bits(nvw);
+            max_claims = std::max(max_claims, j.points.size());
+            for (size_t t = 0; t < j.points.size(); t++) {
+                const size_t need = ((size_t)1 << lo) + ((size_t)1 << (nvw - lo));
+                if (eq_off_ + need > d_eq_.n) throw std::runtime_error("gkr: eq table pool too small");
+                X* elo = d_eq_.p + eq_off_;
+                X* ehi = elo + ((size_t)1 << lo);
+                eq_off_ += need;
+                HG_K(ctx_, KC_GKR_PREP, need * sizeof(X), k_eq_split<FP><<<(unsigned)((need + HG_BLOCK - 1) / HG_BLOCK), HG_BLOCK, 0, s>>>(j.points[t], nvw, lo, elo, ehi));
+                eqs[q].push_back({elo, ehi, lo});
+            }
+        }
+        for (size_t t = 0; t < max_claims; t++) {
+            std::vector<EqAccItem<FP>> items;
+            int blk = 0;
+            size_t bytes = 0;
+            for (size_t q = 0; q < jobs.size(); q++) {
+                const Job& j = jobs[q];
+                if (t >= j.points.size()) continue;
+                Node& n = *nodes_[j.node];
+                EqAccItem<FP> it;
+                it.eq_lo = eqs[q][t].lo; it.eq_hi = eqs[q][t].hi; it.lo_bits = eqs[q][t].lo_bits;
+                it.alpha = j.alpha_idx == (size_t)-1 ? nullptr : ch.d_chal(j.alpha_idx);
+                it.w = n.W.p; it.n = n.out_len; it.t = (int)t; it.blk_start = blk;
+                blk += (int)((n.out_len + HG_BLOCK - 1) / HG_BLOCK);
+                bytes += n.out_len * sizeof(X) * (t ? 2 : 1);
+                items.push_back(it);
+            }
+            if (items.empty()) continue;
+            HG_K(ctx_, KC_GKR_PREP, bytes, k_eq_accumulate<FP><<<blk, HG_BLOCK, 0, s>>>(stage(items), (int)items.size()));
+        }
+        // A per node
+        std::vector<X*> fft_fwd, fft_inv;  // W tables whose transform is needed, grouped by size via a map below
+        std::map<std::pair<int, int>, std::vector<int>> fft_groups;  // (log2 size, inverse) -> node ids
+        for (const Job& j : jobs) {
+            Node& n = *nodes_[j.node];
+            if (n.kind == GKR_FFT) { fft_groups[{n.log2_size, n.fft_inverse ? 1 : 0}].push_back(j.node); continue; }
+            if (n.is_elemmul) {
+                // tables = [in0 | in1]
+                const size_t S = n.out_len;
+                for (int k = 0; k < 2; k++) HG_CUDA(cudaMemcpyAsync(n.Xcat.p + k * S, nodes_[n.preds.at(k)]->value_ptr, S * sizeof(B), cudaMemcpyDeviceToDevice, s));
+                continue;
+            }
+            const size_t S = n.a_pad * n.n_in;
+            HG_K(ctx_, KC_GKR_PREP, S * sizeof(X) * 2, k_wiring_gather<FP><<<(unsigned)((S + HG_BLOCK - 1) / HG_BLOCK), HG_BLOCK, 0, s>>>(n.rev_ptr.p, n.rev_out.p, n.rev_coef.p, n.W.p, S, n.A.p));
+            if (n.a_pad != (size_t)n.arity) HG_CUDA(cudaMemsetAsync(n.Xcat.p + (size_t)n.arity * n.n_in, 0, (n.a_pad - n.arity) * n.n_in * sizeof(B), s));
+            for (int k = 0; k < n.arity; k++) HG_CUDA(cudaMemcpyAsync(n.Xcat.p + (size_t)k * n.n_in, nodes_[n.preds.at(k)]->value_ptr, n.n_in * sizeof(B), cudaMemcpyDeviceToDevice, s));
+            if (n.has_consts) {
+                int blocks = (int)std::min<size_t>((n.out_len + HG_BLOCK - 1) / HG_BLOCK, (size_t)ctx_->sm_count * 2);
+                HG_K(ctx_, KC_GKR_PREP, n.out_len * (sizeof(X) + sizeof(B)),
+                     k_dot_wconst<FP><<<blocks, HG_BLOCK, 0, s>>>(n.W.p, n.consts_full.p, n.out_len, d_partials_.p, d_counters_.p, ch.d_msg(j.const_off)));
+            }
+        }
+        // FFT-matrix weights: A = transform(W) plane by plane, batched over all FFT nodes of the same size and direction
+        for (auto& kv : fft_groups) {
+            const int lg = kv.first.first;
+            const bool inv = kv.first.second != 0;
+            const size_t N = (size_t)1 << lg, cnt = kv.second.size();
+            if (d_planes_.n < 2 * N * cnt) { HG_CUDA(cudaStreamSynchronize(s)); d_planes_.alloc(2 * N * cnt); }
+            for (size_t q = 0; q < cnt; q++) {
+                Node& n = *nodes_[kv.second[q]];
+                HG_K(ctx_, KC_GKR_PREP, N * sizeof(X) * 2, k_ext_split<FP><<<(unsigned)((N + 255) / 256), 256, 0, s>>>(n.W.p, N, d_planes_.p + (2 * q) * N, d_planes_.p + (2 * q + 1) * N));
+            }
+            ntt_->run(d_planes_.p, lg, inv, 2 * cnt);
+            for (size_t q = 0; q < cnt; q++) {
+                Node& n = *nodes_[kv.second[q]];
+                HG_K(ctx_, KC_GKR_PREP, N * sizeof(X) * 2, k_ext_merge<FP><<<(unsigned)((N + 255) / 256), 256, 0, s>>>(d_planes_.p + (2 * q) * N, d_planes_.p + (2 * q + 1) * N, N, n.A.p));
+            }
+        }
+        (void)wo;
+    }
+
+    const X* weights(const Node& n) const { return n.kind == GKR_VANILLA && n.is_elemmul ? n.W.p : n.A.p; }
+    const B* tables(const Node& n) const { return n.kind == GKR_FFT ? nodes_[n.preds.at(0)]->value_ptr : n.Xcat.p; }
+
+    // round r of every job that still has one
+    void launch_round(Channel<FP>& ch, const std::vector<Job>& jobs, int r) {
+        cudaStream_t s = ctx_->stream;
+        std::vector<ProdItem<FP>> items;
+        int blk = 0;
+        size_t part_off = 0, bytes = 0;
+        for (const Job& j : jobs) {
+            if (r >= j.nv) continue;
+            Node& n = *nodes_[j.node];
+            ProdItem<FP> it;
+            it.nt = j.nt;
+            if (r == 0) {
+                it.w_in = weights(n); it.w_out = nullptr; it.tab_in = tables(n); it.tab_out = nullptr; it.n_in = j.S; it.r_prev = nullptr;
+            } else {
+                it.n_in = j.S >> (r - 1);
+                it.w_in = r == 1 ? weights(n) : ((r - 1) & 1 ? n.wbuf0.p : n.wbuf1.p);
+                it.w_out = (r & 1) ? n.wbuf0.p : n.wbuf1.p;
+                it.tab_in = r == 1 ? (const void*)tables(n) : (const void*)((r - 1) & 1 ? n.tbuf0.p : n.tbuf1.p);
+                it.tab_out = (r & 1) ? n.tbuf0.p : n.tbuf1.p;
+                it.r_prev = ch.d_chal(j.r0_idx + r - 1);
+            }
+            it.msg = ch.d_msg(j.msg_off + 4 * (size_t)r);
+            const size_t npairs = r == 0 ? it.n_in / 2 : it.n_in / 4;
+            size_t b = std::max<size_t>(1, std::min<size_t>((npairs + HG_BLOCK - 1) / HG_BLOCK, (size_t)ctx_->sm_count * 4));
+            it.nblk = (int)b; it.bx = (int)b; it.blk_start = blk;
+            blk += it.nblk;
+            it.partials = d_partials_.p + part_off;
+            part_off += b * 4;
+            it.counter = d_counters_.p + 8 + items.size();
+            bytes += it.n_in * ((r <= 1 ? sizeof(B) : sizeof(X)) * j.nt + sizeof(X)) + (r ? (it.n_in / 2) * sizeof(X) * (j.nt + 1) : 0);
+            items.push_back(it);
+        }
+        if (items.empty()) return;
+        if (part_off > d_partials_.n) throw std::runtime_error("gkr: partial-sum pool too small");
+        if (desc_off_ > h_desc_.n - (1 << 16)) { HG_CUDA(cudaStreamSynchronize(s)); desc_off_ = 0; }
+        const ProdItem<FP>* di = stage(items);
+        KernelScope ks(ctx_, KC_GKR_SC, bytes);
+        if (r == 0) k_prod_round_multi<FP, B, false><<<blk, HG_BLOCK, 0, s>>>(di, (int)items.size());
+        else if (r == 1) k_prod_round_multi<FP, B, true><<<blk, HG_BLOCK, 0, s>>>(di, (int)items.size());
+        else k_prod_round_multi<FP, X, true><<<blk, HG_BLOCK, 0, s>>>(di, (int)items.size());
+        HG_LAUNCH_CHECK();
+        // linear layers: the table folded over the low log2(n_in) variables holds the evaluations of the inputs; it is the
+        // output of round m = log2(n_in) and would be overwritten two rounds later, so it is copied out now
+        std::vector<CopyItem<FP>> copies;
+        for (const Job& j : jobs) {
+            Node& n = *nodes_[j.node];
+            if (!(n.kind == GKR_VANILLA && n.is_linear)) continue;
+            const int m = log2sz(n.n_in);
+            if (m != r || m >= j.nv || r == 0) continue;
+            CopyItem<FP> c; c.src = (m & 1) ? n.tbuf0.p : n.tbuf1.p; c.dst = n.capture.p; c.n = n.arity;
+            copies.push_back(c);
+        }
+        if (!copies.empty()) HG_K(ctx_, KC_GKR_SC, copies.size() * 64, k_copy_items<FP><<<(unsigned)copies.size(), 32, 0, s>>>(stage(copies)));
+    }
+
+    // input evaluations: linear layers read them off the table folded over the low variables; FFT / product layers off the last fold
+    void launch_finals(Channel<FP>& ch, const std::vector<Job>& jobs) {
+        cudaStream_t s = ctx_->stream;
+        std::vector<FoldItem<FP>> folds;
+        std::vector<CopyItem<FP>> copies;
+        for (const Job& j : jobs) {
+            Node& n = *nodes_[j.node];
+            // state after the last round launch (round nv-1): tables folded by r_0..r_{nv-2}, length 2
+            const int last = j.nv - 1;
+            const void* tab_last = last == 0 ? (const void*)tables(n) : (const void*)((last & 1) ? n.tbuf0.p : n.tbuf1.p);
+            const bool base_last = last == 0;
+            if (n.kind == GKR_VANILLA && n.is_linear) {
+                const int m = log2sz(n.n_in);  // the table folded by r_0..r_{m-1} has a_pad entries: the evaluations of the inputs
+                if (m == j.nv) {
+                    FoldItem<FP> f; f.in = tab_last; f.out = ch.d_msg(j.evals_off); f.r = ch.d_chal(j.r0_idx + j.nv - 1); f.n_out = 1; f.in_base = base_last;
+                    folds.push_back(f);
+                } else if (m == 0) {
+                    throw std::runtime_error("gkr: empty input tables");
+                } else {  // captured by launch_round(m) into the node's staging buffer
+                    CopyItem<FP> c; c.src = n.capture.p; c.dst = ch.d_msg(j.evals_off); c.n = n.arity;
+                    copies.push_back(c);
+                }
+            } else {
+                FoldItem<FP> f; f.in = tab_last; f.out = ch.d_msg(j.evals_off); f.r = ch.d_chal(j.r0_idx + j.nv - 1); f.n_out = j.nt; f.in_base = base_last;
+                // nt tables of length 2 are contiguous: [t0_0 t0_1 t1_0 t1_1] -> out[q] = fold(in[2q], in[2q+1])
+                folds.push_back(f);
+            }
+        }
+        if (!folds.empty()) HG_K(ctx_, KC_GKR_SC, folds.size() * 64, k_fold_items<FP><<<(unsigned)folds.size(), 32, 0, s>>>(stage(folds)));
+        if (!copies.empty()) HG_K(ctx_, KC_GKR_SC, copies.size() * 64, k_copy_items<FP><<<(unsigned)copies.size(), 32, 0, s>>>(stage(copies)));
+    }
+
+    DeviceCtx* ctx_;
+    NttEngine<FP>* ntt_;
+    std::vector<std::unique_ptr<Node>> nodes_;
+    std::vector<int> topo_;
+    bool evaluated_ = false, planned_ = false;
+    size_t total_chal_ = 0, desc_off_ = 0, eq_off_ = 0;
+    std::unique_ptr<Channel<FP>> ch_;
+    DevBuf<X> d_eq_, d_partials_, d_outpts_;
+    DevBuf<B> d_planes_;
+    DevBuf<unsigned> d_counters_;
+    DevBuf<unsigned char> d_desc_;
+    PinnedBuf<unsigned char> h_desc_;
+};
+
+}  // namespace hg

@@ -1,0 +1,166 @@
+// K11/K12: kernels for the generic GKR layers (Vanilla / FFT nodes of /root/reference/bfv-gkr/src/sk_encryption_circuit.rs:86-293;
+// the engine itself is the un-vendored `gkr` crate, restated in DESIGN.md section 3). Every layer reduces to a product sumcheck
+//        sum_x W[x] * prod_{k<nt} T_k[x]            nt = 1 (linear / FFT layers), nt = 2 (element-wise product layer)
+// where W is an extension-field weight table derived from the claim points (eq tables pushed through the wiring or the FFT
+// matrix) and T_k are the node's input tables. With prefetched challenges all nodes are independent, so round j of every
+// node runs in ONE launch (descriptor table, like gp_kernels.cuh).
+#pragma once
+#include "gp_kernels.cuh"
+
+namespace hg {
+
+// ---- forward evaluation of a Vanilla layer: out[r*ng + g] = c_g + sum coef * in_k[r*sub + w] + sum coef * in*in
+struct VanillaFwd {
+    const u64* add_ptr;   // [ng + 1]
+    const u32* add_in;    // input index
+    const u64* add_wire;
+    const u64* mul_ptr;   // [ng + 1]
+    const u32* mul_in0; const u64* mul_w0; const u32* mul_in1; const u64* mul_w1;
+};
+template <class FP>
+__global__ void k_vanilla_eval(VanillaFwd w, const typename FP::B* __restrict__ add_coef, const typename FP::B* __restrict__ mul_coef,
+                               const typename FP::B* __restrict__ consts, const typename FP::B* const* __restrict__ inputs, size_t ng,
+                               size_t sub, int num_reps, size_t out_len, typename FP::B* __restrict__ out) {
+    typedef typename FP::B B;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= out_len) return;
+    if (t >= ng * num_reps) { out[t] = FP::b_zero(); return; }
+    const size_t r = t / ng, g = t % ng;
+    B v = consts[g];
+    for (u64 e = w.add_ptr[g]; e < w.add_ptr[g + 1]; e++) v = FP::b_add(v, FP::b_mul(add_coef[e], inputs[w.add_in[e]][r * sub + w.add_wire[e]]));
+    for (u64 e = w.mul_ptr[g]; e < w.mul_ptr[g + 1]; e++)
+        v = FP::b_add(v, FP::b_mul(mul_coef[e], FP::b_mul(inputs[w.mul_in0[e]][r * sub + w.mul_w0[e]], inputs[w.mul_in1[e]][r * sub + w.mul_w1[e]])));
+    out[t] = v;
+}
+
+// ---- W += alpha^t * eq(z_t, .) for every (node, claim) pair; eq via two factor tables built by k_eq_split
+template <class FP> struct EqAccItem {
+    const typename FP::X* eq_lo; const typename FP::X* eq_hi;   // of this claim
+    const typename FP::X* alpha;                                // nullptr when the node has a single claim
+    typename FP::X* w;
+    u64 n; int lo_bits, t, blk_start;
+};
+template <class FP> __global__ void k_eq_accumulate(const EqAccItem<FP>* __restrict__ items, int nitems) {
+    typedef typename FP::X X;
+    int k = 0;
+    while (k + 1 < nitems && (int)blockIdx.x >= items[k + 1].blk_start) k++;
+    const EqAccItem<FP> it = items[k];
+    const size_t i = (size_t)(blockIdx.x - it.blk_start) * blockDim.x + threadIdx.x;
+    if (i >= it.n) return;
+    X e = FP::fmul(it.eq_lo[i & (((size_t)1 << it.lo_bits) - 1)], it.eq_hi[i >> it.lo_bits]);
+    if (it.alpha) { X a = *it.alpha, p = FP::x_one(); for (int q = 0; q < it.t; q++) p = FP::fmul(p, a); e = FP::fmul(e, p); }
+    it.w[i] = it.t == 0 ? e : FP::x_add(it.w[i], e);
+}
+// claims of one node are accumulated by consecutive launches (t = 0, 1, ..), so there is no write race on w.
+
+// ---- A[x] = sum_{(o, c) in rev[x]} c * W[o]  (weights pushed through the wiring, reverse CSR), const = sum_g W[g] c_g
+template <class FP>
+__global__ void k_wiring_gather(const u64* __restrict__ rev_ptr, const u32* __restrict__ rev_out, const typename FP::B* __restrict__ rev_coef,
+                                const typename FP::X* __restrict__ w, size_t n, typename FP::X* __restrict__ A) {
+    typedef typename FP::X X;
+    const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    typename FP::XAcc acc = FP::xacc_zero_();
+    for (u64 e = rev_ptr[x]; e < rev_ptr[x + 1]; e++) FP::xacc_mad_b(acc, w[rev_out[e]], rev_coef[e]);
+    A[x] = FP::xacc_reduce_(acc);
+}
+
+// ---- split / merge of extension tables into base planes (the FFT-matrix weights are the transform of W, plane by plane)
+template <class FP> __global__ void k_ext_split(const typename FP::X* __restrict__ in, size_t n, typename FP::B* __restrict__ p0, typename FP::B* __restrict__ p1) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    typename FP::X v = in[i];
+    p0[i] = v.c0; p1[i] = v.c1;
+}
+template <class FP> __global__ void k_ext_merge(const typename FP::B* __restrict__ p0, const typename FP::B* __restrict__ p1, size_t n, typename FP::X* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = gl2_make(p0[i], p1[i]);
+}
+
+// ---- product sumcheck rounds, all nodes per launch. msg slots per round: [h(0), h(inf), h(-1), h(1)] (h(-1) only for nt = 2,
+// h(1) only in round 0; unused slots are written as zero)
+template <class FP> struct ProdItem {
+    const typename FP::X* w_in; typename FP::X* w_out;
+    const void* tab_in; typename FP::X* tab_out;   // nt tables of n_in elements back to back
+    u64 n_in;
+    const typename FP::X* r_prev;
+    typename FP::X* msg; typename FP::X* partials; unsigned* counter;
+    int nt, blk_start, nblk, bx;
+};
+template <class FP, class TIN, bool FOLD>
+__global__ void __launch_bounds__(HG_BLOCK) k_prod_round_multi(const ProdItem<FP>* __restrict__ items, int nitems) {
+    typedef typename FP::X X;
+    typedef typename std::conditional<FOLD, X, TIN>::type EL;
+    int k = 0;
+    while (k + 1 < nitems && (int)blockIdx.x >= items[k + 1].blk_start) k++;
+    const ProdItem<FP> it = items[k];
+    const unsigned lb = blockIdx.x - it.blk_start;
+    const TIN* tab = (const TIN*)it.tab_in;
+    const size_t n_in = it.n_in, npairs = FOLD ? n_in / 4 : n_in / 2, n_out = n_in / 2;
+    X r = FP::x_zero();
+    typename FP::FoldAux aux;
+    if (FOLD) { r = *it.r_prev; aux = FP::fold_aux(r); }
+    X acc[4] = {FP::x_zero(), FP::x_zero(), FP::x_zero(), FP::x_zero()};
+    for (size_t b = (size_t)lb * blockDim.x + threadIdx.x; b < npairs; b += (size_t)it.nblk * blockDim.x) {
+        X wlo, whi;
+        if constexpr (FOLD) {
+            const X* s = it.w_in + 4 * b;
+            wlo = FP::fold(s[0], s[1], r, aux); whi = FP::fold(s[2], s[3], r, aux);
+            it.w_out[2 * b] = wlo; it.w_out[2 * b + 1] = whi;
+        } else { wlo = it.w_in[2 * b]; whi = it.w_in[2 * b + 1]; }
+        EL lo[2], hi[2];
+        for (int q = 0; q < it.nt; q++) {
+            if constexpr (FOLD) {
+                const TIN* s = tab + (size_t)q * n_in + 4 * b;
+                lo[q] = FP::fold(s[0], s[1], r, aux); hi[q] = FP::fold(s[2], s[3], r, aux);
+                X* d = it.tab_out + (size_t)q * n_out + 2 * b;
+                d[0] = lo[q]; d[1] = hi[q];
+            } else { lo[q] = tab[(size_t)q * n_in + 2 * b]; hi[q] = tab[(size_t)q * n_in + 2 * b + 1]; }
+        }
+        if (it.nt == 1) {
+            acc[0] = FP::x_add(acc[0], FP::fmul(wlo, FP::as_x(lo[0])));
+            acc[1] = FP::x_add(acc[1], FP::fmul(FP::slope(wlo, whi), FP::as_x(FP::slope(lo[0], hi[0]))));
+            if (!FOLD) acc[3] = FP::x_add(acc[3], FP::fmul(whi, FP::as_x(hi[0])));
+        } else {
+            acc[0] = FP::x_add(acc[0], FP::fmul(wlo, FP::as_x(FP::fmul(lo[0], lo[1]))));
+            acc[1] = FP::x_add(acc[1], FP::fmul(FP::slope(wlo, whi), FP::as_x(FP::fmul(FP::slope(lo[0], hi[0]), FP::slope(lo[1], hi[1])))));
+            acc[2] = FP::x_add(acc[2], FP::fmul(FP::at_m1(wlo, whi), FP::as_x(FP::fmul(FP::at_m1(lo[0], hi[0]), FP::at_m1(lo[1], hi[1])))));
+            if (!FOLD) acc[3] = FP::x_add(acc[3], FP::fmul(whi, FP::as_x(FP::fmul(hi[0], hi[1]))));
+        }
+    }
+    block_reduce_finalize_ex<FP, 4>(acc, it.partials, it.counter, it.msg, it.nblk, lb);
+}
+
+// ---- final folds and captures: out[i] = in[2 i] + r (in[2 i + 1] - in[2 i]) for tiny tables (one item per block)
+template <class FP> struct FoldItem {
+    const void* in; typename FP::X* out; const typename FP::X* r; int n_out, in_base;
+};
+template <class FP> __global__ void k_fold_items(const FoldItem<FP>* __restrict__ items) {
+    typedef typename FP::B B;
+    typedef typename FP::X X;
+    const FoldItem<FP> it = items[blockIdx.x];
+    const X r = *it.r;
+    const typename FP::FoldAux aux = FP::fold_aux(r);
+    for (int i = threadIdx.x; i < it.n_out; i += blockDim.x) {
+        if (it.in_base) { const B* s = (const B*)it.in; it.out[i] = FP::fold(s[2 * i], s[2 * i + 1], r, aux); }
+        else { const X* s = (const X*)it.in; it.out[i] = FP::fold(s[2 * i], s[2 * i + 1], r, aux); }
+    }
+}
+template <class FP> struct CopyItem { const typename FP::X* src; typename FP::X* dst; int n; };
+template <class FP> __global__ void k_copy_items(const CopyItem<FP>* __restrict__ items) {
+    const CopyItem<FP> it = items[blockIdx.x];
+    for (int i = threadIdx.x; i < it.n; i += blockDim.x) it.dst[i] = it.src[i];
+}
+// constant part of linear layers: out = sum_g W[g] * c[g]
+template <class FP>
+__global__ void k_dot_wconst(const typename FP::X* __restrict__ w, const typename FP::B* __restrict__ c, size_t n, typename FP::X* partials,
+                             unsigned* counter, typename FP::X* out) {
+    typedef typename FP::X X;
+    typename FP::XAcc a = FP::xacc_zero_();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) FP::xacc_mad_b(a, w[i], c[i]);
+    X acc[1] = {FP::xacc_reduce_(a)};
+    block_reduce_finalize<FP, 1>(acc, partials, counter, out);
+}
+
+}  // namespace hg

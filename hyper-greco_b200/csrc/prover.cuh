@@ -34,10 +34,10 @@ struct CudaError : std::runtime_error { using std::runtime_error::runtime_error;
 #define HG_LAUNCH_CHECK() HG_CUDA(cudaGetLastError())
 
 // kernel classes for the per-class event timing bench.py reports (roofline of the dominant kernel)
-enum KernelClass { KC_POLY = 0, KC_COUNTERS, KC_EQ, KC_DOT, KC_HASH, KC_TREE, KC_SC_COLL, KC_SC_GP, KC_MISC, KC_COUNT };
+enum KernelClass { KC_POLY = 0, KC_COUNTERS, KC_EQ, KC_DOT, KC_HASH, KC_TREE, KC_SC_COLL, KC_SC_GP, KC_MISC, KC_NTT, KC_GKR_PREP, KC_GKR_SC, KC_COUNT };
 inline const char* kernel_class_name(int c) {
     static const char* n[] = {"polynomialize", "counters", "eq_build", "mle_dot", "hash_build", "product_tree", "sumcheck_collation",
-                              "sumcheck_grand_product", "misc"};
+                              "sumcheck_grand_product", "misc", "ntt", "gkr_layer_weights", "gkr_layer_sumcheck"};
     return (c >= 0 && c < KC_COUNT) ? n[c] : "?";
 }
 struct DeviceCtx {
@@ -259,15 +259,16 @@ struct ScScratch {
 // true sum s = h(0) + h(1) (= previous true polynomial at the previous challenge) they determine h; the wire message then
 // follows the upstream format under assumptions A3 / A3'.
 template <class FP, int D>
-void emit_round(Channel<FP>& ch, std::shared_ptr<ScHostState<FP>> st, size_t off, const WireOptions& wo, bool round0, size_t next_idx) {
+void emit_round(Channel<FP>& ch, std::shared_ptr<ScHostState<FP>> st, size_t off, const WireOptions& wo, bool round0, size_t next_idx,
+                int slot_h1 = D) {
     typedef typename FP::X X;
     Channel<FP>* chp = &ch;
     WireOptions w = wo;
-    ch.emit([chp, st, off, w, round0, next_idx]() {
+    ch.emit([chp, st, off, w, round0, next_idx, slot_h1]() {
         typedef RoundPoly<FP> RP;
         X s;
         if (round0) {
-            s = FP::x_add(chp->msg(off), chp->msg(off + D));
+            s = FP::x_add(chp->msg(off), chp->msg(off + slot_h1));
         } else {
             X rprev = chp->chal(st->pending_chal);
             s = RP::horner(st->pending_true, rprev);
@@ -301,6 +302,12 @@ void emit_round(Channel<FP>& ch, std::shared_ptr<ScHostState<FP>> st, size_t off
         st->pending_chal = next_idx;
         st->has_pending = true;
     });
+}
+
+// same for the fixed 4-slot layout [h(0), h(inf), h(-1), h(1)] of the generic GKR layer kernels (gkr_kernels.cuh)
+template <class FP, int D>
+void emit_round_slots(Channel<FP>& ch, std::shared_ptr<ScHostState<FP>> st, size_t off, const WireOptions& wo, bool round0, size_t next_idx) {
+    emit_round<FP, D>(ch, st, off, wo, round0, next_idx, 3);
 }
 
 // one launch of k_sc_round with the right instantiation
@@ -575,6 +582,7 @@ template <class FP> class LassoNodeDev {
         size_t v = num_vars_, lm = log2M_;
         total_chal_ = v + v + 2 + gp_chal_count(v) + gp_chal_count(lm);
         size_t msg = 1 + 4 * v + gp_msg_count(v) + gp_msg_count(lm) + pp.C + 2 * nslots_ + m_ + 16;
+        msg_budget_ = msg;
         ch_.reset(new Channel<FP>(ctx, total_chal_ + 4, msg));
 
         // constant coefficient vectors
@@ -604,18 +612,33 @@ template <class FP> class LassoNodeDev {
     void prove(const B* d_inputs, size_t n_inputs, Keccak256Transcript<FP>& tr, ProveMode mode, const WireOptions& wo, std::vector<X>* out_point,
                X* out_value) {
         Channel<FP>& ch = *ch_;
-        cudaStream_t s = ctx_->stream;
         auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         const double t_start = now();
+        enqueue_witness(d_inputs, n_inputs, wo);
+        ch.begin(&tr, mode, total_chal_);  // squeezing (Keccak on the host) overlaps the witness kernels, which need no challenges
+        const double t_begin = now();
+        size_t r_idx = 0, sum_off = 0;
+        enqueue_protocol(ch, mode, wo, &r_idx, &sum_off);
+        const double t_enq = now();
+        ch.flush(&timing_[2], &timing_[3]);
+        timing_[0] = t_begin - t_start;
+        timing_[1] = t_enq - t_begin;
+        if (ch.chal_used() != total_chal_) throw std::runtime_error("LassoNode: challenge count mismatch");
+        if (out_point) { out_point->resize(num_vars_); for (int i = 0; i < num_vars_; i++) (*out_point)[i] = ch.chal(r_idx + i); }
+        if (out_value) *out_value = ch.msg(sum_off);
+    }
+
+    // polynomialize (lasso.rs:157-250): everything that needs no challenge
+    void enqueue_witness(const B* d_inputs, size_t n_inputs, const WireOptions& wo) {
+        cudaStream_t s = ctx_->stream;
         const size_t R = R_, M = M_;
-        const int m = m_, v = num_vars_;
+        const int m = m_;
         const size_t rows = std::min(n_inputs, n_rows_);  // izip! stops at the shorter (Q9)
         {
             size_t np2 = 1;  // lasso.rs:161 num_reads = inputs.len().next_power_of_two(); lasso.rs:79-80 assert_eq!(num_vars, self.num_vars)
             while (np2 < n_inputs) np2 <<= 1;
             if (np2 != R_) throw std::runtime_error("assertion `left == right` failed: num_vars of the input does not match the node (lasso.rs:80)");
         }
-        double t_begin = t_start;
 
         // collation coefficients (A5)
         {
@@ -639,9 +662,13 @@ template <class FP> class LassoNodeDev {
                                                                                   d_read_cts_.p + (size_t)sl * R));
         }
 
-        // the kernels above need no challenges: squeezing (Keccak on the host) overlaps them
-        ch.begin(&tr, mode, total_chal_);
-        t_begin = now();
+    }
+
+    // the interactive part of prove_claim_reduction on an already-begun channel (lasso.rs:85-113)
+    void enqueue_protocol(Channel<FP>& ch, ProveMode mode, const WireOptions& wo, size_t* out_r_idx, size_t* out_sum_off) {
+        cudaStream_t s = ctx_->stream;
+        const size_t R = R_, M = M_;
+        const int m = m_, v = num_vars_;
         // ---- r, claimed sum (lasso.rs:85, :264, :269)
         const size_t r_idx = ch.squeeze(v);
         const size_t sum_off = ch.alloc_msg(1);
@@ -706,14 +733,10 @@ template <class FP> class LassoNodeDev {
                 }
             });
         }
-        const double t_enq = now();
-        ch.flush(&timing_[2], &timing_[3]);
-        timing_[0] = t_begin - t_start;
-        timing_[1] = t_enq - t_begin;
-        if (ch.chal_used() != total_chal_) throw std::runtime_error("LassoNode: challenge count mismatch");
-        if (out_point) { out_point->resize(v); for (int i = 0; i < v; i++) (*out_point)[i] = ch.chal(r_idx + i); }
-        if (out_value) *out_value = ch.msg(sum_off);
+        *out_r_idx = r_idx;
+        *out_sum_off = sum_off;
     }
+    size_t message_budget() const { return msg_budget_; }
 
     // test hooks: copies of the polynomialised witness
     void download_polys(std::vector<u16>* dims, std::vector<u32>* read_cts, std::vector<u32>* final_cts, std::vector<B>* E) {
@@ -962,6 +985,7 @@ template <class FP> class LassoNodeDev {
     }
 
     double timing_[4] = {0, 0, 0, 0};
+    size_t msg_budget_ = 0;
     int eq_nv_ = 0;
     DeviceCtx* ctx_;
     LassoPreprocessing pp_;

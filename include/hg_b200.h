@@ -40,6 +40,7 @@ typedef struct hg_transcript hg_transcript;
 typedef struct hg_lasso_pp hg_lasso_pp;
 typedef struct hg_lasso_node hg_lasso_node;
 typedef struct hg_buf hg_buf;
+typedef struct hg_circuit hg_circuit;
 
 const char* hg_last_error(void);
 int hg_version(void);
@@ -141,6 +142,37 @@ int hg_ntt(hg_ctx* ctx, void* d_data, size_t log_n, int inverse, size_t batch);
 int hg_bfv_evaluate(hg_ctx* ctx, size_t log2_size, size_t K, const uint64_t* qis, const uint64_t* k0is, const uint64_t* r1_bounds,
                     const uint64_t* r2_bounds, uint64_t s_bound, uint64_t e_bound, uint64_t k1_bound, const void* d_s, const void* d_e,
                     const void* d_k1, const void* d_ais, const void* d_r1is, const void* d_r2is, void* d_lasso_inputs, void* d_sum);
+
+/* ---- GKR circuit: gkr::circuit::Circuit::{insert, connect, evaluate} and gkr::prove_gkr for the node shapes bfv-gkr builds
+ *      (bfv-gkr/src/sk_encryption_circuit.rs:86-293, :442, :455-457). The engine is the un-vendored `gkr` crate; the per-node
+ *      protocol restated here is in DESIGN.md section 3 (parity with the crate's bytes is unpinned). Node ids are returned in
+ *      insertion order, as `circuit.insert` does. ------------------------------------------------------------------------- */
+int hg_circuit_new(hg_ctx* ctx, hg_circuit** out);
+void hg_circuit_free(hg_circuit* c);
+int hg_circuit_insert_input(hg_circuit* c, size_t log2_size, size_t num_reps, int* out_id);   /* InputNode::new */
+int hg_circuit_insert_fft(hg_circuit* c, size_t log2_size, int inverse, int* out_id);          /* FftNode::forward / ::inverse */
+int hg_circuit_insert_lasso(hg_circuit* c, hg_lasso_node* node, int* out_id);                  /* LassoNode (ownership stays with the caller) */
+/* VanillaNode::new(input_arity, log2_sub_input_size, gates, num_reps); gates in CSR form:
+ *   gate g = consts[g] (if has_const[g]) + sum_{e in [add_ptr[g], add_ptr[g+1])} add_coef[e] * input[add_input[e]][rep*2^sub + add_wire[e]]
+ *                                        + sum_{e in [mul_ptr[g], mul_ptr[g+1])} mul_coef[e] * input[mul_in0[e]][.. + mul_w0[e]] * input[mul_in1[e]][.. + mul_w1[e]]
+ * Supported on the device: layers with additive gates only, and the element-wise product layer (VanillaGate::mul((0,i),(1,i))). */
+int hg_circuit_insert_vanilla(hg_circuit* c, size_t input_arity, size_t log2_sub_input_size, size_t num_reps, size_t n_gates, const uint8_t* has_const,
+                              const uint64_t* consts, const uint64_t* add_ptr, const uint64_t* add_coef, const uint32_t* add_input,
+                              const uint64_t* add_wire, const uint64_t* mul_ptr, const uint64_t* mul_coef, const uint32_t* mul_in0, const uint64_t* mul_w0,
+                              const uint32_t* mul_in1, const uint64_t* mul_w1, int* out_id);
+int hg_circuit_connect(hg_circuit* c, int from, int to);                                       /* circuit.connect(from, to) */
+/* circuit.evaluate(inputs): device pointers for the input nodes in insertion order; node values stay on the device */
+int hg_circuit_evaluate(hg_circuit* c, const void* const* d_inputs, size_t n_inputs);
+int hg_circuit_node_value(hg_circuit* c, int id, const void** d_ptr, size_t* len);
+/* gkr::prove_gkr(&circuit, &values, &output_claims, &mut transcript): one claim per output node (insertion order); point i has
+ * point_lens[i] extension elements (concatenated in points_ext), values_ext one extension element per claim. The claims that
+ * reach the input nodes are read back with the hg_gkr_input_claim* getters (what verify() checks, :512-516). */
+int hg_gkr_prove(hg_circuit* c, size_t n_output_claims, const size_t* point_lens, const uint64_t* points_ext, const uint64_t* values_ext,
+                 hg_transcript* t, int mode);
+size_t hg_gkr_num_inputs(const hg_circuit* c);
+size_t hg_gkr_num_input_claims(const hg_circuit* c, size_t input);
+size_t hg_gkr_input_claim_num_vars(const hg_circuit* c, size_t input, size_t k);
+int hg_gkr_input_claim(const hg_circuit* c, size_t input, size_t k, uint64_t* point_ext, uint64_t* value_ext);
 
 /* field self-test kernel: out[i] = a[i] (op) b[i] on extension elements, op 0 add 1 sub 2 mul (device arithmetic check) */
 int hg_field_selftest(hg_ctx* ctx, int op, const uint64_t* a_ext, const uint64_t* b_ext, size_t n, uint64_t* out_ext);
