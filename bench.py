@@ -22,16 +22,18 @@ sys.path.insert(0, ROOT)
 METRIC = "gkr_prove_proofs_per_sec"
 UNIT = "proofs/s"
 DEFAULT_CONFIG = "32768_16x59_65537"
+LAST_WITNESS = None
 
 
 def workload_desc(name, P, nv, m):
     return {
-        "workload": f"lasso_node.prove_claim_reduction n={P.N} k={P.K} goldilocks/ext2 (num_vars={nv}, memories={m}, C=4, M=65536), one proof per step per GPU",
-        "scope": "Lasso range-check node = collation sumcheck + 2 grand-product memory-checking trees + openings (README: 76% of the reference's GKR prove); "
-                 "Vanilla/FFT layers not in the timed region yet",
+        "workload": f"gkr::prove_gkr of the BFV SK-encryption circuit n={P.N} k={P.K} goldilocks/ext2: Lasso node (num_vars={nv}, memories={m}, C=4, M=65536) "
+                    f"+ {2 * P.K + 1} FFT layers of 2^{P.log2_size} + {P.K} product layers + the Vanilla relay/scale/sum layers; one proof per step per GPU",
+        "scope": "the reference's `GKR prove` span (sk_encryption_circuit.rs:455-457): every node's claim reduction incl. LassoNode::polynomialize; "
+                 "circuit values resident on the device (witness gen = circuit.evaluate is outside the span, as in the reference)",
         "params": name,
         "parallelism": "one independent proof instance per GPU, no data-path collective",
-        "cache": "working set ~3.5 GB per proof >> 126 MB L2, no explicit flush between steps",
+        "cache": "working set ~4 GB per proof >> 126 MB L2, no explicit flush between steps",
     }
 
 
@@ -87,6 +89,8 @@ def make_case(name, seed):
     P = params.PARAMS[name]
     args = witness.synth_witness(P, seed)
     inp = np.array(witness.lasso_inputs(P, args), dtype=np.uint64)
+    global LAST_WITNESS
+    LAST_WITNESS = witness.get_inputs(P, args)
     return P, inp, witness.lasso_lookup_bounds(P), witness.lasso_lookup_segments(P), witness.lasso_num_vars(P)
 
 
@@ -99,7 +103,8 @@ def oracle_case(hgo, bounds, segs):
 
 def run_reference(args):
     """CPU arm: the reference's own implementation cannot be built here (Rust nightly + un-vendored git deps),
-    so this times the oracle port (oracle/protocol.hpp, OpenMP over all host cores) on the same workload."""
+    so this times the oracle port (oracle/protocol.hpp + oracle/gkr.hpp, OpenMP over all host cores) on the same workload:
+    the `GKR prove` span with the circuit already evaluated."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -109,17 +114,19 @@ def run_reference(args):
     opp, rows = oracle_case(hgo, bounds, segs)
     hgo.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
     cores = hgo.num_threads()
+    ins, ct0is = LAST_WITNESS
+    prep = hgo.bfv_prepare(0, P, ins, ct0is)
     t0 = time.perf_counter()
-    hgo.lasso_prove(0, opp, nv, rows, inp)
+    hgo.bfv_prove_prepared(prep)
     t1 = time.perf_counter() - t0
     budget = 240.0
     steps = max(1, min(args.steps, int(budget / max(t1, 1e-3)) - 1))
     warm = 0 if steps < args.steps else max(0, min(args.warmup - 1, 1))
     for _ in range(warm):
-        hgo.lasso_prove(0, opp, nv, rows, inp)
+        hgo.bfv_prove_prepared(prep)
     t0 = time.perf_counter()
     for _ in range(steps):
-        hgo.lasso_prove(0, opp, nv, rows, inp)
+        hgo.bfv_prove_prepared(prep)
     dt = time.perf_counter() - t0
     v = steps / dt
     sample = f"{steps} full proofs of the same workload (first call {t1:.1f}s used as warm-up" + (f"; --steps {args.steps} capped to fit ~4 min" if steps < args.steps else "") + ")"
@@ -149,13 +156,29 @@ def run_ours(args):
     api.lib()
 
     P, inp, bounds, segs, nv = make_case(args.config, seed=rank)
+    ins, ct0is = LAST_WITNESS
     ctx = api.Context(local)
-    pp = api.LassoPreprocessing.preprocess(bounds)
-    node = api.LassoNode(ctx, pp, nv, segs)
-    d_inp = api.DeviceBuffer.from_numpy(ctx, inp)
-    pinned = torch.empty(inp.size, dtype=torch.int64).pin_memory()
-    h_inp = pinned.numpy().view(np.uint64)
-    h_inp[:] = inp
+    prover = api.BfvSkEncryptProver(ctx, P)                       # setup + configure (sk_encryption_circuit.rs:319-363)
+    pp, node = prover.pp, prover.lasso
+    flat = [ins["s"], ins["e"], ins["k1"]] + list(ins["ais"]) + list(ins["r1is"]) + [ins["r2is"]]
+    host_np = [np.array(v, dtype=np.uint64) for v in flat]
+    n_in_elems = sum(v.size for v in host_np)
+    pinned = torch.empty(n_in_elems, dtype=torch.int64).pin_memory()
+    h_all = pinned.numpy().view(np.uint64)
+    h_views, off = [], 0
+    for v in host_np:
+        h_all[off:off + v.size] = v
+        h_views.append(h_all[off:off + v.size])
+        off += v.size
+    dev_inputs = [api.DeviceBuffer.from_numpy(ctx, v) for v in host_np]
+    ct_np = np.array(ct0is, dtype=np.uint64)
+    d_ct = api.DeviceBuffer.from_numpy(ctx, ct_np)
+    prover.circuit.evaluate(dev_inputs)                            # witness gen (outside the `GKR prove` span, :439-453)
+    tr0 = api.Keccak256Transcript()
+    point = tr0.squeeze_challenges(prover.ct0is_log2_size)         # :445
+    value = api.mle_eval_batch(ctx, d_ct, 1, prover.ct0is_log2_size, point)[0]   # :446
+    el = point.shape[1]
+    out_claims = [(np.zeros((0, el), np.uint64), np.zeros(el, np.uint64)), (point, value)]
     ext = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
 
     def barrier():
@@ -164,19 +187,27 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def step_resident():
+        """the `GKR prove` span: gkr::prove_gkr on device-resident circuit values"""
         tr = api.Keccak256Transcript()
-        node.prove_claim_reduction(d_inp, tr, api.MODE_PREFETCH, n_inputs=inp.size)
+        tr.squeeze_challenges(prover.ct0is_log2_size)
+        prover.circuit.prove_gkr(out_claims, tr, api.MODE_PREFETCH)
         return tr
 
     def step_e2e():
+        """BfvEncrypt::prove from HOST vectors: H2D of the inputs, circuit.evaluate, output claim, prove_gkr, proof bytes on the host"""
+        for buf, hv in zip(dev_inputs, h_views):
+            buf.upload(hv)
         tr = api.Keccak256Transcript()
-        node.prove_claim_reduction(h_inp, tr, api.MODE_PREFETCH)
+        prover.circuit.evaluate(dev_inputs)
+        pt = tr.squeeze_challenges(prover.ct0is_log2_size)
+        val = api.mle_eval_batch(ctx, d_ct, 1, prover.ct0is_log2_size, pt)[0]
+        prover.circuit.prove_gkr([out_claims[0], (pt, val)], tr, api.MODE_PREFETCH)
         return tr.into_proof()
 
     for _ in range(max(args.warmup, 3)):
         tr = step_resident()
     proof_len = len(tr.into_proof())
-    host_phases = node.timing()
+    host_phases = None
     l0 = ctx.launch_count
     step_resident()
     launches_per_step = ctx.launch_count - l0
@@ -254,9 +285,9 @@ def run_ours(args):
             from oracle import hgo
             hgo.build()
             hgo.set_num_threads(os.cpu_count() or 1)
-            opp, rows = oracle_case(hgo, bounds, segs)
+            sess = hgo.bfv_prepare(0, P, ins, ct0is)
             t0 = time.perf_counter()
-            oproof, *_ = hgo.lasso_prove(0, opp, nv, rows, inp)
+            oproof = sess.prove()
             dt = time.perf_counter() - t0
             same = oproof == step_e2e()
             cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": hgo.num_threads(), "kind": "port",
@@ -264,13 +295,13 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
                 "data": "synthetic", "config": workload_desc(args.config, P, nv, pp.num_memories), "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(inp.nbytes + node_chal_bytes(nv)),
-                        "d2h_bytes_per_step": int(proof_len + 64 * nv)},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_in_elems * 8 + node_chal_bytes(nv) + 4096),
+                        "d2h_bytes_per_step": int(proof_len * 2)},
                 "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
                 "wall_ms_per_step": wall_ms / args.steps, "proof_bytes": proof_len, "host_phases_us": host_phases, "roofline": roofline, "cpu_baseline": cpu}
     barrier()
+    prover.circuit.free()
     node.free()
-    d_inp.free()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -180,6 +180,12 @@ int bfv_prove_t(int log2_size, int K, const uint64_t* qis, const uint64_t* k0is,
     memcpy(proof, pr.data(), pr.size());
     return 0;
 }
+template <class F> struct BfvSession {
+    BfvEncrypt<F> bfv;
+    std::vector<std::vector<F>> inputs, values;
+    std::vector<F> ct0is;
+    BfvSession(const BfvParams<F>& P) : bfv(P) {}
+};
 template <class F> int field_op_t(int op, const uint64_t* a, const uint64_t* b, uint64_t* out) {
     typedef typename ExtOf<F>::type E;
     E x = load_ext<F, E>(a), y = load_ext<F, E>(b), z;
@@ -189,7 +195,7 @@ template <class F> int field_op_t(int op, const uint64_t* a, const uint64_t* b, 
 }
 }  // namespace
 
-#define GUARD(body) try { body } catch (const std::exception& e) { g_err = e.what(); return 1; }
+#define GUARD(...) try { __VA_ARGS__ } catch (const std::exception& e) { g_err = e.what(); return 1; }
 
 extern "C" {
 const char* hgo_last_error() { return g_err.c_str(); }
@@ -277,6 +283,34 @@ int hgo_bfv_prove(int field, int log2_size, int K, const uint64_t* qis, const ui
                   const uint64_t* r2is, const uint64_t* ct0is, uint8_t* proof, size_t cap, size_t* len, int verify_only) {
     GUARD(return field == 0 ? bfv_prove_t<Gl>(log2_size, K, qis, k0is, r1b, r2b, sb, eb, k1b, s, e, k1, ais, r1is, r2is, ct0is, proof, cap, len, verify_only)
                             : bfv_prove_t<Fr>(log2_size, K, qis, k0is, r1b, r2b, sb, eb, k1b, s, e, k1, ais, r1is, r2is, ct0is, proof, cap, len, verify_only);)
+}
+// session API for timing the reference's `GKR prove` span alone: circuit built and evaluated once (witness gen), then
+// hgo_bfv_session_prove = squeeze output point + output MLE + prove_gkr (sk_encryption_circuit.rs:444-457)
+void* hgo_bfv_session_new(int field, int log2_size, int K, const uint64_t* qis, const uint64_t* k0is, const uint64_t* r1b, const uint64_t* r2b, uint64_t sb,
+                          uint64_t eb, uint64_t k1b, const uint64_t* s, const uint64_t* e, const uint64_t* k1, const uint64_t* ais, const uint64_t* r1is,
+                          const uint64_t* r2is, const uint64_t* ct0is) {
+    try {
+        if (field != 0) { g_err = "session API: Goldilocks only"; return nullptr; }
+        auto* S = new BfvSession<Gl>(make_params<Gl>(log2_size, K, qis, k0is, r1b, r2b, sb, eb, k1b));
+        S->inputs = load_inputs<Gl>(log2_size, K, s, e, k1, ais, r1is, r2is);
+        S->ct0is = load_base<Gl>(ct0is, (size_t)K << log2_size);
+        S->values = S->bfv.circuit.evaluate(S->inputs);
+        return S;
+    } catch (const std::exception& ex) { g_err = ex.what(); return nullptr; }
+}
+void hgo_bfv_session_free(void* h) { delete (BfvSession<Gl>*)h; }
+int hgo_bfv_session_prove(void* h, uint8_t* proof, size_t cap, size_t* len) {
+    GUARD(
+        auto* S = (BfvSession<Gl>*)h;
+        Transcript<Gl> tr;
+        std::vector<Gl2> point = tr.squeeze_n(S->bfv.ct0is_log2_size());
+        Gl2 value = mle_evaluate<Gl2, Gl>(S->ct0is, point);
+        std::vector<EvalClaim<Gl>> oc = {{{}, Gl2::zero()}, {point, value}};
+        S->bfv.circuit.prove_gkr(S->values, oc, tr);
+        *len = tr.stream.size();
+        if (tr.stream.size() > cap) { g_err = "proof buffer too small"; return 2; }
+        memcpy(proof, tr.stream.data(), tr.stream.size());
+        return 0;)
 }
 int hgo_subtable(int field, int full, uint64_t bound, int log2M, const uint64_t* point, uint64_t* table_out, uint64_t* mle_out) {
     GUARD(return field == 0 ? subtable_t<Gl>(full, bound, log2M, point, table_out, mle_out) : subtable_t<Fr>(full, bound, log2M, point, table_out, mle_out);)

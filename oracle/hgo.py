@@ -63,6 +63,10 @@ def lib():
         L.hgo_ntt.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t]
         L.hgo_bfv_eval.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_uint64] * 3 + [C.c_void_p] * 9
         L.hgo_bfv_prove.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_uint64] * 3 + [C.c_void_p] * 8 + [C.c_size_t, C.c_void_p, C.c_int]
+        L.hgo_bfv_session_new.restype = C.c_void_p
+        L.hgo_bfv_session_new.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_uint64] * 3 + [C.c_void_p] * 7
+        L.hgo_bfv_session_free.argtypes = [C.c_void_p]
+        L.hgo_bfv_session_prove.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.hgo_field_op.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
@@ -310,3 +314,34 @@ def bfv_verify(field, P, ins, ct0is, proof: bytes):
     ln = C.c_size_t(buf.size)
     _chk(lib().hgo_bfv_prove(field, P.log2_size, P.K, _p(a["q"]), _p(a["k0"]), _p(a["r1b"]), _p(a["r2b"]), P.S_BOUND, P.E_BOUND, P.K1_BOUND,
                              _p(a["s"]), _p(a["e"]), _p(a["k1"]), _p(a["ais"]), _p(a["r1is"]), _p(a["r2is"]), _p(a["ct"]), _p(buf), buf.size, C.byref(ln), 1))
+
+
+class BfvSession:
+    """Circuit built and evaluated once (the reference's witness gen); prove() times only the `GKR prove` span."""
+
+    def __init__(self, field, P, ins, ct0is):
+        _, a = _bfv_args(field, P, ins, ct0is)
+        self.h = lib().hgo_bfv_session_new(field, P.log2_size, P.K, _p(a["q"]), _p(a["k0"]), _p(a["r1b"]), _p(a["r2b"]), P.S_BOUND, P.E_BOUND, P.K1_BOUND,
+                                           _p(a["s"]), _p(a["e"]), _p(a["k1"]), _p(a["ais"]), _p(a["r1is"]), _p(a["r2is"]), _p(a["ct"]))
+        if not self.h:
+            raise OracleError(lib().hgo_last_error().decode())
+        self.buf = np.zeros(1 << 24, np.uint8)
+
+    def prove(self) -> bytes:
+        ln = C.c_size_t(0)
+        _chk(lib().hgo_bfv_session_prove(self.h, _p(self.buf), self.buf.size, C.byref(ln)))
+        return self.buf[: ln.value].tobytes()
+
+    def __del__(self):
+        try:
+            lib().hgo_bfv_session_free(self.h)
+        except Exception:
+            pass
+
+
+def bfv_prepare(field, P, ins, ct0is):
+    return BfvSession(field, P, ins, ct0is)
+
+
+def bfv_prove_prepared(session) -> bytes:
+    return session.prove()
