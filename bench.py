@@ -38,7 +38,8 @@ def workload_desc(name, P, nv, m):
 
 
 class ClockSampler:
-    """Samples SM clock and throttle reasons DURING the timed region (pynvml, 20 ms period)."""
+    """Samples SM clock and throttle reasons DURING the timed region (NVML every 100 ms; faster polling measurably slows the
+    launch path through the driver lock)."""
 
     def __init__(self, index):
         self.index, self.samples, self.reasons, self.max_mhz, self._stop, self._t = index, [], set(), None, threading.Event(), None
@@ -67,7 +68,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.1)
 
     def start(self):
         if self.nv:
@@ -207,7 +208,7 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         tr = step_resident()
     proof_len = len(tr.into_proof())
-    host_phases = None
+    host_phases = prover.circuit.timing()
     l0 = ctx.launch_count
     step_resident()
     launches_per_step = ctx.launch_count - l0
@@ -317,7 +318,7 @@ def node_chal_bytes(nv, lm=16):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=DEFAULT_CONFIG)

@@ -31,7 +31,7 @@ SYMBOLS = [
     "hg_lasso_node_log2_input_size", "hg_lasso_node_device_bytes", "hg_lasso_node_prove", "hg_lasso_node_download_polys",
     "hg_lasso_node_num_chunks", "hg_lasso_node_timing", "hg_sumcheck_prove", "hg_mle_eval_batch", "hg_ntt", "hg_bfv_evaluate", "hg_field_selftest",
     "hg_circuit_new", "hg_circuit_free", "hg_circuit_insert_input", "hg_circuit_insert_fft", "hg_circuit_insert_lasso", "hg_circuit_insert_vanilla",
-    "hg_circuit_connect", "hg_circuit_evaluate", "hg_circuit_node_value", "hg_gkr_prove", "hg_gkr_num_inputs", "hg_gkr_num_input_claims",
+    "hg_circuit_connect", "hg_circuit_evaluate", "hg_circuit_node_value", "hg_gkr_prove", "hg_gkr_timing", "hg_gkr_num_challenges", "hg_gkr_num_inputs", "hg_gkr_num_input_claims",
     "hg_gkr_input_claim_num_vars", "hg_gkr_input_claim",
 ]
 
@@ -117,6 +117,10 @@ def lib():
         for f in ("hg_gkr_num_inputs",):
             getattr(L, f).argtypes = [vp]
             getattr(L, f).restype = sz
+        L.hg_gkr_timing.argtypes = [vp, vp]
+        L.hg_gkr_timing.restype = None
+        L.hg_gkr_num_challenges.argtypes = [vp]
+        L.hg_gkr_num_challenges.restype = sz
         L.hg_gkr_num_input_claims.argtypes = [vp, sz]
         L.hg_gkr_num_input_claims.restype = sz
         L.hg_gkr_input_claim_num_vars.argtypes = [vp, sz, sz]
@@ -538,6 +542,13 @@ class Circuit:
                 cl.append((pt, v))
             out.append(cl)
         return out
+
+    def timing(self):
+        out = np.zeros(6, np.float64)
+        lib().hg_gkr_timing(self.h, _p(out))
+        d = dict(zip(("witness_enqueue_us", "challenges_us", "protocol_walk_us", "layer_enqueue_us", "gpu_wait_us", "serialise_us"), (float(x) for x in out)))
+        d["ext_challenges"] = int(lib().hg_gkr_num_challenges(self.h))
+        return d
 
     def free(self):
         if self.h:

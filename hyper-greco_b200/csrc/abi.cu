@@ -481,6 +481,8 @@ int hg_gkr_prove(hg_circuit* c, size_t n_output_claims, const size_t* point_lens
         c->input_claims = c->gl->prove(*t->gl, mode == HG_MODE_INTERACTIVE ? kModeInteractive : kModePrefetch, c->ctx->wire, oc);
     })
 }
+void hg_gkr_timing(const hg_circuit* c, double* out_us6) { for (int i = 0; i < 6; i++) out_us6[i] = c->gl->timing()[i]; }
+size_t hg_gkr_num_challenges(const hg_circuit* c) { return c->gl->total_challenges(); }
 size_t hg_gkr_num_inputs(const hg_circuit* c) { return c->input_claims.size(); }
 size_t hg_gkr_num_input_claims(const hg_circuit* c, size_t input) { return input < c->input_claims.size() ? c->input_claims[input].size() : 0; }
 size_t hg_gkr_input_claim_num_vars(const hg_circuit* c, size_t input, size_t k) { return c->input_claims.at(input).at(k).point.size(); }

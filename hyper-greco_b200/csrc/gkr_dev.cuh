@@ -120,6 +120,10 @@ template <class FP> class GkrCircuitDev {
         topo_.clear();
     }
     size_t num_nodes() const { return nodes_.size(); }
+    // host phases of the last prove, microseconds: [witness enqueue, squeeze + upload challenges, protocol walk (+ Lasso enqueue),
+    // batched layer enqueue, wait for the GPU, serialise]
+    const double* timing() const { return timing_; }
+    size_t total_challenges() const { return total_chal_; }
     size_t node_out_len(int id) const { return nodes_.at(id)->out_len; }
     const B* node_value(int id) const { return nodes_.at(id)->value_ptr; }
 
@@ -162,6 +166,8 @@ template <class FP> class GkrCircuitDev {
                                                const std::vector<InputClaim>& output_claims) {
         if (!evaluated_) throw std::runtime_error("prove_gkr: evaluate the circuit first");
         cudaStream_t s = ctx_->stream;
+        auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double t0 = now();
         plan();
         Channel<FP>& ch = *ch_;
         // Lasso witness kernels need no challenge: enqueue them first so that Keccak squeezing overlaps them
@@ -169,7 +175,9 @@ template <class FP> class GkrCircuitDev {
             const Node& p = *nodes_[n->preds.at(0)];
             n->lasso->enqueue_witness(p.value_ptr, n->lasso->num_rows(), wo);
         }
+        const double t1 = now();
         ch.begin(&tr, mode, total_chal_);
+        const double t2 = now();
         struct Claim { bool by_index; size_t idx; std::vector<X> point_host; int nvars; std::shared_ptr<X> value; };
         std::vector<std::vector<Claim>> claims(nodes_.size());
         // output claims: their points live in extra device slots after the challenges
@@ -259,6 +267,7 @@ template <class FP> class GkrCircuitDev {
             }
             jobs.push_back(job);
         }
+        const double t3 = now();
         if (mode == kModePrefetch) {
             prepare_jobs(ch, jobs, wo);
             int maxv = 0;
@@ -266,7 +275,9 @@ template <class FP> class GkrCircuitDev {
             for (int r = 0; r < maxv; r++) launch_round(ch, jobs, r);
             launch_finals(ch, jobs);
         }
-        ch.flush();
+        const double t4 = now();
+        ch.flush(&timing_[4], &timing_[5]);
+        timing_[0] = t1 - t0; timing_[1] = t2 - t1; timing_[2] = t3 - t2; timing_[3] = t4 - t3;
         if (ch.chal_used() != total_chal_) throw std::runtime_error("prove_gkr: challenge count mismatch");
         std::vector<std::vector<InputClaim>> res;
         for (size_t i = 0; i < nodes_.size(); i++) {
@@ -354,7 +365,7 @@ template <class FP> class GkrCircuitDev {
         total_chal_ = chal;
         ch_.reset(new Channel<FP>(ctx_, chal + 8, msg + 64));
         d_eq_.alloc(eq_elems + 64);
-        d_partials_.alloc(((size_t)ctx_->sm_count * 4 + 8) * 4 * (items + 4));
+        d_partials_.alloc(((size_t)ctx_->sm_count * 16 + 8) * 4 * (items + 4));
         d_counters_.alloc(items + 64);
         HG_CUDA(cudaMemset(d_counters_.p, 0, d_counters_.bytes()));
         h_desc_.alloc(1 << 20);
@@ -382,6 +393,9 @@ template <class FP> class GkrCircuitDev {
         size_t max_claims = 0;
         struct EqRef { X* lo; X* hi; int lo_bits; };
         std::vector<std::vector<EqRef>> eqs(jobs.size());
+        std::vector<EqSplitItem<FP>> splits;
+        int split_blk = 0;
+        size_t split_bytes = 0;
         for (size_t q = 0; q < jobs.size(); q++) {
             const Job& j = jobs[q];
             Node& n = *nodes_[j.node];
@@ -393,10 +407,14 @@ template <class FP> class GkrCircuitDev {
                 X* elo = d_eq_.p + eq_off_;
                 X* ehi = elo + ((size_t)1 << lo);
                 eq_off_ += need;
-                HG_K(ctx_, KC_GKR_PREP, need * sizeof(X), k_eq_split<FP><<<(unsigned)((need + HG_BLOCK - 1) / HG_BLOCK), HG_BLOCK, 0, s>>>(j.points[t], nvw, lo, elo, ehi));
+                EqSplitItem<FP> si; si.point = j.points[t]; si.eq_lo = elo; si.eq_hi = ehi; si.nv = nvw; si.lo_bits = lo; si.blk_start = split_blk;
+                split_blk += (int)((need + HG_BLOCK - 1) / HG_BLOCK);
+                split_bytes += need * sizeof(X);
+                splits.push_back(si);
                 eqs[q].push_back({elo, ehi, lo});
             }
         }
+        if (!splits.empty()) HG_K(ctx_, KC_GKR_PREP, split_bytes, k_eq_split_multi<FP><<<split_blk, HG_BLOCK, 0, s>>>(stage(splits), (int)splits.size()));
         for (size_t t = 0; t < max_claims; t++) {
             std::vector<EqAccItem<FP>> items;
             int blk = 0;
@@ -444,15 +462,13 @@ template <class FP> class GkrCircuitDev {
             const bool inv = kv.first.second != 0;
             const size_t N = (size_t)1 << lg, cnt = kv.second.size();
             if (d_planes_.n < 2 * N * cnt) { HG_CUDA(cudaStreamSynchronize(s)); d_planes_.alloc(2 * N * cnt); }
-            for (size_t q = 0; q < cnt; q++) {
-                Node& n = *nodes_[kv.second[q]];
-                HG_K(ctx_, KC_GKR_PREP, N * sizeof(X) * 2, k_ext_split<FP><<<(unsigned)((N + 255) / 256), 256, 0, s>>>(n.W.p, N, d_planes_.p + (2 * q) * N, d_planes_.p + (2 * q + 1) * N));
-            }
+            std::vector<X*> wt, at;
+            for (size_t q = 0; q < cnt; q++) { wt.push_back(nodes_[kv.second[q]]->W.p); at.push_back(nodes_[kv.second[q]]->A.p); }
+            X* const* d_wt = stage(wt);
+            X* const* d_at = stage(at);
+            HG_K(ctx_, KC_GKR_PREP, N * cnt * sizeof(X) * 2, k_ext_split<FP><<<dim3((unsigned)((N + 255) / 256), (unsigned)cnt), 256, 0, s>>>(d_wt, N, d_planes_.p));
             ntt_->run(d_planes_.p, lg, inv, 2 * cnt);
-            for (size_t q = 0; q < cnt; q++) {
-                Node& n = *nodes_[kv.second[q]];
-                HG_K(ctx_, KC_GKR_PREP, N * sizeof(X) * 2, k_ext_merge<FP><<<(unsigned)((N + 255) / 256), 256, 0, s>>>(d_planes_.p + (2 * q) * N, d_planes_.p + (2 * q + 1) * N, N, n.A.p));
-            }
+            HG_K(ctx_, KC_GKR_PREP, N * cnt * sizeof(X) * 2, k_ext_merge<FP><<<dim3((unsigned)((N + 255) / 256), (unsigned)cnt), 256, 0, s>>>(d_planes_.p, N, d_at));
         }
         (void)wo;
     }
@@ -483,7 +499,7 @@ template <class FP> class GkrCircuitDev {
             }
             it.msg = ch.d_msg(j.msg_off + 4 * (size_t)r);
             const size_t npairs = r == 0 ? it.n_in / 2 : it.n_in / 4;
-            size_t b = std::max<size_t>(1, std::min<size_t>((npairs + HG_BLOCK - 1) / HG_BLOCK, (size_t)ctx_->sm_count * 4));
+            size_t b = std::max<size_t>(1, std::min<size_t>((npairs + HG_BLOCK - 1) / HG_BLOCK, (size_t)ctx_->sm_count * 16));
             it.nblk = (int)b; it.bx = (int)b; it.blk_start = blk;
             blk += it.nblk;
             it.partials = d_partials_.p + part_off;
@@ -547,6 +563,7 @@ template <class FP> class GkrCircuitDev {
         if (!copies.empty()) HG_K(ctx_, KC_GKR_SC, copies.size() * 64, k_copy_items<FP><<<(unsigned)copies.size(), 32, 0, s>>>(stage(copies)));
     }
 
+    double timing_[6] = {0, 0, 0, 0, 0, 0};
     DeviceCtx* ctx_;
     NttEngine<FP>* ntt_;
     std::vector<std::unique_ptr<Node>> nodes_;

@@ -33,6 +33,26 @@ __global__ void k_vanilla_eval(VanillaFwd w, const typename FP::B* __restrict__ 
     out[t] = v;
 }
 
+// ---- eq factor tables of every (node, claim) pair in one launch
+template <class FP> struct EqSplitItem { const typename FP::X* point; typename FP::X* eq_lo; typename FP::X* eq_hi; int nv, lo_bits, blk_start; };
+template <class FP> __global__ void k_eq_split_multi(const EqSplitItem<FP>* __restrict__ items, int nitems) {
+    typedef typename FP::X X;
+    const EqSplitItem<FP> it = items[find_item(items, nitems)];
+    const size_t t = (size_t)(blockIdx.x - it.blk_start) * blockDim.x + threadIdx.x;
+    const size_t nlo = (size_t)1 << it.lo_bits, nhi = (size_t)1 << (it.nv - it.lo_bits);
+    if (t >= nlo + nhi) return;
+    const bool hi = t >= nlo;
+    const size_t k = hi ? t - nlo : t;
+    const int first = hi ? it.lo_bits : 0, last = hi ? it.nv : it.lo_bits;
+    X acc = FP::x_one();
+    for (int i = first; i < last; i++) {
+        X r = it.point[i];
+        X f = ((k >> (i - first)) & 1) ? r : FP::x_sub(FP::x_one(), r);
+        acc = FP::fmul(acc, f);
+    }
+    (hi ? it.eq_hi : it.eq_lo)[k] = acc;
+}
+
 // ---- W += alpha^t * eq(z_t, .) for every (node, claim) pair; eq via two factor tables built by k_eq_split
 template <class FP> struct EqAccItem {
     const typename FP::X* eq_lo; const typename FP::X* eq_hi;   // of this claim
@@ -42,9 +62,7 @@ template <class FP> struct EqAccItem {
 };
 template <class FP> __global__ void k_eq_accumulate(const EqAccItem<FP>* __restrict__ items, int nitems) {
     typedef typename FP::X X;
-    int k = 0;
-    while (k + 1 < nitems && (int)blockIdx.x >= items[k + 1].blk_start) k++;
-    const EqAccItem<FP> it = items[k];
+    const EqAccItem<FP> it = items[find_item(items, nitems)];
     const size_t i = (size_t)(blockIdx.x - it.blk_start) * blockDim.x + threadIdx.x;
     if (i >= it.n) return;
     X e = FP::fmul(it.eq_lo[i & (((size_t)1 << it.lo_bits) - 1)], it.eq_hi[i >> it.lo_bits]);
@@ -66,16 +84,19 @@ __global__ void k_wiring_gather(const u64* __restrict__ rev_ptr, const u32* __re
 }
 
 // ---- split / merge of extension tables into base planes (the FFT-matrix weights are the transform of W, plane by plane)
-template <class FP> __global__ void k_ext_split(const typename FP::X* __restrict__ in, size_t n, typename FP::B* __restrict__ p0, typename FP::B* __restrict__ p1) {
+// tabs[q] = extension table of node q (n elements); planes = [2q][n] | [2q+1][n]
+template <class FP> __global__ void k_ext_split(typename FP::X* const* __restrict__ tabs, size_t n, typename FP::B* __restrict__ planes) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    typename FP::X v = in[i];
-    p0[i] = v.c0; p1[i] = v.c1;
+    const size_t q = blockIdx.y;
+    typename FP::X v = tabs[q][i];
+    planes[(2 * q) * n + i] = v.c0; planes[(2 * q + 1) * n + i] = v.c1;
 }
-template <class FP> __global__ void k_ext_merge(const typename FP::B* __restrict__ p0, const typename FP::B* __restrict__ p1, size_t n, typename FP::X* __restrict__ out) {
+template <class FP> __global__ void k_ext_merge(const typename FP::B* __restrict__ planes, size_t n, typename FP::X* const* __restrict__ tabs) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    out[i] = gl2_make(p0[i], p1[i]);
+    const size_t q = blockIdx.y;
+    tabs[q][i] = gl2_make(planes[(2 * q) * n + i], planes[(2 * q + 1) * n + i]);
 }
 
 // ---- product sumcheck rounds, all nodes per launch. msg slots per round: [h(0), h(inf), h(-1), h(1)] (h(-1) only for nt = 2,
@@ -92,9 +113,7 @@ template <class FP, class TIN, bool FOLD>
 __global__ void __launch_bounds__(HG_BLOCK) k_prod_round_multi(const ProdItem<FP>* __restrict__ items, int nitems) {
     typedef typename FP::X X;
     typedef typename std::conditional<FOLD, X, TIN>::type EL;
-    int k = 0;
-    while (k + 1 < nitems && (int)blockIdx.x >= items[k + 1].blk_start) k++;
-    const ProdItem<FP> it = items[k];
+    const ProdItem<FP> it = items[find_item(items, nitems)];
     const unsigned lb = blockIdx.x - it.blk_start;
     const TIN* tab = (const TIN*)it.tab_in;
     const size_t n_in = it.n_in, npairs = FOLD ? n_in / 4 : n_in / 2, n_out = n_in / 2;

@@ -264,11 +264,16 @@ __device__ __forceinline__ void block_reduce_finalize_ex(typename FP::X (&acc)[N
     }
 }
 
-template <class FP> __device__ __forceinline__ int gp_find_item(const GpItem<FP>* items, int nitems) {
-    int k = 0;
-    while (k + 1 < nitems && (int)blockIdx.x >= items[k + 1].blk_start) k++;
-    return k;
+// which item does this block belong to: largest k with items[k].blk_start <= blockIdx.x (binary search over <= ~70 items)
+template <class ITEM> __device__ __forceinline__ int find_item(const ITEM* items, int nitems) {
+    int lo = 0, hi = nitems - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((int)blockIdx.x >= items[mid].blk_start) lo = mid; else hi = mid - 1;
+    }
+    return lo;
 }
+template <class FP> __device__ __forceinline__ int gp_find_item(const GpItem<FP>* items, int nitems) { return find_item(items, nitems); }
 
 template <class FP, int U>
 __global__ void __launch_bounds__(HG_BLOCK, 2) k_gp_r0_multi(const GpItem<FP>* __restrict__ items, int nitems) {

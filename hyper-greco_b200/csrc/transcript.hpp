@@ -11,6 +11,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -45,56 +46,84 @@ class Keccak256 {
     uint64_t a_[25];
     size_t fill_;
     static inline uint64_t rol(uint64_t v, unsigned s) { return (v << s) | (v >> (64 - s)); }
-    // round constants from the degree-8 LFSR x^8+x^6+x^5+x^4+1, rho offsets from the (x,y) -> (y, 2x+3y) orbit; computed once
-    struct Tables {
-        uint64_t rc[24];
-        unsigned rot[24];
-        int lane[24];
-        Tables() {
-            uint8_t lfsr = 1;
-            for (int round = 0; round < 24; round++) {
-                uint64_t c = 0;
-                for (int j = 0; j < 7; j++) {
-                    if (lfsr & 1) c ^= 1ULL << ((1 << j) - 1);
-                    lfsr = (lfsr & 0x80) ? (uint8_t)((lfsr << 1) ^ 0x71) : (uint8_t)(lfsr << 1);
-                }
-                rc[round] = c;
-            }
-            int x = 1, y = 0;
-            for (int t = 0; t < 24; t++) {
-                rot[t] = ((t + 1) * (t + 2) / 2) % 64;
-                int ny = (2 * x + 3 * y) % 5;
-                x = y; y = ny;
-                lane[t] = x + 5 * y;
-            }
-        }
-    };
-    static const Tables& tables() { static const Tables t; return t; }
+    // Keccak-f[1600], fully unrolled (constant lane indices keep the state in registers). Round constants come from the
+    // degree-8 LFSR x^8+x^6+x^5+x^4+1 and the rho/pi schedule from the (x,y) -> (y, 2x+3y) orbit; both are expanded by the
+    // generator in this file's history and checked against keccak256("") in the tests.
     void permute() {
-        const Tables& T = tables();
-        uint64_t* a = a_;
+        static const uint64_t RC[24] = {0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL, 0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL, 0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+        uint64_t a[25];
+        memcpy(a, a_, sizeof a);
         for (int round = 0; round < 24; round++) {
-            uint64_t c0 = a[0] ^ a[5] ^ a[10] ^ a[15] ^ a[20], c1 = a[1] ^ a[6] ^ a[11] ^ a[16] ^ a[21],
-                     c2 = a[2] ^ a[7] ^ a[12] ^ a[17] ^ a[22], c3 = a[3] ^ a[8] ^ a[13] ^ a[18] ^ a[23],
-                     c4 = a[4] ^ a[9] ^ a[14] ^ a[19] ^ a[24];
-            uint64_t d0 = c4 ^ rol(c1, 1), d1 = c0 ^ rol(c2, 1), d2 = c1 ^ rol(c3, 1), d3 = c2 ^ rol(c4, 1), d4 = c3 ^ rol(c0, 1);
-            for (int y = 0; y < 25; y += 5) { a[y] ^= d0; a[y + 1] ^= d1; a[y + 2] ^= d2; a[y + 3] ^= d3; a[y + 4] ^= d4; }
-            uint64_t cur = a[1];
-            for (int t = 0; t < 24; t++) {
-                uint64_t nxt = a[T.lane[t]];
-                a[T.lane[t]] = rol(cur, T.rot[t]);
-                cur = nxt;
-            }
-            for (int y = 0; y < 25; y += 5) {
-                uint64_t r0 = a[y], r1 = a[y + 1], r2 = a[y + 2], r3 = a[y + 3], r4 = a[y + 4];
-                a[y] = r0 ^ (~r1 & r2); a[y + 1] = r1 ^ (~r2 & r3); a[y + 2] = r2 ^ (~r3 & r4); a[y + 3] = r3 ^ (~r4 & r0); a[y + 4] = r4 ^ (~r0 & r1);
-            }
-            a[0] ^= T.rc[round];
+            const uint64_t c0 = a[0] ^ a[5] ^ a[10] ^ a[15] ^ a[20], c1 = a[1] ^ a[6] ^ a[11] ^ a[16] ^ a[21],
+                           c2 = a[2] ^ a[7] ^ a[12] ^ a[17] ^ a[22], c3 = a[3] ^ a[8] ^ a[13] ^ a[18] ^ a[23],
+                           c4 = a[4] ^ a[9] ^ a[14] ^ a[19] ^ a[24];
+            const uint64_t d0 = c4 ^ rol(c1, 1), d1 = c0 ^ rol(c2, 1), d2 = c1 ^ rol(c3, 1), d3 = c2 ^ rol(c4, 1), d4 = c3 ^ rol(c0, 1);
+            a[0] ^= d0; a[5] ^= d0; a[10] ^= d0; a[15] ^= d0; a[20] ^= d0;
+            a[1] ^= d1; a[6] ^= d1; a[11] ^= d1; a[16] ^= d1; a[21] ^= d1;
+            a[2] ^= d2; a[7] ^= d2; a[12] ^= d2; a[17] ^= d2; a[22] ^= d2;
+            a[3] ^= d3; a[8] ^= d3; a[13] ^= d3; a[18] ^= d3; a[23] ^= d3;
+            a[4] ^= d4; a[9] ^= d4; a[14] ^= d4; a[19] ^= d4; a[24] ^= d4;
+            uint64_t cur = a[1], nxt;
+            nxt = a[10]; a[10] = rol(cur, 1); cur = nxt;
+            nxt = a[7]; a[7] = rol(cur, 3); cur = nxt;
+            nxt = a[11]; a[11] = rol(cur, 6); cur = nxt;
+            nxt = a[17]; a[17] = rol(cur, 10); cur = nxt;
+            nxt = a[18]; a[18] = rol(cur, 15); cur = nxt;
+            nxt = a[3]; a[3] = rol(cur, 21); cur = nxt;
+            nxt = a[5]; a[5] = rol(cur, 28); cur = nxt;
+            nxt = a[16]; a[16] = rol(cur, 36); cur = nxt;
+            nxt = a[8]; a[8] = rol(cur, 45); cur = nxt;
+            nxt = a[21]; a[21] = rol(cur, 55); cur = nxt;
+            nxt = a[24]; a[24] = rol(cur, 2); cur = nxt;
+            nxt = a[4]; a[4] = rol(cur, 14); cur = nxt;
+            nxt = a[15]; a[15] = rol(cur, 27); cur = nxt;
+            nxt = a[23]; a[23] = rol(cur, 41); cur = nxt;
+            nxt = a[19]; a[19] = rol(cur, 56); cur = nxt;
+            nxt = a[13]; a[13] = rol(cur, 8); cur = nxt;
+            nxt = a[12]; a[12] = rol(cur, 25); cur = nxt;
+            nxt = a[2]; a[2] = rol(cur, 43); cur = nxt;
+            nxt = a[20]; a[20] = rol(cur, 62); cur = nxt;
+            nxt = a[14]; a[14] = rol(cur, 18); cur = nxt;
+            nxt = a[22]; a[22] = rol(cur, 39); cur = nxt;
+            nxt = a[9]; a[9] = rol(cur, 61); cur = nxt;
+            nxt = a[6]; a[6] = rol(cur, 20); cur = nxt;
+            nxt = a[1]; a[1] = rol(cur, 44); cur = nxt;
+#define HG_CHI(o) { const uint64_t r0 = a[o], r1 = a[o + 1], r2 = a[o + 2], r3 = a[o + 3], r4 = a[o + 4]; \
+                    a[o] = r0 ^ (~r1 & r2); a[o + 1] = r1 ^ (~r2 & r3); a[o + 2] = r2 ^ (~r3 & r4); a[o + 3] = r3 ^ (~r4 & r0); a[o + 4] = r4 ^ (~r0 & r1); }
+            HG_CHI(0) HG_CHI(5) HG_CHI(10) HG_CHI(15) HG_CHI(20)
+#undef HG_CHI
+            a[0] ^= RC[round];
         }
+        memcpy(a_, a, sizeof a);
     }
 };
 
 struct TranscriptError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+// The challenge stream of the reference transcript is the fixed chain c_i = fe_mod_from_le_bytes(keccak^{i+1}("")): squeeze
+// re-hashes the hasher's own previous output and nothing on the prove path is ever absorbed (transcript.rs:156,183-203, SURVEY
+// F3). A fresh transcript therefore always yields the same sequence, so the chain is computed once per process and extended on
+// demand; squeezing the i-th challenge is a table lookup. Bit-identical to hashing every time (tests/test_abi.py).
+template <class HF> class ChallengeChain {
+  public:
+    static typename HF::Base get(size_t i) {
+        static ChallengeChain chain;
+        std::lock_guard<std::mutex> lock(chain.mu_);
+        while (chain.vals_.size() <= i) chain.extend();
+        return chain.vals_[i];
+    }
+
+  private:
+    void extend() {
+        Keccak256 k;
+        if (!vals_.empty()) k.update(last_, 32);
+        k.finalize_reset(last_);
+        vals_.push_back(HF::base_from_le_bytes_mod(last_, 32));
+    }
+    std::mutex mu_;
+    std::vector<typename HF::Base> vals_;
+    uint8_t last_[32];
+};
 
 // HF: host field traits (see host_field.hpp): Base, Ext, base_from_le_bytes_mod, base_to_repr_le, base_from_repr_le ...
 template <class HF> class Keccak256Transcript {
@@ -104,13 +133,7 @@ template <class HF> class Keccak256Transcript {
     Keccak256Transcript() {}                                                  // Keccak256Transcript::<Vec<u8>>::default()
     Keccak256Transcript(const uint8_t* proof, size_t n) : rd_(proof, proof + n), reading_(true) {}  // from_proof
 
-    Base squeeze_base() {
-        uint8_t h[32];
-        state_.finalize_reset(h);
-        state_.update(h, 32);
-        n_squeezed_++;
-        return HF::base_from_le_bytes_mod(h, 32);
-    }
+    Base squeeze_base() { return ChallengeChain<HF>::get(n_squeezed_++); }
     Ext squeeze_challenge() {
         Base b[HF::DEGREE];
         for (int i = 0; i < HF::DEGREE; i++) b[i] = squeeze_base();
@@ -146,7 +169,6 @@ template <class HF> class Keccak256Transcript {
     size_t read_pos() const { return pos_; }
 
   private:
-    Keccak256 state_;
     std::vector<uint8_t> stream_, rd_;
     size_t pos_ = 0, n_squeezed_ = 0;
     bool reading_ = false;

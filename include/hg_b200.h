@@ -169,6 +169,10 @@ int hg_circuit_node_value(hg_circuit* c, int id, const void** d_ptr, size_t* len
  * reach the input nodes are read back with the hg_gkr_input_claim* getters (what verify() checks, :512-516). */
 int hg_gkr_prove(hg_circuit* c, size_t n_output_claims, const size_t* point_lens, const uint64_t* points_ext, const uint64_t* values_ext,
                  hg_transcript* t, int mode);
+/* host phases of the last hg_gkr_prove in microseconds: [witness kernels enqueue, squeeze+upload challenges, protocol walk,
+ * batched layer enqueue, wait for the GPU, serialise]; number of extension challenges one proof squeezes */
+void hg_gkr_timing(const hg_circuit* c, double* out_us6);
+size_t hg_gkr_num_challenges(const hg_circuit* c);
 size_t hg_gkr_num_inputs(const hg_circuit* c);
 size_t hg_gkr_num_input_claims(const hg_circuit* c, size_t input);
 size_t hg_gkr_input_claim_num_vars(const hg_circuit* c, size_t input, size_t k);
