@@ -23,7 +23,7 @@ DEGREE = {GOLDILOCKS: 2, BN254: 1}
 # every symbol include/hg_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "hg_last_error", "hg_version", "hg_ctx_create", "hg_ctx_destroy", "hg_ctx_set_option", "hg_ctx_synchronize", "hg_ctx_launch_count",
-    "hg_ctx_stream", "hg_ctx_profile", "hg_ctx_profile_read", "hg_kernel_class_count", "hg_kernel_class_name", "hg_buf_alloc", "hg_buf_upload", "hg_buf_download", "hg_buf_device_ptr", "hg_buf_size", "hg_buf_free",
+    "hg_ctx_stream", "hg_ctx_profile", "hg_ctx_profile_read", "hg_kernel_class_count", "hg_kernel_class_name", "hg_buf_alloc", "hg_buf_upload", "hg_buf_download", "hg_buf_device_ptr", "hg_buf_size", "hg_buf_free", "hg_field_base_bytes", "hg_field_encode", "hg_field_decode",
     "hg_transcript_new", "hg_transcript_from_proof", "hg_transcript_free", "hg_transcript_squeeze_challenge", "hg_transcript_write_felt_ext",
     "hg_transcript_read_felt_ext", "hg_transcript_proof_len", "hg_transcript_proof_copy", "hg_transcript_num_squeezed",
     "hg_lasso_preprocess", "hg_lasso_pp_free", "hg_lasso_pp_num_lookups", "hg_lasso_pp_num_subtables", "hg_lasso_pp_num_memories",
@@ -72,6 +72,10 @@ def lib():
         L.hg_buf_size.argtypes = [vp]
         L.hg_buf_size.restype = sz
         L.hg_buf_free.argtypes = [vp]
+        L.hg_field_base_bytes.argtypes = [i32]
+        L.hg_field_base_bytes.restype = sz
+        L.hg_field_encode.argtypes = [vp, vp, sz]
+        L.hg_field_decode.argtypes = [vp, vp, sz]
         L.hg_transcript_new.argtypes = [i32, C.POINTER(vp)]
         L.hg_transcript_from_proof.argtypes = [i32, vp, sz, C.POINTER(vp)]
         L.hg_transcript_free.argtypes = [vp]
@@ -201,6 +205,27 @@ class DeviceBuffer:
         b = cls(ctx, arr.nbytes)
         b.upload(arr)
         return b
+
+    @classmethod
+    def from_field(cls, ctx, limbs):
+        """Upload base-field elements given as canonical little-endian u64 limbs ([n] for Goldilocks, [n, 4] for BN254) and
+        convert them to the device representation (Montgomery form for BN254)."""
+        limbs = np.ascontiguousarray(limbs, np.uint64)
+        b = cls.from_numpy(ctx, limbs)
+        _chk(lib().hg_field_encode(ctx.h, b.ptr, limbs.size // LIMBS[ctx.field]))
+        return b
+
+    def to_field(self, count):
+        """Inverse of from_field: canonical limbs of `count` base elements."""
+        k = LIMBS[self.ctx.field]
+        tmp = DeviceBuffer(self.ctx, count * 8 * k)
+        out = self.download(np.uint64, count * k)
+        if k > 1:
+            tmp.upload(out)
+            _chk(lib().hg_field_decode(self.ctx.h, tmp.ptr, count))
+            out = tmp.download(np.uint64, count * k)
+        tmp.free()
+        return out.reshape(count, k) if k > 1 else out
 
     def upload(self, arr, offset=0):
         arr = np.ascontiguousarray(arr)

@@ -34,32 +34,305 @@ template <class FP> __global__ void k_selftest(int op, const typename FP::X* a, 
 }
 }  // namespace
 
+// ---- field-erased interfaces: every handle carries a field id; the templates behind them are instantiated for
+// GlField (Goldilocks / GoldilocksExt2) and FrField (BN254 Fr, E = F)
+struct ITranscript {
+    int field_id = 0;
+    virtual ~ITranscript() {}
+    virtual void squeeze(uint64_t* out) = 0;
+    virtual void write(const uint64_t* in) = 0;
+    virtual void read(uint64_t* out) = 0;
+    virtual const std::vector<uint8_t>& proof() const = 0;
+    virtual size_t num_squeezed() const = 0;
+    virtual void* raw() = 0;
+};
+template <class FP> struct TranscriptT : ITranscript {
+    Keccak256Transcript<FP> t;
+    TranscriptT() { field_id = FP::FIELD_ID; }
+    TranscriptT(const uint8_t* p, size_t n) : t(p, n) { field_id = FP::FIELD_ID; }
+    void squeeze(uint64_t* out) override { FP::x_to_limbs(t.squeeze_challenge(), out); }
+    void write(const uint64_t* in) override { t.write_felt_ext(FP::x_from_limbs(in)); }
+    void read(uint64_t* out) override { FP::x_to_limbs(t.read_felt_ext(), out); }
+    const std::vector<uint8_t>& proof() const override { return t.proof(); }
+    size_t num_squeezed() const override { return t.num_base_squeezed(); }
+    void* raw() override { return &t; }
+};
+
+template <class FP> __global__ void k_field_encode(typename FP::B* p, size_t n, int decode) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if constexpr (FP::FIELD_ID == 1) {
+        fr v = p[i];
+        if (decode) { u64 t[4]; fr_to_canonical(v, t); p[i] = fr_make(t[0], t[1], t[2], t[3]); }
+        else p[i] = fr_from_canonical(v.l);
+    }
+}
+
+struct ILassoNode {
+    int field_id = 0;
+    size_t log2_input_size = 0;
+    virtual ~ILassoNode() {}
+    virtual void prove(DeviceCtx* dev, const void* inputs, size_t n_inputs, bool on_device, ITranscript* t, int mode, const WireOptions& wo,
+                       uint64_t* out_point, uint64_t* out_value) = 0;
+    virtual size_t device_bytes() const = 0;
+    virtual size_t num_chunks() const = 0;
+    virtual const double* timing() const = 0;
+    virtual void download_polys(uint16_t* dims, uint32_t* read_cts, uint32_t* final_cts, uint64_t* e_polys) = 0;
+    virtual void* raw() = 0;
+};
+template <class FP> struct LassoNodeT : ILassoNode {
+    typedef typename FP::B B;
+    typedef typename FP::X X;
+    LassoNodeDev<FP> node;
+    DevBuf<B> staging;
+    LassoNodeT(DeviceCtx* ctx, const LassoPreprocessing& pp, int nv, const std::vector<uint8_t>& rows) : node(ctx, pp, nv, rows) { field_id = FP::FIELD_ID; }
+    void prove(DeviceCtx* dev, const void* inputs, size_t n_inputs, bool on_device, ITranscript* t, int mode, const WireOptions& wo, uint64_t* out_point,
+               uint64_t* out_value) override {
+        const B* d_in = (const B*)inputs;
+        if (!on_device) {
+            if (staging.n < n_inputs) staging.alloc(n_inputs);
+            HG_CUDA(cudaMemcpyAsync(staging.p, inputs, n_inputs * sizeof(B), cudaMemcpyHostToDevice, dev->stream));
+            if (FP::FIELD_ID == 1) { k_field_encode<FP><<<(unsigned)((n_inputs + 255) / 256), 256, 0, dev->stream>>>(staging.p, n_inputs, 0); HG_LAUNCH_CHECK(); }
+            d_in = staging.p;
+        }
+        std::vector<X> pt;
+        X val;
+        node.prove(d_in, n_inputs, *(Keccak256Transcript<FP>*)t->raw(), mode == HG_MODE_INTERACTIVE ? kModeInteractive : kModePrefetch, wo, &pt, &val);
+        if (out_point) for (size_t i = 0; i < pt.size(); i++) FP::x_to_limbs(pt[i], out_point + FP::X_LIMBS * i);
+        if (out_value) FP::x_to_limbs(val, out_value);
+    }
+    size_t device_bytes() const override { return node.device_bytes(); }
+    size_t num_chunks() const override { return node.chunk_dims().size(); }
+    const double* timing() const override { return node.timing(); }
+    void download_polys(uint16_t* dims, uint32_t* read_cts, uint32_t* final_cts, uint64_t* e_polys) override {
+        std::vector<u16> d; std::vector<u32> r, f; std::vector<B> e;
+        node.download_polys(dims ? &d : nullptr, read_cts ? &r : nullptr, final_cts ? &f : nullptr, e_polys ? &e : nullptr);
+        if (dims) memcpy(dims, d.data(), d.size() * sizeof(u16));
+        if (read_cts) memcpy(read_cts, r.data(), r.size() * sizeof(u32));
+        if (final_cts) memcpy(final_cts, f.data(), f.size() * sizeof(u32));
+        if (e_polys) for (size_t i = 0; i < e.size(); i++) FP::b_to_limbs(e[i], e_polys + i * FP::B_LIMBS);
+    }
+    void* raw() override { return &node; }
+};
+
+struct InputClaimErased { std::vector<uint64_t> point; std::vector<uint64_t> value; size_t nvars; };
+struct ICircuit {
+    int field_id = 0;
+    std::vector<std::vector<InputClaimErased>> input_claims;
+    virtual ~ICircuit() {}
+    virtual int insert_input(size_t log2_size, size_t reps) = 0;
+    virtual int insert_fft(size_t log2_size, bool inverse) = 0;
+    virtual int insert_lasso(ILassoNode* n) = 0;
+    virtual int insert_vanilla(const VanillaDesc& d) = 0;
+    virtual void connect(int a, int b) = 0;
+    virtual void evaluate(const void* const* in, size_t n) = 0;
+    virtual void node_value(int id, const void** p, size_t* len) = 0;
+    virtual void prove(size_t n_claims, const size_t* lens, const uint64_t* pts, const uint64_t* vals, ITranscript* t, int mode, const WireOptions& wo) = 0;
+    virtual const double* timing() const = 0;
+    virtual size_t num_challenges() const = 0;
+};
+template <class FP> struct CircuitT : ICircuit {
+    typedef typename FP::B B;
+    GkrCircuitDev<FP> c;
+    CircuitT(DeviceCtx* ctx, NttEngine<FP>* ntt) : c(ctx, ntt) { field_id = FP::FIELD_ID; }
+    int insert_input(size_t l, size_t r) override { return c.insert_input(l, r); }
+    int insert_fft(size_t l, bool inv) override { return c.insert_fft(l, inv); }
+    int insert_lasso(ILassoNode* n) override {
+        if (n->field_id != FP::FIELD_ID) throw std::runtime_error("lasso node belongs to another field");
+        return c.insert_lasso((LassoNodeDev<FP>*)n->raw());
+    }
+    int insert_vanilla(const VanillaDesc& d) override { return c.insert_vanilla(d); }
+    void connect(int a, int b) override { c.connect(a, b); }
+    void evaluate(const void* const* in, size_t n) override {
+        std::vector<const B*> v;
+        for (size_t i = 0; i < n; i++) v.push_back((const B*)in[i]);
+        c.evaluate(v);
+    }
+    void node_value(int id, const void** p, size_t* len) override {
+        if (id < 0 || (size_t)id >= c.num_nodes()) throw std::runtime_error("no such node");
+        *p = c.node_value(id);
+        *len = c.node_out_len(id);
+    }
+    void prove(size_t n_claims, const size_t* lens, const uint64_t* pts, const uint64_t* vals, ITranscript* t, int mode, const WireOptions& wo) override {
+        if (t->field_id != FP::FIELD_ID) throw std::runtime_error("transcript belongs to another field");
+        std::vector<typename GkrCircuitDev<FP>::InputClaim> oc(n_claims);
+        size_t off = 0;
+        for (size_t i = 0; i < n_claims; i++) {
+            for (size_t k = 0; k < lens[i]; k++) oc[i].point.push_back(FP::x_from_limbs(pts + FP::X_LIMBS * (off + k)));
+            off += lens[i];
+            oc[i].value = FP::x_from_limbs(vals + FP::X_LIMBS * i);
+        }
+        auto res = c.prove(*(Keccak256Transcript<FP>*)t->raw(), mode == HG_MODE_INTERACTIVE ? kModeInteractive : kModePrefetch, wo, oc);
+        input_claims.clear();
+        for (auto& v : res) {
+            std::vector<InputClaimErased> e;
+            for (auto& ic : v) {
+                InputClaimErased x;
+                x.nvars = ic.point.size();
+                x.point.resize(ic.point.size() * FP::X_LIMBS);
+                x.value.resize(FP::X_LIMBS);
+                for (size_t q = 0; q < ic.point.size(); q++) FP::x_to_limbs(ic.point[q], x.point.data() + FP::X_LIMBS * q);
+                FP::x_to_limbs(ic.value, x.value.data());
+                e.push_back(x);
+            }
+            input_claims.push_back(e);
+        }
+    }
+    const double* timing() const override { return c.timing(); }
+    size_t num_challenges() const override { return c.total_challenges(); }
+};
+
+// field-dependent free functions of the ABI
+struct IFieldOps {
+    virtual ~IFieldOps() {}
+    virtual ITranscript* new_transcript() = 0;
+    virtual ILassoNode* new_lasso_node(DeviceCtx* ctx, const LassoPreprocessing& pp, int nv, const std::vector<uint8_t>& rows) = 0;
+    virtual ICircuit* new_circuit(DeviceCtx* ctx) = 0;
+    virtual void sumcheck_prove(DeviceCtx* ctx, const WireOptions& wo, int arity, size_t n_terms, size_t num_vars, const uint64_t* coeffs, const void* d_tables,
+                                const uint64_t* claim, ITranscript* t, int mode, uint64_t* out_point, uint64_t* out_evals) = 0;
+    virtual void mle_eval_batch(DeviceCtx* ctx, const void* d_tables, size_t n_tables, size_t stride, size_t num_vars, const uint64_t* point, uint64_t* out) = 0;
+    virtual void ntt(DeviceCtx* ctx, void* d, int log_n, bool inverse, size_t batch) = 0;
+    virtual void bfv_evaluate(DeviceCtx* ctx, size_t log2_size, size_t K, const uint64_t* qis, const uint64_t* k0is, const uint64_t* r1b, const uint64_t* r2b,
+                              uint64_t sb, uint64_t eb, uint64_t k1b, const void* d_s, const void* d_e, const void* d_k1, const void* d_ais, const void* d_r1is,
+                              const void* d_r2is, void* d_lasso, void* d_sum) = 0;
+    virtual void selftest(DeviceCtx* ctx, int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) = 0;
+    virtual void encode(DeviceCtx* ctx, void* d, size_t n, bool decode) = 0;
+    virtual size_t base_bytes() const = 0;
+};
+template <class FP> struct FieldOpsT : IFieldOps {
+    typedef typename FP::B B;
+    typedef typename FP::X X;
+    std::unique_ptr<NttEngine<FP>> engine;
+    NttEngine<FP>* eng(DeviceCtx* ctx) { if (!engine) engine.reset(new NttEngine<FP>(ctx)); return engine.get(); }
+    ITranscript* new_transcript() override { return new TranscriptT<FP>(); }
+    ILassoNode* new_lasso_node(DeviceCtx* ctx, const LassoPreprocessing& pp, int nv, const std::vector<uint8_t>& rows) override { return new LassoNodeT<FP>(ctx, pp, nv, rows); }
+    ICircuit* new_circuit(DeviceCtx* ctx) override { return new CircuitT<FP>(ctx, eng(ctx)); }
+    size_t base_bytes() const override { return sizeof(B); }
+    void encode(DeviceCtx* ctx, void* d, size_t n, bool decode) override {
+        if (FP::FIELD_ID != 1 || !n) return;
+        k_field_encode<FP><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((B*)d, n, decode ? 1 : 0);
+        HG_LAUNCH_CHECK();
+        HG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    void ntt(DeviceCtx* ctx, void* d, int log_n, bool inverse, size_t batch) override { eng(ctx)->run((B*)d, log_n, inverse, batch); }
+    void selftest(DeviceCtx* ctx, int op, const uint64_t* a_ext, const uint64_t* b_ext, size_t n, uint64_t* out_ext) override {
+        std::vector<X> ha(n), hb(n), ho(n);
+        for (size_t i = 0; i < n; i++) { ha[i] = FP::x_from_limbs(a_ext + i * FP::X_LIMBS); hb[i] = FP::x_from_limbs(b_ext + i * FP::X_LIMBS); }
+        DevBuf<X> a, b, o;
+        a.alloc(n); b.alloc(n); o.alloc(n);
+        HG_CUDA(cudaMemcpy(a.p, ha.data(), n * sizeof(X), cudaMemcpyHostToDevice));
+        HG_CUDA(cudaMemcpy(b.p, hb.data(), n * sizeof(X), cudaMemcpyHostToDevice));
+        k_selftest<FP><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(op, a.p, b.p, n, o.p);
+        HG_LAUNCH_CHECK();
+        HG_CUDA(cudaStreamSynchronize(ctx->stream));
+        HG_CUDA(cudaMemcpy(ho.data(), o.p, n * sizeof(X), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; i++) FP::x_to_limbs(ho[i], out_ext + i * FP::X_LIMBS);
+    }
+    void sumcheck_prove(DeviceCtx* dev, const WireOptions& wo, int arity, size_t n_terms, size_t num_vars, const uint64_t* coeffs_ext, const void* d_tables,
+                        const uint64_t* claim_ext, ITranscript* t, int mode, uint64_t* out_point, uint64_t* out_evals) override {
+        if (arity != 1 && arity != 2) throw std::runtime_error("arity must be 1 or 2");
+        if (num_vars < 1 || num_vars > 30) throw std::runtime_error("num_vars out of range");
+        if (t->field_id != FP::FIELD_ID) throw std::runtime_error("transcript belongs to another field");
+        const size_t n = (size_t)1 << num_vars, ntab = n_terms * arity;
+        DevBuf<X> coeffs, bufA, bufB, partials;
+        DevBuf<unsigned> counters;
+        coeffs.alloc(n_terms);
+        std::vector<X> hc(n_terms);
+        for (size_t i = 0; i < n_terms; i++) hc[i] = FP::x_from_limbs(coeffs_ext + FP::X_LIMBS * i);
+        HG_CUDA(cudaMemcpy(coeffs.p, hc.data(), n_terms * sizeof(X), cudaMemcpyHostToDevice));
+        bufA.alloc(std::max<size_t>(ntab * (n / 2), ntab));
+        bufB.alloc(std::max<size_t>(ntab * (n / 4), ntab));
+        ScScratch sc;
+        sc.max_blocks = dev->sm_count * 8;
+        partials.alloc((size_t)sc.max_blocks * 4);
+        counters.alloc(4);
+        HG_CUDA(cudaMemset(counters.p, 0, counters.bytes()));
+        sc.partials = partials.p; sc.counters = counters.p;
+        Channel<FP> ch(dev, num_vars + 1, 4 * num_vars + ntab + 4);
+        ch.begin((Keccak256Transcript<FP>*)t->raw(), mode == HG_MODE_INTERACTIVE ? kModeInteractive : kModePrefetch, num_vars);
+        auto st = std::make_shared<ScHostState<FP>>();
+        st->claim = FP::x_from_limbs(claim_ext);
+        size_t first = 0, eo = 0;
+        if (arity == 1) sumcheck_dev<FP, 1>(dev, KC_SC_COLL, ch, wo, (const B*)d_tables, n, (int)n_terms, coeffs.p, bufA.p, bufB.p, sc, st, &first, &eo);
+        else sumcheck_dev<FP, 2>(dev, KC_SC_GP, ch, wo, (const B*)d_tables, n, (int)n_terms, coeffs.p, bufA.p, bufB.p, sc, st, &first, &eo);
+        ch.flush();
+        if (out_point) for (size_t i = 0; i < num_vars; i++) FP::x_to_limbs(ch.chal(first + i), out_point + FP::X_LIMBS * i);
+        if (out_evals) for (size_t i = 0; i < ntab; i++) FP::x_to_limbs(ch.msg(eo + i), out_evals + FP::X_LIMBS * i);
+    }
+    void mle_eval_batch(DeviceCtx* dev, const void* d_tables, size_t n_tables, size_t stride, size_t num_vars, const uint64_t* point_ext, uint64_t* out_ext) override {
+        const size_t n = (size_t)1 << num_vars;
+        cudaStream_t s = dev->stream;
+        DevBuf<X> pt, eq, partials, out;
+        DevBuf<unsigned> counters;
+        std::vector<X> hp(num_vars);
+        for (size_t i = 0; i < num_vars; i++) hp[i] = FP::x_from_limbs(point_ext + FP::X_LIMBS * i);
+        pt.alloc(std::max<size_t>(num_vars, 1));
+        HG_CUDA(cudaMemcpy(pt.p, hp.data(), num_vars * sizeof(X), cudaMemcpyHostToDevice));
+        const int lo = num_vars < 12 ? (int)num_vars : 12;
+        const size_t nlo = (size_t)1 << lo, nhi = n >> lo;
+        eq.alloc(nlo + nhi);
+        out.alloc(n_tables);
+        int blocks = (int)std::min<size_t>(nhi, (size_t)dev->sm_count * 2);
+        partials.alloc((size_t)blocks * n_tables);
+        counters.alloc(n_tables);
+        HG_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), s));
+        HG_K(dev, KC_EQ, (nlo + nhi) * sizeof(X), k_eq_split<FP><<<(unsigned)((nlo + nhi + HG_BLOCK - 1) / HG_BLOCK), HG_BLOCK, 0, s>>>(pt.p, (int)num_vars, lo, eq.p, eq.p + nlo));
+        HG_K(dev, KC_DOT, n_tables * n * sizeof(B),
+             k_dot_eq<FP, B><<<dim3(blocks, (unsigned)n_tables), HG_BLOCK, 0, s>>>((const B*)d_tables, stride, n, lo, eq.p, eq.p + nlo, partials.p, counters.p, out.p));
+        std::vector<X> ho(n_tables);
+        HG_CUDA(cudaMemcpyAsync(ho.data(), out.p, n_tables * sizeof(X), cudaMemcpyDeviceToHost, s));
+        HG_CUDA(cudaStreamSynchronize(s));
+        for (size_t i = 0; i < n_tables; i++) FP::x_to_limbs(ho[i], out_ext + FP::X_LIMBS * i);
+    }
+    void bfv_evaluate(DeviceCtx* dev, size_t log2_size, size_t K, const uint64_t* qis, const uint64_t* k0is, const uint64_t* r1_bounds, const uint64_t* r2_bounds,
+                      uint64_t s_bound, uint64_t e_bound, uint64_t k1_bound, const void* d_s, const void* d_e, const void* d_k1, const void* d_ais,
+                      const void* d_r1is, const void* d_r2is, void* d_lasso_inputs, void* d_sum) override {
+        cudaStream_t s = dev->stream;
+        const size_t N2 = (size_t)1 << log2_size, r2_len = K * (N2 / 2);
+        BfvShape sh;
+        sh.log2_size = (int)log2_size; sh.K = (int)K; sh.n_chunks = (int)std::max<size_t>(1, (r2_len + N2 - 1) / N2);
+        std::vector<B> consts(3 * K);
+        for (size_t i = 0; i < K; i++) { consts[i] = FP::b_from_u64(qis[i]); consts[K + i] = FP::b_from_u64(k0is[i]); consts[2 * K + i] = FP::b_from_u64(r1_bounds[i]); }
+        DevBuf<B> d_consts, d_sai, d_seval;
+        d_consts.alloc(3 * K);
+        HG_CUDA(cudaMemcpyAsync(d_consts.p, consts.data(), consts.size() * sizeof(B), cudaMemcpyHostToDevice, s));
+        const size_t total = (K + sh.n_chunks + 3) * N2;
+        HG_K(dev, KC_MISC, total * 2 * sizeof(B),
+             k_bfv_lasso_inputs<FP><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(sh, (const B*)d_s, (const B*)d_e, (const B*)d_k1, (const B*)d_r1is, (const B*)d_r2is,
+                                                                                  r2_len, d_consts.p + 2 * K, FP::b_from_u64(r2_bounds[0]), FP::b_from_u64(s_bound),
+                                                                                  FP::b_from_u64(e_bound), FP::b_from_u64(k1_bound), (B*)d_lasso_inputs));
+        d_seval.alloc(N2);
+        d_sai.alloc(K * N2);
+        HG_CUDA(cudaMemcpyAsync(d_seval.p, d_s, N2 * sizeof(B), cudaMemcpyDeviceToDevice, s));
+        HG_CUDA(cudaMemcpyAsync(d_sai.p, d_ais, K * N2 * sizeof(B), cudaMemcpyDeviceToDevice, s));
+        eng(dev)->run(d_seval.p, (int)log2_size, false, 1);
+        eng(dev)->run(d_sai.p, (int)log2_size, false, K);
+        HG_K(dev, KC_MISC, 3 * K * N2 * sizeof(B), k_pointwise_mul_bcast<FP><<<dim3((unsigned)((N2 + 255) / 256), (unsigned)K), 256, 0, s>>>(d_sai.p, d_seval.p, N2));
+        eng(dev)->run(d_sai.p, (int)log2_size, true, K);
+        HG_K(dev, KC_MISC, 4 * K * N2 * sizeof(B),
+             k_bfv_sum<FP><<<dim3((unsigned)((N2 + 255) / 256), (unsigned)K), 256, 0, s>>>(sh, d_sai.p, (const B*)d_e, (const B*)d_k1, (const B*)d_r1is, (const B*)d_r2is,
+                                                                                         d_consts.p, d_consts.p + K, (B*)d_sum));
+        HG_CUDA(cudaStreamSynchronize(s));
+    }
+};
+
 struct hg_ctx {
     DeviceCtx dev;
     int field_id;
     WireOptions wire;
-    std::unique_ptr<NttEngine<GlField>> ntt;
+    std::unique_ptr<IFieldOps> ops;
 };
 struct hg_circuit {
     hg_ctx* ctx;
-    std::unique_ptr<GkrCircuitDev<GlField>> gl;
-    std::vector<std::vector<GkrCircuitDev<GlField>::InputClaim>> input_claims;
+    std::unique_ptr<ICircuit> c;
 };
-
-namespace {
-void ntt_run(hg_ctx* ctx, u64* d_data, int log_n, bool inverse, size_t batch) {
-    if (!ctx->ntt) ctx->ntt.reset(new NttEngine<GlField>(&ctx->dev));
-    ctx->ntt->run(d_data, log_n, inverse, batch);
-}
-}  // namespace
 struct hg_buf {
     void* p = nullptr;
     size_t bytes = 0;
     int device = 0;
 };
 struct hg_transcript {
-    int field_id;
-    std::unique_ptr<Keccak256Transcript<GlField>> gl;
+    std::unique_ptr<ITranscript> t;
 };
 struct hg_lasso_pp {
     LassoPreprocessing pp;
@@ -67,28 +340,33 @@ struct hg_lasso_pp {
 };
 struct hg_lasso_node {
     hg_ctx* ctx;
-    std::unique_ptr<LassoNodeDev<GlField>> gl;
-    DevBuf<u64> staging;  // device copy of host inputs
-    size_t log2_input_size = 0;
+    std::unique_ptr<ILassoNode> n;
 };
 
-static void need_gl(int field_id) {
-    if (field_id != HG_FIELD_GOLDILOCKS) throw std::runtime_error("field not supported by this build (only HG_FIELD_GOLDILOCKS)");
+static IFieldOps* make_ops(int field_id) {
+    if (field_id == HG_FIELD_GOLDILOCKS) return new FieldOpsT<GlField>();
+    if (field_id == HG_FIELD_BN254) return new FieldOpsT<FrField>();
+    throw std::runtime_error("unknown field id");
+}
+static ITranscript* make_transcript(int field_id, const uint8_t* proof, size_t len, bool reading) {
+    if (field_id == HG_FIELD_GOLDILOCKS) return reading ? (ITranscript*)new TranscriptT<GlField>(proof, len) : new TranscriptT<GlField>();
+    if (field_id == HG_FIELD_BN254) return reading ? (ITranscript*)new TranscriptT<FrField>(proof, len) : new TranscriptT<FrField>();
+    throw std::runtime_error("unknown field id");
 }
 
 extern "C" {
 
 const char* hg_last_error(void) { return g_err.c_str(); }
-int hg_version(void) { return 1; }
+int hg_version(void) { return 2; }
 
 int hg_ctx_create(int device, int field_id, hg_ctx** out) {
     HG_TRY({
-        need_gl(field_id);
         int n = 0;
         HG_CUDA(cudaGetDeviceCount(&n));
         if (device < 0 || device >= n) throw std::runtime_error("no such CUDA device");
         HG_CUDA(cudaSetDevice(device));
         std::unique_ptr<hg_ctx> c(new hg_ctx());
+        c->ops.reset(make_ops(field_id));
         c->dev.device = device;
         c->field_id = field_id;
         HG_CUDA(cudaStreamCreateWithFlags(&c->dev.stream, cudaStreamNonBlocking));
@@ -99,6 +377,7 @@ int hg_ctx_create(int device, int field_id, hg_ctx** out) {
 void hg_ctx_destroy(hg_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->dev.device);
+    ctx->ops.reset();
     if (ctx->dev.stream) cudaStreamDestroy(ctx->dev.stream);
     delete ctx;
 }
@@ -133,6 +412,7 @@ int hg_ctx_profile_read(hg_ctx* ctx, int kernel_class, uint64_t* launches, doubl
 int hg_kernel_class_count(void) { return KC_COUNT; }
 const char* hg_kernel_class_name(int kernel_class) { return kernel_class_name(kernel_class); }
 void* hg_ctx_stream(hg_ctx* ctx) { return (void*)ctx->dev.stream; }
+size_t hg_field_base_bytes(int field_id) { return field_id == HG_FIELD_BN254 ? 32 : 8; }
 
 int hg_buf_alloc(hg_ctx* ctx, size_t bytes, hg_buf** out) {
     HG_TRY({
@@ -168,39 +448,39 @@ void hg_buf_free(hg_buf* buf) {
     cudaFree(buf->p);
     delete buf;
 }
+// device tables hold the library's internal representation: canonical u64 for Goldilocks, 4x64 Montgomery for BN254.
+// hg_field_encode converts n base elements uploaded as canonical little-endian limbs in place; hg_field_decode goes back.
+int hg_field_encode(hg_ctx* ctx, void* d_data, size_t n) { HG_TRY({ HG_CUDA(cudaSetDevice(ctx->dev.device)); ctx->ops->encode(&ctx->dev, d_data, n, false); }) }
+int hg_field_decode(hg_ctx* ctx, void* d_data, size_t n) { HG_TRY({ HG_CUDA(cudaSetDevice(ctx->dev.device)); ctx->ops->encode(&ctx->dev, d_data, n, true); }) }
 
 // ---- transcript
 int hg_transcript_new(int field_id, hg_transcript** out) {
     HG_TRY({
-        need_gl(field_id);
         std::unique_ptr<hg_transcript> t(new hg_transcript());
-        t->field_id = field_id;
-        t->gl.reset(new Keccak256Transcript<GlField>());
+        t->t.reset(make_transcript(field_id, nullptr, 0, false));
         *out = t.release();
     })
 }
 int hg_transcript_from_proof(int field_id, const uint8_t* proof, size_t len, hg_transcript** out) {
     HG_TRY({
-        need_gl(field_id);
         std::unique_ptr<hg_transcript> t(new hg_transcript());
-        t->field_id = field_id;
-        t->gl.reset(new Keccak256Transcript<GlField>(proof, len));
+        t->t.reset(make_transcript(field_id, proof, len, true));
         *out = t.release();
     })
 }
 void hg_transcript_free(hg_transcript* t) { delete t; }
-int hg_transcript_squeeze_challenge(hg_transcript* t, uint64_t* out_ext) { HG_TRY({ GlField::x_to_limbs(t->gl->squeeze_challenge(), out_ext); }) }
-int hg_transcript_write_felt_ext(hg_transcript* t, const uint64_t* ext) { HG_TRY({ t->gl->write_felt_ext(GlField::x_from_limbs(ext)); }) }
-int hg_transcript_read_felt_ext(hg_transcript* t, uint64_t* out_ext) { HG_TRY({ GlField::x_to_limbs(t->gl->read_felt_ext(), out_ext); }) }
-size_t hg_transcript_proof_len(const hg_transcript* t) { return t->gl->proof().size(); }
+int hg_transcript_squeeze_challenge(hg_transcript* t, uint64_t* out_ext) { HG_TRY({ t->t->squeeze(out_ext); }) }
+int hg_transcript_write_felt_ext(hg_transcript* t, const uint64_t* ext) { HG_TRY({ t->t->write(ext); }) }
+int hg_transcript_read_felt_ext(hg_transcript* t, uint64_t* out_ext) { HG_TRY({ t->t->read(out_ext); }) }
+size_t hg_transcript_proof_len(const hg_transcript* t) { return t->t->proof().size(); }
 int hg_transcript_proof_copy(const hg_transcript* t, uint8_t* out, size_t cap) {
     HG_TRY({
-        auto& p = t->gl->proof();
+        auto& p = t->t->proof();
         if (p.size() > cap) throw std::runtime_error("hg_transcript_proof_copy: buffer too small");
         memcpy(out, p.data(), p.size());
     })
 }
-size_t hg_transcript_num_squeezed(const hg_transcript* t) { return t->gl->num_base_squeezed(); }
+size_t hg_transcript_num_squeezed(const hg_transcript* t) { return t->t->num_squeezed(); }
 
 // ---- preprocessing
 int hg_lasso_preprocess(const uint64_t* bounds, size_t n_bounds, size_t C, size_t M, hg_lasso_pp** out) {
@@ -253,8 +533,8 @@ int hg_lasso_node_new(hg_ctx* ctx, const hg_lasso_pp* pp, size_t num_vars, const
         }
         std::unique_ptr<hg_lasso_node> n(new hg_lasso_node());
         n->ctx = ctx;
-        n->gl.reset(new LassoNodeDev<GlField>(&ctx->dev, pp->pp, (int)num_vars, rows));
-        n->log2_input_size = std::max<size_t>(num_vars, ilog2u(pp->pp.M));  // lasso.rs:45-47
+        n->n.reset(ctx->ops->new_lasso_node(&ctx->dev, pp->pp, (int)num_vars, rows));
+        n->n->log2_input_size = std::max<size_t>(num_vars, ilog2u(pp->pp.M));  // lasso.rs:45-47
         *out = n.release();
     })
 }
@@ -263,149 +543,55 @@ void hg_lasso_node_free(hg_lasso_node* node) {
     cudaSetDevice(node->ctx->dev.device);
     delete node;
 }
-size_t hg_lasso_node_log2_input_size(const hg_lasso_node* node) { return node->log2_input_size; }
-size_t hg_lasso_node_device_bytes(const hg_lasso_node* node) { return node->gl->device_bytes(); }
-size_t hg_lasso_node_num_chunks(const hg_lasso_node* node) { return node->gl->chunk_dims().size(); }
-void hg_lasso_node_timing(const hg_lasso_node* node, double* out_us4) { for (int i = 0; i < 4; i++) out_us4[i] = node->gl->timing()[i]; }
+size_t hg_lasso_node_log2_input_size(const hg_lasso_node* node) { return node->n->log2_input_size; }
+size_t hg_lasso_node_device_bytes(const hg_lasso_node* node) { return node->n->device_bytes(); }
+size_t hg_lasso_node_num_chunks(const hg_lasso_node* node) { return node->n->num_chunks(); }
+void hg_lasso_node_timing(const hg_lasso_node* node, double* out_us4) { for (int i = 0; i < 4; i++) out_us4[i] = node->n->timing()[i]; }
 
 int hg_lasso_node_prove(hg_lasso_node* node, const void* inputs, size_t n_inputs, int inputs_on_device, hg_transcript* t, int mode,
                         uint64_t* out_point, uint64_t* out_value) {
     HG_TRY({
         hg_ctx* ctx = node->ctx;
         HG_CUDA(cudaSetDevice(ctx->dev.device));
-        const u64* d_in = (const u64*)inputs;
-        if (!inputs_on_device) {
-            if (node->staging.n < n_inputs) node->staging.alloc(n_inputs);
-            HG_CUDA(cudaMemcpyAsync(node->staging.p, inputs, n_inputs * sizeof(u64), cudaMemcpyHostToDevice, ctx->dev.stream));
-            d_in = node->staging.p;
-        }
-        std::vector<gl2> pt;
-        gl2 val;
-        node->gl->prove(d_in, n_inputs, *t->gl, mode == HG_MODE_INTERACTIVE ? kModeInteractive : kModePrefetch, ctx->wire, &pt, &val);
-        if (out_point) for (size_t i = 0; i < pt.size(); i++) GlField::x_to_limbs(pt[i], out_point + 2 * i);
-        if (out_value) GlField::x_to_limbs(val, out_value);
+        if (t->t->field_id != node->n->field_id) throw std::runtime_error("transcript belongs to another field");
+        node->n->prove(&ctx->dev, inputs, n_inputs, inputs_on_device != 0, t->t.get(), mode, ctx->wire, out_point, out_value);
     })
 }
 int hg_lasso_node_download_polys(hg_lasso_node* node, uint16_t* dims, uint32_t* read_cts, uint32_t* final_cts, uint64_t* e_polys) {
     HG_TRY({
         HG_CUDA(cudaSetDevice(node->ctx->dev.device));
-        std::vector<u16> d; std::vector<u32> r, f; std::vector<u64> e;
-        node->gl->download_polys(dims ? &d : nullptr, read_cts ? &r : nullptr, final_cts ? &f : nullptr, e_polys ? &e : nullptr);
-        if (dims) memcpy(dims, d.data(), d.size() * sizeof(u16));
-        if (read_cts) memcpy(read_cts, r.data(), r.size() * sizeof(u32));
-        if (final_cts) memcpy(final_cts, f.data(), f.size() * sizeof(u32));
-        if (e_polys) memcpy(e_polys, e.data(), e.size() * sizeof(u64));
+        node->n->download_polys(dims, read_cts, final_cts, e_polys);
     })
 }
 
-// ---- generic sumcheck
+// ---- generic sumcheck / MLE / NTT / forward evaluation
 int hg_sumcheck_prove(hg_ctx* ctx, int arity, size_t n_terms, size_t num_vars, const uint64_t* coeffs_ext, const void* d_tables,
                       const uint64_t* claim_ext, hg_transcript* t, int mode, uint64_t* out_point, uint64_t* out_evals) {
     HG_TRY({
-        typedef GlField FP;
         HG_CUDA(cudaSetDevice(ctx->dev.device));
-        if (arity != 1 && arity != 2) throw std::runtime_error("arity must be 1 or 2");
-        if (num_vars < 1 || num_vars > 30) throw std::runtime_error("num_vars out of range");
-        const size_t n = (size_t)1 << num_vars, ntab = n_terms * arity;
-        DevBuf<gl2> coeffs, bufA, bufB, partials;
-        DevBuf<unsigned> counters;
-        coeffs.alloc(n_terms);
-        std::vector<gl2> hc(n_terms);
-        for (size_t i = 0; i < n_terms; i++) hc[i] = FP::x_from_limbs(coeffs_ext + 2 * i);
-        HG_CUDA(cudaMemcpy(coeffs.p, hc.data(), n_terms * sizeof(gl2), cudaMemcpyHostToDevice));
-        bufA.alloc(std::max<size_t>(ntab * (n / 2), ntab));
-        bufB.alloc(std::max<size_t>(ntab * (n / 4), ntab));
-        ScScratch sc;
-        sc.max_blocks = ctx->dev.sm_count * 8;
-        partials.alloc((size_t)sc.max_blocks * 4);
-        counters.alloc(4);
-        HG_CUDA(cudaMemset(counters.p, 0, counters.bytes()));
-        sc.partials = partials.p; sc.counters = counters.p;
-        Channel<FP> ch(&ctx->dev, num_vars + 1, 4 * num_vars + ntab + 4);
-        ch.begin(t->gl.get(), mode == HG_MODE_INTERACTIVE ? kModeInteractive : kModePrefetch, num_vars);
-        auto st = std::make_shared<ScHostState<FP>>();
-        st->claim = FP::x_from_limbs(claim_ext);
-        size_t first = 0, eo = 0;
-        if (arity == 1) sumcheck_dev<FP, 1>(&ctx->dev, KC_SC_COLL, ch, ctx->wire, (const u64*)d_tables, n, (int)n_terms, coeffs.p, bufA.p, bufB.p, sc, st, &first, &eo);
-        else sumcheck_dev<FP, 2>(&ctx->dev, KC_SC_GP, ch, ctx->wire, (const u64*)d_tables, n, (int)n_terms, coeffs.p, bufA.p, bufB.p, sc, st, &first, &eo);
-        ch.flush();
-        if (out_point) for (size_t i = 0; i < num_vars; i++) FP::x_to_limbs(ch.chal(first + i), out_point + 2 * i);
-        if (out_evals) for (size_t i = 0; i < ntab; i++) FP::x_to_limbs(ch.msg(eo + i), out_evals + 2 * i);
+        ctx->ops->sumcheck_prove(&ctx->dev, ctx->wire, arity, n_terms, num_vars, coeffs_ext, d_tables, claim_ext, t->t.get(), mode, out_point, out_evals);
     })
 }
-
 int hg_mle_eval_batch(hg_ctx* ctx, const void* d_tables, size_t n_tables, size_t stride, size_t num_vars, const uint64_t* point_ext,
                       uint64_t* out_ext) {
     HG_TRY({
-        typedef GlField FP;
         HG_CUDA(cudaSetDevice(ctx->dev.device));
-        const size_t n = (size_t)1 << num_vars;
-        cudaStream_t s = ctx->dev.stream;
-        DevBuf<gl2> pt, eq, partials, out;
-        DevBuf<unsigned> counters;
-        std::vector<gl2> hp(num_vars);
-        for (size_t i = 0; i < num_vars; i++) hp[i] = FP::x_from_limbs(point_ext + 2 * i);
-        pt.alloc(std::max<size_t>(num_vars, 1));
-        HG_CUDA(cudaMemcpy(pt.p, hp.data(), num_vars * sizeof(gl2), cudaMemcpyHostToDevice));
-        const int lo = num_vars < 12 ? (int)num_vars : 12;
-        const size_t nlo = (size_t)1 << lo, nhi = n >> lo;
-        eq.alloc(nlo + nhi);
-        out.alloc(n_tables);
-        int blocks = (int)std::min<size_t>(nhi, (size_t)ctx->dev.sm_count * 2);
-        partials.alloc((size_t)blocks * n_tables);
-        counters.alloc(n_tables);
-        HG_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), s));
-        HG_K(&ctx->dev, KC_EQ, (nlo + nhi) * sizeof(gl2), k_eq_split<FP><<<(unsigned)((nlo + nhi + HG_BLOCK - 1) / HG_BLOCK), HG_BLOCK, 0, s>>>(pt.p, (int)num_vars, lo, eq.p, eq.p + nlo));
-        HG_K(&ctx->dev, KC_DOT, n_tables * n * 8,
-             k_dot_eq<FP, u64><<<dim3(blocks, (unsigned)n_tables), HG_BLOCK, 0, s>>>((const u64*)d_tables, stride, n, lo, eq.p, eq.p + nlo, partials.p, counters.p, out.p));
-        std::vector<gl2> ho(n_tables);
-        HG_CUDA(cudaMemcpyAsync(ho.data(), out.p, n_tables * sizeof(gl2), cudaMemcpyDeviceToHost, s));
-        HG_CUDA(cudaStreamSynchronize(s));
-        for (size_t i = 0; i < n_tables; i++) FP::x_to_limbs(ho[i], out_ext + 2 * i);
+        ctx->ops->mle_eval_batch(&ctx->dev, d_tables, n_tables, stride, num_vars, point_ext, out_ext);
     })
 }
-
 int hg_ntt(hg_ctx* ctx, void* d_data, size_t log_n, int inverse, size_t batch) {
     HG_TRY({
         HG_CUDA(cudaSetDevice(ctx->dev.device));
-        ntt_run(ctx, (u64*)d_data, (int)log_n, inverse != 0, batch);
+        ctx->ops->ntt(&ctx->dev, d_data, (int)log_n, inverse != 0, batch);
     })
 }
-
 int hg_bfv_evaluate(hg_ctx* ctx, size_t log2_size, size_t K, const uint64_t* qis, const uint64_t* k0is, const uint64_t* r1_bounds,
                     const uint64_t* r2_bounds, uint64_t s_bound, uint64_t e_bound, uint64_t k1_bound, const void* d_s, const void* d_e,
                     const void* d_k1, const void* d_ais, const void* d_r1is, const void* d_r2is, void* d_lasso_inputs, void* d_sum) {
     HG_TRY({
-        typedef GlField FP;
         HG_CUDA(cudaSetDevice(ctx->dev.device));
-        cudaStream_t s = ctx->dev.stream;
-        const size_t N2 = (size_t)1 << log2_size, r2_len = K * (N2 / 2);
-        BfvShape sh;
-        sh.log2_size = (int)log2_size; sh.K = (int)K; sh.n_chunks = (int)std::max<size_t>(1, (r2_len + N2 - 1) / N2);
-        // per-modulus constants as field elements (F::from_str_vartime(QIS/K0IS), sk_encryption_circuit.rs:109,135)
-        std::vector<u64> consts(3 * K);
-        for (size_t i = 0; i < K; i++) { consts[i] = gl_from_u64(qis[i]); consts[K + i] = gl_from_u64(k0is[i]); consts[2 * K + i] = gl_from_u64(r1_bounds[i]); }
-        DevBuf<u64> d_consts, d_sai, d_seval;
-        d_consts.alloc(3 * K);
-        HG_CUDA(cudaMemcpyAsync(d_consts.p, consts.data(), consts.size() * 8, cudaMemcpyHostToDevice, s));
-        const size_t total = (K + sh.n_chunks + 3) * N2;
-        HG_K(&ctx->dev, KC_MISC, total * 16,
-             k_bfv_lasso_inputs<FP><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(sh, (const u64*)d_s, (const u64*)d_e, (const u64*)d_k1, (const u64*)d_r1is,
-                                                                                  (const u64*)d_r2is, r2_len, d_consts.p + 2 * K, gl_from_u64(r2_bounds[0]),
-                                                                                  gl_from_u64(s_bound), gl_from_u64(e_bound), gl_from_u64(k1_bound), (u64*)d_lasso_inputs));
-        // s_eval = FFT(s); ai_eval = FFT(ai); sai = IFFT(s_eval . ai_eval)   (sk_encryption_circuit.rs:224-260)
-        d_seval.alloc(N2);
-        d_sai.alloc(K * N2);
-        HG_CUDA(cudaMemcpyAsync(d_seval.p, d_s, N2 * 8, cudaMemcpyDeviceToDevice, s));
-        HG_CUDA(cudaMemcpyAsync(d_sai.p, d_ais, K * N2 * 8, cudaMemcpyDeviceToDevice, s));
-        ntt_run(ctx, d_seval.p, (int)log2_size, false, 1);
-        ntt_run(ctx, d_sai.p, (int)log2_size, false, K);
-        HG_K(&ctx->dev, KC_MISC, 3 * K * N2 * 8, k_pointwise_mul_bcast<FP><<<dim3((unsigned)((N2 + 255) / 256), (unsigned)K), 256, 0, s>>>(d_sai.p, d_seval.p, N2));
-        ntt_run(ctx, d_sai.p, (int)log2_size, true, K);
-        HG_K(&ctx->dev, KC_MISC, 4 * K * N2 * 8,
-             k_bfv_sum<FP><<<dim3((unsigned)((N2 + 255) / 256), (unsigned)K), 256, 0, s>>>(sh, d_sai.p, (const u64*)d_e, (const u64*)d_k1, (const u64*)d_r1is,
-                                                                                         (const u64*)d_r2is, d_consts.p, d_consts.p + K, (u64*)d_sum));
-        HG_CUDA(cudaStreamSynchronize(s));  // temporaries are freed on return
+        ctx->ops->bfv_evaluate(&ctx->dev, log2_size, K, qis, k0is, r1_bounds, r2_bounds, s_bound, e_bound, k1_bound, d_s, d_e, d_k1, d_ais, d_r1is, d_r2is,
+                               d_lasso_inputs, d_sum);
     })
 }
 
@@ -413,10 +599,9 @@ int hg_bfv_evaluate(hg_ctx* ctx, size_t log2_size, size_t K, const uint64_t* qis
 int hg_circuit_new(hg_ctx* ctx, hg_circuit** out) {
     HG_TRY({
         HG_CUDA(cudaSetDevice(ctx->dev.device));
-        if (!ctx->ntt) ctx->ntt.reset(new NttEngine<GlField>(&ctx->dev));
         std::unique_ptr<hg_circuit> c(new hg_circuit());
         c->ctx = ctx;
-        c->gl.reset(new GkrCircuitDev<GlField>(&ctx->dev, ctx->ntt.get()));
+        c->c.reset(ctx->ops->new_circuit(&ctx->dev));
         *out = c.release();
     })
 }
@@ -425,87 +610,61 @@ void hg_circuit_free(hg_circuit* c) {
     cudaSetDevice(c->ctx->dev.device);
     delete c;
 }
-int hg_circuit_insert_input(hg_circuit* c, size_t log2_size, size_t num_reps, int* out_id) { HG_TRY({ *out_id = c->gl->insert_input(log2_size, num_reps); }) }
+int hg_circuit_insert_input(hg_circuit* c, size_t log2_size, size_t num_reps, int* out_id) { HG_TRY({ *out_id = c->c->insert_input(log2_size, num_reps); }) }
 int hg_circuit_insert_fft(hg_circuit* c, size_t log2_size, int inverse, int* out_id) {
-    HG_TRY({ HG_CUDA(cudaSetDevice(c->ctx->dev.device)); *out_id = c->gl->insert_fft(log2_size, inverse != 0); })
+    HG_TRY({ HG_CUDA(cudaSetDevice(c->ctx->dev.device)); *out_id = c->c->insert_fft(log2_size, inverse != 0); })
 }
-int hg_circuit_insert_lasso(hg_circuit* c, hg_lasso_node* node, int* out_id) { HG_TRY({ *out_id = c->gl->insert_lasso(node->gl.get()); }) }
+int hg_circuit_insert_lasso(hg_circuit* c, hg_lasso_node* node, int* out_id) { HG_TRY({ *out_id = c->c->insert_lasso(node->n.get()); }) }
 int hg_circuit_insert_vanilla(hg_circuit* c, size_t input_arity, size_t log2_sub_input_size, size_t num_reps, size_t n_gates, const uint8_t* has_const,
                               const uint64_t* consts, const uint64_t* add_ptr, const uint64_t* add_coef, const uint32_t* add_input,
                               const uint64_t* add_wire, const uint64_t* mul_ptr, const uint64_t* mul_coef, const uint32_t* mul_in0, const uint64_t* mul_w0,
                               const uint32_t* mul_in1, const uint64_t* mul_w1, int* out_id) {
     HG_TRY({
         HG_CUDA(cudaSetDevice(c->ctx->dev.device));
+        const size_t L = c->c->field_id == HG_FIELD_BN254 ? 4 : 1;  // limbs per coefficient
         VanillaDesc d;
         d.arity = input_arity; d.log2_sub = log2_sub_input_size; d.num_reps = num_reps; d.n_gates = n_gates;
         d.has_const.assign(has_const, has_const + n_gates);
-        d.consts.assign(consts, consts + n_gates);
+        d.consts.assign(consts, consts + n_gates * L);
         d.add_ptr.assign(add_ptr, add_ptr + n_gates + 1);
         const size_t na = d.add_ptr[n_gates];
-        d.add_coef.assign(add_coef, add_coef + na); d.add_in.assign(add_input, add_input + na); d.add_wire.assign(add_wire, add_wire + na);
+        d.add_coef.assign(add_coef, add_coef + na * L); d.add_in.assign(add_input, add_input + na); d.add_wire.assign(add_wire, add_wire + na);
         d.mul_ptr.assign(mul_ptr, mul_ptr + n_gates + 1);
         const size_t nm = d.mul_ptr[n_gates];
-        d.mul_coef.assign(mul_coef, mul_coef + nm); d.mul_in0.assign(mul_in0, mul_in0 + nm); d.mul_w0.assign(mul_w0, mul_w0 + nm);
+        d.mul_coef.assign(mul_coef, mul_coef + nm * L); d.mul_in0.assign(mul_in0, mul_in0 + nm); d.mul_w0.assign(mul_w0, mul_w0 + nm);
         d.mul_in1.assign(mul_in1, mul_in1 + nm); d.mul_w1.assign(mul_w1, mul_w1 + nm);
-        *out_id = c->gl->insert_vanilla(d);
+        *out_id = c->c->insert_vanilla(d);
     })
 }
-int hg_circuit_connect(hg_circuit* c, int from, int to) { HG_TRY({ c->gl->connect(from, to); }) }
+int hg_circuit_connect(hg_circuit* c, int from, int to) { HG_TRY({ c->c->connect(from, to); }) }
 int hg_circuit_evaluate(hg_circuit* c, const void* const* d_inputs, size_t n_inputs) {
-    HG_TRY({
-        HG_CUDA(cudaSetDevice(c->ctx->dev.device));
-        std::vector<const u64*> in;
-        for (size_t i = 0; i < n_inputs; i++) in.push_back((const u64*)d_inputs[i]);
-        c->gl->evaluate(in);
-    })
+    HG_TRY({ HG_CUDA(cudaSetDevice(c->ctx->dev.device)); c->c->evaluate(d_inputs, n_inputs); })
 }
-int hg_circuit_node_value(hg_circuit* c, int id, const void** d_ptr, size_t* len) {
-    HG_TRY({
-        if (id < 0 || (size_t)id >= c->gl->num_nodes()) throw std::runtime_error("no such node");
-        *d_ptr = c->gl->node_value(id);
-        *len = c->gl->node_out_len(id);
-    })
-}
+int hg_circuit_node_value(hg_circuit* c, int id, const void** d_ptr, size_t* len) { HG_TRY({ c->c->node_value(id, d_ptr, len); }) }
 int hg_gkr_prove(hg_circuit* c, size_t n_output_claims, const size_t* point_lens, const uint64_t* points_ext, const uint64_t* values_ext,
                  hg_transcript* t, int mode) {
     HG_TRY({
-        typedef GlField FP;
         HG_CUDA(cudaSetDevice(c->ctx->dev.device));
-        std::vector<GkrCircuitDev<FP>::InputClaim> oc(n_output_claims);
-        size_t off = 0;
-        for (size_t i = 0; i < n_output_claims; i++) {
-            for (size_t k = 0; k < point_lens[i]; k++) oc[i].point.push_back(FP::x_from_limbs(points_ext + 2 * (off + k)));
-            off += point_lens[i];
-            oc[i].value = FP::x_from_limbs(values_ext + 2 * i);
-        }
-        c->input_claims = c->gl->prove(*t->gl, mode == HG_MODE_INTERACTIVE ? kModeInteractive : kModePrefetch, c->ctx->wire, oc);
+        c->c->prove(n_output_claims, point_lens, points_ext, values_ext, t->t.get(), mode, c->ctx->wire);
     })
 }
-void hg_gkr_timing(const hg_circuit* c, double* out_us6) { for (int i = 0; i < 6; i++) out_us6[i] = c->gl->timing()[i]; }
-size_t hg_gkr_num_challenges(const hg_circuit* c) { return c->gl->total_challenges(); }
-size_t hg_gkr_num_inputs(const hg_circuit* c) { return c->input_claims.size(); }
-size_t hg_gkr_num_input_claims(const hg_circuit* c, size_t input) { return input < c->input_claims.size() ? c->input_claims[input].size() : 0; }
-size_t hg_gkr_input_claim_num_vars(const hg_circuit* c, size_t input, size_t k) { return c->input_claims.at(input).at(k).point.size(); }
+void hg_gkr_timing(const hg_circuit* c, double* out_us6) { for (int i = 0; i < 6; i++) out_us6[i] = c->c->timing()[i]; }
+size_t hg_gkr_num_challenges(const hg_circuit* c) { return c->c->num_challenges(); }
+size_t hg_gkr_num_inputs(const hg_circuit* c) { return c->c->input_claims.size(); }
+size_t hg_gkr_num_input_claims(const hg_circuit* c, size_t input) { return input < c->c->input_claims.size() ? c->c->input_claims[input].size() : 0; }
+size_t hg_gkr_input_claim_num_vars(const hg_circuit* c, size_t input, size_t k) { return c->c->input_claims.at(input).at(k).nvars; }
 int hg_gkr_input_claim(const hg_circuit* c, size_t input, size_t k, uint64_t* point_ext, uint64_t* value_ext) {
     HG_TRY({
-        const auto& ic = c->input_claims.at(input).at(k);
-        for (size_t q = 0; q < ic.point.size(); q++) GlField::x_to_limbs(ic.point[q], point_ext + 2 * q);
-        GlField::x_to_limbs(ic.value, value_ext);
+        const auto& ic = c->c->input_claims.at(input).at(k);
+        memcpy(point_ext, ic.point.data(), ic.point.size() * 8);
+        memcpy(value_ext, ic.value.data(), ic.value.size() * 8);
     })
 }
 
 int hg_field_selftest(hg_ctx* ctx, int op, const uint64_t* a_ext, const uint64_t* b_ext, size_t n, uint64_t* out_ext) {
     HG_TRY({
-        typedef GlField FP;
         HG_CUDA(cudaSetDevice(ctx->dev.device));
-        DevBuf<gl2> a, b, o;
-        a.alloc(n); b.alloc(n); o.alloc(n);
-        HG_CUDA(cudaMemcpy(a.p, a_ext, n * sizeof(gl2), cudaMemcpyHostToDevice));
-        HG_CUDA(cudaMemcpy(b.p, b_ext, n * sizeof(gl2), cudaMemcpyHostToDevice));
-        k_selftest<FP><<<(unsigned)((n + 255) / 256), 256, 0, ctx->dev.stream>>>(op, a.p, b.p, n, o.p);
-        HG_LAUNCH_CHECK();
-        HG_CUDA(cudaStreamSynchronize(ctx->dev.stream));
-        HG_CUDA(cudaMemcpy(out_ext, o.p, n * sizeof(gl2), cudaMemcpyDeviceToHost));
+        ctx->ops->selftest(&ctx->dev, op, a_ext, b_ext, n, out_ext);
     })
 }
 

@@ -21,8 +21,13 @@ struct GlField {
     HG_HD static B b_sub(B a, B b) { return gl_sub(a, b); }
     HG_HD static B b_mul(B a, B b) { return gl_mul(a, b); }
     HG_HD static B b_inv(B a) { return gl_inv(a); }
-    HG_HD static B root_of_unity_2_32() { return 0x185629dcda58878cULL; }  // 7^((p-1)/2^32), goldilocks ROOT_OF_UNITY (A9)
+    HG_HD static B root_of_unity() { return 0x185629dcda58878cULL; }  // 7^((p-1)/2^32), goldilocks ROOT_OF_UNITY (A9)
     static constexpr int TWO_ADICITY = 32;
+    static constexpr int PLANES = 2;  // base planes per extension element
+    static constexpr int GP_TAIL_LOG = 6, GP_MIN_BLOCKS = 2;
+    HG_HD static bool b_eq(B a, B b) { return a == b; }
+    HG_HD static B plane(X a, int p) { return p ? a.c1 : a.c0; }
+    HG_HD static X from_planes(const B* p) { return gl2_make(p[0], p[1]); }
     HG_HD static X x_zero() { return gl2_zero(); }
     HG_HD static X x_one() { return gl2_one(); }
     HG_HD static X lift(B a) { return gl2_lift(a); }
@@ -107,6 +112,9 @@ struct GlField {
     __device__ __forceinline__ static X at_m1(X lo, X hi) {
         return gl2_make(gl_add_cs(lo.c0, gl_sub_cs(lo.c0, hi.c0)), gl_add_cs(lo.c1, gl_sub_cs(lo.c1, hi.c1)));
     }
+    __device__ __forceinline__ static B to_base(unsigned short v) { return (B)v; }
+    __device__ __forceinline__ static B to_base(unsigned int v) { return (B)v; }
+    __device__ __forceinline__ static B to_base(B v) { return v; }
     __device__ __forceinline__ static X x_ldcg(const X* p) {
         ulonglong2 t = __ldcg(reinterpret_cast<const ulonglong2*>(p));
         return gl2_make(t.x, t.y);

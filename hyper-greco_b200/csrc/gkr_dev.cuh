@@ -71,7 +71,7 @@ template <class FP> class GkrCircuitDev {
             bool ok = d.arity == 2 && n_add == 0 && n_mul == ng && d.num_reps == 1;
             for (size_t g = 0; ok && g < ng; g++) {
                 ok = !d.has_const[g] && d.mul_ptr[g] == g && d.mul_in0[g] == 0 && d.mul_in1[g] == 1 && d.mul_w0[g] == g && d.mul_w1[g] == g &&
-                     FP::b_from_limbs(&d.mul_coef[g * FP::B_LIMBS]) == FP::b_one();
+                     FP::b_eq(FP::b_from_limbs(&d.mul_coef[g * FP::B_LIMBS]), FP::b_one());
             }
             if (!ok) throw std::runtime_error("VanillaNode: only linear gates and the element-wise product layer are supported on the device");
             n.is_elemmul = true;
@@ -461,13 +461,13 @@ template <class FP> class GkrCircuitDev {
             const int lg = kv.first.first;
             const bool inv = kv.first.second != 0;
             const size_t N = (size_t)1 << lg, cnt = kv.second.size();
-            if (d_planes_.n < 2 * N * cnt) { HG_CUDA(cudaStreamSynchronize(s)); d_planes_.alloc(2 * N * cnt); }
+            if (d_planes_.n < FP::PLANES * N * cnt) { HG_CUDA(cudaStreamSynchronize(s)); d_planes_.alloc(FP::PLANES * N * cnt); }
             std::vector<X*> wt, at;
             for (size_t q = 0; q < cnt; q++) { wt.push_back(nodes_[kv.second[q]]->W.p); at.push_back(nodes_[kv.second[q]]->A.p); }
             X* const* d_wt = stage(wt);
             X* const* d_at = stage(at);
             HG_K(ctx_, KC_GKR_PREP, N * cnt * sizeof(X) * 2, k_ext_split<FP><<<dim3((unsigned)((N + 255) / 256), (unsigned)cnt), 256, 0, s>>>(d_wt, N, d_planes_.p));
-            ntt_->run(d_planes_.p, lg, inv, 2 * cnt);
+            ntt_->run(d_planes_.p, lg, inv, FP::PLANES * cnt);
             HG_K(ctx_, KC_GKR_PREP, N * cnt * sizeof(X) * 2, k_ext_merge<FP><<<dim3((unsigned)((N + 255) / 256), (unsigned)cnt), 256, 0, s>>>(d_planes_.p, N, d_at));
         }
         (void)wo;

@@ -84,19 +84,23 @@ __global__ void k_wiring_gather(const u64* __restrict__ rev_ptr, const u32* __re
 }
 
 // ---- split / merge of extension tables into base planes (the FFT-matrix weights are the transform of W, plane by plane)
-// tabs[q] = extension table of node q (n elements); planes = [2q][n] | [2q+1][n]
+// tabs[q] = extension table of node q (n elements); planes = [PLANES*q + p][n]
 template <class FP> __global__ void k_ext_split(typename FP::X* const* __restrict__ tabs, size_t n, typename FP::B* __restrict__ planes) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const size_t q = blockIdx.y;
     typename FP::X v = tabs[q][i];
-    planes[(2 * q) * n + i] = v.c0; planes[(2 * q + 1) * n + i] = v.c1;
+#pragma unroll
+    for (int p = 0; p < FP::PLANES; p++) planes[(FP::PLANES * q + p) * n + i] = FP::plane(v, p);
 }
 template <class FP> __global__ void k_ext_merge(const typename FP::B* __restrict__ planes, size_t n, typename FP::X* const* __restrict__ tabs) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const size_t q = blockIdx.y;
-    tabs[q][i] = gl2_make(planes[(2 * q) * n + i], planes[(2 * q + 1) * n + i]);
+    typename FP::B b[FP::PLANES];
+#pragma unroll
+    for (int p = 0; p < FP::PLANES; p++) b[p] = planes[(FP::PLANES * q + p) * n + i];
+    tabs[q][i] = FP::from_planes(b);
 }
 
 // ---- product sumcheck rounds, all nodes per launch. msg slots per round: [h(0), h(inf), h(-1), h(1)] (h(-1) only for nt = 2,

@@ -14,6 +14,7 @@
 //     the integer ALU pipe, not by HBM, so instruction count is what matters (profiles/).
 // Message slots: [h(0), h(inf), h(-1)] and, in round 0 only, [.., h(1)].
 #pragma once
+#include "bn254.cuh"
 #include "kernels.cuh"
 
 namespace hg {
@@ -36,6 +37,19 @@ __device__ __forceinline__ void load4(const gl2* p, gl2 (&v)[4]) {
 }
 __device__ __forceinline__ void load2(const u64* p, u64 (&v)[2]) { ldg128(p, v[0], v[1]); }
 __device__ __forceinline__ void store2(gl2* p, gl2 a, gl2 b) { stg256(p, a.c0, a.c1, b.c0, b.c1); }
+// BN254: one element = one 256-bit access
+__device__ __forceinline__ void load4(const fr* p, fr (&v)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) ldg256(p + i, v[i].l[0], v[i].l[1], v[i].l[2], v[i].l[3]);
+}
+__device__ __forceinline__ void load2(const fr* p, fr (&v)[2]) {
+    ldg256(p, v[0].l[0], v[0].l[1], v[0].l[2], v[0].l[3]);
+    ldg256(p + 1, v[1].l[0], v[1].l[1], v[1].l[2], v[1].l[3]);
+}
+__device__ __forceinline__ void store2(fr* p, fr a, fr b) {
+    stg256(p, a.l[0], a.l[1], a.l[2], a.l[3]);
+    stg256(p + 1, b.l[0], b.l[1], b.l[2], b.l[3]);
+}
 // pull the bytes a later iteration will load into L2 (costs no registers; the loop is otherwise latency-bound, profiles/)
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -184,8 +198,8 @@ __global__ void k_gp_coeffs(const typename FP::X* __restrict__ gamma, const type
 // shared memory. ~430 launches per proof become ~20.
 namespace hg {
 
-constexpr int HG_GP_TAIL_LOG = 6;
-constexpr int HG_GP_TAIL = 1 << HG_GP_TAIL_LOG;  // table length at which a layer moves to the shared-memory tail kernel
+// table length at which a layer moves to the shared-memory tail kernel: FP::GP_TAIL_LOG (64 elements of 16 B for
+// Goldilocks, 32 elements of 32 B for BN254: 2*m tables * 1.5 * that must fit 227 KB)
 constexpr int HG_TAIL_THREADS = 512;
 #ifndef HG_GP_PREFETCH
 #define HG_GP_PREFETCH 2
@@ -276,7 +290,7 @@ template <class ITEM> __device__ __forceinline__ int find_item(const ITEM* items
 template <class FP> __device__ __forceinline__ int gp_find_item(const GpItem<FP>* items, int nitems) { return find_item(items, nitems); }
 
 template <class FP, int U>
-__global__ void __launch_bounds__(HG_BLOCK, 2) k_gp_r0_multi(const GpItem<FP>* __restrict__ items, int nitems) {
+__global__ void __launch_bounds__(HG_BLOCK, FP::GP_MIN_BLOCKS) k_gp_r0_multi(const GpItem<FP>* __restrict__ items, int nitems) {
     typedef typename FP::B B;
     typedef typename FP::X X;
     constexpr int NP = 4;
@@ -333,7 +347,7 @@ __global__ void __launch_bounds__(HG_BLOCK, 2) k_gp_r0_multi(const GpItem<FP>* _
 }
 
 template <class FP, class TIN, bool SCALE>
-__global__ void __launch_bounds__(HG_BLOCK, 2) k_gp_fold_multi(const GpItem<FP>* __restrict__ items, int nitems) {
+__global__ void __launch_bounds__(HG_BLOCK, FP::GP_MIN_BLOCKS) k_gp_fold_multi(const GpItem<FP>* __restrict__ items, int nitems) {
     typedef typename FP::X X;
     constexpr int NP = 3;
     const GpItem<FP> it = items[gp_find_item<FP>(items, nitems)];
@@ -462,9 +476,10 @@ template <class FP> __global__ void __launch_bounds__(HG_TAIL_THREADS) k_gp_tail
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const GpTailItem<FP> it = items[blockIdx.x];
     const int ntab = 2 * it.nvec;
-    X* A = reinterpret_cast<X*>(smem_raw);                 // [ntab][HG_GP_TAIL]
-    X* Bf = A + (size_t)ntab * HG_GP_TAIL;                 // [ntab][HG_GP_TAIL/2]
-    X* red = Bf + (size_t)ntab * (HG_GP_TAIL / 2);         // [32][4]
+    constexpr int TAIL = 1 << FP::GP_TAIL_LOG;
+    X* A = reinterpret_cast<X*>(smem_raw);          // [ntab][TAIL]
+    X* Bf = A + (size_t)ntab * TAIL;                // [ntab][TAIL/2]
+    X* red = Bf + (size_t)ntab * (TAIL / 2);        // [32][4]
     int len = it.n;
     if (it.from_base) {
         const B* base = (const B*)it.in;  // vector i = [l_i (n) | r_i (n)] -> tables 2i, 2i+1 are consecutive runs of n

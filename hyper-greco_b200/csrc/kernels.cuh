@@ -181,10 +181,7 @@ __global__ void k_eq_split(const typename FP::X* __restrict__ point, int nv, int
     (hi ? eq_hi : eq_lo)[k] = acc;
 }
 
-template <class FP, class T> struct ToBase;
-template <class FP> struct ToBase<FP, u16> { __device__ __forceinline__ static typename FP::B f(u16 v) { return FP::b_from_u64(v); } };
-template <class FP> struct ToBase<FP, u32> { __device__ __forceinline__ static typename FP::B f(u32 v) { return FP::b_from_u64(v); } };
-template <class FP> struct ToBase<FP, u64> { __device__ __forceinline__ static typename FP::B f(u64 v) { return v; } };
+template <class FP, class T> struct ToBase { __device__ __forceinline__ static typename FP::B f(T v) { return FP::to_base(v); } };
 
 // Batched MLE evaluation (mod.rs:80-93, lasso.rs:422-454): out[y] = sum_k eq(point, k) * tables[y][k], one streaming pass
 // per table. Row kh of 2^lo_bits elements is reduced against eq_lo with unreduced accumulation, then scaled by eq_hi[kh].

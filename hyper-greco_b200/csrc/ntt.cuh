@@ -17,13 +17,13 @@ constexpr int HG_NTT_TILE = 16;
 constexpr int HG_NTT_THREADS = 256;
 
 // table[k] = w^k for k < n, w = primitive n-th root (or its inverse)
-template <class FP> __global__ void k_ntt_twiddles(int log_n, int inverse, typename FP::B root_2_32, typename FP::B* __restrict__ table) {
+template <class FP> __global__ void k_ntt_twiddles(int log_n, int inverse, typename FP::B root, typename FP::B* __restrict__ table) {
     typedef typename FP::B B;
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t n = (size_t)1 << log_n;
     if (k >= n) return;
-    B w = root_2_32;  // primitive 2^32-th root of unity
-    for (int i = log_n; i < 32; i++) w = FP::b_mul(w, w);
+    B w = root;  // primitive 2^TWO_ADICITY-th root of unity
+    for (int i = log_n; i < FP::TWO_ADICITY; i++) w = FP::b_mul(w, w);
     if (inverse) w = FP::b_inv(w);
     B r = FP::b_one(), b = w;
     size_t e = k;

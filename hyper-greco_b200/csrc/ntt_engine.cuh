@@ -14,7 +14,7 @@ template <class FP> class NttEngine {
     explicit NttEngine(DeviceCtx* ctx) : ctx_(ctx) {}
     // batched in-place transform of `batch` consecutive vectors of 2^log_n base elements at d_data (device)
     void run(B* d_data, int log_n, bool inverse, size_t batch) {
-        if (log_n < 1 || log_n > 24) throw std::runtime_error("hg_ntt: log_n out of range (1..24)");
+        if (log_n < 1 || log_n > 24 || log_n > FP::TWO_ADICITY) throw std::runtime_error("hg_ntt: log_n out of range");
         cudaStream_t s = ctx_->stream;
         const size_t N = (size_t)1 << log_n;
         const int key = log_n * 2 + (inverse ? 1 : 0);
@@ -22,7 +22,7 @@ template <class FP> class NttEngine {
         if (!tw) {
             tw.reset(new DevBuf<B>());
             tw->alloc(N);
-            HG_K(ctx_, KC_MISC, N * sizeof(B), k_ntt_twiddles<FP><<<(unsigned)((N + 255) / 256), 256, 0, s>>>(log_n, inverse ? 1 : 0, FP::root_of_unity_2_32(), tw->p));
+            HG_K(ctx_, KC_MISC, N * sizeof(B), k_ntt_twiddles<FP><<<(unsigned)((N + 255) / 256), 256, 0, s>>>(log_n, inverse ? 1 : 0, FP::root_of_unity(), tw->p));
         }
         if (scratch_.n < N * batch) { HG_CUDA(cudaStreamSynchronize(s)); scratch_.alloc(N * batch); }
         const int log_n1 = (log_n + 1) / 2, log_n2 = log_n - log_n1;

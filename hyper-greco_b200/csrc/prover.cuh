@@ -570,7 +570,7 @@ template <class FP> class LassoNodeDev {
         h_desc_.alloc(1 << 16);
         d_desc_.alloc(1 << 16);
         HG_CUDA(cudaFuncSetAttribute(k_gp_tail<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)((size_t)2 * (2 * m_) * (HG_GP_TAIL + HG_GP_TAIL / 2) * sizeof(X) + 32 * 4 * sizeof(X))));
+                                     (int)((size_t)2 * (2 * m_) * ((1 << FP::GP_TAIL_LOG) + (1 << FP::GP_TAIL_LOG) / 2) * sizeof(X) + 32 * 4 * sizeof(X))));
         max_blocks_ = ctx->sm_count * 8;
         size_t batch = std::max<size_t>((size_t)m_, pp.C);
         d_partials_.alloc((size_t)max_blocks_ * 4 * batch);
@@ -867,7 +867,7 @@ template <class FP> class LassoNodeDev {
             const auto& j = jobs[k];
             coef[k] = d_gp_coeffs_.p + coef_off;
             coef_off += 2 * (size_t)j.nvec;
-            if (j.n > (size_t)HG_GP_TAIL) {
+            if (j.n > ((size_t)1 << FP::GP_TAIL_LOG)) {
                 size_t a = 2 * (size_t)j.nvec * (j.n / 2), b = 2 * (size_t)j.nvec * (j.n / 4);
                 bufA[k] = d_pool_.p + pool_off; pool_off += a;
                 bufB[k] = d_pool_.p + pool_off; pool_off += b;
@@ -883,7 +883,7 @@ template <class FP> class LassoNodeDev {
             citems[k].c = coef[k]; citems[k].cr = coef[k] + j.nvec; citems[k].n = j.nvec;
         }
         int maxJ = -1;
-        for (auto& j : jobs) if (j.n > (size_t)HG_GP_TAIL) maxJ = std::max(maxJ, j.nv - HG_GP_TAIL_LOG);
+        for (auto& j : jobs) if (j.n > ((size_t)1 << FP::GP_TAIL_LOG)) maxJ = std::max(maxJ, j.nv - FP::GP_TAIL_LOG);
         std::vector<std::vector<GpItem<FP>>> rounds(maxJ + 1);
         std::vector<size_t> round_bytes(maxJ + 1, 0);
         size_t part_need = 0;
@@ -893,7 +893,7 @@ template <class FP> class LassoNodeDev {
             size_t part_off = 0;
             for (int k = 0; k < nl; k++) {
                 const auto& j = jobs[k];
-                if (j.n <= (size_t)HG_GP_TAIL || r > j.nv - HG_GP_TAIL_LOG) continue;
+                if (j.n <= ((size_t)1 << FP::GP_TAIL_LOG) || r > j.nv - FP::GP_TAIL_LOG) continue;
                 GpItem<FP> it;
                 const int ntab = 2 * j.nvec;
                 it.nvec = j.nvec;
@@ -939,15 +939,15 @@ template <class FP> class LassoNodeDev {
             const auto& j = jobs[k];
             GpTailItem<FP>& t = titems[k];
             t.c = coef[k]; t.nvec = j.nvec; t.evals = ch.d_msg(j.evals_off);
-            if (j.n <= (size_t)HG_GP_TAIL) {
+            if (j.n <= ((size_t)1 << FP::GP_TAIL_LOG)) {
                 t.from_base = 1; t.in = j.tables; t.n = (int)j.n; t.rounds = j.nv - 1;
                 t.chal = ch.d_chal(j.r0_idx); t.msg0 = ch.d_msg(j.msg_off); t.msg = ch.d_msg(j.msg_off + 4);
                 tail_bytes += 2 * (size_t)j.nvec * j.n * sizeof(B);
             } else {
-                const int J = j.nv - HG_GP_TAIL_LOG;
-                t.from_base = 0; t.in = (J & 1) ? bufA[k] : bufB[k]; t.n = HG_GP_TAIL; t.rounds = HG_GP_TAIL_LOG - 1;
+                const int J = j.nv - FP::GP_TAIL_LOG;
+                t.from_base = 0; t.in = (J & 1) ? bufA[k] : bufB[k]; t.n = 1 << FP::GP_TAIL_LOG; t.rounds = FP::GP_TAIL_LOG - 1;
                 t.chal = ch.d_chal(j.r0_idx + J); t.msg0 = nullptr; t.msg = ch.d_msg(j.msg_off + 4 + 3 * (size_t)J);
-                tail_bytes += 2 * (size_t)j.nvec * HG_GP_TAIL * sizeof(X);
+                tail_bytes += 2 * (size_t)j.nvec * ((size_t)1 << FP::GP_TAIL_LOG) * sizeof(X);
             }
         }
         // upload descriptors
@@ -977,7 +977,7 @@ template <class FP> class LassoNodeDev {
             HG_LAUNCH_CHECK();
         }
         {
-            const size_t smem = (size_t)2 * (2 * m_) * (HG_GP_TAIL + HG_GP_TAIL / 2) * sizeof(X) + 32 * 4 * sizeof(X);
+            const size_t smem = (size_t)2 * (2 * m_) * ((1 << FP::GP_TAIL_LOG) + (1 << FP::GP_TAIL_LOG) / 2) * sizeof(X) + 32 * 4 * sizeof(X);
             KernelScope ks(ctx_, KC_SC_GP, tail_bytes);
             k_gp_tail<FP><<<nl, HG_TAIL_THREADS, smem, s>>>((const GpTailItem<FP>*)(d_desc_.p + t_off));
             HG_LAUNCH_CHECK();

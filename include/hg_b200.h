@@ -70,6 +70,14 @@ void* hg_buf_device_ptr(hg_buf* buf);
 size_t hg_buf_size(const hg_buf* buf);
 void hg_buf_free(hg_buf* buf);
 
+/* Device tables hold the library's internal representation: canonical u64 for Goldilocks, 4x64-bit Montgomery form for BN254
+ * (32 bytes per element). hg_field_encode converts n base elements that were uploaded as canonical little-endian limbs, in
+ * place; hg_field_decode converts back. Both are no-ops for Goldilocks. Host-pointer inputs of hg_lasso_node_prove are encoded
+ * by the library. */
+size_t hg_field_base_bytes(int field_id);
+int hg_field_encode(hg_ctx* ctx, void* d_data, size_t n);
+int hg_field_decode(hg_ctx* ctx, void* d_data, size_t n);
+
 /* ---- transcript: replaces Keccak256Transcript (bfv-gkr/src/transcript.rs:117-203) ----------------------------- */
 int hg_transcript_new(int field_id, hg_transcript** out);                                      /* ::default()      :431 of sk_encryption_circuit.rs */
 int hg_transcript_from_proof(int field_id, const uint8_t* proof, size_t len, hg_transcript** out); /* ::from_proof  transcript.rs:131-135 */

@@ -36,6 +36,17 @@ for name in ["1024_1x27_65537", "2048_1x52_65537", "4096_2x55_65537"]:
         np.savez_compressed(os.path.join(OUT, f"circuit_io_{name}.npz"), s=u(ins["s"]), e=u(ins["e"]), k1=u(ins["k1"]), ais=u(ins["ais"]),
                             r1is=u(ins["r1is"]), r2is=u(ins["r2is"]), ct0is=u(ct0is))
 
+# BN254 witnesses of the reference (bfv-gkr/src/data/bn254): Lasso inputs as canonical 4 x u64 limbs
+REF_BN = "/root/reference/bfv-gkr/src/data/bn254"
+for name in ["1024_1x27_65537", "2048_1x52_65537"]:
+    P = params.PARAMS[name]
+    args = witness.load_args_json(os.path.join(REF_BN, f"sk_enc_{name}.json"))
+    assert witness.check_circuit_identity(P, args, p=witness.BN_R), name
+    vals = witness.lasso_inputs(P, args, p=witness.BN_R)
+    limbs = np.array([[(v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)] for v in vals], dtype=np.uint64)
+    np.savez_compressed(os.path.join(OUT, f"lasso_inputs_bn254_{name}.npz"), inputs=limbs)
+    print("bn254", name, limbs.shape)
+
 kat = {
     "keccak256_empty": "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470",
     "chain_hashes": [

@@ -342,3 +342,88 @@ def test_full_gkr_prove_full_size_properties(api, ctx, oracle):
     oracle.bfv_verify(0, P, ins, ct0is, proof)
     proof2, _ = prover.prove(dev, d_ct, 0)
     assert proof2 == proof
+
+
+# ------------------------------------------------------------------------------------------------ BN254 Fr (E = F)
+BN_R = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+
+
+@pytest.fixture(scope="module")
+def ctx_bn(api):
+    c = api.Context(0, api.BN254)
+    yield c
+    c.close()
+
+
+def rand_fr(rng, shape):
+    vals = [int.from_bytes(rng.bytes(40), "little") % BN_R for _ in range(int(np.prod(shape)))]
+    return np.array([[(v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)] for v in vals], dtype=np.uint64).reshape(*shape, 4)
+
+
+def test_bn254_device_field_arithmetic(api, ctx_bn, oracle):
+    rng = np.random.default_rng(1)
+    a, b = rand_fr(rng, (300,)), rand_fr(rng, (300,))
+    edge = np.array([[0, 0, 0, 0], [1, 0, 0, 0], [0x43e1f593f0000000, 0x2833e84879b97091, 0xb85045b68181585d, 0x30644e72e131a029]], np.uint64)
+    a[:3], b[:3] = edge, edge[::-1]
+    to_int = lambda l: [sum(int(x[j]) << (64 * j) for j in range(4)) for x in l]
+    ai, bi = to_int(a), to_int(b)
+    for op, f in ((0, lambda x, y: (x + y) % BN_R), (1, lambda x, y: (x - y) % BN_R), (2, lambda x, y: x * y % BN_R)):
+        got = to_int(api.field_selftest(ctx_bn, op, a, b))
+        assert got == [f(x, y) for x, y in zip(ai, bi)], op
+
+
+@pytest.mark.parametrize("arity,nterms,nv", [(1, 3, 4), (2, 1, 1), (2, 4, 7), (2, 6, 3)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_bn254_sumcheck_matches_oracle(api, ctx_bn, oracle, arity, nterms, nv, mode):
+    rng = np.random.default_rng(nv * 10 + nterms)
+    tables = rand_fr(rng, (nterms * arity, 1 << nv))
+    coeffs, claim = rand_fr(rng, (nterms,)), rand_fr(rng, (1,))[0]
+    oproof, te, orr, ofe = oracle.sumcheck_prove(1, arity, coeffs, tables, nv, claim)
+    d = api.DeviceBuffer.from_field(ctx_bn, tables)
+    t = api.Keccak256Transcript(api.BN254)
+    pt, ev = api.sumcheck_prove(ctx_bn, arity, coeffs, d, nv, claim, t, mode)
+    assert t.into_proof() == oproof
+    assert (pt == orr).all() and (ev == ofe).all()
+    d.free()
+
+
+@pytest.mark.parametrize("name", ["1024_1x27_65537", "2048_1x52_65537"])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_bn254_lasso_node_proof_bytes_match_oracle(api, ctx_bn, oracle, golden_dir, name, mode):
+    """The reference's BN254 witnesses (bfv-gkr/src/data/bn254): Lasso node proof bytes == oracle, oracle verifier accepts."""
+    import os
+    from hyper_greco_b200 import params, witness
+    P = params.PARAMS[name]
+    inp = np.load(os.path.join(golden_dir, f"lasso_inputs_bn254_{name}.npz"))["inputs"]
+    bounds, segs, nv = witness.lasso_lookup_bounds(P), witness.lasso_lookup_segments(P), witness.lasso_num_vars(P)
+    opp = oracle.Preprocessing(bounds)
+    rows = np.concatenate([np.full(l, opp.lookup_index(b), np.int32) for b, l in segs])
+    oproof, orr, osum, nsq = oracle.lasso_prove(1, opp, nv, rows, inp)
+    pp = api.LassoPreprocessing.preprocess(bounds)
+    node = api.LassoNode(ctx_bn, pp, nv, segs)
+    tr = api.Keccak256Transcript(api.BN254)
+    if mode == 0:
+        buf = api.DeviceBuffer.from_field(ctx_bn, inp)
+        pt, val = node.prove_claim_reduction(buf, tr, mode, n_inputs=inp.shape[0])
+    else:
+        pt, val = node.prove_claim_reduction(inp, tr, mode)
+    assert tr.into_proof() == oproof
+    assert tr.num_squeezed == nsq
+    assert (pt.reshape(-1) == orr).all() and (val == osum).all()
+    oracle.lasso_verify(1, opp, nv, tr.into_proof())
+    dims, rd, fc, e = node.download_polys()
+    od, ord_, ofc, oe = oracle.lasso_polynomialize(1, opp, nv, rows, inp)
+    assert (dims == od).all() and (e == oe).all()
+    node.free()
+
+
+def test_bn254_ntt_matches_oracle(api, ctx_bn, oracle):
+    rng = np.random.default_rng(2)
+    for log_n in (3, 10, 13):
+        x = rand_fr(rng, (2, 1 << log_n))
+        for inverse in (False, True):
+            d = api.DeviceBuffer.from_field(ctx_bn, x)
+            api.ntt(ctx_bn, d, log_n, inverse, 2)
+            got = d.to_field(2 << log_n).reshape(x.shape)
+            assert (got == oracle.ntt(1, x, log_n, inverse).reshape(x.shape)).all(), (log_n, inverse)
+            d.free()

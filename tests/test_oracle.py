@@ -252,3 +252,25 @@ def test_ntt_is_the_dft_over_the_2_adic_root(oracle):
     assert [int(v) for v in got] == want
     back = oracle.ntt(0, got.reshape(1, -1), log_n, True)[0]
     assert [int(v) for v in back] == x
+
+
+@pytest.mark.parametrize("name", ["1024_1x27_65537", "2048_1x52_65537"])
+def test_bn254_reference_fixture_prove_verify_roundtrip(oracle, golden_dir, name):
+    """test_sk_enc_valid_bn254_* (sk_encryption_circuit.rs:616-620) restricted to the Lasso node: F = E = bn256::Fr."""
+    import hyper_greco_b200  # noqa: F401
+    from hyper_greco_b200 import params, witness
+    P = params.PARAMS[name]
+    inp = np.load(os.path.join(golden_dir, f"lasso_inputs_bn254_{name}.npz"))["inputs"]
+    opp = oracle.Preprocessing(witness.lasso_lookup_bounds(P))
+    rows = np.concatenate([np.full(l, opp.lookup_index(b), np.int32) for b, l in witness.lasso_lookup_segments(P)])
+    nv = witness.lasso_num_vars(P)
+    proof, r, s, nsq = oracle.lasso_prove(1, opp, nv, rows, inp)
+    r2, s2, used = oracle.lasso_verify(1, opp, nv, proof)
+    assert used == len(proof) and (r == r2).all() and (s == s2).all()
+    padded = np.zeros((1 << nv, 4), np.uint64)
+    padded[: inp.shape[0]] = inp
+    assert (oracle.mle_eval(1, padded, nv, r) == s).all()
+    bad = bytearray(proof)
+    bad[-1] ^= 1
+    with pytest.raises(oracle.OracleError):
+        oracle.lasso_verify(1, opp, nv, bytes(bad))
