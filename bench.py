@@ -5,7 +5,9 @@
     python bench.py --impl reference --gpus 1 --steps K --warmup W   # CPU arm: the oracle port on the host cores
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # one rank per GPU, weak scaling
 
-A step = one proof: LassoNode::prove_claim_reduction (lasso/src/lasso.rs:57-114) on a synthetic BFV SK-encryption witness
+    torchrun ... bench.py --gpus N --shard                         # extra: ONE Lasso-node proof split over N GPUs (strong scaling)
+
+A step = one proof: gkr::prove_gkr of the BFV SK-encryption circuit (sk_encryption_circuit.rs:455-457) on a synthetic witness
 of the n=32768, k=16, Goldilocks parameter set (BASELINE.json metric config). Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -310,6 +312,71 @@ def run_ours(args):
         print(json.dumps(line))
 
 
+def run_shard(args):
+    """SURVEY.md §8e: one LassoNode::prove_claim_reduction split over the ranks by grand-product terms. Every rank holds the
+    node input on its device; per step each rank proves its shard, the message buffers are gathered to rank 0 over NCCL and
+    summed in the field, rank 0 serialises. Time = wall clock of K steps between barriers, max over ranks (the step
+    includes a host-side merge, so device events alone would miss part of it)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import hyper_greco_b200  # noqa: F401
+    from hyper_greco_b200 import api
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    P, inp, bounds, segs, nv = make_case(args.config, seed=0)      # the SAME witness on every rank
+    ctx = api.Context(local)
+    pp = api.LassoPreprocessing.preprocess(bounds)
+    node = api.LassoNode(ctx, pp, nv, segs)
+    buf = api.DeviceBuffer.from_numpy(ctx, inp)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        tr = api.Keccak256Transcript()
+        part = node.prove_shard(buf, tr, rank, world, n_inputs=inp.size)
+        merged = api.gather_and_merge(api.GOLDILOCKS, part, None) if world > 1 else part
+        if rank == 0:
+            node.emit_shard(merged)
+            return tr.into_proof()
+        return None
+
+    for _ in range(max(args.warmup, 3)):
+        proof = step()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    barrier()
+    t = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    same = None
+    if rank == 0:
+        tr = api.Keccak256Transcript()
+        node.prove_claim_reduction(buf, tr, api.MODE_PREFETCH, n_inputs=inp.size)
+        same = tr.into_proof() == proof
+        print(json.dumps({"metric": "lasso_node_sharded_proofs_per_sec", "value": args.steps / float(t[0]), "unit": UNIT, "n_gpus": world,
+                          "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1000.0 * float(t[0]) / args.steps,
+                          "higher_is_better": True, "scaling": "strong", "dtype": "u64", "data": "synthetic",
+                          "config": {"workload": f"ONE LassoNode::prove_claim_reduction (num_vars={nv}, memories={pp.num_memories}) split over {world} GPUs by "
+                                                 "grand-product terms; message buffers gathered to rank 0 and summed in the field", "params": args.config},
+                          "sharded_proof_equals_single_gpu_proof": same}))
+    barrier()
+    node.free()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def node_chal_bytes(nv, lm=16):
     gp = lambda k: sum(1 + ((1 + j) if j else 0) for j in range(k))
     return 16 * (2 * nv + 2 + gp(nv) + gp(lm))
@@ -323,9 +390,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=DEFAULT_CONFIG)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", action="store_true", help="extra measurement: one Lasso-node proof split over the N GPUs (strong scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.shard:
+        run_shard(args)
     else:
         run_ours(args)
 

@@ -29,7 +29,8 @@ SYMBOLS = [
     "hg_lasso_preprocess", "hg_lasso_pp_free", "hg_lasso_pp_num_lookups", "hg_lasso_pp_num_subtables", "hg_lasso_pp_num_memories",
     "hg_lasso_pp_lookup_index", "hg_lasso_pp_memory_maps", "hg_lasso_pp_subtable_id", "hg_lasso_node_new", "hg_lasso_node_free",
     "hg_lasso_node_log2_input_size", "hg_lasso_node_device_bytes", "hg_lasso_node_prove", "hg_lasso_node_download_polys",
-    "hg_lasso_node_num_chunks", "hg_lasso_node_timing", "hg_sumcheck_prove", "hg_mle_eval_batch", "hg_ntt", "hg_bfv_evaluate", "hg_field_selftest",
+    "hg_lasso_node_num_chunks", "hg_lasso_node_timing", "hg_lasso_node_shard_words", "hg_lasso_node_prove_shard", "hg_lasso_node_emit_shard",
+    "hg_shard_merge", "hg_sumcheck_prove", "hg_mle_eval_batch", "hg_ntt", "hg_bfv_evaluate", "hg_field_selftest",
     "hg_circuit_new", "hg_circuit_free", "hg_circuit_insert_input", "hg_circuit_insert_fft", "hg_circuit_insert_lasso", "hg_circuit_insert_vanilla",
     "hg_circuit_connect", "hg_circuit_evaluate", "hg_circuit_node_value", "hg_gkr_prove", "hg_gkr_timing", "hg_gkr_num_challenges", "hg_gkr_num_inputs", "hg_gkr_num_input_claims",
     "hg_gkr_input_claim_num_vars", "hg_gkr_input_claim",
@@ -104,6 +105,11 @@ def lib():
         L.hg_lasso_node_timing.restype = None
         L.hg_lasso_node_prove.argtypes = [vp, vp, sz, i32, vp, i32, vp, vp]
         L.hg_lasso_node_download_polys.argtypes = [vp, vp, vp, vp, vp]
+        L.hg_lasso_node_shard_words.argtypes = [vp]
+        L.hg_lasso_node_shard_words.restype = sz
+        L.hg_lasso_node_prove_shard.argtypes = [vp, vp, sz, i32, vp, i32, i32, vp, sz, C.POINTER(sz)]
+        L.hg_lasso_node_emit_shard.argtypes = [vp, vp, sz, vp, vp]
+        L.hg_shard_merge.argtypes = [i32, vp, vp, sz]
         L.hg_sumcheck_prove.argtypes = [vp, i32, sz, sz, vp, vp, vp, vp, i32, vp, vp]
         L.hg_mle_eval_batch.argtypes = [vp, vp, sz, sz, sz, vp, vp]
         L.hg_field_selftest.argtypes = [vp, i32, vp, vp, sz, vp]
@@ -399,6 +405,43 @@ class LassoNode:
             _chk(lib().hg_lasso_node_prove(self.h, _p(arr), n, 0, transcript.h, mode, _p(pt), _p(val)))
         return pt, val
 
+    # ---- one proof over several GPUs (include/hg_b200.h, "one proof over several GPUs")
+    def prove_shard(self, inputs, transcript: Keccak256Transcript, rank: int, world: int, n_inputs=None):
+        """This rank's part of the node's message buffer (uint64 words, device representation; slots of other ranks are 0)."""
+        cap = int(lib().hg_lasso_node_shard_words(self.h))
+        out = np.zeros(cap, np.uint64)
+        nw = C.c_size_t(0)
+        if isinstance(inputs, DeviceBuffer):
+            n = n_inputs if n_inputs is not None else inputs.nbytes // (8 * LIMBS[self.ctx.field])
+            _chk(lib().hg_lasso_node_prove_shard(self.h, inputs.ptr, n, 1, transcript.h, rank, world, _p(out), cap, C.byref(nw)))
+        else:
+            arr = np.ascontiguousarray(inputs, np.uint64)
+            n = arr.size // LIMBS[self.ctx.field]
+            _chk(lib().hg_lasso_node_prove_shard(self.h, _p(arr), n, 0, transcript.h, rank, world, _p(out), cap, C.byref(nw)))
+        return out[: nw.value]
+
+    def emit_shard(self, merged):
+        """Rank 0, after prove_shard on this node: serialise the merged message buffer into the transcript given to prove_shard."""
+        merged = np.ascontiguousarray(merged, np.uint64)
+        pt = np.zeros((self.num_vars, self._el), np.uint64)
+        val = np.zeros(self._el, np.uint64)
+        _chk(lib().hg_lasso_node_emit_shard(self.h, _p(merged), merged.size, _p(pt), _p(val)))
+        return pt, val
+
+    def prove_claim_reduction_sharded(self, inputs, transcript: Keccak256Transcript, group=None, n_inputs=None):
+        """prove_claim_reduction with the node's grand-product terms split over the ranks of a torch.distributed group
+        (one process per GPU, every rank holds the inputs and a transcript in the same state). The only exchange is one
+        gather of the message buffers to rank 0, which sums them and writes the proof; other ranks return None."""
+        import torch
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        part = self.prove_shard(inputs, transcript, rank, world, n_inputs)
+        merged = gather_and_merge(self.ctx.field, part, group)
+        if rank != 0:
+            return None
+        return self.emit_shard(merged)
+
     def timing(self):
         """Host phases of the last prove in microseconds: squeeze+upload challenges, enqueue, wait for GPU, serialise."""
         out = np.zeros(4, np.float64)
@@ -424,6 +467,39 @@ class LassoNode:
             self.free()
         except Exception:
             pass
+
+
+def shard_merge(field: int, acc, part):
+    """acc += part element-wise in the field (message buffers of LassoNode.prove_shard); in place, returns acc."""
+    acc = np.ascontiguousarray(acc, np.uint64)
+    part = np.ascontiguousarray(part, np.uint64)
+    if acc.size != part.size:
+        raise HgError("shard_merge: buffers of different length")
+    _chk(lib().hg_shard_merge(field, _p(acc), _p(part), acc.size))
+    return acc
+
+
+def gather_and_merge(field: int, part, group=None):
+    """Gathers the per-rank message buffers on rank 0 (NCCL when the group has it, else gloo) and sums them in the field.
+    Returns the merged buffer on rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world == 1:
+        return part
+    backend = dist.get_backend(group)
+    t = torch.from_numpy(part.view(np.int64))
+    if backend == "nccl":
+        t = t.cuda()
+    bufs = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+    dist.gather(t, bufs, dst=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    if rank != 0:
+        return None
+    acc = part.copy()
+    for r in range(1, world):
+        shard_merge(field, acc, bufs[r].cpu().numpy().view(np.uint64))
+    return acc
 
 
 def sumcheck_prove(ctx: Context, arity, coeffs_ext, d_tables: DeviceBuffer, num_vars, claim_ext, transcript, mode=MODE_PREFETCH):

@@ -74,6 +74,10 @@ struct ILassoNode {
     virtual ~ILassoNode() {}
     virtual void prove(DeviceCtx* dev, const void* inputs, size_t n_inputs, bool on_device, ITranscript* t, int mode, const WireOptions& wo,
                        uint64_t* out_point, uint64_t* out_value) = 0;
+    virtual void prove_shard(DeviceCtx* dev, const void* inputs, size_t n_inputs, bool on_device, ITranscript* t, const WireOptions& wo, int rank, int world,
+                             uint64_t* out_words, size_t cap_words, size_t* n_words) = 0;
+    virtual void emit_shard(const uint64_t* merged, size_t n_words, uint64_t* out_point, uint64_t* out_value) = 0;
+    virtual size_t shard_words() const = 0;
     virtual size_t device_bytes() const = 0;
     virtual size_t num_chunks() const = 0;
     virtual const double* timing() const = 0;
@@ -101,6 +105,31 @@ template <class FP> struct LassoNodeT : ILassoNode {
         if (out_point) for (size_t i = 0; i < pt.size(); i++) FP::x_to_limbs(pt[i], out_point + FP::X_LIMBS * i);
         if (out_value) FP::x_to_limbs(val, out_value);
     }
+    const B* stage(DeviceCtx* dev, const void* inputs, size_t n_inputs, bool on_device) {
+        if (on_device) return (const B*)inputs;
+        if (staging.n < n_inputs) staging.alloc(n_inputs);
+        HG_CUDA(cudaMemcpyAsync(staging.p, inputs, n_inputs * sizeof(B), cudaMemcpyHostToDevice, dev->stream));
+        if (FP::FIELD_ID == 1) { k_field_encode<FP><<<(unsigned)((n_inputs + 255) / 256), 256, 0, dev->stream>>>(staging.p, n_inputs, 0); HG_LAUNCH_CHECK(); }
+        return staging.p;
+    }
+    static constexpr size_t XW = sizeof(X) / sizeof(uint64_t);  // messages cross the boundary in the device representation
+    void prove_shard(DeviceCtx* dev, const void* inputs, size_t n_inputs, bool on_device, ITranscript* t, const WireOptions& wo, int rank, int world,
+                     uint64_t* out_words, size_t cap_words, size_t* n_words) override {
+        size_t count = 0;
+        const X* part = node.prove_shard(stage(dev, inputs, n_inputs, on_device), n_inputs, *(Keccak256Transcript<FP>*)t->raw(), wo, rank, world, &count);
+        if (count * XW > cap_words) throw std::runtime_error("prove_shard: message buffer too small (see hg_lasso_node_shard_words)");
+        memcpy(out_words, part, count * sizeof(X));
+        *n_words = count * XW;
+    }
+    void emit_shard(const uint64_t* merged, size_t n_words, uint64_t* out_point, uint64_t* out_value) override {
+        if (n_words % XW) throw std::runtime_error("emit_shard: truncated message buffer");
+        std::vector<X> pt;
+        X val;
+        node.emit_shard((const X*)merged, n_words / XW, &pt, &val);
+        if (out_point) for (size_t i = 0; i < pt.size(); i++) FP::x_to_limbs(pt[i], out_point + FP::X_LIMBS * i);
+        if (out_value) FP::x_to_limbs(val, out_value);
+    }
+    size_t shard_words() const override { return node.shard_message_count() * XW; }
     size_t device_bytes() const override { return node.device_bytes(); }
     size_t num_chunks() const override { return node.chunk_dims().size(); }
     const double* timing() const override { return node.timing(); }
@@ -197,6 +226,7 @@ struct IFieldOps {
                               const void* d_r2is, void* d_lasso, void* d_sum) = 0;
     virtual void selftest(DeviceCtx* ctx, int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) = 0;
     virtual void encode(DeviceCtx* ctx, void* d, size_t n, bool decode) = 0;
+    virtual void shard_merge(uint64_t* acc, const uint64_t* part, size_t n_words) = 0;
     virtual size_t base_bytes() const = 0;
 };
 template <class FP> struct FieldOpsT : IFieldOps {
@@ -208,6 +238,13 @@ template <class FP> struct FieldOpsT : IFieldOps {
     ILassoNode* new_lasso_node(DeviceCtx* ctx, const LassoPreprocessing& pp, int nv, const std::vector<uint8_t>& rows) override { return new LassoNodeT<FP>(ctx, pp, nv, rows); }
     ICircuit* new_circuit(DeviceCtx* ctx) override { return new CircuitT<FP>(ctx, eng(ctx)); }
     size_t base_bytes() const override { return sizeof(B); }
+    void shard_merge(uint64_t* acc, const uint64_t* part, size_t n_words) override {
+        constexpr size_t XW = sizeof(X) / sizeof(uint64_t);
+        if (n_words % XW) throw std::runtime_error("shard_merge: truncated message buffer");
+        X* a = (X*)acc;
+        const X* b = (const X*)part;
+        for (size_t i = 0; i < n_words / XW; i++) a[i] = FP::x_add(a[i], b[i]);
+    }
     void encode(DeviceCtx* ctx, void* d, size_t n, bool decode) override {
         if (FP::FIELD_ID != 1 || !n) return;
         k_field_encode<FP><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((B*)d, n, decode ? 1 : 0);
@@ -346,6 +383,12 @@ struct hg_lasso_node {
 static IFieldOps* make_ops(int field_id) {
     if (field_id == HG_FIELD_GOLDILOCKS) return new FieldOpsT<GlField>();
     if (field_id == HG_FIELD_BN254) return new FieldOpsT<FrField>();
+    throw std::runtime_error("unknown field id");
+}
+static IFieldOps* ops_for_field(int field_id) {  // host-only helpers that need no context
+    static std::unique_ptr<IFieldOps> gl(make_ops(HG_FIELD_GOLDILOCKS)), fr(make_ops(HG_FIELD_BN254));
+    if (field_id == HG_FIELD_GOLDILOCKS) return gl.get();
+    if (field_id == HG_FIELD_BN254) return fr.get();
     throw std::runtime_error("unknown field id");
 }
 static ITranscript* make_transcript(int field_id, const uint8_t* proof, size_t len, bool reading) {
@@ -556,6 +599,22 @@ int hg_lasso_node_prove(hg_lasso_node* node, const void* inputs, size_t n_inputs
         if (t->t->field_id != node->n->field_id) throw std::runtime_error("transcript belongs to another field");
         node->n->prove(&ctx->dev, inputs, n_inputs, inputs_on_device != 0, t->t.get(), mode, ctx->wire, out_point, out_value);
     })
+}
+size_t hg_lasso_node_shard_words(const hg_lasso_node* node) { return node->n->shard_words(); }
+int hg_lasso_node_prove_shard(hg_lasso_node* node, const void* inputs, size_t n_inputs, int inputs_on_device, hg_transcript* t, int rank, int world,
+                              uint64_t* out_words, size_t cap_words, size_t* n_words) {
+    HG_TRY({
+        hg_ctx* ctx = node->ctx;
+        HG_CUDA(cudaSetDevice(ctx->dev.device));
+        if (t->t->field_id != node->n->field_id) throw std::runtime_error("transcript belongs to another field");
+        node->n->prove_shard(&ctx->dev, inputs, n_inputs, inputs_on_device != 0, t->t.get(), ctx->wire, rank, world, out_words, cap_words, n_words);
+    })
+}
+int hg_lasso_node_emit_shard(hg_lasso_node* node, const uint64_t* merged_words, size_t n_words, uint64_t* out_point, uint64_t* out_value) {
+    HG_TRY({ node->n->emit_shard(merged_words, n_words, out_point, out_value); })
+}
+int hg_shard_merge(int field, uint64_t* acc_words, const uint64_t* part_words, size_t n_words) {
+    HG_TRY({ ops_for_field(field)->shard_merge(acc_words, part_words, n_words); })
 }
 int hg_lasso_node_download_polys(hg_lasso_node* node, uint16_t* dims, uint32_t* read_cts, uint32_t* final_cts, uint64_t* e_polys) {
     HG_TRY({

@@ -217,6 +217,8 @@ template <class FP> struct GpItem {
     unsigned* counter;
     int nvec, tpg, bx, groups;
     int blk_start, nblk;
+    int i_begin, i_end;              // terms (vectors) this device owns: a proof can be split over GPUs by terms (h is linear in them)
+    int write_t0;                    // table 0 (= t_0) is folded by every device; written here when term 0 is not owned
 };
 
 template <class FP, int NP>
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(HG_BLOCK, FP::GP_MIN_BLOCKS) k_gp_r0_multi(con
     const unsigned bxi = lb % it.bx, grp = lb / it.bx;
     const B* tables = (const B*)it.in;
     const size_t n = it.n_in, npairs = n / 2, stride = (size_t)it.bx * blockDim.x;
-    const int i0 = grp * it.tpg, i1 = min(it.nvec, i0 + it.tpg);
+    const int i0 = it.i_begin + grp * it.tpg, i1 = min(it.i_end, i0 + it.tpg);
     typename FP::XAcc accx[NP];
 #pragma unroll
     for (int p = 0; p < NP; p++) accx[p] = FP::xacc_zero_();
@@ -356,7 +358,7 @@ __global__ void __launch_bounds__(HG_BLOCK, FP::GP_MIN_BLOCKS) k_gp_fold_multi(c
     const TIN* in = (const TIN*)it.in;
     X* out = it.out;
     const size_t n_in = it.n_in, npairs = n_in / 4, n_out = n_in / 2;
-    const int i0 = grp * it.tpg, i1 = min(it.nvec, i0 + it.tpg);
+    const int i0 = it.i_begin + grp * it.tpg, i1 = min(it.i_end, i0 + it.tpg);
     const X r = *it.r_prev;
     const typename FP::FoldAux aux = FP::fold_aux(r);
     X acc[NP];
@@ -369,6 +371,7 @@ __global__ void __launch_bounds__(HG_BLOCK, FP::GP_MIN_BLOCKS) k_gp_fold_multi(c
             load4(in + 4 * b, a);
             X lo = FP::fold(a[0], a[1], r, aux), hi = FP::fold(a[2], a[3], r, aux);
             t0[0] = lo; t0[1] = FP::slope(lo, hi); t0[2] = FP::at_m1(lo, hi);
+            if (it.write_t0 && grp == 0) store2(out + 2 * b, lo, hi);
         }
         typename FP::XAcc P[NP];
 #pragma unroll
@@ -444,6 +447,7 @@ template <class FP> struct GpTailItem {
     typename FP::X* msg;            // 3 slots per tail round
     typename FP::X* evals;          // 2*nvec final evaluations (l_i for i > 0 scaled by c_i)
     int from_base, n, nvec, rounds;
+    int i_begin, i_end;             // owned terms (see GpItem)
 };
 
 template <class FP, int NP>
@@ -488,8 +492,8 @@ template <class FP> __global__ void __launch_bounds__(HG_TAIL_THREADS) k_gp_tail
         // round 0 on the unscaled tables: h(0), h(inf), h(-1), h(1)
         X acc[4] = {FP::x_zero(), FP::x_zero(), FP::x_zero(), FP::x_zero()};
         const int npairs = len / 2;
-        for (int e = threadIdx.x; e < it.nvec * npairs; e += blockDim.x) {
-            const int i = e / npairs, b = e % npairs;
+        for (int e = threadIdx.x; e < (it.i_end - it.i_begin) * npairs; e += blockDim.x) {
+            const int i = it.i_begin + e / npairs, b = e % npairs;
             const X t_lo = A[2 * b], t_hi = A[2 * b + 1];
             const X l_lo = A[(2 * i) * len + 2 * b], l_hi = A[(2 * i) * len + 2 * b + 1];
             const X r_lo = A[(2 * i + 1) * len + 2 * b], r_hi = A[(2 * i + 1) * len + 2 * b + 1];
@@ -519,8 +523,14 @@ template <class FP> __global__ void __launch_bounds__(HG_TAIL_THREADS) k_gp_tail
         const typename FP::FoldAux aux = FP::fold_aux(r);
         const int npairs = len / 4, half = len / 2;
         X acc[3] = {FP::x_zero(), FP::x_zero(), FP::x_zero()};
-        for (int e = threadIdx.x; e < it.nvec * npairs; e += blockDim.x) {
-            const int i = e / npairs, b = e % npairs;
+        if (it.i_begin > 0)  // t_0's table is folded on every device
+            for (int b = threadIdx.x; b < npairs; b += blockDim.x) {
+                const X* t = cur + 4 * b;
+                nxt[2 * b] = FP::fold(t[0], t[1], r, aux);
+                nxt[2 * b + 1] = FP::fold(t[2], t[3], r, aux);
+            }
+        for (int e = threadIdx.x; e < (it.i_end - it.i_begin) * npairs; e += blockDim.x) {
+            const int i = it.i_begin + e / npairs, b = e % npairs;
             const X* t = cur + 4 * b;
             const X* l = cur + (2 * i) * len + 4 * b;
             const X* q = cur + (2 * i + 1) * len + 4 * b;
@@ -545,7 +555,7 @@ template <class FP> __global__ void __launch_bounds__(HG_TAIL_THREADS) k_gp_tail
     // len == 2: final evaluations
     const X r = it.chal[it.rounds];
     const typename FP::FoldAux aux = FP::fold_aux(r);
-    for (int t = threadIdx.x; t < ntab; t += blockDim.x) it.evals[t] = FP::fold(cur[2 * t], cur[2 * t + 1], r, aux);
+    for (int t = 2 * it.i_begin + threadIdx.x; t < 2 * it.i_end; t += blockDim.x) it.evals[t] = FP::fold(cur[2 * t], cur[2 * t + 1], r, aux);
 }
 
 }  // namespace hg

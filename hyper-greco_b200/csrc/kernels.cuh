@@ -277,9 +277,10 @@ __global__ void k_tree_up(const typename FP::B* __restrict__ in, typename FP::B*
 }
 // roots (prover.rs:197-203) and the nv = 0 layer's evaluations (prover.rs:232-236) from the top layer [nvec][2]
 template <class FP>
-__global__ void k_tree_top(const typename FP::B* __restrict__ top, int nvec, typename FP::X* __restrict__ roots, typename FP::X* __restrict__ evals) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nvec) return;
+__global__ void k_tree_top(const typename FP::B* __restrict__ top, int i_begin, int i_end, typename FP::X* __restrict__ roots,
+                           typename FP::X* __restrict__ evals) {
+    const int i = i_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i_end) return;
     typename FP::B l = top[2 * i], r = top[2 * i + 1];
     roots[i] = FP::lift(FP::b_mul(l, r));
     evals[2 * i] = FP::lift(l);

@@ -181,6 +181,24 @@ template <class FP> class Channel {
         if (wait_us) *wait_us = t1 - t0;
         if (emit_us) *emit_us = now() - t1;
     }
+    // ---- a proof split over several devices (LassoNodeDev::prove_shard): every device fills the message slots of the terms
+    // it owns and leaves the others zero; the element-wise sum over devices is the message buffer of the whole proof
+    void zero_messages() { HG_CUDA(cudaMemsetAsync(d_msg_.p, 0, d_msg_.bytes(), ctx_->stream)); }
+    // bring every message to the host WITHOUT serialising (the serialisers stay queued for emit_merged)
+    const X* download_partial(size_t* count) {
+        HG_CUDA(cudaMemcpyAsync(h_msg_.p, d_msg_.p, msg_cursor_ * sizeof(X), cudaMemcpyDeviceToHost, ctx_->stream));
+        HG_CUDA(cudaStreamSynchronize(ctx_->stream));
+        *count = msg_cursor_;
+        return h_msg_.p;
+    }
+    // replace the host copy of the messages by the merged one and serialise
+    void emit_merged(const X* merged, size_t count) {
+        if (count != msg_cursor_) throw std::runtime_error("Channel: merged message count does not match this proof");
+        memcpy(h_msg_.p, merged, count * sizeof(X));
+        msg_ready_ = msg_cursor_;
+        for (; deferred_done_ < deferred_.size(); deferred_done_++) deferred_[deferred_done_]();
+    }
+    size_t msg_used() const { return msg_cursor_; }
     const X* d_chal(size_t i) const { return d_chal_.p + i; }
     X* d_msg(size_t i) { return d_msg_.p + i; }
     X chal(size_t i) const { if (i >= chal_ready_) throw std::runtime_error("Channel: challenge not squeezed yet"); return h_chal_.p[i]; }
@@ -337,7 +355,7 @@ void launch_sc_round(DeviceCtx* ctx, int kclass, bool in_base, bool fold, const 
 template <class FP, int ARITY>
 void sumcheck_dev(DeviceCtx* ctx, int kclass, Channel<FP>& ch, const WireOptions& wo, const typename FP::B* d_tables, size_t n, int nterm,
                   const typename FP::X* d_coeffs, typename FP::X* bufA, typename FP::X* bufB, const ScScratch& sc,
-                  std::shared_ptr<ScHostState<FP>> st, size_t* first_chal, size_t* evals_off) {
+                  std::shared_ptr<ScHostState<FP>> st, size_t* first_chal, size_t* evals_off, bool launch = true) {
     typedef typename FP::B B;
     typedef typename FP::X X;
     constexpr int D = ARITY + 1;
@@ -352,10 +370,10 @@ void sumcheck_dev(DeviceCtx* ctx, int kclass, Channel<FP>& ch, const WireOptions
     for (int j = 0; j < nv; j++) {
         size_t off = ch.alloc_msg(j == 0 ? D + 1 : D);
         if (j == 0) {
-            launch_sc_round<FP, ARITY>(ctx, kclass, true, false, d_tables, nullptr, n, nterm, d_coeffs, nullptr, sc, ch.d_msg(off));
+            if (launch) launch_sc_round<FP, ARITY>(ctx, kclass, true, false, d_tables, nullptr, n, nterm, d_coeffs, nullptr, sc, ch.d_msg(off));
         } else {
             X* out = (j & 1) ? bufA : bufB;
-            launch_sc_round<FP, ARITY>(ctx, kclass, in_base, true, cur_in, out, n_in, nterm, d_coeffs, ch.d_chal(prev_chal), sc, ch.d_msg(off));
+            if (launch) launch_sc_round<FP, ARITY>(ctx, kclass, in_base, true, cur_in, out, n_in, nterm, d_coeffs, ch.d_chal(prev_chal), sc, ch.d_msg(off));
             cur_in = out; in_base = false; n_in >>= 1;
         }
         const size_t next_idx = ch.next_index();  // the challenge squeezed right after this message
@@ -366,10 +384,11 @@ void sumcheck_dev(DeviceCtx* ctx, int kclass, Channel<FP>& ch, const WireOptions
     }
     // final evaluations: the tables now have 2 elements each
     size_t eo = ch.alloc_msg(ntab);
+    if (evals_off) *evals_off = eo;
+    if (!launch) return;
     int blocks = (ntab + HG_BLOCK - 1) / HG_BLOCK;
     if (in_base) HG_K(ctx, kclass, 2 * ntab * sizeof(B), k_fold_final<FP, B><<<blocks, HG_BLOCK, 0, ctx->stream>>>((const B*)cur_in, ntab, ch.d_chal(prev_chal), ch.d_msg(eo)));
     else HG_K(ctx, kclass, 2 * ntab * sizeof(X), k_fold_final<FP, X><<<blocks, HG_BLOCK, 0, ctx->stream>>>((const X*)cur_in, ntab, ch.d_chal(prev_chal), ch.d_msg(eo)));
-    if (evals_off) *evals_off = eo;
 }
 
 // one layer sumcheck recorded for batched execution (prefetch mode): everything the device needs is static
@@ -628,6 +647,34 @@ template <class FP> class LassoNodeDev {
         if (out_value) *out_value = ch.msg(sum_off);
     }
 
+    // ---- one proof over `world` devices. The round polynomials of the grand-product sumchecks are sums over
+    // the 2m vectors (terms c_i * t_0 * l_i * r_i), the final evaluations / roots / openings belong to one vector or memory
+    // each: device `rank` computes the terms it owns from its own copy of the witness, every message slot it does not own
+    // stays zero, and the element-wise field sum of the message buffers over devices is the buffer a single device would
+    // have produced. The challenges do not depend on the messages, so no device waits for another; the only
+    // exchange is that one sum of `shard_message_count()` elements, after which rank 0 serialises (emit_shard).
+    // Returns this device's partial message buffer (pinned host memory, valid until the next prove).
+    const X* prove_shard(const B* d_inputs, size_t n_inputs, Keccak256Transcript<FP>& tr, const WireOptions& wo, int rank, int world, size_t* count) {
+        if (world < 1 || rank < 0 || rank >= world || world > 2 * m_) throw std::runtime_error("LassoNode: bad shard rank / world size");
+        Channel<FP>& ch = *ch_;
+        shard_rank_ = rank; shard_world_ = world;
+        struct Reset { LassoNodeDev* n; ~Reset() { n->shard_rank_ = 0; n->shard_world_ = 1; } } reset{this};
+        enqueue_witness(d_inputs, n_inputs, wo);
+        ch.zero_messages();
+        ch.begin(&tr, kModePrefetch, total_chal_);
+        enqueue_protocol(ch, kModePrefetch, wo, &shard_r_idx_, &shard_sum_off_);
+        if (ch.chal_used() != total_chal_) throw std::runtime_error("LassoNode: challenge count mismatch");
+        return ch.download_partial(count);
+    }
+    // rank 0, after prove_shard on the same node: write the proof from the merged message buffer
+    void emit_shard(const X* merged, size_t count, std::vector<X>* out_point, X* out_value) {
+        Channel<FP>& ch = *ch_;
+        ch.emit_merged(merged, count);
+        if (out_point) { out_point->resize(num_vars_); for (int i = 0; i < num_vars_; i++) (*out_point)[i] = ch.chal(shard_r_idx_ + i); }
+        if (out_value) *out_value = ch.msg(shard_sum_off_);
+    }
+    size_t shard_message_count() const { return msg_budget_; }
+
     // polynomialize (lasso.rs:157-250): everything that needs no challenge
     void enqueue_witness(const B* d_inputs, size_t n_inputs, const WireOptions& wo) {
         cudaStream_t s = ctx_->stream;
@@ -672,7 +719,8 @@ template <class FP> class LassoNodeDev {
         // ---- r, claimed sum (lasso.rs:85, :264, :269)
         const size_t r_idx = ch.squeeze(v);
         const size_t sum_off = ch.alloc_msg(1);
-        eval_tables<B>(ch, d_out_.p, R, 1, R, r_idx, v, sum_off);
+        const bool lead = shard_rank_ == 0;  // the claim, the collation sumcheck and the dim / counter openings belong to rank 0
+        if (lead) eval_tables<B>(ch, d_out_.p, R, 1, R, r_idx, v, sum_off);
         auto coll_state = std::make_shared<ScHostState<FP>>();
         {
             Channel<FP>* chp = &ch;
@@ -688,7 +736,7 @@ template <class FP> class LassoNodeDev {
             // g(E_0, S) = E_0 * (0 * E_0 + 1 * S): nterm = 2, arity 1, tables [E_0 | S]
             HG_CUDA(cudaMemcpyAsync(d_gp_coeffs_.p, one_one, sizeof one_one, cudaMemcpyHostToDevice, s));
             HG_CUDA(cudaStreamSynchronize(s));
-            sumcheck_dev<FP, 1>(ctx_, KC_SC_COLL, ch, wo, d_coll_.p, R, 2, d_gp_coeffs_.p, d_bufA_.p, d_bufB_.p, sc_, coll_state, nullptr, nullptr);
+            sumcheck_dev<FP, 1>(ctx_, KC_SC_COLL, ch, wo, d_coll_.p, R, 2, d_gp_coeffs_.p, d_bufA_.p, d_bufB_.p, sc_, coll_state, nullptr, nullptr, lead);
         }
         // ---- gamma, tau (lasso.rs:99)
         const size_t gt_idx = ch.squeeze(2);
@@ -715,11 +763,18 @@ template <class FP> class LassoNodeDev {
         // ---- openings (prover.rs:173-178, mod.rs:80-93)
         const size_t o_dims = ch.alloc_msg(pp_.C), o_rts = ch.alloc_msg(nslots_), o_fcs = ch.alloc_msg(nslots_), o_e = ch.alloc_msg(m);
         build_eq(ch, x_idx, v);
-        dot_tables<u16>(ch, d_dims_.p, R, (int)pp_.C, R, o_dims);
-        dot_tables<u32>(ch, d_read_cts_.p, R, nslots_, R, o_rts);
-        dot_tables<B>(ch, d_E_.p, R, m, R, o_e);
-        build_eq(ch, y_idx, log2M_);
-        dot_tables<u32>(ch, d_final_cts_.p, M, nslots_, M, o_fcs);
+        if (lead) {
+            dot_tables<u16>(ch, d_dims_.p, R, (int)pp_.C, R, o_dims);
+            dot_tables<u32>(ch, d_read_cts_.p, R, nslots_, R, o_rts);
+        }
+        {   // E_i openings: memories split evenly over the devices
+            const int e0 = (int)((size_t)m * shard_rank_ / shard_world_), e1 = (int)((size_t)m * (shard_rank_ + 1) / shard_world_);
+            if (e1 > e0) dot_tables<B>(ch, d_E_.p + (size_t)e0 * R, R, e1 - e0, R, o_e + e0);
+        }
+        if (lead) {
+            build_eq(ch, y_idx, log2M_);
+            dot_tables<u32>(ch, d_final_cts_.p, M, nslots_, M, o_fcs);
+        }
         {
             Channel<FP>* chp = &ch;
             auto dims = chunk_dims_; auto mems = chunk_mems_;
@@ -799,7 +854,7 @@ template <class FP> class LassoNodeDev {
             HG_K(ctx_, KC_TREE, (size_t)nvec * h * 3 * sizeof(B), k_tree_up<FP><<<dim3((unsigned)((h + HG_BLOCK - 1) / HG_BLOCK), nvec), HG_BLOCK, 0, s>>>(layer[k - 1], layer[k], h));
         }
         const size_t roots_off = ch.alloc_msg(nvec), ev0_off = ch.alloc_msg(2 * nvec);
-        HG_K(ctx_, KC_TREE, (size_t)nvec * 2 * sizeof(B), k_tree_top<FP><<<(nvec + HG_BLOCK - 1) / HG_BLOCK, HG_BLOCK, 0, s>>>(layer[nvars - 1], nvec, ch.d_msg(roots_off), ch.d_msg(ev0_off)));
+        HG_K(ctx_, KC_TREE, (size_t)nvec * 2 * sizeof(B), k_tree_top<FP><<<(nvec + HG_BLOCK - 1) / HG_BLOCK, HG_BLOCK, 0, s>>>(layer[nvars - 1], own_begin(nvec), own_end(nvec), ch.d_msg(roots_off), ch.d_msg(ev0_off)));
         struct GpHost { std::vector<X> claimed; std::vector<X> evals; size_t mu_idx = 0; bool pending = false; };
         auto gp = std::make_shared<GpHost>();
         Channel<FP>* chp = &ch;
@@ -897,13 +952,15 @@ template <class FP> class LassoNodeDev {
                 GpItem<FP> it;
                 const int ntab = 2 * j.nvec;
                 it.nvec = j.nvec;
+                it.i_begin = own_begin(j.nvec); it.i_end = own_end(j.nvec); it.write_t0 = it.i_begin > 0;
+                const int nown = it.i_end - it.i_begin;
                 it.c = coef[k]; it.cr = coef[k] + j.nvec;
                 size_t threads_x;
                 if (r == 0) {
                     it.in = j.tables; it.out = nullptr; it.n_in = j.n; it.r_prev = nullptr;
                     it.msg = ch.d_msg(j.msg_off);
                     threads_x = (j.n / 2 + 1) / 2;  // U = 2
-                    round_bytes[r] += (size_t)ntab * j.n * sizeof(B);
+                    round_bytes[r] += (size_t)(2 * nown + it.write_t0) * j.n * sizeof(B);
                 } else {
                     it.n_in = j.n >> (r - 1);
                     it.in = (r == 1) ? (const void*)j.tables : (const void*)(((r - 1) & 1) ? bufA[k] : bufB[k]);
@@ -911,14 +968,15 @@ template <class FP> class LassoNodeDev {
                     it.r_prev = ch.d_chal(j.r0_idx + r - 1);
                     it.msg = ch.d_msg(j.msg_off + 4 + 3 * (size_t)(r - 1));
                     threads_x = it.n_in / 4;
-                    round_bytes[r] += (size_t)ntab * it.n_in * (r == 1 ? sizeof(B) : sizeof(X)) + (size_t)ntab * (it.n_in / 2) * sizeof(X);
+                    round_bytes[r] += (size_t)(2 * nown + it.write_t0) * (it.n_in * (r == 1 ? sizeof(B) : sizeof(X)) + (it.n_in / 2) * sizeof(X));
+                    (void)ntab;
                 }
                 size_t b = (threads_x + HG_BLOCK - 1) / HG_BLOCK;
                 if (b < 1) b = 1;
                 if (b > (size_t)max_blocks_) b = max_blocks_;
-                int g = (int)std::min<size_t>((size_t)j.nvec, std::max<size_t>(1, ((size_t)target_blocks + b - 1) / b));
-                it.tpg = (j.nvec + g - 1) / g;
-                it.groups = (j.nvec + it.tpg - 1) / it.tpg;
+                int g = (int)std::min<size_t>((size_t)nown, std::max<size_t>(1, ((size_t)target_blocks + b - 1) / b));
+                it.tpg = (nown + g - 1) / g;
+                it.groups = (nown + it.tpg - 1) / it.tpg;
                 it.bx = (int)b;
                 it.nblk = it.bx * it.groups;
                 it.blk_start = blk;
@@ -939,6 +997,7 @@ template <class FP> class LassoNodeDev {
             const auto& j = jobs[k];
             GpTailItem<FP>& t = titems[k];
             t.c = coef[k]; t.nvec = j.nvec; t.evals = ch.d_msg(j.evals_off);
+            t.i_begin = own_begin(j.nvec); t.i_end = own_end(j.nvec);
             if (j.n <= ((size_t)1 << FP::GP_TAIL_LOG)) {
                 t.from_base = 1; t.in = j.tables; t.n = (int)j.n; t.rounds = j.nv - 1;
                 t.chal = ch.d_chal(j.r0_idx); t.msg0 = ch.d_msg(j.msg_off); t.msg = ch.d_msg(j.msg_off + 4);
@@ -984,6 +1043,11 @@ template <class FP> class LassoNodeDev {
         }
     }
 
+    // vectors [own_begin, own_end) of a grand product belong to this device (all of them unless prove_shard is running)
+    int own_begin(int nvec) const { return (int)((size_t)nvec * shard_rank_ / shard_world_); }
+    int own_end(int nvec) const { return (int)((size_t)nvec * (shard_rank_ + 1) / shard_world_); }
+    int shard_rank_ = 0, shard_world_ = 1;
+    size_t shard_r_idx_ = 0, shard_sum_off_ = 0;
     double timing_[4] = {0, 0, 0, 0};
     size_t msg_budget_ = 0;
     int eq_nv_ = 0;

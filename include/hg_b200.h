@@ -116,6 +116,19 @@ size_t hg_lasso_node_device_bytes(const hg_lasso_node* node);
  * out_point[num_vars] / out_value hold the single EvalClaim the node returns for its input (lasso.rs:97,113). */
 int hg_lasso_node_prove(hg_lasso_node* node, const void* inputs, size_t n_inputs, int inputs_on_device, hg_transcript* t, int mode,
                         uint64_t* out_point, uint64_t* out_value);
+/* ---- one proof over several GPUs. Every message of the node is either a sum over the 2m grand-product
+ * vectors (round polynomials) or belongs to a single vector / memory (roots, evaluations, openings), and the verifier's
+ * challenges do not depend on the messages. Rank r of `world` computes the part owned by r from its own
+ * copy of the inputs and returns the node's message buffer with every other slot zero. The caller adds the buffers of all
+ * ranks element-wise (hg_shard_merge, or any exchange that sums field elements) and rank 0 serialises the result into its
+ * transcript with hg_lasso_node_emit_shard; the bytes equal those of hg_lasso_node_prove on one GPU. Words are the
+ * library's device representation (not canonical limbs): only add them with hg_shard_merge. All ranks must pass
+ * transcripts in the same state. */
+size_t hg_lasso_node_shard_words(const hg_lasso_node* node); /* capacity (64-bit words) that always fits the message buffer */
+int hg_lasso_node_prove_shard(hg_lasso_node* node, const void* inputs, size_t n_inputs, int inputs_on_device, hg_transcript* t, int rank, int world,
+                              uint64_t* out_words, size_t cap_words, size_t* n_words);
+int hg_shard_merge(int field_id, uint64_t* acc_words, const uint64_t* part_words, size_t n_words); /* acc += part, element-wise in the field */
+int hg_lasso_node_emit_shard(hg_lasso_node* node, const uint64_t* merged_words, size_t n_words, uint64_t* out_point, uint64_t* out_value);
 /* test hook: polynomialised witness of the last prove (lasso.rs:157-250). dims: C x R u16, read_cts: chunks x R u32,
  * final_cts: chunks x M u32, e_polys: num_memories x R base elements. Any pointer may be NULL. */
 int hg_lasso_node_download_polys(hg_lasso_node* node, uint16_t* dims, uint32_t* read_cts, uint32_t* final_cts, uint64_t* e_polys);

@@ -231,6 +231,79 @@ def test_lasso_node_full_size_properties(api, ctx, oracle):
     node.free()
 
 
+def _prove_sharded_on_one_gpu(api, ctx, field, bounds, segs, nv, inp, world, skip_ext=0):
+    """SURVEY.md §8e on one device: `world` node objects play the ranks; their message buffers are summed by hg_shard_merge
+    and rank 0 serialises. The result must be the proof a single device writes."""
+    pp = api.LassoPreprocessing.preprocess(bounds)
+    nodes = [api.LassoNode(ctx, pp, nv, segs) for _ in range(world)]
+    trs = [api.Keccak256Transcript(field) for _ in range(world)]
+    parts = []
+    for r in range(world):
+        if skip_ext:
+            trs[r].squeeze_challenges(skip_ext)
+        parts.append(nodes[r].prove_shard(inp, trs[r], r, world).copy())
+    # slots are owned by exactly one rank or are sums: ranks other than 0 leave most slots zero
+    assert all(p.size == parts[0].size for p in parts)
+    merged = parts[0].copy()
+    for r in range(1, world):
+        api.shard_merge(field, merged, parts[r])
+    pt, val = nodes[0].emit_shard(merged)
+    proof = trs[0].into_proof()
+    for n in nodes:
+        n.free()
+    return proof, pt, val, parts
+
+
+@pytest.mark.parametrize("name,world", [("1024_1x27_65537", 2), ("2048_1x52_65537", 3), ("4096_2x55_65537", 4), ("4096_2x55_65537", 8)])
+def test_lasso_node_sharded_proof_equals_single_device_proof(api, ctx, oracle, golden_dir, name, world):
+    P, inp, bounds, segs, nv, opp, rows = load_case(name, oracle, golden_dir)
+    oproof, orr, osum, _ = oracle.lasso_prove(0, opp, nv, rows, inp)
+    proof, pt, val, parts = _prove_sharded_on_one_gpu(api, ctx, api.GOLDILOCKS, bounds, segs, nv, inp, world)
+    assert proof == oproof
+    assert (pt.reshape(-1) == orr).all() and (val == osum).all()
+    # the work really is split: every rank contributes, and no rank alone holds the whole buffer
+    for p in parts:
+        assert p.any()
+        assert (p == 0).sum() > p.size // (2 * world)
+    # a shard followed by an ordinary proof on the same node still gives the single-device bytes
+    pp = api.LassoPreprocessing.preprocess(bounds)
+    node = api.LassoNode(ctx, pp, nv, segs)
+    node.prove_shard(inp, api.Keccak256Transcript(), 1, world)
+    tr = api.Keccak256Transcript()
+    node.prove_claim_reduction(inp, tr)
+    assert tr.into_proof() == oproof
+    with pytest.raises(api.HgError):
+        node.prove_shard(inp, api.Keccak256Transcript(), world, world)
+    node.free()
+
+
+def test_lasso_node_sharded_full_size_and_offset(api, ctx, oracle):
+    """Full-size node (num_vars 21, 25 memories, 50 vectors) over 4 ranks with an advanced transcript == one device."""
+    P, inp, bounds, segs, nv, opp, rows = load_case("32768_16x59_65537", oracle, seed=0)
+    pp = api.LassoPreprocessing.preprocess(bounds)
+    node = api.LassoNode(ctx, pp, nv, segs)
+    tr = api.Keccak256Transcript()
+    tr.squeeze_challenges(7)
+    node.prove_claim_reduction(inp, tr)
+    node.free()
+    proof, pt, val, _ = _prove_sharded_on_one_gpu(api, ctx, api.GOLDILOCKS, bounds, segs, nv, inp, 4, skip_ext=7)
+    assert proof == tr.into_proof()
+
+
+def test_bn254_lasso_node_sharded(api, ctx_bn, oracle, golden_dir):
+    import os
+    from hyper_greco_b200 import params, witness
+    name = "1024_1x27_65537"
+    P = params.PARAMS[name]
+    inp = np.load(os.path.join(golden_dir, f"lasso_inputs_bn254_{name}.npz"))["inputs"]
+    bounds, segs, nv = witness.lasso_lookup_bounds(P), witness.lasso_lookup_segments(P), witness.lasso_num_vars(P)
+    opp = oracle.Preprocessing(bounds)
+    rows = np.concatenate([np.full(l, opp.lookup_index(b), np.int32) for b, l in segs])
+    oproof, *_ = oracle.lasso_prove(1, opp, nv, rows, inp)
+    proof, pt, val, _ = _prove_sharded_on_one_gpu(api, ctx_bn, api.BN254, bounds, segs, nv, inp, 2)
+    assert proof == oproof
+
+
 @pytest.mark.parametrize("log_n,batch", [(1, 3), (2, 1), (5, 4), (8, 2), (11, 3), (13, 2), (16, 3), (17, 1)])
 def test_ntt_matches_oracle(api, ctx, oracle, log_n, batch):
     """FftNode forward / inverse evaluation (assumption A9: natural order, inverse scaled by 1/n)."""
