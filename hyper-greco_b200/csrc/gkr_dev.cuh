@@ -207,10 +207,12 @@ template <class FP> class GkrCircuitDev {
             if (n.kind == GKR_INPUT) continue;
             if (n.kind == GKR_LASSO) {
                 size_t r_idx = 0, sum_off = 0;
+                const bool side = ch.begin_side();  // its serialisation overlaps the layer kernels enqueued below
                 n.lasso->enqueue_protocol(ch, mode, wo, &r_idx, &sum_off);
                 Claim c; c.by_index = true; c.idx = r_idx; c.nvars = n.lasso->num_vars(); c.value = std::make_shared<X>(FP::x_zero());
                 auto vp = c.value;
                 ch.emit([chp, vp, sum_off]() { *vp = chp->msg(sum_off); });
+                if (side) ch.end_side();
                 claims[n.preds.at(0)].push_back(c);
                 continue;
             }

@@ -132,11 +132,21 @@ template <class FP> class Channel {
     Channel(DeviceCtx* ctx, size_t chal_cap, size_t msg_cap) : ctx_(ctx) {
         d_chal_.alloc(chal_cap); h_chal_.alloc(chal_cap);
         d_msg_.alloc(msg_cap); h_msg_.alloc(msg_cap);
+        HG_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+        HG_CUDA(cudaEventCreateWithFlags(&ev_side_done_, cudaEventDisableTiming));
+        HG_CUDA(cudaEventCreateWithFlags(&ev_side_copied_, cudaEventDisableTiming));
     }
+    ~Channel() {
+        cudaEventDestroy(ev_side_done_); cudaEventDestroy(ev_side_copied_);
+        cudaStreamDestroy(copy_stream_);
+    }
+    Channel(const Channel&) = delete;
+    Channel& operator=(const Channel&) = delete;
     void begin(Keccak256Transcript<FP>* tr, ProveMode mode, size_t total_chal) {
-        tr_ = tr; mode_ = mode;
+        tr_ = tr; active_tr_ = tr; mode_ = mode;
         chal_cursor_ = chal_ready_ = msg_cursor_ = msg_ready_ = 0;
         deferred_.clear(); deferred_done_ = 0;
+        side_state_ = 0;
         if (total_chal > d_chal_.n) throw std::runtime_error("Channel: challenge capacity exceeded");
         if (mode_ == kModePrefetch) {
             for (size_t i = 0; i < total_chal; i++) h_chal_.p[i] = tr_->squeeze_challenge();
@@ -166,20 +176,64 @@ template <class FP> class Channel {
         return off;
     }
     void emit(std::function<void()> fn) { deferred_.push_back(std::move(fn)); }
+    // ---- side segment (prefetch mode): a run of messages whose serialisers depend on nothing emitted before them (the Lasso
+    // node: it ignores its incoming claim, lasso.rs:60). Its messages are copied to the host as soon as its kernels finish and
+    // serialised into a side buffer while the device works on what was enqueued after it; flush() splices the bytes in place.
+    bool begin_side() {
+        if (mode_ != kModePrefetch || side_state_ != 0) return false;
+        side_state_ = 1; side_def_begin_ = deferred_.size(); side_msg_begin_ = msg_cursor_;
+        return true;
+    }
+    void end_side() {  // call when every kernel of the segment has been enqueued
+        if (side_state_ != 1) return;
+        side_state_ = 2; side_def_end_ = deferred_.size(); side_msg_end_ = msg_cursor_;
+        HG_CUDA(cudaEventRecord(ev_side_done_, ctx_->stream));
+        HG_CUDA(cudaStreamWaitEvent(copy_stream_, ev_side_done_, 0));
+        if (side_msg_end_ > side_msg_begin_)
+            HG_CUDA(cudaMemcpyAsync(h_msg_.p + side_msg_begin_, d_msg_.p + side_msg_begin_, (side_msg_end_ - side_msg_begin_) * sizeof(X),
+                                    cudaMemcpyDeviceToHost, copy_stream_));
+        HG_CUDA(cudaEventRecord(ev_side_copied_, copy_stream_));
+    }
     // bring finished messages to the host and serialise everything emitted so far, in order
     void flush(double* wait_us = nullptr, double* emit_us = nullptr) {
         auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         const double t0 = now();
-        if (msg_cursor_ > msg_ready_) {
-            HG_CUDA(cudaMemcpyAsync(h_msg_.p + msg_ready_, d_msg_.p + msg_ready_, (msg_cursor_ - msg_ready_) * sizeof(X),
-                                    cudaMemcpyDeviceToHost, ctx_->stream));
-            msg_ready_ = msg_cursor_;
+        double side_us = 0;
+        if (side_state_ == 1) side_state_ = 0;  // never closed: plain in-order flush
+        auto copy_range = [&](size_t a, size_t b) {
+            if (b > a) HG_CUDA(cudaMemcpyAsync(h_msg_.p + a, d_msg_.p + a, (b - a) * sizeof(X), cudaMemcpyDeviceToHost, ctx_->stream));
+        };
+        if (side_state_ == 2) {
+            copy_range(msg_ready_, side_msg_begin_);
+            copy_range(side_msg_end_, msg_cursor_);
+            HG_CUDA(cudaEventSynchronize(ev_side_copied_));
+            const double s0 = now();
+            Keccak256Transcript<FP> side;
+            active_tr_ = &side;
+            msg_ready_ = side_msg_end_;  // side serialisers read their own range only
+            for (size_t i = side_def_begin_; i < side_def_end_; i++) deferred_[i]();
+            active_tr_ = tr_;
+            side_bytes_ = side.proof();
+            side_state_ = 3;
+            side_us = now() - s0;
+        } else {
+            copy_range(msg_ready_, msg_cursor_);
         }
-        HG_CUDA(cudaStreamSynchronize(ctx_->stream));
+        msg_ready_ = msg_cursor_;
         const double t1 = now();
-        for (; deferred_done_ < deferred_.size(); deferred_done_++) deferred_[deferred_done_]();
-        if (wait_us) *wait_us = t1 - t0;
-        if (emit_us) *emit_us = now() - t1;
+        HG_CUDA(cudaStreamSynchronize(ctx_->stream));
+        const double t2 = now();
+        while (deferred_done_ < deferred_.size()) {
+            if (side_state_ == 3 && deferred_done_ == side_def_begin_) {
+                tr_->append_bytes(side_bytes_);
+                deferred_done_ = side_def_end_;
+                side_state_ = 0;
+                continue;
+            }
+            deferred_[deferred_done_++]();
+        }
+        if (wait_us) *wait_us = (t1 - t0 - side_us) + (t2 - t1);
+        if (emit_us) *emit_us = side_us + (now() - t2);
     }
     // ---- a proof split over several devices (LassoNodeDev::prove_shard): every device fills the message slots of the terms
     // it owns and leaves the others zero; the element-wise sum over devices is the message buffer of the whole proof
@@ -203,13 +257,19 @@ template <class FP> class Channel {
     X* d_msg(size_t i) { return d_msg_.p + i; }
     X chal(size_t i) const { if (i >= chal_ready_) throw std::runtime_error("Channel: challenge not squeezed yet"); return h_chal_.p[i]; }
     X msg(size_t i) const { if (i >= msg_ready_) throw std::runtime_error("Channel: message not downloaded yet"); return h_msg_.p[i]; }
-    Keccak256Transcript<FP>& transcript() { return *tr_; }
+    Keccak256Transcript<FP>& transcript() { return *active_tr_; }
     size_t chal_used() const { return chal_cursor_; }
     size_t next_index() const { return chal_cursor_; }
 
   private:
     DeviceCtx* ctx_;
     Keccak256Transcript<FP>* tr_ = nullptr;
+    Keccak256Transcript<FP>* active_tr_ = nullptr;  // where serialisers write: tr_, or the side buffer
+    cudaStream_t copy_stream_ = nullptr;
+    cudaEvent_t ev_side_done_ = nullptr, ev_side_copied_ = nullptr;
+    int side_state_ = 0;  // 0 none, 1 open, 2 closed (copy in flight), 3 serialised
+    size_t side_def_begin_ = 0, side_def_end_ = 0, side_msg_begin_ = 0, side_msg_end_ = 0;
+    std::vector<uint8_t> side_bytes_;
     ProveMode mode_ = kModePrefetch;
     DevBuf<X> d_chal_, d_msg_;
     PinnedBuf<X> h_chal_, h_msg_;
@@ -261,8 +321,9 @@ template <class FP> struct ScHostState {
     typedef typename FP::X X;
     X claim;                         // the claim the WIRE polynomial is checked against (prove_sum_check's running claim)
     bool has_pending = false;
-    std::vector<X> pending_wire;     // coefficients of the polynomial that went on the wire last round
-    std::vector<X> pending_true;     // coefficients of the TRUE round polynomial of the last round
+    X pending_wire[4];               // coefficients of the polynomial that went on the wire last round (degree pending_deg)
+    X pending_true[4];               // coefficients of the TRUE round polynomial of the last round
+    int pending_deg = 0;
     size_t pending_chal = 0;
 };
 
@@ -284,16 +345,17 @@ void emit_round(Channel<FP>& ch, std::shared_ptr<ScHostState<FP>> st, size_t off
     WireOptions w = wo;
     ch.emit([chp, st, off, w, round0, next_idx, slot_h1]() {
         typedef RoundPoly<FP> RP;
+        auto horner = [](const X* c, int deg, X x) { X r = c[deg]; for (int i = deg; i-- > 0;) r = FP::x_add(FP::x_mul(r, x), c[i]); return r; };
         X s;
         if (round0) {
             s = FP::x_add(chp->msg(off), chp->msg(off + slot_h1));
         } else {
             X rprev = chp->chal(st->pending_chal);
-            s = RP::horner(st->pending_true, rprev);
-            st->claim = RP::horner(st->pending_wire, rprev);
+            s = horner(st->pending_true, st->pending_deg, rprev);
+            st->claim = horner(st->pending_wire, st->pending_deg, rprev);
         }
         const X h0 = chp->msg(off), hinf = chp->msg(off + 1);
-        std::vector<X> tc(D + 1);
+        X tc[D + 1];
         tc[0] = h0;
         tc[D] = hinf;
         X a = FP::x_sub(FP::x_sub(s, FP::x_add(h0, h0)), hinf);  // sum of the middle coefficients
@@ -305,18 +367,41 @@ void emit_round(Channel<FP>& ch, std::shared_ptr<ScHostState<FP>> st, size_t off
             tc[2] = FP::x_mul(FP::x_add(a, bv), inv2);
             tc[1] = FP::x_mul(FP::x_sub(a, bv), inv2);
         }
-        std::vector<X> ev(D + 1);
-        for (int k = 0; k <= D; k++) ev[k] = RP::horner(tc, RP::small(k));
-        std::vector<X> co = tc;
-        if (w.a3_h1 == 0) {
-            ev[1] = FP::x_sub(st->claim, ev[0]);
-            co = RP::interpolate(ev);
-        }
+        X co[D + 1];
         auto& tr = chp->transcript();
-        if (w.a3_wire == 0) { tr.write_felt_ext(co[0]); for (int p = 2; p <= D; p++) tr.write_felt_ext(co[p]); }
-        else { tr.write_felt_ext(ev[0]); for (int p = 2; p <= D; p++) tr.write_felt_ext(ev[p]); }
-        st->pending_wire = co;
-        st->pending_true = tc;
+        if (w.a3_h1 == 0 && w.a3_wire == 0) {
+            // default wire format: coefficients of the polynomial through (0, h(0)), (1, claim - h(0)), (k, h(k)) for k >= 2.
+            // It differs from h by delta * L_1 with L_1 the Lagrange basis polynomial of node 1 over {0..D}:
+            // D = 2: 2X - X^2;  D = 3: (6X - 5X^2 + X^3) / 2
+            X h1 = tc[0];
+            for (int k = 1; k <= D; k++) h1 = FP::x_add(h1, tc[k]);
+            const X delta = FP::x_sub(FP::x_sub(st->claim, h0), h1);
+            co[0] = tc[0];
+            if (D == 2) {
+                co[1] = FP::x_add(tc[1], FP::x_add(delta, delta));
+                co[2] = FP::x_sub(tc[2], delta);
+            } else {
+                static const X k3 = RP::small(3), k52 = FP::x_mul(RP::small(5), RP::inv_small(2)), k12 = RP::inv_small(2);
+                co[1] = FP::x_add(tc[1], FP::x_mul(delta, k3));
+                co[2] = FP::x_sub(tc[2], FP::x_mul(delta, k52));
+                co[3] = FP::x_add(tc[3], FP::x_mul(delta, k12));
+            }
+            tr.write_felt_ext(co[0]);
+            for (int q = 2; q <= D; q++) tr.write_felt_ext(co[q]);
+        } else {
+            std::vector<X> tcv(tc, tc + D + 1), ev(D + 1);
+            for (int k = 0; k <= D; k++) ev[k] = RP::horner(tcv, RP::small(k));
+            std::vector<X> cov = tcv;
+            if (w.a3_h1 == 0) {
+                ev[1] = FP::x_sub(st->claim, ev[0]);
+                cov = RP::interpolate(ev);
+            }
+            for (int k = 0; k <= D; k++) co[k] = cov[k];
+            if (w.a3_wire == 0) { tr.write_felt_ext(co[0]); for (int q = 2; q <= D; q++) tr.write_felt_ext(co[q]); }
+            else { tr.write_felt_ext(ev[0]); for (int q = 2; q <= D; q++) tr.write_felt_ext(ev[q]); }
+        }
+        for (int k = 0; k <= D; k++) { st->pending_wire[k] = co[k]; st->pending_true[k] = tc[k]; }
+        st->pending_deg = D;
         st->pending_chal = next_idx;
         st->has_pending = true;
     });

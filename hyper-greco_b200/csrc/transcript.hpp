@@ -143,7 +143,10 @@ template <class HF> class Keccak256Transcript {
     void write_felt(const Base& f) {
         uint8_t b[HF::REPR_BYTES];
         HF::base_to_repr_le(f, b);
-        for (int i = HF::REPR_BYTES - 1; i >= 0; i--) stream_.push_back(b[i]);
+        const size_t o = stream_.size();
+        stream_.resize(o + HF::REPR_BYTES);
+        uint8_t* dst = stream_.data() + o;
+        for (int i = 0; i < HF::REPR_BYTES; i++) dst[i] = b[HF::REPR_BYTES - 1 - i];
     }
     void write_felt_ext(const Ext& e) {
         Base b[HF::DEGREE];
@@ -165,6 +168,7 @@ template <class HF> class Keccak256Transcript {
         return HF::ext_from_bases(b);
     }
     const std::vector<uint8_t>& proof() const { return stream_; }  // into_proof
+    void append_bytes(const std::vector<uint8_t>& b) { stream_.insert(stream_.end(), b.begin(), b.end()); }  // messages serialised elsewhere
     size_t num_base_squeezed() const { return n_squeezed_; }
     size_t read_pos() const { return pos_; }
 
