@@ -413,6 +413,14 @@ int hg_ctx_create(int device, int field_id, hg_ctx** out) {
         c->dev.device = device;
         c->field_id = field_id;
         HG_CUDA(cudaStreamCreateWithFlags(&c->dev.stream, cudaStreamNonBlocking));
+        {   // second stream for work that is independent of the Lasso node (the generic layer sumchecks): higher priority so
+            // that its short kernels are dispatched as soon as blocks of the long streaming kernels retire
+            int lo = 0, hi = 0;
+            HG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            HG_CUDA(cudaStreamCreateWithPriority(&c->dev.stream2, cudaStreamNonBlocking, hi));
+            HG_CUDA(cudaEventCreateWithFlags(&c->dev.ev_fork, cudaEventDisableTiming));
+            HG_CUDA(cudaEventCreateWithFlags(&c->dev.ev_join, cudaEventDisableTiming));
+        }
         HG_CUDA(cudaDeviceGetAttribute(&c->dev.sm_count, cudaDevAttrMultiProcessorCount, device));
         *out = c.release();
     })
@@ -421,6 +429,9 @@ void hg_ctx_destroy(hg_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->dev.device);
     ctx->ops.reset();
+    if (ctx->dev.ev_fork) cudaEventDestroy(ctx->dev.ev_fork);
+    if (ctx->dev.ev_join) cudaEventDestroy(ctx->dev.ev_join);
+    if (ctx->dev.stream2) cudaStreamDestroy(ctx->dev.stream2);
     if (ctx->dev.stream) cudaStreamDestroy(ctx->dev.stream);
     delete ctx;
 }
@@ -429,6 +440,7 @@ int hg_ctx_set_option(hg_ctx* ctx, int option, int value) {
         if (option == HG_OPT_A3_WIRE) ctx->wire.a3_wire = value;
         else if (option == HG_OPT_A3_H1) ctx->wire.a3_h1 = value;
         else if (option == HG_OPT_A5_ASCENDING) ctx->wire.a5_ascending = value;
+        else if (option == HG_OPT_TWO_STREAMS) ctx->dev.two_streams = value != 0;
         else throw std::runtime_error("unknown option");
     })
 }

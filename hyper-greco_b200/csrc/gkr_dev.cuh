@@ -170,14 +170,6 @@ template <class FP> class GkrCircuitDev {
         const double t0 = now();
         plan();
         Channel<FP>& ch = *ch_;
-        // Lasso witness kernels need no challenge: enqueue them first so that Keccak squeezing overlaps them
-        for (auto& n : nodes_) if (n->kind == GKR_LASSO) {
-            const Node& p = *nodes_[n->preds.at(0)];
-            n->lasso->enqueue_witness(p.value_ptr, n->lasso->num_rows(), wo);
-        }
-        const double t1 = now();
-        ch.begin(&tr, mode, total_chal_);
-        const double t2 = now();
         struct Claim { bool by_index; size_t idx; std::vector<X> point_host; int nvars; std::shared_ptr<X> value; };
         std::vector<std::vector<Claim>> claims(nodes_.size());
         // output claims: their points live in extra device slots after the challenges
@@ -195,8 +187,32 @@ template <class FP> class GkrCircuitDev {
                 claims[outs[i]].push_back(c);
             }
             if (slot > d_outpts_.n) d_outpts_.alloc(slot + 16);
-            if (!stage.empty()) { HG_CUDA(cudaMemcpyAsync(d_outpts_.p, stage.data(), stage.size() * sizeof(X), cudaMemcpyHostToDevice, s)); HG_CUDA(cudaStreamSynchronize(s)); }
+            if (slot > h_outpts_.n) h_outpts_.alloc(slot + 16);
+            if (!stage.empty()) {  // pinned staging: no host wait (the previous proof's flush has synchronised the stream)
+                memcpy(h_outpts_.p, stage.data(), stage.size() * sizeof(X));
+                HG_CUDA(cudaMemcpyAsync(d_outpts_.p, h_outpts_.p, stage.size() * sizeof(X), cudaMemcpyHostToDevice, s));
+            }
         }
+        // In prefetch mode the layer sumchecks depend on nothing the Lasso node computes: they go to the context's second
+        // stream, forked here (after the challenge upload) and joined before the messages are downloaded. Per-launch
+        // profiling keeps everything on one stream so that launches are timed one at a time.
+        const bool fork = mode == kModePrefetch && ctx_->two_streams && !ctx_->profile && ctx_->stream2 != nullptr;
+        double t1 = t0;
+        if (fork) {
+            ch.begin(&tr, mode, total_chal_);
+            HG_CUDA(cudaEventRecord(ctx_->ev_fork, s));
+            t1 = now();
+        }
+        // Lasso witness kernels need no challenge
+        for (auto& n : nodes_) if (n->kind == GKR_LASSO) {
+            const Node& p = *nodes_[n->preds.at(0)];
+            n->lasso->enqueue_witness(p.value_ptr, n->lasso->num_rows(), wo);
+        }
+        if (!fork) {
+            t1 = now();
+            ch.begin(&tr, mode, total_chal_);  // Keccak squeezing overlaps the witness kernels
+        }
+        const double t2 = now();
         auto point_ptr = [&](const Claim& c) -> const X* { return c.by_index ? ch.d_chal(c.idx) : d_outpts_.p + c.idx; };
         std::vector<Job> jobs;
         auto ord = topo();
@@ -271,6 +287,15 @@ template <class FP> class GkrCircuitDev {
         }
         const double t3 = now();
         if (mode == kModePrefetch) {
+            struct StreamSwap {  // every helper reads ctx->stream when it launches
+                DeviceCtx* c; cudaStream_t main; bool on;
+                StreamSwap(DeviceCtx* ctx, bool enable) : c(ctx), main(ctx->stream), on(enable) {
+                    if (on) { c->stream = c->stream2; cudaStreamWaitEvent(c->stream2, c->ev_fork, 0); }
+                }
+                ~StreamSwap() {
+                    if (on) { cudaEventRecord(c->ev_join, c->stream2); c->stream = main; cudaStreamWaitEvent(main, c->ev_join, 0); }
+                }
+            } swap(ctx_, fork);
             prepare_jobs(ch, jobs, wo);
             int maxv = 0;
             for (auto& j : jobs) maxv = std::max(maxv, j.nv);
@@ -574,6 +599,7 @@ template <class FP> class GkrCircuitDev {
     size_t total_chal_ = 0, desc_off_ = 0, eq_off_ = 0;
     std::unique_ptr<Channel<FP>> ch_;
     DevBuf<X> d_eq_, d_partials_, d_outpts_;
+    PinnedBuf<X> h_outpts_;
     DevBuf<B> d_planes_;
     DevBuf<unsigned> d_counters_;
     DevBuf<unsigned char> d_desc_;

@@ -107,21 +107,44 @@ HG_HD gl2 gl2_inv(gl2 a) {
 //   * products are accumulated UNREDUCED in a 160-bit accumulator (lo, hi, carry word) and reduced once;
 //   * subtraction needs only its subtrahend canonical; results are "lazy" (any representative in [0, 2^64)).
 #if defined(__CUDACC__)
+// Unreduced sum of 64x64-bit products, kept as TWO column accumulators so that every 32x32 partial product lands on an
+// aligned 64-bit register pair and one IMAD.WIDE.U32 (with carry) adds it:
+//     value = (e01 + 2^64 e23 + 2^128 e4)  +  2^32 (o01 + 2^64 o2)
+// "even" columns take x0*y0 (weight 2^0) and x1*y1 (2^64), "odd" columns the cross products (2^32). acc_mad is
+// 4 IMAD.WIDE.U32 + 3 carry adds (the single-accumulator form needed 15 instructions); the columns are merged once, in
+// acc_reduce. Capacity: 2^31 products.
 struct acc192 {
-    u64 lo, hi;
-    u32 c;
+    u64 e01, e23, o01;
+    u32 e4, o2;
 };
-__device__ __forceinline__ acc192 acc_zero() { acc192 a; a.lo = 0; a.hi = 0; a.c = 0; return a; }
+__device__ __forceinline__ acc192 acc_zero() { acc192 a; a.e01 = 0; a.e23 = 0; a.o01 = 0; a.e4 = 0; a.o2 = 0; return a; }
+__device__ __forceinline__ acc192 acc_from(u64 v) { acc192 a = acc_zero(); a.e01 = v; return a; }
 // a += x * y   (x, y any 64-bit values)
 __device__ __forceinline__ void acc_mad(acc192& a, u64 x, u64 y) {
-    u64 lo = x * y, hi = __umul64hi(x, y);
-    asm("add.cc.u64 %0, %0, %3; addc.cc.u64 %1, %1, %4; addc.u32 %2, %2, 0;" : "+l"(a.lo), "+l"(a.hi), "+r"(a.c) : "l"(lo), "l"(hi));
+    asm("{\n\t.reg .u32 x0, x1, y0, y1, a0, a1, a2, a3, b0, b1;\n\t"
+        "mov.b64 {x0, x1}, %5;\n\tmov.b64 {y0, y1}, %6;\n\t"
+        "mov.b64 {a0, a1}, %0;\n\tmov.b64 {a2, a3}, %1;\n\tmov.b64 {b0, b1}, %3;\n\t"
+        "mad.lo.cc.u32 a0, x0, y0, a0;\n\t"
+        "madc.hi.cc.u32 a1, x0, y0, a1;\n\t"
+        "madc.lo.cc.u32 a2, x1, y1, a2;\n\t"
+        "madc.hi.cc.u32 a3, x1, y1, a3;\n\t"
+        "addc.u32 %2, %2, 0;\n\t"
+        "mad.lo.cc.u32 b0, x0, y1, b0;\n\t"
+        "madc.hi.cc.u32 b1, x0, y1, b1;\n\t"
+        "addc.u32 %4, %4, 0;\n\t"
+        "mad.lo.cc.u32 b0, x1, y0, b0;\n\t"
+        "madc.hi.cc.u32 b1, x1, y0, b1;\n\t"
+        "addc.u32 %4, %4, 0;\n\t"
+        "mov.b64 %0, {a0, a1};\n\tmov.b64 %1, {a2, a3};\n\tmov.b64 %3, {b0, b1};\n\t}"
+        : "+l"(a.e01), "+l"(a.e23), "+r"(a.e4), "+l"(a.o01), "+r"(a.o2)
+        : "l"(x), "l"(y));
 }
 __device__ __forceinline__ void acc_add(acc192& a, u64 x) {
-    asm("add.cc.u64 %0, %0, %3; addc.cc.u64 %1, %1, 0; addc.u32 %2, %2, 0;" : "+l"(a.lo), "+l"(a.hi), "+r"(a.c) : "l"(x));
+    asm("add.cc.u64 %0, %0, %3; addc.cc.u64 %1, %1, 0; addc.u32 %2, %2, 0;" : "+l"(a.e01), "+l"(a.e23), "+r"(a.e4) : "l"(x));
 }
 __device__ __forceinline__ void acc_merge(acc192& a, const acc192& b) {
-    asm("add.cc.u64 %0, %0, %3; addc.cc.u64 %1, %1, %4; addc.u32 %2, %2, %5;" : "+l"(a.lo), "+l"(a.hi), "+r"(a.c) : "l"(b.lo), "l"(b.hi), "r"(b.c));
+    asm("add.cc.u64 %0, %0, %3; addc.cc.u64 %1, %1, %4; addc.u32 %2, %2, %5;" : "+l"(a.e01), "+l"(a.e23), "+r"(a.e4) : "l"(b.e01), "l"(b.e23), "r"(b.e4));
+    asm("add.cc.u64 %0, %0, %2; addc.u32 %1, %1, %3;" : "+l"(a.o01), "+r"(a.o2) : "l"(b.o01), "r"(b.o2));
 }
 // a - b mod p for CANONICAL b (a may be lazy); result lazy, canonical when a is canonical
 __device__ __forceinline__ u64 gl_sub_cs(u64 a, u64 b) {
@@ -144,16 +167,21 @@ __device__ __forceinline__ u64 gl_canon(u64 r) {
     asm("add.cc.u64 %0, %2, %3; addc.u32 %1, 0, 0;" : "=l"(t), "=r"(c) : "l"(r), "l"(GL_EPS));  // t = r - p (mod 2^64), carry iff r >= p
     return c ? t : r;
 }
-// (lo + 2^64 hi + 2^128 c) mod p, canonical.  2^64 = 2^32 - 1, 2^96 = -1, 2^128 = -2^32 (mod p); c < 2^31
+// value mod p, canonical.  2^64 = 2^32 - 1, 2^96 = -1, 2^128 = -2^32 (mod p)
 __device__ __forceinline__ u64 acc_reduce(const acc192& a) {
-    const u64 s1 = (a.hi >> 32) | ((u64)a.c << 32);  // hi_hi + c * 2^32, canonical (< 2^63)
-    u64 t0 = gl_sub_cs(a.lo, s1);
-    const u64 hl = a.hi & GL_EPS;
-    const u64 t1 = (hl << 32) - hl;  // hi_lo * (2^32 - 1) < 2^64 - 2^33 + 2
+    // merge the odd columns: (lo, hi, c) = E + 2^32 O, c < 2^31
+    u32 e0 = (u32)a.e01, e1 = (u32)(a.e01 >> 32), e2 = (u32)a.e23, e3 = (u32)(a.e23 >> 32), c = a.e4;
+    const u32 o0 = (u32)a.o01, o1 = (u32)(a.o01 >> 32);
+    asm("add.cc.u32 %0, %0, %4; addc.cc.u32 %1, %1, %5; addc.cc.u32 %2, %2, %6; addc.u32 %3, %3, 0;"
+        : "+r"(e1), "+r"(e2), "+r"(e3), "+r"(c) : "r"(o0), "r"(o1), "r"(a.o2));
+    const u64 lo = e0 | ((u64)e1 << 32);
+    const u64 s1 = e3 | ((u64)c << 32);  // hi_hi + c * 2^32, canonical (< 2^63)
+    u64 t0 = gl_sub_cs(lo, s1);
+    const u64 t1 = ((u64)e2 << 32) - e2;  // hi_lo * (2^32 - 1) < 2^64 - 2^33 + 2
     u64 r;
-    u32 c;
-    asm("add.cc.u64 %0, %2, %3; addc.u32 %1, 0, 0;" : "=l"(r), "=r"(c) : "l"(t0), "l"(t1));
-    r += (u64)(0u - c);  // cannot wrap twice
+    u32 cy;
+    asm("add.cc.u64 %0, %2, %3; addc.u32 %1, 0, 0;" : "=l"(r), "=r"(cy) : "l"(t0), "l"(t1));
+    r += (u64)(0u - cy);  // cannot wrap twice
     return gl_canon(r);
 }
 // extension-field accumulator: sum of products x*y kept as three unreduced base accumulators
@@ -179,9 +207,7 @@ __device__ __forceinline__ gl2 xacc_reduce(const xacc& a) {
 // fold: a0 + r * (a1 - a0), canonical inputs, canonical output; r7 = 7 * r.c1 mod p
 __device__ __forceinline__ gl2 gl2_fold(gl2 a0, gl2 a1, gl2 r, u64 r7) {
     const u64 d0 = gl_sub_cs(a1.c0, a0.c0), d1 = gl_sub_cs(a1.c1, a0.c1);
-    acc192 c0 = acc_zero(), c1 = acc_zero();
-    c0.lo = a0.c0;
-    c1.lo = a0.c1;
+    acc192 c0 = acc_from(a0.c0), c1 = acc_from(a0.c1);
     acc_mad(c0, r.c0, d0);
     acc_mad(c0, r7, d1);
     acc_mad(c1, r.c0, d1);
@@ -190,8 +216,7 @@ __device__ __forceinline__ gl2 gl2_fold(gl2 a0, gl2 a1, gl2 r, u64 r7) {
 }
 __device__ __forceinline__ gl2 gl2_fold(u64 a0, u64 a1, gl2 r, u64) {
     const u64 d = gl_sub_cs(a1, a0);
-    acc192 c0 = acc_zero(), c1 = acc_zero();
-    c0.lo = a0;
+    acc192 c0 = acc_from(a0), c1 = acc_zero();
     acc_mad(c0, r.c0, d);
     acc_mad(c1, r.c1, d);
     return gl2_make(acc_reduce(c0), acc_reduce(c1));

@@ -42,7 +42,10 @@ inline const char* kernel_class_name(int c) {
 }
 struct DeviceCtx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;    // the launching stream (KernelScope, HG_K and every helper read it at call time)
+    cudaStream_t stream2 = nullptr;   // see hg_ctx_create
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool two_streams = true;
     int sm_count = 148;
     size_t launches = 0;  // kernels enqueued (bench.py "gpu_launches")
     // optional per-launch CUDA-event timing on the launching stream
@@ -772,12 +775,16 @@ template <class FP> class LassoNodeDev {
             if (np2 != R_) throw std::runtime_error("assertion `left == right` failed: num_vars of the input does not match the node (lasso.rs:80)");
         }
 
-        // collation coefficients (A5)
-        {
+        // collation coefficients (A5): uploaded when the option changes, not per proof
+        if (coll_coeff_state_ != (wo.a5_ascending ? 1 : 2)) {
             std::vector<B> cc = coll_coeff_host_;
             if (!wo.a5_ascending) std::reverse(cc.begin(), cc.end());
             HG_CUDA(cudaMemcpyAsync(d_coeff_coll_.p, cc.data(), cc.size() * sizeof(B), cudaMemcpyHostToDevice, s));
-            HG_CUDA(cudaStreamSynchronize(s));  // cc is a stack temporary
+            X one_one[2] = {FP::x_zero(), FP::x_one()};  // g(E_0, S) = E_0 * (0 * E_0 + 1 * S), see enqueue_protocol
+            if (!d_coll_terms_.n) d_coll_terms_.alloc(2);
+            HG_CUDA(cudaMemcpyAsync(d_coll_terms_.p, one_one, sizeof one_one, cudaMemcpyHostToDevice, s));
+            HG_CUDA(cudaStreamSynchronize(s));  // stack temporaries
+            coll_coeff_state_ = wo.a5_ascending ? 1 : 2;
         }
         // ---- polynomialize (lasso.rs:157-250)
         B* d_S = d_coll_.p + R;
@@ -817,11 +824,8 @@ template <class FP> class LassoNodeDev {
         }
         // ---- collation sumcheck (lasso.rs:271-279): t_0 * sum_i c_i t_i == E_0 * S with S = sum_i c_i E_i
         {
-            X one_one[2] = {FP::x_zero(), FP::x_one()};
-            // g(E_0, S) = E_0 * (0 * E_0 + 1 * S): nterm = 2, arity 1, tables [E_0 | S]
-            HG_CUDA(cudaMemcpyAsync(d_gp_coeffs_.p, one_one, sizeof one_one, cudaMemcpyHostToDevice, s));
-            HG_CUDA(cudaStreamSynchronize(s));
-            sumcheck_dev<FP, 1>(ctx_, KC_SC_COLL, ch, wo, d_coll_.p, R, 2, d_gp_coeffs_.p, d_bufA_.p, d_bufB_.p, sc_, coll_state, nullptr, nullptr, lead);
+            // g(E_0, S) = E_0 * (0 * E_0 + 1 * S): nterm = 2, arity 1, tables [E_0 | S]; coefficients {0, 1} live in d_coll_terms_
+            sumcheck_dev<FP, 1>(ctx_, KC_SC_COLL, ch, wo, d_coll_.p, R, 2, d_coll_terms_.p, d_bufA_.p, d_bufB_.p, sc_, coll_state, nullptr, nullptr, lead);
         }
         // ---- gamma, tau (lasso.rs:99)
         const size_t gt_idx = ch.squeeze(2);
@@ -1027,7 +1031,12 @@ template <class FP> class LassoNodeDev {
         std::vector<std::vector<GpItem<FP>>> rounds(maxJ + 1);
         std::vector<size_t> round_bytes(maxJ + 1, 0);
         size_t part_need = 0;
-        const int target_blocks = ctx_->sm_count * 4;
+        // grid shape of the streaming launches: at most gp_max_bx blocks along a table, term groups added until an item has
+        // about gp_target blocks (tunable for experiments through HG_GP_MAXBX / HG_GP_TARGET, in units of the SM count)
+        static const int env_maxbx = getenv("HG_GP_MAXBX") ? atoi(getenv("HG_GP_MAXBX")) : 4;
+        static const int env_target = getenv("HG_GP_TARGET") ? atoi(getenv("HG_GP_TARGET")) : 2;
+        const int target_blocks = ctx_->sm_count * env_target;
+        const size_t gp_max_bx = (size_t)ctx_->sm_count * env_maxbx;
         for (int r = 0; r <= maxJ; r++) {
             int blk = 0;
             size_t part_off = 0;
@@ -1058,7 +1067,7 @@ template <class FP> class LassoNodeDev {
                 }
                 size_t b = (threads_x + HG_BLOCK - 1) / HG_BLOCK;
                 if (b < 1) b = 1;
-                if (b > (size_t)max_blocks_) b = max_blocks_;
+                if (b > gp_max_bx) b = gp_max_bx;
                 int g = (int)std::min<size_t>((size_t)nown, std::max<size_t>(1, ((size_t)target_blocks + b - 1) / b));
                 it.tpg = (nown + g - 1) / g;
                 it.groups = (nown + it.tpg - 1) / it.tpg;
@@ -1152,7 +1161,8 @@ template <class FP> class LassoNodeDev {
     DevBuf<u16> d_dims_, d_blk_hist_;
     DevBuf<u32> d_read_cts_, d_final_cts_, d_blk_base_;
     DevBuf<int> d_pos_mem_, d_pos_dim_, d_pos_slot_, d_pos_sub_;
-    DevBuf<X> d_eq_, d_gp_coeffs_, d_bufA_, d_bufB_, d_partials_;
+    DevBuf<X> d_eq_, d_gp_coeffs_, d_bufA_, d_bufB_, d_partials_, d_coll_terms_;
+    int coll_coeff_state_ = 0;  // 0 not uploaded, 1 ascending, 2 descending
     DevBuf<unsigned> d_counters_, d_gp_counters_;
     DevBuf<X> d_pool_, d_gp_partials_;
     DevBuf<unsigned char> d_desc_;

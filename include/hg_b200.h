@@ -34,6 +34,8 @@ extern "C" {
 #define HG_OPT_A3_WIRE 3       /* 0 coefficients c0,c2..cd (default) / 1 evaluations h(0),h(2)..h(d) */
 #define HG_OPT_A3_H1 31        /* 0 h(1) := claim - h(0) (default) / 1 h(1) from the tables */
 #define HG_OPT_A5_ASCENDING 5  /* distribute_powers: 1 ascending (default) / 0 first expression highest power */
+#define HG_OPT_TWO_STREAMS 100 /* scheduling only, no effect on results: 1 (default) hg_gkr_prove runs the layer sumchecks on a second
+                                * stream next to the Lasso node in prefetch mode / 0 everything on the context's stream */
 
 typedef struct hg_ctx hg_ctx;
 typedef struct hg_transcript hg_transcript;
