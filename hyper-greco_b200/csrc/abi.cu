@@ -420,6 +420,9 @@ int hg_ctx_create(int device, int field_id, hg_ctx** out) {
             HG_CUDA(cudaStreamCreateWithPriority(&c->dev.stream2, cudaStreamNonBlocking, hi));
             HG_CUDA(cudaEventCreateWithFlags(&c->dev.ev_fork, cudaEventDisableTiming));
             HG_CUDA(cudaEventCreateWithFlags(&c->dev.ev_join, cudaEventDisableTiming));
+            HG_CUDA(cudaStreamCreateWithFlags(&c->dev.stream3, cudaStreamNonBlocking));
+            HG_CUDA(cudaEventCreateWithFlags(&c->dev.ev_fork3, cudaEventDisableTiming));
+            HG_CUDA(cudaEventCreateWithFlags(&c->dev.ev_join3, cudaEventDisableTiming));
         }
         HG_CUDA(cudaDeviceGetAttribute(&c->dev.sm_count, cudaDevAttrMultiProcessorCount, device));
         *out = c.release();
@@ -431,6 +434,9 @@ void hg_ctx_destroy(hg_ctx* ctx) {
     ctx->ops.reset();
     if (ctx->dev.ev_fork) cudaEventDestroy(ctx->dev.ev_fork);
     if (ctx->dev.ev_join) cudaEventDestroy(ctx->dev.ev_join);
+    if (ctx->dev.ev_fork3) cudaEventDestroy(ctx->dev.ev_fork3);
+    if (ctx->dev.ev_join3) cudaEventDestroy(ctx->dev.ev_join3);
+    if (ctx->dev.stream3) cudaStreamDestroy(ctx->dev.stream3);
     if (ctx->dev.stream2) cudaStreamDestroy(ctx->dev.stream2);
     if (ctx->dev.stream) cudaStreamDestroy(ctx->dev.stream);
     delete ctx;

@@ -215,7 +215,9 @@ struct FrField {
     __device__ __forceinline__ static void xacc_mad_(XAcc& a, X x, X y) { a = fr_add(a, fr_mul(x, y)); }
     __device__ __forceinline__ static void xacc_mad_b(XAcc& a, X x, B y) { a = fr_add(a, fr_mul(x, y)); }
     __device__ __forceinline__ static X xacc_reduce_(const XAcc& a) { return a; }
+    __device__ __forceinline__ static void xacc_mad_any(XAcc& a, X x, X y) { a = fr_add(a, fr_mul(x, y)); }
     __device__ __forceinline__ static X fmul(X x, X y) { return fr_mul(x, y); }
+    __device__ __forceinline__ static X fmul_any(X x, X y) { return fr_mul(x, y); }
     __device__ __forceinline__ static X fold(X a0, X a1, X r, FoldAux) { return fr_add(a0, fr_mul(r, fr_sub(a1, a0))); }
     __device__ __forceinline__ static X fold_scaled(B a0, B a1, X c, X cr) { return fr_add(fr_mul(c, a0), fr_mul(cr, fr_sub(a1, a0))); }
     __device__ __forceinline__ static X slope(X lo, X hi) { return fr_sub(hi, lo); }

@@ -92,8 +92,16 @@ struct GlField {
     __device__ __forceinline__ static void xacc_mad_(XAcc& a, X x, X y) { xacc_mad(a, x, y); }
     __device__ __forceinline__ static void xacc_mad_b(XAcc& a, X x, B y) { xacc_mad_base(a, x, y); }
     __device__ __forceinline__ static X xacc_reduce_(const XAcc& a) { return xacc_reduce(a); }
+    __device__ __forceinline__ static void xacc_mad_any(XAcc& a, X x, X y) { xacc_mad(a, x, y); }
+    __device__ __forceinline__ static void xacc_mad_any(XAcc& a, X x, B y) { xacc_mad_base(a, x, y); }
     __device__ __forceinline__ static B fmul(B x, B y) { return gl_mul_fast(x, y); }
     __device__ __forceinline__ static X fmul(X x, X y) { return gl2_mul_fast(x, y); }
+    __device__ __forceinline__ static X fmul_any(X x, X y) { return gl2_mul_fast(x, y); }
+    __device__ __forceinline__ static X fmul_any(X x, B y) {  // extension * base: two products
+        acc192 c0 = acc_zero(), c1 = acc_zero();
+        acc_mad(c0, x.c0, y); acc_mad(c1, x.c1, y);
+        return gl2_make(acc_reduce(c0), acc_reduce(c1));
+    }
     // a0 + r (a1 - a0): canonical in, canonical out
     __device__ __forceinline__ static X fold(X a0, X a1, X r, FoldAux aux) { return gl2_fold(a0, a1, r, aux.r7); }
     __device__ __forceinline__ static X fold(B a0, B a1, X r, FoldAux aux) { return gl2_fold(a0, a1, r, aux.r7); }

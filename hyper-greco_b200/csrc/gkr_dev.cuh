@@ -526,7 +526,9 @@ template <class FP> class GkrCircuitDev {
             }
             it.msg = ch.d_msg(j.msg_off + 4 * (size_t)r);
             const size_t npairs = r == 0 ? it.n_in / 2 : it.n_in / 4;
-            size_t b = std::max<size_t>(1, std::min<size_t>((npairs + HG_BLOCK - 1) / HG_BLOCK, (size_t)ctx_->sm_count * 16));
+            // several pairs per thread: the block-level reduction that ends every block costs about as much as eight pairs (measured optimum 8-16)
+            static const size_t ppt = getenv("HG_PROD_PPT") ? (size_t)atoi(getenv("HG_PROD_PPT")) : 16;
+            size_t b = std::max<size_t>(1, std::min<size_t>((npairs + HG_BLOCK * ppt - 1) / (HG_BLOCK * ppt), (size_t)ctx_->sm_count * 16));
             it.nblk = (int)b; it.bx = (int)b; it.blk_start = blk;
             blk += it.nblk;
             it.partials = d_partials_.p + part_off;

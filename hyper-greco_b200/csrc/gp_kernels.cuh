@@ -36,6 +36,7 @@ __device__ __forceinline__ void load4(const gl2* p, gl2 (&v)[4]) {
     ldg256(p + 2, v[2].c0, v[2].c1, v[3].c0, v[3].c1);
 }
 __device__ __forceinline__ void load2(const u64* p, u64 (&v)[2]) { ldg128(p, v[0], v[1]); }
+__device__ __forceinline__ void load2(const gl2* p, gl2 (&v)[2]) { ldg256(p, v[0].c0, v[0].c1, v[1].c0, v[1].c1); }
 __device__ __forceinline__ void store2(gl2* p, gl2 a, gl2 b) { stg256(p, a.c0, a.c1, b.c0, b.c1); }
 // BN254: one element = one 256-bit access
 __device__ __forceinline__ void load4(const fr* p, fr (&v)[4]) {

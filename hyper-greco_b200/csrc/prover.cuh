@@ -44,7 +44,9 @@ struct DeviceCtx {
     int device = 0;
     cudaStream_t stream = nullptr;    // the launching stream (KernelScope, HG_K and every helper read it at call time)
     cudaStream_t stream2 = nullptr;   // see hg_ctx_create
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t stream3 = nullptr;   // Lasso access counters next to the claim / collation sumcheck
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork3 = nullptr, ev_join3 = nullptr;
+    bool join3_pending = false;
     bool two_streams = true;
     int sm_count = 148;
     size_t launches = 0;  // kernels enqueued (bench.py "gpu_launches")
@@ -792,15 +794,29 @@ template <class FP> class LassoNodeDev {
              k_polynomialize<FP><<<(unsigned)((R + HG_BLOCK - 1) / HG_BLOCK), HG_BLOCK, 0, s>>>(d_inputs, rows, d_row_lookup_.p, d_meta_.p, d_subtables_.p,
                                                                                                 d_coeff_coll_.p, d_wpow_.p, R, d_dims_.p, d_E_.p, d_S, d_out_.p));
         HG_CUDA(cudaMemcpyAsync(d_coll_.p, d_E_.p, R * sizeof(B), cudaMemcpyDeviceToDevice, s));
-        HG_CUDA(cudaMemsetAsync(d_read_cts_.p, 0, d_read_cts_.bytes(), s));
+        // access counters: needed only by the hash build (after gamma, tau), so they run on a side stream next to the claim
+        // evaluation and the collation sumcheck; enqueue_protocol joins before the first kernel that reads them
+        const bool side = ctx_->two_streams && !ctx_->profile && ctx_->stream3 != nullptr;
+        cudaStream_t cs = s;
+        if (side) {
+            HG_CUDA(cudaEventRecord(ctx_->ev_fork3, s));
+            HG_CUDA(cudaStreamWaitEvent(ctx_->stream3, ctx_->ev_fork3, 0));
+            cs = ctx_->stream3;
+            ctx_->stream = cs;  // HG_K times / counts on the launching stream
+        }
+        HG_CUDA(cudaMemsetAsync(d_read_cts_.p, 0, d_read_cts_.bytes(), cs));
         for (int sl = 0; sl < nslots_; sl++) {
             const u16* addr = d_dims_.p + (size_t)slot_addr_dim_[sl] * R;
-            HG_K(ctx_, KC_COUNTERS, rows * 3, k_cnt_hist<<<nblk_cnt_, 1024, M * 2, s>>>(addr, d_row_lookup_.p, slot_used_[sl], rows, rows_per_block_, d_blk_hist_.p, log2M_));
-            HG_K(ctx_, KC_COUNTERS, M * 4, k_cnt_scan<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(d_blk_hist_.p, nblk_cnt_, log2M_, d_blk_base_.p, d_final_cts_.p + (size_t)sl * M));
-            HG_K(ctx_, KC_COUNTERS, rows * 7, k_cnt_rank<<<nblk_cnt_, 1024, 0, s>>>(addr, d_row_lookup_.p, slot_used_[sl], rows, R, rows_per_block_, d_blk_base_.p, log2M_,
-                                                                                  d_read_cts_.p + (size_t)sl * R));
+            HG_K(ctx_, KC_COUNTERS, rows * 3, k_cnt_hist<<<nblk_cnt_, 1024, M * 2, cs>>>(addr, d_row_lookup_.p, slot_used_[sl], rows, rows_per_block_, d_blk_hist_.p, log2M_));
+            HG_K(ctx_, KC_COUNTERS, M * 4, k_cnt_scan<<<(unsigned)((M + 255) / 256), 256, 0, cs>>>(d_blk_hist_.p, nblk_cnt_, log2M_, d_blk_base_.p, d_final_cts_.p + (size_t)sl * M));
+            HG_K(ctx_, KC_COUNTERS, rows * 7, k_cnt_rank<<<nblk_cnt_, 1024, 0, cs>>>(addr, d_row_lookup_.p, slot_used_[sl], rows, R, rows_per_block_, d_blk_base_.p, log2M_,
+                                                                                   d_read_cts_.p + (size_t)sl * R));
         }
-
+        if (side) {
+            ctx_->stream = s;
+            HG_CUDA(cudaEventRecord(ctx_->ev_join3, cs));
+            ctx_->join3_pending = true;
+        }
     }
 
     // the interactive part of prove_claim_reduction on an already-begun channel (lasso.rs:85-113)
@@ -829,6 +845,10 @@ template <class FP> class LassoNodeDev {
         }
         // ---- gamma, tau (lasso.rs:99)
         const size_t gt_idx = ch.squeeze(2);
+        if (ctx_->join3_pending) {  // the access counters (enqueue_witness) are read from here on
+            HG_CUDA(cudaStreamWaitEvent(s, ctx_->ev_join3, 0));
+            ctx_->join3_pending = false;
+        }
         // ---- memory checking (lasso.rs:292-339, prover.rs:35-181)
         const bool fused_up = R >= 4;  // hash build fused with the first tree level
         if (fused_up)
