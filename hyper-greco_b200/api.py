@@ -23,8 +23,8 @@ DEGREE = {GOLDILOCKS: 2, BN254: 1}
 # every symbol include/hg_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "hg_last_error", "hg_version", "hg_ctx_create", "hg_ctx_destroy", "hg_ctx_set_option", "hg_ctx_synchronize", "hg_ctx_launch_count",
-    "hg_ctx_stream", "hg_ctx_profile", "hg_ctx_profile_read", "hg_kernel_class_count", "hg_kernel_class_name", "hg_buf_alloc", "hg_buf_upload", "hg_buf_download", "hg_buf_device_ptr", "hg_buf_size", "hg_buf_free", "hg_field_base_bytes", "hg_field_encode", "hg_field_decode",
-    "hg_transcript_new", "hg_transcript_from_proof", "hg_transcript_free", "hg_transcript_squeeze_challenge", "hg_transcript_write_felt_ext",
+    "hg_ctx_stream", "hg_ctx_profile", "hg_ctx_profile_read", "hg_kernel_class_count", "hg_kernel_class_name", "hg_buf_alloc", "hg_buf_upload", "hg_buf_upload_async", "hg_buf_download", "hg_buf_device_ptr", "hg_buf_size", "hg_buf_free", "hg_field_base_bytes", "hg_field_encode", "hg_field_decode",
+    "hg_transcript_new", "hg_transcript_from_proof", "hg_transcript_free", "hg_transcript_squeeze_challenge", "hg_transcript_squeeze_challenges", "hg_transcript_write_felt_ext",
     "hg_transcript_read_felt_ext", "hg_transcript_proof_len", "hg_transcript_proof_copy", "hg_transcript_num_squeezed",
     "hg_lasso_preprocess", "hg_lasso_pp_free", "hg_lasso_pp_num_lookups", "hg_lasso_pp_num_subtables", "hg_lasso_pp_num_memories",
     "hg_lasso_pp_lookup_index", "hg_lasso_pp_memory_maps", "hg_lasso_pp_subtable_id", "hg_lasso_node_new", "hg_lasso_node_free",
@@ -32,7 +32,7 @@ SYMBOLS = [
     "hg_lasso_node_num_chunks", "hg_lasso_node_timing", "hg_lasso_node_shard_words", "hg_lasso_node_prove_shard", "hg_lasso_node_emit_shard",
     "hg_shard_merge", "hg_sumcheck_prove", "hg_mle_eval_batch", "hg_ntt", "hg_bfv_evaluate", "hg_field_selftest",
     "hg_circuit_new", "hg_circuit_free", "hg_circuit_insert_input", "hg_circuit_insert_fft", "hg_circuit_insert_lasso", "hg_circuit_insert_vanilla",
-    "hg_circuit_connect", "hg_circuit_evaluate", "hg_circuit_node_value", "hg_gkr_prove", "hg_gkr_timing", "hg_gkr_num_challenges", "hg_gkr_num_inputs", "hg_gkr_num_input_claims",
+    "hg_circuit_connect", "hg_circuit_evaluate", "hg_circuit_evaluate_host", "hg_circuit_node_value", "hg_gkr_prove", "hg_gkr_timing", "hg_gkr_num_challenges", "hg_gkr_num_inputs", "hg_gkr_num_input_claims",
     "hg_gkr_input_claim_num_vars", "hg_gkr_input_claim",
 ]
 
@@ -68,6 +68,7 @@ def lib():
         L.hg_buf_alloc.argtypes = [vp, sz, C.POINTER(vp)]
         L.hg_buf_upload.argtypes = [vp, vp, sz, vp, sz]
         L.hg_buf_download.argtypes = [vp, vp, sz, vp, sz]
+        L.hg_buf_upload_async.argtypes = [vp, vp, sz, vp, sz]
         L.hg_buf_device_ptr.argtypes = [vp]
         L.hg_buf_device_ptr.restype = vp
         L.hg_buf_size.argtypes = [vp]
@@ -81,6 +82,7 @@ def lib():
         L.hg_transcript_from_proof.argtypes = [i32, vp, sz, C.POINTER(vp)]
         L.hg_transcript_free.argtypes = [vp]
         L.hg_transcript_squeeze_challenge.argtypes = [vp, vp]
+        L.hg_transcript_squeeze_challenges.argtypes = [vp, sz, vp]
         L.hg_transcript_write_felt_ext.argtypes = [vp, vp]
         L.hg_transcript_read_felt_ext.argtypes = [vp, vp]
         L.hg_transcript_proof_len.argtypes = [vp]
@@ -122,6 +124,7 @@ def lib():
         L.hg_circuit_insert_vanilla.argtypes = [vp, sz, sz, sz, sz] + [vp] * 12 + [C.POINTER(i32)]
         L.hg_circuit_connect.argtypes = [vp, i32, i32]
         L.hg_circuit_evaluate.argtypes = [vp, vp, sz]
+        L.hg_circuit_evaluate_host.argtypes = [vp, vp, vp, sz]
         L.hg_circuit_node_value.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(sz)]
         L.hg_gkr_prove.argtypes = [vp, sz, vp, vp, vp, vp, i32]
         for f in ("hg_gkr_num_inputs",):
@@ -237,6 +240,13 @@ class DeviceBuffer:
         arr = np.ascontiguousarray(arr)
         _chk(lib().hg_buf_upload(self.ctx.h, self.h, offset, _p(arr), arr.nbytes))
 
+    def upload_async(self, arr, offset=0):
+        """No wait: `arr` (contiguous, ideally pinned) must stay alive until the next synchronising call."""
+        if not arr.flags["C_CONTIGUOUS"]:
+            raise HgError("upload_async needs a contiguous array")
+        self._keepalive = arr
+        _chk(lib().hg_buf_upload_async(self.ctx.h, self.h, offset, _p(arr), arr.nbytes))
+
     def download(self, dtype, count, offset=0):
         out = np.zeros(count, dtype)
         _chk(lib().hg_buf_download(self.ctx.h, self.h, offset, _p(out), out.nbytes))
@@ -281,7 +291,10 @@ class Keccak256Transcript:
         return out
 
     def squeeze_challenges(self, n):
-        return np.stack([self.squeeze_challenge() for _ in range(n)]) if n else np.zeros((0, self._el), np.uint64)
+        out = np.zeros((n, self._el), np.uint64)
+        if n:
+            _chk(lib().hg_transcript_squeeze_challenges(self.h, n, _p(out)))
+        return out
 
     def write_felt_ext(self, e):
         _chk(lib().hg_transcript_write_felt_ext(self.h, _p(np.ascontiguousarray(e, np.uint64))))
@@ -621,6 +634,16 @@ class Circuit:
         ptrs = (C.c_void_p * len(dev_inputs))(*[b.ptr for b in dev_inputs])
         _chk(lib().hg_circuit_evaluate(self.h, ptrs, len(dev_inputs)))
 
+    def evaluate_host(self, host_inputs):
+        """Circuit::evaluate from host vectors (numpy uint64 arrays of canonical limbs; pinned memory makes the copies
+        asynchronous). The arrays must stay alive until the next synchronising call (prove_gkr, mle_eval_batch)."""
+        arrs = [np.ascontiguousarray(a, np.uint64) for a in host_inputs]
+        limbs = LIMBS[self.ctx.field]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        lens = (C.c_size_t * len(arrs))(*[a.size // limbs for a in arrs])
+        self._host_keepalive = arrs
+        _chk(lib().hg_circuit_evaluate_host(self.h, ptrs, lens, len(arrs)))
+
     def node_value(self, node_id):
         p, n = C.c_void_p(), C.c_size_t(0)
         _chk(lib().hg_circuit_node_value(self.h, node_id, C.byref(p), C.byref(n)))
@@ -753,6 +776,23 @@ class BfvSkEncryptProver:
     def upload_inputs(self, ins):
         u = lambda v: DeviceBuffer.from_numpy(self.ctx, np.asarray(v, dtype=np.uint64).reshape(-1))
         return [u(ins["s"]), u(ins["e"]), u(ins["k1"])] + [u(a) for a in ins["ais"]] + [u(a) for a in ins["r1is"]] + [u(ins["r2is"])]
+
+    def prove_host(self, host_inputs, host_ct0is, mode=MODE_PREFETCH):
+        """BfvEncrypt::prove (:417-460) from HOST vectors (get_inputs order: s, e, k1, ais.., r1is.., r2is; ct0is concatenated):
+        uploads, circuit.evaluate, output claim, prove_gkr. Returns (proof bytes, input claims)."""
+        ct = np.ascontiguousarray(host_ct0is, np.uint64).reshape(-1)
+        if getattr(self, "_d_ct", None) is None or self._d_ct.nbytes != ct.nbytes:
+            self._d_ct = DeviceBuffer(self.ctx, ct.nbytes)
+        tr = Keccak256Transcript(self.ctx.field)                                                 # :431
+        self.circuit.evaluate_host(host_inputs)                                                  # :438-442
+        self._d_ct.upload_async(ct)
+        if self.ctx.field == BN254:
+            _chk(lib().hg_field_encode(self.ctx.h, self._d_ct.ptr, ct.size // LIMBS[BN254]))
+        point = tr.squeeze_challenges(self.ct0is_log2_size)                                      # :445
+        value = mle_eval_batch(self.ctx, self._d_ct, 1, self.ct0is_log2_size, point)[0]          # :446
+        el = point.shape[1]
+        claims = self.circuit.prove_gkr([(np.zeros((0, el), np.uint64), np.zeros(el, np.uint64)), (point, value)], tr, mode)   # :450-457
+        return tr.into_proof(), claims                                                           # :459
 
     def prove(self, dev_inputs, d_ct0is: DeviceBuffer, mode=MODE_PREFETCH):
         """BfvEncrypt::prove (:417-460). Returns (proof bytes, input claims)."""

@@ -155,6 +155,7 @@ struct ICircuit {
     virtual int insert_vanilla(const VanillaDesc& d) = 0;
     virtual void connect(int a, int b) = 0;
     virtual void evaluate(const void* const* in, size_t n) = 0;
+    virtual void evaluate_host(DeviceCtx* dev, const void* const* in, const size_t* n_elems, size_t n) = 0;
     virtual void node_value(int id, const void** p, size_t* len) = 0;
     virtual void prove(size_t n_claims, const size_t* lens, const uint64_t* pts, const uint64_t* vals, ITranscript* t, int mode, const WireOptions& wo) = 0;
     virtual const double* timing() const = 0;
@@ -175,6 +176,23 @@ template <class FP> struct CircuitT : ICircuit {
     void evaluate(const void* const* in, size_t n) override {
         std::vector<const B*> v;
         for (size_t i = 0; i < n; i++) v.push_back((const B*)in[i]);
+        c.evaluate(v);
+    }
+    // the circuit's own copy of the inputs (allocated once): host vectors are uploaded and, for BN254, brought to the device
+    // representation, all asynchronously on the context's stream; evaluate follows in stream order
+    std::vector<std::unique_ptr<DevBuf<B>>> host_inputs;
+    void evaluate_host(DeviceCtx* dev, const void* const* in, const size_t* n_elems, size_t n) override {
+        const std::vector<size_t> lens = c.input_lens();
+        if (n != lens.size()) throw std::runtime_error("evaluate: wrong number of inputs");
+        if (host_inputs.size() != n) { host_inputs.clear(); for (size_t i = 0; i < n; i++) { host_inputs.emplace_back(new DevBuf<B>()); host_inputs.back()->alloc(lens[i]); } }
+        std::vector<const B*> v;
+        for (size_t i = 0; i < n; i++) {
+            if (n_elems[i] != lens[i]) throw std::runtime_error("evaluate: input length does not match the input node");
+            if (host_inputs[i]->n != lens[i]) host_inputs[i]->alloc(lens[i]);
+            HG_CUDA(cudaMemcpyAsync(host_inputs[i]->p, in[i], lens[i] * sizeof(B), cudaMemcpyHostToDevice, dev->stream));
+            if (FP::FIELD_ID == 1) { k_field_encode<FP><<<(unsigned)((lens[i] + 255) / 256), 256, 0, dev->stream>>>(host_inputs[i]->p, lens[i], 0); HG_LAUNCH_CHECK(); }
+            v.push_back(host_inputs[i]->p);
+        }
         c.evaluate(v);
     }
     void node_value(int id, const void** p, size_t* len) override {
@@ -299,28 +317,34 @@ template <class FP> struct FieldOpsT : IFieldOps {
     void mle_eval_batch(DeviceCtx* dev, const void* d_tables, size_t n_tables, size_t stride, size_t num_vars, const uint64_t* point_ext, uint64_t* out_ext) override {
         const size_t n = (size_t)1 << num_vars;
         cudaStream_t s = dev->stream;
-        DevBuf<X> pt, eq, partials, out;
-        DevBuf<unsigned> counters;
-        std::vector<X> hp(num_vars);
-        for (size_t i = 0; i < num_vars; i++) hp[i] = FP::x_from_limbs(point_ext + FP::X_LIMBS * i);
-        pt.alloc(std::max<size_t>(num_vars, 1));
-        HG_CUDA(cudaMemcpy(pt.p, hp.data(), num_vars * sizeof(X), cudaMemcpyHostToDevice));
+        // work buffers persist across calls (a cudaMalloc / cudaFree pair per buffer costs more than the evaluation)
+        DevBuf<X>&pt = mle_pt_, &eq = mle_eq_, &partials = mle_partials_, &out = mle_out_;
+        DevBuf<unsigned>& counters = mle_counters_;
+        auto grow = [&](auto& buf, size_t need) { if (buf.n < need) { HG_CUDA(cudaStreamSynchronize(s)); buf.alloc(need + need / 2); } };
+        const size_t np = std::max<size_t>(num_vars, 1);
+        grow(pt, np);
+        if (mle_hpt_.n < np + n_tables) mle_hpt_.alloc(2 * (np + n_tables));
+        for (size_t i = 0; i < num_vars; i++) mle_hpt_.p[i] = FP::x_from_limbs(point_ext + FP::X_LIMBS * i);
+        HG_CUDA(cudaMemcpyAsync(pt.p, mle_hpt_.p, num_vars * sizeof(X), cudaMemcpyHostToDevice, s));
         const int lo = num_vars < 12 ? (int)num_vars : 12;
         const size_t nlo = (size_t)1 << lo, nhi = n >> lo;
-        eq.alloc(nlo + nhi);
-        out.alloc(n_tables);
+        grow(eq, nlo + nhi);
+        grow(out, n_tables);
         int blocks = (int)std::min<size_t>(nhi, (size_t)dev->sm_count * 2);
-        partials.alloc((size_t)blocks * n_tables);
-        counters.alloc(n_tables);
-        HG_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), s));
+        grow(partials, (size_t)blocks * n_tables);
+        grow(counters, n_tables);
+        HG_CUDA(cudaMemsetAsync(counters.p, 0, n_tables * sizeof(unsigned), s));
         HG_K(dev, KC_EQ, (nlo + nhi) * sizeof(X), k_eq_split<FP><<<(unsigned)((nlo + nhi + HG_BLOCK - 1) / HG_BLOCK), HG_BLOCK, 0, s>>>(pt.p, (int)num_vars, lo, eq.p, eq.p + nlo));
         HG_K(dev, KC_DOT, n_tables * n * sizeof(B),
              k_dot_eq<FP, B><<<dim3(blocks, (unsigned)n_tables), HG_BLOCK, 0, s>>>((const B*)d_tables, stride, n, lo, eq.p, eq.p + nlo, partials.p, counters.p, out.p));
-        std::vector<X> ho(n_tables);
-        HG_CUDA(cudaMemcpyAsync(ho.data(), out.p, n_tables * sizeof(X), cudaMemcpyDeviceToHost, s));
+        X* ho = mle_hpt_.p + np;  // pinned
+        HG_CUDA(cudaMemcpyAsync(ho, out.p, n_tables * sizeof(X), cudaMemcpyDeviceToHost, s));
         HG_CUDA(cudaStreamSynchronize(s));
         for (size_t i = 0; i < n_tables; i++) FP::x_to_limbs(ho[i], out_ext + FP::X_LIMBS * i);
     }
+    DevBuf<X> mle_pt_, mle_eq_, mle_partials_, mle_out_;
+    DevBuf<unsigned> mle_counters_;
+    PinnedBuf<X> mle_hpt_;
     void bfv_evaluate(DeviceCtx* dev, size_t log2_size, size_t K, const uint64_t* qis, const uint64_t* k0is, const uint64_t* r1_bounds, const uint64_t* r2_bounds,
                       uint64_t s_bound, uint64_t e_bound, uint64_t k1_bound, const void* d_s, const void* d_e, const void* d_k1, const void* d_ais,
                       const void* d_r1is, const void* d_r2is, void* d_lasso_inputs, void* d_sum) override {
@@ -493,6 +517,13 @@ int hg_buf_upload(hg_ctx* ctx, hg_buf* buf, size_t offset, const void* host, siz
         HG_CUDA(cudaStreamSynchronize(ctx->dev.stream));
     })
 }
+int hg_buf_upload_async(hg_ctx* ctx, hg_buf* buf, size_t offset, const void* host, size_t bytes) {
+    HG_TRY({
+        if (offset + bytes > buf->bytes) throw std::runtime_error("hg_buf_upload_async: out of range");
+        HG_CUDA(cudaSetDevice(ctx->dev.device));
+        HG_CUDA(cudaMemcpyAsync((char*)buf->p + offset, host, bytes, cudaMemcpyHostToDevice, ctx->dev.stream));
+    })
+}
 int hg_buf_download(hg_ctx* ctx, const hg_buf* buf, size_t offset, void* host, size_t bytes) {
     HG_TRY({
         if (offset + bytes > buf->bytes) throw std::runtime_error("hg_buf_download: out of range");
@@ -531,6 +562,12 @@ int hg_transcript_from_proof(int field_id, const uint8_t* proof, size_t len, hg_
 }
 void hg_transcript_free(hg_transcript* t) { delete t; }
 int hg_transcript_squeeze_challenge(hg_transcript* t, uint64_t* out_ext) { HG_TRY({ t->t->squeeze(out_ext); }) }
+int hg_transcript_squeeze_challenges(hg_transcript* t, size_t n, uint64_t* out_ext) {
+    HG_TRY({
+        const size_t el = t->t->field_id == HG_FIELD_GOLDILOCKS ? 2 : 4;
+        for (size_t i = 0; i < n; i++) t->t->squeeze(out_ext + i * el);
+    })
+}
 int hg_transcript_write_felt_ext(hg_transcript* t, const uint64_t* ext) { HG_TRY({ t->t->write(ext); }) }
 int hg_transcript_read_felt_ext(hg_transcript* t, uint64_t* out_ext) { HG_TRY({ t->t->read(out_ext); }) }
 size_t hg_transcript_proof_len(const hg_transcript* t) { return t->t->proof().size(); }
@@ -716,6 +753,9 @@ int hg_circuit_insert_vanilla(hg_circuit* c, size_t input_arity, size_t log2_sub
 int hg_circuit_connect(hg_circuit* c, int from, int to) { HG_TRY({ c->c->connect(from, to); }) }
 int hg_circuit_evaluate(hg_circuit* c, const void* const* d_inputs, size_t n_inputs) {
     HG_TRY({ HG_CUDA(cudaSetDevice(c->ctx->dev.device)); c->c->evaluate(d_inputs, n_inputs); })
+}
+int hg_circuit_evaluate_host(hg_circuit* c, const void* const* host_inputs, const size_t* n_elems, size_t n_inputs) {
+    HG_TRY({ HG_CUDA(cudaSetDevice(c->ctx->dev.device)); c->c->evaluate_host(&c->ctx->dev, host_inputs, n_elems, n_inputs); })
 }
 int hg_circuit_node_value(hg_circuit* c, int id, const void** d_ptr, size_t* len) { HG_TRY({ c->c->node_value(id, d_ptr, len); }) }
 int hg_gkr_prove(hg_circuit* c, size_t n_output_claims, const size_t* point_lens, const uint64_t* points_ext, const uint64_t* values_ext,

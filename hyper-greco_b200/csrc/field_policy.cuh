@@ -24,7 +24,7 @@ struct GlField {
     HG_HD static B root_of_unity() { return 0x185629dcda58878cULL; }  // 7^((p-1)/2^32), goldilocks ROOT_OF_UNITY (A9)
     static constexpr int TWO_ADICITY = 32;
     static constexpr int PLANES = 2;  // base planes per extension element
-    static constexpr int GP_TAIL_LOG = 6, GP_MIN_BLOCKS = 2;
+    static constexpr int GP_TAIL_LOG = 6, GP_MIN_BLOCKS = 2, GP_R0_U = 4, GP_R0A_QPT = 4;
     HG_HD static bool b_eq(B a, B b) { return a == b; }
     HG_HD static B plane(X a, int p) { return p ? a.c1 : a.c0; }
     HG_HD static X from_planes(const B* p) { return gl2_make(p[0], p[1]); }

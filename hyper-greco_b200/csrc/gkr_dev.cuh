@@ -118,8 +118,14 @@ template <class FP> class GkrCircuitDev {
         nodes_[to]->preds.push_back(from);
         nodes_[from]->succs.push_back(to);
         topo_.clear();
+        eval_planned_ = false;
     }
     size_t num_nodes() const { return nodes_.size(); }
+    std::vector<size_t> input_lens() const {  // output length of every input node, insertion order
+        std::vector<size_t> v;
+        for (auto& n : nodes_) if (n->kind == GKR_INPUT) v.push_back(n->out_len);
+        return v;
+    }
     // host phases of the last prove, microseconds: [witness enqueue, squeeze + upload challenges, protocol walk (+ Lasso enqueue),
     // batched layer enqueue, wait for the GPU, serialise]
     const double* timing() const { return timing_; }
@@ -127,35 +133,42 @@ template <class FP> class GkrCircuitDev {
     size_t node_out_len(int id) const { return nodes_.at(id)->out_len; }
     const B* node_value(int id) const { return nodes_.at(id)->value_ptr; }
 
-    // Circuit::evaluate (sk_encryption_circuit.rs:442): inputs = device pointers for the input nodes in insertion order
+    // Circuit::evaluate (sk_encryption_circuit.rs:442): inputs = device pointers for the input nodes in insertion order.
+    // Nodes are processed level by level (level = longest path from an input); the FFT nodes of one level with the same size
+    // and direction share one contiguous arena and are transformed by ONE batched NTT (the circuit has 2K+1 forward
+    // transforms on one level). Nothing here waits for the device.
     void evaluate(const std::vector<const B*>& inputs) {
         cudaStream_t s = ctx_->stream;
         size_t next = 0;
         for (auto& n : nodes_) if (n->kind == GKR_INPUT) { if (next >= inputs.size()) throw std::runtime_error("evaluate: too few inputs"); n->value_ptr = inputs[next++]; }
         if (next != inputs.size()) throw std::runtime_error("evaluate: too many inputs");
-        for (int id : topo()) {
-            Node& n = *nodes_[id];
-            if (n.kind == GKR_INPUT) continue;
-            if (n.kind == GKR_LASSO) { n.value_ptr = nullptr; continue; }
-            if (n.kind == GKR_FFT) {
-                const Node& p = *nodes_[n.preds.at(0)];
-                if (p.out_len != n.out_len) throw std::runtime_error("evaluate: FFT input size mismatch");
-                HG_CUDA(cudaMemcpyAsync(n.value.p, p.value_ptr, n.out_len * sizeof(B), cudaMemcpyDeviceToDevice, s));
-                ntt_->run(n.value.p, n.log2_size, n.fft_inverse, 1);
-                n.value_ptr = n.value.p;
-                continue;
+        plan_evaluate();
+        for (auto& lvl : eval_levels_) {
+            for (auto& grp : lvl.fft_groups) {
+                const Node& first = *nodes_[grp.nodes[0]];
+                const size_t N = first.out_len;
+                for (size_t k = 0; k < grp.nodes.size(); k++) {
+                    Node& n = *nodes_[grp.nodes[k]];
+                    const Node& p = *nodes_[n.preds.at(0)];
+                    HG_CUDA(cudaMemcpyAsync(grp.arena->p + k * N, p.value_ptr, N * sizeof(B), cudaMemcpyDeviceToDevice, s));
+                    n.value_ptr = grp.arena->p + k * N;
+                }
+                ntt_->run(grp.arena->p, first.log2_size, first.fft_inverse, grp.nodes.size());
             }
-            if ((int)n.preds.size() != n.arity) throw std::runtime_error("evaluate: Vanilla node arity does not match its connections");
-            std::vector<const B*> ptrs;
-            for (int pid : n.preds) { if (nodes_[pid]->out_len != n.n_in) throw std::runtime_error("evaluate: Vanilla input size mismatch"); ptrs.push_back(nodes_[pid]->value_ptr); }
-            n.in_ptrs.alloc(ptrs.size());
-            HG_CUDA(cudaMemcpyAsync(n.in_ptrs.p, ptrs.data(), ptrs.size() * sizeof(B*), cudaMemcpyHostToDevice, s));
-            HG_CUDA(cudaStreamSynchronize(s));
-            VanillaFwd w{n.add_ptr.p, n.add_in.p, n.add_wire.p, n.mul_ptr.p, n.mul_in0.p, n.mul_w0.p, n.mul_in1.p, n.mul_w1.p};
-            HG_K(ctx_, KC_MISC, n.out_len * sizeof(B) * 2,
-                 k_vanilla_eval<FP><<<(unsigned)((n.out_len + 255) / 256), 256, 0, s>>>(w, n.add_coef.p, n.mul_coef.p, n.consts.p, (const B* const*)n.in_ptrs.p, n.ng,
-                                                                                      (size_t)1 << n.log2_sub, n.num_reps, n.out_len, n.value.p));
-            n.value_ptr = n.value.p;
+            for (int id : lvl.vanilla) {
+                Node& n = *nodes_[id];
+                bool changed = false;
+                for (size_t k = 0; k < n.preds.size(); k++) {
+                    const B* p = nodes_[n.preds[k]]->value_ptr;
+                    if (n.h_in_ptrs.p[k] != p) { n.h_in_ptrs.p[k] = p; changed = true; }
+                }
+                if (changed) HG_CUDA(cudaMemcpyAsync(n.in_ptrs.p, n.h_in_ptrs.p, n.preds.size() * sizeof(B*), cudaMemcpyHostToDevice, s));
+                VanillaFwd w{n.add_ptr.p, n.add_in.p, n.add_wire.p, n.mul_ptr.p, n.mul_in0.p, n.mul_w0.p, n.mul_in1.p, n.mul_w1.p};
+                HG_K(ctx_, KC_MISC, n.out_len * sizeof(B) * 2,
+                     k_vanilla_eval<FP><<<(unsigned)((n.out_len + 255) / 256), 256, 0, s>>>(w, n.add_coef.p, n.mul_coef.p, n.consts.p, (const B* const*)n.in_ptrs.p, n.ng,
+                                                                                          (size_t)1 << n.log2_sub, n.num_reps, n.out_len, n.value.p));
+                n.value_ptr = n.value.p;
+            }
         }
         evaluated_ = true;
     }
@@ -169,6 +182,7 @@ template <class FP> class GkrCircuitDev {
         auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         const double t0 = now();
         plan();
+        desc_off_ = 0; eq_off_ = 0;  // the previous proof ended with a synchronised flush: its staging regions are free
         Channel<FP>& ch = *ch_;
         struct Claim { bool by_index; size_t idx; std::vector<X> point_host; int nvars; std::shared_ptr<X> value; };
         std::vector<std::vector<Claim>> claims(nodes_.size());
@@ -332,6 +346,7 @@ template <class FP> class GkrCircuitDev {
         DevBuf<u32> add_in, mul_in0, mul_in1, rev_out;
         DevBuf<B> add_coef, mul_coef, consts, consts_full, rev_coef, value;
         DevBuf<const B*> in_ptrs;
+        PinnedBuf<const B*> h_in_ptrs;  // what in_ptrs holds (uploaded again only when an input pointer changes)
         const B* value_ptr = nullptr;
         LassoNodeDev<FP>* lasso = nullptr;
         // per-node work buffers of the layer sumcheck
@@ -343,6 +358,48 @@ template <class FP> class GkrCircuitDev {
         size_t S = 0, alpha_idx = (size_t)-1, const_off = 0, msg_off = 0, r0_idx = 0, evals_off = 0;
         std::vector<const X*> points;
     };
+
+    struct FftGroup { std::vector<int> nodes; std::unique_ptr<DevBuf<B>> arena; };
+    struct EvalLevel { std::vector<FftGroup> fft_groups; std::vector<int> vanilla; };
+    // static schedule of evaluate(): levels, FFT batches, pointer tables
+    void plan_evaluate() {
+        if (eval_planned_) return;
+        std::vector<int> depth(nodes_.size(), 0);
+        int maxd = 0;
+        for (int id : topo()) {
+            Node& n = *nodes_[id];
+            for (int p : n.preds) depth[id] = std::max(depth[id], depth[p] + 1);
+            maxd = std::max(maxd, depth[id]);
+        }
+        eval_levels_.clear();
+        eval_levels_.resize(maxd + 1);
+        for (int id : topo()) {
+            Node& n = *nodes_[id];
+            if (n.kind == GKR_INPUT) continue;
+            if (n.kind == GKR_LASSO) { n.value_ptr = nullptr; continue; }
+            EvalLevel& lvl = eval_levels_[depth[id]];
+            if (n.kind == GKR_FFT) {
+                if (nodes_[n.preds.at(0)]->out_len != n.out_len) throw std::runtime_error("evaluate: FFT input size mismatch");
+                FftGroup* g = nullptr;
+                for (auto& cand : lvl.fft_groups) {
+                    const Node& f = *nodes_[cand.nodes[0]];
+                    if (f.log2_size == n.log2_size && f.fft_inverse == n.fft_inverse) { g = &cand; break; }
+                }
+                if (!g) { lvl.fft_groups.emplace_back(); g = &lvl.fft_groups.back(); }
+                g->nodes.push_back(id);
+                continue;
+            }
+            if ((int)n.preds.size() != n.arity) throw std::runtime_error("evaluate: Vanilla node arity does not match its connections");
+            for (int pid : n.preds) if (nodes_[pid]->out_len != n.n_in) throw std::runtime_error("evaluate: Vanilla input size mismatch");
+            n.in_ptrs.alloc(n.preds.size());
+            n.h_in_ptrs.alloc(n.preds.size());
+            for (size_t k = 0; k < n.preds.size(); k++) n.h_in_ptrs.p[k] = nullptr;
+            lvl.vanilla.push_back(id);
+        }
+        for (auto& lvl : eval_levels_)
+            for (auto& g : lvl.fft_groups) { g.arena.reset(new DevBuf<B>()); g.arena->alloc(g.nodes.size() * nodes_[g.nodes[0]]->out_len); }
+        eval_planned_ = true;
+    }
 
     static size_t pad2(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }
     static int log2sz(size_t n) { int l = 0; while (((size_t)1 << l) < n) l++; return l; }
@@ -597,7 +654,8 @@ template <class FP> class GkrCircuitDev {
     NttEngine<FP>* ntt_;
     std::vector<std::unique_ptr<Node>> nodes_;
     std::vector<int> topo_;
-    bool evaluated_ = false, planned_ = false;
+    bool evaluated_ = false, planned_ = false, eval_planned_ = false;
+    std::vector<EvalLevel> eval_levels_;
     size_t total_chal_ = 0, desc_off_ = 0, eq_off_ = 0;
     std::unique_ptr<Channel<FP>> ch_;
     DevBuf<X> d_eq_, d_partials_, d_outpts_;

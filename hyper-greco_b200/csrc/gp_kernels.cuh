@@ -208,6 +208,7 @@ constexpr int HG_TAIL_THREADS = 512;
 
 template <class FP> struct GpItem {
     const void* in;                  // tables read this round (base in rounds 0/1, extension later): [2*nvec][n_in]
+    const void* parent;              // round 0, first half: the tree layer above, [nvec][n_in] base elements = l_i * r_i
     typename FP::X* out;             // folded tables written this round: [2*nvec][n_in/2]
     unsigned long long n_in;
     const typename FP::X* c;         // c_i
@@ -224,7 +225,7 @@ template <class FP> struct GpItem {
 
 template <class FP, int NP>
 __device__ __forceinline__ void block_reduce_finalize_ex(typename FP::X (&acc)[NP], typename FP::X* partials, unsigned* counter,
-                                                         typename FP::X* out, unsigned nblk, unsigned bid) {
+                                                         typename FP::X* out, unsigned nblk, unsigned bid, int out_stride = 1) {
     typedef typename FP::X X;
     __shared__ X sm[32][NP];
     __shared__ bool is_last;
@@ -275,7 +276,7 @@ __device__ __forceinline__ void block_reduce_finalize_ex(typename FP::X (&acc)[N
             X v = lane < nwarps ? sm[lane][p] : FP::x_zero();
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) v = FP::x_add(v, FP::x_shfl_down(v, off));
-            if (lane == 0) out[p] = v;
+            if (lane == 0) out[p * out_stride] = v;
         }
         if (lane == 0) *counter = 0;
     }
@@ -292,11 +293,62 @@ template <class ITEM> __device__ __forceinline__ int find_item(const ITEM* items
 }
 template <class FP> __device__ __forceinline__ int gp_find_item(const GpItem<FP>* items, int nitems) { return find_item(items, nitems); }
 
+// Round 0 is split in two launches.
+// (a) h(0) and h(1): l_i(2b) * r_i(2b) and l_i(2b+1) * r_i(2b+1) are entries 2b, 2b+1 of the tree layer ABOVE (Layer::up,
+//     prover.rs:332-354, already in memory), so these two samples need no product of l and r:
+//         h(0) = sum_b t_0(2b) * sum_i c_i parent_i(2b),   h(1) the same at 2b+1         -> msg[0], msg[3]
+//     computed as sum_i c_i * D_i with the base-field dot products D_i = sum_b t_0(2b) parent_i(2b) (resp. 2b+1): per entry
+//     one unreduced 64x64 multiply-add; c_i is applied once per term and thread.
+template <class FP>
+__global__ void __launch_bounds__(HG_BLOCK, 2) k_gp_r0a_multi(const GpItem<FP>* __restrict__ items, int nitems) {
+    typedef typename FP::B B;
+    typedef typename FP::X X;
+    constexpr int QPT = FP::GP_R0A_QPT;  // quads (4 consecutive entries = two pairs) per thread and term
+    const GpItem<FP> it = items[gp_find_item<FP>(items, nitems)];
+    const unsigned lb = blockIdx.x - it.blk_start;
+    const unsigned bxi = lb % it.bx, grp = lb / it.bx;
+    const B* tables = (const B*)it.in;
+    const B* parent = (const B*)it.parent;
+    const size_t n = it.n_in, nquads = n / 4;
+    const int i0 = it.i_begin + grp * it.tpg, i1 = min(it.i_end, i0 + it.tpg);
+    typename FP::XAcc accx[2] = {FP::xacc_zero_(), FP::xacc_zero_()};
+    for (size_t q0 = (size_t)bxi * (blockDim.x * QPT) + threadIdx.x; q0 < nquads; q0 += (size_t)it.bx * blockDim.x * QPT) {
+        for (int i = i0; i < i1; i++) {
+            const B* pi = parent + (size_t)i * n;
+            B p[QPT][4];
+#pragma unroll
+            for (int k = 0; k < QPT; k++) {
+                const size_t q = q0 + (size_t)k * blockDim.x;
+#pragma unroll
+                for (int e = 0; e < 4; e++) p[k][e] = FP::b_zero();
+                if (q < nquads) load4(pi + 4 * q, p[k]);
+            }
+            typename FP::BAcc d0 = FP::bacc_zero(), d1 = FP::bacc_zero();
+#pragma unroll
+            for (int k = 0; k < QPT; k++) {
+                const size_t q = q0 + (size_t)k * blockDim.x;
+                if (q < nquads) {
+                    const B* t = tables + 4 * q;  // t_0: the same addresses for every term, served by L1
+                    FP::bacc_mad(d0, t[0], p[k][0]);
+                    FP::bacc_mad(d1, t[1], p[k][1]);
+                    FP::bacc_mad(d0, t[2], p[k][2]);
+                    FP::bacc_mad(d1, t[3], p[k][3]);
+                }
+            }
+            const X c = it.c[i];
+            FP::xacc_mad_b(accx[0], c, FP::bacc_reduce(d0));
+            FP::xacc_mad_b(accx[1], c, FP::bacc_reduce(d1));
+        }
+    }
+    X acc[2] = {FP::xacc_reduce_(accx[0]), FP::xacc_reduce_(accx[1])};
+    block_reduce_finalize_ex<FP, 2>(acc, it.partials, it.counter, it.msg, it.nblk, lb, 3);
+}
+// (b) h(inf) and h(-1) from the slopes / values at -1 of t_0, l_i, r_i                       -> msg[1], msg[2]
 template <class FP, int U>
 __global__ void __launch_bounds__(HG_BLOCK, FP::GP_MIN_BLOCKS) k_gp_r0_multi(const GpItem<FP>* __restrict__ items, int nitems) {
     typedef typename FP::B B;
     typedef typename FP::X X;
-    constexpr int NP = 4;
+    constexpr int NP = 2;
     const GpItem<FP> it = items[gp_find_item<FP>(items, nitems)];
     const unsigned lb = blockIdx.x - it.blk_start;
     const unsigned bxi = lb % it.bx, grp = lb / it.bx;
@@ -313,7 +365,7 @@ __global__ void __launch_bounds__(HG_BLOCK, FP::GP_MIN_BLOCKS) k_gp_r0_multi(con
             const size_t b = b0 + u * stride;
             B p[2] = {FP::b_zero(), FP::b_zero()};
             if (b < npairs) load2(tables + 2 * b, p);
-            t0[u][0] = p[0]; t0[u][1] = FP::slope(p[0], p[1]); t0[u][2] = FP::at_m1(p[0], p[1]); t0[u][3] = p[1];
+            t0[u][0] = FP::slope(p[0], p[1]); t0[u][1] = FP::at_m1(p[0], p[1]);
         }
         for (int i = i0; i < i1; i++) {
             const B* li = tables + (size_t)i * 2 * n;
@@ -333,10 +385,8 @@ __global__ void __launch_bounds__(HG_BLOCK, FP::GP_MIN_BLOCKS) k_gp_r0_multi(con
             for (int p = 0; p < NP; p++) s[p] = FP::bacc_zero();
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                FP::bacc_mad(s[0], t0[u][0], FP::fmul(l[u][0], r[u][0]));
-                FP::bacc_mad(s[1], t0[u][1], FP::fmul(FP::slope(l[u][0], l[u][1]), FP::slope(r[u][0], r[u][1])));
-                FP::bacc_mad(s[2], t0[u][2], FP::fmul(FP::at_m1(l[u][0], l[u][1]), FP::at_m1(r[u][0], r[u][1])));
-                FP::bacc_mad(s[3], t0[u][3], FP::fmul(l[u][1], r[u][1]));
+                FP::bacc_mad(s[0], t0[u][0], FP::fmul(FP::slope(l[u][0], l[u][1]), FP::slope(r[u][0], r[u][1])));
+                FP::bacc_mad(s[1], t0[u][1], FP::fmul(FP::at_m1(l[u][0], l[u][1]), FP::at_m1(r[u][0], r[u][1])));
             }
             const X c = it.c[i];
 #pragma unroll
@@ -346,7 +396,7 @@ __global__ void __launch_bounds__(HG_BLOCK, FP::GP_MIN_BLOCKS) k_gp_r0_multi(con
     X acc[NP];
 #pragma unroll
     for (int p = 0; p < NP; p++) acc[p] = FP::xacc_reduce_(accx[p]);
-    block_reduce_finalize_ex<FP, NP>(acc, it.partials, it.counter, it.msg, it.nblk, lb);
+    block_reduce_finalize_ex<FP, NP>(acc, it.partials, it.counter, it.msg + 1, it.nblk, lb);
 }
 
 template <class FP, class TIN, bool SCALE>

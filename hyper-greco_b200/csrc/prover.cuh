@@ -484,6 +484,7 @@ void sumcheck_dev(DeviceCtx* ctx, int kclass, Channel<FP>& ch, const WireOptions
 // one layer sumcheck recorded for batched execution (prefetch mode): everything the device needs is static
 template <class FP> struct GpLayerJob {
     const typename FP::B* tables;  // [nvec][2n]
+    const typename FP::B* parent;  // [nvec][n]: the tree layer above (entries l_i * r_i), read by round 0
     size_t n;
     int nvec, nv;
     size_t gamma_idx, r0_idx, msg_off, evals_off;
@@ -496,7 +497,7 @@ template <class FP>
 void gp_sumcheck_dev(DeviceCtx* ctx, Channel<FP>& ch, const WireOptions& wo, const typename FP::B* d_tables, size_t n, int nvec,
                      const typename FP::X* d_gamma, typename FP::X* d_coeffs, typename FP::X* bufA, typename FP::X* bufB, const ScScratch& sc,
                      std::shared_ptr<ScHostState<FP>> st, size_t* first_chal, size_t* evals_off, bool* scaled,
-                     std::vector<GpLayerJob<FP>>* batch = nullptr, size_t gamma_idx = 0) {
+                     std::vector<GpLayerJob<FP>>* batch = nullptr, size_t gamma_idx = 0, const typename FP::B* d_parent = nullptr) {
     typedef typename FP::B B;
     typedef typename FP::X X;
     constexpr int D = 3;
@@ -506,7 +507,8 @@ void gp_sumcheck_dev(DeviceCtx* ctx, Channel<FP>& ch, const WireOptions& wo, con
     if (batch) {
         // prefetch mode: only the protocol bookkeeping happens here; LassoNodeDev::run_gp_batch launches the work
         GpLayerJob<FP> job;
-        job.tables = d_tables; job.n = n; job.nvec = nvec; job.nv = nv; job.gamma_idx = gamma_idx;
+        job.tables = d_tables; job.parent = d_parent; job.n = n; job.nvec = nvec; job.nv = nv; job.gamma_idx = gamma_idx;
+        if (!d_parent) throw std::runtime_error("gp_sumcheck_dev: batched mode needs the parent layer");
         for (int j = 0; j < nv; j++) {
             size_t off = ch.alloc_msg(j == 0 ? D + 1 : D);
             if (j == 0) job.msg_off = off;
@@ -997,7 +999,8 @@ template <class FP> class LassoNodeDev {
             size_t sc_first = 0, ev_off = 0;
             bool scaled = false;
             const B* tables = layer[nvars - 1 - nv];
-            gp_sumcheck_dev<FP>(ctx_, ch, wo, tables, (size_t)1 << nv, nvec, ch.d_chal(gamma_idx), d_gp_coeffs_.p, d_bufA_.p, d_bufB_.p, sc_, st, &sc_first, &ev_off, &scaled, batch, gamma_idx);
+            gp_sumcheck_dev<FP>(ctx_, ch, wo, tables, (size_t)1 << nv, nvec, ch.d_chal(gamma_idx), d_gp_coeffs_.p, d_bufA_.p, d_bufB_.p, sc_, st, &sc_first, &ev_off, &scaled, batch, gamma_idx,
+                                layer[nvars - nv]);
             ch.emit([chp, gp, ev_off, nvec, scaled, gamma_idx, asc]() {
                 auto& t = chp->transcript();
                 // the device keeps l_i (i > 0) pre-multiplied by c_i (gp_kernels.cuh); undo it exactly with c_i^{-1}
@@ -1049,6 +1052,9 @@ template <class FP> class LassoNodeDev {
         int maxJ = -1;
         for (auto& j : jobs) if (j.n > ((size_t)1 << FP::GP_TAIL_LOG)) maxJ = std::max(maxJ, j.nv - FP::GP_TAIL_LOG);
         std::vector<std::vector<GpItem<FP>>> rounds(maxJ + 1);
+        std::vector<GpItem<FP>> round0a;  // first half of round 0 (k_gp_r0a_multi): own geometry, partials and counters
+        size_t round0a_bytes = 0, part0a_off = 0;
+        int blk0a = 0;
         std::vector<size_t> round_bytes(maxJ + 1, 0);
         size_t part_need = 0;
         // grid shape of the streaming launches: at most gp_max_bx blocks along a table, term groups added until an item has
@@ -1066,6 +1072,7 @@ template <class FP> class LassoNodeDev {
                 GpItem<FP> it;
                 const int ntab = 2 * j.nvec;
                 it.nvec = j.nvec;
+                it.parent = j.parent;
                 it.i_begin = own_begin(j.nvec); it.i_end = own_end(j.nvec); it.write_t0 = it.i_begin > 0;
                 const int nown = it.i_end - it.i_begin;
                 it.c = coef[k]; it.cr = coef[k] + j.nvec;
@@ -1073,7 +1080,7 @@ template <class FP> class LassoNodeDev {
                 if (r == 0) {
                     it.in = j.tables; it.out = nullptr; it.n_in = j.n; it.r_prev = nullptr;
                     it.msg = ch.d_msg(j.msg_off);
-                    threads_x = (j.n / 2 + 1) / 2;  // U = 2
+                    threads_x = (j.n / 2 + FP::GP_R0_U - 1) / FP::GP_R0_U;
                     round_bytes[r] += (size_t)(2 * nown + it.write_t0) * j.n * sizeof(B);
                 } else {
                     it.n_in = j.n >> (r - 1);
@@ -1099,12 +1106,33 @@ template <class FP> class LassoNodeDev {
                 part_off += (size_t)it.nblk * 4;
                 it.counter = d_gp_counters_.p + rounds[r].size();
                 rounds[r].push_back(it);
+                if (r == 0) {  // the parent-layer half: 4 pairs per thread, term groups until the item has ~target blocks
+                    GpItem<FP> a = it;
+                    size_t ba = (j.n / 4 + FP::GP_R0A_QPT * HG_BLOCK - 1) / (FP::GP_R0A_QPT * HG_BLOCK);  // GP_R0A_QPT quads of parent entries per thread and term
+                    if (ba < 1) ba = 1;
+                    if (ba > gp_max_bx) ba = gp_max_bx;
+                    int ga = (int)std::min<size_t>((size_t)nown, std::max<size_t>(1, ((size_t)target_blocks + ba - 1) / ba));
+                    a.tpg = (nown + ga - 1) / ga;
+                    a.groups = (nown + a.tpg - 1) / a.tpg;
+                    a.bx = (int)ba;
+                    a.nblk = a.bx * a.groups;
+                    a.blk_start = blk0a;
+                    blk0a += a.nblk;
+                    a.partials = nullptr;  // assigned below, behind the partials of the largest round
+                    part0a_off += (size_t)a.nblk * 2;
+                    a.counter = d_gp_counters_.p + 64 + round0a.size();
+                    round0a_bytes += (size_t)nown * j.n * sizeof(B);  // actual traffic of the parent-layer half (not algorithmic)
+                    round0a.push_back(a);
+                }
             }
             part_need = std::max(part_need, part_off);
-            if (rounds[r].size() > d_gp_counters_.n) throw std::runtime_error("run_gp_batch: too many layers");
+            if (rounds[r].size() > 64) throw std::runtime_error("run_gp_batch: too many layers");
         }
-        if (part_need > d_gp_partials_.n) { d_gp_partials_.alloc(part_need * 2); /* re-point */
+        if (part_need + part0a_off > d_gp_partials_.n) { d_gp_partials_.alloc((part_need + part0a_off) * 2); /* re-point */
             for (auto& rv : rounds) { size_t off = 0; for (auto& it : rv) { it.partials = d_gp_partials_.p + off; off += (size_t)it.nblk * 4; } } }
+        (void)round0a_bytes;
+        { size_t off = part_need; for (auto& a : round0a) { a.partials = d_gp_partials_.p + off; off += (size_t)a.nblk * 2; } }
+        if (round0a.size() + 64 > d_gp_counters_.n) throw std::runtime_error("run_gp_batch: too many layers");
         std::vector<GpTailItem<FP>> titems(nl);
         size_t tail_bytes = 0;
         for (int k = 0; k < nl; k++) {
@@ -1125,7 +1153,8 @@ template <class FP> class LassoNodeDev {
         }
         // upload descriptors
         size_t bytes = citems.size() * sizeof(GpCoeffItem<FP>) + titems.size() * sizeof(GpTailItem<FP>);
-        for (auto& rv : rounds) bytes += rv.size() * sizeof(GpItem<FP>);
+        for (auto& rv : rounds) bytes += rv.size() * sizeof(GpItem<FP>) + 16;
+        bytes += round0a.size() * sizeof(GpItem<FP>) + 64;
         if (h_desc_.n < bytes) { h_desc_.alloc(bytes * 2); d_desc_.alloc(bytes * 2); }
         unsigned char* hp = h_desc_.p;
         size_t off = 0;
@@ -1134,6 +1163,7 @@ template <class FP> class LassoNodeDev {
         std::vector<size_t> r_off(rounds.size());
         for (size_t r = 0; r < rounds.size(); r++) r_off[r] = put(rounds[r].data(), rounds[r].size() * sizeof(GpItem<FP>));
         size_t t_off = put(titems.data(), titems.size() * sizeof(GpTailItem<FP>));
+        size_t a_off = put(round0a.data(), round0a.size() * sizeof(GpItem<FP>));
         if (off > h_desc_.n) throw std::runtime_error("run_gp_batch: descriptor staging overflow");
         HG_CUDA(cudaMemcpyAsync(d_desc_.p, h_desc_.p, off, cudaMemcpyHostToDevice, s));
         // launches
@@ -1143,8 +1173,13 @@ template <class FP> class LassoNodeDev {
             const auto& last = rounds[r].back();
             const int grid = last.blk_start + last.nblk, ni = (int)rounds[r].size();
             const GpItem<FP>* di = (const GpItem<FP>*)(d_desc_.p + r_off[r]);
+            if (r == 0 && !round0a.empty()) {
+                KernelScope ka(ctx_, KC_SC_GP, 0);  // reads the parent layer: no algorithmic bytes of its own (SURVEY.md 8d counts round 0 once)
+                k_gp_r0a_multi<FP><<<blk0a, HG_BLOCK, 0, s>>>((const GpItem<FP>*)(d_desc_.p + a_off), (int)round0a.size());
+                HG_LAUNCH_CHECK();
+            }
             KernelScope ks(ctx_, KC_SC_GP, round_bytes[r]);
-            if (r == 0) k_gp_r0_multi<FP, 2><<<grid, HG_BLOCK, 0, s>>>(di, ni);
+            if (r == 0) k_gp_r0_multi<FP, FP::GP_R0_U><<<grid, HG_BLOCK, 0, s>>>(di, ni);
             else if (r == 1) k_gp_fold_multi<FP, B, true><<<grid, HG_BLOCK, 0, s>>>(di, ni);
             else k_gp_fold_multi<FP, X, false><<<grid, HG_BLOCK, 0, s>>>(di, ni);
             HG_LAUNCH_CHECK();

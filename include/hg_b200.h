@@ -67,6 +67,8 @@ void* hg_ctx_stream(hg_ctx* ctx);
 /* ---- device buffers (owned by the caller through the handle; Rust frees them in Drop) --------------------------- */
 int hg_buf_alloc(hg_ctx* ctx, size_t bytes, hg_buf** out);
 int hg_buf_upload(hg_ctx* ctx, hg_buf* buf, size_t offset, const void* host, size_t bytes);
+/* the same without waiting: `host` must stay valid (and should be page-locked) until a later call synchronises the context */
+int hg_buf_upload_async(hg_ctx* ctx, hg_buf* buf, size_t offset, const void* host, size_t bytes);
 int hg_buf_download(hg_ctx* ctx, const hg_buf* buf, size_t offset, void* host, size_t bytes);
 void* hg_buf_device_ptr(hg_buf* buf);
 size_t hg_buf_size(const hg_buf* buf);
@@ -85,6 +87,7 @@ int hg_transcript_new(int field_id, hg_transcript** out);                       
 int hg_transcript_from_proof(int field_id, const uint8_t* proof, size_t len, hg_transcript** out); /* ::from_proof  transcript.rs:131-135 */
 void hg_transcript_free(hg_transcript* t);
 int hg_transcript_squeeze_challenge(hg_transcript* t, uint64_t* out_ext);   /* transcript.rs:149-154 */
+int hg_transcript_squeeze_challenges(hg_transcript* t, size_t n, uint64_t* out_ext); /* n consecutive squeezes (TranscriptWrite::squeeze_challenges) */
 int hg_transcript_write_felt_ext(hg_transcript* t, const uint64_t* ext);    /* transcript.rs:191-195 */
 int hg_transcript_read_felt_ext(hg_transcript* t, uint64_t* out_ext);       /* transcript.rs:172-177 */
 size_t hg_transcript_proof_len(const hg_transcript* t);                     /* into_proof, transcript.rs:126-128 */
@@ -186,6 +189,11 @@ int hg_circuit_insert_vanilla(hg_circuit* c, size_t input_arity, size_t log2_sub
 int hg_circuit_connect(hg_circuit* c, int from, int to);                                       /* circuit.connect(from, to) */
 /* circuit.evaluate(inputs): device pointers for the input nodes in insertion order; node values stay on the device */
 int hg_circuit_evaluate(hg_circuit* c, const void* const* d_inputs, size_t n_inputs);
+/* The same from HOST vectors, as the reference passes them (sk_encryption_circuit.rs:438-442): input i has n_elems[i] base
+ * elements in canonical little-endian limbs. They are copied into device buffers owned by the circuit (asynchronously when the
+ * host memory is page-locked) and the circuit is evaluated; the host vectors must stay valid until the next call that
+ * synchronises the context (hg_gkr_prove, hg_mle_eval_batch, hg_ctx_synchronize). */
+int hg_circuit_evaluate_host(hg_circuit* c, const void* const* host_inputs, const size_t* n_elems, size_t n_inputs);
 int hg_circuit_node_value(hg_circuit* c, int id, const void** d_ptr, size_t* len);
 /* gkr::prove_gkr(&circuit, &values, &output_claims, &mut transcript): one claim per output node (insertion order); point i has
  * point_lens[i] extension elements (concatenated in points_ext), values_ext one extension element per claim. The claims that

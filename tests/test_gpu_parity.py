@@ -399,6 +399,13 @@ def test_full_gkr_prove_matches_oracle_on_reference_fixtures(api, ctx, oracle, g
     # forward evaluation kept on the device: the sum layer equals ct0is
     ptr, n = prover.circuit.node_value(prover.ids["sum"])
     assert n == io["ct0is"].size
+    # BfvEncrypt::prove from host vectors (uploads + level-batched evaluate inside): the same bytes, twice (buffers are reused)
+    for _ in range(2):
+        proof_h, claims_h = prover.prove_host(flat, io["ct0is"], mode)
+        assert proof_h == oproof
+    assert all((a[0][1] == b[0][1]).all() for a, b in zip(claims, claims_h))
+    with pytest.raises(api.HgError):
+        prover.circuit.evaluate_host(flat[:-1])
 
 
 def test_full_gkr_prove_full_size_properties(api, ctx, oracle):
@@ -415,6 +422,9 @@ def test_full_gkr_prove_full_size_properties(api, ctx, oracle):
     oracle.bfv_verify(0, P, ins, ct0is, proof)
     proof2, _ = prover.prove(dev, d_ct, 0)
     assert proof2 == proof
+    flat = [ins["s"], ins["e"], ins["k1"]] + list(ins["ais"]) + list(ins["r1is"]) + [ins["r2is"]]
+    proof3, _ = prover.prove_host([np.array(v, dtype=np.uint64) for v in flat], np.array(ct0is, dtype=np.uint64), 0)
+    assert proof3 == proof
 
 
 # ------------------------------------------------------------------------------------------------ BN254 Fr (E = F)
