@@ -265,14 +265,16 @@ def run_ours(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
         achieved = (dby / 1e9) / (dms / 1e3) if dms > 0 else 0.0
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dn)
+        traffic = traffic_step = None
+        try:   # ncu DRAM bytes of the same kernels (profiles/traffic.json, written by scripts/make_profiles.py from an ncu run of this command)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dn)
+            traffic, traffic_step = tj["bytes_per_launch"], tj["bytes_per_step"]
         except Exception:
             pass
         total_ms = sum(v[1] for v in prof.values())
         roofline = {"bound": "hbm", "kernel": dn, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                    "traffic": traffic, "peak_source": peak_src, "launches_per_step": dl / prof_steps, "avg_launch_us": 1000.0 * dms / max(dl, 1),
+                    "traffic": traffic, "traffic_bytes_per_step": traffic_step, "algorithmic_bytes_per_launch": dby / max(dl, 1),
+                    "algorithmic_bytes_per_step": dby / prof_steps, "peak_source": peak_src, "launches_per_step": dl / prof_steps, "avg_launch_us": 1000.0 * dms / max(dl, 1),
                     "share_of_step_kernel_time": dms / total_ms if total_ms else None,
                     "per_class": {k: {"launches": v[0] / prof_steps, "ms": v[1] / prof_steps, "alg_GB": v[2] / prof_steps / 1e9,
                                       "GBps": (v[2] / 1e9) / (v[1] / 1e3) if v[1] > 0 else None} for k, v in prof.items()},
