@@ -621,8 +621,19 @@ class Circuit:
         a = lambda v, t: np.ascontiguousarray(v if v is not None else (z64 if t == np.uint64 else z32), t)
         hc = np.ascontiguousarray(has_const, np.uint8)
         mp = a(mul_ptr if mul_ptr is not None else np.zeros(ng + 1, np.uint64), np.uint64)
-        arrs = [hc, a(consts, np.uint64), a(add_ptr, np.uint64), a(add_coef, np.uint64), a(add_in, np.uint32), a(add_wire, np.uint64), mp,
-                a(mul_coef, np.uint64), a(mul_in0, np.uint32), a(mul_w0, np.uint64), a(mul_in1, np.uint32), a(mul_w1, np.uint64)]
+        limbs = LIMBS[self.ctx.field]
+
+        def felts(v):
+            """field elements cross the ABI as `limbs` little-endian u64 words each: widen small (u64) coefficients"""
+            v = a(v, np.uint64)
+            if limbs == 1 or (v.ndim == 2 and v.shape[1] == limbs):
+                return np.ascontiguousarray(v.reshape(-1))
+            out = np.zeros((v.size, limbs), np.uint64)
+            out[:, 0] = v.reshape(-1)
+            return out.reshape(-1)
+
+        arrs = [hc, felts(consts), a(add_ptr, np.uint64), felts(add_coef), a(add_in, np.uint32), a(add_wire, np.uint64), mp,
+                felts(mul_coef), a(mul_in0, np.uint32), a(mul_w0, np.uint64), a(mul_in1, np.uint32), a(mul_w1, np.uint64)]
         i = C.c_int(-1)
         _chk(lib().hg_circuit_insert_vanilla(self.h, arity, log2_sub, num_reps, ng, *[_p(x) for x in arrs], C.byref(i)))
         return i.value

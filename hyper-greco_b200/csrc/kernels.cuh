@@ -186,17 +186,53 @@ template <class FP, class T> struct ToBase { __device__ __forceinline__ static t
 // Batched MLE evaluation (mod.rs:80-93, lasso.rs:422-454): out[y] = sum_k eq(point, k) * tables[y][k], one streaming pass
 // per table. Row kh of 2^lo_bits elements is reduced against eq_lo with unreduced accumulation, then scaled by eq_hi[kh].
 // grid = (blocks, ntables)
+// four consecutive table entries with one load where the type allows it
+template <class FP, class T> struct Load4 {
+    __device__ __forceinline__ static void f(const T* p, typename FP::B (&v)[4]) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) v[e] = FP::to_base(p[e]);
+    }
+};
+template <class FP> struct Load4<FP, unsigned short> {
+    __device__ __forceinline__ static void f(const unsigned short* p, typename FP::B (&v)[4]) {
+        const ushort4 t = __ldg(reinterpret_cast<const ushort4*>(p));
+        v[0] = FP::to_base(t.x); v[1] = FP::to_base(t.y); v[2] = FP::to_base(t.z); v[3] = FP::to_base(t.w);
+    }
+};
+template <class FP> struct Load4<FP, unsigned int> {
+    __device__ __forceinline__ static void f(const unsigned int* p, typename FP::B (&v)[4]) {
+        const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+        v[0] = FP::to_base(t.x); v[1] = FP::to_base(t.y); v[2] = FP::to_base(t.z); v[3] = FP::to_base(t.w);
+    }
+};
+template <class FP> struct Load4<FP, u64> {
+    __device__ __forceinline__ static void f(const u64* p, typename FP::B (&v)[4]) {
+        const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2*>(p)), b = __ldg(reinterpret_cast<const ulonglong2*>(p) + 1);
+        v[0] = FP::to_base((u64)a.x); v[1] = FP::to_base((u64)a.y); v[2] = FP::to_base((u64)b.x); v[3] = FP::to_base((u64)b.y);
+    }
+};
 template <class FP, class T>
-__global__ void k_dot_eq(const T* __restrict__ tables, size_t stride, size_t n, int lo_bits, const typename FP::X* __restrict__ eq_lo,
+__global__ void __launch_bounds__(HG_BLOCK) k_dot_eq(const T* __restrict__ tables, size_t stride, size_t n, int lo_bits, const typename FP::X* __restrict__ eq_lo,
                          const typename FP::X* __restrict__ eq_hi, typename FP::X* partials, unsigned* counter, typename FP::X* out) {
     typedef typename FP::X X;
+    typedef typename FP::B B;
     const T* t = tables + (size_t)blockIdx.y * stride;
     const size_t nlo = (size_t)1 << lo_bits, nhi = n >> lo_bits;
     X acc[1] = {FP::x_zero()};
     for (size_t kh = blockIdx.x; kh < nhi; kh += gridDim.x) {
         typename FP::XAcc a = FP::xacc_zero_();
         const T* row = t + kh * nlo;
-        for (size_t kl = threadIdx.x; kl < nlo; kl += blockDim.x) FP::xacc_mad_b(a, eq_lo[kl], ToBase<FP, T>::f(row[kl]));
+        if (nlo >= 4) {
+#pragma unroll 4
+            for (size_t kl = 4 * (size_t)threadIdx.x; kl < nlo; kl += 4 * (size_t)blockDim.x) {
+                B v[4];
+                Load4<FP, T>::f(row + kl, v);
+#pragma unroll
+                for (int e = 0; e < 4; e++) FP::xacc_mad_b(a, eq_lo[kl + e], v[e]);
+            }
+        } else {
+            for (size_t kl = threadIdx.x; kl < nlo; kl += blockDim.x) FP::xacc_mad_b(a, eq_lo[kl], ToBase<FP, T>::f(row[kl]));
+        }
         acc[0] = FP::x_add(acc[0], FP::fmul(FP::xacc_reduce_(a), eq_hi[kh]));
     }
     block_reduce_finalize<FP, 1>(acc, partials, counter, out);

@@ -46,6 +46,12 @@ for name in ["1024_1x27_65537", "2048_1x52_65537"]:
     limbs = np.array([[(v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)] for v in vals], dtype=np.uint64)
     np.savez_compressed(os.path.join(OUT, f"lasso_inputs_bn254_{name}.npz"), inputs=limbs)
     print("bn254", name, limbs.shape)
+    if name == "1024_1x27_65537":
+        # circuit inputs / output of the BN254 witness (get_inputs), canonical 4 x u64 limbs per element
+        ins, ct0is = witness.get_inputs(P, args)
+        lm = lambda v: np.array([[(int(x) >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)] for x in v], dtype=np.uint64)
+        np.savez_compressed(os.path.join(OUT, f"circuit_io_bn254_{name}.npz"), s=lm(ins["s"]), e=lm(ins["e"]), k1=lm(ins["k1"]),
+                            ais=np.stack([lm(a) for a in ins["ais"]]), r1is=np.stack([lm(a) for a in ins["r1is"]]), r2is=lm(ins["r2is"]), ct0is=lm(ct0is))
 
 kat = {
     "keccak256_empty": "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470",

@@ -500,6 +500,29 @@ def test_bn254_lasso_node_proof_bytes_match_oracle(api, ctx_bn, oracle, golden_d
     node.free()
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_bn254_full_gkr_prove_matches_oracle(api, ctx_bn, oracle, golden_dir, mode):
+    """BfvEncrypt::prove over BN254 Fr (E = F) on the reference's own BN254 witness (bfv-gkr/src/data/bn254, n=1024): every
+    node of the circuit on the device, from host vectors; proof bytes == oracle, oracle verifier accepts."""
+    import os
+    from hyper_greco_b200 import params
+    name = "1024_1x27_65537"
+    P = params.PARAMS[name]
+    io = np.load(os.path.join(golden_dir, f"circuit_io_bn254_{name}.npz"))
+    ints = lambda a: [sum(int(r[j]) << (64 * j) for j in range(4)) for r in a.reshape(-1, 4)]
+    ins = dict(s=ints(io["s"]), e=ints(io["e"]), k1=ints(io["k1"]), ais=[ints(a) for a in io["ais"]], r1is=[ints(a) for a in io["r1is"]],
+               r2is=ints(io["r2is"]))
+    ct0is = ints(io["ct0is"])
+    oproof = oracle.bfv_prove(1, P, ins, ct0is)
+    oracle.bfv_verify(1, P, ins, ct0is, oproof)
+    prover = api.BfvSkEncryptProver(ctx_bn, P)
+    flat = [io["s"], io["e"], io["k1"]] + list(io["ais"]) + list(io["r1is"]) + [io["r2is"]]
+    proof, claims = prover.prove_host([np.ascontiguousarray(v).reshape(-1) for v in flat], io["ct0is"].reshape(-1), mode)
+    assert proof == oproof
+    oracle.bfv_verify(1, P, ins, ct0is, proof)
+    assert len(claims) == len(flat)
+
+
 def test_bn254_ntt_matches_oracle(api, ctx_bn, oracle):
     rng = np.random.default_rng(2)
     for log_n in (3, 10, 13):
