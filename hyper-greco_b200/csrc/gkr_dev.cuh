@@ -311,9 +311,12 @@ template <class FP> class GkrCircuitDev {
                 }
             } swap(ctx_, fork);
             prepare_jobs(ch, jobs, wo);
+            use_tail_ = true;
+            struct TailOff { bool* f; ~TailOff() { *f = false; } } tail_off{&use_tail_};
             int maxv = 0;
-            for (auto& j : jobs) maxv = std::max(maxv, j.nv);
+            for (auto& j : jobs) maxv = std::max(maxv, std::min(j.nv, tail_start(j)));
             for (int r = 0; r < maxv; r++) launch_round(ch, jobs, r);
+            launch_tail(ch, jobs);
             launch_finals(ch, jobs);
         }
         const double t4 = now();
@@ -492,6 +495,7 @@ template <class FP> class GkrCircuitDev {
                 X* ehi = elo + ((size_t)1 << lo);
                 eq_off_ += need;
                 EqSplitItem<FP> si; si.point = j.points[t]; si.eq_lo = elo; si.eq_hi = ehi; si.nv = nvw; si.lo_bits = lo; si.blk_start = split_blk;
+                si.alpha = j.alpha_idx == (size_t)-1 ? nullptr : ch.d_chal(j.alpha_idx); si.t = (int)t;
                 split_blk += (int)((need + HG_BLOCK - 1) / HG_BLOCK);
                 split_bytes += need * sizeof(X);
                 splits.push_back(si);
@@ -499,25 +503,26 @@ template <class FP> class GkrCircuitDev {
             }
         }
         if (!splits.empty()) HG_K(ctx_, KC_GKR_PREP, split_bytes, k_eq_split_multi<FP><<<split_blk, HG_BLOCK, 0, s>>>(stage(splits), (int)splits.size()));
-        for (size_t t = 0; t < max_claims; t++) {
+        {
             std::vector<EqAccItem<FP>> items;
             int blk = 0;
             size_t bytes = 0;
             for (size_t q = 0; q < jobs.size(); q++) {
                 const Job& j = jobs[q];
-                if (t >= j.points.size()) continue;
+                if (j.points.empty()) continue;
                 Node& n = *nodes_[j.node];
                 EqAccItem<FP> it;
-                it.eq_lo = eqs[q][t].lo; it.eq_hi = eqs[q][t].hi; it.lo_bits = eqs[q][t].lo_bits;
-                it.alpha = j.alpha_idx == (size_t)-1 ? nullptr : ch.d_chal(j.alpha_idx);
-                it.w = n.W.p; it.n = n.out_len; it.t = (int)t; it.blk_start = blk;
+                it.eq0 = eqs[q][0].lo; it.lo_bits = eqs[q][0].lo_bits;
+                it.stride = ((size_t)1 << it.lo_bits) + (n.out_len >> it.lo_bits);
+                it.n_claims = (int)j.points.size();
+                it.w = n.W.p; it.n = n.out_len; it.blk_start = blk;
                 blk += (int)((n.out_len + HG_BLOCK - 1) / HG_BLOCK);
-                bytes += n.out_len * sizeof(X) * (t ? 2 : 1);
+                bytes += n.out_len * sizeof(X);
                 items.push_back(it);
             }
-            if (items.empty()) continue;
-            HG_K(ctx_, KC_GKR_PREP, bytes, k_eq_accumulate<FP><<<blk, HG_BLOCK, 0, s>>>(stage(items), (int)items.size()));
+            if (!items.empty()) HG_K(ctx_, KC_GKR_PREP, bytes, k_eq_accumulate<FP><<<blk, HG_BLOCK, 0, s>>>(stage(items), (int)items.size()));
         }
+        (void)max_claims;
         // A per node
         std::vector<X*> fft_fwd, fft_inv;  // W tables whose transform is needed, grouped by size via a map below
         std::map<std::pair<int, int>, std::vector<int>> fft_groups;  // (log2 size, inverse) -> node ids
@@ -567,7 +572,7 @@ template <class FP> class GkrCircuitDev {
         int blk = 0;
         size_t part_off = 0, bytes = 0;
         for (const Job& j : jobs) {
-            if (r >= j.nv) continue;
+            if (r >= j.nv || r >= tail_start(j)) continue;
             Node& n = *nodes_[j.node];
             ProdItem<FP> it;
             it.nt = j.nt;
@@ -610,11 +615,46 @@ template <class FP> class GkrCircuitDev {
             Node& n = *nodes_[j.node];
             if (!(n.kind == GKR_VANILLA && n.is_linear)) continue;
             const int m = log2sz(n.n_in);
-            if (m != r || m >= j.nv || r == 0) continue;
+            if (m != r || m >= j.nv || r == 0 || m >= tail_start(j)) continue;
             CopyItem<FP> c; c.src = (m & 1) ? n.tbuf0.p : n.tbuf1.p; c.dst = n.capture.p; c.n = n.arity;
             copies.push_back(c);
         }
         if (!copies.empty()) HG_K(ctx_, KC_GKR_SC, copies.size() * 64, k_copy_items<FP><<<(unsigned)copies.size(), 32, 0, s>>>(stage(copies)));
+    }
+
+    // first round that is NOT streamed: the tail kernel takes over there (prefetch mode only; nv when the job has no tail)
+    int tail_start(const Job& j) const { return (use_tail_ && j.nv >= 3) ? std::max(2, j.nv - HG_PROD_TAIL_LOG) : j.nv; }
+    // rounds tail_start .. nv-1 and the input evaluations of every job that has a tail, one CTA per job
+    void launch_tail(Channel<FP>& ch, const std::vector<Job>& jobs) {
+        cudaStream_t s = ctx_->stream;
+        std::vector<ProdTailItem<FP>> items;
+        size_t smem = 0, bytes = 0;
+        for (const Job& j : jobs) {
+            const int rt = tail_start(j);
+            if (rt >= j.nv) continue;
+            Node& n = *nodes_[j.node];
+            ProdTailItem<FP> t;
+            t.n_in = (int)(j.S >> (rt - 1)); t.nt = j.nt; t.rounds = j.nv - rt;
+            t.w_in = ((rt - 1) & 1) ? n.wbuf0.p : n.wbuf1.p;
+            t.tab_in = ((rt - 1) & 1) ? n.tbuf0.p : n.tbuf1.p;
+            t.chal = ch.d_chal(j.r0_idx + rt - 1);
+            t.msg = ch.d_msg(j.msg_off + 4 * (size_t)rt);
+            t.evals = ch.d_msg(j.evals_off);
+            t.linear = n.kind == GKR_VANILLA && n.is_linear;
+            t.arity = n.arity; t.capture = nullptr; t.cap_round = -1;
+            if (t.linear) {
+                const int m = log2sz(n.n_in);
+                if (m == 0) throw std::runtime_error("gkr: empty input tables");
+                if (m < rt) t.capture = n.capture.p;
+                else if (m < j.nv) t.cap_round = m - rt;
+            }
+            smem = std::max(smem, ((size_t)(j.nt + 1) * (t.n_in + t.n_in / 2) + 96) * sizeof(X));
+            bytes += (size_t)(j.nt + 1) * t.n_in * sizeof(X);
+            items.push_back(t);
+        }
+        if (items.empty()) return;
+        if (smem > tail_smem_) { HG_CUDA(cudaFuncSetAttribute(k_prod_tail<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); tail_smem_ = smem; }
+        HG_K(ctx_, KC_GKR_SC, bytes, k_prod_tail<FP><<<(unsigned)items.size(), 256, smem, s>>>(stage(items)));
     }
 
     // input evaluations: linear layers read them off the table folded over the low variables; FFT / product layers off the last fold
@@ -623,6 +663,7 @@ template <class FP> class GkrCircuitDev {
         std::vector<FoldItem<FP>> folds;
         std::vector<CopyItem<FP>> copies;
         for (const Job& j : jobs) {
+            if (tail_start(j) < j.nv) continue;  // done by launch_tail
             Node& n = *nodes_[j.node];
             // state after the last round launch (round nv-1): tables folded by r_0..r_{nv-2}, length 2
             const int last = j.nv - 1;
@@ -654,7 +695,8 @@ template <class FP> class GkrCircuitDev {
     NttEngine<FP>* ntt_;
     std::vector<std::unique_ptr<Node>> nodes_;
     std::vector<int> topo_;
-    bool evaluated_ = false, planned_ = false, eval_planned_ = false;
+    bool evaluated_ = false, planned_ = false, eval_planned_ = false, use_tail_ = false;
+    size_t tail_smem_ = 0;
     std::vector<EvalLevel> eval_levels_;
     size_t total_chal_ = 0, desc_off_ = 0, eq_off_ = 0;
     std::unique_ptr<Channel<FP>> ch_;

@@ -34,7 +34,11 @@ __global__ void k_vanilla_eval(VanillaFwd w, const typename FP::B* __restrict__ 
 }
 
 // ---- eq factor tables of every (node, claim) pair in one launch
-template <class FP> struct EqSplitItem { const typename FP::X* point; typename FP::X* eq_lo; typename FP::X* eq_hi; int nv, lo_bits, blk_start; };
+// eq_lo of claim t carries the factor alpha^t (alpha = nullptr: single claim), so W = sum_t eq_lo_t (x) eq_hi_t needs no scaling pass
+template <class FP> struct EqSplitItem {
+    const typename FP::X* point; typename FP::X* eq_lo; typename FP::X* eq_hi; const typename FP::X* alpha;
+    int nv, lo_bits, blk_start, t;
+};
 template <class FP> __global__ void k_eq_split_multi(const EqSplitItem<FP>* __restrict__ items, int nitems) {
     typedef typename FP::X X;
     const EqSplitItem<FP> it = items[find_item(items, nitems)];
@@ -45,6 +49,7 @@ template <class FP> __global__ void k_eq_split_multi(const EqSplitItem<FP>* __re
     const size_t k = hi ? t - nlo : t;
     const int first = hi ? it.lo_bits : 0, last = hi ? it.nv : it.lo_bits;
     X acc = FP::x_one();
+    if (!hi && it.alpha) { const X a = *it.alpha; for (int q = 0; q < it.t; q++) acc = FP::fmul(acc, a); }
     for (int i = first; i < last; i++) {
         X r = it.point[i];
         X f = ((k >> (i - first)) & 1) ? r : FP::x_sub(FP::x_one(), r);
@@ -53,23 +58,27 @@ template <class FP> __global__ void k_eq_split_multi(const EqSplitItem<FP>* __re
     (hi ? it.eq_hi : it.eq_lo)[k] = acc;
 }
 
-// ---- W += alpha^t * eq(z_t, .) for every (node, claim) pair; eq via two factor tables built by k_eq_split
+// ---- W = sum_t alpha^t * eq(z_t, .) for every node in one launch; the factor tables of a node's claims lie back to back
+// ([eq_lo_t | eq_hi_t], stride elements apart), alpha^t is already in eq_lo_t
 template <class FP> struct EqAccItem {
-    const typename FP::X* eq_lo; const typename FP::X* eq_hi;   // of this claim
-    const typename FP::X* alpha;                                // nullptr when the node has a single claim
+    const typename FP::X* eq0;   // eq_lo of claim 0
     typename FP::X* w;
-    u64 n; int lo_bits, t, blk_start;
+    u64 n, stride;
+    int lo_bits, n_claims, blk_start;
 };
 template <class FP> __global__ void k_eq_accumulate(const EqAccItem<FP>* __restrict__ items, int nitems) {
     typedef typename FP::X X;
     const EqAccItem<FP> it = items[find_item(items, nitems)];
     const size_t i = (size_t)(blockIdx.x - it.blk_start) * blockDim.x + threadIdx.x;
     if (i >= it.n) return;
-    X e = FP::fmul(it.eq_lo[i & (((size_t)1 << it.lo_bits) - 1)], it.eq_hi[i >> it.lo_bits]);
-    if (it.alpha) { X a = *it.alpha, p = FP::x_one(); for (int q = 0; q < it.t; q++) p = FP::fmul(p, a); e = FP::fmul(e, p); }
-    it.w[i] = it.t == 0 ? e : FP::x_add(it.w[i], e);
+    const size_t nlo = (size_t)1 << it.lo_bits, lo = i & (nlo - 1), hi = i >> it.lo_bits;
+    typename FP::XAcc a = FP::xacc_zero_();
+    for (int t = 0; t < it.n_claims; t++) {
+        const X* e = it.eq0 + (size_t)t * it.stride;
+        FP::xacc_mad_(a, e[lo], e[nlo + hi]);
+    }
+    it.w[i] = FP::xacc_reduce_(a);
 }
-// claims of one node are accumulated by consecutive launches (t = 0, 1, ..), so there is no write race on w.
 
 // ---- A[x] = sum_{(o, c) in rev[x]} c * W[o]  (weights pushed through the wiring, reverse CSR), const = sum_g W[g] c_g
 template <class FP>
@@ -173,6 +182,69 @@ __global__ void __launch_bounds__(HG_BLOCK) k_prod_round_multi(const ProdItem<FP
     if (it.nt == 1) prod_round_item<FP, TIN, FOLD, 1>(it, lb, acc);
     else prod_round_item<FP, TIN, FOLD, 2>(it, lb, acc);
     block_reduce_finalize_ex<FP, 4>(acc, it.partials, it.counter, it.msg, it.nblk, lb);
+}
+
+// ---- the last rounds of every node sumcheck in ONE launch: one CTA per node, weights and tables (extension elements, at most
+// 2^(HG_PROD_TAIL_LOG+1) entries each) in shared memory. Replaces ~10 launches of a few microseconds of work each.
+constexpr int HG_PROD_TAIL_LOG = 9;
+template <class FP> struct ProdTailItem {
+    const typename FP::X* w_in; const typename FP::X* tab_in;   // output of streaming round rt-1: n_in entries each (nt tables back to back)
+    const typename FP::X* chal;                                  // r_{rt-1} .. r_{nv-1}
+    typename FP::X* msg;                                         // slot of round rt (4 per round)
+    typename FP::X* evals;
+    const typename FP::X* capture;                               // linear layers whose capture round ran in the streaming part, else nullptr
+    int n_in, nt, rounds, linear, arity, cap_round;              // cap_round: index (0-based within the tail) of the round whose folded table holds the input evaluations, -1: none
+};
+template <class FP> __global__ void __launch_bounds__(256) k_prod_tail(const ProdTailItem<FP>* __restrict__ items) {
+    typedef typename FP::X X;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const ProdTailItem<FP> it = items[blockIdx.x];
+    const int nt = it.nt, ntab = nt + 1;
+    int len = it.n_in;
+    X* cur = reinterpret_cast<X*>(smem_raw);            // [ntab][n_in]: table 0 = weights
+    X* nxt = cur + (size_t)ntab * it.n_in;              // [ntab][n_in/2]
+    X* red = nxt + (size_t)ntab * (it.n_in / 2);        // [32][3]
+    for (int e = threadIdx.x; e < len; e += blockDim.x) cur[e] = it.w_in[e];
+    for (int e = threadIdx.x; e < nt * len; e += blockDim.x) cur[len + e] = it.tab_in[e];
+    __syncthreads();
+    for (int rd = 0; rd < it.rounds; rd++) {
+        const X r = it.chal[rd];
+        const typename FP::FoldAux aux = FP::fold_aux(r);
+        const int npairs = len / 4, half = len / 2;
+        X acc[3] = {FP::x_zero(), FP::x_zero(), FP::x_zero()};
+        for (int b = threadIdx.x; b < npairs; b += blockDim.x) {
+            X lo[3], hi[3];
+            for (int q = 0; q < ntab; q++) {
+                const X* s = cur + (size_t)q * len + 4 * b;
+                lo[q] = FP::fold(s[0], s[1], r, aux); hi[q] = FP::fold(s[2], s[3], r, aux);
+                nxt[(size_t)q * half + 2 * b] = lo[q]; nxt[(size_t)q * half + 2 * b + 1] = hi[q];
+            }
+            if (nt == 1) {
+                acc[0] = FP::x_add(acc[0], FP::fmul(lo[0], lo[1]));
+                acc[1] = FP::x_add(acc[1], FP::fmul(FP::slope(lo[0], hi[0]), FP::slope(lo[1], hi[1])));
+            } else {
+                acc[0] = FP::x_add(acc[0], FP::fmul(lo[0], FP::fmul(lo[1], lo[2])));
+                acc[1] = FP::x_add(acc[1], FP::fmul(FP::slope(lo[0], hi[0]), FP::fmul(FP::slope(lo[1], hi[1]), FP::slope(lo[2], hi[2]))));
+                acc[2] = FP::x_add(acc[2], FP::fmul(FP::at_m1(lo[0], hi[0]), FP::fmul(FP::at_m1(lo[1], hi[1]), FP::at_m1(lo[2], hi[2]))));
+            }
+        }
+        tail_block_sum<FP, 3>(acc, red, it.msg + 4 * (size_t)rd);  // ends with a barrier: nxt is complete
+        if (threadIdx.x == 0) it.msg[4 * (size_t)rd + 3] = FP::x_zero();
+        if (rd == it.cap_round)  // linear layer: the table folded over the low variables holds the evaluations of the inputs
+            for (int kk = threadIdx.x; kk < it.arity; kk += blockDim.x) it.evals[kk] = nxt[half + kk];
+        X* t = cur; cur = nxt; nxt = t;
+        len = half;
+        __syncthreads();
+    }
+    // len == 2: final fold with the last challenge
+    const X r = it.chal[it.rounds];
+    const typename FP::FoldAux aux = FP::fold_aux(r);
+    if (it.linear) {
+        if (it.capture) { for (int kk = threadIdx.x; kk < it.arity; kk += blockDim.x) it.evals[kk] = it.capture[kk]; }
+        else if (it.cap_round < 0 && threadIdx.x == 0) it.evals[0] = FP::fold(cur[len], cur[len + 1], r, aux);  // single input: its evaluation is the last fold
+    } else {
+        for (int q = threadIdx.x; q < nt; q += blockDim.x) it.evals[q] = FP::fold(cur[(size_t)(q + 1) * len], cur[(size_t)(q + 1) * len + 1], r, aux);
+    }
 }
 
 // ---- final folds and captures: out[i] = in[2 i] + r (in[2 i + 1] - in[2 i]) for tiny tables (one item per block)
