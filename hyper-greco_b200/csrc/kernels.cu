@@ -4,10 +4,15 @@
 
 namespace hg {
 
-__global__ void k_cnt_hist(const u16* __restrict__ addr, const u8* __restrict__ row_lookup, u64 used_mask, size_t n_rows, int rows_per_block,
-                           u16* __restrict__ blk_hist, int log2M) {
+// All kernels below handle every chunk slot in one launch (blockIdx.y = slot): the slots are independent and each of them
+// alone does not fill the GPU.
+__global__ void k_cnt_hist(CntSlots sl, const u8* __restrict__ row_lookup, size_t n_rows, int rows_per_block, u16* __restrict__ blk_hist_all,
+                           int nblk, int log2M) {
     extern __shared__ u32 sh[];  // M/2 words, two 16-bit counters per word
     const size_t M = (size_t)1 << log2M, words = M >> 1;
+    const u16* __restrict__ addr = sl.addr[blockIdx.y];
+    const u64 used_mask = sl.used[blockIdx.y];
+    u16* __restrict__ blk_hist = blk_hist_all + (size_t)blockIdx.y * nblk * M;
     for (size_t i = threadIdx.x; i < words; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const size_t row0 = (size_t)blockIdx.x * rows_per_block;
@@ -24,10 +29,13 @@ __global__ void k_cnt_hist(const u16* __restrict__ addr, const u8* __restrict__ 
     for (size_t i = threadIdx.x; i < words; i += blockDim.x) dst[i] = sh[i];
 }
 
-__global__ void k_cnt_scan(const u16* __restrict__ blk_hist, int nblk, int log2M, u32* __restrict__ blk_base, u32* __restrict__ final_cts) {
+__global__ void k_cnt_scan(const u16* __restrict__ blk_hist_all, int nblk, int log2M, u32* __restrict__ blk_base_all, u32* __restrict__ final_cts_all) {
     const size_t M = (size_t)1 << log2M;
     const size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= M) return;
+    const u16* __restrict__ blk_hist = blk_hist_all + (size_t)blockIdx.y * nblk * M;
+    u32* __restrict__ blk_base = blk_base_all + (size_t)blockIdx.y * nblk * M;
+    u32* __restrict__ final_cts = final_cts_all + (size_t)blockIdx.y * M;
     u32 run = 0;
     for (int b = 0; b < nblk; b++) {
         u32 c = blk_hist[(size_t)b * M + a];
@@ -40,10 +48,13 @@ __global__ void k_cnt_scan(const u16* __restrict__ blk_hist, int nblk, int log2M
 // Ordered rank inside a block of rows_per_block (<= 4096) rows, fully parallel: sort the keys (address << 12 | local row)
 // with a bitonic network in shared memory, find the start of every equal-address run with a max-scan, and the rank of a
 // row is its distance from the run start. Cross-block order comes from blk_base (k_cnt_scan). blockDim.x = 1024.
-__global__ void __launch_bounds__(1024) k_cnt_rank(const u16* __restrict__ addr, const u8* __restrict__ row_lookup, u64 used_mask, size_t n_rows,
-                                                   size_t R, int rows_per_block, const u32* __restrict__ blk_base, int log2M,
-                                                   u32* __restrict__ read_cts) {
+__global__ void __launch_bounds__(1024) k_cnt_rank(CntSlots sl, const u8* __restrict__ row_lookup, size_t n_rows, size_t R, int rows_per_block,
+                                                   const u32* __restrict__ blk_base_all, int nblk, int log2M, u32* __restrict__ read_cts_all) {
     constexpr int N = 4096;
+    const u16* __restrict__ addr = sl.addr[blockIdx.y];
+    const u64 used_mask = sl.used[blockIdx.y];
+    const u32* __restrict__ blk_base = blk_base_all + (size_t)blockIdx.y * nblk * ((size_t)1 << log2M);
+    u32* __restrict__ read_cts = read_cts_all + (size_t)blockIdx.y * R;
     __shared__ u32 key[N];
     __shared__ u32 runstart[N];
     __shared__ u32 warp_max[32];

@@ -153,11 +153,13 @@ __global__ void k_polynomialize(const typename FP::B* __restrict__ inputs, size_
 // K2 counters (lasso.rs:177-196): read_cts[j] = number of earlier rows that touch the same address of memory `mem`,
 // final_cts[a] = total. Order-dependent, so: per-block histogram -> per-address scan over blocks -> ordered rank.
 // rows_per_block <= 65535 so that 16-bit packed shared counters cannot overflow.
-__global__ void k_cnt_hist(const u16* __restrict__ addr, const u8* __restrict__ row_lookup, u64 used_mask, size_t n_rows,
-                           int rows_per_block, u16* __restrict__ blk_hist /*[nblk][M]*/, int log2M);
-__global__ void k_cnt_scan(const u16* __restrict__ blk_hist, int nblk, int log2M, u32* __restrict__ blk_base, u32* __restrict__ final_cts);
-__global__ void k_cnt_rank(const u16* __restrict__ addr, const u8* __restrict__ row_lookup, u64 used_mask, size_t n_rows, size_t R,
-                           int rows_per_block, const u32* __restrict__ blk_base, int log2M, u32* __restrict__ read_cts);
+struct CntSlots { const u16* addr[HG_MAX_C]; u64 used[HG_MAX_C]; };  // per chunk slot: its address column and the lookup types that use it
+__global__ void k_cnt_hist(CntSlots sl, const u8* __restrict__ row_lookup, size_t n_rows, int rows_per_block, u16* __restrict__ blk_hist /*[slot][nblk][M]*/,
+                           int nblk, int log2M);
+__global__ void k_cnt_scan(const u16* __restrict__ blk_hist, int nblk, int log2M, u32* __restrict__ blk_base /*[slot][nblk][M]*/,
+                           u32* __restrict__ final_cts /*[slot][M]*/);
+__global__ void k_cnt_rank(CntSlots sl, const u8* __restrict__ row_lookup, size_t n_rows, size_t R, int rows_per_block, const u32* __restrict__ blk_base,
+                           int nblk, int log2M, u32* __restrict__ read_cts /*[slot][R]*/);
 
 // ---------------------------------------------------------------------------------------------------------
 // eq(point, k) = prod_i (k_i ? r_i : 1 - r_i), k_0 = LSB (plonkish MultilinearPolynomial::eq_xy, lasso.rs:432), kept as
@@ -309,7 +311,19 @@ __global__ void k_tree_up(const typename FP::B* __restrict__ in, typename FP::B*
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= h) return;
     const typename FP::B* v = in + (size_t)blockIdx.y * 2 * h;
-    out[(size_t)blockIdx.y * h + k] = FP::b_mul(v[k], v[k + h]);
+    out[(size_t)blockIdx.y * h + k] = FP::fmul(v[k], v[k + h]);
+}
+// two levels per launch: in [nvec][4q] -> out1 [nvec][2q] -> out2 [nvec][q]; the intermediate layer is written but not re-read
+template <class FP>
+__global__ void k_tree_up2(const typename FP::B* __restrict__ in, typename FP::B* __restrict__ out1, typename FP::B* __restrict__ out2, size_t q) {
+    typedef typename FP::B B;
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= q) return;
+    const B* v = in + (size_t)blockIdx.y * 4 * q;
+    const B a = FP::fmul(v[k], v[k + 2 * q]), b = FP::fmul(v[k + q], v[k + 3 * q]);
+    B* o1 = out1 + (size_t)blockIdx.y * 2 * q;
+    o1[k] = a; o1[k + q] = b;
+    out2[(size_t)blockIdx.y * q + k] = FP::fmul(a, b);
 }
 // roots (prover.rs:197-203) and the nv = 0 layer's evaluations (prover.rs:232-236) from the top layer [nvec][2]
 template <class FP>

@@ -661,8 +661,9 @@ template <class FP> class LassoNodeDev {
         d_final_cts_.alloc((size_t)nslots_ * M_);
         rows_per_block_ = 4096;
         nblk_cnt_ = (int)((std::max<size_t>(n_rows_, 1) + rows_per_block_ - 1) / rows_per_block_);
-        d_blk_hist_.alloc((size_t)nblk_cnt_ * M_);
-        d_blk_base_.alloc((size_t)nblk_cnt_ * M_);
+        if (nslots_ > HG_MAX_C) throw std::runtime_error("LassoNode: too many chunks");
+        d_blk_hist_.alloc((size_t)nslots_ * nblk_cnt_ * M_);   // every chunk slot has its own scratch: the slots run in the same launches
+        d_blk_base_.alloc((size_t)nslots_ * nblk_cnt_ * M_);
         d_eq_.alloc(std::max(R_, M_));
         d_coeff_coll_.alloc(m_);
         d_wpow_.alloc(HG_MAX_C);
@@ -807,12 +808,13 @@ template <class FP> class LassoNodeDev {
             ctx_->stream = cs;  // HG_K times / counts on the launching stream
         }
         HG_CUDA(cudaMemsetAsync(d_read_cts_.p, 0, d_read_cts_.bytes(), cs));
-        for (int sl = 0; sl < nslots_; sl++) {
-            const u16* addr = d_dims_.p + (size_t)slot_addr_dim_[sl] * R;
-            HG_K(ctx_, KC_COUNTERS, rows * 3, k_cnt_hist<<<nblk_cnt_, 1024, M * 2, cs>>>(addr, d_row_lookup_.p, slot_used_[sl], rows, rows_per_block_, d_blk_hist_.p, log2M_));
-            HG_K(ctx_, KC_COUNTERS, M * 4, k_cnt_scan<<<(unsigned)((M + 255) / 256), 256, 0, cs>>>(d_blk_hist_.p, nblk_cnt_, log2M_, d_blk_base_.p, d_final_cts_.p + (size_t)sl * M));
-            HG_K(ctx_, KC_COUNTERS, rows * 7, k_cnt_rank<<<nblk_cnt_, 1024, 0, cs>>>(addr, d_row_lookup_.p, slot_used_[sl], rows, R, rows_per_block_, d_blk_base_.p, log2M_,
-                                                                                   d_read_cts_.p + (size_t)sl * R));
+        {
+            CntSlots sl;
+            for (int q = 0; q < HG_MAX_C; q++) { sl.addr[q] = nullptr; sl.used[q] = 0; }
+            for (int q = 0; q < nslots_; q++) { sl.addr[q] = d_dims_.p + (size_t)slot_addr_dim_[q] * R; sl.used[q] = slot_used_[q]; }
+            HG_K(ctx_, KC_COUNTERS, (size_t)nslots_ * rows * 3, k_cnt_hist<<<dim3(nblk_cnt_, nslots_), 1024, M * 2, cs>>>(sl, d_row_lookup_.p, rows, rows_per_block_, d_blk_hist_.p, nblk_cnt_, log2M_));
+            HG_K(ctx_, KC_COUNTERS, (size_t)nslots_ * M * 4, k_cnt_scan<<<dim3((unsigned)((M + 255) / 256), nslots_), 256, 0, cs>>>(d_blk_hist_.p, nblk_cnt_, log2M_, d_blk_base_.p, d_final_cts_.p));
+            HG_K(ctx_, KC_COUNTERS, (size_t)nslots_ * rows * 7, k_cnt_rank<<<dim3(nblk_cnt_, nslots_), 1024, 0, cs>>>(sl, d_row_lookup_.p, rows, R, rows_per_block_, d_blk_base_.p, nblk_cnt_, log2M_, d_read_cts_.p));
         }
         if (side) {
             ctx_->stream = s;
@@ -958,11 +960,18 @@ template <class FP> class LassoNodeDev {
         // layer k has vectors of length N >> k, k = 0..nvars-1 (prover.rs:191-195)
         std::vector<B*> layer(nvars);
         layer[0] = tree;
-        for (int k = 1; k < nvars; k++) {
-            layer[k] = layer[k - 1] + (size_t)nvec * (N >> (k - 1));
-            size_t h = N >> k;
-            if (k == 1 && level1_done) continue;
-            HG_K(ctx_, KC_TREE, (size_t)nvec * h * 3 * sizeof(B), k_tree_up<FP><<<dim3((unsigned)((h + HG_BLOCK - 1) / HG_BLOCK), nvec), HG_BLOCK, 0, s>>>(layer[k - 1], layer[k], h));
+        for (int k = 1; k < nvars; k++) layer[k] = layer[k - 1] + (size_t)nvec * (N >> (k - 1));
+        for (int k = (level1_done ? 2 : 1); k < nvars;) {
+            if (k + 1 < nvars) {  // two levels per launch: layer k is written and never re-read by the build
+                const size_t q = N >> (k + 1);
+                HG_K(ctx_, KC_TREE, (size_t)nvec * q * 7 * sizeof(B),
+                     k_tree_up2<FP><<<dim3((unsigned)((q + HG_BLOCK - 1) / HG_BLOCK), nvec), HG_BLOCK, 0, s>>>(layer[k - 1], layer[k], layer[k + 1], q));
+                k += 2;
+            } else {
+                const size_t h = N >> k;
+                HG_K(ctx_, KC_TREE, (size_t)nvec * h * 3 * sizeof(B), k_tree_up<FP><<<dim3((unsigned)((h + HG_BLOCK - 1) / HG_BLOCK), nvec), HG_BLOCK, 0, s>>>(layer[k - 1], layer[k], h));
+                k += 1;
+            }
         }
         const size_t roots_off = ch.alloc_msg(nvec), ev0_off = ch.alloc_msg(2 * nvec);
         HG_K(ctx_, KC_TREE, (size_t)nvec * 2 * sizeof(B), k_tree_top<FP><<<(nvec + HG_BLOCK - 1) / HG_BLOCK, HG_BLOCK, 0, s>>>(layer[nvars - 1], own_begin(nvec), own_end(nvec), ch.d_msg(roots_off), ch.d_msg(ev0_off)));
