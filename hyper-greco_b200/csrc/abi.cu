@@ -180,19 +180,33 @@ template <class FP> struct CircuitT : ICircuit {
     }
     // the circuit's own copy of the inputs (allocated once): host vectors are uploaded and, for BN254, brought to the device
     // representation, all asynchronously on the context's stream; evaluate follows in stream order
-    std::vector<std::unique_ptr<DevBuf<B>>> host_inputs;
+    DevBuf<B> host_arena;   // all inputs back to back, in input-node order
     void evaluate_host(DeviceCtx* dev, const void* const* in, const size_t* n_elems, size_t n) override {
         const std::vector<size_t> lens = c.input_lens();
         if (n != lens.size()) throw std::runtime_error("evaluate: wrong number of inputs");
-        if (host_inputs.size() != n) { host_inputs.clear(); for (size_t i = 0; i < n; i++) { host_inputs.emplace_back(new DevBuf<B>()); host_inputs.back()->alloc(lens[i]); } }
-        std::vector<const B*> v;
+        size_t total = 0;
         for (size_t i = 0; i < n; i++) {
             if (n_elems[i] != lens[i]) throw std::runtime_error("evaluate: input length does not match the input node");
-            if (host_inputs[i]->n != lens[i]) host_inputs[i]->alloc(lens[i]);
-            HG_CUDA(cudaMemcpyAsync(host_inputs[i]->p, in[i], lens[i] * sizeof(B), cudaMemcpyHostToDevice, dev->stream));
-            if (FP::FIELD_ID == 1) { k_field_encode<FP><<<(unsigned)((lens[i] + 255) / 256), 256, 0, dev->stream>>>(host_inputs[i]->p, lens[i], 0); HG_LAUNCH_CHECK(); }
-            v.push_back(host_inputs[i]->p);
+            total += lens[i];
         }
+        if (host_arena.n != total) host_arena.alloc(total);
+        std::vector<const B*> v;
+        // host vectors that are adjacent in memory (one pinned block, as a caller that wants speed lays them out) go in one copy
+        size_t off = 0, run_off = 0, run_len = 0;
+        const char* run_src = nullptr;
+        auto flush = [&]() {
+            if (run_len) HG_CUDA(cudaMemcpyAsync(host_arena.p + run_off, run_src, run_len * sizeof(B), cudaMemcpyHostToDevice, dev->stream));
+            run_len = 0;
+        };
+        for (size_t i = 0; i < n; i++) {
+            const char* src = (const char*)in[i];
+            if (run_len && src == run_src + run_len * sizeof(B)) run_len += lens[i];
+            else { flush(); run_src = src; run_off = off; run_len = lens[i]; }
+            v.push_back(host_arena.p + off);
+            off += lens[i];
+        }
+        flush();
+        if (FP::FIELD_ID == 1) { k_field_encode<FP><<<(unsigned)((total + 255) / 256), 256, 0, dev->stream>>>(host_arena.p, total, 0); HG_LAUNCH_CHECK(); }
         c.evaluate(v);
     }
     void node_value(int id, const void** p, size_t* len) override {

@@ -26,11 +26,12 @@ __global__ void k_vanilla_eval(VanillaFwd w, const typename FP::B* __restrict__ 
     if (t >= out_len) return;
     if (t >= ng * num_reps) { out[t] = FP::b_zero(); return; }
     const size_t r = t / ng, g = t % ng;
-    B v = consts[g];
-    for (u64 e = w.add_ptr[g]; e < w.add_ptr[g + 1]; e++) v = FP::b_add(v, FP::b_mul(add_coef[e], inputs[w.add_in[e]][r * sub + w.add_wire[e]]));
+    // unreduced sum of products, one reduction per gate
+    typename FP::BAcc acc = FP::bacc_zero();
+    for (u64 e = w.add_ptr[g]; e < w.add_ptr[g + 1]; e++) FP::bacc_mad(acc, add_coef[e], inputs[w.add_in[e]][r * sub + w.add_wire[e]]);
     for (u64 e = w.mul_ptr[g]; e < w.mul_ptr[g + 1]; e++)
-        v = FP::b_add(v, FP::b_mul(mul_coef[e], FP::b_mul(inputs[w.mul_in0[e]][r * sub + w.mul_w0[e]], inputs[w.mul_in1[e]][r * sub + w.mul_w1[e]])));
-    out[t] = v;
+        FP::bacc_mad(acc, mul_coef[e], FP::fmul(inputs[w.mul_in0[e]][r * sub + w.mul_w0[e]], inputs[w.mul_in1[e]][r * sub + w.mul_w1[e]]));
+    out[t] = FP::b_add(consts[g], FP::bacc_reduce(acc));
 }
 
 // ---- eq factor tables of every (node, claim) pair in one launch
