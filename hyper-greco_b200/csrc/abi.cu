@@ -191,21 +191,24 @@ template <class FP> struct CircuitT : ICircuit {
         }
         if (host_arena.n != total) host_arena.alloc(total);
         std::vector<const B*> v;
-        // host vectors that are adjacent in memory (one pinned block, as a caller that wants speed lays them out) go in one copy
-        size_t off = 0, run_off = 0, run_len = 0;
-        const char* run_src = nullptr;
-        auto flush = [&]() {
-            if (run_len) HG_CUDA(cudaMemcpyAsync(host_arena.p + run_off, run_src, run_len * sizeof(B), cudaMemcpyHostToDevice, dev->stream));
-            run_len = 0;
-        };
-        for (size_t i = 0; i < n; i++) {
-            const char* src = (const char*)in[i];
-            if (run_len && src == run_src + run_len * sizeof(B)) run_len += lens[i];
-            else { flush(); run_src = src; run_off = off; run_len = lens[i]; }
-            v.push_back(host_arena.p + off);
-            off += lens[i];
+        // host vectors that are adjacent in memory (one pinned block, as a caller that wants speed lays them out) go in one copy.
+        // Adjacent addresses can also belong to two separate page-locked allocations, for which one copy is invalid: then the
+        // run is copied vector by vector.
+        size_t off = 0;
+        std::vector<size_t> offs(n);
+        for (size_t i = 0; i < n; i++) { offs[i] = off; v.push_back(host_arena.p + off); off += lens[i]; }
+        for (size_t i = 0; i < n;) {
+            size_t k = i + 1, run_len = lens[i];
+            while (k < n && (const char*)in[k] == (const char*)in[i] + run_len * sizeof(B)) { run_len += lens[k]; k++; }
+            cudaError_t e = cudaMemcpyAsync(host_arena.p + offs[i], in[i], run_len * sizeof(B), cudaMemcpyHostToDevice, dev->stream);
+            if (e != cudaSuccess && k > i + 1) {
+                cudaGetLastError();
+                for (size_t q = i; q < k; q++) HG_CUDA(cudaMemcpyAsync(host_arena.p + offs[q], in[q], lens[q] * sizeof(B), cudaMemcpyHostToDevice, dev->stream));
+            } else if (e != cudaSuccess) {
+                HG_CUDA(e);
+            }
+            i = k;
         }
-        flush();
         if (FP::FIELD_ID == 1) { k_field_encode<FP><<<(unsigned)((total + 255) / 256), 256, 0, dev->stream>>>(host_arena.p, total, 0); HG_LAUNCH_CHECK(); }
         c.evaluate(v);
     }

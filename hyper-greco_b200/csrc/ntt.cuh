@@ -35,20 +35,22 @@ __device__ __forceinline__ unsigned bitrev(unsigned x, int bits) { return bits ?
 
 // DIF NTT of `tile` interleaved transforms of length n = 2^logn held as s[j*ts + c] (ts = padded tile stride);
 // root table: tw[k*tw_stride] = w_n^k
+// All sizes are powers of two: index arithmetic is shifts and masks (a runtime division costs more than the butterfly).
 template <class FP>
-__device__ __forceinline__ void smem_ntt_dif(typename FP::B* s, int logn, int tile, int ts, const typename FP::B* __restrict__ tw, size_t tw_stride) {
+__device__ __forceinline__ void smem_ntt_dif(typename FP::B* s, int logn, int log_tile, int ts, const typename FP::B* __restrict__ tw, size_t tw_stride) {
     typedef typename FP::B B;
-    const int n = 1 << logn;
-    for (int len = n >> 1; len >= 1; len >>= 1) {
-        const int nbf = (n >> 1) * tile;
-        const int step = (n >> 1) / len;  // exponent step of this stage
+    const int n = 1 << logn, tmask = (1 << log_tile) - 1;
+    const int nbf = (n >> 1) << log_tile;
+    for (int loglen = logn - 1; loglen >= 0; loglen--) {
+        const int len = 1 << loglen;
+        const int logstep = logn - 1 - loglen;  // exponent step of this stage = (n/2) / len
         for (int q = threadIdx.x; q < nbf; q += blockDim.x) {
-            const int c = q % tile, bf = q / tile;
-            const int j = bf % len, i = (bf / len) * 2 * len + j;
-            B u = s[i * ts + c], v = s[(i + len) * ts + c];
+            const int c = q & tmask, bf = q >> log_tile;
+            const int j = bf & (len - 1), i = ((bf >> loglen) << (loglen + 1)) | j;
+            const B u = s[i * ts + c], v = s[(i + len) * ts + c];
             s[i * ts + c] = FP::b_add(u, v);
-            B d = FP::b_sub(u, v);
-            s[(i + len) * ts + c] = j ? FP::b_mul(d, tw[(size_t)(j * step) * tw_stride]) : d;
+            const B d = FP::b_sub(u, v);
+            s[(i + len) * ts + c] = j ? FP::fmul(d, tw[((size_t)j << logstep) * tw_stride]) : d;
         }
         __syncthreads();
     }
@@ -64,22 +66,23 @@ __global__ void __launch_bounds__(HG_NTT_THREADS) k_ntt_cols(const typename FP::
     const int n1 = 1 << log_n1, n2 = 1 << log_n2;
     const size_t N = (size_t)n1 * n2;
     const int j2_0 = blockIdx.x * tile, ts = tile | 1;
+    const int log_tile = 31 - __clz(tile), tmask = tile - 1;
     const B* xb = x + (size_t)blockIdx.y * N;
     B* yb = y + (size_t)blockIdx.y * N;
     for (int q = threadIdx.x; q < n1 * tile; q += blockDim.x) {
-        const int c = q % tile, j1 = q / tile;
-        s[j1 * ts + c] = xb[(size_t)j1 * n2 + j2_0 + c];
+        const int c = q & tmask, j1 = q >> log_tile;
+        s[j1 * ts + c] = xb[((size_t)j1 << log_n2) + j2_0 + c];
     }
     __syncthreads();
-    smem_ntt_dif<FP>(s, log_n1, tile, ts, tw, (size_t)n2);  // w_{N1} = w_N^{N2}
+    smem_ntt_dif<FP>(s, log_n1, log_tile, ts, tw, (size_t)n2);  // w_{N1} = w_N^{N2}
     for (int q = threadIdx.x; q < n1 * tile; q += blockDim.x) {
-        const int c = q % tile, pos = q / tile;
+        const int c = q & tmask, pos = q >> log_tile;
         const int k1 = (int)bitrev((unsigned)pos, log_n1);
         const int j2 = j2_0 + c;
         B v = s[pos * ts + c];
         const size_t e = ((size_t)j2 * k1) & (N - 1);
-        if (e) v = FP::b_mul(v, tw[e]);
-        yb[(size_t)k1 * n2 + j2] = v;
+        if (e) v = FP::fmul(v, tw[e]);
+        yb[((size_t)k1 << log_n2) + j2] = v;
     }
 }
 
@@ -94,20 +97,21 @@ __global__ void __launch_bounds__(HG_NTT_THREADS) k_ntt_rows(const typename FP::
     const int n1 = 1 << log_n1, n2 = 1 << log_n2;
     const size_t N = (size_t)n1 * n2;
     const int k1_0 = blockIdx.x * tile, ts = tile | 1;
+    const int log_tile = 31 - __clz(tile), tmask = tile - 1;
     const B* yb = y + (size_t)blockIdx.y * N;
     B* ob = out + (size_t)blockIdx.y * N;
     for (int q = threadIdx.x; q < n2 * tile; q += blockDim.x) {
-        const int j2 = q % n2, r = q / n2;  // contiguous rows
-        s[j2 * ts + r] = yb[(size_t)(k1_0 + r) * n2 + j2];
+        const int j2 = q & (n2 - 1), r = q >> log_n2;  // contiguous rows
+        s[j2 * ts + r] = yb[((size_t)(k1_0 + r) << log_n2) + j2];
     }
     __syncthreads();
-    smem_ntt_dif<FP>(s, log_n2, tile, ts, tw, (size_t)n1);  // w_{N2} = w_N^{N1}
+    smem_ntt_dif<FP>(s, log_n2, log_tile, ts, tw, (size_t)n1);  // w_{N2} = w_N^{N1}
     for (int q = threadIdx.x; q < n2 * tile; q += blockDim.x) {
-        const int r = q % tile, pos = q / tile;
+        const int r = q & tmask, pos = q >> log_tile;
         const int k2 = (int)bitrev((unsigned)pos, log_n2);
         B v = s[pos * ts + r];
-        if (do_scale) v = FP::b_mul(v, scale);
-        ob[(size_t)(k1_0 + r) + (size_t)n1 * k2] = v;
+        if (do_scale) v = FP::fmul(v, scale);
+        ob[(size_t)(k1_0 + r) + ((size_t)k2 << log_n1)] = v;
     }
 }
 

@@ -31,4 +31,4 @@ ctx.profile(True)
 for _ in range(3): step()
 prof = ctx.profile_read(); ctx.profile(False)
 tag = " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("HG_"))
-print(f"[{tag}] {dt*1e3:.3f} ms/proof sha={hashlib.sha256(pr).hexdigest()[:10]} " + " ".join(f"{k}={v[1]/3:.3f}" for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:6]))
+print(f"[{tag}] {dt*1e3:.3f} ms/proof sha={hashlib.sha256(pr).hexdigest()[:10]} " + " ".join(f"{k}={v[1]/3:.3f}" for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]))
