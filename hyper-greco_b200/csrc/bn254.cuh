@@ -49,22 +49,101 @@ HG_HD void fr_sub_mod_inplace(u64* a) {
     u64 bw = 0;
     a[0] = subb64(a[0], FR_MOD0, bw); a[1] = subb64(a[1], FR_MOD1, bw); a[2] = subb64(a[2], FR_MOD2, bw); a[3] = subb64(a[3], FR_MOD3, bw);
 }
+#if defined(__CUDACC__)
+// ---- device arithmetic with PTX carry chains (the portable C below compiles to compare/select sequences: 724 vs 481
+// instructions per multiplication). Same results: Montgomery CIOS, fully reduced outputs.
+__device__ __forceinline__ fr fr_cond_sub_dev(u64 t0, u64 t1, u64 t2, u64 t3, u64 t4) {  // (t4:t3:t2:t1:t0) < 2r  ->  mod r
+    u64 s0, s1, s2, s3, bw;
+    asm("sub.cc.u64 %0, %5, %9; subc.cc.u64 %1, %6, %10; subc.cc.u64 %2, %7, %11; subc.cc.u64 %3, %8, %12; subc.u64 %4, %13, 0;"
+        : "=l"(s0), "=l"(s1), "=l"(s2), "=l"(s3), "=l"(bw)
+        : "l"(t0), "l"(t1), "l"(t2), "l"(t3), "l"(FR_MOD0), "l"(FR_MOD1), "l"(FR_MOD2), "l"(FR_MOD3), "l"(t4));
+    const bool keep = (bw >> 63) != 0;  // borrow out of the 5-limb subtraction: t < r
+    fr r;
+    r.l[0] = keep ? t0 : s0; r.l[1] = keep ? t1 : s1; r.l[2] = keep ? t2 : s2; r.l[3] = keep ? t3 : s3;
+    return r;
+}
+__device__ __forceinline__ fr fr_add_dev(const fr& a, const fr& b) {
+    u64 t0, t1, t2, t3;
+    asm("add.cc.u64 %0, %4, %8; addc.cc.u64 %1, %5, %9; addc.cc.u64 %2, %6, %10; addc.u64 %3, %7, %11;"
+        : "=l"(t0), "=l"(t1), "=l"(t2), "=l"(t3)
+        : "l"(a.l[0]), "l"(a.l[1]), "l"(a.l[2]), "l"(a.l[3]), "l"(b.l[0]), "l"(b.l[1]), "l"(b.l[2]), "l"(b.l[3]));
+    return fr_cond_sub_dev(t0, t1, t2, t3, 0);  // a + b < 2^255: no carry out of limb 3
+}
+__device__ __forceinline__ fr fr_sub_dev(const fr& a, const fr& b) {
+    u64 t0, t1, t2, t3, bw;
+    asm("sub.cc.u64 %0, %5, %9; subc.cc.u64 %1, %6, %10; subc.cc.u64 %2, %7, %11; subc.cc.u64 %3, %8, %12; subc.u64 %4, 0, 0;"
+        : "=l"(t0), "=l"(t1), "=l"(t2), "=l"(t3), "=l"(bw)
+        : "l"(a.l[0]), "l"(a.l[1]), "l"(a.l[2]), "l"(a.l[3]), "l"(b.l[0]), "l"(b.l[1]), "l"(b.l[2]), "l"(b.l[3]));
+    // bw = 0 or all ones: add r masked
+    asm("add.cc.u64 %0, %0, %4; addc.cc.u64 %1, %1, %5; addc.cc.u64 %2, %2, %6; addc.u64 %3, %3, %7;"
+        : "+l"(t0), "+l"(t1), "+l"(t2), "+l"(t3) : "l"(FR_MOD0 & bw), "l"(FR_MOD1 & bw), "l"(FR_MOD2 & bw), "l"(FR_MOD3 & bw));
+    fr r;
+    r.l[0] = t0; r.l[1] = t1; r.l[2] = t2; r.l[3] = t3;
+    return r;
+}
+__device__ __forceinline__ fr fr_mul_dev(const fr& a, const fr& b) {
+    u64 t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const u64 bi = b.l[i];
+        asm("{\n\t.reg .u64 m;\n\t"
+            "mad.lo.cc.u64  %0, %6, %10, %0;\n\t"
+            "madc.lo.cc.u64 %1, %7, %10, %1;\n\t"
+            "madc.lo.cc.u64 %2, %8, %10, %2;\n\t"
+            "madc.lo.cc.u64 %3, %9, %10, %3;\n\t"
+            "addc.cc.u64    %4, %4, 0;\n\t"
+            "addc.u64       %5, 0, 0;\n\t"
+            "mad.hi.cc.u64  %1, %6, %10, %1;\n\t"
+            "madc.hi.cc.u64 %2, %7, %10, %2;\n\t"
+            "madc.hi.cc.u64 %3, %8, %10, %3;\n\t"
+            "madc.hi.cc.u64 %4, %9, %10, %4;\n\t"
+            "addc.u64       %5, %5, 0;\n\t"
+            "mul.lo.u64     m, %0, %11;\n\t"
+            "mad.lo.cc.u64  %0, m, %12, %0;\n\t"
+            "madc.lo.cc.u64 %1, m, %13, %1;\n\t"
+            "madc.lo.cc.u64 %2, m, %14, %2;\n\t"
+            "madc.lo.cc.u64 %3, m, %15, %3;\n\t"
+            "addc.cc.u64    %4, %4, 0;\n\t"
+            "addc.u64       %5, %5, 0;\n\t"
+            "mad.hi.cc.u64  %1, m, %12, %1;\n\t"
+            "madc.hi.cc.u64 %2, m, %13, %2;\n\t"
+            "madc.hi.cc.u64 %3, m, %14, %3;\n\t"
+            "madc.hi.cc.u64 %4, m, %15, %4;\n\t"
+            "addc.u64       %5, %5, 0;\n\t}"
+            : "+l"(t0), "+l"(t1), "+l"(t2), "+l"(t3), "+l"(t4), "+l"(t5)
+            : "l"(a.l[0]), "l"(a.l[1]), "l"(a.l[2]), "l"(a.l[3]), "l"(bi), "l"(FR_INV), "l"(FR_MOD0), "l"(FR_MOD1), "l"(FR_MOD2), "l"(FR_MOD3));
+        t0 = t1; t1 = t2; t2 = t3; t3 = t4; t4 = t5; t5 = 0;  // the low limb is zero after the reduction step
+    }
+    return fr_cond_sub_dev(t0, t1, t2, t3, t4);
+}
+#endif
 HG_HD fr fr_add(const fr& a, const fr& b) {
+#if defined(__CUDA_ARCH__)
+    return fr_add_dev(a, b);
+#else
     fr r;
     u64 c = 0;
     for (int i = 0; i < 4; i++) r.l[i] = addc64(a.l[i], b.l[i], c);
     if (c || fr_geq_mod(r.l)) fr_sub_mod_inplace(r.l);  // r < 2^254 so c is always 0; kept for clarity
     return r;
+#endif
 }
 HG_HD fr fr_sub(const fr& a, const fr& b) {
+#if defined(__CUDA_ARCH__)
+    return fr_sub_dev(a, b);
+#else
     fr r;
     u64 bw = 0;
     for (int i = 0; i < 4; i++) r.l[i] = subb64(a.l[i], b.l[i], bw);
     if (bw) { u64 c = 0; r.l[0] = addc64(r.l[0], FR_MOD0, c); r.l[1] = addc64(r.l[1], FR_MOD1, c); r.l[2] = addc64(r.l[2], FR_MOD2, c); r.l[3] = addc64(r.l[3], FR_MOD3, c); }
     return r;
+#endif
 }
 // Montgomery product a * b * R^{-1} mod r (CIOS, 4 limbs)
 HG_HD fr fr_mul(const fr& a, const fr& b) {
+#if defined(__CUDA_ARCH__)
+    return fr_mul_dev(a, b);
+#else
     u64 t[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -110,6 +189,7 @@ HG_HD fr fr_mul(const fr& a, const fr& b) {
     fr r = fr_make(t[0], t[1], t[2], t[3]);
     if (t[4] || fr_geq_mod(r.l)) fr_sub_mod_inplace(r.l);
     return r;
+#endif
 }
 HG_HD fr fr_from_canonical(const u64* x) { return fr_mul(fr_make(x[0], x[1], x[2], x[3]), fr_make(FR_R2_0, FR_R2_1, FR_R2_2, FR_R2_3)); }
 HG_HD void fr_to_canonical(const fr& a, u64* out) {
