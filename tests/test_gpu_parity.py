@@ -523,6 +523,38 @@ def test_bn254_full_gkr_prove_matches_oracle(api, ctx_bn, oracle, golden_dir, mo
     assert len(claims) == len(flat)
 
 
+def test_device_proofs_equal_committed_golden_bytes(api, ctx, ctx_bn, golden_dir):
+    """Device output against the COMMITTED proof bytes (tests/golden/golden_proofs.json), without the oracle in the loop:
+    Lasso node and whole BfvEncrypt::prove, Goldilocks and BN254, on the reference's n=1024 witnesses."""
+    import hashlib
+    import json
+    import os
+    from hyper_greco_b200 import params, witness
+    name = "1024_1x27_65537"
+    P = params.PARAMS[name]
+    meta = json.load(open(os.path.join(golden_dir, "golden_proofs.json")))["files"]
+
+    def golden(fname):
+        data = open(os.path.join(golden_dir, fname), "rb").read()
+        assert hashlib.sha256(data).hexdigest() == meta[fname]["sha256"]
+        return data
+
+    bounds, segs, nv = witness.lasso_lookup_bounds(P), witness.lasso_lookup_segments(P), witness.lasso_num_vars(P)
+    for field, c, tag, lasso_file, io_file in ((api.GOLDILOCKS, ctx, "goldilocks", f"lasso_inputs_{name}.npz", f"circuit_io_{name}.npz"),
+                                               (api.BN254, ctx_bn, "bn254", f"lasso_inputs_bn254_{name}.npz", f"circuit_io_bn254_{name}.npz")):
+        inp = np.load(os.path.join(golden_dir, lasso_file))["inputs"]
+        node = api.LassoNode(c, api.LassoPreprocessing.preprocess(bounds), nv, segs)
+        tr = api.Keccak256Transcript(field)
+        node.prove_claim_reduction(inp, tr)
+        assert tr.into_proof() == golden(f"proof_{tag}_lasso_node_{name}.bin"), tag
+        node.free()
+        io = np.load(os.path.join(golden_dir, io_file))
+        flat = [io["s"], io["e"], io["k1"]] + list(io["ais"]) + list(io["r1is"]) + [io["r2is"]]
+        prover = api.BfvSkEncryptProver(c, P)
+        proof, _ = prover.prove_host([np.ascontiguousarray(v).reshape(-1) for v in flat], np.ascontiguousarray(io["ct0is"]).reshape(-1))
+        assert proof == golden(f"proof_{tag}_bfv_encrypt_{name}.bin"), tag
+
+
 def test_bn254_ntt_matches_oracle(api, ctx_bn, oracle):
     rng = np.random.default_rng(2)
     for log_n in (3, 10, 13):

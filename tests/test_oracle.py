@@ -274,3 +274,32 @@ def test_bn254_reference_fixture_prove_verify_roundtrip(oracle, golden_dir, name
     bad[-1] ^= 1
     with pytest.raises(oracle.OracleError):
         oracle.lasso_verify(1, opp, nv, bytes(bad))
+
+
+def _golden_proof(golden_dir, fname):
+    import hashlib
+    meta = json.load(open(os.path.join(golden_dir, "golden_proofs.json")))
+    data = open(os.path.join(golden_dir, fname), "rb").read()
+    assert hashlib.sha256(data).hexdigest() == meta["files"][fname]["sha256"] and len(data) == meta["files"][fname]["bytes"]
+    return data, meta["files"][fname]
+
+
+def test_oracle_reproduces_committed_golden_proofs(oracle, golden_dir):
+    """The committed proof bytes (tests/golden/make_golden_proofs.py) are what the oracle produces today: any change of the
+    restatement shows up here, and the same files are what the GPU tests and an off-box Rust run compare against."""
+    name = "1024_1x27_65537"
+    P, inp, bounds, segs, nv, opp, rows = load_case(name, oracle, golden_dir)
+    want, info = _golden_proof(golden_dir, f"proof_goldilocks_lasso_node_{name}.bin")
+    proof, r, s, nsq = oracle.lasso_prove(0, opp, nv, rows, inp)
+    assert proof == want and nsq == info["base_squeezes"]
+    oracle.lasso_verify(0, opp, nv, want)
+    inp_bn = np.load(os.path.join(golden_dir, f"lasso_inputs_bn254_{name}.npz"))["inputs"]
+    want, info = _golden_proof(golden_dir, f"proof_bn254_lasso_node_{name}.bin")
+    proof, r, s, nsq = oracle.lasso_prove(1, opp, nv, rows, inp_bn)
+    assert proof == want and nsq == info["base_squeezes"]
+    io = np.load(os.path.join(golden_dir, f"circuit_io_{name}.npz"))
+    ins = dict(s=[int(v) for v in io["s"]], e=[int(v) for v in io["e"]], k1=[int(v) for v in io["k1"]], ais=[[int(v) for v in a] for a in io["ais"]],
+               r1is=[[int(v) for v in a] for a in io["r1is"]], r2is=[int(v) for v in io["r2is"]])
+    want, _ = _golden_proof(golden_dir, f"proof_goldilocks_bfv_encrypt_{name}.bin")
+    assert oracle.bfv_prove(0, P, ins, [int(v) for v in io["ct0is"]]) == want
+    oracle.bfv_verify(0, P, ins, [int(v) for v in io["ct0is"]], want)
