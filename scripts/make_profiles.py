@@ -2,7 +2,7 @@
 
     gpurun_out/r1_launches.csv : ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none
                                  -c 3000 --csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline
-    gpurun_out/r1_gp.ncu-rep   : ncu --set full --clock-control none --import-source on -k regex:"k_gp_(r0a|r0|fold)_multi" -s 34 -c 4
+    gpurun_out/r1_gp.ncu-rep   : ncu --set full --clock-control none --import-source on -k regex:"k_gp_(r0a|r0|fold)_multi" -s 32 -c 4
                                  python scripts/dev_gp_grid.py
 Writes profiles/r1_launch_list.md, profiles/traffic.json, profiles/r1_ncu_gp_kernels.txt."""
 import collections
@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CLASSES = [
     ("sumcheck_grand_product", r"k_gp_r0a_multi|k_gp_r0_multi|k_gp_fold_multi|k_gp_tail"),
     ("misc", r"k_gp_coeffs_multi"),
-    ("gkr_layer_sumcheck", r"k_prod_round_multi|k_copy_items|k_fold_items"),
+    ("gkr_layer_sumcheck", r"k_prod_round_multi|k_prod_tail|k_copy_items|k_fold_items"),
     ("gkr_layer_weights", r"k_eq_split_multi|k_eq_accumulate|k_wiring_gather|k_ext_split|k_ext_merge|k_dot_wconst"),
     ("counters", r"k_cnt_"),
     ("hash_build", r"k_hash_"),
@@ -100,7 +100,7 @@ def main():
         keep = re.compile(r"k_gp_|gpu__time_duration.sum|dram__bytes_(read|write).sum |gpu__dram_throughput.avg.pct|sm__throughput.avg.pct|launch__registers_per_thread |"
                           r"launch__grid_size|launch__occupancy_limit_registers|sm__warps_active.avg.pct|smsp__inst_executed.sum |sm__pipe_(alu|fma)_cycles_active.avg.pct_of_peak_sustained_active|"
                           r"smsp__issue_active.avg.pct|smsp__average_warps_issue_stalled_(barrier|dispatch_stall|long_scoreboard|math_pipe_throttle|not_selected|wait|short_scoreboard|no_instruction)_per_issue_active")
-        txt = ["ncu --set full --clock-control none --import-source on -k regex:\"k_gp_(r0a|r0|fold)_multi\" -s 34 -c 4 python scripts/dev_gp_grid.py",
+        txt = ["ncu --set full --clock-control none --import-source on -k regex:\"k_gp_(r0a|r0|fold)_multi\" -s 32 -c 4 python scripts/dev_gp_grid.py",
                "(third proof of the run; rounds 0a, 0b, 1, 2 of the batched grand-product sumchecks: 35 layers of both memory-checking trees per launch)", ""]
         for l in raw.splitlines():
             if keep.search(l) and "not_issued" not in l:
