@@ -516,7 +516,7 @@ template <class FP> class GkrCircuitDev {
                 it.stride = ((size_t)1 << it.lo_bits) + (n.out_len >> it.lo_bits);
                 it.n_claims = (int)j.points.size();
                 it.w = n.W.p; it.n = n.out_len; it.blk_start = blk;
-                blk += (int)((n.out_len + HG_BLOCK - 1) / HG_BLOCK);
+                blk += (int)((n.out_len + HG_BLOCK * HG_EQACC_PER_THREAD - 1) / (HG_BLOCK * HG_EQACC_PER_THREAD));
                 bytes += n.out_len * sizeof(X);
                 items.push_back(it);
             }
@@ -526,25 +526,40 @@ template <class FP> class GkrCircuitDev {
         // A per node
         std::vector<X*> fft_fwd, fft_inv;  // W tables whose transform is needed, grouped by size via a map below
         std::map<std::pair<int, int>, std::vector<int>> fft_groups;  // (log2 size, inverse) -> node ids
+        std::vector<WiringItem<FP>> wires;
+        std::vector<ConcatItem<FP>> cats;
+        int wire_blk = 0, cat_blk = 0;
+        size_t wire_bytes = 0, cat_bytes = 0;
+        auto cat = [&](const B* src, B* dst, size_t cnt) {
+            ConcatItem<FP> c; c.src = src; c.dst = dst; c.n = cnt; c.blk_start = cat_blk;
+            cat_blk += (int)((cnt + HG_BLOCK * HG_CONCAT_PER_THREAD - 1) / (HG_BLOCK * HG_CONCAT_PER_THREAD));
+            cat_bytes += cnt * sizeof(B) * 2;
+            cats.push_back(c);
+        };
         for (const Job& j : jobs) {
             Node& n = *nodes_[j.node];
             if (n.kind == GKR_FFT) { fft_groups[{n.log2_size, n.fft_inverse ? 1 : 0}].push_back(j.node); continue; }
             if (n.is_elemmul) {
                 // tables = [in0 | in1]
                 const size_t S = n.out_len;
-                for (int k = 0; k < 2; k++) HG_CUDA(cudaMemcpyAsync(n.Xcat.p + k * S, nodes_[n.preds.at(k)]->value_ptr, S * sizeof(B), cudaMemcpyDeviceToDevice, s));
+                for (int k = 0; k < 2; k++) cat(nodes_[n.preds.at(k)]->value_ptr, n.Xcat.p + k * S, S);
                 continue;
             }
             const size_t S = n.a_pad * n.n_in;
-            HG_K(ctx_, KC_GKR_PREP, S * sizeof(X) * 2, k_wiring_gather<FP><<<(unsigned)((S + HG_BLOCK - 1) / HG_BLOCK), HG_BLOCK, 0, s>>>(n.rev_ptr.p, n.rev_out.p, n.rev_coef.p, n.W.p, S, n.A.p));
-            if (n.a_pad != (size_t)n.arity) HG_CUDA(cudaMemsetAsync(n.Xcat.p + (size_t)n.arity * n.n_in, 0, (n.a_pad - n.arity) * n.n_in * sizeof(B), s));
-            for (int k = 0; k < n.arity; k++) HG_CUDA(cudaMemcpyAsync(n.Xcat.p + (size_t)k * n.n_in, nodes_[n.preds.at(k)]->value_ptr, n.n_in * sizeof(B), cudaMemcpyDeviceToDevice, s));
+            WiringItem<FP> wi; wi.rev_ptr = n.rev_ptr.p; wi.rev_out = n.rev_out.p; wi.rev_coef = n.rev_coef.p; wi.w = n.W.p; wi.A = n.A.p; wi.n = S; wi.blk_start = wire_blk;
+            wire_blk += (int)((S + HG_BLOCK - 1) / HG_BLOCK);
+            wire_bytes += S * sizeof(X) * 2;
+            wires.push_back(wi);
+            if (n.a_pad != (size_t)n.arity) cat(nullptr, n.Xcat.p + (size_t)n.arity * n.n_in, (n.a_pad - n.arity) * n.n_in);
+            for (int k = 0; k < n.arity; k++) cat(nodes_[n.preds.at(k)]->value_ptr, n.Xcat.p + (size_t)k * n.n_in, n.n_in);
             if (n.has_consts) {
                 int blocks = (int)std::min<size_t>((n.out_len + HG_BLOCK - 1) / HG_BLOCK, (size_t)ctx_->sm_count * 2);
                 HG_K(ctx_, KC_GKR_PREP, n.out_len * (sizeof(X) + sizeof(B)),
                      k_dot_wconst<FP><<<blocks, HG_BLOCK, 0, s>>>(n.W.p, n.consts_full.p, n.out_len, d_partials_.p, d_counters_.p, ch.d_msg(j.const_off)));
             }
         }
+        if (!wires.empty()) HG_K(ctx_, KC_GKR_PREP, wire_bytes, k_wiring_gather<FP><<<wire_blk, HG_BLOCK, 0, s>>>(stage(wires), (int)wires.size()));
+        if (!cats.empty()) HG_K(ctx_, KC_GKR_PREP, cat_bytes, k_concat_items<FP><<<cat_blk, HG_BLOCK, 0, s>>>(stage(cats), (int)cats.size()));
         // FFT-matrix weights: A = transform(W) plane by plane, batched over all FFT nodes of the same size and direction
         for (auto& kv : fft_groups) {
             const int lg = kv.first.first;
@@ -571,6 +586,8 @@ template <class FP> class GkrCircuitDev {
         std::vector<ProdItem<FP>> items;
         int blk = 0;
         size_t part_off = 0, bytes = 0;
+        size_t round_pairs = 0;  // small rounds get one pair per thread (more CTAs), large ones up to 16 (fewer block-level reductions)
+        for (const Job& j : jobs) if (r < j.nv && r < tail_start(j)) round_pairs += r == 0 ? j.S / 2 : (j.S >> (r - 1)) / 4;
         for (const Job& j : jobs) {
             if (r >= j.nv || r >= tail_start(j)) continue;
             Node& n = *nodes_[j.node];
@@ -589,7 +606,8 @@ template <class FP> class GkrCircuitDev {
             it.msg = ch.d_msg(j.msg_off + 4 * (size_t)r);
             const size_t npairs = r == 0 ? it.n_in / 2 : it.n_in / 4;
             // several pairs per thread: the block-level reduction that ends every block costs about as much as eight pairs (measured optimum 8-16)
-            static const size_t ppt = getenv("HG_PROD_PPT") ? (size_t)atoi(getenv("HG_PROD_PPT")) : 16;
+            static const size_t ppt_max = getenv("HG_PROD_PPT") ? (size_t)atoi(getenv("HG_PROD_PPT")) : 16;
+            const size_t ppt = std::max<size_t>(1, std::min<size_t>(ppt_max, round_pairs / ((size_t)HG_BLOCK * ctx_->sm_count * 4)));
             size_t b = std::max<size_t>(1, std::min<size_t>((npairs + HG_BLOCK * ppt - 1) / (HG_BLOCK * ppt), (size_t)ctx_->sm_count * 16));
             it.nblk = (int)b; it.bx = (int)b; it.blk_start = blk;
             blk += it.nblk;

@@ -67,33 +67,52 @@ template <class FP> struct EqAccItem {
     u64 n, stride;
     int lo_bits, n_claims, blk_start;
 };
+constexpr int HG_EQACC_PER_THREAD = 8;  // one element per thread made the launch block-dispatch bound (47 616 CTAs, 230 us)
 template <class FP> __global__ void k_eq_accumulate(const EqAccItem<FP>* __restrict__ items, int nitems) {
     typedef typename FP::X X;
     const EqAccItem<FP> it = items[find_item(items, nitems)];
-    const size_t i = (size_t)(blockIdx.x - it.blk_start) * blockDim.x + threadIdx.x;
-    if (i >= it.n) return;
-    const size_t nlo = (size_t)1 << it.lo_bits, lo = i & (nlo - 1), hi = i >> it.lo_bits;
-    typename FP::XAcc a = FP::xacc_zero_();
-    for (int t = 0; t < it.n_claims; t++) {
-        const X* e = it.eq0 + (size_t)t * it.stride;
-        FP::xacc_mad_(a, e[lo], e[nlo + hi]);
+    const size_t nlo = (size_t)1 << it.lo_bits;
+    const size_t base = (size_t)(blockIdx.x - it.blk_start) * blockDim.x * HG_EQACC_PER_THREAD + threadIdx.x;
+#pragma unroll 2
+    for (int k = 0; k < HG_EQACC_PER_THREAD; k++) {
+        const size_t i = base + (size_t)k * blockDim.x;
+        if (i >= it.n) return;
+        const size_t lo = i & (nlo - 1), hi = i >> it.lo_bits;
+        typename FP::XAcc a = FP::xacc_zero_();
+        for (int t = 0; t < it.n_claims; t++) {
+            const X* e = it.eq0 + (size_t)t * it.stride;
+            FP::xacc_mad_(a, e[lo], e[nlo + hi]);
+        }
+        it.w[i] = FP::xacc_reduce_(a);
     }
-    it.w[i] = FP::xacc_reduce_(a);
 }
 
 // ---- A[x] = sum_{(o, c) in rev[x]} c * W[o]  (weights pushed through the wiring, reverse CSR), const = sum_g W[g] c_g
-template <class FP>
-__global__ void k_wiring_gather(const u64* __restrict__ rev_ptr, const u32* __restrict__ rev_out, const typename FP::B* __restrict__ rev_coef,
-                                const typename FP::X* __restrict__ w, size_t n, typename FP::X* __restrict__ A) {
-    typedef typename FP::X X;
-    const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= n) return;
+template <class FP> struct WiringItem {
+    const u64* rev_ptr; const u32* rev_out; const typename FP::B* rev_coef; const typename FP::X* w; typename FP::X* A;
+    u64 n; int blk_start;
+};
+template <class FP> __global__ void k_wiring_gather(const WiringItem<FP>* __restrict__ items, int nitems) {
+    const WiringItem<FP> it = items[find_item(items, nitems)];
+    const size_t x = (size_t)(blockIdx.x - it.blk_start) * blockDim.x + threadIdx.x;
+    if (x >= it.n) return;
     typename FP::XAcc acc = FP::xacc_zero_();
-    for (u64 e = rev_ptr[x]; e < rev_ptr[x + 1]; e++) FP::xacc_mad_b(acc, w[rev_out[e]], rev_coef[e]);
-    A[x] = FP::xacc_reduce_(acc);
+    for (u64 e = it.rev_ptr[x]; e < it.rev_ptr[x + 1]; e++) FP::xacc_mad_b(acc, it.w[it.rev_out[e]], it.rev_coef[e]);
+    it.A[x] = FP::xacc_reduce_(acc);
+}
+// concatenated input tables of the layer sumchecks: dst[0..n) = src[0..n) (src = nullptr: zeros), every node's pieces in one launch
+template <class FP> struct ConcatItem { const typename FP::B* src; typename FP::B* dst; u64 n; int blk_start; };
+constexpr int HG_CONCAT_PER_THREAD = 8;
+template <class FP> __global__ void k_concat_items(const ConcatItem<FP>* __restrict__ items, int nitems) {
+    const ConcatItem<FP> it = items[find_item(items, nitems)];
+    const size_t base = (size_t)(blockIdx.x - it.blk_start) * blockDim.x * HG_CONCAT_PER_THREAD + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < HG_CONCAT_PER_THREAD; k++) {
+        const size_t i = base + (size_t)k * blockDim.x;
+        if (i < it.n) it.dst[i] = it.src ? it.src[i] : FP::b_zero();
+    }
 }
 
-// ---- split / merge of extension tables into base planes (the FFT-matrix weights are the transform of W, plane by plane)
 // tabs[q] = extension table of node q (n elements); planes = [PLANES*q + p][n]
 template <class FP> __global__ void k_ext_split(typename FP::X* const* __restrict__ tabs, size_t n, typename FP::B* __restrict__ planes) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
