@@ -215,10 +215,8 @@ template <class FP> struct ProdTailItem {
     const typename FP::X* capture;                               // linear layers whose capture round ran in the streaming part, else nullptr
     int n_in, nt, rounds, linear, arity, cap_round;              // cap_round: index (0-based within the tail) of the round whose folded table holds the input evaluations, -1: none
 };
-template <class FP> __global__ void __launch_bounds__(256) k_prod_tail(const ProdTailItem<FP>* __restrict__ items) {
+template <class FP> __device__ __forceinline__ void prod_tail_body(const ProdTailItem<FP>& it, unsigned char* smem_raw) {
     typedef typename FP::X X;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const ProdTailItem<FP> it = items[blockIdx.x];
     const int nt = it.nt, ntab = nt + 1;
     int len = it.n_in;
     X* cur = reinterpret_cast<X*>(smem_raw);            // [ntab][n_in]: table 0 = weights
@@ -265,6 +263,15 @@ template <class FP> __global__ void __launch_bounds__(256) k_prod_tail(const Pro
     } else {
         for (int q = threadIdx.x; q < nt; q += blockDim.x) it.evals[q] = FP::fold(cur[(size_t)(q + 1) * len], cur[(size_t)(q + 1) * len + 1], r, aux);
     }
+}
+template <class FP> __global__ void __launch_bounds__(256) k_prod_tail(const ProdTailItem<FP>* __restrict__ items) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    prod_tail_body<FP>(items[blockIdx.x], smem_raw);
+}
+// a single sumcheck (the Lasso collation sumcheck): descriptor by value
+template <class FP> __global__ void __launch_bounds__(256) k_prod_tail_one(const ProdTailItem<FP> it) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    prod_tail_body<FP>(it, smem_raw);
 }
 
 // ---- final folds and captures: out[i] = in[2 i] + r (in[2 i + 1] - in[2 i]) for tiny tables (one item per block)

@@ -18,6 +18,7 @@
 #include <string>
 #include <vector>
 
+#include "gkr_kernels.cuh"
 #include "gp_kernels.cuh"
 #include "kernels.cuh"
 #include "lasso_host.hpp"
@@ -263,6 +264,7 @@ template <class FP> class Channel {
     X chal(size_t i) const { if (i >= chal_ready_) throw std::runtime_error("Channel: challenge not squeezed yet"); return h_chal_.p[i]; }
     X msg(size_t i) const { if (i >= msg_ready_) throw std::runtime_error("Channel: message not downloaded yet"); return h_msg_.p[i]; }
     Keccak256Transcript<FP>& transcript() { return *active_tr_; }
+    bool prefetching() const { return mode_ == kModePrefetch; }
     size_t chal_used() const { return chal_cursor_; }
     size_t next_index() const { return chal_cursor_; }
 
@@ -445,7 +447,7 @@ void launch_sc_round(DeviceCtx* ctx, int kclass, bool in_base, bool fold, const 
 template <class FP, int ARITY>
 void sumcheck_dev(DeviceCtx* ctx, int kclass, Channel<FP>& ch, const WireOptions& wo, const typename FP::B* d_tables, size_t n, int nterm,
                   const typename FP::X* d_coeffs, typename FP::X* bufA, typename FP::X* bufB, const ScScratch& sc,
-                  std::shared_ptr<ScHostState<FP>> st, size_t* first_chal, size_t* evals_off, bool launch = true) {
+                  std::shared_ptr<ScHostState<FP>> st, size_t* first_chal, size_t* evals_off, bool launch = true, bool product_of_two = false) {
     typedef typename FP::B B;
     typedef typename FP::X X;
     constexpr int D = ARITY + 1;
@@ -453,18 +455,26 @@ void sumcheck_dev(DeviceCtx* ctx, int kclass, Channel<FP>& ch, const WireOptions
     int nv = 0;
     while (((size_t)1 << nv) < n) nv++;
     if (nv < 1) throw std::runtime_error("sumcheck_dev: num_vars must be positive");
+    // g = t_0 * t_1 (the collation sumcheck: coefficients {0, 1}) with all challenges known: the last rounds run in one
+    // shared-memory launch (k_prod_tail_one), the streamed rounds stop at jt
+    const bool tail = product_of_two && ARITY == 1 && nterm == 2 && ch.prefetching() && nv >= 3;
+    const int jt = tail ? std::max(2, nv - HG_PROD_TAIL_LOG) : nv;
     const void* cur_in = d_tables;
     bool in_base = true;
     size_t n_in = n;
-    size_t prev_chal = 0;
+    size_t prev_chal = 0, tail_msg = 0, tail_chal = 0;
     for (int j = 0; j < nv; j++) {
-        size_t off = ch.alloc_msg(j == 0 ? D + 1 : D);
-        if (j == 0) {
-            if (launch) launch_sc_round<FP, ARITY>(ctx, kclass, true, false, d_tables, nullptr, n, nterm, d_coeffs, nullptr, sc, ch.d_msg(off));
-        } else {
-            X* out = (j & 1) ? bufA : bufB;
-            if (launch) launch_sc_round<FP, ARITY>(ctx, kclass, in_base, true, cur_in, out, n_in, nterm, d_coeffs, ch.d_chal(prev_chal), sc, ch.d_msg(off));
-            cur_in = out; in_base = false; n_in >>= 1;
+        const bool streamed = j < jt;
+        size_t off = ch.alloc_msg(streamed ? (j == 0 ? D + 1 : D) : 4);  // the tail kernel writes 4 slots per round: [h(0), h(inf), -, 0]
+        if (j == jt) { tail_msg = off; tail_chal = prev_chal; }
+        if (streamed) {
+            if (j == 0) {
+                if (launch) launch_sc_round<FP, ARITY>(ctx, kclass, true, false, d_tables, nullptr, n, nterm, d_coeffs, nullptr, sc, ch.d_msg(off));
+            } else {
+                X* out = (j & 1) ? bufA : bufB;
+                if (launch) launch_sc_round<FP, ARITY>(ctx, kclass, in_base, true, cur_in, out, n_in, nterm, d_coeffs, ch.d_chal(prev_chal), sc, ch.d_msg(off));
+                cur_in = out; in_base = false; n_in >>= 1;
+            }
         }
         const size_t next_idx = ch.next_index();  // the challenge squeezed right after this message
         emit_round<FP, D>(ch, st, off, wo, j == 0, next_idx);
@@ -476,6 +486,17 @@ void sumcheck_dev(DeviceCtx* ctx, int kclass, Channel<FP>& ch, const WireOptions
     size_t eo = ch.alloc_msg(ntab);
     if (evals_off) *evals_off = eo;
     if (!launch) return;
+    if (tail) {
+        ProdTailItem<FP> t;
+        t.w_in = (const X*)cur_in; t.tab_in = (const X*)cur_in + n_in; t.n_in = (int)n_in; t.nt = 1; t.rounds = nv - jt;
+        t.chal = ch.d_chal(tail_chal); t.msg = ch.d_msg(tail_msg); t.evals = ch.d_msg(eo) + 1;  // evals[0] (= t_0) is not produced: the caller of the collation sumcheck discards both
+        t.capture = nullptr; t.linear = 0; t.arity = 1; t.cap_round = -1;
+        const size_t smem = ((size_t)2 * (n_in + n_in / 2) + 96) * sizeof(X);
+        KernelScope ks(ctx, kclass, 2 * n_in * sizeof(X));
+        k_prod_tail_one<FP><<<1, 256, smem, ctx->stream>>>(t);
+        HG_LAUNCH_CHECK();
+        return;
+    }
     int blocks = (ntab + HG_BLOCK - 1) / HG_BLOCK;
     if (in_base) HG_K(ctx, kclass, 2 * ntab * sizeof(B), k_fold_final<FP, B><<<blocks, HG_BLOCK, 0, ctx->stream>>>((const B*)cur_in, ntab, ch.d_chal(prev_chal), ch.d_msg(eo)));
     else HG_K(ctx, kclass, 2 * ntab * sizeof(X), k_fold_final<FP, X><<<blocks, HG_BLOCK, 0, ctx->stream>>>((const X*)cur_in, ntab, ch.d_chal(prev_chal), ch.d_msg(eo)));
@@ -709,6 +730,8 @@ template <class FP> class LassoNodeDev {
             HG_CUDA(cudaMemcpy(d_wpow_.p, wp.data(), wp.size() * sizeof(B), cudaMemcpyHostToDevice));
         }
         HG_CUDA(cudaFuncSetAttribute(k_cnt_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(M_ * 2)));
+        HG_CUDA(cudaFuncSetAttribute(k_prod_tail_one<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(((size_t)2 * 3 * ((size_t)1 << HG_PROD_TAIL_LOG) + 96) * sizeof(X))));
     }
 
     size_t device_bytes() const {
@@ -845,7 +868,7 @@ template <class FP> class LassoNodeDev {
         // ---- collation sumcheck (lasso.rs:271-279): t_0 * sum_i c_i t_i == E_0 * S with S = sum_i c_i E_i
         {
             // g(E_0, S) = E_0 * (0 * E_0 + 1 * S): nterm = 2, arity 1, tables [E_0 | S]; coefficients {0, 1} live in d_coll_terms_
-            sumcheck_dev<FP, 1>(ctx_, KC_SC_COLL, ch, wo, d_coll_.p, R, 2, d_coll_terms_.p, d_bufA_.p, d_bufB_.p, sc_, coll_state, nullptr, nullptr, lead);
+            sumcheck_dev<FP, 1>(ctx_, KC_SC_COLL, ch, wo, d_coll_.p, R, 2, d_coll_terms_.p, d_bufA_.p, d_bufB_.p, sc_, coll_state, nullptr, nullptr, lead, true);
         }
         // ---- gamma, tau (lasso.rs:99)
         const size_t gt_idx = ch.squeeze(2);
