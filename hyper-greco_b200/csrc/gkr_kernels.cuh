@@ -274,6 +274,49 @@ template <class FP> __global__ void __launch_bounds__(256) k_prod_tail_one(const
     prod_tail_body<FP>(it, smem_raw);
 }
 
+// ---- streamed rounds of g = t_0 * t_1 on two tables laid out back to back (the Lasso collation sumcheck after the rewrite of
+// DESIGN.md 2.1): fold with the previous challenge, write the folded pair of tables, sample h(0), h(inf) (and h(1) in round 0).
+// Unreduced accumulation over HG_COLL_PER_THREAD pairs per thread. msg slots: [h(0), h(inf)] (+ [h(1)] in round 0).
+constexpr int HG_COLL_PER_THREAD = 8;
+template <class FP, class TIN, bool FOLD>
+__global__ void __launch_bounds__(HG_BLOCK) k_coll_round(const TIN* __restrict__ in, typename FP::X* __restrict__ out, size_t n_in,
+                                                       const typename FP::X* __restrict__ r_prev, typename FP::X* partials, unsigned* counter,
+                                                       typename FP::X* msg) {
+    typedef typename FP::X X;
+    constexpr int NP = FOLD ? 2 : 3;
+    const size_t npairs = FOLD ? n_in / 4 : n_in / 2, n_out = n_in / 2;
+    X acc[NP];
+    if constexpr (FOLD) {
+        const X r = *r_prev;
+        const typename FP::FoldAux aux = FP::fold_aux(r);
+        typename FP::XAcc P0 = FP::xacc_zero_(), P1 = FP::xacc_zero_();
+        for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < npairs; b += (size_t)gridDim.x * blockDim.x) {
+            TIN q0[4], q1[4];
+            load4(in + 4 * b, q0);
+            load4(in + n_in + 4 * b, q1);
+            const X lo0 = FP::fold(q0[0], q0[1], r, aux), hi0 = FP::fold(q0[2], q0[3], r, aux);
+            const X lo1 = FP::fold(q1[0], q1[1], r, aux), hi1 = FP::fold(q1[2], q1[3], r, aux);
+            store2(out + 2 * b, lo0, hi0);
+            store2(out + n_out + 2 * b, lo1, hi1);
+            FP::xacc_mad_(P0, lo0, lo1);
+            FP::xacc_mad_(P1, FP::slope(lo0, hi0), FP::slope(lo1, hi1));
+        }
+        acc[0] = FP::xacc_reduce_(P0); acc[1] = FP::xacc_reduce_(P1);
+    } else {
+        typename FP::BAcc P0 = FP::bacc_zero(), P1 = FP::bacc_zero(), P2 = FP::bacc_zero();
+        for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < npairs; b += (size_t)gridDim.x * blockDim.x) {
+            TIN a[2], c[2];
+            load2(in + 2 * b, a);
+            load2(in + n_in + 2 * b, c);
+            FP::bacc_mad(P0, a[0], c[0]);
+            FP::bacc_mad(P1, FP::slope(a[0], a[1]), FP::slope(c[0], c[1]));
+            FP::bacc_mad(P2, a[1], c[1]);
+        }
+        acc[0] = FP::lift(FP::bacc_reduce(P0)); acc[1] = FP::lift(FP::bacc_reduce(P1)); acc[2] = FP::lift(FP::bacc_reduce(P2));
+    }
+    block_reduce_finalize_ex<FP, NP>(acc, partials, counter, msg, gridDim.x, blockIdx.x);
+}
+
 // ---- final folds and captures: out[i] = in[2 i] + r (in[2 i + 1] - in[2 i]) for tiny tables (one item per block)
 template <class FP> struct FoldItem {
     const void* in; typename FP::X* out; const typename FP::X* r; int n_out, in_base;

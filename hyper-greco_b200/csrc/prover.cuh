@@ -468,13 +468,20 @@ void sumcheck_dev(DeviceCtx* ctx, int kclass, Channel<FP>& ch, const WireOptions
         size_t off = ch.alloc_msg(streamed ? (j == 0 ? D + 1 : D) : 4);  // the tail kernel writes 4 slots per round: [h(0), h(inf), -, 0]
         if (j == jt) { tail_msg = off; tail_chal = prev_chal; }
         if (streamed) {
-            if (j == 0) {
-                if (launch) launch_sc_round<FP, ARITY>(ctx, kclass, true, false, d_tables, nullptr, n, nterm, d_coeffs, nullptr, sc, ch.d_msg(off));
-            } else {
-                X* out = (j & 1) ? bufA : bufB;
-                if (launch) launch_sc_round<FP, ARITY>(ctx, kclass, in_base, true, cur_in, out, n_in, nterm, d_coeffs, ch.d_chal(prev_chal), sc, ch.d_msg(off));
-                cur_in = out; in_base = false; n_in >>= 1;
+            X* out = j == 0 ? nullptr : ((j & 1) ? bufA : bufB);
+            if (launch && product_of_two && ARITY == 1 && nterm == 2) {  // g = t_0 * t_1: dedicated streaming kernel
+                const size_t npairs = j == 0 ? n_in / 2 : n_in / 4;
+                int blocks = (int)std::min<size_t>(std::max<size_t>(1, (npairs + HG_BLOCK * HG_COLL_PER_THREAD - 1) / (HG_BLOCK * HG_COLL_PER_THREAD)), (size_t)sc.max_blocks);
+                KernelScope ks(ctx, kclass, 2 * n_in * (in_base ? sizeof(B) : sizeof(X)) + (j ? n_in * sizeof(X) : 0));
+                if (j == 0) k_coll_round<FP, B, false><<<blocks, HG_BLOCK, 0, ctx->stream>>>(d_tables, nullptr, n_in, nullptr, (X*)sc.partials, sc.counters, ch.d_msg(off));
+                else if (in_base) k_coll_round<FP, B, true><<<blocks, HG_BLOCK, 0, ctx->stream>>>((const B*)cur_in, out, n_in, ch.d_chal(prev_chal), (X*)sc.partials, sc.counters, ch.d_msg(off));
+                else k_coll_round<FP, X, true><<<blocks, HG_BLOCK, 0, ctx->stream>>>((const X*)cur_in, out, n_in, ch.d_chal(prev_chal), (X*)sc.partials, sc.counters, ch.d_msg(off));
+                HG_LAUNCH_CHECK();
+            } else if (launch) {
+                if (j == 0) launch_sc_round<FP, ARITY>(ctx, kclass, true, false, d_tables, nullptr, n, nterm, d_coeffs, nullptr, sc, ch.d_msg(off));
+                else launch_sc_round<FP, ARITY>(ctx, kclass, in_base, true, cur_in, out, n_in, nterm, d_coeffs, ch.d_chal(prev_chal), sc, ch.d_msg(off));
             }
+            if (j > 0) { cur_in = out; in_base = false; n_in >>= 1; }
         }
         const size_t next_idx = ch.next_index();  // the challenge squeezed right after this message
         emit_round<FP, D>(ch, st, off, wo, j == 0, next_idx);
