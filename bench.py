@@ -23,6 +23,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# BASELINE.md row "Goldilocks/Ext2, n=32768, 59, 16 - GKR prove: 5.06 s (0.198 proofs/s)" (reference README.md:44, Apple M1):
+# the only published number for this metric; vs_baseline = value / this
+PUBLISHED_PROOFS_PER_SEC = 1.0 / 5.06
 METRIC = "gkr_prove_proofs_per_sec"
 UNIT = "proofs/s"
 DEFAULT_CONFIG = "32768_16x59_65537"
@@ -136,7 +139,7 @@ def run_reference(args):
     v = steps / dt
     sample = f"{steps} full proofs of the same workload (first call {t1:.1f}s used as warm-up" + (f"; --steps {args.steps} capped to fit ~4 min" if steps < args.steps else "") + ")"
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm + 1,
-            "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": v / PUBLISHED_PROOFS_PER_SEC, "dtype": "u64", "data": "synthetic",
             "config": workload_desc(args.config, P, nv, opp.num_memories),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -366,7 +369,9 @@ def run_ours(args):
                    witness="one synthetic witness per rank (seed = rank), proved by every slot of the rank")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_total / args.steps, "ms_per_proof": ms_total / (args.steps * B), "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": cfg, "clocks": clocks,
+                "vs_baseline": value / PUBLISHED_PROOFS_PER_SEC if args.config == DEFAULT_CONFIG else None,
+                "vs_baseline_note": "published: 5.06 s/proof on an Apple M1 (reference README.md:44, BASELINE.md); other hardware",
+                "dtype": "u64", "data": "synthetic", "config": cfg, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * ((n_in_elems + ct_np.size) * 8 + node_chal_bytes(nv) + 4096)),
                         "d2h_bytes_per_step": int(B * proof_len * 2), "single_proof_latency_ms": e2e_latency_ms},
                 "gpu_launches": int(launches_per_proof * args.steps * B), "gpu_launches_per_proof": int(launches_per_proof),

@@ -427,6 +427,24 @@ def test_full_gkr_prove_full_size_properties(api, ctx, oracle):
     assert proof3 == proof
 
 
+def test_full_gkr_prove_n16384_k8(api, ctx, oracle):
+    """BASELINE.json config 3 (n=16384, log q=54, k=8, Goldilocks): whole BfvEncrypt::prove from host vectors; the oracle
+    verifier accepts, every input claim is the MLE of its input, prefetch and interactive modes agree."""
+    from hyper_greco_b200 import params, witness
+    P = params.by_n(16384)
+    args = witness.synth_witness(P, 3)
+    ins, ct0is = witness.get_inputs(P, args)
+    flat = [np.array(v, dtype=np.uint64) for v in [ins["s"], ins["e"], ins["k1"]] + list(ins["ais"]) + list(ins["r1is"]) + [ins["r2is"]]]
+    prover = api.BfvSkEncryptProver(ctx, P)
+    proof, claims = prover.prove_host(flat, np.array(ct0is, dtype=np.uint64), 0)
+    oracle.bfv_verify(0, P, ins, ct0is, proof)
+    for vec, cl in zip(flat, claims):
+        for pt, v in cl:
+            assert (oracle.mle_eval(0, vec, pt.shape[0], pt) == v).all()
+    proof_i, _ = prover.prove_host(flat, np.array(ct0is, dtype=np.uint64), 1)
+    assert proof_i == proof
+
+
 # ------------------------------------------------------------------------------------------------ BN254 Fr (E = F)
 BN_R = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
 
