@@ -240,6 +240,10 @@ __global__ void __launch_bounds__(HG_BLOCK) k_dot_eq(const T* __restrict__ table
     block_reduce_finalize<FP, 1>(acc, partials, counter, out);
 }
 
+// two consecutive base elements with one store where the type allows it (p 16-byte aligned)
+__device__ __forceinline__ void store_pair(u64* p, u64 a, u64 b) { *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(a, b); }
+template <class T> __device__ __forceinline__ void store_pair(T* p, const T& a, const T& b) { p[0] = a; p[1] = b; }
+
 // ---------------------------------------------------------------------------------------------------------
 // K6 multiset hashes (prover.rs:35-89): h(a,v,t) = a + v*gamma + t*gamma^2 - tau, gamma/tau truncated to the base
 // field (prover.rs:38-39). V = [reads (m, chunk-major) | writes (m)] x R.
@@ -268,25 +272,47 @@ __global__ void k_hash_rw_up(const u16* __restrict__ dims, const u32* __restrict
                              typename FP::B* __restrict__ up) {
     typedef typename FP::B B;
     const size_t h = R / 2;
-    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int pos = blockIdx.y;
-    if (j >= h) return;
     const B gamma = FP::x_base0(gamma_tau[0]), tau = FP::x_base0(gamma_tau[1]), gamma2 = FP::b_mul(gamma, gamma);
     const u16* dm = dims + (size_t)pos_dim[pos] * R;
     const u32* ts = read_cts + (size_t)pos_slot[pos] * R;
     const B* e = E + (size_t)pos_mem[pos] * R;
-    B rd[2], wr[2];
+    // a + e*gamma + t*gamma^2 - tau with one reduction (unreduced accumulator, field_policy.cuh)
+    auto hash = [&](size_t q) {
+        typename FP::BAcc acc = FP::bacc_zero();
+        FP::bacc_mad(acc, e[q], gamma);
+        FP::bacc_mad(acc, FP::b_from_u64(ts[q]), gamma2);
+        return FP::b_sub(FP::b_add(FP::bacc_reduce(acc), FP::b_from_u64(dm[q])), tau);
+    };
+    // two neighbouring rows per thread: 16-byte stores of the bottom layer and of layer 1
+    const size_t j0 = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+    if (j0 >= h) return;
+    B rd[2][2], wr[2][2];  // [row j0 + u][half s]
 #pragma unroll
-    for (int s = 0; s < 2; s++) {
-        const size_t q = j + s * h;
-        B a = FP::b_from_u64(dm[q]), t = FP::b_from_u64(ts[q]);
-        rd[s] = FP::b_sub(FP::b_add(FP::b_add(a, FP::b_mul(e[q], gamma)), FP::b_mul(t, gamma2)), tau);
-        wr[s] = FP::b_add(rd[s], gamma2);
-        V[(size_t)pos * R + q] = rd[s];
-        V[(size_t)(m + pos) * R + q] = wr[s];
+    for (int u = 0; u < 2; u++)
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const size_t q = j0 + u + s * h;
+            if (j0 + u < h) { rd[u][s] = hash(q); wr[u][s] = FP::b_add(rd[u][s], gamma2); }
+            else { rd[u][s] = FP::b_zero(); wr[u][s] = FP::b_zero(); }
+        }
+    B* Vr = V + (size_t)pos * R;
+    B* Vw = V + (size_t)(m + pos) * R;
+    B* ur = up + (size_t)pos * h;
+    B* uw = up + (size_t)(m + pos) * h;
+    if (j0 + 1 < h) {
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            store_pair(Vr + j0 + s * h, rd[0][s], rd[1][s]);
+            store_pair(Vw + j0 + s * h, wr[0][s], wr[1][s]);
+        }
+        store_pair(ur + j0, FP::fmul(rd[0][0], rd[0][1]), FP::fmul(rd[1][0], rd[1][1]));
+        store_pair(uw + j0, FP::fmul(wr[0][0], wr[0][1]), FP::fmul(wr[1][0], wr[1][1]));
+    } else {  // odd tail (h is a power of two >= 2 in practice, so this is h == 1 only)
+        for (int s = 0; s < 2; s++) { Vr[j0 + s * h] = rd[0][s]; Vw[j0 + s * h] = wr[0][s]; }
+        ur[j0] = FP::fmul(rd[0][0], rd[0][1]);
+        uw[j0] = FP::fmul(wr[0][0], wr[0][1]);
     }
-    up[(size_t)pos * h + j] = FP::b_mul(rd[0], rd[1]);
-    up[(size_t)(m + pos) * h + j] = FP::b_mul(wr[0], wr[1]);
 }
 // V2 = [inits (m) | final_reads (m)] x M
 template <class FP>

@@ -887,7 +887,7 @@ template <class FP> class LassoNodeDev {
         const bool fused_up = R >= 4;  // hash build fused with the first tree level
         if (fused_up)
             HG_K(ctx_, KC_HASH, (size_t)m * R * (2 + 4 + 4 * sizeof(B)),
-                 k_hash_rw_up<FP><<<dim3((unsigned)((R / 2 + HG_BLOCK - 1) / HG_BLOCK), m), HG_BLOCK, 0, s>>>(
+                 k_hash_rw_up<FP><<<dim3((unsigned)((R / 4 + HG_BLOCK - 1) / HG_BLOCK + (R < 4 ? 1 : 0)), m), HG_BLOCK, 0, s>>>(
                      d_dims_.p, d_read_cts_.p, d_E_.p, d_pos_mem_.p, d_pos_dim_.p, d_pos_slot_.p, ch.d_chal(gt_idx), R, m, d_tree1_.p,
                      d_tree1_.p + (size_t)2 * m * R));
         else
