@@ -340,16 +340,60 @@ __global__ void k_tree_up(const typename FP::B* __restrict__ in, typename FP::B*
     out[(size_t)blockIdx.y * h + k] = FP::fmul(v[k], v[k + h]);
 }
 // two levels per launch: in [nvec][4q] -> out1 [nvec][2q] -> out2 [nvec][q]; the intermediate layer is written but not re-read
+__device__ __forceinline__ void load_pair(const u64* p, u64& a, u64& b) { const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(p); a = t.x; b = t.y; }
+template <class T> __device__ __forceinline__ void load_pair(const T* p, T& a, T& b) { a = p[0]; b = p[1]; }
 template <class FP>
 __global__ void k_tree_up2(const typename FP::B* __restrict__ in, typename FP::B* __restrict__ out1, typename FP::B* __restrict__ out2, size_t q) {
     typedef typename FP::B B;
-    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= q) return;
     const B* v = in + (size_t)blockIdx.y * 4 * q;
-    const B a = FP::fmul(v[k], v[k + 2 * q]), b = FP::fmul(v[k + q], v[k + 3 * q]);
     B* o1 = out1 + (size_t)blockIdx.y * 2 * q;
-    o1[k] = a; o1[k + q] = b;
-    out2[(size_t)blockIdx.y * q + k] = FP::fmul(a, b);
+    B* o2 = out2 + (size_t)blockIdx.y * q;
+    if (q >= 2) {  // two neighbouring entries per thread: 16-byte accesses
+        const size_t k = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+        if (k >= q) return;
+        B x[4][2];
+#pragma unroll
+        for (int s = 0; s < 4; s++) load_pair(v + k + s * q, x[s][0], x[s][1]);
+        B a[2], b[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) { a[u] = FP::fmul(x[0][u], x[2][u]); b[u] = FP::fmul(x[1][u], x[3][u]); }
+        store_pair(o1 + k, a[0], a[1]);
+        store_pair(o1 + k + q, b[0], b[1]);
+        store_pair(o2 + k, FP::fmul(a[0], b[0]), FP::fmul(a[1], b[1]));
+    } else {
+        const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (k >= q) return;
+        const B a = FP::fmul(v[k], v[k + 2 * q]), b = FP::fmul(v[k + q], v[k + 3 * q]);
+        o1[k] = a; o1[k + q] = b;
+        o2[k] = FP::fmul(a, b);
+    }
+}
+// every remaining level of a tree whose vectors have at most HG_TREE_TAIL elements, one CTA per vector, levels in shared
+// memory: layer k (vector length len) -> layers k+1, k+2, ... down to vector length 2. Layers are stored back to back:
+// layer[k+1] = layer[k] + nvec * len(k).
+constexpr int HG_TREE_TAIL = 2048;
+template <class FP>
+__global__ void __launch_bounds__(256) k_tree_tail(typename FP::B* __restrict__ layer, int nvec, int len) {
+    typedef typename FP::B B;
+    extern __shared__ __align__(16) unsigned char tree_smem[];
+    B* cur = reinterpret_cast<B*>(tree_smem);  // [len]
+    const int vec = blockIdx.x;
+    for (int e = threadIdx.x; e < len; e += blockDim.x) cur[e] = layer[(size_t)vec * len + e];
+    __syncthreads();
+    B* base = layer;
+    while (len > 2) {
+        const int h = len / 2;
+        B* next = base + (size_t)nvec * len;
+        B keep[(HG_TREE_TAIL / 2 + 255) / 256];
+        int cnt = 0;
+        for (int e = threadIdx.x; e < h; e += blockDim.x) keep[cnt++] = FP::fmul(cur[e], cur[e + h]);
+        __syncthreads();
+        cnt = 0;
+        for (int e = threadIdx.x; e < h; e += blockDim.x) { const B v = keep[cnt++]; cur[e] = v; next[(size_t)vec * h + e] = v; }
+        __syncthreads();
+        base = next;
+        len = h;
+    }
 }
 // roots (prover.rs:197-203) and the nv = 0 layer's evaluations (prover.rs:232-236) from the top layer [nvec][2]
 template <class FP>

@@ -737,6 +737,7 @@ template <class FP> class LassoNodeDev {
             HG_CUDA(cudaMemcpy(d_wpow_.p, wp.data(), wp.size() * sizeof(B), cudaMemcpyHostToDevice));
         }
         HG_CUDA(cudaFuncSetAttribute(k_cnt_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(M_ * 2)));
+        HG_CUDA(cudaFuncSetAttribute(k_tree_tail<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HG_TREE_TAIL * sizeof(B))));
         HG_CUDA(cudaFuncSetAttribute(k_prod_tail_one<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)(((size_t)2 * 3 * ((size_t)1 << HG_PROD_TAIL_LOG) + 96) * sizeof(X))));
     }
@@ -992,10 +993,16 @@ template <class FP> class LassoNodeDev {
         layer[0] = tree;
         for (int k = 1; k < nvars; k++) layer[k] = layer[k - 1] + (size_t)nvec * (N >> (k - 1));
         for (int k = (level1_done ? 2 : 1); k < nvars;) {
+            const size_t len_prev = N >> (k - 1);  // vector length of the layer this step reads
+            if (len_prev <= (size_t)HG_TREE_TAIL && len_prev > 2) {  // the rest of the tree in one launch (shared memory)
+                HG_K(ctx_, KC_TREE, (size_t)nvec * len_prev * 2 * sizeof(B),
+                     k_tree_tail<FP><<<nvec, 256, len_prev * sizeof(B), s>>>(layer[k - 1], nvec, (int)len_prev));
+                break;
+            }
             if (k + 1 < nvars) {  // two levels per launch: layer k is written and never re-read by the build
                 const size_t q = N >> (k + 1);
                 HG_K(ctx_, KC_TREE, (size_t)nvec * q * 7 * sizeof(B),
-                     k_tree_up2<FP><<<dim3((unsigned)((q + HG_BLOCK - 1) / HG_BLOCK), nvec), HG_BLOCK, 0, s>>>(layer[k - 1], layer[k], layer[k + 1], q));
+                     k_tree_up2<FP><<<dim3((unsigned)(((q >= 2 ? q / 2 : q) + HG_BLOCK - 1) / HG_BLOCK), nvec), HG_BLOCK, 0, s>>>(layer[k - 1], layer[k], layer[k + 1], q));
                 k += 2;
             } else {
                 const size_t h = N >> k;
