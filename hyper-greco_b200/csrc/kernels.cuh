@@ -225,12 +225,23 @@ __global__ void __launch_bounds__(HG_BLOCK) k_dot_eq(const T* __restrict__ table
         typename FP::XAcc a = FP::xacc_zero_();
         const T* row = t + kh * nlo;
         if (nlo >= 4) {
-#pragma unroll 4
-            for (size_t kl = 4 * (size_t)threadIdx.x; kl < nlo; kl += 4 * (size_t)blockDim.x) {
-                B v[4];
-                Load4<FP, T>::f(row + kl, v);
+            // four strides per step with all table loads issued first: 128 bytes in flight per thread
+            const size_t step = 4 * (size_t)blockDim.x;
+            for (size_t k0 = 4 * (size_t)threadIdx.x; k0 < nlo; k0 += 4 * step) {
+                B v[4][4];
 #pragma unroll
-                for (int e = 0; e < 4; e++) FP::xacc_mad_b(a, eq_lo[kl + e], v[e]);
+                for (int u = 0; u < 4; u++) {
+                    const size_t kl = k0 + u * step;
+                    if (kl < nlo) Load4<FP, T>::f(row + kl, v[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const size_t kl = k0 + u * step;
+                    if (kl < nlo) {
+#pragma unroll
+                        for (int e = 0; e < 4; e++) FP::xacc_mad_b(a, eq_lo[kl + e], v[u][e]);
+                    }
+                }
             }
         } else {
             for (size_t kl = threadIdx.x; kl < nlo; kl += blockDim.x) FP::xacc_mad_b(a, eq_lo[kl], ToBase<FP, T>::f(row[kl]));

@@ -971,7 +971,10 @@ template <class FP> class LassoNodeDev {
     template <class T> void dot_tables(Channel<FP>& ch, const T* tables, size_t stride, int ntab, size_t n, size_t msg_off) {
         const int lo = eq_lo_bits(eq_nv_);
         if (n != (size_t)1 << eq_nv_) throw std::runtime_error("dot_tables: eq tables were built for another size");
-        int blocks = (int)std::min<size_t>(n >> lo, (size_t)ctx_->sm_count * 2);
+        // about 6 CTAs per SM over all tables of the launch: every CTA ends with a block-level reduction that costs as much as
+        // ~100 elements per thread, so few long CTAs beat many short ones
+        const size_t per_table = std::max<size_t>(1, ((size_t)ctx_->sm_count * 6 + ntab - 1) / ntab);
+        int blocks = (int)std::min<size_t>(n >> lo, std::min<size_t>(per_table, (size_t)ctx_->sm_count * 2));
         if (blocks < 1) blocks = 1;
         HG_K(ctx_, KC_DOT, (size_t)ntab * n * sizeof(T),
              k_dot_eq<FP, T><<<dim3(blocks, ntab), HG_BLOCK, 0, ctx_->stream>>>(tables, stride, n, lo, d_eq_.p, d_eq_.p + ((size_t)1 << lo), d_partials_.p, d_counters_.p, ch.d_msg(msg_off)));
