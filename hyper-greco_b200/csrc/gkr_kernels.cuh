@@ -155,6 +155,22 @@ __device__ __forceinline__ void prod_round_item(const ProdItem<FP>& it, unsigned
     typename FP::FoldAux aux;
     if (FOLD) { r = *it.r_prev; aux = FP::fold_aux(r); }
     (void)NS;
+    if constexpr (NT == 1 && !FOLD) {
+        // round 0 of a degree-2 node (most of the bytes of the class): extension weight times BASE table entry, three samples,
+        // unreduced accumulation (two 64x64 products per sample; 16 registers per accumulator because the X^2 column stays empty)
+        typename FP::XAcc P0 = FP::xacc_zero_(), P1 = FP::xacc_zero_(), P3 = FP::xacc_zero_();
+        for (size_t b = (size_t)lb * blockDim.x + threadIdx.x; b < npairs; b += (size_t)it.nblk * blockDim.x) {
+            X w[2];
+            TIN t[2];
+            load2(it.w_in + 2 * b, w);
+            load2(tab + 2 * b, t);
+            FP::xacc_mad_b(P0, w[0], t[0]);
+            FP::xacc_mad_b(P1, FP::slope(w[0], w[1]), FP::slope(t[0], t[1]));
+            FP::xacc_mad_b(P3, w[1], t[1]);
+        }
+        acc[0] = FP::xacc_reduce_(P0); acc[1] = FP::xacc_reduce_(P1); acc[3] = FP::xacc_reduce_(P3);
+        return;
+    }
     for (size_t b = (size_t)lb * blockDim.x + threadIdx.x; b < npairs; b += (size_t)it.nblk * blockDim.x) {
         X wlo, whi;
         if constexpr (FOLD) {
