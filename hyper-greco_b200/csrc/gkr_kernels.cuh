@@ -159,6 +159,7 @@ __device__ __forceinline__ void prod_round_item(const ProdItem<FP>& it, unsigned
         // round 0 of a degree-2 node (most of the bytes of the class): extension weight times BASE table entry, three samples,
         // unreduced accumulation (two 64x64 products per sample; 16 registers per accumulator because the X^2 column stays empty)
         typename FP::XAcc P0 = FP::xacc_zero_(), P1 = FP::xacc_zero_(), P3 = FP::xacc_zero_();
+#pragma unroll 2
         for (size_t b = (size_t)lb * blockDim.x + threadIdx.x; b < npairs; b += (size_t)it.nblk * blockDim.x) {
             X w[2];
             TIN t[2];
@@ -210,7 +211,7 @@ __device__ __forceinline__ void prod_round_item(const ProdItem<FP>& it, unsigned
     }
 }
 template <class FP, class TIN, bool FOLD>
-__global__ void __launch_bounds__(HG_BLOCK) k_prod_round_multi(const ProdItem<FP>* __restrict__ items, int nitems) {
+__global__ void __launch_bounds__(HG_BLOCK, (FOLD || sizeof(typename FP::B) > 8) ? 1 : 3) k_prod_round_multi(const ProdItem<FP>* __restrict__ items, int nitems) {
     typedef typename FP::X X;
     const ProdItem<FP> it = items[find_item(items, nitems)];
     const unsigned lb = blockIdx.x - it.blk_start;

@@ -221,32 +221,42 @@ __global__ void __launch_bounds__(HG_BLOCK) k_dot_eq(const T* __restrict__ table
     const T* t = tables + (size_t)blockIdx.y * stride;
     const size_t nlo = (size_t)1 << lo_bits, nhi = n >> lo_bits;
     X acc[1] = {FP::x_zero()};
-    for (size_t kh = blockIdx.x; kh < nhi; kh += gridDim.x) {
-        typename FP::XAcc a = FP::xacc_zero_();
-        const T* row = t + kh * nlo;
-        if (nlo >= 4) {
-            // four strides per step with all table loads issued first: 128 bytes in flight per thread
-            const size_t step = 4 * (size_t)blockDim.x;
-            for (size_t k0 = 4 * (size_t)threadIdx.x; k0 < nlo; k0 += 4 * step) {
-                B v[4][4];
+    if (nlo == 16 * (size_t)blockDim.x) {
+        // the usual shape (2^12 low entries, 256 threads): a thread always meets the same 16 entries of eq_lo, so they live in
+        // registers for the whole launch and a row costs only its own 4 loads of 4 table entries, all issued up front
+        X el[4][4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const size_t kl = k0 + u * step;
-                    if (kl < nlo) Load4<FP, T>::f(row + kl, v[u]);
-                }
+        for (int u = 0; u < 4; u++)
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const size_t kl = k0 + u * step;
-                    if (kl < nlo) {
+            for (int e = 0; e < 4; e++) el[u][e] = eq_lo[4 * (size_t)threadIdx.x + (size_t)u * 4 * blockDim.x + e];
+        for (size_t kh = blockIdx.x; kh < nhi; kh += gridDim.x) {
+            const T* row = t + kh * nlo;
+            B v[4][4];
 #pragma unroll
-                        for (int e = 0; e < 4; e++) FP::xacc_mad_b(a, eq_lo[kl + e], v[u][e]);
-                    }
-                }
-            }
-        } else {
-            for (size_t kl = threadIdx.x; kl < nlo; kl += blockDim.x) FP::xacc_mad_b(a, eq_lo[kl], ToBase<FP, T>::f(row[kl]));
+            for (int u = 0; u < 4; u++) Load4<FP, T>::f(row + 4 * (size_t)threadIdx.x + (size_t)u * 4 * blockDim.x, v[u]);
+            typename FP::XAcc a = FP::xacc_zero_();
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) FP::xacc_mad_b(a, el[u][e], v[u][e]);
+            acc[0] = FP::x_add(acc[0], FP::fmul(FP::xacc_reduce_(a), eq_hi[kh]));
         }
-        acc[0] = FP::x_add(acc[0], FP::fmul(FP::xacc_reduce_(a), eq_hi[kh]));
+    } else {
+        for (size_t kh = blockIdx.x; kh < nhi; kh += gridDim.x) {
+            typename FP::XAcc a = FP::xacc_zero_();
+            const T* row = t + kh * nlo;
+            if (nlo >= 4) {
+                for (size_t kl = 4 * (size_t)threadIdx.x; kl < nlo; kl += 4 * (size_t)blockDim.x) {
+                    B v[4];
+                    Load4<FP, T>::f(row + kl, v);
+#pragma unroll
+                    for (int e = 0; e < 4; e++) FP::xacc_mad_b(a, eq_lo[kl + e], v[e]);
+                }
+            } else {
+                for (size_t kl = threadIdx.x; kl < nlo; kl += blockDim.x) FP::xacc_mad_b(a, eq_lo[kl], ToBase<FP, T>::f(row[kl]));
+            }
+            acc[0] = FP::x_add(acc[0], FP::fmul(FP::xacc_reduce_(a), eq_hi[kh]));
+        }
     }
     block_reduce_finalize<FP, 1>(acc, partials, counter, out);
 }
