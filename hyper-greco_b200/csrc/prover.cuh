@@ -1109,8 +1109,10 @@ template <class FP> class LassoNodeDev {
         // grid shape of the streaming launches: at most gp_max_bx blocks along a table, term groups added until an item has
         // about gp_target blocks (tunable for experiments through HG_GP_MAXBX / HG_GP_TARGET, in units of the SM count)
         static const int env_maxbx = getenv("HG_GP_MAXBX") ? atoi(getenv("HG_GP_MAXBX")) : 4;
-        static const int env_target = getenv("HG_GP_TARGET") ? atoi(getenv("HG_GP_TARGET")) : 2;
-        const int target_blocks = ctx_->sm_count * env_target;
+        // measured optimum: one term group (every thread loops over all terms of its pairs and reuses t_0) as soon as a table gives
+        // ~37 CTAs; smaller layers get term groups so that no layer runs on fewer CTAs than that
+        static const double env_target = getenv("HG_GP_TARGET") ? atof(getenv("HG_GP_TARGET")) : 0.25;
+        const int target_blocks = std::max(1, (int)(ctx_->sm_count * env_target));
         const size_t gp_max_bx = (size_t)ctx_->sm_count * env_maxbx;
         for (int r = 0; r <= maxJ; r++) {
             int blk = 0;
