@@ -203,7 +203,7 @@ namespace hg {
 // Goldilocks, 32 elements of 32 B for BN254: 2*m tables * 1.5 * that must fit 227 KB)
 constexpr int HG_TAIL_THREADS = 512;
 #ifndef HG_GP_PREFETCH
-#define HG_GP_PREFETCH 2
+#define HG_GP_PREFETCH 1
 #endif
 
 template <class FP> struct GpItem {
