@@ -547,7 +547,7 @@ template <class FP> class GkrCircuitDev {
             }
             const size_t S = n.a_pad * n.n_in;
             WiringItem<FP> wi; wi.rev_ptr = n.rev_ptr.p; wi.rev_out = n.rev_out.p; wi.rev_coef = n.rev_coef.p; wi.w = n.W.p; wi.A = n.A.p; wi.n = S; wi.blk_start = wire_blk;
-            wire_blk += (int)((S + HG_BLOCK - 1) / HG_BLOCK);
+            wire_blk += (int)((S + HG_BLOCK * HG_WIRING_PER_THREAD - 1) / (HG_BLOCK * HG_WIRING_PER_THREAD));
             wire_bytes += S * sizeof(X) * 2;
             wires.push_back(wi);
             if (n.a_pad != (size_t)n.arity) cat(nullptr, n.Xcat.p + (size_t)n.arity * n.n_in, (n.a_pad - n.arity) * n.n_in);

@@ -92,13 +92,25 @@ template <class FP> struct WiringItem {
     const u64* rev_ptr; const u32* rev_out; const typename FP::B* rev_coef; const typename FP::X* w; typename FP::X* A;
     u64 n; int blk_start;
 };
+constexpr int HG_WIRING_PER_THREAD = 4;  // independent pointer-chasing chains per thread (ptr -> edge -> W): memory-level parallelism
 template <class FP> __global__ void k_wiring_gather(const WiringItem<FP>* __restrict__ items, int nitems) {
     const WiringItem<FP> it = items[find_item(items, nitems)];
-    const size_t x = (size_t)(blockIdx.x - it.blk_start) * blockDim.x + threadIdx.x;
-    if (x >= it.n) return;
-    typename FP::XAcc acc = FP::xacc_zero_();
-    for (u64 e = it.rev_ptr[x]; e < it.rev_ptr[x + 1]; e++) FP::xacc_mad_b(acc, it.w[it.rev_out[e]], it.rev_coef[e]);
-    it.A[x] = FP::xacc_reduce_(acc);
+    const size_t base = (size_t)(blockIdx.x - it.blk_start) * blockDim.x * HG_WIRING_PER_THREAD + threadIdx.x;
+    u64 e0[HG_WIRING_PER_THREAD], e1[HG_WIRING_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < HG_WIRING_PER_THREAD; k++) {
+        const size_t x = base + (size_t)k * blockDim.x;
+        e0[k] = e1[k] = 0;
+        if (x < it.n) { e0[k] = it.rev_ptr[x]; e1[k] = it.rev_ptr[x + 1]; }
+    }
+#pragma unroll
+    for (int k = 0; k < HG_WIRING_PER_THREAD; k++) {
+        const size_t x = base + (size_t)k * blockDim.x;
+        if (x >= it.n) continue;
+        typename FP::XAcc acc = FP::xacc_zero_();
+        for (u64 e = e0[k]; e < e1[k]; e++) FP::xacc_mad_b(acc, it.w[it.rev_out[e]], it.rev_coef[e]);
+        it.A[x] = FP::xacc_reduce_(acc);
+    }
 }
 // concatenated input tables of the layer sumchecks: dst[0..n) = src[0..n) (src = nullptr: zeros), every node's pieces in one launch
 template <class FP> struct ConcatItem { const typename FP::B* src; typename FP::B* dst; u64 n; int blk_start; };
