@@ -160,6 +160,17 @@ __global__ void k_cnt_scan(const u16* __restrict__ blk_hist, int nblk, int log2M
                            u32* __restrict__ final_cts /*[slot][M]*/);
 __global__ void k_cnt_rank(CntSlots sl, const u8* __restrict__ row_lookup, size_t n_rows, size_t R, int rows_per_block, const u32* __restrict__ blk_base,
                            int nblk, int log2M, u32* __restrict__ read_cts /*[slot][R]*/);
+// the same counters by a stable two-pass radix sort of (address, row) (kernels.cu): scratch proportional to the rows
+__global__ void k_cnt_digit_hist(int pass, CntSlots sl, const u8* __restrict__ row_lookup, size_t n_rows, size_t cap, const u64* __restrict__ src,
+                                 const u32* __restrict__ n_valid, int nblk, u32* __restrict__ blk_hist /*[slot][nblk][256]*/);
+__global__ void k_cnt_digit_scan(int nblk, const u32* __restrict__ blk_hist, u32* __restrict__ blk_base, u32* __restrict__ digit_start /*[slot][256]*/,
+                                 u32* __restrict__ n_valid);
+__global__ void k_cnt_digit_scatter(int pass, CntSlots sl, const u8* __restrict__ row_lookup, size_t n_rows, size_t cap, const u64* __restrict__ src,
+                                    const u32* __restrict__ n_valid, int nblk, const u32* __restrict__ blk_base, const u32* __restrict__ digit_start,
+                                    u64* __restrict__ dst);
+__global__ void k_cnt_heads(size_t cap, const u64* __restrict__ sorted, const u32* __restrict__ n_valid, size_t M, u32* __restrict__ start, u32* __restrict__ end);
+__global__ void k_cnt_finish(size_t cap, const u64* __restrict__ sorted, const u32* __restrict__ n_valid, size_t M, const u32* __restrict__ start,
+                             const u32* __restrict__ end, size_t R, u32* __restrict__ read_cts, u32* __restrict__ final_cts);
 
 // ---------------------------------------------------------------------------------------------------------
 // eq(point, k) = prod_i (k_i ? r_i : 1 - r_i), k_0 = LSB (plonkish MultilinearPolynomial::eq_xy, lasso.rs:432), kept as

@@ -690,8 +690,13 @@ template <class FP> class LassoNodeDev {
         rows_per_block_ = 4096;
         nblk_cnt_ = (int)((std::max<size_t>(n_rows_, 1) + rows_per_block_ - 1) / rows_per_block_);
         if (nslots_ > HG_MAX_C) throw std::runtime_error("LassoNode: too many chunks");
-        d_blk_hist_.alloc((size_t)nslots_ * nblk_cnt_ * M_);   // every chunk slot has its own scratch: the slots run in the same launches
-        d_blk_base_.alloc((size_t)nslots_ * nblk_cnt_ * M_);
+        // counter scratch (radix sort of (address, row), kernels.cu): two element buffers, tile histograms, run boundaries
+        cnt_cap_ = (size_t)nblk_cnt_ * rows_per_block_;
+        d_cnt_a_.alloc((size_t)nslots_ * cnt_cap_);
+        d_cnt_b_.alloc((size_t)nslots_ * cnt_cap_);
+        d_cnt_hist_.alloc((size_t)2 * nslots_ * nblk_cnt_ * 256);  // tile histograms | their prefixes
+        d_cnt_misc_.alloc((size_t)nslots_ * (256 + 8));           // digit starts, then n_valid
+        d_cnt_runs_.alloc((size_t)2 * nslots_ * M_);              // start | end of every address run
         d_eq_.alloc(std::max(R_, M_));
         d_coeff_coll_.alloc(m_);
         d_wpow_.alloc(HG_MAX_C);
@@ -736,15 +741,14 @@ template <class FP> class LassoNodeDev {
             for (int t = 0; t < HG_MAX_C; t++) { wp[t] = p; p = FP::b_mul(p, FP::b_from_u64(M_)); }
             HG_CUDA(cudaMemcpy(d_wpow_.p, wp.data(), wp.size() * sizeof(B), cudaMemcpyHostToDevice));
         }
-        HG_CUDA(cudaFuncSetAttribute(k_cnt_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(M_ * 2)));
         HG_CUDA(cudaFuncSetAttribute(k_tree_tail<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HG_TREE_TAIL * sizeof(B))));
         HG_CUDA(cudaFuncSetAttribute(k_prod_tail_one<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)(((size_t)2 * 3 * ((size_t)1 << HG_PROD_TAIL_LOG) + 96) * sizeof(X))));
     }
 
     size_t device_bytes() const {
-        return d_dims_.bytes() + d_E_.bytes() + d_coll_.bytes() + d_out_.bytes() + d_read_cts_.bytes() + d_final_cts_.bytes() + d_blk_hist_.bytes() +
-               d_blk_base_.bytes() + d_eq_.bytes() + d_tree1_.bytes() + d_tree2_.bytes() + d_bufA_.bytes() + d_bufB_.bytes() + d_pool_.bytes() + d_subtables_.bytes();
+        return d_dims_.bytes() + d_E_.bytes() + d_coll_.bytes() + d_out_.bytes() + d_read_cts_.bytes() + d_final_cts_.bytes() + d_cnt_a_.bytes() + d_cnt_b_.bytes() +
+               d_cnt_hist_.bytes() + d_cnt_runs_.bytes() + d_eq_.bytes() + d_tree1_.bytes() + d_tree2_.bytes() + d_bufA_.bytes() + d_bufB_.bytes() + d_pool_.bytes() + d_subtables_.bytes();
     }
     size_t num_rows() const { return n_rows_; }
     int num_vars() const { return num_vars_; }
@@ -843,9 +847,27 @@ template <class FP> class LassoNodeDev {
             CntSlots sl;
             for (int q = 0; q < HG_MAX_C; q++) { sl.addr[q] = nullptr; sl.used[q] = 0; }
             for (int q = 0; q < nslots_; q++) { sl.addr[q] = d_dims_.p + (size_t)slot_addr_dim_[q] * R; sl.used[q] = slot_used_[q]; }
-            HG_K(ctx_, KC_COUNTERS, (size_t)nslots_ * rows * 3, k_cnt_hist<<<dim3(nblk_cnt_, nslots_), 1024, M * 2, cs>>>(sl, d_row_lookup_.p, rows, rows_per_block_, d_blk_hist_.p, nblk_cnt_, log2M_));
-            HG_K(ctx_, KC_COUNTERS, (size_t)nslots_ * M * 4, k_cnt_scan<<<dim3((unsigned)((M + 255) / 256), nslots_), 256, 0, cs>>>(d_blk_hist_.p, nblk_cnt_, log2M_, d_blk_base_.p, d_final_cts_.p));
-            HG_K(ctx_, KC_COUNTERS, (size_t)nslots_ * rows * 7, k_cnt_rank<<<dim3(nblk_cnt_, nslots_), 1024, 0, cs>>>(sl, d_row_lookup_.p, rows, R, rows_per_block_, d_blk_base_.p, nblk_cnt_, log2M_, d_read_cts_.p));
+            // stable radix sort of (address, row) by the low then the high address byte; counters from the run boundaries
+            u32* d_digit_start = d_cnt_misc_.p;
+            u32* d_nvalid = d_cnt_misc_.p + (size_t)nslots_ * 256;
+            u32* d_cnt_base = d_cnt_hist_.p + (size_t)nslots_ * nblk_cnt_ * 256;
+            u32* d_start = d_cnt_runs_.p;
+            u32* d_end = d_cnt_runs_.p + (size_t)nslots_ * M;
+            HG_CUDA(cudaMemsetAsync(d_cnt_runs_.p, 0, d_cnt_runs_.bytes(), cs));
+            const dim3 tiles(nblk_cnt_, nslots_);
+            for (int pass = 0; pass < 2; pass++) {
+                const u64* src = pass == 0 ? nullptr : d_cnt_a_.p;
+                u64* dst = pass == 0 ? d_cnt_a_.p : d_cnt_b_.p;
+                HG_K(ctx_, KC_COUNTERS, (size_t)nslots_ * rows * (pass ? 8 : 3),
+                     k_cnt_digit_hist<<<tiles, 1024, 0, cs>>>(pass, sl, d_row_lookup_.p, rows, cnt_cap_, src, d_nvalid, nblk_cnt_, d_cnt_hist_.p));
+                HG_K(ctx_, KC_COUNTERS, (size_t)nslots_ * nblk_cnt_ * 256 * 8, k_cnt_digit_scan<<<nslots_, 1024, 0, cs>>>(nblk_cnt_, d_cnt_hist_.p, d_cnt_base, d_digit_start, d_nvalid));
+                HG_K(ctx_, KC_COUNTERS, (size_t)nslots_ * rows * (pass ? 16 : 11),
+                     k_cnt_digit_scatter<<<tiles, 1024, 0, cs>>>(pass, sl, d_row_lookup_.p, rows, cnt_cap_, src, d_nvalid, nblk_cnt_, d_cnt_base, d_digit_start, dst));
+            }
+            const unsigned fin_blocks = (unsigned)((std::max<size_t>(cnt_cap_, M) + 255) / 256);
+            HG_K(ctx_, KC_COUNTERS, (size_t)nslots_ * rows * 8, k_cnt_heads<<<dim3(fin_blocks, nslots_), 256, 0, cs>>>(cnt_cap_, d_cnt_b_.p, d_nvalid, M, d_start, d_end));
+            HG_K(ctx_, KC_COUNTERS, (size_t)nslots_ * (rows * 12 + M * 12),
+                 k_cnt_finish<<<dim3(fin_blocks, nslots_), 256, 0, cs>>>(cnt_cap_, d_cnt_b_.p, d_nvalid, M, d_start, d_end, R, d_read_cts_.p, d_final_cts_.p));
         }
         if (side) {
             ctx_->stream = s;
@@ -1264,8 +1286,10 @@ template <class FP> class LassoNodeDev {
     DevBuf<NodeMeta> d_meta_;
     DevBuf<u8> d_row_lookup_;
     DevBuf<B> d_subtables_, d_E_, d_coll_, d_out_, d_coeff_coll_, d_wpow_, d_tree1_, d_tree2_;
-    DevBuf<u16> d_dims_, d_blk_hist_;
-    DevBuf<u32> d_read_cts_, d_final_cts_, d_blk_base_;
+    DevBuf<u16> d_dims_;
+    DevBuf<u32> d_read_cts_, d_final_cts_, d_cnt_hist_, d_cnt_misc_, d_cnt_runs_;
+    DevBuf<u64> d_cnt_a_, d_cnt_b_;
+    size_t cnt_cap_ = 0;
     DevBuf<int> d_pos_mem_, d_pos_dim_, d_pos_slot_, d_pos_sub_;
     DevBuf<X> d_eq_, d_gp_coeffs_, d_bufA_, d_bufB_, d_partials_, d_coll_terms_;
     int coll_coeff_state_ = 0;  // 0 not uploaded, 1 ascending, 2 descending
