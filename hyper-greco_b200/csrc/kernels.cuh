@@ -151,20 +151,13 @@ __global__ void k_polynomialize(const typename FP::B* __restrict__ inputs, size_
 
 // ---------------------------------------------------------------------------------------------------------
 // K2 counters (lasso.rs:177-196): read_cts[j] = number of earlier rows that touch the same address of memory `mem`,
-// final_cts[a] = total. Order-dependent, so: per-block histogram -> per-address scan over blocks -> ordered rank.
-// rows_per_block <= 65535 so that 16-bit packed shared counters cannot overflow.
+// final_cts[a] = total. Order-dependent: a stable two-pass radix sort of (address, row) groups the rows of an address in row
+// order; the counters are read off the run boundaries (kernels.cu).
 struct CntSlots { const u16* addr[HG_MAX_C]; u64 used[HG_MAX_C]; };  // per chunk slot: its address column and the lookup types that use it
-__global__ void k_cnt_hist(CntSlots sl, const u8* __restrict__ row_lookup, size_t n_rows, int rows_per_block, u16* __restrict__ blk_hist /*[slot][nblk][M]*/,
-                           int nblk, int log2M);
-__global__ void k_cnt_scan(const u16* __restrict__ blk_hist, int nblk, int log2M, u32* __restrict__ blk_base /*[slot][nblk][M]*/,
-                           u32* __restrict__ final_cts /*[slot][M]*/);
-__global__ void k_cnt_rank(CntSlots sl, const u8* __restrict__ row_lookup, size_t n_rows, size_t R, int rows_per_block, const u32* __restrict__ blk_base,
-                           int nblk, int log2M, u32* __restrict__ read_cts /*[slot][R]*/);
-// the same counters by a stable two-pass radix sort of (address, row) (kernels.cu): scratch proportional to the rows
 __global__ void k_cnt_digit_hist(int pass, CntSlots sl, const u8* __restrict__ row_lookup, size_t n_rows, size_t cap, const u64* __restrict__ src,
                                  const u32* __restrict__ n_valid, int nblk, u32* __restrict__ blk_hist /*[slot][nblk][256]*/);
-__global__ void k_cnt_digit_scan(int nblk, const u32* __restrict__ blk_hist, u32* __restrict__ blk_base, u32* __restrict__ digit_start /*[slot][256]*/,
-                                 u32* __restrict__ n_valid);
+__global__ void k_cnt_digit_scan(int nblk, const u32* __restrict__ blk_hist, u32* __restrict__ blk_base, u32* __restrict__ digit_total /*[slot][256]*/);
+__global__ void k_cnt_digit_starts(const u32* __restrict__ digit_total, u32* __restrict__ digit_start /*[slot][256]*/, u32* __restrict__ n_valid);
 __global__ void k_cnt_digit_scatter(int pass, CntSlots sl, const u8* __restrict__ row_lookup, size_t n_rows, size_t cap, const u64* __restrict__ src,
                                     const u32* __restrict__ n_valid, int nblk, const u32* __restrict__ blk_base, const u32* __restrict__ digit_start,
                                     u64* __restrict__ dst);

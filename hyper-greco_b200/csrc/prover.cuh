@@ -695,7 +695,7 @@ template <class FP> class LassoNodeDev {
         d_cnt_a_.alloc((size_t)nslots_ * cnt_cap_);
         d_cnt_b_.alloc((size_t)nslots_ * cnt_cap_);
         d_cnt_hist_.alloc((size_t)2 * nslots_ * nblk_cnt_ * 256);  // tile histograms | their prefixes
-        d_cnt_misc_.alloc((size_t)nslots_ * (256 + 8));           // digit starts, then n_valid
+        d_cnt_misc_.alloc((size_t)nslots_ * (512 + 8));           // digit starts, n_valid, digit totals
         d_cnt_runs_.alloc((size_t)2 * nslots_ * M_);              // start | end of every address run
         d_eq_.alloc(std::max(R_, M_));
         d_coeff_coll_.alloc(m_);
@@ -851,6 +851,7 @@ template <class FP> class LassoNodeDev {
             u32* d_digit_start = d_cnt_misc_.p;
             u32* d_nvalid = d_cnt_misc_.p + (size_t)nslots_ * 256;
             u32* d_cnt_base = d_cnt_hist_.p + (size_t)nslots_ * nblk_cnt_ * 256;
+            u32* d_digit_total = d_cnt_misc_.p + (size_t)nslots_ * 256 + 8;
             u32* d_start = d_cnt_runs_.p;
             u32* d_end = d_cnt_runs_.p + (size_t)nslots_ * M;
             HG_CUDA(cudaMemsetAsync(d_cnt_runs_.p, 0, d_cnt_runs_.bytes(), cs));
@@ -860,7 +861,8 @@ template <class FP> class LassoNodeDev {
                 u64* dst = pass == 0 ? d_cnt_a_.p : d_cnt_b_.p;
                 HG_K(ctx_, KC_COUNTERS, (size_t)nslots_ * rows * (pass ? 8 : 3),
                      k_cnt_digit_hist<<<tiles, 1024, 0, cs>>>(pass, sl, d_row_lookup_.p, rows, cnt_cap_, src, d_nvalid, nblk_cnt_, d_cnt_hist_.p));
-                HG_K(ctx_, KC_COUNTERS, (size_t)nslots_ * nblk_cnt_ * 256 * 8, k_cnt_digit_scan<<<nslots_, 1024, 0, cs>>>(nblk_cnt_, d_cnt_hist_.p, d_cnt_base, d_digit_start, d_nvalid));
+                HG_K(ctx_, KC_COUNTERS, (size_t)nslots_ * nblk_cnt_ * 256 * 8, k_cnt_digit_scan<<<dim3(8, nslots_), 1024, 0, cs>>>(nblk_cnt_, d_cnt_hist_.p, d_cnt_base, d_digit_total));
+                HG_K(ctx_, KC_COUNTERS, (size_t)nslots_ * 2048, k_cnt_digit_starts<<<nslots_, 256, 0, cs>>>(d_digit_total, d_digit_start, d_nvalid));
                 HG_K(ctx_, KC_COUNTERS, (size_t)nslots_ * rows * (pass ? 16 : 11),
                      k_cnt_digit_scatter<<<tiles, 1024, 0, cs>>>(pass, sl, d_row_lookup_.p, rows, cnt_cap_, src, d_nvalid, nblk_cnt_, d_cnt_base, d_digit_start, dst));
             }
