@@ -73,6 +73,21 @@ template <class FP> __global__ void k_eq_accumulate(const EqAccItem<FP>* __restr
     const EqAccItem<FP> it = items[find_item(items, nitems)];
     const size_t nlo = (size_t)1 << it.lo_bits;
     const size_t base = (size_t)(blockIdx.x - it.blk_start) * blockDim.x * HG_EQACC_PER_THREAD + threadIdx.x;
+    if (it.n_claims == 1) {  // almost every node: all loads first, then the products
+        X lo[HG_EQACC_PER_THREAD], hi[HG_EQACC_PER_THREAD];
+#pragma unroll
+        for (int k = 0; k < HG_EQACC_PER_THREAD; k++) {
+            const size_t i = base + (size_t)k * blockDim.x;
+            lo[k] = hi[k] = FP::x_zero();
+            if (i < it.n) { lo[k] = it.eq0[i & (nlo - 1)]; hi[k] = it.eq0[nlo + (i >> it.lo_bits)]; }
+        }
+#pragma unroll
+        for (int k = 0; k < HG_EQACC_PER_THREAD; k++) {
+            const size_t i = base + (size_t)k * blockDim.x;
+            if (i < it.n) it.w[i] = FP::fmul(lo[k], hi[k]);
+        }
+        return;
+    }
 #pragma unroll 2
     for (int k = 0; k < HG_EQACC_PER_THREAD; k++) {
         const size_t i = base + (size_t)k * blockDim.x;
