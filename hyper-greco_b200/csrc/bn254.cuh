@@ -213,7 +213,8 @@ struct FrField {
     static constexpr int FIELD_ID = 1;
     static constexpr int B_LIMBS = 4, X_LIMBS = 4;
     static constexpr int PLANES = 1;  // base planes per extension element
-    static constexpr int GP_TAIL_LOG = 5, GP_MIN_BLOCKS = 1, GP_R0_U = 2, GP_R0A_QPT = 1;
+    static constexpr int GP_TAIL_LOG = 5, GP_MIN_BLOCKS = 1, GP_R0_U = 2, GP_R0A_QPT = 1, GP_BLOCK = 256;
+    static constexpr double GP_TARGET = 2.0;
     HG_HD static B b_zero() { return fr_zero(); }
     HG_HD static B b_one() { return fr_one(); }
     HG_HD static B b_from_u64(u64 x) { return fr_from_u64(x); }

@@ -24,7 +24,8 @@ struct GlField {
     HG_HD static B root_of_unity() { return 0x185629dcda58878cULL; }  // 7^((p-1)/2^32), goldilocks ROOT_OF_UNITY (A9)
     static constexpr int TWO_ADICITY = 32;
     static constexpr int PLANES = 2;  // base planes per extension element
-    static constexpr int GP_TAIL_LOG = 6, GP_MIN_BLOCKS = 2, GP_R0_U = 4, GP_R0A_QPT = 4;
+    static constexpr int GP_TAIL_LOG = 6, GP_MIN_BLOCKS = 2, GP_R0_U = 4, GP_R0A_QPT = 4, GP_BLOCK = 128;
+    static constexpr double GP_TARGET = 0.25;  // CTAs per SM (of 256 threads) from which a layer runs with one term group (prover.cuh)
     HG_HD static bool b_eq(B a, B b) { return a == b; }
     HG_HD static B plane(X a, int p) { return p ? a.c1 : a.c0; }
     HG_HD static X from_planes(const B* p) { return gl2_make(p[0], p[1]); }

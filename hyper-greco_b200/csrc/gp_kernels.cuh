@@ -202,10 +202,8 @@ namespace hg {
 // table length at which a layer moves to the shared-memory tail kernel: FP::GP_TAIL_LOG (64 elements of 16 B for
 // Goldilocks, 32 elements of 32 B for BN254: 2*m tables * 1.5 * that must fit 227 KB)
 constexpr int HG_TAIL_THREADS = 512;
-// threads per CTA of the batched streaming kernels (same registers per thread: HG_BLOCK / HG_GP_BLOCK times more CTAs per SM)
-#ifndef HG_GP_BLOCK
-#define HG_GP_BLOCK 128
-#endif
+// threads per CTA of the batched streaming kernels: FP::GP_BLOCK (128 for Goldilocks: same registers per thread, twice the CTAs
+// per SM, 3 % faster; 256 for BN254)
 #ifndef HG_GP_PREFETCH
 #define HG_GP_PREFETCH 1
 #endif
@@ -304,7 +302,7 @@ template <class FP> __device__ __forceinline__ int gp_find_item(const GpItem<FP>
 //     computed as sum_i c_i * D_i with the base-field dot products D_i = sum_b t_0(2b) parent_i(2b) (resp. 2b+1): per entry
 //     one unreduced 64x64 multiply-add; c_i is applied once per term and thread.
 template <class FP>
-__global__ void __launch_bounds__(HG_GP_BLOCK, 2 * (HG_BLOCK / HG_GP_BLOCK)) k_gp_r0a_multi(const GpItem<FP>* __restrict__ items, int nitems) {
+__global__ void __launch_bounds__(FP::GP_BLOCK, 2 * (HG_BLOCK / FP::GP_BLOCK)) k_gp_r0a_multi(const GpItem<FP>* __restrict__ items, int nitems) {
     typedef typename FP::B B;
     typedef typename FP::X X;
     constexpr int QPT = FP::GP_R0A_QPT;  // quads (4 consecutive entries = two pairs) per thread and term
@@ -349,7 +347,7 @@ __global__ void __launch_bounds__(HG_GP_BLOCK, 2 * (HG_BLOCK / HG_GP_BLOCK)) k_g
 }
 // (b) h(inf) and h(-1) from the slopes / values at -1 of t_0, l_i, r_i                       -> msg[1], msg[2]
 template <class FP, int U>
-__global__ void __launch_bounds__(HG_GP_BLOCK, FP::GP_MIN_BLOCKS * (HG_BLOCK / HG_GP_BLOCK)) k_gp_r0_multi(const GpItem<FP>* __restrict__ items, int nitems) {
+__global__ void __launch_bounds__(FP::GP_BLOCK, FP::GP_MIN_BLOCKS * (HG_BLOCK / FP::GP_BLOCK)) k_gp_r0_multi(const GpItem<FP>* __restrict__ items, int nitems) {
     typedef typename FP::B B;
     typedef typename FP::X X;
     constexpr int NP = 2;
@@ -404,7 +402,7 @@ __global__ void __launch_bounds__(HG_GP_BLOCK, FP::GP_MIN_BLOCKS * (HG_BLOCK / H
 }
 
 template <class FP, class TIN, bool SCALE>
-__global__ void __launch_bounds__(HG_GP_BLOCK, FP::GP_MIN_BLOCKS * (HG_BLOCK / HG_GP_BLOCK)) k_gp_fold_multi(const GpItem<FP>* __restrict__ items, int nitems) {
+__global__ void __launch_bounds__(FP::GP_BLOCK, FP::GP_MIN_BLOCKS * (HG_BLOCK / FP::GP_BLOCK)) k_gp_fold_multi(const GpItem<FP>* __restrict__ items, int nitems) {
     typedef typename FP::X X;
     constexpr int NP = 3;
     const GpItem<FP> it = items[gp_find_item<FP>(items, nitems)];

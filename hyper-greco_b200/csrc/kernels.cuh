@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(HG_BLOCK) k_dot_eq(const T* __restrict__ table
     const T* t = tables + (size_t)blockIdx.y * stride;
     const size_t nlo = (size_t)1 << lo_bits, nhi = n >> lo_bits;
     X acc[1] = {FP::x_zero()};
-    if (nlo == 16 * (size_t)blockDim.x) {
+    if (sizeof(X) <= 16 && nlo == 16 * (size_t)blockDim.x) {  // (64 registers of cached eq_lo for Goldilocks; too many for a 32-byte field)
         // the usual shape (2^12 low entries, 256 threads): a thread always meets the same 16 entries of eq_lo, so they live in
         // registers for the whole launch and a row costs only its own 4 loads of 4 table entries, all issued up front
         X el[4][4];
@@ -309,6 +309,17 @@ __global__ void k_hash_rw_up(const u16* __restrict__ dims, const u32* __restrict
         FP::bacc_mad(acc, FP::b_from_u64(ts[q]), gamma2);
         return FP::b_sub(FP::b_add(FP::bacc_reduce(acc), FP::b_from_u64(dm[q])), tau);
     };
+    if constexpr (sizeof(B) > 8) {  // wide fields: one row per thread (register pressure)
+        for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < h; j += (size_t)gridDim.x * blockDim.x) {
+            B r0 = hash(j), r1 = hash(j + h);
+            B w0 = FP::b_add(r0, gamma2), w1 = FP::b_add(r1, gamma2);
+            V[(size_t)pos * R + j] = r0; V[(size_t)pos * R + j + h] = r1;
+            V[(size_t)(m + pos) * R + j] = w0; V[(size_t)(m + pos) * R + j + h] = w1;
+            up[(size_t)pos * h + j] = FP::fmul(r0, r1);
+            up[(size_t)(m + pos) * h + j] = FP::fmul(w0, w1);
+        }
+        return;
+    }
     // two neighbouring rows per thread: 16-byte stores of the bottom layer and of layer 1
     const size_t j0 = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
     if (j0 >= h) return;

@@ -1135,9 +1135,9 @@ template <class FP> class LassoNodeDev {
         static const int env_maxbx = getenv("HG_GP_MAXBX") ? atoi(getenv("HG_GP_MAXBX")) : 4;
         // measured optimum: one term group (every thread loops over all terms of its pairs and reuses t_0) as soon as a table gives
         // ~37 CTAs; smaller layers get term groups so that no layer runs on fewer CTAs than that
-        static const double env_target = getenv("HG_GP_TARGET") ? atof(getenv("HG_GP_TARGET")) : 0.25;
-        const int target_blocks = std::max(1, (int)(ctx_->sm_count * env_target * (HG_BLOCK / HG_GP_BLOCK)));
-        const size_t gp_max_bx = (size_t)ctx_->sm_count * env_maxbx * (HG_BLOCK / HG_GP_BLOCK);
+        static const double env_target = getenv("HG_GP_TARGET") ? atof(getenv("HG_GP_TARGET")) : FP::GP_TARGET;
+        const int target_blocks = std::max(1, (int)(ctx_->sm_count * env_target * (HG_BLOCK / FP::GP_BLOCK)));
+        const size_t gp_max_bx = (size_t)ctx_->sm_count * env_maxbx * (HG_BLOCK / FP::GP_BLOCK);
         for (int r = 0; r <= maxJ; r++) {
             int blk = 0;
             size_t part_off = 0;
@@ -1167,7 +1167,7 @@ template <class FP> class LassoNodeDev {
                     round_bytes[r] += (size_t)(2 * nown + it.write_t0) * (it.n_in * (r == 1 ? sizeof(B) : sizeof(X)) + (it.n_in / 2) * sizeof(X));
                     (void)ntab;
                 }
-                size_t b = (threads_x + HG_GP_BLOCK - 1) / HG_GP_BLOCK;
+                size_t b = (threads_x + FP::GP_BLOCK - 1) / FP::GP_BLOCK;
                 if (b < 1) b = 1;
                 if (b > gp_max_bx) b = gp_max_bx;
                 int g = (int)std::min<size_t>((size_t)nown, std::max<size_t>(1, ((size_t)target_blocks + b - 1) / b));
@@ -1183,7 +1183,7 @@ template <class FP> class LassoNodeDev {
                 rounds[r].push_back(it);
                 if (r == 0) {  // the parent-layer half: 4 pairs per thread, term groups until the item has ~target blocks
                     GpItem<FP> a = it;
-                    size_t ba = (j.n / 4 + FP::GP_R0A_QPT * HG_GP_BLOCK - 1) / (FP::GP_R0A_QPT * HG_GP_BLOCK);  // GP_R0A_QPT quads of parent entries per thread and term
+                    size_t ba = (j.n / 4 + FP::GP_R0A_QPT * FP::GP_BLOCK - 1) / (FP::GP_R0A_QPT * FP::GP_BLOCK);  // GP_R0A_QPT quads of parent entries per thread and term
                     if (ba < 1) ba = 1;
                     if (ba > gp_max_bx) ba = gp_max_bx;
                     int ga = (int)std::min<size_t>((size_t)nown, std::max<size_t>(1, ((size_t)target_blocks + ba - 1) / ba));
@@ -1250,13 +1250,13 @@ template <class FP> class LassoNodeDev {
             const GpItem<FP>* di = (const GpItem<FP>*)(d_desc_.p + r_off[r]);
             if (r == 0 && !round0a.empty()) {
                 KernelScope ka(ctx_, KC_SC_GP, 0);  // reads the parent layer: no algorithmic bytes of its own (SURVEY.md 8d counts round 0 once)
-                k_gp_r0a_multi<FP><<<blk0a, HG_GP_BLOCK, 0, s>>>((const GpItem<FP>*)(d_desc_.p + a_off), (int)round0a.size());
+                k_gp_r0a_multi<FP><<<blk0a, FP::GP_BLOCK, 0, s>>>((const GpItem<FP>*)(d_desc_.p + a_off), (int)round0a.size());
                 HG_LAUNCH_CHECK();
             }
             KernelScope ks(ctx_, KC_SC_GP, round_bytes[r]);
-            if (r == 0) k_gp_r0_multi<FP, FP::GP_R0_U><<<grid, HG_GP_BLOCK, 0, s>>>(di, ni);
-            else if (r == 1) k_gp_fold_multi<FP, B, true><<<grid, HG_GP_BLOCK, 0, s>>>(di, ni);
-            else k_gp_fold_multi<FP, X, false><<<grid, HG_GP_BLOCK, 0, s>>>(di, ni);
+            if (r == 0) k_gp_r0_multi<FP, FP::GP_R0_U><<<grid, FP::GP_BLOCK, 0, s>>>(di, ni);
+            else if (r == 1) k_gp_fold_multi<FP, B, true><<<grid, FP::GP_BLOCK, 0, s>>>(di, ni);
+            else k_gp_fold_multi<FP, X, false><<<grid, FP::GP_BLOCK, 0, s>>>(di, ni);
             HG_LAUNCH_CHECK();
         }
         {
