@@ -1242,7 +1242,7 @@ template <class FP> class LassoNodeDev {
         if (off > h_desc_.n) throw std::runtime_error("run_gp_batch: descriptor staging overflow");
         HG_CUDA(cudaMemcpyAsync(d_desc_.p, h_desc_.p, off, cudaMemcpyHostToDevice, s));
         // launches
-        HG_K(ctx_, KC_MISC, 0, k_gp_coeffs_multi<FP><<<nl, 32, 0, s>>>((const GpCoeffItem<FP>*)(d_desc_.p + c_off), wo.a5_ascending));
+        HG_K(ctx_, KC_MISC, 0, k_gp_coeffs_multi<FP><<<nl, 64, 0, s>>>((const GpCoeffItem<FP>*)(d_desc_.p + c_off), wo.a5_ascending));
         for (size_t r = 0; r < rounds.size(); r++) {
             if (rounds[r].empty()) continue;
             const auto& last = rounds[r].back();
