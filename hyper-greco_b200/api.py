@@ -30,7 +30,7 @@ SYMBOLS = [
     "hg_lasso_pp_lookup_index", "hg_lasso_pp_memory_maps", "hg_lasso_pp_subtable_id", "hg_lasso_node_new", "hg_lasso_node_free",
     "hg_lasso_node_log2_input_size", "hg_lasso_node_device_bytes", "hg_lasso_node_prove", "hg_lasso_node_download_polys",
     "hg_lasso_node_num_chunks", "hg_lasso_node_timing", "hg_lasso_node_shard_words", "hg_lasso_node_prove_shard", "hg_lasso_node_emit_shard",
-    "hg_shard_merge", "hg_sumcheck_prove", "hg_mle_eval_batch", "hg_ntt", "hg_bfv_evaluate", "hg_field_selftest",
+    "hg_shard_merge", "hg_lasso_node_verify", "hg_sumcheck_prove", "hg_mle_eval_batch", "hg_ntt", "hg_bfv_evaluate", "hg_field_selftest",
     "hg_circuit_new", "hg_circuit_free", "hg_circuit_insert_input", "hg_circuit_insert_fft", "hg_circuit_insert_lasso", "hg_circuit_insert_vanilla",
     "hg_circuit_connect", "hg_circuit_evaluate", "hg_circuit_evaluate_host", "hg_circuit_node_value", "hg_gkr_prove", "hg_gkr_timing", "hg_gkr_num_challenges", "hg_gkr_num_inputs", "hg_gkr_num_input_claims",
     "hg_gkr_input_claim_num_vars", "hg_gkr_input_claim",
@@ -112,6 +112,7 @@ def lib():
         L.hg_lasso_node_prove_shard.argtypes = [vp, vp, sz, i32, vp, i32, i32, vp, sz, C.POINTER(sz)]
         L.hg_lasso_node_emit_shard.argtypes = [vp, vp, sz, vp, vp]
         L.hg_shard_merge.argtypes = [i32, vp, vp, sz]
+        L.hg_lasso_node_verify.argtypes = [vp, sz, vp, vp, vp, vp]
         L.hg_sumcheck_prove.argtypes = [vp, i32, sz, sz, vp, vp, vp, vp, i32, vp, vp]
         L.hg_mle_eval_batch.argtypes = [vp, vp, sz, sz, sz, vp, vp]
         L.hg_field_selftest.argtypes = [vp, i32, vp, vp, sz, vp]
@@ -480,6 +481,18 @@ class LassoNode:
             self.free()
         except Exception:
             pass
+
+
+def lasso_node_verify(preprocessing: "LassoPreprocessing", num_vars: int, transcript: "Keccak256Transcript", options=None):
+    """Node::verify_claim_reduction on the host (no GPU): reads the node's messages from a transcript built with
+    Keccak256Transcript(field, proof=...). Returns (point [num_vars, el], claimed_sum [el]); raises HgError when the reference
+    would return Err / panic. options = (a3_wire, a3_h1, a5_ascending) or None."""
+    el = LIMBS[transcript.field] * DEGREE[transcript.field]
+    pt = np.zeros((num_vars, el), np.uint64)
+    val = np.zeros(el, np.uint64)
+    opt = None if options is None else np.array(options, np.int32)
+    _chk(lib().hg_lasso_node_verify(preprocessing.h, num_vars, transcript.h, None if opt is None else _p(opt), _p(pt), _p(val)))
+    return pt, val
 
 
 def shard_merge(field: int, acc, part):

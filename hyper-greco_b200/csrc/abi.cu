@@ -12,6 +12,7 @@
 #include "bfv.cuh"
 #include "gkr_dev.cuh"
 #include "prover.cuh"
+#include "lasso_verify.hpp"
 
 using namespace hg;
 
@@ -262,6 +263,7 @@ struct IFieldOps {
     virtual void selftest(DeviceCtx* ctx, int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) = 0;
     virtual void encode(DeviceCtx* ctx, void* d, size_t n, bool decode) = 0;
     virtual void shard_merge(uint64_t* acc, const uint64_t* part, size_t n_words) = 0;
+    virtual void lasso_verify(const LassoPreprocessing& pp, int num_vars, ITranscript* t, const WireOptions& wo, uint64_t* out_point, uint64_t* out_value) = 0;
     virtual size_t base_bytes() const = 0;
 };
 template <class FP> struct FieldOpsT : IFieldOps {
@@ -273,6 +275,14 @@ template <class FP> struct FieldOpsT : IFieldOps {
     ILassoNode* new_lasso_node(DeviceCtx* ctx, const LassoPreprocessing& pp, int nv, const std::vector<uint8_t>& rows) override { return new LassoNodeT<FP>(ctx, pp, nv, rows); }
     ICircuit* new_circuit(DeviceCtx* ctx) override { return new CircuitT<FP>(ctx, eng(ctx)); }
     size_t base_bytes() const override { return sizeof(B); }
+    void lasso_verify(const LassoPreprocessing& pp, int num_vars, ITranscript* t, const WireOptions& wo, uint64_t* out_point, uint64_t* out_value) override {
+        LassoVerifier<FP> v(pp, num_vars, wo);
+        std::vector<X> r;
+        X sum;
+        v.verify(*(Keccak256Transcript<FP>*)t->raw(), &r, &sum);
+        if (out_point) for (size_t i = 0; i < r.size(); i++) FP::x_to_limbs(r[i], out_point + FP::X_LIMBS * i);
+        if (out_value) FP::x_to_limbs(sum, out_value);
+    }
     void shard_merge(uint64_t* acc, const uint64_t* part, size_t n_words) override {
         constexpr size_t XW = sizeof(X) / sizeof(uint64_t);
         if (n_words % XW) throw std::runtime_error("shard_merge: truncated message buffer");
@@ -684,6 +694,13 @@ int hg_lasso_node_prove_shard(hg_lasso_node* node, const void* inputs, size_t n_
 }
 int hg_lasso_node_emit_shard(hg_lasso_node* node, const uint64_t* merged_words, size_t n_words, uint64_t* out_point, uint64_t* out_value) {
     HG_TRY({ node->n->emit_shard(merged_words, n_words, out_point, out_value); })
+}
+int hg_lasso_node_verify(const hg_lasso_pp* pp, size_t num_vars, hg_transcript* t, const int* options3, uint64_t* out_point, uint64_t* out_value) {
+    HG_TRY({
+        WireOptions wo;
+        if (options3) { wo.a3_wire = options3[0]; wo.a3_h1 = options3[1]; wo.a5_ascending = options3[2]; }
+        ops_for_field(t->t->field_id)->lasso_verify(pp->pp, (int)num_vars, t->t.get(), wo, out_point, out_value);
+    })
 }
 int hg_shard_merge(int field, uint64_t* acc_words, const uint64_t* part_words, size_t n_words) {
     HG_TRY({ ops_for_field(field)->shard_merge(acc_words, part_words, n_words); })

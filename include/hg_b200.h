@@ -121,6 +121,12 @@ size_t hg_lasso_node_device_bytes(const hg_lasso_node* node);
  * out_point[num_vars] / out_value hold the single EvalClaim the node returns for its input (lasso.rs:97,113). */
 int hg_lasso_node_prove(hg_lasso_node* node, const void* inputs, size_t n_inputs, int inputs_on_device, hg_transcript* t, int mode,
                         uint64_t* out_point, uint64_t* out_value);
+/* Node::verify_claim_reduction (lasso/src/lasso.rs:116-139; memory_checking/verifier.rs:61-95,130-235) on the HOST: reads the node's
+ * part of the proof from `t` (a transcript made by hg_transcript_from_proof, positioned where the node starts and having
+ * squeezed what the prover had squeezed before it), checks the grand-product base relation and the memory hashes, and returns
+ * the node's claim (point of num_vars challenges, claimed sum). options3 = {HG_OPT_A3_WIRE, HG_OPT_A3_H1, HG_OPT_A5_ASCENDING}
+ * values or NULL for the defaults. Needs no GPU and no context. Error (non-zero) = the reference's Err / panic. */
+int hg_lasso_node_verify(const hg_lasso_pp* pp, size_t num_vars, hg_transcript* t, const int* options3, uint64_t* out_point, uint64_t* out_value);
 /* ---- one proof over several GPUs. Every message of the node is either a sum over the 2m grand-product
  * vectors (round polynomials) or belongs to a single vector / memory (roots, evaluations, openings), and the verifier's
  * challenges do not depend on the messages. Rank r of `world` computes the part owned by r from its own

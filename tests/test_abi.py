@@ -92,3 +92,54 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in src.lower().replace("no oracle", ""), os.path.join(dp, f)
+
+
+def test_host_verifier_accepts_golden_lasso_proofs_and_rejects_tampering():
+    """hg_lasso_node_verify (host C++, no GPU): the product's own restatement of Node::verify_claim_reduction
+    (lasso.rs:116-139, verifier.rs:61-95,130-235) accepts the committed golden proofs of the reference's n=1024 witnesses in
+    both fields, returns the claim the prover returned, and rejects a flipped byte / a truncated proof."""
+    import json
+    import os
+    import sys
+    sys.path.insert(0, ROOT)
+    import hyper_greco_b200  # noqa: F401
+    from hyper_greco_b200 import api, params, witness
+    name = "1024_1x27_65537"
+    P = params.PARAMS[name]
+    bounds, nv = witness.lasso_lookup_bounds(P), witness.lasso_num_vars(P)
+    pp = api.LassoPreprocessing.preprocess(bounds)
+    gdir = os.path.join(ROOT, "tests", "golden")
+    meta = json.load(open(os.path.join(gdir, "golden_proofs.json")))["files"]
+    for field, tag in ((api.GOLDILOCKS, "goldilocks"), (api.BN254, "bn254")):
+        fname = f"proof_{tag}_lasso_node_{name}.bin"
+        proof = open(os.path.join(gdir, fname), "rb").read()
+        tr = api.Keccak256Transcript(field, proof)
+        pt, val = api.lasso_node_verify(pp, nv, tr)
+        assert tr.num_squeezed == meta[fname]["base_squeezes"]
+        assert pt.shape[0] == nv and val.any()
+        # the claim is (r, claimed_sum): claimed_sum is the first element of the proof (lasso.rs:269), big-endian limbs
+        el = pt.shape[1]
+        first = np.frombuffer(proof[: 8 * el], dtype=">u8")
+        if field == api.GOLDILOCKS:
+            assert (first == val).all()
+        else:
+            assert (first[::-1] == val).all()
+        # what the reference verifier checks: the grand-product base relation and the hash relations of the openings
+        # (verifier.rs:79-92,203-211). The openings are the last elements of the node's proof:
+        for pos in (len(proof) - 5, len(proof) - 8 * el - 3, len(proof) - 3 * 8 * el - 1):
+            bad = bytearray(proof)
+            bad[pos] ^= 0x10
+            with pytest.raises(api.HgError):
+                api.lasso_node_verify(pp, nv, api.Keccak256Transcript(field, bytes(bad)))
+        # the claimed sum itself is NOT checked by the node (the collation sumcheck result is discarded, lasso.rs:129-133,
+        # SURVEY Q11): a changed claimed sum is accepted here and returned, to be caught by the caller's input check
+        bad = bytearray(proof)
+        bad[8 * el - 1] ^= 0x01
+        pt2, val2 = api.lasso_node_verify(pp, nv, api.Keccak256Transcript(field, bytes(bad)))
+        assert (pt2 == pt).all() and not (val2 == val).all()
+        with pytest.raises(api.HgError):
+            api.lasso_node_verify(pp, nv, api.Keccak256Transcript(field, proof[:-16]))
+        bad = bytearray(proof)
+        bad[0:8] = b"\xff" * 8  # first base element = 2^64 - 1 (or >= 2^255): not a canonical field element (transcript.rs:162-170)
+        with pytest.raises(api.HgError):
+            api.lasso_node_verify(pp, nv, api.Keccak256Transcript(field, bytes(bad)))

@@ -215,6 +215,9 @@ def test_lasso_node_full_size_properties(api, ctx, oracle):
     proof = tr.into_proof()
     r, s, used = oracle.lasso_verify(0, opp, nv, proof)
     assert used == len(proof) and (r == pt.reshape(-1)).all() and (s == val).all()
+    # the product's own host verifier (hg_lasso_node_verify) agrees with the oracle's
+    vpt, vval = api.lasso_node_verify(pp, nv, api.Keccak256Transcript(api.GOLDILOCKS, proof))
+    assert (vpt == pt).all() and (vval == val).all()
     padded = np.zeros(1 << nv, np.uint64)
     padded[: inp.size] = inp
     assert (oracle.mle_eval(0, padded, nv, pt.reshape(-1)) == val).all()
