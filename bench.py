@@ -423,7 +423,7 @@ def run_shard(args):
             return tr.into_proof()
         return None
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 3) + 20):   # + device spin-up, as in the main arm
         proof = step()
     barrier()
     w0 = time.perf_counter()

@@ -265,6 +265,11 @@ __global__ void __launch_bounds__(HG_BLOCK) k_dot_eq(const T* __restrict__ table
     block_reduce_finalize<FP, 1>(acc, partials, counter, out);
 }
 
+// Vectors a device needs when one proof is split over several devices (LassoNodeDev::prove_shard): the ones it owns and
+// vector 0, whose first half is the common factor t_0 of every term. All of them when the proof is not split.
+struct VecRange { int lo, hi; };
+__device__ __forceinline__ bool vec_needed(VecRange r, int v) { return v == 0 || (v >= r.lo && v < r.hi); }
+
 // two consecutive base elements with one store where the type allows it (p 16-byte aligned)
 __device__ __forceinline__ void store_pair(u64* p, u64 a, u64 b) { *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(a, b); }
 template <class T> __device__ __forceinline__ void store_pair(T* p, const T& a, const T& b) { p[0] = a; p[1] = b; }
@@ -294,10 +299,12 @@ template <class FP>
 __global__ void k_hash_rw_up(const u16* __restrict__ dims, const u32* __restrict__ read_cts, const typename FP::B* __restrict__ E,
                              const int* __restrict__ pos_mem, const int* __restrict__ pos_dim, const int* __restrict__ pos_slot,
                              const typename FP::X* __restrict__ gamma_tau, size_t R, int m, typename FP::B* __restrict__ V,
-                             typename FP::B* __restrict__ up) {
+                             typename FP::B* __restrict__ up, VecRange own) {
     typedef typename FP::B B;
     const size_t h = R / 2;
     const int pos = blockIdx.y;
+    const bool need_r = vec_needed(own, pos), need_w = vec_needed(own, m + pos);  // vector pos = reads, m + pos = writes of this memory
+    if (!need_r && !need_w) return;
     const B gamma = FP::x_base0(gamma_tau[0]), tau = FP::x_base0(gamma_tau[1]), gamma2 = FP::b_mul(gamma, gamma);
     const u16* dm = dims + (size_t)pos_dim[pos] * R;
     const u32* ts = read_cts + (size_t)pos_slot[pos] * R;
@@ -313,10 +320,8 @@ __global__ void k_hash_rw_up(const u16* __restrict__ dims, const u32* __restrict
         for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < h; j += (size_t)gridDim.x * blockDim.x) {
             B r0 = hash(j), r1 = hash(j + h);
             B w0 = FP::b_add(r0, gamma2), w1 = FP::b_add(r1, gamma2);
-            V[(size_t)pos * R + j] = r0; V[(size_t)pos * R + j + h] = r1;
-            V[(size_t)(m + pos) * R + j] = w0; V[(size_t)(m + pos) * R + j + h] = w1;
-            up[(size_t)pos * h + j] = FP::fmul(r0, r1);
-            up[(size_t)(m + pos) * h + j] = FP::fmul(w0, w1);
+            if (need_r) { V[(size_t)pos * R + j] = r0; V[(size_t)pos * R + j + h] = r1; up[(size_t)pos * h + j] = FP::fmul(r0, r1); }
+            if (need_w) { V[(size_t)(m + pos) * R + j] = w0; V[(size_t)(m + pos) * R + j + h] = w1; up[(size_t)(m + pos) * h + j] = FP::fmul(w0, w1); }
         }
         return;
     }
@@ -337,13 +342,16 @@ __global__ void k_hash_rw_up(const u16* __restrict__ dims, const u32* __restrict
     B* ur = up + (size_t)pos * h;
     B* uw = up + (size_t)(m + pos) * h;
     if (j0 + 1 < h) {
+        if (need_r) {
 #pragma unroll
-        for (int s = 0; s < 2; s++) {
-            store_pair(Vr + j0 + s * h, rd[0][s], rd[1][s]);
-            store_pair(Vw + j0 + s * h, wr[0][s], wr[1][s]);
+            for (int s = 0; s < 2; s++) store_pair(Vr + j0 + s * h, rd[0][s], rd[1][s]);
+            store_pair(ur + j0, FP::fmul(rd[0][0], rd[0][1]), FP::fmul(rd[1][0], rd[1][1]));
         }
-        store_pair(ur + j0, FP::fmul(rd[0][0], rd[0][1]), FP::fmul(rd[1][0], rd[1][1]));
-        store_pair(uw + j0, FP::fmul(wr[0][0], wr[0][1]), FP::fmul(wr[1][0], wr[1][1]));
+        if (need_w) {
+#pragma unroll
+            for (int s = 0; s < 2; s++) store_pair(Vw + j0 + s * h, wr[0][s], wr[1][s]);
+            store_pair(uw + j0, FP::fmul(wr[0][0], wr[0][1]), FP::fmul(wr[1][0], wr[1][1]));
+        }
     } else {  // odd tail (h is a power of two >= 2 in practice, so this is h == 1 only)
         for (int s = 0; s < 2; s++) { Vr[j0 + s * h] = rd[0][s]; Vw[j0 + s * h] = wr[0][s]; }
         ur[j0] = FP::fmul(rd[0][0], rd[0][1]);
@@ -354,11 +362,11 @@ __global__ void k_hash_rw_up(const u16* __restrict__ dims, const u32* __restrict
 template <class FP>
 __global__ void k_hash_if(const typename FP::B* __restrict__ subtables, const u32* __restrict__ final_cts, const int* __restrict__ pos_sub,
                           const int* __restrict__ pos_slot, const typename FP::X* __restrict__ gamma_tau, size_t M, int m,
-                          typename FP::B* __restrict__ V) {
+                          typename FP::B* __restrict__ V, VecRange own) {
     typedef typename FP::B B;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int pos = blockIdx.y;
-    if (i >= M) return;
+    if (i >= M || !(vec_needed(own, pos) || vec_needed(own, m + pos))) return;
     const B gamma = FP::x_base0(gamma_tau[0]), tau = FP::x_base0(gamma_tau[1]), gamma2 = FP::b_mul(gamma, gamma);
     B v = subtables[(size_t)pos_sub[pos] * M + i];
     B in = FP::b_sub(FP::b_add(FP::b_from_u64(i), FP::b_mul(v, gamma)), tau);
@@ -369,9 +377,9 @@ __global__ void k_hash_if(const typename FP::B* __restrict__ subtables, const u3
 
 // K7 product-tree layer (prover.rs:332-354): out[i][k] = in[i][k] * in[i][k + h]; halves = top index bit
 template <class FP>
-__global__ void k_tree_up(const typename FP::B* __restrict__ in, typename FP::B* __restrict__ out, size_t h) {
+__global__ void k_tree_up(const typename FP::B* __restrict__ in, typename FP::B* __restrict__ out, size_t h, VecRange own) {
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= h) return;
+    if (k >= h || !vec_needed(own, blockIdx.y)) return;
     const typename FP::B* v = in + (size_t)blockIdx.y * 2 * h;
     out[(size_t)blockIdx.y * h + k] = FP::fmul(v[k], v[k + h]);
 }
@@ -379,8 +387,10 @@ __global__ void k_tree_up(const typename FP::B* __restrict__ in, typename FP::B*
 __device__ __forceinline__ void load_pair(const u64* p, u64& a, u64& b) { const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(p); a = t.x; b = t.y; }
 template <class T> __device__ __forceinline__ void load_pair(const T* p, T& a, T& b) { a = p[0]; b = p[1]; }
 template <class FP>
-__global__ void k_tree_up2(const typename FP::B* __restrict__ in, typename FP::B* __restrict__ out1, typename FP::B* __restrict__ out2, size_t q) {
+__global__ void k_tree_up2(const typename FP::B* __restrict__ in, typename FP::B* __restrict__ out1, typename FP::B* __restrict__ out2, size_t q,
+                           VecRange own) {
     typedef typename FP::B B;
+    if (!vec_needed(own, blockIdx.y)) return;
     const B* v = in + (size_t)blockIdx.y * 4 * q;
     B* o1 = out1 + (size_t)blockIdx.y * 2 * q;
     B* o2 = out2 + (size_t)blockIdx.y * q;
@@ -409,9 +419,10 @@ __global__ void k_tree_up2(const typename FP::B* __restrict__ in, typename FP::B
 // layer[k+1] = layer[k] + nvec * len(k).
 constexpr int HG_TREE_TAIL = 2048;
 template <class FP>
-__global__ void __launch_bounds__(256) k_tree_tail(typename FP::B* __restrict__ layer, int nvec, int len) {
+__global__ void __launch_bounds__(256) k_tree_tail(typename FP::B* __restrict__ layer, int nvec, int len, VecRange own) {
     typedef typename FP::B B;
     extern __shared__ __align__(16) unsigned char tree_smem[];
+    if (!vec_needed(own, blockIdx.x)) return;
     B* cur = reinterpret_cast<B*>(tree_smem);  // [len]
     const int vec = blockIdx.x;
     for (int e = threadIdx.x; e < len; e += blockDim.x) cur[e] = layer[(size_t)vec * len + e];

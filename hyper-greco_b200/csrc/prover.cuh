@@ -914,14 +914,14 @@ template <class FP> class LassoNodeDev {
             HG_K(ctx_, KC_HASH, (size_t)m * R * (2 + 4 + 4 * sizeof(B)),
                  k_hash_rw_up<FP><<<dim3((unsigned)((R / 4 + HG_BLOCK - 1) / HG_BLOCK + (R < 4 ? 1 : 0)), m), HG_BLOCK, 0, s>>>(
                      d_dims_.p, d_read_cts_.p, d_E_.p, d_pos_mem_.p, d_pos_dim_.p, d_pos_slot_.p, ch.d_chal(gt_idx), R, m, d_tree1_.p,
-                     d_tree1_.p + (size_t)2 * m * R));
+                     d_tree1_.p + (size_t)2 * m * R, own_range(2 * m)));
         else
             HG_K(ctx_, KC_HASH, (size_t)m * R * (2 + 4 + 3 * sizeof(B)),
                  k_hash_rw<FP><<<dim3((unsigned)((R + HG_BLOCK - 1) / HG_BLOCK), m), HG_BLOCK, 0, s>>>(d_dims_.p, d_read_cts_.p, d_E_.p, d_pos_mem_.p, d_pos_dim_.p,
                                                                                                        d_pos_slot_.p, ch.d_chal(gt_idx), R, m, d_tree1_.p));
         HG_K(ctx_, KC_HASH, (size_t)m * M * (4 + 3 * sizeof(B)),
              k_hash_if<FP><<<dim3((unsigned)((M + HG_BLOCK - 1) / HG_BLOCK), m), HG_BLOCK, 0, s>>>(d_subtables_.p, d_final_cts_.p, d_pos_sub_.p, d_pos_slot_.p,
-                                                                                                   ch.d_chal(gt_idx), M, m, d_tree2_.p));
+                                                                                                   ch.d_chal(gt_idx), M, m, d_tree2_.p, own_range(2 * m)));
         size_t x_idx = 0, y_idx = 0;
         std::vector<GpLayerJob<FP>> jobs;
         std::vector<GpLayerJob<FP>>* batch = (mode == kModePrefetch) ? &jobs : nullptr;
@@ -1023,17 +1023,17 @@ template <class FP> class LassoNodeDev {
             const size_t len_prev = N >> (k - 1);  // vector length of the layer this step reads
             if (len_prev <= (size_t)HG_TREE_TAIL && len_prev > 2) {  // the rest of the tree in one launch (shared memory)
                 HG_K(ctx_, KC_TREE, (size_t)nvec * len_prev * 2 * sizeof(B),
-                     k_tree_tail<FP><<<nvec, 256, len_prev * sizeof(B), s>>>(layer[k - 1], nvec, (int)len_prev));
+                     k_tree_tail<FP><<<nvec, 256, len_prev * sizeof(B), s>>>(layer[k - 1], nvec, (int)len_prev, own_range(nvec)));
                 break;
             }
             if (k + 1 < nvars) {  // two levels per launch: layer k is written and never re-read by the build
                 const size_t q = N >> (k + 1);
                 HG_K(ctx_, KC_TREE, (size_t)nvec * q * 7 * sizeof(B),
-                     k_tree_up2<FP><<<dim3((unsigned)(((q >= 2 ? q / 2 : q) + HG_BLOCK - 1) / HG_BLOCK), nvec), HG_BLOCK, 0, s>>>(layer[k - 1], layer[k], layer[k + 1], q));
+                     k_tree_up2<FP><<<dim3((unsigned)(((q >= 2 ? q / 2 : q) + HG_BLOCK - 1) / HG_BLOCK), nvec), HG_BLOCK, 0, s>>>(layer[k - 1], layer[k], layer[k + 1], q, own_range(nvec)));
                 k += 2;
             } else {
                 const size_t h = N >> k;
-                HG_K(ctx_, KC_TREE, (size_t)nvec * h * 3 * sizeof(B), k_tree_up<FP><<<dim3((unsigned)((h + HG_BLOCK - 1) / HG_BLOCK), nvec), HG_BLOCK, 0, s>>>(layer[k - 1], layer[k], h));
+                HG_K(ctx_, KC_TREE, (size_t)nvec * h * 3 * sizeof(B), k_tree_up<FP><<<dim3((unsigned)((h + HG_BLOCK - 1) / HG_BLOCK), nvec), HG_BLOCK, 0, s>>>(layer[k - 1], layer[k], h, own_range(nvec)));
                 k += 1;
             }
         }
@@ -1268,6 +1268,7 @@ template <class FP> class LassoNodeDev {
     }
 
     // vectors [own_begin, own_end) of a grand product belong to this device (all of them unless prove_shard is running)
+    VecRange own_range(int nvec) const { VecRange r; r.lo = own_begin(nvec); r.hi = own_end(nvec); return r; }
     int own_begin(int nvec) const { return (int)((size_t)nvec * shard_rank_ / shard_world_); }
     int own_end(int nvec) const { return (int)((size_t)nvec * (shard_rank_ + 1) / shard_world_); }
     int shard_rank_ = 0, shard_world_ = 1;
