@@ -37,10 +37,14 @@ __device__ __forceinline__ unsigned bitrev(unsigned x, int bits) { return bits ?
 // root table: tw[k*tw_stride] = w_n^k
 // All sizes are powers of two: index arithmetic is shifts and masks (a runtime division costs more than the butterfly).
 template <class FP>
-__device__ __forceinline__ void smem_ntt_dif(typename FP::B* s, int logn, int log_tile, int ts, const typename FP::B* __restrict__ tw, size_t tw_stride) {
+__device__ __forceinline__ void smem_ntt_dif(typename FP::B* s, int logn, int log_tile, int ts, const typename FP::B* __restrict__ tw_global, size_t tw_stride) {
     typedef typename FP::B B;
     const int n = 1 << logn, tmask = (1 << log_tile) - 1;
     const int nbf = (n >> 1) << log_tile;
+    // the n/2 twiddles of this transform size, once per CTA, behind the data tile (the launch reserves the space)
+    B* tw = s + (size_t)n * ts;
+    for (int k = threadIdx.x; k < (n >> 1); k += blockDim.x) tw[k] = tw_global[(size_t)k * tw_stride];
+    __syncthreads();
     for (int loglen = logn - 1; loglen >= 0; loglen--) {
         const int len = 1 << loglen;
         const int logstep = logn - 1 - loglen;  // exponent step of this stage = (n/2) / len
@@ -50,7 +54,7 @@ __device__ __forceinline__ void smem_ntt_dif(typename FP::B* s, int logn, int lo
             const B u = s[i * ts + c], v = s[(i + len) * ts + c];
             s[i * ts + c] = FP::b_add(u, v);
             const B d = FP::b_sub(u, v);
-            s[(i + len) * ts + c] = j ? FP::fmul(d, tw[((size_t)j << logstep) * tw_stride]) : d;
+            s[(i + len) * ts + c] = j ? FP::fmul(d, tw[j << logstep]) : d;
         }
         __syncthreads();
     }

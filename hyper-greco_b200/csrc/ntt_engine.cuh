@@ -28,7 +28,8 @@ template <class FP> class NttEngine {
         const int log_n1 = (log_n + 1) / 2, log_n2 = log_n - log_n1;
         const int n1 = 1 << log_n1, n2 = 1 << log_n2;
         const int tile_c = std::min(HG_NTT_TILE, n2), tile_r = std::min(HG_NTT_TILE, n1);
-        const size_t smem_c = (size_t)n1 * (tile_c | 1) * sizeof(B), smem_r = (size_t)n2 * (tile_r | 1) * sizeof(B);
+        // data tile + the n/2 twiddles of the in-tile transform
+        const size_t smem_c = ((size_t)n1 * (tile_c | 1) + n1 / 2 + 1) * sizeof(B), smem_r = ((size_t)n2 * (tile_r | 1) + n2 / 2 + 1) * sizeof(B);
         if (smem_c > 200 * 1024 || smem_r > 200 * 1024) throw std::runtime_error("hg_ntt: transform too large for the shared-memory tiles");
         HG_CUDA(cudaFuncSetAttribute(k_ntt_cols<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
         HG_CUDA(cudaFuncSetAttribute(k_ntt_rows<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
