@@ -607,8 +607,8 @@ template <class FP> class GkrCircuitDev {
             const size_t npairs = r == 0 ? it.n_in / 2 : it.n_in / 4;
             // several pairs per thread: the block-level reduction that ends every block costs about as much as eight pairs (measured optimum 8-16)
             static const size_t ppt_max = getenv("HG_PROD_PPT") ? (size_t)atoi(getenv("HG_PROD_PPT")) : 16;
-            const size_t ppt = std::max<size_t>(1, std::min<size_t>(ppt_max, round_pairs / ((size_t)HG_BLOCK * ctx_->sm_count * 4)));
-            size_t b = std::max<size_t>(1, std::min<size_t>((npairs + HG_BLOCK * ppt - 1) / (HG_BLOCK * ppt), (size_t)ctx_->sm_count * 16));
+            const size_t ppt = std::max<size_t>(1, std::min<size_t>(ppt_max, round_pairs / ((size_t)HG_PROD_BLOCK * ctx_->sm_count * 4)));
+            size_t b = std::max<size_t>(1, std::min<size_t>((npairs + HG_PROD_BLOCK * ppt - 1) / (HG_PROD_BLOCK * ppt), (size_t)ctx_->sm_count * 16 * (HG_BLOCK / HG_PROD_BLOCK)));
             it.nblk = (int)b; it.bx = (int)b; it.blk_start = blk;
             blk += it.nblk;
             it.partials = d_partials_.p + part_off;
@@ -622,9 +622,9 @@ template <class FP> class GkrCircuitDev {
         if (desc_off_ > h_desc_.n - (1 << 16)) { HG_CUDA(cudaStreamSynchronize(s)); desc_off_ = 0; }
         const ProdItem<FP>* di = stage(items);
         KernelScope ks(ctx_, KC_GKR_SC, bytes);
-        if (r == 0) k_prod_round_multi<FP, B, false><<<blk, HG_BLOCK, 0, s>>>(di, (int)items.size());
-        else if (r == 1) k_prod_round_multi<FP, B, true><<<blk, HG_BLOCK, 0, s>>>(di, (int)items.size());
-        else k_prod_round_multi<FP, X, true><<<blk, HG_BLOCK, 0, s>>>(di, (int)items.size());
+        if (r == 0) k_prod_round_multi<FP, B, false><<<blk, HG_PROD_BLOCK, 0, s>>>(di, (int)items.size());
+        else if (r == 1) k_prod_round_multi<FP, B, true><<<blk, HG_PROD_BLOCK, 0, s>>>(di, (int)items.size());
+        else k_prod_round_multi<FP, X, true><<<blk, HG_PROD_BLOCK, 0, s>>>(di, (int)items.size());
         HG_LAUNCH_CHECK();
         // linear layers: the table folded over the low log2(n_in) variables holds the evaluations of the inputs; it is the
         // output of round m = log2(n_in) and would be overwritten two rounds later, so it is copied out now

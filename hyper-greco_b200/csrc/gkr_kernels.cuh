@@ -237,8 +237,9 @@ __device__ __forceinline__ void prod_round_item(const ProdItem<FP>& it, unsigned
         }
     }
 }
+constexpr int HG_PROD_BLOCK = 128;  // threads per CTA of the streamed layer-sumcheck rounds
 template <class FP, class TIN, bool FOLD>
-__global__ void __launch_bounds__(HG_BLOCK, (FOLD || sizeof(typename FP::B) > 8) ? 1 : 3) k_prod_round_multi(const ProdItem<FP>* __restrict__ items, int nitems) {
+__global__ void __launch_bounds__(HG_PROD_BLOCK, ((FOLD || sizeof(typename FP::B) > 8) ? 1 : 3) * (HG_BLOCK / HG_PROD_BLOCK)) k_prod_round_multi(const ProdItem<FP>* __restrict__ items, int nitems) {
     typedef typename FP::X X;
     const ProdItem<FP> it = items[find_item(items, nitems)];
     const unsigned lb = blockIdx.x - it.blk_start;
