@@ -129,24 +129,26 @@ __global__ void k_polynomialize(const typename FP::B* __restrict__ inputs, size_
         d[c] = (l == 0xFF) ? 0 : (u16)v;
         dims[(size_t)c * R + j] = d[c];
     }
-    B s = FP::b_zero();
+    // sums of products are accumulated unreduced (field_policy.cuh): one reduction for S, one for the lookup output
+    typename FP::BAcc s = FP::bacc_zero();
     for (int mi = 0; mi < m; mi++) {
         B e = FP::b_zero();
-        if (l != 0xFF && ((meta->mem_used[mi] >> l) & 1)) e = subtables[(size_t)meta->mem_sub[mi] * M + d[meta->mem_dim[mi]]];
+        if (l != 0xFF && ((meta->mem_used[mi] >> l) & 1)) {
+            e = subtables[(size_t)meta->mem_sub[mi] * M + d[meta->mem_dim[mi]]];
+            FP::bacc_mad(s, coll_coeff[mi], e);
+        }
         E[(size_t)mi * R + j] = e;
-        s = FP::b_add(s, FP::b_mul(coll_coeff[mi], e));
     }
-    S[j] = s;
-    B o = FP::b_zero();
+    S[j] = FP::bacc_reduce(s);
+    typename FP::BAcc o = FP::bacc_zero();
     if (l != 0xFF) {
         int nm = meta->lookup_nmem[l];
         for (int t = 0; t < nm; t++) {
             int mi = meta->lookup_mem[l][t];
-            B e = subtables[(size_t)meta->mem_sub[mi] * M + d[meta->mem_dim[mi]]];
-            o = FP::b_add(o, FP::b_mul(wpow[t], e));
+            FP::bacc_mad(o, wpow[t], subtables[(size_t)meta->mem_sub[mi] * M + d[meta->mem_dim[mi]]]);
         }
     }
-    out[j] = o;
+    out[j] = FP::bacc_reduce(o);
 }
 
 // ---------------------------------------------------------------------------------------------------------
