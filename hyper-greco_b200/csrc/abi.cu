@@ -51,6 +51,7 @@ template <class FP> struct TranscriptT : ITranscript {
     Keccak256Transcript<FP> t;
     TranscriptT() { field_id = FP::FIELD_ID; }
     TranscriptT(const uint8_t* p, size_t n) : t(p, n) { field_id = FP::FIELD_ID; }
+    explicit TranscriptT(const TranscriptHooks& h) : t(h) { field_id = FP::FIELD_ID; }
     void squeeze(uint64_t* out) override { FP::x_to_limbs(t.squeeze_challenge(), out); }
     void write(const uint64_t* in) override { t.write_felt_ext(FP::x_from_limbs(in)); }
     void read(uint64_t* out) override { FP::x_to_limbs(t.read_felt_ext(), out); }
@@ -331,7 +332,8 @@ template <class FP> struct FieldOpsT : IFieldOps {
         HG_CUDA(cudaMemset(counters.p, 0, counters.bytes()));
         sc.partials = partials.p; sc.counters = counters.p;
         Channel<FP> ch(dev, num_vars + 1, 4 * num_vars + ntab + 4);
-        ch.begin((Keccak256Transcript<FP>*)t->raw(), mode == HG_MODE_INTERACTIVE ? kModeInteractive : kModePrefetch, num_vars);
+        Keccak256Transcript<FP>* trp = (Keccak256Transcript<FP>*)t->raw();
+        ch.begin(trp, (mode == HG_MODE_INTERACTIVE || !trp->prefetch_legal()) ? kModeInteractive : kModePrefetch, num_vars);
         auto st = std::make_shared<ScHostState<FP>>();
         st->claim = FP::x_from_limbs(claim_ext);
         size_t first = 0, eo = 0;
@@ -584,6 +586,20 @@ int hg_transcript_from_proof(int field_id, const uint8_t* proof, size_t len, hg_
     HG_TRY({
         std::unique_ptr<hg_transcript> t(new hg_transcript());
         t->t.reset(make_transcript(field_id, proof, len, true));
+        *out = t.release();
+    })
+}
+int hg_transcript_from_callbacks(int field_id, void* user, hg_squeeze_fn squeeze, hg_write_fn write, hg_read_fn read, int message_independent,
+                                 hg_transcript** out) {
+    HG_TRY({
+        if (!out) throw std::runtime_error("hg_transcript_from_callbacks: out is NULL");
+        if (!squeeze) throw std::runtime_error("hg_transcript_from_callbacks: a squeeze callback is required");
+        TranscriptHooks h;
+        h.user = user; h.squeeze = squeeze; h.write = write; h.read = read; h.message_independent = message_independent != 0;
+        std::unique_ptr<hg_transcript> t(new hg_transcript());
+        if (field_id == HG_FIELD_GOLDILOCKS) t->t.reset(new TranscriptT<GlField>(h));
+        else if (field_id == HG_FIELD_BN254) t->t.reset(new TranscriptT<FrField>(h));
+        else throw std::runtime_error("unknown field id");
         *out = t.release();
     })
 }

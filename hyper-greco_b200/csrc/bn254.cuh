@@ -214,6 +214,7 @@ struct FrField {
     static constexpr int B_LIMBS = 4, X_LIMBS = 4;
     static constexpr int PLANES = 1;  // base planes per extension element
     static constexpr int GP_TAIL_LOG = 5, GP_MIN_BLOCKS = 1, GP_R0_U = 2, GP_R0A_QPT = 1, GP_BLOCK = 256;
+    static constexpr int FUSED_MIN_BLOCKS = 2;
     static constexpr double GP_TARGET = 2.0;
     HG_HD static B b_zero() { return fr_zero(); }
     HG_HD static B b_one() { return fr_one(); }
@@ -291,6 +292,8 @@ struct FrField {
     __device__ __forceinline__ static FoldAux fold_aux(X) { FoldAux a; a.unused = 0; return a; }
     __device__ __forceinline__ static BAcc bacc_zero() { return fr_zero(); }
     __device__ __forceinline__ static void bacc_mad(BAcc& a, B x, B y) { a = fr_add(a, fr_mul(x, y)); }
+    __device__ __forceinline__ static void bacc_add(BAcc& a, B x) { a = fr_add(a, x); }
+    __device__ __forceinline__ static B b_shfl_down(B v, int off) { return x_shfl_down(v, off); }
     __device__ __forceinline__ static B bacc_reduce(const BAcc& a) { return a; }
     __device__ __forceinline__ static XAcc xacc_zero_() { return fr_zero(); }
     __device__ __forceinline__ static void xacc_mad_(XAcc& a, X x, X y) { a = fr_add(a, fr_mul(x, y)); }
@@ -303,6 +306,7 @@ struct FrField {
     __device__ __forceinline__ static X fold_scaled(B a0, B a1, X c, X cr) { return fr_add(fr_mul(c, a0), fr_mul(cr, fr_sub(a1, a0))); }
     __device__ __forceinline__ static X slope(X lo, X hi) { return fr_sub(hi, lo); }
     __device__ __forceinline__ static X at_m1(X lo, X hi) { return fr_sub(fr_add(lo, lo), hi); }
+    __device__ __forceinline__ static B q_at_m1(B q0, B q1, B qinf) { const B s = fr_add(q0, qinf); return fr_sub(fr_add(s, s), q1); }
     __device__ __forceinline__ static B to_base(unsigned short v) { return fr_from_u64(v); }
     __device__ __forceinline__ static B to_base(unsigned int v) { return fr_from_u64(v); }
     __device__ __forceinline__ static B to_base(B v) { return v; }

@@ -25,6 +25,7 @@ struct GlField {
     static constexpr int TWO_ADICITY = 32;
     static constexpr int PLANES = 2;  // base planes per extension element
     static constexpr int GP_TAIL_LOG = 6, GP_MIN_BLOCKS = 2, GP_R0_U = 4, GP_R0A_QPT = 4, GP_BLOCK = 128;
+    static constexpr int FUSED_MIN_BLOCKS = 4;  // CTAs of HG_FUSED_BLOCK threads per SM the fused tree builders are compiled for (gp_fused.cuh)
     static constexpr double GP_TARGET = 0.25;  // CTAs per SM (of 256 threads) from which a layer runs with one term group (prover.cuh)
     HG_HD static bool b_eq(B a, B b) { return a == b; }
     HG_HD static B plane(X a, int p) { return p ? a.c1 : a.c0; }
@@ -88,6 +89,8 @@ struct GlField {
     __device__ __forceinline__ static FoldAux fold_aux(X r) { FoldAux a; a.r7 = gl_mul7(r.c1); return a; }
     __device__ __forceinline__ static BAcc bacc_zero() { return acc_zero(); }
     __device__ __forceinline__ static void bacc_mad(BAcc& a, B x, B y) { acc_mad(a, x, y); }
+    __device__ __forceinline__ static void bacc_add(BAcc& a, B x) { acc_add(a, x); }
+    __device__ __forceinline__ static B b_shfl_down(B v, int off) { return __shfl_down_sync(0xffffffffu, v, off); }
     __device__ __forceinline__ static B bacc_reduce(const BAcc& a) { return acc_reduce(a); }
     __device__ __forceinline__ static XAcc xacc_zero_() { return xacc_zero(); }
     __device__ __forceinline__ static void xacc_mad_(XAcc& a, X x, X y) { xacc_mad(a, x, y); }
@@ -120,6 +123,11 @@ struct GlField {
     __device__ __forceinline__ static X slope(X lo, X hi) { return gl2_make(gl_sub_cs(hi.c0, lo.c0), gl_sub_cs(hi.c1, lo.c1)); }
     __device__ __forceinline__ static X at_m1(X lo, X hi) {
         return gl2_make(gl_add_cs(lo.c0, gl_sub_cs(lo.c0, hi.c0)), gl_add_cs(lo.c1, gl_sub_cs(lo.c1, hi.c1)));
+    }
+    // 2 q0 - q1 + 2 qinf for canonical inputs; some 64-bit representative (the result only feeds a multiplication)
+    __device__ __forceinline__ static B q_at_m1(B q0, B q1, B qinf) {
+        const u64 w = gl_add_cs(q0, gl_sub_cs(q0, q1));  // canonical + canonical-or-lazy
+        return gl_add_cs(qinf, gl_add_cs(qinf, w));
     }
     __device__ __forceinline__ static B to_base(unsigned short v) { return (B)v; }
     __device__ __forceinline__ static B to_base(unsigned int v) { return (B)v; }

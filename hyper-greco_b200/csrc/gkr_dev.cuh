@@ -178,6 +178,7 @@ template <class FP> class GkrCircuitDev {
     std::vector<std::vector<InputClaim>> prove(Keccak256Transcript<FP>& tr, ProveMode mode, const WireOptions& wo,
                                                const std::vector<InputClaim>& output_claims) {
         if (!evaluated_) throw std::runtime_error("prove_gkr: evaluate the circuit first");
+        if (!tr.prefetch_legal()) mode = kModeInteractive;
         cudaStream_t s = ctx_->stream;
         auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         const double t0 = now();

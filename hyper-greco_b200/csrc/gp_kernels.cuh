@@ -110,7 +110,8 @@ k_gp_r0(const typename FP::B* __restrict__ tables, size_t n, int nvec, int tpg, 
 
 // ---- rounds >= 1: fold by r_prev, write the folded tables, evaluate the next round polynomial on them
 //   in : [2*nvec][n_in] (TIN = B in round 1, X later);  out: [2*nvec][n_in/2]
-//   SCALE (round 1, TIN = B): l_i (i > 0) is written as c_i * l_i; cr[i] = c_i * r_prev is precomputed (k_gp_coeffs)
+//   SCALE (round 1, TIN = B): l_i (i > 0) is written as c_i * l_i and r_0 as c_0 * r_0 (l_0 stays: it is also t_0);
+//   cr[i] = c_i * r_prev is precomputed (k_gp_coeffs)
 //   msg: h(0), h(inf), h(-1)
 template <class FP, class TIN, bool SCALE>
 __global__ void __launch_bounds__(HG_BLOCK)
@@ -141,34 +142,26 @@ k_gp_fold(const TIN* __restrict__ in, typename FP::X* __restrict__ out, size_t n
             TIN a[4], c[4];
             load4(in + (size_t)(2 * i) * n_in + 4 * b, a);
             load4(in + (size_t)(2 * i + 1) * n_in + 4 * b, c);
-            X l_lo, l_hi;
+            X l_lo, l_hi, r_lo, r_hi;
             if constexpr (SCALE) {
+                // term i carries c_i on l_i; term 0 carries c_0 on r_0, because l_0 is also the common factor t_0
+                const X ci = coeffs[i], cri = cr[i];
                 if (i > 0) {
-                    const X ci = coeffs[i], cri = cr[i];
-                    l_lo = FP::fold_scaled(a[0], a[1], ci, cri);
-                    l_hi = FP::fold_scaled(a[2], a[3], ci, cri);
+                    l_lo = FP::fold_scaled(a[0], a[1], ci, cri); l_hi = FP::fold_scaled(a[2], a[3], ci, cri);
+                    r_lo = FP::fold(c[0], c[1], r, aux); r_hi = FP::fold(c[2], c[3], r, aux);
                 } else {
-                    l_lo = FP::fold(a[0], a[1], r, aux);
-                    l_hi = FP::fold(a[2], a[3], r, aux);
+                    l_lo = FP::fold(a[0], a[1], r, aux); l_hi = FP::fold(a[2], a[3], r, aux);
+                    r_lo = FP::fold_scaled(c[0], c[1], ci, cri); r_hi = FP::fold_scaled(c[2], c[3], ci, cri);
                 }
             } else {
-                l_lo = FP::fold(a[0], a[1], r, aux);
-                l_hi = FP::fold(a[2], a[3], r, aux);
+                l_lo = FP::fold(a[0], a[1], r, aux); l_hi = FP::fold(a[2], a[3], r, aux);
+                r_lo = FP::fold(c[0], c[1], r, aux); r_hi = FP::fold(c[2], c[3], r, aux);
             }
-            const X r_lo = FP::fold(c[0], c[1], r, aux), r_hi = FP::fold(c[2], c[3], r, aux);
             store2(out + (size_t)(2 * i) * n_out + 2 * b, l_lo, l_hi);
             store2(out + (size_t)(2 * i + 1) * n_out + 2 * b, r_lo, r_hi);
-            if (i == 0) {
-                // term 0 keeps l_0 unscaled (it is also t_0), so its products take c_0 explicitly
-                const X c0 = coeffs[0];
-                FP::xacc_mad_(P[0], FP::fmul(c0, l_lo), r_lo);
-                FP::xacc_mad_(P[1], FP::fmul(c0, FP::slope(l_lo, l_hi)), FP::slope(r_lo, r_hi));
-                FP::xacc_mad_(P[2], FP::fmul(c0, FP::at_m1(l_lo, l_hi)), FP::at_m1(r_lo, r_hi));
-            } else {
-                FP::xacc_mad_(P[0], l_lo, r_lo);
-                FP::xacc_mad_(P[1], FP::slope(l_lo, l_hi), FP::slope(r_lo, r_hi));
-                FP::xacc_mad_(P[2], FP::at_m1(l_lo, l_hi), FP::at_m1(r_lo, r_hi));
-            }
+            FP::xacc_mad_(P[0], l_lo, r_lo);
+            FP::xacc_mad_(P[1], FP::slope(l_lo, l_hi), FP::slope(r_lo, r_hi));
+            FP::xacc_mad_(P[2], FP::at_m1(l_lo, l_hi), FP::at_m1(r_lo, r_hi));
         }
 #pragma unroll
         for (int p = 0; p < NP; p++) acc[p] = FP::x_add(acc[p], FP::fmul(t0[p], FP::xacc_reduce_(P[p])));
@@ -437,36 +430,34 @@ __global__ void __launch_bounds__(FP::GP_BLOCK, FP::GP_MIN_BLOCKS * (HG_BLOCK / 
                 prefetch_l2(in + (size_t)(2 * (i + HG_GP_PREFETCH)) * n_in + 4 * b);
                 prefetch_l2(in + (size_t)(2 * (i + HG_GP_PREFETCH) + 1) * n_in + 4 * b);
             }
-            X l_lo, l_hi;
+            X l_lo, l_hi, r_lo, r_hi;
             if constexpr (SCALE) {
+                // term i carries c_i on l_i; term 0 carries c_0 on r_0, because l_0 is also the common factor t_0
+                const X ci = it.c[i], cri = it.cr[i];
                 if (i > 0) {
-                    const X ci = it.c[i], cri = it.cr[i];
-                    l_lo = FP::fold_scaled(a[0], a[1], ci, cri);
-                    l_hi = FP::fold_scaled(a[2], a[3], ci, cri);
+                    l_lo = FP::fold_scaled(a[0], a[1], ci, cri); l_hi = FP::fold_scaled(a[2], a[3], ci, cri);
+                    r_lo = FP::fold(c[0], c[1], r, aux); r_hi = FP::fold(c[2], c[3], r, aux);
                 } else {
-                    l_lo = FP::fold(a[0], a[1], r, aux);
-                    l_hi = FP::fold(a[2], a[3], r, aux);
+                    l_lo = FP::fold(a[0], a[1], r, aux); l_hi = FP::fold(a[2], a[3], r, aux);
+                    r_lo = FP::fold_scaled(c[0], c[1], ci, cri); r_hi = FP::fold_scaled(c[2], c[3], ci, cri);
                 }
             } else {
-                l_lo = FP::fold(a[0], a[1], r, aux);
-                l_hi = FP::fold(a[2], a[3], r, aux);
+                l_lo = FP::fold(a[0], a[1], r, aux); l_hi = FP::fold(a[2], a[3], r, aux);
+                r_lo = FP::fold(c[0], c[1], r, aux); r_hi = FP::fold(c[2], c[3], r, aux);
             }
-            const X r_lo = FP::fold(c[0], c[1], r, aux), r_hi = FP::fold(c[2], c[3], r, aux);
             store2(out + (size_t)(2 * i) * n_out + 2 * b, l_lo, l_hi);
             store2(out + (size_t)(2 * i + 1) * n_out + 2 * b, r_lo, r_hi);
-            if (i == 0) {
-                const X c0 = it.c[0];
-                FP::xacc_mad_(P[0], FP::fmul(c0, l_lo), r_lo);
-                FP::xacc_mad_(P[1], FP::fmul(c0, FP::slope(l_lo, l_hi)), FP::slope(r_lo, r_hi));
-                FP::xacc_mad_(P[2], FP::fmul(c0, FP::at_m1(l_lo, l_hi)), FP::at_m1(r_lo, r_hi));
-            } else {
-                FP::xacc_mad_(P[0], l_lo, r_lo);
-                FP::xacc_mad_(P[1], FP::slope(l_lo, l_hi), FP::slope(r_lo, r_hi));
-                FP::xacc_mad_(P[2], FP::at_m1(l_lo, l_hi), FP::at_m1(r_lo, r_hi));
-            }
+            // q_i(X) = l_i(X) r_i(X) is quadratic: sampled at X = 0, 1, inf (no value at -1 inside the term loop)
+            FP::xacc_mad_(P[0], l_lo, r_lo);
+            FP::xacc_mad_(P[1], FP::slope(l_lo, l_hi), FP::slope(r_lo, r_hi));
+            FP::xacc_mad_(P[2], l_hi, r_hi);
         }
-#pragma unroll
-        for (int p = 0; p < NP; p++) acc[p] = FP::x_add(acc[p], FP::fmul(t0[p], FP::xacc_reduce_(P[p])));
+        // Q(-1) = 2 Q(0) - Q(1) + 2 Q(inf) for the summed quadratic Q = sum_i q_i; h sampled at 0, inf, -1 as before
+        const X Q0 = FP::xacc_reduce_(P[0]), Qi = FP::xacc_reduce_(P[1]), Q1 = FP::xacc_reduce_(P[2]);
+        const X Qs = FP::x_add(Q0, Qi), Qm = FP::x_sub(FP::x_add(Qs, Qs), Q1);
+        acc[0] = FP::x_add(acc[0], FP::fmul(t0[0], Q0));
+        acc[1] = FP::x_add(acc[1], FP::fmul(t0[1], Qi));
+        acc[2] = FP::x_add(acc[2], FP::fmul(t0[2], Qm));
     }
     block_reduce_finalize_ex<FP, NP>(acc, it.partials, it.counter, it.msg, it.nblk, lb);
 }
@@ -499,9 +490,11 @@ template <class FP> struct GpTailItem {
     const typename FP::X* chal;     // chal[k] = challenge folded in the k-th tail round; chal[rounds] = last challenge (final fold)
     typename FP::X* msg0;           // from_base: 4 slots for round 0
     typename FP::X* msg;            // 3 slots per tail round
-    typename FP::X* evals;          // 2*nvec final evaluations (l_i for i > 0 scaled by c_i)
+    typename FP::X* evals;          // 2*nvec final evaluations (l_i for i > 0 scaled by c_i, r_0 by c_0)
     int from_base, n, nvec, rounds;
     int i_begin, i_end;             // owned terms (see GpItem)
+    const typename FP::X* r0part;   // !from_base: round-0 partial sums of the fused tree builders (gp_fused.cuh), [r0n][4], summed into msg0
+    int r0n;
 };
 
 template <class FP, int NP>
@@ -558,20 +551,26 @@ template <class FP> __global__ void __launch_bounds__(HG_TAIL_THREADS) k_gp_tail
             acc[3] = FP::x_add(acc[3], FP::fmul(FP::fmul(ci, t_hi), FP::fmul(l_hi, r_hi)));
         }
         tail_block_sum<FP, 4>(acc, red, it.msg0);
-        // pre-scale l_i by c_i (i > 0), as round 1 of the streaming kernels does
-        for (int e = threadIdx.x; e < (it.nvec - 1) * len; e += blockDim.x) {
-            const int i = 1 + e / len, k = e % len;
-            A[(2 * i) * len + k] = FP::fmul(A[(2 * i) * len + k], it.c[i]);
+        // pre-scale l_i by c_i (i > 0) and r_0 by c_0, as round 1 of the streaming kernels does
+        for (int e = threadIdx.x; e < it.nvec * len; e += blockDim.x) {
+            const int i = e / len, k = e % len, tab = i ? 2 * i : 1;
+            A[tab * len + k] = FP::fmul(A[tab * len + k], it.c[i]);
         }
         __syncthreads();
     } else {
         const X* src = (const X*)it.in;
         for (int e = threadIdx.x; e < ntab * len; e += blockDim.x) A[e] = src[e];
+        if (it.r0n > 0) {  // round 0 was sampled while the tree was built: add up the CTA partials
+            X acc[4] = {FP::x_zero(), FP::x_zero(), FP::x_zero(), FP::x_zero()};
+            for (int b = threadIdx.x; b < it.r0n; b += blockDim.x)
+#pragma unroll
+                for (int p = 0; p < 4; p++) acc[p] = FP::x_add(acc[p], it.r0part[(size_t)b * 4 + p]);
+            tail_block_sum<FP, 4>(acc, red, it.msg0);
+        }
         __syncthreads();
     }
     X* cur = A;
     X* nxt = Bf;
-    const X c0 = it.c[0];
     for (int rd = 0; rd < it.rounds; rd++) {
         const X r = it.chal[rd];
         const typename FP::FoldAux aux = FP::fold_aux(r);
@@ -595,9 +594,8 @@ template <class FP> __global__ void __launch_bounds__(HG_TAIL_THREADS) k_gp_tail
             nxt[(2 * i) * half + 2 * b + 1] = l_hi;
             nxt[(2 * i + 1) * half + 2 * b] = r_lo;
             nxt[(2 * i + 1) * half + 2 * b + 1] = r_hi;
-            X p0 = FP::fmul(l_lo, r_lo), p1 = FP::fmul(FP::slope(l_lo, l_hi), FP::slope(r_lo, r_hi)),
-              p2 = FP::fmul(FP::at_m1(l_lo, l_hi), FP::at_m1(r_lo, r_hi));
-            if (i == 0) { p0 = FP::fmul(p0, c0); p1 = FP::fmul(p1, c0); p2 = FP::fmul(p2, c0); }
+            const X p0 = FP::fmul(l_lo, r_lo), p1 = FP::fmul(FP::slope(l_lo, l_hi), FP::slope(r_lo, r_hi)),
+                    p2 = FP::fmul(FP::at_m1(l_lo, l_hi), FP::at_m1(r_lo, r_hi));
             acc[0] = FP::x_add(acc[0], FP::fmul(t_lo, p0));
             acc[1] = FP::x_add(acc[1], FP::fmul(FP::slope(t_lo, t_hi), p1));
             acc[2] = FP::x_add(acc[2], FP::fmul(FP::at_m1(t_lo, t_hi), p2));

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "gkr_kernels.cuh"
+#include "gp_fused.cuh"
 #include "gp_kernels.cuh"
 #include "kernels.cuh"
 #include "lasso_host.hpp"
@@ -186,7 +187,7 @@ template <class FP> class Channel {
     // node: it ignores its incoming claim, lasso.rs:60). Its messages are copied to the host as soon as its kernels finish and
     // serialised into a side buffer while the device works on what was enqueued after it; flush() splices the bytes in place.
     bool begin_side() {
-        if (mode_ != kModePrefetch || side_state_ != 0) return false;
+        if (mode_ != kModePrefetch || side_state_ != 0 || tr_->hooked()) return false;  // a caller-owned transcript takes its messages one by one, in order
         side_state_ = 1; side_def_begin_ = deferred_.size(); side_msg_begin_ = msg_cursor_;
         return true;
     }
@@ -516,6 +517,9 @@ template <class FP> struct GpLayerJob {
     size_t n;
     int nvec, nv;
     size_t gamma_idx, r0_idx, msg_off, evals_off;
+    typename FP::X* coef = nullptr;          // [c_i | c_i * r_0], assigned by LassoNodeDev::prepare_gp_coeffs
+    const typename FP::X* r0part = nullptr;  // round 0 sampled by the fused tree builders (gp_fused.cuh): [r0n][4] CTA partials
+    int r0n = 0;
 };
 
 // Grand-product layer sumcheck with the specialised kernels of gp_kernels.cuh. tables: [nvec][2n] base elements.
@@ -711,6 +715,8 @@ template <class FP> class LassoNodeDev {
         d_pool_.alloc(3 * (size_t)m_ * (R_ + M_) + 64);
         d_gp_partials_.alloc((size_t)ctx->sm_count * 64 * 4 + 4096);
         d_gp_counters_.alloc(128);
+        // CTA partial sums of the fused round 0 (gp_fused.cuh): <= sm_count*64 + 2m blocks per launch and layer, two layers per tree launch
+        d_r0part_.alloc(4 * ((size_t)ctx->sm_count * 64 + 4 * (size_t)m_) * (size_t)(num_vars_ + log2M_ + 2));
         HG_CUDA(cudaMemset(d_gp_counters_.p, 0, d_gp_counters_.bytes()));
         h_desc_.alloc(1 << 16);
         d_desc_.alloc(1 << 16);
@@ -758,6 +764,7 @@ template <class FP> class LassoNodeDev {
     // Output: the claim (r, claimed_sum) for input 0 (lasso.rs:97,113).
     void prove(const B* d_inputs, size_t n_inputs, Keccak256Transcript<FP>& tr, ProveMode mode, const WireOptions& wo, std::vector<X>* out_point,
                X* out_value) {
+        if (!tr.prefetch_legal()) mode = kModeInteractive;  // a transcript that may absorb messages: one round trip per squeeze
         Channel<FP>& ch = *ch_;
         auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         const double t_start = now();
@@ -784,6 +791,7 @@ template <class FP> class LassoNodeDev {
     // Returns this device's partial message buffer (pinned host memory, valid until the next prove).
     const X* prove_shard(const B* d_inputs, size_t n_inputs, Keccak256Transcript<FP>& tr, const WireOptions& wo, int rank, int world, size_t* count) {
         if (world < 1 || rank < 0 || rank >= world || world > 2 * m_) throw std::runtime_error("LassoNode: bad shard rank / world size");
+        if (!tr.prefetch_legal()) throw std::runtime_error("LassoNode: a sharded proof needs a transcript whose challenges do not depend on the messages");
         Channel<FP>& ch = *ch_;
         shard_rank_ = rank; shard_world_ = world;
         struct Reset { LassoNodeDev* n; ~Reset() { n->shard_rank_ = 0; n->shard_world_ = 1; } } reset{this};
@@ -910,6 +918,46 @@ template <class FP> class LassoNodeDev {
         }
         // ---- memory checking (lasso.rs:292-339, prover.rs:35-181)
         const bool fused_up = R >= 4;  // hash build fused with the first tree level
+        size_t x_idx = 0, y_idx = 0;
+        std::vector<GpLayerJob<FP>> jobs;
+        if (mode == kModePrefetch) {
+            // all challenges are on the device already: do the protocol bookkeeping of both grand products first (message
+            // slots, challenge indices), then launch coefficients -> hashes -> trees (+ round 0) -> rounds >= 1
+            GpPlan plan1, plan2;
+            grand_product(ch, wo, d_tree1_.p, R, &x_idx, &jobs, fused_up, &plan1);
+            grand_product(ch, wo, d_tree2_.p, M, &y_idx, &jobs, false, &plan2);
+            prepare_gp_coeffs(ch, wo, jobs);
+            static const bool env_fuse = getenv("HG_GP_FUSE_R0") ? atoi(getenv("HG_GP_FUSE_R0")) != 0 : true;
+            const bool fuse = env_fuse;
+            const bool fuse_hash = fuse && fused_up && gp_needs_r0(R, 0, plan1.nvars);
+            if (fuse_hash) {
+                GpLayerJob<FP>& j0 = jobs[plan1.job_begin + plan1.nvars - 2];  // the sumcheck on layer 0
+                const size_t work = R / 4;                                      // row pairs per memory
+                const int nxb = fused_nxb(work, m);
+                X* part = r0_alloc((size_t)nxb * m);
+                j0.r0part = part; j0.r0n = nxb * m;
+                HG_K(ctx_, KC_HASH, 0, k_hash_t0<FP><<<(unsigned)((R / 4 + HG_BLOCK - 1) / HG_BLOCK), HG_BLOCK, 0, s>>>(d_dims_.p, d_read_cts_.p, d_E_.p, d_pos_mem_.p, d_pos_dim_.p,
+                                                                                                                    d_pos_slot_.p, ch.d_chal(gt_idx), R, d_tree1_.p));
+                HG_K(ctx_, KC_HASH, (size_t)m * R * (2 + 4 + 4 * sizeof(B)),
+                     k_hash_rw_up_r0<FP><<<nxb * m, HG_FUSED_BLOCK, 0, s>>>(d_dims_.p, d_read_cts_.p, d_E_.p, d_pos_mem_.p, d_pos_dim_.p, d_pos_slot_.p, ch.d_chal(gt_idx), R, m,
+                                                                          d_tree1_.p, d_tree1_.p + (size_t)2 * m * R, own_range(2 * m), j0.coef, part, nxb));
+            } else if (fused_up) {
+                HG_K(ctx_, KC_HASH, (size_t)m * R * (2 + 4 + 4 * sizeof(B)),
+                     k_hash_rw_up<FP><<<dim3((unsigned)((R / 4 + HG_BLOCK - 1) / HG_BLOCK + (R < 4 ? 1 : 0)), m), HG_BLOCK, 0, s>>>(
+                         d_dims_.p, d_read_cts_.p, d_E_.p, d_pos_mem_.p, d_pos_dim_.p, d_pos_slot_.p, ch.d_chal(gt_idx), R, m, d_tree1_.p,
+                         d_tree1_.p + (size_t)2 * m * R, own_range(2 * m)));
+            } else {
+                HG_K(ctx_, KC_HASH, (size_t)m * R * (2 + 4 + 3 * sizeof(B)),
+                     k_hash_rw<FP><<<dim3((unsigned)((R + HG_BLOCK - 1) / HG_BLOCK), m), HG_BLOCK, 0, s>>>(d_dims_.p, d_read_cts_.p, d_E_.p, d_pos_mem_.p, d_pos_dim_.p,
+                                                                                                           d_pos_slot_.p, ch.d_chal(gt_idx), R, m, d_tree1_.p));
+            }
+            HG_K(ctx_, KC_HASH, (size_t)m * M * (4 + 3 * sizeof(B)),
+                 k_hash_if<FP><<<dim3((unsigned)((M + HG_BLOCK - 1) / HG_BLOCK), m), HG_BLOCK, 0, s>>>(d_subtables_.p, d_final_cts_.p, d_pos_sub_.p, d_pos_slot_.p,
+                                                                                                       ch.d_chal(gt_idx), M, m, d_tree2_.p, own_range(2 * m)));
+            build_tree(ch, plan1, jobs, fuse);
+            build_tree(ch, plan2, jobs, fuse);
+            run_gp_batch(ch, wo, jobs);
+        } else {
         if (fused_up)
             HG_K(ctx_, KC_HASH, (size_t)m * R * (2 + 4 + 4 * sizeof(B)),
                  k_hash_rw_up<FP><<<dim3((unsigned)((R / 4 + HG_BLOCK - 1) / HG_BLOCK + (R < 4 ? 1 : 0)), m), HG_BLOCK, 0, s>>>(
@@ -922,12 +970,9 @@ template <class FP> class LassoNodeDev {
         HG_K(ctx_, KC_HASH, (size_t)m * M * (4 + 3 * sizeof(B)),
              k_hash_if<FP><<<dim3((unsigned)((M + HG_BLOCK - 1) / HG_BLOCK), m), HG_BLOCK, 0, s>>>(d_subtables_.p, d_final_cts_.p, d_pos_sub_.p, d_pos_slot_.p,
                                                                                                    ch.d_chal(gt_idx), M, m, d_tree2_.p, own_range(2 * m)));
-        size_t x_idx = 0, y_idx = 0;
-        std::vector<GpLayerJob<FP>> jobs;
-        std::vector<GpLayerJob<FP>>* batch = (mode == kModePrefetch) ? &jobs : nullptr;
-        grand_product(ch, wo, d_tree1_.p, R, &x_idx, batch, fused_up);
-        grand_product(ch, wo, d_tree2_.p, M, &y_idx, batch, false);
-        if (batch) run_gp_batch(ch, wo, jobs);
+        grand_product(ch, wo, d_tree1_.p, R, &x_idx, nullptr, fused_up);
+        grand_product(ch, wo, d_tree2_.p, M, &y_idx, nullptr, false);
+        }
         // ---- openings (prover.rs:173-178, mod.rs:80-93)
         const size_t o_dims = ch.alloc_msg(pp_.C), o_rts = ch.alloc_msg(nslots_), o_fcs = ch.alloc_msg(nslots_), o_e = ch.alloc_msg(m);
         build_eq(ch, x_idx, v);
@@ -1009,8 +1054,85 @@ template <class FP> class LassoNodeDev {
     }
 
     // prove_grand_product (prover.rs:183-266) over nvec = 2m vectors of length N stored at tree (layer 0), upper layers appended
+    // a grand product whose launches were deferred (prefetch mode): what build_tree needs
+    struct GpPlan { B* tree = nullptr; size_t N = 0; int nvars = 0; size_t roots_off = 0, ev0_off = 0, job_begin = 0; bool level1_done = false; };
+    // does layer k of a tree over vectors of length N get its round 0 from a streaming kernel (tables longer than the tail kernel takes)?
+    static bool gp_needs_r0(size_t N, int k, int nvars) { return k <= nvars - 2 && ((N >> k) / 2) > ((size_t)1 << FP::GP_TAIL_LOG); }
+    // position blocks per vector of the fused builders: every CTA ends with a block-level reduction that costs about as much as
+    // one pass over its data, so CTAs are long (~16 per SM over the whole launch, at least 8 positions per thread)
+    int fused_nxb(size_t work, int nvec) const {
+        static const int env_cps = getenv("HG_FUSED_CPS") ? atoi(getenv("HG_FUSED_CPS")) : 16;
+        const size_t by_work = (work + (size_t)HG_FUSED_BLOCK * 8 - 1) / ((size_t)HG_FUSED_BLOCK * 8);
+        const size_t by_grid = std::max<size_t>(1, (size_t)ctx_->sm_count * env_cps / nvec);
+        return (int)std::max<size_t>(1, std::min(by_work, by_grid));
+    }
+    X* r0_alloc(size_t nblk) {
+        const size_t need = nblk * 4;
+        if (r0_used_ + need > d_r0part_.n) throw std::runtime_error("LassoNode: round-0 partial pool too small");
+        X* p = d_r0part_.p + r0_used_;
+        r0_used_ += need;
+        return p;
+    }
+    // product tree of one grand product (prover.rs:191-195, Layer::up :332-354); with `fuse` the builders also sample round 0 of
+    // every layer that is streamed (gp_fused.cuh) and the layer jobs get the partial-sum regions
+    void build_tree(Channel<FP>& ch, const GpPlan& pl, std::vector<GpLayerJob<FP>>& jobs, bool fuse) {
+        cudaStream_t s = ctx_->stream;
+        const int nvec = 2 * m_, nvars = pl.nvars;
+        const size_t N = pl.N;
+        std::vector<B*> layer(nvars);
+        layer[0] = pl.tree;
+        for (int k = 1; k < nvars; k++) layer[k] = layer[k - 1] + (size_t)nvec * (N >> (k - 1));
+        auto job_of = [&](int k) -> GpLayerJob<FP>& { return jobs[pl.job_begin + (size_t)(nvars - 2 - k)]; };  // sumcheck nv = nvars-1-k is job nv-1
+        int cur = pl.level1_done ? 1 : 0;  // last layer that is complete
+        if (fuse) {
+            while (cur < nvars - 1 && gp_needs_r0(N, cur, nvars)) {
+                const bool two = cur + 2 <= nvars - 1 && gp_needs_r0(N, cur + 1, nvars);
+                const size_t len = N >> cur, q = two ? len / 4 : len / 2;
+                TreeR0Args<FP> a;
+                a.in = layer[cur]; a.out1 = layer[cur + 1]; a.out2 = two ? layer[cur + 2] : nullptr;
+                a.q = q; a.nvec = nvec; a.own = own_range(nvec);
+                a.nxb = fused_nxb(q / 2, nvec);
+                const size_t nblk = (size_t)a.nxb * nvec;
+                GpLayerJob<FP>& ja = job_of(cur);
+                a.cA = ja.coef; a.partA = r0_alloc(nblk);
+                ja.r0part = a.partA; ja.r0n = (int)nblk;
+                a.cB = nullptr; a.partB = nullptr;
+                if (two) {
+                    GpLayerJob<FP>& jb = job_of(cur + 1);
+                    a.cB = jb.coef; a.partB = r0_alloc(nblk);
+                    jb.r0part = a.partB; jb.r0n = (int)nblk;
+                }
+                // bytes: the layer read once, the layer(s) above written once
+                KernelScope ks(ctx_, KC_TREE, (size_t)nvec * (len + len / 2 + (two ? len / 4 : 0)) * sizeof(B));
+                if (two) k_tree_up_r0<FP, true><<<(unsigned)nblk, HG_FUSED_BLOCK, 0, s>>>(a);
+                else k_tree_up_r0<FP, false><<<(unsigned)nblk, HG_FUSED_BLOCK, 0, s>>>(a);
+                HG_LAUNCH_CHECK();
+                cur += two ? 2 : 1;
+            }
+        }
+        for (int k = cur + 1; k < nvars;) {
+            const size_t len_prev = N >> (k - 1);  // vector length of the layer this step reads
+            if (len_prev <= (size_t)HG_TREE_TAIL && len_prev > 2) {  // the rest of the tree in one launch (shared memory)
+                HG_K(ctx_, KC_TREE, (size_t)nvec * len_prev * 2 * sizeof(B),
+                     k_tree_tail<FP><<<nvec, 256, len_prev * sizeof(B), s>>>(layer[k - 1], nvec, (int)len_prev, own_range(nvec)));
+                break;
+            }
+            if (k + 1 < nvars) {  // two levels per launch: layer k is written and never re-read by the build
+                const size_t q = N >> (k + 1);
+                HG_K(ctx_, KC_TREE, (size_t)nvec * q * 7 * sizeof(B),
+                     k_tree_up2<FP><<<dim3((unsigned)(((q >= 2 ? q / 2 : q) + HG_BLOCK - 1) / HG_BLOCK), nvec), HG_BLOCK, 0, s>>>(layer[k - 1], layer[k], layer[k + 1], q, own_range(nvec)));
+                k += 2;
+            } else {
+                const size_t h = N >> k;
+                HG_K(ctx_, KC_TREE, (size_t)nvec * h * 3 * sizeof(B), k_tree_up<FP><<<dim3((unsigned)((h + HG_BLOCK - 1) / HG_BLOCK), nvec), HG_BLOCK, 0, s>>>(layer[k - 1], layer[k], h, own_range(nvec)));
+                k += 1;
+            }
+        }
+        HG_K(ctx_, KC_TREE, (size_t)nvec * 2 * sizeof(B), k_tree_top<FP><<<(nvec + HG_BLOCK - 1) / HG_BLOCK, HG_BLOCK, 0, s>>>(layer[nvars - 1], own_begin(nvec), own_end(nvec), ch.d_msg(pl.roots_off), ch.d_msg(pl.ev0_off)));
+    }
+
     void grand_product(Channel<FP>& ch, const WireOptions& wo, B* tree, size_t N, size_t* point_idx, std::vector<GpLayerJob<FP>>* batch,
-                       bool level1_done) {
+                       bool level1_done, GpPlan* defer = nullptr) {
         cudaStream_t s = ctx_->stream;
         const int nvec = 2 * m_;
         int nvars = 0;
@@ -1019,7 +1141,8 @@ template <class FP> class LassoNodeDev {
         std::vector<B*> layer(nvars);
         layer[0] = tree;
         for (int k = 1; k < nvars; k++) layer[k] = layer[k - 1] + (size_t)nvec * (N >> (k - 1));
-        for (int k = (level1_done ? 2 : 1); k < nvars;) {
+        if (defer) { defer->tree = tree; defer->N = N; defer->nvars = nvars; defer->level1_done = level1_done; defer->job_begin = batch ? batch->size() : 0; }
+        for (int k = (level1_done ? 2 : 1); k < nvars && !defer;) {
             const size_t len_prev = N >> (k - 1);  // vector length of the layer this step reads
             if (len_prev <= (size_t)HG_TREE_TAIL && len_prev > 2) {  // the rest of the tree in one launch (shared memory)
                 HG_K(ctx_, KC_TREE, (size_t)nvec * len_prev * 2 * sizeof(B),
@@ -1038,7 +1161,8 @@ template <class FP> class LassoNodeDev {
             }
         }
         const size_t roots_off = ch.alloc_msg(nvec), ev0_off = ch.alloc_msg(2 * nvec);
-        HG_K(ctx_, KC_TREE, (size_t)nvec * 2 * sizeof(B), k_tree_top<FP><<<(nvec + HG_BLOCK - 1) / HG_BLOCK, HG_BLOCK, 0, s>>>(layer[nvars - 1], own_begin(nvec), own_end(nvec), ch.d_msg(roots_off), ch.d_msg(ev0_off)));
+        if (defer) { defer->roots_off = roots_off; defer->ev0_off = ev0_off; }
+        else HG_K(ctx_, KC_TREE, (size_t)nvec * 2 * sizeof(B), k_tree_top<FP><<<(nvec + HG_BLOCK - 1) / HG_BLOCK, HG_BLOCK, 0, s>>>(layer[nvars - 1], own_begin(nvec), own_end(nvec), ch.d_msg(roots_off), ch.d_msg(ev0_off)));
         struct GpHost { std::vector<X> claimed; std::vector<X> evals; size_t mu_idx = 0; bool pending = false; };
         auto gp = std::make_shared<GpHost>();
         Channel<FP>* chp = &ch;
@@ -1076,13 +1200,13 @@ template <class FP> class LassoNodeDev {
                                 layer[nvars - nv]);
             ch.emit([chp, gp, ev_off, nvec, scaled, gamma_idx, asc]() {
                 auto& t = chp->transcript();
-                // the device keeps l_i (i > 0) pre-multiplied by c_i (gp_kernels.cuh); undo it exactly with c_i^{-1}
+                // the device keeps l_i (i > 0) and r_0 pre-multiplied by c_i (gp_kernels.cuh); undo it exactly with c_i^{-1}
                 X ginv = FP::x_inv(chp->chal(gamma_idx)), p = FP::x_one();
                 std::vector<X> cinv(nvec);
                 for (int i = 0; i < nvec; i++) { cinv[asc ? i : nvec - 1 - i] = p; p = FP::x_mul(p, ginv); }
                 for (int i = 0; i < 2 * nvec; i++) {
                     X e = chp->msg(ev_off + i);
-                    if (scaled && (i & 1) == 0 && i > 0) e = FP::x_mul(e, cinv[i / 2]);
+                    if (scaled && (i == 1 || ((i & 1) == 0 && i > 0))) e = FP::x_mul(e, cinv[i / 2]);  // c_i sits on l_i (i > 0) and on r_0
                     gp->evals[i] = e;
                     t.write_felt_ext(e);  // prover.rs:257
                 }
@@ -1096,32 +1220,48 @@ template <class FP> class LassoNodeDev {
     }
 
     // all layer sumchecks of both grand products, batched: round j of every layer in one launch, then one tail launch
+    // coefficient tables [c_i | c_i r_0] of every layer of both grand products, one launch (needs only challenges)
+    void prepare_gp_coeffs(Channel<FP>& ch, const WireOptions& wo, std::vector<GpLayerJob<FP>>& jobs) {
+        cudaStream_t s = ctx_->stream;
+        const int nl = (int)jobs.size();
+        r0_used_ = 0;
+        if (!nl) return;
+        size_t coef_off = 0;
+        std::vector<GpCoeffItem<FP>> citems(nl);
+        for (int k = 0; k < nl; k++) {
+            auto& j = jobs[k];
+            j.coef = d_gp_coeffs_.p + coef_off;
+            coef_off += 2 * (size_t)j.nvec;
+            citems[k].gamma = ch.d_chal(j.gamma_idx);
+            citems[k].r0 = j.nv >= 2 ? ch.d_chal(j.r0_idx) : nullptr;
+            citems[k].c = j.coef; citems[k].cr = j.coef + j.nvec; citems[k].n = j.nvec;
+        }
+        if (coef_off > d_gp_coeffs_.n) throw std::runtime_error("prepare_gp_coeffs: pool too small");
+        const size_t bytes = citems.size() * sizeof(GpCoeffItem<FP>);
+        if (h_cdesc_.n < bytes) { h_cdesc_.alloc(bytes * 2); d_cdesc_.alloc(bytes * 2); }
+        memcpy(h_cdesc_.p, citems.data(), bytes);
+        HG_CUDA(cudaMemcpyAsync(d_cdesc_.p, h_cdesc_.p, bytes, cudaMemcpyHostToDevice, s));
+        HG_K(ctx_, KC_MISC, 0, k_gp_coeffs_multi<FP><<<nl, 64, 0, s>>>((const GpCoeffItem<FP>*)d_cdesc_.p, wo.a5_ascending));
+    }
+
     void run_gp_batch(Channel<FP>& ch, const WireOptions& wo, const std::vector<GpLayerJob<FP>>& jobs) {
         cudaStream_t s = ctx_->stream;
         const int nl = (int)jobs.size();
         if (!nl) return;
+        (void)wo;
         // carve per-layer regions out of the pools
         std::vector<X*> bufA(nl, nullptr), bufB(nl, nullptr), coef(nl, nullptr);
-        size_t pool_off = 0, coef_off = 0;
+        size_t pool_off = 0;
         for (int k = 0; k < nl; k++) {
             const auto& j = jobs[k];
-            coef[k] = d_gp_coeffs_.p + coef_off;
-            coef_off += 2 * (size_t)j.nvec;
+            coef[k] = j.coef;
             if (j.n > ((size_t)1 << FP::GP_TAIL_LOG)) {
                 size_t a = 2 * (size_t)j.nvec * (j.n / 2), b = 2 * (size_t)j.nvec * (j.n / 4);
                 bufA[k] = d_pool_.p + pool_off; pool_off += a;
                 bufB[k] = d_pool_.p + pool_off; pool_off += b;
             }
         }
-        if (pool_off > d_pool_.n || coef_off > d_gp_coeffs_.n) throw std::runtime_error("run_gp_batch: pool too small");
-        // host staging of every descriptor table, one upload
-        std::vector<GpCoeffItem<FP>> citems(nl);
-        for (int k = 0; k < nl; k++) {
-            const auto& j = jobs[k];
-            citems[k].gamma = ch.d_chal(j.gamma_idx);
-            citems[k].r0 = j.nv >= 2 ? ch.d_chal(j.r0_idx) : nullptr;
-            citems[k].c = coef[k]; citems[k].cr = coef[k] + j.nvec; citems[k].n = j.nvec;
-        }
+        if (pool_off > d_pool_.n) throw std::runtime_error("run_gp_batch: pool too small");
         int maxJ = -1;
         for (auto& j : jobs) if (j.n > ((size_t)1 << FP::GP_TAIL_LOG)) maxJ = std::max(maxJ, j.nv - FP::GP_TAIL_LOG);
         std::vector<std::vector<GpItem<FP>>> rounds(maxJ + 1);
@@ -1144,6 +1284,7 @@ template <class FP> class LassoNodeDev {
             for (int k = 0; k < nl; k++) {
                 const auto& j = jobs[k];
                 if (j.n <= ((size_t)1 << FP::GP_TAIL_LOG) || r > j.nv - FP::GP_TAIL_LOG) continue;
+                if (r == 0 && j.r0n > 0) continue;  // sampled by the fused tree builders
                 GpItem<FP> it;
                 const int ntab = 2 * j.nvec;
                 it.nvec = j.nvec;
@@ -1215,6 +1356,7 @@ template <class FP> class LassoNodeDev {
             GpTailItem<FP>& t = titems[k];
             t.c = coef[k]; t.nvec = j.nvec; t.evals = ch.d_msg(j.evals_off);
             t.i_begin = own_begin(j.nvec); t.i_end = own_end(j.nvec);
+            t.r0part = j.r0part; t.r0n = j.r0n;
             if (j.n <= ((size_t)1 << FP::GP_TAIL_LOG)) {
                 t.from_base = 1; t.in = j.tables; t.n = (int)j.n; t.rounds = j.nv - 1;
                 t.chal = ch.d_chal(j.r0_idx); t.msg0 = ch.d_msg(j.msg_off); t.msg = ch.d_msg(j.msg_off + 4);
@@ -1222,19 +1364,18 @@ template <class FP> class LassoNodeDev {
             } else {
                 const int J = j.nv - FP::GP_TAIL_LOG;
                 t.from_base = 0; t.in = (J & 1) ? bufA[k] : bufB[k]; t.n = 1 << FP::GP_TAIL_LOG; t.rounds = FP::GP_TAIL_LOG - 1;
-                t.chal = ch.d_chal(j.r0_idx + J); t.msg0 = nullptr; t.msg = ch.d_msg(j.msg_off + 4 + 3 * (size_t)J);
+                t.chal = ch.d_chal(j.r0_idx + J); t.msg0 = ch.d_msg(j.msg_off); t.msg = ch.d_msg(j.msg_off + 4 + 3 * (size_t)J);
                 tail_bytes += 2 * (size_t)j.nvec * ((size_t)1 << FP::GP_TAIL_LOG) * sizeof(X);
             }
         }
         // upload descriptors
-        size_t bytes = citems.size() * sizeof(GpCoeffItem<FP>) + titems.size() * sizeof(GpTailItem<FP>);
+        size_t bytes = titems.size() * sizeof(GpTailItem<FP>);
         for (auto& rv : rounds) bytes += rv.size() * sizeof(GpItem<FP>) + 16;
         bytes += round0a.size() * sizeof(GpItem<FP>) + 64;
         if (h_desc_.n < bytes) { h_desc_.alloc(bytes * 2); d_desc_.alloc(bytes * 2); }
         unsigned char* hp = h_desc_.p;
         size_t off = 0;
         auto put = [&](const void* src, size_t n) { size_t o = off; memcpy(hp + off, src, n); off += (n + 15) & ~(size_t)15; return o; };
-        size_t c_off = put(citems.data(), citems.size() * sizeof(GpCoeffItem<FP>));
         std::vector<size_t> r_off(rounds.size());
         for (size_t r = 0; r < rounds.size(); r++) r_off[r] = put(rounds[r].data(), rounds[r].size() * sizeof(GpItem<FP>));
         size_t t_off = put(titems.data(), titems.size() * sizeof(GpTailItem<FP>));
@@ -1242,7 +1383,6 @@ template <class FP> class LassoNodeDev {
         if (off > h_desc_.n) throw std::runtime_error("run_gp_batch: descriptor staging overflow");
         HG_CUDA(cudaMemcpyAsync(d_desc_.p, h_desc_.p, off, cudaMemcpyHostToDevice, s));
         // launches
-        HG_K(ctx_, KC_MISC, 0, k_gp_coeffs_multi<FP><<<nl, 64, 0, s>>>((const GpCoeffItem<FP>*)(d_desc_.p + c_off), wo.a5_ascending));
         for (size_t r = 0; r < rounds.size(); r++) {
             if (rounds[r].empty()) continue;
             const auto& last = rounds[r].back();
@@ -1297,9 +1437,10 @@ template <class FP> class LassoNodeDev {
     DevBuf<X> d_eq_, d_gp_coeffs_, d_bufA_, d_bufB_, d_partials_, d_coll_terms_;
     int coll_coeff_state_ = 0;  // 0 not uploaded, 1 ascending, 2 descending
     DevBuf<unsigned> d_counters_, d_gp_counters_;
-    DevBuf<X> d_pool_, d_gp_partials_;
-    DevBuf<unsigned char> d_desc_;
-    PinnedBuf<unsigned char> h_desc_;
+    DevBuf<X> d_pool_, d_gp_partials_, d_r0part_;
+    size_t r0_used_ = 0;
+    DevBuf<unsigned char> d_desc_, d_cdesc_;
+    PinnedBuf<unsigned char> h_desc_, h_cdesc_;
     ScScratch sc_;
     std::unique_ptr<Channel<FP>> ch_;
 };

@@ -125,6 +125,18 @@ template <class HF> class ChallengeChain {
     uint8_t last_[32];
 };
 
+// A transcript owned by the CALLER: the three primitives the prove / verify path uses (squeeze_challenge, write_felt_ext,
+// read_felt_ext: transcript.rs:146-157, :172-177, :191-195) as C callbacks over canonical little-endian limbs. This is what a
+// `&mut dyn TranscriptWrite<F, E>` handed to Node::prove_claim_reduction (lasso.rs:58-63) is wrapped into.
+// Non-zero return = the callback failed (mapped to TranscriptError).
+struct TranscriptHooks {
+    void* user = nullptr;
+    int (*squeeze)(void* user, uint64_t* out_ext) = nullptr;
+    int (*write)(void* user, const uint64_t* ext) = nullptr;
+    int (*read)(void* user, uint64_t* out_ext) = nullptr;
+    bool message_independent = false;  // the caller guarantees challenges do not depend on written messages (prefetch mode allowed)
+};
+
 // HF: host field traits (see host_field.hpp): Base, Ext, base_from_le_bytes_mod, base_to_repr_le, base_from_repr_le ...
 template <class HF> class Keccak256Transcript {
   public:
@@ -132,9 +144,23 @@ template <class HF> class Keccak256Transcript {
     typedef typename HF::Ext Ext;
     Keccak256Transcript() {}                                                  // Keccak256Transcript::<Vec<u8>>::default()
     Keccak256Transcript(const uint8_t* proof, size_t n) : rd_(proof, proof + n), reading_(true) {}  // from_proof
+    explicit Keccak256Transcript(const TranscriptHooks& h) : hooks_(h), hooked_(true) {}             // caller-owned transcript behind callbacks
 
-    Base squeeze_base() { return ChallengeChain<HF>::get(n_squeezed_++); }
+    bool hooked() const { return hooked_; }
+    // may every challenge of a proof be squeezed before any message is written? True for the reference transcript (it never
+    // absorbs, transcript.rs:156,183-203); for a caller-owned one only if the caller says so
+    bool prefetch_legal() const { return !hooked_ || hooks_.message_independent; }
+    Base squeeze_base() {
+        if (hooked_) throw TranscriptError("squeeze_base on a callback transcript");
+        return ChallengeChain<HF>::get(n_squeezed_++);
+    }
     Ext squeeze_challenge() {
+        if (hooked_) {
+            uint64_t limbs[8] = {0};
+            if (!hooks_.squeeze || hooks_.squeeze(hooks_.user, limbs)) throw TranscriptError("transcript callback squeeze_challenge failed");
+            n_squeezed_ += HF::DEGREE;
+            return HF::x_from_limbs(limbs);
+        }
         Base b[HF::DEGREE];
         for (int i = 0; i < HF::DEGREE; i++) b[i] = squeeze_base();
         return HF::ext_from_bases(b);
@@ -149,6 +175,12 @@ template <class HF> class Keccak256Transcript {
         for (int i = 0; i < HF::REPR_BYTES; i++) dst[i] = b[HF::REPR_BYTES - 1 - i];
     }
     void write_felt_ext(const Ext& e) {
+        if (hooked_) {
+            uint64_t limbs[8] = {0};
+            HF::x_to_limbs(e, limbs);
+            if (!hooks_.write || hooks_.write(hooks_.user, limbs)) throw TranscriptError("transcript callback write_felt_ext failed");
+            return;
+        }
         Base b[HF::DEGREE];
         HF::ext_as_bases(e, b);
         for (int i = 0; i < HF::DEGREE; i++) write_felt(b[i]);
@@ -163,12 +195,20 @@ template <class HF> class Keccak256Transcript {
         return f;
     }
     Ext read_felt_ext() {
+        if (hooked_) {
+            uint64_t limbs[8] = {0};
+            if (!hooks_.read || hooks_.read(hooks_.user, limbs)) throw TranscriptError("transcript callback read_felt_ext failed");
+            return HF::x_from_limbs(limbs);
+        }
         Base b[HF::DEGREE];
         for (int i = 0; i < HF::DEGREE; i++) b[i] = read_felt();
         return HF::ext_from_bases(b);
     }
     const std::vector<uint8_t>& proof() const { return stream_; }  // into_proof
-    void append_bytes(const std::vector<uint8_t>& b) { stream_.insert(stream_.end(), b.begin(), b.end()); }  // messages serialised elsewhere
+    void append_bytes(const std::vector<uint8_t>& b) {  // messages serialised elsewhere (never for a callback transcript: Channel::begin_side)
+        if (hooked_) throw TranscriptError("append_bytes on a callback transcript");
+        stream_.insert(stream_.end(), b.begin(), b.end());
+    }
     size_t num_base_squeezed() const { return n_squeezed_; }
     size_t read_pos() const { return pos_; }
 
@@ -176,6 +216,8 @@ template <class HF> class Keccak256Transcript {
     std::vector<uint8_t> stream_, rd_;
     size_t pos_ = 0, n_squeezed_ = 0;
     bool reading_ = false;
+    TranscriptHooks hooks_;
+    bool hooked_ = false;
 };
 
 }  // namespace hg

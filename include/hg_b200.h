@@ -85,6 +85,22 @@ int hg_field_decode(hg_ctx* ctx, void* d_data, size_t n);
 /* ---- transcript: replaces Keccak256Transcript (bfv-gkr/src/transcript.rs:117-203) ----------------------------- */
 int hg_transcript_new(int field_id, hg_transcript** out);                                      /* ::default()      :431 of sk_encryption_circuit.rs */
 int hg_transcript_from_proof(int field_id, const uint8_t* proof, size_t len, hg_transcript** out); /* ::from_proof  transcript.rs:131-135 */
+/* A transcript OWNED BY THE CALLER, i.e. the `&mut dyn TranscriptWrite<F, E>` / `&mut dyn TranscriptRead<F, E>` that
+ * gkr::prove_gkr hands to Node::prove_claim_reduction / verify_claim_reduction (lasso/src/lasso.rs:58-63, :117-121). The three
+ * primitives the path uses are forwarded to C callbacks over canonical little-endian limbs (same encoding as everywhere
+ * in this header): squeeze_challenge (transcript.rs:146-157), write_felt_ext (:191-195), read_felt_ext (:172-177). A
+ * callback returns 0 on success; anything else aborts the call with an error. `write` may be NULL for a verifier
+ * transcript, `read` for a prover one. Such a transcript may absorb what is written to it, so every prove call that
+ * receives it runs in HG_MODE_INTERACTIVE (one round trip per squeeze, messages delivered strictly in protocol order)
+ * unless message_independent != 0, by which the caller promises that challenges do not depend on written messages (true
+ * for the reference's Keccak256Transcript, transcript.rs:156,183-203) and thereby allows HG_MODE_PREFETCH: all challenges
+ * of the call are squeezed first, all messages are written afterwards, still in protocol order.
+ * hg_transcript_proof_len/_copy return nothing for it (the bytes live with the caller). */
+typedef int (*hg_squeeze_fn)(void* user, uint64_t* out_ext);
+typedef int (*hg_write_fn)(void* user, const uint64_t* ext);
+typedef int (*hg_read_fn)(void* user, uint64_t* out_ext);
+int hg_transcript_from_callbacks(int field_id, void* user, hg_squeeze_fn squeeze, hg_write_fn write, hg_read_fn read, int message_independent,
+                                 hg_transcript** out);
 void hg_transcript_free(hg_transcript* t);
 int hg_transcript_squeeze_challenge(hg_transcript* t, uint64_t* out_ext);   /* transcript.rs:149-154 */
 int hg_transcript_squeeze_challenges(hg_transcript* t, size_t n, uint64_t* out_ext); /* n consecutive squeezes (TranscriptWrite::squeeze_challenges) */
