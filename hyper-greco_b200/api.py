@@ -24,7 +24,7 @@ DEGREE = {GOLDILOCKS: 2, BN254: 1}
 SYMBOLS = [
     "hg_last_error", "hg_version", "hg_ctx_create", "hg_ctx_destroy", "hg_ctx_set_option", "hg_ctx_synchronize", "hg_ctx_launch_count",
     "hg_ctx_stream", "hg_ctx_profile", "hg_ctx_profile_read", "hg_kernel_class_count", "hg_kernel_class_name", "hg_buf_alloc", "hg_buf_upload", "hg_buf_upload_async", "hg_buf_download", "hg_buf_device_ptr", "hg_buf_size", "hg_buf_free", "hg_field_base_bytes", "hg_field_encode", "hg_field_decode",
-    "hg_transcript_new", "hg_transcript_from_proof", "hg_transcript_free", "hg_transcript_squeeze_challenge", "hg_transcript_squeeze_challenges", "hg_transcript_write_felt_ext",
+    "hg_transcript_new", "hg_transcript_from_proof", "hg_transcript_from_callbacks", "hg_transcript_free", "hg_transcript_squeeze_challenge", "hg_transcript_squeeze_challenges", "hg_transcript_write_felt_ext",
     "hg_transcript_read_felt_ext", "hg_transcript_proof_len", "hg_transcript_proof_copy", "hg_transcript_num_squeezed",
     "hg_lasso_preprocess", "hg_lasso_pp_free", "hg_lasso_pp_num_lookups", "hg_lasso_pp_num_subtables", "hg_lasso_pp_num_memories",
     "hg_lasso_pp_lookup_index", "hg_lasso_pp_memory_maps", "hg_lasso_pp_subtable_id", "hg_lasso_node_new", "hg_lasso_node_free",
@@ -35,6 +35,11 @@ SYMBOLS = [
     "hg_circuit_connect", "hg_circuit_evaluate", "hg_circuit_evaluate_host", "hg_circuit_node_value", "hg_gkr_prove", "hg_gkr_timing", "hg_gkr_num_challenges", "hg_gkr_num_inputs", "hg_gkr_num_input_claims",
     "hg_gkr_input_claim_num_vars", "hg_gkr_input_claim",
 ]
+
+# callback types of hg_transcript_from_callbacks (include/hg_b200.h)
+SQUEEZE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64))
+WRITE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64))
+READ_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64))
 
 _lib = None
 
@@ -81,6 +86,7 @@ def lib():
         L.hg_transcript_new.argtypes = [i32, C.POINTER(vp)]
         L.hg_transcript_from_proof.argtypes = [i32, vp, sz, C.POINTER(vp)]
         L.hg_transcript_free.argtypes = [vp]
+        L.hg_transcript_from_callbacks.argtypes = [i32, vp, SQUEEZE_FN, WRITE_FN, READ_FN, i32, C.POINTER(vp)]
         L.hg_transcript_squeeze_challenge.argtypes = [vp, vp]
         L.hg_transcript_squeeze_challenges.argtypes = [vp, sz, vp]
         L.hg_transcript_write_felt_ext.argtypes = [vp, vp]
@@ -322,6 +328,54 @@ class Keccak256Transcript:
                 self.h = None
         except Exception:
             pass
+
+
+class CallbackTranscript(Keccak256Transcript):
+    """A transcript owned by the CALLER, handed to the library as callbacks (hg_transcript_from_callbacks): what the Rust shim
+    does with the `&mut dyn TranscriptWrite<F, E>` it receives in Node::prove_claim_reduction (lasso.rs:58-63). `inner` is any
+    object with squeeze_challenge() / write_felt_ext(e) / read_felt_ext(); every call the library makes is forwarded to it and
+    recorded in `log` as ("squeeze" | "write" | "read", limbs). A callback that raises makes the library call fail."""
+
+    def __init__(self, inner, field=GOLDILOCKS, message_independent=False):
+        self.field, self.inner, self.log = field, inner, []
+        self._el = LIMBS[field] * DEGREE[field]
+        el = self._el
+
+        def squeeze(_user, out):
+            try:
+                v = np.asarray(self.inner.squeeze_challenge(), np.uint64)
+                for i in range(el):
+                    out[i] = int(v[i])
+                self.log.append(("squeeze", tuple(int(x) for x in v)))
+                return 0
+            except Exception:
+                return 1
+
+        def write(_user, ext):
+            try:
+                v = np.array([ext[i] for i in range(el)], np.uint64)
+                self.inner.write_felt_ext(v)
+                self.log.append(("write", tuple(int(x) for x in v)))
+                return 0
+            except Exception:
+                return 1
+
+        def read(_user, out):
+            try:
+                v = np.asarray(self.inner.read_felt_ext(), np.uint64)
+                for i in range(el):
+                    out[i] = int(v[i])
+                self.log.append(("read", tuple(int(x) for x in v)))
+                return 0
+            except Exception:
+                return 1
+
+        self._cbs = (SQUEEZE_FN(squeeze), WRITE_FN(write), READ_FN(read))  # keep the trampolines alive
+        self.h = C.c_void_p()
+        _chk(lib().hg_transcript_from_callbacks(field, None, self._cbs[0], self._cbs[1], self._cbs[2], 1 if message_independent else 0, C.byref(self.h)))
+
+    def into_proof(self) -> bytes:
+        return self.inner.into_proof()
 
 
 class LassoPreprocessing:

@@ -303,12 +303,13 @@ template <class FP> struct FieldOpsT : IFieldOps {
         for (size_t i = 0; i < n; i++) { ha[i] = FP::x_from_limbs(a_ext + i * FP::X_LIMBS); hb[i] = FP::x_from_limbs(b_ext + i * FP::X_LIMBS); }
         DevBuf<X> a, b, o;
         a.alloc(n); b.alloc(n); o.alloc(n);
-        HG_CUDA(cudaMemcpy(a.p, ha.data(), n * sizeof(X), cudaMemcpyHostToDevice));
-        HG_CUDA(cudaMemcpy(b.p, hb.data(), n * sizeof(X), cudaMemcpyHostToDevice));
+        // stream-ordered copies: a blocking cudaMemcpy from pageable memory runs on the legacy stream, which a non-blocking stream does not wait for
+        HG_CUDA(cudaMemcpyAsync(a.p, ha.data(), n * sizeof(X), cudaMemcpyHostToDevice, ctx->stream));
+        HG_CUDA(cudaMemcpyAsync(b.p, hb.data(), n * sizeof(X), cudaMemcpyHostToDevice, ctx->stream));
         k_selftest<FP><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(op, a.p, b.p, n, o.p);
         HG_LAUNCH_CHECK();
+        HG_CUDA(cudaMemcpyAsync(ho.data(), o.p, n * sizeof(X), cudaMemcpyDeviceToHost, ctx->stream));
         HG_CUDA(cudaStreamSynchronize(ctx->stream));
-        HG_CUDA(cudaMemcpy(ho.data(), o.p, n * sizeof(X), cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < n; i++) FP::x_to_limbs(ho[i], out_ext + i * FP::X_LIMBS);
     }
     void sumcheck_prove(DeviceCtx* dev, const WireOptions& wo, int arity, size_t n_terms, size_t num_vars, const uint64_t* coeffs_ext, const void* d_tables,
@@ -322,7 +323,8 @@ template <class FP> struct FieldOpsT : IFieldOps {
         coeffs.alloc(n_terms);
         std::vector<X> hc(n_terms);
         for (size_t i = 0; i < n_terms; i++) hc[i] = FP::x_from_limbs(coeffs_ext + FP::X_LIMBS * i);
-        HG_CUDA(cudaMemcpy(coeffs.p, hc.data(), n_terms * sizeof(X), cudaMemcpyHostToDevice));
+        HG_CUDA(cudaMemcpyAsync(coeffs.p, hc.data(), n_terms * sizeof(X), cudaMemcpyHostToDevice, dev->stream));
+        HG_CUDA(cudaStreamSynchronize(dev->stream));  // hc is a stack temporary
         bufA.alloc(std::max<size_t>(ntab * (n / 2), ntab));
         bufB.alloc(std::max<size_t>(ntab * (n / 4), ntab));
         ScScratch sc;
@@ -461,7 +463,8 @@ int hg_ctx_create(int device, int field_id, hg_ctx** out) {
         HG_CUDA(cudaGetDeviceCount(&n));
         if (device < 0 || device >= n) throw std::runtime_error("no such CUDA device");
         HG_CUDA(cudaSetDevice(device));
-        std::unique_ptr<hg_ctx> c(new hg_ctx());
+        struct CtxDeleter { void operator()(hg_ctx* p) const { hg_ctx_destroy(p); } };  // a failing call below must not leak the streams / events made before it
+        std::unique_ptr<hg_ctx, CtxDeleter> c(new hg_ctx());
         c->ops.reset(make_ops(field_id));
         c->dev.device = device;
         c->field_id = field_id;
@@ -790,6 +793,14 @@ int hg_circuit_insert_vanilla(hg_circuit* c, size_t input_arity, size_t log2_sub
         d.arity = input_arity; d.log2_sub = log2_sub_input_size; d.num_reps = num_reps; d.n_gates = n_gates;
         d.has_const.assign(has_const, has_const + n_gates);
         d.consts.assign(consts, consts + n_gates * L);
+        if (!has_const || !consts || !add_ptr || !mul_ptr || !out_id || n_gates < 1) throw std::runtime_error("hg_circuit_insert_vanilla: NULL argument or no gates");
+        // the edge arrays are sized by the CSR pointers: check those before anything is read through them
+        if (add_ptr[0] != 0 || mul_ptr[0] != 0) throw std::runtime_error("hg_circuit_insert_vanilla: CSR pointers must start at 0");
+        for (size_t g = 0; g < n_gates; g++)
+            if (add_ptr[g + 1] < add_ptr[g] || mul_ptr[g + 1] < mul_ptr[g]) throw std::runtime_error("hg_circuit_insert_vanilla: CSR pointers must be non-decreasing");
+        if (add_ptr[n_gates] > ((uint64_t)1 << 40) || mul_ptr[n_gates] > ((uint64_t)1 << 40)) throw std::runtime_error("hg_circuit_insert_vanilla: implausible edge count");
+        if ((add_ptr[n_gates] && (!add_coef || !add_input || !add_wire)) || (mul_ptr[n_gates] && (!mul_coef || !mul_in0 || !mul_w0 || !mul_in1 || !mul_w1)))
+            throw std::runtime_error("hg_circuit_insert_vanilla: NULL edge array");
         d.add_ptr.assign(add_ptr, add_ptr + n_gates + 1);
         const size_t na = d.add_ptr[n_gates];
         d.add_coef.assign(add_coef, add_coef + na * L); d.add_in.assign(add_input, add_input + na); d.add_wire.assign(add_wire, add_wire + na);
@@ -819,7 +830,10 @@ void hg_gkr_timing(const hg_circuit* c, double* out_us6) { for (int i = 0; i < 6
 size_t hg_gkr_num_challenges(const hg_circuit* c) { return c->c->num_challenges(); }
 size_t hg_gkr_num_inputs(const hg_circuit* c) { return c->c->input_claims.size(); }
 size_t hg_gkr_num_input_claims(const hg_circuit* c, size_t input) { return input < c->c->input_claims.size() ? c->c->input_claims[input].size() : 0; }
-size_t hg_gkr_input_claim_num_vars(const hg_circuit* c, size_t input, size_t k) { return c->c->input_claims.at(input).at(k).nvars; }
+size_t hg_gkr_input_claim_num_vars(const hg_circuit* c, size_t input, size_t k) {  // 0 for an index out of range: no exception crosses the boundary
+    if (!c || input >= c->c->input_claims.size() || k >= c->c->input_claims[input].size()) return 0;
+    return c->c->input_claims[input][k].nvars;
+}
 int hg_gkr_input_claim(const hg_circuit* c, size_t input, size_t k, uint64_t* point_ext, uint64_t* value_ext) {
     HG_TRY({
         const auto& ic = c->c->input_claims.at(input).at(k);

@@ -63,7 +63,21 @@ template <class FP> class GkrCircuitDev {
         n.n_in = d.num_reps << d.log2_sub;
         n.a_pad = pad2(d.arity);
         const size_t ng = d.n_gates, sub = (size_t)1 << d.log2_sub;
-        const size_t n_add = d.add_ptr.at(ng), n_mul = d.mul_ptr.at(ng);
+        // the CSR comes from the caller: validate it before it indexes host arrays here and device arrays in the kernels
+        if (d.arity < 1 || d.arity > 4096 || d.log2_sub > 40 || d.num_reps < 1 || ng < 1) throw std::runtime_error("VanillaNode: bad shape");
+        if (d.add_ptr.size() != ng + 1 || d.mul_ptr.size() != ng + 1 || d.has_const.size() != ng) throw std::runtime_error("VanillaNode: CSR pointer arrays must have n_gates + 1 entries");
+        if (d.add_ptr[0] != 0 || d.mul_ptr[0] != 0) throw std::runtime_error("VanillaNode: CSR pointers must start at 0");
+        for (size_t g = 0; g < ng; g++)
+            if (d.add_ptr[g + 1] < d.add_ptr[g] || d.mul_ptr[g + 1] < d.mul_ptr[g]) throw std::runtime_error("VanillaNode: CSR pointers must be non-decreasing");
+        const size_t n_add = d.add_ptr[ng], n_mul = d.mul_ptr[ng];
+        if (d.add_in.size() < n_add || d.add_wire.size() < n_add || d.add_coef.size() < n_add * FP::B_LIMBS) throw std::runtime_error("VanillaNode: additive edge arrays are shorter than add_ptr[n_gates]");
+        if (d.mul_in0.size() < n_mul || d.mul_in1.size() < n_mul || d.mul_w0.size() < n_mul || d.mul_w1.size() < n_mul || d.mul_coef.size() < n_mul * FP::B_LIMBS)
+            throw std::runtime_error("VanillaNode: multiplicative edge arrays are shorter than mul_ptr[n_gates]");
+        for (size_t e = 0; e < n_add; e++)
+            if (d.add_in[e] >= d.arity || d.add_wire[e] >= sub) throw std::runtime_error("VanillaNode: additive edge " + std::to_string(e) + " points outside the inputs");
+        for (size_t e = 0; e < n_mul; e++)
+            if (d.mul_in0[e] >= d.arity || d.mul_in1[e] >= d.arity || d.mul_w0[e] >= sub || d.mul_w1[e] >= sub)
+                throw std::runtime_error("VanillaNode: multiplicative edge " + std::to_string(e) + " points outside the inputs");
         // classify
         n.is_linear = n_mul == 0;
         n.is_elemmul = false;
@@ -110,6 +124,7 @@ template <class FP> class GkrCircuitDev {
             }
         }
         n.value.alloc(n.out_len);
+        HG_CUDA(cudaDeviceSynchronize());  // blocking uploads from pageable memory vs non-blocking streams (see LassoNodeDev's constructor)
         nodes_.push_back(std::move(np));
         return (int)nodes_.size() - 1;
     }
@@ -431,7 +446,12 @@ template <class FP> class GkrCircuitDev {
         for (int id : topo()) {
             Node& n = *nodes_[id];
             if (n.kind == GKR_INPUT) continue;
-            if (n.kind == GKR_LASSO) { chal += n.lasso->total_challenges(); msg += n.lasso->message_budget(); continue; }
+            if (n.kind == GKR_LASSO) {
+                if (n.preds.size() != 1) throw std::runtime_error("prove_gkr: the Lasso node takes exactly one input (lasso.rs:64)");
+                if (nodes_[n.preds[0]]->out_len < n.lasso->num_rows()) throw std::runtime_error("prove_gkr: the Lasso node's input is shorter than its lookups");
+                chal += n.lasso->total_challenges(); msg += n.lasso->message_budget();
+                continue;
+            }
             const size_t S = n.kind == GKR_FFT || n.is_elemmul ? n.out_len : n.a_pad * n.n_in;
             const int nv = log2sz(S), nt = n.is_elemmul ? 2 : 1;
             size_t n_claims = std::max<size_t>(1, n.succs.size());  // one claim per successor edge (upper bound: every successor pushes one)

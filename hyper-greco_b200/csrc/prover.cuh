@@ -102,8 +102,8 @@ template <class T> struct DevBuf {
     ~DevBuf() { release(); }
     void alloc(size_t count) {
         release();
-        n = count;
         if (count) HG_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+        n = count;  // only after the allocation succeeded: `buf.n < need` checks must not skip a retry
     }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
     size_t bytes() const { return n * sizeof(T); }
@@ -720,8 +720,15 @@ template <class FP> class LassoNodeDev {
         HG_CUDA(cudaMemset(d_gp_counters_.p, 0, d_gp_counters_.bytes()));
         h_desc_.alloc(1 << 16);
         d_desc_.alloc(1 << 16);
-        HG_CUDA(cudaFuncSetAttribute(k_gp_tail<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)((size_t)2 * (2 * m_) * ((1 << FP::GP_TAIL_LOG) + (1 << FP::GP_TAIL_LOG) / 2) * sizeof(X) + 32 * 4 * sizeof(X))));
+        {
+            const size_t tail_smem = (size_t)2 * (2 * m_) * ((1 << FP::GP_TAIL_LOG) + (1 << FP::GP_TAIL_LOG) / 2) * sizeof(X) + 32 * 4 * sizeof(X);
+            int smem_max = 0;
+            HG_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+            if (tail_smem > (size_t)smem_max)
+                throw std::runtime_error("LassoNode: " + std::to_string(m_) + " memories need " + std::to_string(tail_smem) + " bytes of shared memory in the grand-product tail kernel, the device offers " +
+                                         std::to_string(smem_max) + " (at most " + std::to_string((smem_max - 32 * 4 * sizeof(X)) / (6 * ((size_t)1 << FP::GP_TAIL_LOG) * sizeof(X))) + " memories for this field)");
+            HG_CUDA(cudaFuncSetAttribute(k_gp_tail<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
+        }
         max_blocks_ = ctx->sm_count * 8;
         size_t batch = std::max<size_t>((size_t)m_, pp.C);
         d_partials_.alloc((size_t)max_blocks_ * 4 * batch);
@@ -748,6 +755,9 @@ template <class FP> class LassoNodeDev {
             HG_CUDA(cudaMemcpy(d_wpow_.p, wp.data(), wp.size() * sizeof(B), cudaMemcpyHostToDevice));
         }
         HG_CUDA(cudaFuncSetAttribute(k_tree_tail<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HG_TREE_TAIL * sizeof(B))));
+        // the uploads above are blocking cudaMemcpy calls from pageable memory (legacy stream); the proof kernels run on non-blocking
+        // streams that do not wait for it, so make everything land now
+        HG_CUDA(cudaDeviceSynchronize());
         HG_CUDA(cudaFuncSetAttribute(k_prod_tail_one<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)(((size_t)2 * 3 * ((size_t)1 << HG_PROD_TAIL_LOG) + 96) * sizeof(X))));
     }
@@ -844,6 +854,10 @@ template <class FP> class LassoNodeDev {
         // evaluation and the collation sumcheck; enqueue_protocol joins before the first kernel that reads them
         const bool side = ctx_->two_streams && !ctx_->profile && ctx_->stream3 != nullptr;
         cudaStream_t cs = s;
+        struct StreamRestore {  // an exception between here and the join must not leave the context launching on stream3
+            DeviceCtx* c; cudaStream_t main;
+            ~StreamRestore() { c->stream = main; }
+        } restore{ctx_, s};
         if (side) {
             HG_CUDA(cudaEventRecord(ctx_->ev_fork3, s));
             HG_CUDA(cudaStreamWaitEvent(ctx_->stream3, ctx_->ev_fork3, 0));

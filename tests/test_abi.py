@@ -60,6 +60,32 @@ def test_transcript_matches_oracle_chain(api, oracle):
         api.Keccak256Transcript.from_proof(b"\xff" * 16).read_felt_ext()
 
 
+def test_callback_transcript_forwards_every_primitive(api):
+    """hg_transcript_from_callbacks: the caller-owned transcript of Node::prove_claim_reduction (lasso.rs:58-63). Squeezes,
+    writes and reads reach the callbacks with canonical limbs; a failing callback becomes an error code."""
+    for field in (api.GOLDILOCKS, api.BN254):
+        inner = api.Keccak256Transcript(field)
+        ref = api.Keccak256Transcript(field)
+        t = api.CallbackTranscript(inner, field)
+        c = t.squeeze_challenge()
+        assert (c == ref.squeeze_challenge()).all()
+        t.write_felt_ext(c)
+        ref.write_felt_ext(c)
+        assert t.into_proof() == ref.into_proof() and len(t.into_proof()) == (16 if field == api.GOLDILOCKS else 32)
+        assert [k for k, _ in t.log] == ["squeeze", "write"] and t.log[1][1] == tuple(int(x) for x in c)
+        rd = api.CallbackTranscript(api.Keccak256Transcript.from_proof(ref.into_proof(), field), field)
+        assert (rd.read_felt_ext() == c).all()
+        with pytest.raises(api.HgError):   # the inner transcript is exhausted: its exception becomes a non-zero callback return
+            rd.read_felt_ext()
+
+    class Broken:
+        def squeeze_challenge(self):
+            raise RuntimeError("no")
+
+    with pytest.raises(api.HgError):
+        api.CallbackTranscript(Broken()).squeeze_challenge()
+
+
 def test_preprocessing_matches_oracle(api, oracle):
     from hyper_greco_b200 import params, witness
     for name, P in params.PARAMS.items():

@@ -586,3 +586,141 @@ def test_bn254_ntt_matches_oracle(api, ctx_bn, oracle):
             got = d.to_field(2 << log_n).reshape(x.shape)
             assert (got == oracle.ntt(1, x, log_n, inverse).reshape(x.shape)).all(), (log_n, inverse)
             d.free()
+
+
+# ------------------------------------------------------------------------------------------------ full-size byte parity
+def _fullsize_meta(golden_dir, key):
+    import json
+    import os
+    meta = json.load(open(os.path.join(golden_dir, "golden_proofs.json"))).get("fullsize", {})
+    if key not in meta:
+        pytest.skip(f"{key} not generated yet (tests/golden/make_golden_fullsize.py)")
+    return meta[key]
+
+
+def _assert_hash(proof, meta, what):
+    import hashlib
+    assert len(proof) == meta["bytes"], what
+    assert hashlib.sha256(proof).hexdigest() == meta["sha256"], f"{what}: device proof bytes differ from the CPU oracle's (committed sha256)"
+
+
+def test_fullsize_lasso_node_bytes_equal_oracle_hash(api, ctx, golden_dir):
+    """BASELINE.json config 4 (n=32768, k=16, Goldilocks): the Lasso node's proof BYTES equal the CPU oracle's, through the
+    committed sha256 (tests/golden/make_golden_fullsize.py). Host input and device-resident input, prefetch mode; interactive too."""
+    from hyper_greco_b200 import params, witness
+    meta = _fullsize_meta(golden_dir, "goldilocks_lasso_node_n32768_seed0")
+    P = params.by_n(32768)
+    inp = np.array(witness.lasso_inputs(P, witness.synth_witness(P, 0)), dtype=np.uint64)
+    bounds, segs, nv = witness.lasso_lookup_bounds(P), witness.lasso_lookup_segments(P), witness.lasso_num_vars(P)
+    node, pp, tr, pt, val = _prove_gpu(api, ctx, bounds, segs, nv, inp, 0, device_resident=True)
+    _assert_hash(tr.into_proof(), meta, "lasso node n=32768 (prefetch)")
+    tr = api.Keccak256Transcript()
+    node.prove_claim_reduction(inp, tr, 1)
+    _assert_hash(tr.into_proof(), meta, "lasso node n=32768 (interactive)")
+    node.free()
+
+
+@pytest.mark.parametrize("n,seed", [(32768, 5), (16384, 3)])
+def test_fullsize_bfv_encrypt_bytes_equal_oracle_hash(api, ctx, golden_dir, n, seed):
+    """BASELINE.json configs 3 and 4: whole BfvEncrypt::prove from HOST vectors (prove_host: H2D, evaluate, output claim,
+    prove_gkr) gives the CPU oracle's bytes at n=16384 k=8 and n=32768 k=16."""
+    from hyper_greco_b200 import params, witness
+    meta = _fullsize_meta(golden_dir, f"goldilocks_bfv_encrypt_n{n}_seed{seed}")
+    P = params.by_n(n)
+    ins, ct0is = witness.get_inputs(P, witness.synth_witness(P, seed))
+    flat = [np.array(v, dtype=np.uint64) for v in [ins["s"], ins["e"], ins["k1"]] + list(ins["ais"]) + list(ins["r1is"]) + [ins["r2is"]]]
+    prover = api.BfvSkEncryptProver(ctx, P)
+    proof, _ = prover.prove_host(flat, np.array(ct0is, dtype=np.uint64), 0)
+    _assert_hash(proof, meta, f"BfvEncrypt::prove n={n}")
+    prover.circuit.free()
+    prover.lasso.free()
+
+
+def _bn_limbs(vals):
+    return np.array([[(int(v) >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)] for v in vals], dtype=np.uint64)
+
+
+def test_fullsize_bn254_bytes_equal_oracle_hash(api, ctx_bn, oracle, golden_dir):
+    """BASELINE.json config 5 (n=32768, k=16, BN254 Fr): Lasso node and whole BfvEncrypt::prove against the CPU oracle's
+    sha256; the oracle verifier accepts the device proof of the node."""
+    from hyper_greco_b200 import params, witness
+    P = params.by_n(32768)
+    bounds, segs, nv = witness.lasso_lookup_bounds(P), witness.lasso_lookup_segments(P), witness.lasso_num_vars(P)
+    meta = _fullsize_meta(golden_dir, "bn254_lasso_node_n32768_seed0")
+    inp = _bn_limbs(witness.lasso_inputs(P, witness.synth_witness(P, 0, p=witness.BN_R), p=witness.BN_R))
+    pp = api.LassoPreprocessing.preprocess(bounds)
+    node = api.LassoNode(ctx_bn, pp, nv, segs)
+    tr = api.Keccak256Transcript(api.BN254)
+    node.prove_claim_reduction(inp, tr, 0)
+    proof = tr.into_proof()
+    node.free()
+    _assert_hash(proof, meta, "bn254 lasso node n=32768")
+    oracle.lasso_verify(1, oracle.Preprocessing(bounds), nv, proof)
+    meta = _fullsize_meta(golden_dir, "bn254_bfv_encrypt_n32768_seed5")
+    ins, ct0is = witness.get_inputs(P, witness.synth_witness(P, 5, p=witness.BN_R))
+    flat = [_bn_limbs(v).reshape(-1) for v in [ins["s"], ins["e"], ins["k1"]] + list(ins["ais"]) + list(ins["r1is"]) + [ins["r2is"]]]
+    prover = api.BfvSkEncryptProver(ctx_bn, P)
+    proof, _ = prover.prove_host(flat, _bn_limbs(ct0is).reshape(-1), 0)
+    _assert_hash(proof, meta, "bn254 BfvEncrypt::prove n=32768")
+    prover.circuit.free()
+    prover.lasso.free()
+
+
+# ------------------------------------------------------------------------------------------------ caller-owned transcript
+@pytest.mark.parametrize("independent", [False, True])
+def test_lasso_node_with_callback_transcript(api, ctx, golden_dir, independent):
+    """hg_transcript_from_callbacks: the `&mut dyn TranscriptWrite<F, E>` of Node::prove_claim_reduction (lasso.rs:58-63) as C
+    callbacks. The library is asked for prefetch mode; a transcript that may absorb messages forces the interactive schedule
+    (squeezes interleaved with writes, in protocol order), one declared message-independent is prefetched (all squeezes of the
+    node first). Either way the bytes the CALLER's transcript ends up with are the committed golden proof."""
+    import os
+    from hyper_greco_b200 import params, witness
+    name = "1024_1x27_65537"
+    P = params.PARAMS[name]
+    golden = open(os.path.join(golden_dir, f"proof_goldilocks_lasso_node_{name}.bin"), "rb").read()
+    inp = np.load(os.path.join(golden_dir, f"lasso_inputs_{name}.npz"))["inputs"]
+    bounds, segs, nv = witness.lasso_lookup_bounds(P), witness.lasso_lookup_segments(P), witness.lasso_num_vars(P)
+    node = api.LassoNode(ctx, api.LassoPreprocessing.preprocess(bounds), nv, segs)
+    tr = api.CallbackTranscript(api.Keccak256Transcript(), message_independent=independent)
+    pt, val = node.prove_claim_reduction(inp, tr, api.MODE_PREFETCH)
+    assert tr.into_proof() == golden
+    kinds = [k for k, _ in tr.log]
+    n_sq, first_write = kinds.count("squeeze"), kinds.index("write")
+    assert kinds.count("write") * 16 == len(golden)
+    if independent:
+        assert first_write == n_sq                      # every challenge of the node was squeezed before the first message
+    else:
+        assert first_write == nv                        # r (lasso.rs:85), then the claimed sum (:269): strictly protocol order
+        assert "squeeze" in kinds[first_write:]         # and challenges keep coming between messages
+    assert [tuple(int(x) for x in p) for p in pt] == [v for k, v in tr.log if k == "squeeze"][:nv]
+    # a callback that fails surfaces as an error, not as a crash
+    class Failing(api.Keccak256Transcript):
+        def write_felt_ext(self, e):
+            raise RuntimeError("sink is full")
+    with pytest.raises(api.HgError):
+        node.prove_claim_reduction(inp, api.CallbackTranscript(Failing()), api.MODE_PREFETCH)
+    tr2 = api.Keccak256Transcript()                     # the node is still usable afterwards
+    node.prove_claim_reduction(inp, tr2, api.MODE_PREFETCH)
+    assert tr2.into_proof() == golden
+    node.free()
+
+
+def test_full_gkr_prove_with_callback_transcript(api, ctx, golden_dir):
+    """gkr::prove_gkr of the whole circuit with a caller-owned transcript (interactive schedule): committed golden bytes."""
+    import os
+    from hyper_greco_b200 import params
+    name = "1024_1x27_65537"
+    P = params.PARAMS[name]
+    golden = open(os.path.join(golden_dir, f"proof_goldilocks_bfv_encrypt_{name}.bin"), "rb").read()
+    io = np.load(os.path.join(golden_dir, f"circuit_io_{name}.npz"))
+    prover = api.BfvSkEncryptProver(ctx, P)
+    dev = prover.upload_inputs({k: io[k] for k in ("s", "e", "k1", "ais", "r1is", "r2is")})
+    d_ct = api.DeviceBuffer.from_numpy(ctx, io["ct0is"])
+    prover.circuit.evaluate(dev)
+    tr = api.CallbackTranscript(api.Keccak256Transcript())
+    L = prover.ct0is_log2_size
+    point = tr.squeeze_challenges(L)
+    value = api.mle_eval_batch(ctx, d_ct, 1, L, point)[0]
+    el = point.shape[1]
+    prover.circuit.prove_gkr([(np.zeros((0, el), np.uint64), np.zeros(el, np.uint64)), (point, value)], tr, api.MODE_PREFETCH)
+    assert tr.into_proof() == golden
