@@ -30,7 +30,7 @@ SYMBOLS = [
     "hg_lasso_pp_lookup_index", "hg_lasso_pp_memory_maps", "hg_lasso_pp_subtable_id", "hg_lasso_node_new", "hg_lasso_node_free",
     "hg_lasso_node_log2_input_size", "hg_lasso_node_device_bytes", "hg_lasso_node_prove", "hg_lasso_node_download_polys",
     "hg_lasso_node_num_chunks", "hg_lasso_node_timing", "hg_lasso_node_shard_words", "hg_lasso_node_prove_shard", "hg_lasso_node_emit_shard",
-    "hg_shard_merge", "hg_lasso_node_verify", "hg_sumcheck_prove", "hg_mle_eval_batch", "hg_ntt", "hg_bfv_evaluate", "hg_field_selftest",
+    "hg_shard_merge", "hg_lasso_node_prove_shard_dev", "hg_lasso_node_emit_shard_dev", "hg_shard_merge_device", "hg_gkr_shard_words", "hg_gkr_prove_shard_dev", "hg_gkr_emit_shard_dev", "hg_lasso_node_verify", "hg_sumcheck_prove", "hg_mle_eval_batch", "hg_ntt", "hg_bfv_evaluate", "hg_field_selftest",
     "hg_circuit_new", "hg_circuit_free", "hg_circuit_insert_input", "hg_circuit_insert_fft", "hg_circuit_insert_lasso", "hg_circuit_insert_vanilla",
     "hg_circuit_connect", "hg_circuit_evaluate", "hg_circuit_evaluate_host", "hg_circuit_node_value", "hg_gkr_prove", "hg_gkr_timing", "hg_gkr_num_challenges", "hg_gkr_num_inputs", "hg_gkr_num_input_claims",
     "hg_gkr_input_claim_num_vars", "hg_gkr_input_claim",
@@ -118,6 +118,13 @@ def lib():
         L.hg_lasso_node_prove_shard.argtypes = [vp, vp, sz, i32, vp, i32, i32, vp, sz, C.POINTER(sz)]
         L.hg_lasso_node_emit_shard.argtypes = [vp, vp, sz, vp, vp]
         L.hg_shard_merge.argtypes = [i32, vp, vp, sz]
+        L.hg_lasso_node_prove_shard_dev.argtypes = [vp, vp, sz, i32, vp, i32, i32, vp, sz, C.POINTER(sz)]
+        L.hg_lasso_node_emit_shard_dev.argtypes = [vp, vp, sz, vp, vp]
+        L.hg_shard_merge_device.argtypes = [vp, vp, i32, sz, vp]
+        L.hg_gkr_shard_words.argtypes = [vp]
+        L.hg_gkr_shard_words.restype = sz
+        L.hg_gkr_prove_shard_dev.argtypes = [vp, sz, vp, vp, vp, vp, i32, i32, vp, sz, C.POINTER(sz)]
+        L.hg_gkr_emit_shard_dev.argtypes = [vp, vp, sz]
         L.hg_lasso_node_verify.argtypes = [vp, sz, vp, vp, vp, vp]
         L.hg_sumcheck_prove.argtypes = [vp, i32, sz, sz, vp, vp, vp, vp, i32, vp, vp]
         L.hg_mle_eval_batch.argtypes = [vp, vp, sz, sz, sz, vp, vp]
@@ -165,6 +172,7 @@ class Context:
 
     def __init__(self, device=0, field=GOLDILOCKS):
         self.field = field
+        self.device = device
         self.h = C.c_void_p()
         _chk(lib().hg_ctx_create(device, field, C.byref(self.h)))
 
@@ -496,6 +504,29 @@ class LassoNode:
         _chk(lib().hg_lasso_node_emit_shard(self.h, _p(merged), merged.size, _p(pt), _p(val)))
         return pt, val
 
+    @property
+    def shard_words(self):
+        return int(lib().hg_lasso_node_shard_words(self.h))
+
+    def prove_shard_dev(self, inputs, transcript: Keccak256Transcript, rank: int, world: int, d_out_ptr: int, cap_words: int, n_inputs=None):
+        """prove_shard without leaving the device: this rank's partial message buffer is copied to device memory at d_out_ptr
+        (stream-ordered on the context's stream). Returns the number of 64-bit words written."""
+        nw = C.c_size_t(0)
+        if isinstance(inputs, DeviceBuffer):
+            n = n_inputs if n_inputs is not None else inputs.nbytes // (8 * LIMBS[self.ctx.field])
+            _chk(lib().hg_lasso_node_prove_shard_dev(self.h, inputs.ptr, n, 1, transcript.h, rank, world, C.c_void_p(d_out_ptr), cap_words, C.byref(nw)))
+        else:
+            arr = np.ascontiguousarray(inputs, np.uint64)
+            n = arr.size // LIMBS[self.ctx.field]
+            _chk(lib().hg_lasso_node_prove_shard_dev(self.h, _p(arr), n, 0, transcript.h, rank, world, C.c_void_p(d_out_ptr), cap_words, C.byref(nw)))
+        return int(nw.value)
+
+    def emit_shard_dev(self, d_merged_ptr: int, n_words: int):
+        pt = np.zeros((self.num_vars, self._el), np.uint64)
+        val = np.zeros(self._el, np.uint64)
+        _chk(lib().hg_lasso_node_emit_shard_dev(self.h, C.c_void_p(d_merged_ptr), n_words, _p(pt), _p(val)))
+        return pt, val
+
     def prove_claim_reduction_sharded(self, inputs, transcript: Keccak256Transcript, group=None, n_inputs=None):
         """prove_claim_reduction with the node's grand-product terms split over the ranks of a torch.distributed group
         (one process per GPU, every rank holds the inputs and a transcript in the same state). The only exchange is one
@@ -557,6 +588,46 @@ def shard_merge(field: int, acc, part):
         raise HgError("shard_merge: buffers of different length")
     _chk(lib().hg_shard_merge(field, _p(acc), _p(part), acc.size))
     return acc
+
+
+def shard_merge_device(ctx: "Context", d_parts_ptr: int, world: int, n_words: int, d_acc_ptr: int):
+    """acc = element-wise field sum of the `world` gathered message buffers ([world][n_words] at d_parts_ptr), on the context's stream."""
+    _chk(lib().hg_shard_merge_device(ctx.h, C.c_void_p(d_parts_ptr), world, n_words, C.c_void_p(d_acc_ptr)))
+
+
+class ShardExchange:
+    """Device-side exchange of one sharded proof (hg_b200.h): per-rank partial buffer -> NCCL all-gather over NVLink (enqueued
+    behind the library's stream) -> one merge kernel -> rank 0 serialises. Buffers are torch tensors owned by this object."""
+
+    def __init__(self, ctx: "Context", cap_words: int, group=None):
+        import torch
+        import torch.distributed as dist
+        self.ctx, self.group, self.cap = ctx, group, cap_words
+        self.dist = dist if dist.is_available() and dist.is_initialized() else None
+        self.rank = self.dist.get_rank(group) if self.dist else 0
+        self.world = self.dist.get_world_size(group) if self.dist else 1
+        dev = torch.device("cuda", ctx.device)
+        self.torch = torch
+        self.part = torch.zeros(cap_words, dtype=torch.int64, device=dev)
+        self.gathered = torch.zeros(self.world * cap_words, dtype=torch.int64, device=dev)
+        self.merged = torch.zeros(cap_words, dtype=torch.int64, device=dev)
+        self.stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def run(self, prove_shard_dev, emit_shard_dev):
+        """prove_shard_dev(rank, world, d_out_ptr, cap) -> n_words;  emit_shard_dev(d_merged_ptr, n_words) -> result (rank 0 only)."""
+        n = prove_shard_dev(self.rank, self.world, self.part.data_ptr(), self.cap)
+        if self.world == 1:
+            return emit_shard_dev(self.part.data_ptr(), n)
+        with self.torch.cuda.stream(self.stream):     # the collective waits for everything the library enqueued
+            g = self.gathered[: self.world * n]
+            self.dist.all_gather_into_tensor(g, self.part[:n], group=self.group)
+        shard_merge_device(self.ctx, g.data_ptr(), self.world, n, self.merged.data_ptr())
+        if self.rank != 0:
+            self.ctx.synchronize()
+            return None
+        return emit_shard_dev(self.merged.data_ptr(), n)
+
+    exchange_bytes_per_rank = property(lambda self: 8 * self.cap)
 
 
 def gather_and_merge(field: int, part, group=None):
@@ -729,11 +800,12 @@ class Circuit:
 
     def prove_gkr(self, output_claims, transcript: Keccak256Transcript, mode=MODE_PREFETCH):
         """output_claims: [(point [nv, el] uint64, value [el] uint64), ...]. Returns per input node a list of (point, value)."""
-        el = self.ctx and LIMBS[self.ctx.field] * DEGREE[self.ctx.field]
-        lens = np.array([len(p) for p, _ in output_claims], dtype=np.uint64)
-        pts = np.concatenate([np.asarray(p, np.uint64).reshape(-1) for p, _ in output_claims] + [np.zeros(0, np.uint64)])
-        vals = np.concatenate([np.asarray(v, np.uint64).reshape(-1) for _, v in output_claims])
-        _chk(lib().hg_gkr_prove(self.h, len(output_claims), _p(lens), _p(np.ascontiguousarray(pts)), _p(np.ascontiguousarray(vals)), transcript.h, mode))
+        lens, pts, vals = self._claims_args(output_claims)
+        _chk(lib().hg_gkr_prove(self.h, len(output_claims), _p(lens), _p(pts), _p(vals), transcript.h, mode))
+        return self._read_input_claims()
+
+    def _read_input_claims(self):
+        el = LIMBS[self.ctx.field] * DEGREE[self.ctx.field]
         out = []
         for i in range(lib().hg_gkr_num_inputs(self.h)):
             cl = []
@@ -751,6 +823,29 @@ class Circuit:
         d = dict(zip(("witness_enqueue_us", "challenges_us", "protocol_walk_us", "layer_enqueue_us", "gpu_wait_us", "serialise_us"), (float(x) for x in out)))
         d["ext_challenges"] = int(lib().hg_gkr_num_challenges(self.h))
         return d
+
+    @property
+    def shard_words(self):
+        return int(lib().hg_gkr_shard_words(self.h))
+
+    def _claims_args(self, output_claims):
+        lens = np.array([len(p) for p, _ in output_claims], dtype=np.uint64)
+        pts = np.concatenate([np.asarray(p, np.uint64).reshape(-1) for p, _ in output_claims] + [np.zeros(0, np.uint64)])
+        vals = np.concatenate([np.asarray(v, np.uint64).reshape(-1) for _, v in output_claims] + [np.zeros(0, np.uint64)])
+        return lens, np.ascontiguousarray(pts), np.ascontiguousarray(vals)
+
+    def prove_gkr_shard_dev(self, output_claims, transcript: "Keccak256Transcript", rank: int, world: int, d_out_ptr: int, cap_words: int):
+        """This rank's part of ONE gkr::prove_gkr split over `world` GPUs (hg_gkr_prove_shard_dev): its partial message buffer is
+        copied to device memory at d_out_ptr. Returns the number of words."""
+        lens, pts, vals = self._claims_args(output_claims)
+        nw = C.c_size_t(0)
+        _chk(lib().hg_gkr_prove_shard_dev(self.h, len(output_claims), _p(lens), _p(pts), _p(vals), transcript.h, rank, world, C.c_void_p(d_out_ptr), cap_words, C.byref(nw)))
+        return int(nw.value)
+
+    def emit_shard_dev(self, d_merged_ptr: int, n_words: int):
+        """Rank 0: serialise the merged buffer into the transcript given to prove_gkr_shard_dev; returns the input claims."""
+        _chk(lib().hg_gkr_emit_shard_dev(self.h, C.c_void_p(d_merged_ptr), n_words))
+        return self._read_input_claims()
 
     def free(self):
         if self.h:

@@ -70,6 +70,15 @@ template <class FP> __global__ void k_field_encode(typename FP::B* p, size_t n, 
     }
 }
 
+// acc[i] = sum over parts of parts[r][i] in the extension field (the message buffers of the devices of one sharded proof)
+template <class FP> __global__ void k_shard_merge(const typename FP::X* __restrict__ parts, int world, size_t n, typename FP::X* __restrict__ acc) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    typename FP::X s = parts[i];
+    for (int r = 1; r < world; r++) s = FP::x_add(s, parts[(size_t)r * n + i]);
+    acc[i] = s;
+}
+
 struct ILassoNode {
     int field_id = 0;
     size_t log2_input_size = 0;
@@ -79,6 +88,9 @@ struct ILassoNode {
     virtual void prove_shard(DeviceCtx* dev, const void* inputs, size_t n_inputs, bool on_device, ITranscript* t, const WireOptions& wo, int rank, int world,
                              uint64_t* out_words, size_t cap_words, size_t* n_words) = 0;
     virtual void emit_shard(const uint64_t* merged, size_t n_words, uint64_t* out_point, uint64_t* out_value) = 0;
+    virtual size_t prove_shard_dev(DeviceCtx* dev, const void* inputs, size_t n_inputs, bool on_device, ITranscript* t, const WireOptions& wo, int rank, int world,
+                                   void* d_out_words, size_t cap_words) = 0;
+    virtual void emit_shard_dev(const void* d_merged, size_t n_words, uint64_t* out_point, uint64_t* out_value) = 0;
     virtual size_t shard_words() const = 0;
     virtual size_t device_bytes() const = 0;
     virtual size_t num_chunks() const = 0;
@@ -131,6 +143,18 @@ template <class FP> struct LassoNodeT : ILassoNode {
         if (out_point) for (size_t i = 0; i < pt.size(); i++) FP::x_to_limbs(pt[i], out_point + FP::X_LIMBS * i);
         if (out_value) FP::x_to_limbs(val, out_value);
     }
+    size_t prove_shard_dev(DeviceCtx* dev, const void* inputs, size_t n_inputs, bool on_device, ITranscript* t, const WireOptions& wo, int rank, int world,
+                           void* d_out_words, size_t cap_words) override {
+        return XW * node.prove_shard_dev(stage(dev, inputs, n_inputs, on_device), n_inputs, *(Keccak256Transcript<FP>*)t->raw(), wo, rank, world, (X*)d_out_words, cap_words / XW);
+    }
+    void emit_shard_dev(const void* d_merged, size_t n_words, uint64_t* out_point, uint64_t* out_value) override {
+        if (n_words % XW) throw std::runtime_error("emit_shard: truncated message buffer");
+        std::vector<X> pt;
+        X val;
+        node.emit_shard_dev((const X*)d_merged, n_words / XW, &pt, &val);
+        if (out_point) for (size_t i = 0; i < pt.size(); i++) FP::x_to_limbs(pt[i], out_point + FP::X_LIMBS * i);
+        if (out_value) FP::x_to_limbs(val, out_value);
+    }
     size_t shard_words() const override { return node.shard_message_count() * XW; }
     size_t device_bytes() const override { return node.device_bytes(); }
     size_t num_chunks() const override { return node.chunk_dims().size(); }
@@ -162,6 +186,10 @@ struct ICircuit {
     virtual void prove(size_t n_claims, const size_t* lens, const uint64_t* pts, const uint64_t* vals, ITranscript* t, int mode, const WireOptions& wo) = 0;
     virtual const double* timing() const = 0;
     virtual size_t num_challenges() const = 0;
+    virtual size_t shard_words() = 0;
+    virtual size_t prove_shard_dev(size_t n_claims, const size_t* lens, const uint64_t* pts, const uint64_t* vals, ITranscript* t, const WireOptions& wo, int rank, int world,
+                                   void* d_out_words, size_t cap_words) = 0;
+    virtual void emit_shard_dev(const void* d_merged, size_t n_words) = 0;
 };
 template <class FP> struct CircuitT : ICircuit {
     typedef typename FP::B B;
@@ -219,8 +247,9 @@ template <class FP> struct CircuitT : ICircuit {
         *p = c.node_value(id);
         *len = c.node_out_len(id);
     }
-    void prove(size_t n_claims, const size_t* lens, const uint64_t* pts, const uint64_t* vals, ITranscript* t, int mode, const WireOptions& wo) override {
-        if (t->field_id != FP::FIELD_ID) throw std::runtime_error("transcript belongs to another field");
+    typedef typename FP::X X;
+    static constexpr size_t XW = sizeof(X) / sizeof(uint64_t);
+    std::vector<typename GkrCircuitDev<FP>::InputClaim> output_claims(size_t n_claims, const size_t* lens, const uint64_t* pts, const uint64_t* vals) {
         std::vector<typename GkrCircuitDev<FP>::InputClaim> oc(n_claims);
         size_t off = 0;
         for (size_t i = 0; i < n_claims; i++) {
@@ -228,7 +257,23 @@ template <class FP> struct CircuitT : ICircuit {
             off += lens[i];
             oc[i].value = FP::x_from_limbs(vals + FP::X_LIMBS * i);
         }
-        auto res = c.prove(*(Keccak256Transcript<FP>*)t->raw(), mode == HG_MODE_INTERACTIVE ? kModeInteractive : kModePrefetch, wo, oc);
+        return oc;
+    }
+    size_t shard_words() override { return c.shard_message_count() * XW; }
+    size_t prove_shard_dev(size_t n_claims, const size_t* lens, const uint64_t* pts, const uint64_t* vals, ITranscript* t, const WireOptions& wo, int rank, int world,
+                           void* d_out_words, size_t cap_words) override {
+        if (t->field_id != FP::FIELD_ID) throw std::runtime_error("transcript belongs to another field");
+        return XW * c.prove_shard_dev(*(Keccak256Transcript<FP>*)t->raw(), wo, output_claims(n_claims, lens, pts, vals), rank, world, (X*)d_out_words, cap_words / XW);
+    }
+    void emit_shard_dev(const void* d_merged, size_t n_words) override {
+        if (n_words % XW) throw std::runtime_error("emit_shard: truncated message buffer");
+        set_input_claims(c.emit_shard_dev((const X*)d_merged, n_words / XW));
+    }
+    void prove(size_t n_claims, const size_t* lens, const uint64_t* pts, const uint64_t* vals, ITranscript* t, int mode, const WireOptions& wo) override {
+        if (t->field_id != FP::FIELD_ID) throw std::runtime_error("transcript belongs to another field");
+        set_input_claims(c.prove(*(Keccak256Transcript<FP>*)t->raw(), mode == HG_MODE_INTERACTIVE ? kModeInteractive : kModePrefetch, wo, output_claims(n_claims, lens, pts, vals)));
+    }
+    void set_input_claims(const std::vector<std::vector<typename GkrCircuitDev<FP>::InputClaim>>& res) {
         input_claims.clear();
         for (auto& v : res) {
             std::vector<InputClaimErased> e;
@@ -254,6 +299,7 @@ struct IFieldOps {
     virtual ITranscript* new_transcript() = 0;
     virtual ILassoNode* new_lasso_node(DeviceCtx* ctx, const LassoPreprocessing& pp, int nv, const std::vector<uint8_t>& rows) = 0;
     virtual ICircuit* new_circuit(DeviceCtx* ctx) = 0;
+    virtual void shard_merge_device(DeviceCtx* ctx, const void* d_parts, int world, size_t n_words, void* d_acc) = 0;
     virtual void sumcheck_prove(DeviceCtx* ctx, const WireOptions& wo, int arity, size_t n_terms, size_t num_vars, const uint64_t* coeffs, const void* d_tables,
                                 const uint64_t* claim, ITranscript* t, int mode, uint64_t* out_point, uint64_t* out_evals) = 0;
     virtual void mle_eval_batch(DeviceCtx* ctx, const void* d_tables, size_t n_tables, size_t stride, size_t num_vars, const uint64_t* point, uint64_t* out) = 0;
@@ -311,6 +357,13 @@ template <class FP> struct FieldOpsT : IFieldOps {
         HG_CUDA(cudaMemcpyAsync(ho.data(), o.p, n * sizeof(X), cudaMemcpyDeviceToHost, ctx->stream));
         HG_CUDA(cudaStreamSynchronize(ctx->stream));
         for (size_t i = 0; i < n; i++) FP::x_to_limbs(ho[i], out_ext + i * FP::X_LIMBS);
+    }
+    void shard_merge_device(DeviceCtx* ctx, const void* d_parts, int world, size_t n_words, void* d_acc) override {
+        constexpr size_t XW = sizeof(X) / sizeof(uint64_t);
+        if (n_words % XW || world < 1) throw std::runtime_error("hg_shard_merge_device: bad arguments");
+        const size_t n = n_words / XW;
+        if (!n) return;
+        HG_K(ctx, KC_MISC, 0, k_shard_merge<FP><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const X*)d_parts, world, n, (X*)d_acc));
     }
     void sumcheck_prove(DeviceCtx* dev, const WireOptions& wo, int arity, size_t n_terms, size_t num_vars, const uint64_t* coeffs_ext, const void* d_tables,
                         const uint64_t* claim_ext, ITranscript* t, int mode, uint64_t* out_point, uint64_t* out_evals) override {
@@ -709,6 +762,43 @@ int hg_lasso_node_prove_shard(hg_lasso_node* node, const void* inputs, size_t n_
         HG_CUDA(cudaSetDevice(ctx->dev.device));
         if (t->t->field_id != node->n->field_id) throw std::runtime_error("transcript belongs to another field");
         node->n->prove_shard(&ctx->dev, inputs, n_inputs, inputs_on_device != 0, t->t.get(), ctx->wire, rank, world, out_words, cap_words, n_words);
+    })
+}
+int hg_lasso_node_prove_shard_dev(hg_lasso_node* node, const void* inputs, size_t n_inputs, int inputs_on_device, hg_transcript* t, int rank, int world,
+                                  void* d_out_words, size_t cap_words, size_t* n_words) {
+    HG_TRY({
+        HG_CUDA(cudaSetDevice(node->ctx->dev.device));
+        if (!d_out_words || !n_words) throw std::runtime_error("hg_lasso_node_prove_shard_dev: NULL output");
+        *n_words = node->n->prove_shard_dev(&node->ctx->dev, inputs, n_inputs, inputs_on_device != 0, t->t.get(), node->ctx->wire, rank, world, d_out_words, cap_words);
+    })
+}
+int hg_lasso_node_emit_shard_dev(hg_lasso_node* node, const void* d_merged_words, size_t n_words, uint64_t* out_point, uint64_t* out_value) {
+    HG_TRY({
+        HG_CUDA(cudaSetDevice(node->ctx->dev.device));
+        node->n->emit_shard_dev(d_merged_words, n_words, out_point, out_value);
+    })
+}
+int hg_shard_merge_device(hg_ctx* ctx, const void* d_parts_words, int world, size_t n_words, void* d_acc_words) {
+    HG_TRY({
+        HG_CUDA(cudaSetDevice(ctx->dev.device));
+        ctx->ops->shard_merge_device(&ctx->dev, d_parts_words, world, n_words, d_acc_words);
+    })
+}
+size_t hg_gkr_shard_words(hg_circuit* c) {
+    try { return c->c->shard_words(); } catch (...) { cudaGetLastError(); return 0; }
+}
+int hg_gkr_prove_shard_dev(hg_circuit* c, size_t n_output_claims, const size_t* point_lens, const uint64_t* points_ext, const uint64_t* values_ext, hg_transcript* t,
+                           int rank, int world, void* d_out_words, size_t cap_words, size_t* n_words) {
+    HG_TRY({
+        HG_CUDA(cudaSetDevice(c->ctx->dev.device));
+        if (!d_out_words || !n_words) throw std::runtime_error("hg_gkr_prove_shard_dev: NULL output");
+        *n_words = c->c->prove_shard_dev(n_output_claims, point_lens, points_ext, values_ext, t->t.get(), c->ctx->wire, rank, world, d_out_words, cap_words);
+    })
+}
+int hg_gkr_emit_shard_dev(hg_circuit* c, const void* d_merged_words, size_t n_words) {
+    HG_TRY({
+        HG_CUDA(cudaSetDevice(c->ctx->dev.device));
+        c->c->emit_shard_dev(d_merged_words, n_words);
     })
 }
 int hg_lasso_node_emit_shard(hg_lasso_node* node, const uint64_t* merged_words, size_t n_words, uint64_t* out_point, uint64_t* out_value) {

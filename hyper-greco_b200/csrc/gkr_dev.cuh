@@ -192,16 +192,71 @@ template <class FP> class GkrCircuitDev {
     // order), point given by value (the caller squeezed it from the same transcript). Returns the claims on the input nodes.
     std::vector<std::vector<InputClaim>> prove(Keccak256Transcript<FP>& tr, ProveMode mode, const WireOptions& wo,
                                                const std::vector<InputClaim>& output_claims) {
-        if (!evaluated_) throw std::runtime_error("prove_gkr: evaluate the circuit first");
         if (!tr.prefetch_legal()) mode = kModeInteractive;
+        enqueue(tr, mode, wo, output_claims, 0, 1);
+        ch_->flush(&timing_[4], &timing_[5]);
+        return collect();
+    }
+    // ---- ONE gkr::prove_gkr over `world` devices. With prefetched challenges every node's claim reduction is
+    // an independent job whose messages land in disjoint slots of one message buffer, except the Lasso node's grand-product
+    // round polynomials, which are sums over its 2m vectors. Device `rank` runs the generic node sumchecks q with q % world ==
+    // rank and its share of the Lasso node (LassoNodeDev::set_shard), leaves every other slot zero, and copies its buffer into
+    // d_out; the element-wise field sum over devices (one all-gather of shard_message_count() elements + k_shard_merge) is the
+    // buffer a single device produces, which rank 0 serialises with emit_shard_dev. Nothing here waits for the device.
+    size_t prove_shard_dev(Keccak256Transcript<FP>& tr, const WireOptions& wo, const std::vector<InputClaim>& output_claims, int rank, int world, X* d_out,
+                           size_t cap) {
+        if (world < 1 || rank < 0 || rank >= world) throw std::runtime_error("prove_gkr: bad shard rank / world size");
+        if (!tr.prefetch_legal()) throw std::runtime_error("prove_gkr: a sharded proof needs a transcript whose challenges do not depend on the messages");
+        enqueue(tr, kModePrefetch, wo, output_claims, rank, world);
+        return ch_->copy_partial_to(d_out, cap);
+    }
+    std::vector<std::vector<InputClaim>> emit_shard_dev(const X* d_merged, size_t count) {
+        ch_->emit_merged_device(d_merged, count);
+        return collect();
+    }
+    size_t shard_message_count() { plan(); return msg_budget_; }
+
+  private:
+    struct Claim { bool by_index; size_t idx; std::vector<X> point_host; int nvars; std::shared_ptr<X> value; };
+    std::vector<std::vector<Claim>> pending_claims_;
+    size_t msg_budget_ = 0;
+    // the claims that reached the input nodes (what verify() checks, sk_encryption_circuit.rs:512-516), after the messages are on the host
+    std::vector<std::vector<InputClaim>> collect() {
+        Channel<FP>& ch = *ch_;
+        if (ch.chal_used() != total_chal_) throw std::runtime_error("prove_gkr: challenge count mismatch");
+        std::vector<std::vector<InputClaim>> res;
+        for (size_t i = 0; i < nodes_.size(); i++) {
+            if (nodes_[i]->kind != GKR_INPUT) continue;
+            std::vector<InputClaim> v;
+            for (auto& c : pending_claims_[i]) {
+                InputClaim ic;
+                if (c.by_index) { ic.point.resize(c.nvars); for (int q = 0; q < c.nvars; q++) ic.point[q] = ch.chal(c.idx + q); }
+                else ic.point = c.point_host;
+                ic.value = *c.value;
+                v.push_back(ic);
+            }
+            res.push_back(v);
+        }
+        return res;
+    }
+    // everything of prove() up to (not including) the download of the messages
+    void enqueue(Keccak256Transcript<FP>& tr, ProveMode mode, const WireOptions& wo, const std::vector<InputClaim>& output_claims, int rank, int world) {
+        if (!evaluated_) throw std::runtime_error("prove_gkr: evaluate the circuit first");
+        const bool sharded = world > 1;
         cudaStream_t s = ctx_->stream;
         auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         const double t0 = now();
         plan();
         desc_off_ = 0; eq_off_ = 0;  // the previous proof ended with a synchronised flush: its staging regions are free
         Channel<FP>& ch = *ch_;
-        struct Claim { bool by_index; size_t idx; std::vector<X> point_host; int nvars; std::shared_ptr<X> value; };
-        std::vector<std::vector<Claim>> claims(nodes_.size());
+        if (sharded) ch.zero_messages();  // slots this device does not own must read as zero in the sum over devices
+        pending_claims_.assign(nodes_.size(), {});
+        std::vector<std::vector<Claim>>& claims = pending_claims_;
+        struct ShardScope {  // the Lasso nodes work for this device while this call enqueues them
+            GkrCircuitDev* c;
+            ShardScope(GkrCircuitDev* cc, int r, int w) : c(cc) { for (auto& n : c->nodes_) if (n->kind == GKR_LASSO) n->lasso->set_shard(r, w); }
+            ~ShardScope() { for (auto& n : c->nodes_) if (n->kind == GKR_LASSO) n->lasso->set_shard(0, 1); }
+        } shard_scope(this, rank, world);
         // output claims: their points live in extra device slots after the challenges
         std::vector<int> outs;
         for (size_t i = 0; i < nodes_.size(); i++) if (nodes_[i]->succs.empty() && nodes_[i]->kind != GKR_INPUT) outs.push_back((int)i);
@@ -253,7 +308,7 @@ template <class FP> class GkrCircuitDev {
             if (n.kind == GKR_INPUT) continue;
             if (n.kind == GKR_LASSO) {
                 size_t r_idx = 0, sum_off = 0;
-                const bool side = ch.begin_side();  // its serialisation overlaps the layer kernels enqueued below
+                const bool side = !sharded && ch.begin_side();  // its serialisation overlaps the layer kernels enqueued below
                 n.lasso->enqueue_protocol(ch, mode, wo, &r_idx, &sum_off);
                 Claim c; c.by_index = true; c.idx = r_idx; c.nvars = n.lasso->num_vars(); c.value = std::make_shared<X>(FP::x_zero());
                 auto vp = c.value;
@@ -326,36 +381,21 @@ template <class FP> class GkrCircuitDev {
                     if (on) { cudaEventRecord(c->ev_join, c->stream2); c->stream = main; cudaStreamWaitEvent(main, c->ev_join, 0); }
                 }
             } swap(ctx_, fork);
-            prepare_jobs(ch, jobs, wo);
+            std::vector<Job> mine;  // the node sumchecks this device runs (all of them unless the proof is sharded)
+            for (size_t q = 0; q < jobs.size(); q++) if (!sharded || (int)(q % (size_t)world) == rank) mine.push_back(jobs[q]);
+            prepare_jobs(ch, mine, wo);
             use_tail_ = true;
             struct TailOff { bool* f; ~TailOff() { *f = false; } } tail_off{&use_tail_};
             int maxv = 0;
-            for (auto& j : jobs) maxv = std::max(maxv, std::min(j.nv, tail_start(j)));
-            for (int r = 0; r < maxv; r++) launch_round(ch, jobs, r);
-            launch_tail(ch, jobs);
-            launch_finals(ch, jobs);
+            for (auto& j : mine) maxv = std::max(maxv, std::min(j.nv, tail_start(j)));
+            for (int r = 0; r < maxv; r++) launch_round(ch, mine, r);
+            launch_tail(ch, mine);
+            launch_finals(ch, mine);
         }
         const double t4 = now();
-        ch.flush(&timing_[4], &timing_[5]);
         timing_[0] = t1 - t0; timing_[1] = t2 - t1; timing_[2] = t3 - t2; timing_[3] = t4 - t3;
-        if (ch.chal_used() != total_chal_) throw std::runtime_error("prove_gkr: challenge count mismatch");
-        std::vector<std::vector<InputClaim>> res;
-        for (size_t i = 0; i < nodes_.size(); i++) {
-            if (nodes_[i]->kind != GKR_INPUT) continue;
-            std::vector<InputClaim> v;
-            for (auto& c : claims[i]) {
-                InputClaim ic;
-                if (c.by_index) { ic.point.resize(c.nvars); for (int q = 0; q < c.nvars; q++) ic.point[q] = ch.chal(c.idx + q); }
-                else ic.point = c.point_host;
-                ic.value = *c.value;
-                v.push_back(ic);
-            }
-            res.push_back(v);
-        }
-        return res;
     }
 
-  private:
     struct Node {
         int kind = GKR_INPUT, log2_size = 0, num_reps = 1, arity = 0, log2_sub = 0;
         bool fft_inverse = false, is_linear = false, is_elemmul = false, has_consts = false;
@@ -471,6 +511,7 @@ template <class FP> class GkrCircuitDev {
             n.capture.alloc(n.a_pad + 2);
         }
         total_chal_ = chal;
+        msg_budget_ = msg + 64;
         ch_.reset(new Channel<FP>(ctx_, chal + 8, msg + 64));
         d_eq_.alloc(eq_elems + 64);
         d_partials_.alloc(((size_t)ctx_->sm_count * 16 + 8) * 4 * (items + 4));

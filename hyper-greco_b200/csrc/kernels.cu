@@ -32,10 +32,10 @@ __device__ __forceinline__ bool cnt_fetch(int pass, const CntSlots& sl, int slot
     *digit = (u32)(*elem >> 40) & 255u;
     return true;
 }
-__global__ void __launch_bounds__(1024) k_cnt_digit_hist(int pass, CntSlots sl, const u8* __restrict__ row_lookup, size_t n_rows, size_t cap, const u64* __restrict__ src_all,
+__global__ void __launch_bounds__(1024) k_cnt_digit_hist(SlotMap sm, int pass, CntSlots sl, const u8* __restrict__ row_lookup, size_t n_rows, size_t cap, const u64* __restrict__ src_all,
                                                         const u32* __restrict__ n_valid, int nblk, u32* __restrict__ blk_hist_all /*[slot][nblk][256]*/) {
     __shared__ u32 h[256];
-    const int slot = blockIdx.y;
+    const int slot = sm.s[blockIdx.y];
     if (threadIdx.x < 256) h[threadIdx.x] = 0;
     __syncthreads();
     const u64* src = src_all + (size_t)slot * cap;
@@ -52,10 +52,10 @@ __global__ void __launch_bounds__(1024) k_cnt_digit_hist(int pass, CntSlots sl, 
 }
 // per (slot, digit): exclusive prefix over tiles. grid = (8, slots): a CTA owns 32 digits, its 1024 threads are 32 groups of
 // tiles x 32 digits (separate input and output arrays: the loads do not wait for the stores). Digit totals -> digit_total.
-__global__ void __launch_bounds__(1024) k_cnt_digit_scan(int nblk, const u32* __restrict__ blk_hist_all, u32* __restrict__ blk_base_all,
+__global__ void __launch_bounds__(1024) k_cnt_digit_scan(SlotMap sm, int nblk, const u32* __restrict__ blk_hist_all, u32* __restrict__ blk_base_all,
                                                         u32* __restrict__ digit_total_all /*[slot][256]*/) {
     __shared__ u32 part[32][33];
-    const int slot = blockIdx.y, dl = threadIdx.x & 31, grp = threadIdx.x >> 5, d = blockIdx.x * 32 + dl;
+    const int slot = sm.s[blockIdx.y], dl = threadIdx.x & 31, grp = threadIdx.x >> 5, d = blockIdx.x * 32 + dl;
     const u32* bh = blk_hist_all + (size_t)slot * nblk * 256;
     u32* bb = blk_base_all + (size_t)slot * nblk * 256;
     const int per = (nblk + 31) / 32, b0 = min(nblk, grp * per), b1 = min(nblk, b0 + per);
@@ -71,9 +71,9 @@ __global__ void __launch_bounds__(1024) k_cnt_digit_scan(int nblk, const u32* __
     if (grp == 31) digit_total_all[slot * 256 + d] = run;  // the last group ends with the grand total (empty groups pass the sum through)
 }
 // digit totals -> exclusive digit starts, n_valid. One CTA of 256 threads per slot.
-__global__ void __launch_bounds__(256) k_cnt_digit_starts(const u32* __restrict__ digit_total_all, u32* __restrict__ digit_start_all, u32* __restrict__ n_valid) {
+__global__ void __launch_bounds__(256) k_cnt_digit_starts(SlotMap sm, const u32* __restrict__ digit_total_all, u32* __restrict__ digit_start_all, u32* __restrict__ n_valid) {
     __shared__ u32 tot[256];
-    const int slot = blockIdx.x, d = threadIdx.x;
+    const int slot = sm.s[blockIdx.x], d = threadIdx.x;
     tot[d] = digit_total_all[slot * 256 + d];
     __syncthreads();
     // inclusive scan in shared memory (Hillis-Steele, 8 steps)
@@ -86,14 +86,14 @@ __global__ void __launch_bounds__(256) k_cnt_digit_starts(const u32* __restrict_
     digit_start_all[slot * 256 + d] = d ? tot[d - 1] : 0;
     if (d == 255) n_valid[slot] = tot[255];
 }
-__global__ void __launch_bounds__(1024) k_cnt_digit_scatter(int pass, CntSlots sl, const u8* __restrict__ row_lookup, size_t n_rows, size_t cap,
+__global__ void __launch_bounds__(1024) k_cnt_digit_scatter(SlotMap sm, int pass, CntSlots sl, const u8* __restrict__ row_lookup, size_t n_rows, size_t cap,
                                                            const u64* __restrict__ src_all, const u32* __restrict__ n_valid, int nblk,
                                                            const u32* __restrict__ blk_base_all, const u32* __restrict__ digit_start_all,
                                                            u64* __restrict__ dst_all) {
     __shared__ unsigned short cnt[32][257];  // per warp and digit: elements of this chunk, then their exclusive prefix over warps
     __shared__ u32 run[256];                 // global offset of (tile, digit) plus the elements of earlier chunks of this tile
     __shared__ u32 tot[256];
-    const int slot = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = sm.s[blockIdx.y], lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u64* src = src_all + (size_t)slot * cap;
     u64* dst = dst_all + (size_t)slot * cap;
     if (threadIdx.x < 256)
@@ -123,9 +123,9 @@ __global__ void __launch_bounds__(1024) k_cnt_digit_scatter(int pass, CntSlots s
     }
 }
 // sorted: run boundaries of every address
-__global__ void k_cnt_heads(size_t cap, const u64* __restrict__ sorted_all, const u32* __restrict__ n_valid, size_t M, u32* __restrict__ start_all,
+__global__ void k_cnt_heads(SlotMap sm, size_t cap, const u64* __restrict__ sorted_all, const u32* __restrict__ n_valid, size_t M, u32* __restrict__ start_all,
                             u32* __restrict__ end_all) {
-    const int slot = blockIdx.y;
+    const int slot = sm.s[blockIdx.y];
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const u32 n = n_valid[slot];
     if (p >= n) return;
@@ -135,9 +135,9 @@ __global__ void k_cnt_heads(size_t cap, const u64* __restrict__ sorted_all, cons
     if (p + 1 == n || (u32)(s[p + 1] >> 32) != a) end_all[(size_t)slot * M + a] = (u32)(p + 1);
 }
 // read_cts[row] = position inside the run of its address; final_cts[address] = run length (0 for addresses never read)
-__global__ void k_cnt_finish(size_t cap, const u64* __restrict__ sorted_all, const u32* __restrict__ n_valid, size_t M, const u32* __restrict__ start_all,
+__global__ void k_cnt_finish(SlotMap sm, size_t cap, const u64* __restrict__ sorted_all, const u32* __restrict__ n_valid, size_t M, const u32* __restrict__ start_all,
                              const u32* __restrict__ end_all, size_t R, u32* __restrict__ read_cts_all, u32* __restrict__ final_cts_all) {
-    const int slot = blockIdx.y;
+    const int slot = sm.s[blockIdx.y];
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < M) final_cts_all[(size_t)slot * M + p] = end_all[(size_t)slot * M + p] - start_all[(size_t)slot * M + p];
     if (p >= n_valid[slot]) return;

@@ -156,15 +156,16 @@ __global__ void k_polynomialize(const typename FP::B* __restrict__ inputs, size_
 // final_cts[a] = total. Order-dependent: a stable two-pass radix sort of (address, row) groups the rows of an address in row
 // order; the counters are read off the run boundaries (kernels.cu).
 struct CntSlots { const u16* addr[HG_MAX_C]; u64 used[HG_MAX_C]; };  // per chunk slot: its address column and the lookup types that use it
-__global__ void k_cnt_digit_hist(int pass, CntSlots sl, const u8* __restrict__ row_lookup, size_t n_rows, size_t cap, const u64* __restrict__ src,
+struct SlotMap { int s[HG_MAX_C]; };  // blockIdx.y (.x in k_cnt_digit_starts) -> chunk slot: a device of a sharded proof counts only the slots it needs
+__global__ void k_cnt_digit_hist(SlotMap sm, int pass, CntSlots sl, const u8* __restrict__ row_lookup, size_t n_rows, size_t cap, const u64* __restrict__ src,
                                  const u32* __restrict__ n_valid, int nblk, u32* __restrict__ blk_hist /*[slot][nblk][256]*/);
-__global__ void k_cnt_digit_scan(int nblk, const u32* __restrict__ blk_hist, u32* __restrict__ blk_base, u32* __restrict__ digit_total /*[slot][256]*/);
-__global__ void k_cnt_digit_starts(const u32* __restrict__ digit_total, u32* __restrict__ digit_start /*[slot][256]*/, u32* __restrict__ n_valid);
-__global__ void k_cnt_digit_scatter(int pass, CntSlots sl, const u8* __restrict__ row_lookup, size_t n_rows, size_t cap, const u64* __restrict__ src,
+__global__ void k_cnt_digit_scan(SlotMap sm, int nblk, const u32* __restrict__ blk_hist, u32* __restrict__ blk_base, u32* __restrict__ digit_total /*[slot][256]*/);
+__global__ void k_cnt_digit_starts(SlotMap sm, const u32* __restrict__ digit_total, u32* __restrict__ digit_start /*[slot][256]*/, u32* __restrict__ n_valid);
+__global__ void k_cnt_digit_scatter(SlotMap sm, int pass, CntSlots sl, const u8* __restrict__ row_lookup, size_t n_rows, size_t cap, const u64* __restrict__ src,
                                     const u32* __restrict__ n_valid, int nblk, const u32* __restrict__ blk_base, const u32* __restrict__ digit_start,
                                     u64* __restrict__ dst);
-__global__ void k_cnt_heads(size_t cap, const u64* __restrict__ sorted, const u32* __restrict__ n_valid, size_t M, u32* __restrict__ start, u32* __restrict__ end);
-__global__ void k_cnt_finish(size_t cap, const u64* __restrict__ sorted, const u32* __restrict__ n_valid, size_t M, const u32* __restrict__ start,
+__global__ void k_cnt_heads(SlotMap sm, size_t cap, const u64* __restrict__ sorted, const u32* __restrict__ n_valid, size_t M, u32* __restrict__ start, u32* __restrict__ end);
+__global__ void k_cnt_finish(SlotMap sm, size_t cap, const u64* __restrict__ sorted, const u32* __restrict__ n_valid, size_t M, const u32* __restrict__ start,
                              const u32* __restrict__ end, size_t R, u32* __restrict__ read_cts, u32* __restrict__ final_cts);
 
 // ---------------------------------------------------------------------------------------------------------

@@ -252,6 +252,21 @@ template <class FP> class Channel {
         *count = msg_cursor_;
         return h_msg_.p;
     }
+    // the same without leaving the device: copy this device's partial message buffer into a caller-owned device buffer
+    // (stream-ordered, no host synchronisation); the caller sums the buffers of all devices (k_shard_merge after an NCCL
+    // all-gather) and rank 0 hands the sum back to emit_merged_device
+    size_t copy_partial_to(X* d_out, size_t cap) {
+        if (msg_cursor_ > cap) throw std::runtime_error("Channel: shard message buffer too small");
+        HG_CUDA(cudaMemcpyAsync(d_out, d_msg_.p, msg_cursor_ * sizeof(X), cudaMemcpyDeviceToDevice, ctx_->stream));
+        return msg_cursor_;
+    }
+    void emit_merged_device(const X* d_merged, size_t count) {
+        if (count != msg_cursor_) throw std::runtime_error("Channel: merged message count does not match this proof");
+        HG_CUDA(cudaMemcpyAsync(h_msg_.p, d_merged, count * sizeof(X), cudaMemcpyDeviceToHost, ctx_->stream));
+        HG_CUDA(cudaStreamSynchronize(ctx_->stream));
+        msg_ready_ = msg_cursor_;
+        for (; deferred_done_ < deferred_.size(); deferred_done_++) deferred_[deferred_done_]();
+    }
     // replace the host copy of the messages by the merged one and serialise
     void emit_merged(const X* merged, size_t count) {
         if (count != msg_cursor_) throw std::runtime_error("Channel: merged message count does not match this proof");
@@ -646,6 +661,7 @@ template <class FP> class LassoNodeDev {
             }
         }
         nslots_ = (int)chunk_dims_.size();
+        pos_slot_host_ = pos_slot;
 
         NodeMeta meta;
         memset(&meta, 0, sizeof meta);
@@ -803,8 +819,8 @@ template <class FP> class LassoNodeDev {
         if (world < 1 || rank < 0 || rank >= world || world > 2 * m_) throw std::runtime_error("LassoNode: bad shard rank / world size");
         if (!tr.prefetch_legal()) throw std::runtime_error("LassoNode: a sharded proof needs a transcript whose challenges do not depend on the messages");
         Channel<FP>& ch = *ch_;
-        shard_rank_ = rank; shard_world_ = world;
-        struct Reset { LassoNodeDev* n; ~Reset() { n->shard_rank_ = 0; n->shard_world_ = 1; } } reset{this};
+        set_shard(rank, world);
+        struct Reset { LassoNodeDev* n; ~Reset() { n->set_shard(0, 1); } } reset{this};
         enqueue_witness(d_inputs, n_inputs, wo);
         ch.zero_messages();
         ch.begin(&tr, kModePrefetch, total_chal_);
@@ -820,6 +836,29 @@ template <class FP> class LassoNodeDev {
         if (out_value) *out_value = ch.msg(shard_sum_off_);
     }
     size_t shard_message_count() const { return msg_budget_; }
+    // device-resident variant: the partial buffer is copied into d_out (device memory of the caller) on the context's stream,
+    // nothing waits for the device
+    size_t prove_shard_dev(const B* d_inputs, size_t n_inputs, Keccak256Transcript<FP>& tr, const WireOptions& wo, int rank, int world, X* d_out, size_t cap) {
+        if (world < 1 || rank < 0 || rank >= world || world > 2 * m_) throw std::runtime_error("LassoNode: bad shard rank / world size");
+        if (!tr.prefetch_legal()) throw std::runtime_error("LassoNode: a sharded proof needs a transcript whose challenges do not depend on the messages");
+        Channel<FP>& ch = *ch_;
+        set_shard(rank, world);
+        struct Reset { LassoNodeDev* n; ~Reset() { n->set_shard(0, 1); } } reset{this};
+        enqueue_witness(d_inputs, n_inputs, wo);
+        ch.zero_messages();
+        ch.begin(&tr, kModePrefetch, total_chal_);
+        enqueue_protocol(ch, kModePrefetch, wo, &shard_r_idx_, &shard_sum_off_);
+        if (ch.chal_used() != total_chal_) throw std::runtime_error("LassoNode: challenge count mismatch");
+        return ch.copy_partial_to(d_out, cap);
+    }
+    void emit_shard_dev(const X* d_merged, size_t count, std::vector<X>* out_point, X* out_value) {
+        Channel<FP>& ch = *ch_;
+        ch.emit_merged_device(d_merged, count);
+        if (out_point) { out_point->resize(num_vars_); for (int i = 0; i < num_vars_; i++) (*out_point)[i] = ch.chal(shard_r_idx_ + i); }
+        if (out_value) *out_value = ch.msg(shard_sum_off_);
+    }
+    // which device of a sharded proof this node works for (GkrCircuitDev::enqueue sets it around the node's two enqueue calls)
+    void set_shard(int rank, int world) { shard_rank_ = rank; shard_world_ = world; }
 
     // polynomialize (lasso.rs:157-250): everything that needs no challenge
     void enqueue_witness(const B* d_inputs, size_t n_inputs, const WireOptions& wo) {
@@ -877,21 +916,31 @@ template <class FP> class LassoNodeDev {
             u32* d_start = d_cnt_runs_.p;
             u32* d_end = d_cnt_runs_.p + (size_t)nslots_ * M;
             HG_CUDA(cudaMemsetAsync(d_cnt_runs_.p, 0, d_cnt_runs_.bytes(), cs));
-            const dim3 tiles(nblk_cnt_, nslots_);
-            for (int pass = 0; pass < 2; pass++) {
+            // a device of a sharded proof counts only the chunk slots its vectors (and its share of the openings) read
+            SlotMap sm;
+            int ns = 0;
+            for (int q = 0; q < HG_MAX_C; q++) sm.s[q] = 0;
+            for (int q = 0; q < nslots_; q++) if (slot_needed(q)) sm.s[ns++] = q;
+            const dim3 tiles(nblk_cnt_, ns);
+            // algorithmic bytes of the class (booked on the first launch): address column and lookup type read once, both
+            // counter tables written once. The sort scratch (~3x that) is traffic, not algorithm.
+            const size_t cnt_alg = (size_t)ns * (rows * (2 + 1 + 4) + M * 4);
+            for (int pass = 0; pass < 2 && ns > 0; pass++) {
                 const u64* src = pass == 0 ? nullptr : d_cnt_a_.p;
                 u64* dst = pass == 0 ? d_cnt_a_.p : d_cnt_b_.p;
-                HG_K(ctx_, KC_COUNTERS, (size_t)nslots_ * rows * (pass ? 8 : 3),
-                     k_cnt_digit_hist<<<tiles, 1024, 0, cs>>>(pass, sl, d_row_lookup_.p, rows, cnt_cap_, src, d_nvalid, nblk_cnt_, d_cnt_hist_.p));
-                HG_K(ctx_, KC_COUNTERS, (size_t)nslots_ * nblk_cnt_ * 256 * 8, k_cnt_digit_scan<<<dim3(8, nslots_), 1024, 0, cs>>>(nblk_cnt_, d_cnt_hist_.p, d_cnt_base, d_digit_total));
-                HG_K(ctx_, KC_COUNTERS, (size_t)nslots_ * 2048, k_cnt_digit_starts<<<nslots_, 256, 0, cs>>>(d_digit_total, d_digit_start, d_nvalid));
-                HG_K(ctx_, KC_COUNTERS, (size_t)nslots_ * rows * (pass ? 16 : 11),
-                     k_cnt_digit_scatter<<<tiles, 1024, 0, cs>>>(pass, sl, d_row_lookup_.p, rows, cnt_cap_, src, d_nvalid, nblk_cnt_, d_cnt_base, d_digit_start, dst));
+                HG_K(ctx_, KC_COUNTERS, pass == 0 ? cnt_alg : 0,
+                     k_cnt_digit_hist<<<tiles, 1024, 0, cs>>>(sm, pass, sl, d_row_lookup_.p, rows, cnt_cap_, src, d_nvalid, nblk_cnt_, d_cnt_hist_.p));
+                HG_K(ctx_, KC_COUNTERS, 0, k_cnt_digit_scan<<<dim3(8, ns), 1024, 0, cs>>>(sm, nblk_cnt_, d_cnt_hist_.p, d_cnt_base, d_digit_total));
+                HG_K(ctx_, KC_COUNTERS, 0, k_cnt_digit_starts<<<ns, 256, 0, cs>>>(sm, d_digit_total, d_digit_start, d_nvalid));
+                HG_K(ctx_, KC_COUNTERS, 0,
+                     k_cnt_digit_scatter<<<tiles, 1024, 0, cs>>>(sm, pass, sl, d_row_lookup_.p, rows, cnt_cap_, src, d_nvalid, nblk_cnt_, d_cnt_base, d_digit_start, dst));
             }
             const unsigned fin_blocks = (unsigned)((std::max<size_t>(cnt_cap_, M) + 255) / 256);
-            HG_K(ctx_, KC_COUNTERS, (size_t)nslots_ * rows * 8, k_cnt_heads<<<dim3(fin_blocks, nslots_), 256, 0, cs>>>(cnt_cap_, d_cnt_b_.p, d_nvalid, M, d_start, d_end));
-            HG_K(ctx_, KC_COUNTERS, (size_t)nslots_ * (rows * 12 + M * 12),
-                 k_cnt_finish<<<dim3(fin_blocks, nslots_), 256, 0, cs>>>(cnt_cap_, d_cnt_b_.p, d_nvalid, M, d_start, d_end, R, d_read_cts_.p, d_final_cts_.p));
+            if (ns > 0) {
+                HG_K(ctx_, KC_COUNTERS, 0, k_cnt_heads<<<dim3(fin_blocks, ns), 256, 0, cs>>>(sm, cnt_cap_, d_cnt_b_.p, d_nvalid, M, d_start, d_end));
+                HG_K(ctx_, KC_COUNTERS, 0,
+                     k_cnt_finish<<<dim3(fin_blocks, ns), 256, 0, cs>>>(sm, cnt_cap_, d_cnt_b_.p, d_nvalid, M, d_start, d_end, R, d_read_cts_.p, d_final_cts_.p));
+            }
         }
         if (side) {
             ctx_->stream = s;
@@ -908,7 +957,7 @@ template <class FP> class LassoNodeDev {
         // ---- r, claimed sum (lasso.rs:85, :264, :269)
         const size_t r_idx = ch.squeeze(v);
         const size_t sum_off = ch.alloc_msg(1);
-        const bool lead = shard_rank_ == 0;  // the claim, the collation sumcheck and the dim / counter openings belong to rank 0
+        const bool lead = shard_rank_ == 0;  // the claim and the collation sumcheck belong to rank 0 (the openings are distributed, see below)
         if (lead) eval_tables<B>(ch, d_out_.p, R, 1, R, r_idx, v, sum_off);
         auto coll_state = std::make_shared<ScHostState<FP>>();
         {
@@ -990,17 +1039,24 @@ template <class FP> class LassoNodeDev {
         // ---- openings (prover.rs:173-178, mod.rs:80-93)
         const size_t o_dims = ch.alloc_msg(pp_.C), o_rts = ch.alloc_msg(nslots_), o_fcs = ch.alloc_msg(nslots_), o_e = ch.alloc_msg(m);
         build_eq(ch, x_idx, v);
-        if (lead) {
-            dot_tables<u16>(ch, d_dims_.p, R, (int)pp_.C, R, o_dims);
-            dot_tables<u32>(ch, d_read_cts_.p, R, nslots_, R, o_rts);
-        }
-        {   // E_i openings: memories split evenly over the devices
+        {   // dim(x) openings and E_i(x) openings: tables split evenly over the devices
+            const int c0 = (int)(pp_.C * shard_rank_ / shard_world_), c1 = (int)(pp_.C * (shard_rank_ + 1) / shard_world_);
+            if (c1 > c0) dot_tables<u16>(ch, d_dims_.p + (size_t)c0 * R, R, c1 - c0, R, o_dims + c0);
             const int e0 = (int)((size_t)m * shard_rank_ / shard_world_), e1 = (int)((size_t)m * (shard_rank_ + 1) / shard_world_);
             if (e1 > e0) dot_tables<B>(ch, d_E_.p + (size_t)e0 * R, R, e1 - e0, R, o_e + e0);
         }
-        if (lead) {
+        // read_ts(x) / final_cts(y) of a chunk slot: on the device that owns the slot's first read vector (it has the counters)
+        if (shard_world_ == 1) {
+            dot_tables<u32>(ch, d_read_cts_.p, R, nslots_, R, o_rts);
             build_eq(ch, y_idx, log2M_);
             dot_tables<u32>(ch, d_final_cts_.p, M, nslots_, M, o_fcs);
+        } else {
+            bool any = false;
+            for (int q = 0; q < nslots_; q++) if (slot_owner(q) == shard_rank_) { dot_tables<u32>(ch, d_read_cts_.p + (size_t)q * R, R, 1, R, o_rts + q); any = true; }
+            if (any) {
+                build_eq(ch, y_idx, log2M_);
+                for (int q = 0; q < nslots_; q++) if (slot_owner(q) == shard_rank_) dot_tables<u32>(ch, d_final_cts_.p + (size_t)q * M, M, 1, M, o_fcs + q);
+            }
         }
         {
             Channel<FP>* chp = &ch;
@@ -1421,6 +1477,22 @@ template <class FP> class LassoNodeDev {
         }
     }
 
+    // device that opens read_ts / final_cts of chunk slot q: the owner of the slot's first read vector
+    int slot_owner(int q) const {
+        const int nvec = 2 * m_;
+        for (int pos = 0; pos < m_; pos++)
+            if (pos_slot_host_[pos] == q)
+                for (int r = 0; r < shard_world_; r++)
+                    if (pos >= (int)((size_t)nvec * r / shard_world_) && pos < (int)((size_t)nvec * (r + 1) / shard_world_)) return r;
+        return 0;
+    }
+    // does this device read the access counters of chunk slot q? (hashes of its own vectors and of vector 0, its counter openings)
+    bool slot_needed(int q) const {
+        if (shard_world_ == 1) return true;
+        if (pos_slot_host_[0] == q || slot_owner(q) == shard_rank_) return true;
+        for (int v = own_begin(2 * m_); v < own_end(2 * m_); v++) if (pos_slot_host_[v % m_] == q) return true;
+        return false;
+    }
     // vectors [own_begin, own_end) of a grand product belong to this device (all of them unless prove_shard is running)
     VecRange own_range(int nvec) const { VecRange r; r.lo = own_begin(nvec); r.hi = own_end(nvec); return r; }
     int own_begin(int nvec) const { return (int)((size_t)nvec * shard_rank_ / shard_world_); }
@@ -1438,6 +1510,7 @@ template <class FP> class LassoNodeDev {
     std::vector<int> chunk_dims_;
     std::vector<std::vector<int>> chunk_mems_;
     std::vector<u64> slot_used_;
+    std::vector<int> pos_slot_host_;  // chunk slot of the memory at chunk-major position pos
     std::vector<int> slot_addr_dim_;
     std::vector<B> coll_coeff_host_;
     DevBuf<NodeMeta> d_meta_;

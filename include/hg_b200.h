@@ -156,6 +156,16 @@ int hg_lasso_node_prove_shard(hg_lasso_node* node, const void* inputs, size_t n_
                               uint64_t* out_words, size_t cap_words, size_t* n_words);
 int hg_shard_merge(int field_id, uint64_t* acc_words, const uint64_t* part_words, size_t n_words); /* acc += part, element-wise in the field */
 int hg_lasso_node_emit_shard(hg_lasso_node* node, const uint64_t* merged_words, size_t n_words, uint64_t* out_point, uint64_t* out_value);
+/* The same exchange without leaving the devices (what bench.py and the multi-GPU tests use): every rank's partial buffer is
+ * copied into device memory of the caller (d_out_words, stream-ordered on the context's stream, no host synchronisation),
+ * the caller all-gathers the buffers of all ranks over NVLink (NCCL all_gather enqueued behind hg_ctx_stream(); world *
+ * n_words * 8 bytes, ~80 KB per rank at n = 32768), hg_shard_merge_device sums the `world` gathered buffers ([world][n_words],
+ * rank-major) in the field with one kernel, and rank 0 serialises the sum with the *_emit_shard_dev call (one device-to-host
+ * copy of n_words * 8 bytes). The collective carries messages only: tables never cross the link. */
+int hg_lasso_node_prove_shard_dev(hg_lasso_node* node, const void* inputs, size_t n_inputs, int inputs_on_device, hg_transcript* t, int rank, int world,
+                                  void* d_out_words, size_t cap_words, size_t* n_words);
+int hg_shard_merge_device(hg_ctx* ctx, const void* d_parts_words, int world, size_t n_words, void* d_acc_words);
+int hg_lasso_node_emit_shard_dev(hg_lasso_node* node, const void* d_merged_words, size_t n_words, uint64_t* out_point, uint64_t* out_value);
 /* test hook: polynomialised witness of the last prove (lasso.rs:157-250). dims: C x R u16, read_cts: chunks x R u32,
  * final_cts: chunks x M u32, e_polys: num_memories x R base elements. Any pointer may be NULL. */
 int hg_lasso_node_download_polys(hg_lasso_node* node, uint16_t* dims, uint32_t* read_cts, uint32_t* final_cts, uint64_t* e_polys);
@@ -222,6 +232,16 @@ int hg_circuit_node_value(hg_circuit* c, int id, const void** d_ptr, size_t* len
  * reach the input nodes are read back with the hg_gkr_input_claim* getters (what verify() checks, :512-516). */
 int hg_gkr_prove(hg_circuit* c, size_t n_output_claims, const size_t* point_lens, const uint64_t* points_ext, const uint64_t* values_ext,
                  hg_transcript* t, int mode);
+/* ONE gkr::prove_gkr over `world` GPUs (BASELINE.json config 4). With prefetched challenges every node's claim reduction is an
+ * independent job; rank r runs the generic node sumchecks q with q % world == r and its share of the Lasso node (grand-product
+ * vectors, openings and access counters split as in hg_lasso_node_prove_shard), every other message slot stays zero. Same
+ * exchange as above: all-gather of hg_gkr_shard_words() words per rank, hg_shard_merge_device, then rank 0 calls
+ * hg_gkr_emit_shard_dev, which writes the proof into the transcript given to ITS prove call and fills the input claims.
+ * Every rank must have evaluated the circuit on the same inputs and pass transcripts in the same state. */
+size_t hg_gkr_shard_words(hg_circuit* c);
+int hg_gkr_prove_shard_dev(hg_circuit* c, size_t n_output_claims, const size_t* point_lens, const uint64_t* points_ext, const uint64_t* values_ext, hg_transcript* t,
+                           int rank, int world, void* d_out_words, size_t cap_words, size_t* n_words);
+int hg_gkr_emit_shard_dev(hg_circuit* c, const void* d_merged_words, size_t n_words);
 /* host phases of the last hg_gkr_prove in microseconds: [witness kernels enqueue, squeeze+upload challenges, protocol walk,
  * batched layer enqueue, wait for the GPU, serialise]; number of extension challenges one proof squeezes */
 void hg_gkr_timing(const hg_circuit* c, double* out_us6);

@@ -1,6 +1,8 @@
 """GPU parity tests (run with -m gpu on the B200 box). Everything goes through the C ABI (hyper_greco_b200.api ->
 libhg_b200.so) and is compared bit-for-bit with the CPU oracle on the same inputs; at the BASELINE.json sizes the checks are
 size-independent properties (oracle VERIFIER acceptance, claim == input MLE, prefetch == interactive, determinism)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -724,3 +726,92 @@ def test_full_gkr_prove_with_callback_transcript(api, ctx, golden_dir):
     el = point.shape[1]
     prover.circuit.prove_gkr([(np.zeros((0, el), np.uint64), np.zeros(el, np.uint64)), (point, value)], tr, api.MODE_PREFETCH)
     assert tr.into_proof() == golden
+
+
+# ------------------------------------------------------------------------------------------------ one proof over several GPUs, device-side exchange
+def _emulate_ranks_dev(api, ctx, world, cap_words, prove_shard_dev, emit_shard_dev):
+    """The exchange of api.ShardExchange with all `world` ranks emulated on one device: every rank writes its partial buffer into
+    its row of the gathered buffer (what the NCCL all-gather produces), one merge kernel, rank 0 serialises."""
+    import torch
+    gathered = torch.zeros(world * cap_words, dtype=torch.int64, device="cuda")
+    merged = torch.zeros(cap_words, dtype=torch.int64, device="cuda")
+    n = None
+    for r in range(world - 1, -1, -1):        # rank 0 last: its node / circuit keeps the deferred serialisers
+        part = torch.zeros(cap_words, dtype=torch.int64, device="cuda")
+        nw = prove_shard_dev(r, world, part.data_ptr(), cap_words)
+        ctx.synchronize()
+        assert n is None or n == nw
+        n = nw
+        gathered[r * n:(r + 1) * n] = part[:n]
+    torch.cuda.synchronize()
+    api.shard_merge_device(ctx, gathered.data_ptr(), world, n, merged.data_ptr())
+    return emit_shard_dev(merged.data_ptr(), n)
+
+
+@pytest.mark.parametrize("name,world", [("1024_1x27_65537", 2), ("4096_2x55_65537", 4), ("4096_2x55_65537", 8)])
+def test_lasso_node_sharded_device_exchange(api, ctx, oracle, golden_dir, name, world):
+    P, inp, bounds, segs, nv, opp, rows = load_case(name, oracle, golden_dir)
+    node, pp, tr0, pt0, val0 = _prove_gpu(api, ctx, bounds, segs, nv, inp)
+    want = tr0.into_proof()
+    tr = api.Keccak256Transcript()
+    buf = api.DeviceBuffer.from_numpy(ctx, inp)
+    pt, val = _emulate_ranks_dev(api, ctx, world, node.shard_words,
+                                 lambda r, w, ptr, cap: node.prove_shard_dev(buf, tr if r == 0 else api.Keccak256Transcript(), r, w, ptr, cap, n_inputs=inp.size),
+                                 node.emit_shard_dev)
+    assert tr.into_proof() == want and (pt == pt0).all() and (val == val0).all()
+    node.free()
+
+
+@pytest.mark.parametrize("name,world", [("1024_1x27_65537", 2), ("4096_2x55_65537", 3), ("4096_2x55_65537", 8)])
+def test_full_gkr_prove_sharded_equals_single_device(api, ctx, golden_dir, name, world):
+    """hg_gkr_prove_shard_dev: ONE gkr::prove_gkr (every Vanilla / FFT / product node and the Lasso node) split over `world`
+    ranks, all emulated on this device; merged bytes == the single-device proof, input claims identical."""
+    from hyper_greco_b200 import params
+    P = params.PARAMS[name]
+    io = np.load(os.path.join(golden_dir, f"circuit_io_{name}.npz"))
+    prover = api.BfvSkEncryptProver(ctx, P)
+    dev = prover.upload_inputs({k: io[k] for k in ("s", "e", "k1", "ais", "r1is", "r2is")})
+    d_ct = api.DeviceBuffer.from_numpy(ctx, io["ct0is"])
+    want, claims0 = prover.prove(dev, d_ct, 0)
+    L = prover.ct0is_log2_size
+
+    def out_claims(tr):
+        point = tr.squeeze_challenges(L)
+        value = api.mle_eval_batch(ctx, d_ct, 1, L, point)[0]
+        return [(np.zeros((0, point.shape[1]), np.uint64), np.zeros(point.shape[1], np.uint64)), (point, value)]
+
+    tr = api.Keccak256Transcript()
+
+    def shard(r, w, ptr, cap):
+        t = tr if r == 0 else api.Keccak256Transcript()
+        return prover.circuit.prove_gkr_shard_dev(out_claims(t), t, r, w, ptr, cap)
+
+    claims = _emulate_ranks_dev(api, ctx, world, prover.circuit.shard_words, shard, prover.circuit.emit_shard_dev)
+    assert tr.into_proof() == want
+    assert all((a[0] == b[0]).all() and (a[1] == b[1]).all() for ca, cb in zip(claims0, claims) for a, b in zip(ca, cb))
+    # the unsharded path still works on the same circuit afterwards
+    again, _ = prover.prove(dev, d_ct, 0)
+    assert again == want
+
+
+def test_full_gkr_prove_sharded_full_size(api, ctx, golden_dir):
+    """BASELINE.json config 4 (n=32768 k=16 Goldilocks, one proof over 2/4/8 GPUs): 4 emulated ranks give the committed sha256."""
+    from hyper_greco_b200 import params, witness
+    meta = _fullsize_meta(golden_dir, "goldilocks_bfv_encrypt_n32768_seed5")
+    P = params.by_n(32768)
+    ins, ct0is = witness.get_inputs(P, witness.synth_witness(P, 5))
+    prover = api.BfvSkEncryptProver(ctx, P)
+    dev = prover.upload_inputs(ins)
+    d_ct = api.DeviceBuffer.from_numpy(ctx, np.array(ct0is, dtype=np.uint64))
+    prover.circuit.evaluate(dev)
+    L = prover.ct0is_log2_size
+    tr = api.Keccak256Transcript()
+
+    def shard(r, w, ptr, cap):
+        t = tr if r == 0 else api.Keccak256Transcript()
+        point = t.squeeze_challenges(L)
+        value = api.mle_eval_batch(ctx, d_ct, 1, L, point)[0]
+        return prover.circuit.prove_gkr_shard_dev([(np.zeros((0, 2), np.uint64), np.zeros(2, np.uint64)), (point, value)], t, r, w, ptr, cap)
+
+    _emulate_ranks_dev(api, ctx, 4, prover.circuit.shard_words, shard, prover.circuit.emit_shard_dev)
+    _assert_hash(tr.into_proof(), meta, "sharded BfvEncrypt::prove n=32768, 4 ranks")
