@@ -5,8 +5,9 @@ import numpy as np
 import bench
 import hyper_greco_b200  # noqa
 from hyper_greco_b200 import api
-P, inp, bounds, segs, nv = bench.make_case(bench.DEFAULT_CONFIG, 0)
-ins, ct0is = bench.LAST_WITNESS
+from hyper_greco_b200 import params
+P = params.PARAMS[bench.DEFAULT_CONFIG]
+ins, ct0is = bench.make_witness(bench.DEFAULT_CONFIG, 0)
 ctx = api.Context(0)
 prover = api.BfvSkEncryptProver(ctx, P)
 flat = [ins["s"], ins["e"], ins["k1"]] + list(ins["ais"]) + list(ins["r1is"]) + [ins["r2is"]]
