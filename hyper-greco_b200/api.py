@@ -30,7 +30,8 @@ SYMBOLS = [
     "hg_lasso_pp_lookup_index", "hg_lasso_pp_memory_maps", "hg_lasso_pp_subtable_id", "hg_lasso_node_new", "hg_lasso_node_free",
     "hg_lasso_node_log2_input_size", "hg_lasso_node_device_bytes", "hg_lasso_node_prove", "hg_lasso_node_download_polys",
     "hg_lasso_node_num_chunks", "hg_lasso_node_timing", "hg_lasso_node_shard_words", "hg_lasso_node_prove_shard", "hg_lasso_node_emit_shard",
-    "hg_shard_merge", "hg_lasso_node_prove_shard_dev", "hg_lasso_node_emit_shard_dev", "hg_shard_merge_device", "hg_gkr_shard_words", "hg_gkr_prove_shard_dev", "hg_gkr_emit_shard_dev", "hg_lasso_node_verify", "hg_sumcheck_prove", "hg_mle_eval_batch", "hg_ntt", "hg_bfv_evaluate", "hg_field_selftest",
+    "hg_shard_merge", "hg_lasso_node_prove_shard_dev", "hg_lasso_node_emit_shard_dev", "hg_shard_merge_device", "hg_gkr_shard_words", "hg_gkr_prove_shard_dev", "hg_gkr_emit_shard_dev",
+    "hg_circuit_new_host", "hg_circuit_insert_lasso_host", "hg_gkr_verify", "hg_mle_eval_host", "hg_lasso_node_verify", "hg_sumcheck_prove", "hg_mle_eval_batch", "hg_ntt", "hg_bfv_evaluate", "hg_field_selftest",
     "hg_circuit_new", "hg_circuit_free", "hg_circuit_insert_input", "hg_circuit_insert_fft", "hg_circuit_insert_lasso", "hg_circuit_insert_vanilla",
     "hg_circuit_connect", "hg_circuit_evaluate", "hg_circuit_evaluate_host", "hg_circuit_node_value", "hg_gkr_prove", "hg_gkr_timing", "hg_gkr_num_challenges", "hg_gkr_num_inputs", "hg_gkr_num_input_claims",
     "hg_gkr_input_claim_num_vars", "hg_gkr_input_claim",
@@ -125,6 +126,10 @@ def lib():
         L.hg_gkr_shard_words.restype = sz
         L.hg_gkr_prove_shard_dev.argtypes = [vp, sz, vp, vp, vp, vp, i32, i32, vp, sz, C.POINTER(sz)]
         L.hg_gkr_emit_shard_dev.argtypes = [vp, vp, sz]
+        L.hg_circuit_new_host.argtypes = [i32, C.POINTER(vp)]
+        L.hg_circuit_insert_lasso_host.argtypes = [vp, vp, sz, C.POINTER(i32)]
+        L.hg_gkr_verify.argtypes = [vp, sz, vp, vp, vp, vp, vp]
+        L.hg_mle_eval_host.argtypes = [i32, vp, sz, sz, vp, vp]
         L.hg_lasso_node_verify.argtypes = [vp, sz, vp, vp, vp, vp]
         L.hg_sumcheck_prove.argtypes = [vp, i32, sz, sz, vp, vp, vp, vp, i32, vp, vp]
         L.hg_mle_eval_batch.argtypes = [vp, vp, sz, sz, sz, vp, vp]
@@ -741,13 +746,26 @@ class VanillaGate:
         self.const, self.adds, self.muls = const, list(adds), list(muls)
 
 
+def mle_eval_host(field: int, table_limbs, num_vars: int, point_ext):
+    """MultilinearPoly::evaluate on the HOST (no GPU): table of 2^num_vars base elements as canonical limbs."""
+    t = np.ascontiguousarray(table_limbs, np.uint64)
+    out = np.zeros(LIMBS[field] * DEGREE[field], np.uint64)
+    _chk(lib().hg_mle_eval_host(field, _p(t), t.size // LIMBS[field], num_vars, _p(np.ascontiguousarray(point_ext, np.uint64)), _p(out)))
+    return out
+
+
 class Circuit:
     """gkr::circuit::Circuit on the device (sk_encryption_circuit.rs:434-437): insert / connect / evaluate / prove_gkr."""
 
-    def __init__(self, ctx: Context):
+    def __init__(self, ctx: Context = None, field=None):
+        """ctx given: a circuit on that device. ctx None: a host-only DESCRIPTION of `field` (hg_circuit_new_host), for verify_gkr."""
         self.ctx = ctx
+        self.field = ctx.field if ctx is not None else (GOLDILOCKS if field is None else field)
         self.h = C.c_void_p()
-        _chk(lib().hg_circuit_new(ctx.h, C.byref(self.h)))
+        if ctx is not None:
+            _chk(lib().hg_circuit_new(ctx.h, C.byref(self.h)))
+        else:
+            _chk(lib().hg_circuit_new_host(self.field, C.byref(self.h)))
         self._keep = []
 
     def insert_input(self, log2_size, num_reps=1):
@@ -766,6 +784,21 @@ class Circuit:
         self._keep.append(node)
         return i.value
 
+    def insert_lasso_host(self, preprocessing: "LassoPreprocessing", num_vars: int):
+        """the Lasso node of a host-only circuit: described by its preprocessing and num_vars"""
+        i = C.c_int(-1)
+        _chk(lib().hg_circuit_insert_lasso_host(self.h, preprocessing.h, num_vars, C.byref(i)))
+        self._keep.append(preprocessing)
+        return i.value
+
+    def verify_gkr(self, output_claims, transcript: "Keccak256Transcript", options=None):
+        """gkr::verify_gkr (sk_encryption_circuit.rs:509-510) on the host. Returns per input node a list of (point, value); raises
+        HgError where the reference returns Err / panics."""
+        lens, pts, vals = self._claims_args(output_claims)
+        opt = None if options is None else np.array(options, np.int32)
+        _chk(lib().hg_gkr_verify(self.h, len(output_claims), _p(lens), _p(pts), _p(vals), transcript.h, _p(opt)))
+        return self._read_input_claims()
+
     def insert_vanilla_arrays(self, arity, log2_sub, num_reps, has_const, consts, add_ptr, add_coef, add_in, add_wire,
                               mul_ptr=None, mul_coef=None, mul_in0=None, mul_w0=None, mul_in1=None, mul_w1=None):
         """VanillaNode::new with the gates already in CSR arrays (numpy); see include/hg_b200.h."""
@@ -774,7 +807,7 @@ class Circuit:
         a = lambda v, t: np.ascontiguousarray(v if v is not None else (z64 if t == np.uint64 else z32), t)
         hc = np.ascontiguousarray(has_const, np.uint8)
         mp = a(mul_ptr if mul_ptr is not None else np.zeros(ng + 1, np.uint64), np.uint64)
-        limbs = LIMBS[self.ctx.field]
+        limbs = LIMBS[self.field]
 
         def felts(v):
             """field elements cross the ABI as `limbs` little-endian u64 words each: widen small (u64) coefficients"""
@@ -802,7 +835,7 @@ class Circuit:
         """Circuit::evaluate from host vectors (numpy uint64 arrays of canonical limbs; pinned memory makes the copies
         asynchronous). The arrays must stay alive until the next synchronising call (prove_gkr, mle_eval_batch)."""
         arrs = [np.ascontiguousarray(a, np.uint64) for a in host_inputs]
-        limbs = LIMBS[self.ctx.field]
+        limbs = LIMBS[self.field]
         ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
         lens = (C.c_size_t * len(arrs))(*[a.size // limbs for a in arrs])
         self._host_keepalive = arrs
@@ -820,7 +853,7 @@ class Circuit:
         return self._read_input_claims()
 
     def _read_input_claims(self):
-        el = LIMBS[self.ctx.field] * DEGREE[self.ctx.field]
+        el = LIMBS[self.field] * DEGREE[self.field]
         out = []
         for i in range(lib().hg_gkr_num_inputs(self.h)):
             cl = []
@@ -874,6 +907,120 @@ class Circuit:
             pass
 
 
+def build_bfv_circuit(c: Circuit, P, insert_lasso):
+    """BfvEncryptBlock::configure (sk_encryption_circuit.rs:86-293): the same node order and connections, for a device circuit
+    (prover) or a host-only description (verifier). insert_lasso() inserts the Lasso node and returns its id. Returns the ids of
+    a few named nodes."""
+    L, K = P.log2_size, P.K
+    N2 = 1 << L
+    idx = np.arange(N2, dtype=np.uint64)
+    ones = lambda n: np.ones(n, np.uint64)
+
+    def linear(arity, log2_sub, reps, in_idx, wires, coefs, consts=None):
+        ng = len(wires)
+        hc = np.zeros(ng, np.uint8) if consts is None else np.ones(ng, np.uint8)
+        cs = np.zeros(ng, np.uint64) if consts is None else np.asarray(consts, np.uint64)
+        return c.insert_vanilla_arrays(arity, log2_sub, reps, hc, cs, np.arange(ng + 1, dtype=np.uint64), coefs, in_idx, wires)
+
+    s, e, k1 = c.insert_input(L), c.insert_input(L), c.insert_input(L)
+    tile = np.tile(idx, K)
+    es = linear(1, L, 1, np.zeros(K * N2, np.uint32), tile, ones(K * N2))                    # :97-103
+    k1kis = linear(1, L, 1, np.zeros(K * N2, np.uint32), tile, np.repeat(np.array(P.K0IS, np.uint64), N2))   # :105-115
+    c.connect(e, es)
+    c.connect(k1, k1kis)
+    ais = [c.insert_input(L) for _ in range(K)]
+    r1is = [c.insert_input(L) for _ in range(K)]
+    r1iqis = linear(K, L, 1, np.repeat(np.arange(K, dtype=np.uint32), N2), tile, np.repeat(np.array(P.QIS, np.uint64), N2))  # :130-141
+    for r in r1is:
+        c.connect(r, r1iqis)
+    r2is = c.insert_input(P.N_LOG2, K)                                                       # :147
+    r2_log2 = P.N_LOG2 + (K.bit_length() - 1)
+    chunks = []
+    for start in range(0, 1 << r2_log2, N2):                                                 # :150-161
+        cnt = min(N2, (1 << r2_log2) - start)
+        ng = N2
+        add_ptr = np.minimum(np.arange(ng + 1, dtype=np.uint64), cnt)
+        hc = np.zeros(ng, np.uint8)
+        hc[cnt:] = 1
+        nd = c.insert_vanilla_arrays(1, r2_log2, 1, hc, np.zeros(ng, np.uint64), add_ptr, ones(cnt), np.zeros(cnt, np.uint32),
+                                     np.arange(start, start + cnt, dtype=np.uint64))
+        c.connect(r2is, nd)
+        chunks.append(nd)
+    shifts = list(P.R1_BOUNDS[:K]) + [P.R2_BOUNDS[0]] * len(chunks) + [P.S_BOUND, P.E_BOUND, P.K1_BOUND]   # :163-181 (Q7)
+    na = len(shifts)
+    lasso_in = linear(na, L, 1, np.repeat(np.arange(na, dtype=np.uint32), N2), np.tile(idx, na), ones(na * N2),
+                      consts=np.repeat(np.array(shifts, np.uint64), N2))
+    lasso = insert_lasso()                                                                   # :205-209
+    for r in r1is:
+        c.connect(r, lasso_in)
+    for ch in chunks:
+        c.connect(ch, lasso_in)
+    for x in (s, e, k1):
+        c.connect(x, lasso_in)
+    c.connect(lasso_in, lasso)
+    s_eval = c.insert_fft(L, False)                                                          # :224
+    c.connect(s, s_eval)
+    s_copy = linear(1, L, 1, np.zeros(N2, np.uint32), idx, ones(N2))                         # :227-235
+    c.connect(s_eval, s_copy)
+    sai_par = linear(K, L, 1, np.repeat(np.arange(K, dtype=np.uint32), N2), tile, ones(K * N2))   # :237-243
+    for ai in ais:                                                                           # :245-260
+        ai_eval = c.insert_fft(L, False)
+        sai_eval = c.insert_vanilla_arrays(2, L, 1, np.zeros(N2, np.uint8), np.zeros(N2, np.uint64), np.zeros(N2 + 1, np.uint64), None, None, None,
+                                           np.arange(N2 + 1, dtype=np.uint64), ones(N2), np.zeros(N2, np.uint32), idx, np.ones(N2, np.uint32), idx)
+        sai = c.insert_fft(L, True)
+        c.connect(ai, ai_eval)
+        c.connect(s_copy, sai_eval)
+        c.connect(ai_eval, sai_eval)
+        c.connect(sai_eval, sai)
+        c.connect(sai, sai_par)
+    n = 1 << P.N_LOG2                                                                        # :262-278
+    w = np.arange(n - 1, dtype=np.uint64)
+    add_ptr = np.concatenate([np.arange(n, dtype=np.uint64), [n - 1], n - 1 + np.arange(1, n, dtype=np.uint64), [2 * n - 2]]).astype(np.uint64)
+    hc = np.zeros(2 * n, np.uint8)
+    hc[n - 1] = hc[2 * n - 1] = 1
+    cyclo = c.insert_vanilla_arrays(1, P.N_LOG2, K, hc, np.zeros(2 * n, np.uint64), add_ptr, ones(2 * n - 2), np.zeros(2 * n - 2, np.uint32),
+                                    np.concatenate([w, w]))
+    summ = c.insert_vanilla_arrays(5, L, K, np.zeros(N2, np.uint8), np.zeros(N2, np.uint64), np.arange(0, 5 * N2 + 1, 5, dtype=np.uint64), ones(5 * N2),
+                                   np.tile(np.arange(5, dtype=np.uint32), N2), np.repeat(idx, 5))   # :280-285
+    c.connect(r2is, cyclo)
+    for x in (sai_par, es, k1kis, r1iqis, cyclo):
+        c.connect(x, summ)
+    return dict(s=s, e=e, k1=k1, lasso_in=lasso_in, sum=summ)
+
+
+class BfvSkEncryptVerifier:
+    """BfvEncrypt::{setup, configure, verify} (sk_encryption_circuit.rs:300-363, :462-517) on the HOST: no GPU, no context."""
+
+    def __init__(self, params, field=GOLDILOCKS):
+        from . import witness
+        self.P, self.field = params, field
+        self.pp = LassoPreprocessing.preprocess(witness.lasso_lookup_bounds(params))
+        self.circuit = Circuit(None, field)
+        nv = witness.lasso_num_vars(params)
+        self.ids = build_bfv_circuit(self.circuit, params, lambda: self.circuit.insert_lasso_host(self.pp, nv))
+        self.ct0is_log2_size = params.log2_size + (params.K.bit_length() - 1)
+
+    def verify(self, host_inputs, host_ct0is, proof: bytes, options=None):
+        """verify (:462-517): inputs in get_inputs order as canonical limbs. Raises HgError if the proof is rejected."""
+        tr = Keccak256Transcript.from_proof(proof, self.field)                                   # :476
+        L = self.ct0is_log2_size
+        point = tr.squeeze_challenges(L)                                                          # :499
+        value = mle_eval_host(self.field, host_ct0is, L, point)                                   # :500
+        el = point.shape[1]
+        claims = self.circuit.verify_gkr([(np.zeros((0, el), np.uint64), np.zeros(el, np.uint64)), (point, value)], tr, options)   # :504-510
+        if len(claims) != len(host_inputs):
+            raise HgError("verify: input count mismatch")
+        for vec, cl in zip(host_inputs, claims):                                                  # :512-516
+            for pt, v in cl:
+                if not (mle_eval_host(self.field, vec, pt.shape[0], pt) == v).all():
+                    raise HgError("verify: input claim does not match the input (sk_encryption_circuit.rs:515)")
+        try:
+            tr.read_felt_ext()
+        except HgError:
+            return claims
+        raise HgError("verify: trailing bytes in proof")
+
+
 class BfvSkEncryptProver:
     """BfvEncrypt::{setup, configure, prove} (sk_encryption_circuit.rs:300-460) with every table on the device."""
 
@@ -881,85 +1028,11 @@ class BfvSkEncryptProver:
         from . import witness
         P = self.P = params
         self.ctx = ctx
-        L, K = P.log2_size, P.K
-        N2 = 1 << L
         self.pp = LassoPreprocessing.preprocess(witness.lasso_lookup_bounds(P))                 # setup(): :327-341
         self.lasso = LassoNode(ctx, self.pp, witness.lasso_num_vars(P), witness.lasso_lookup_segments(P))
         c = self.circuit = Circuit(ctx)                                                         # configure(): :351-363, :86-293
-        idx = np.arange(N2, dtype=np.uint64)
-        ones = lambda n: np.ones(n, np.uint64)
-
-        def linear(arity, log2_sub, reps, in_idx, wires, coefs, consts=None):
-            ng = len(wires)
-            hc = np.zeros(ng, np.uint8) if consts is None else np.ones(ng, np.uint8)
-            cs = np.zeros(ng, np.uint64) if consts is None else np.asarray(consts, np.uint64)
-            return c.insert_vanilla_arrays(arity, log2_sub, reps, hc, cs, np.arange(ng + 1, dtype=np.uint64), coefs, in_idx, wires)
-
-        s, e, k1 = c.insert_input(L), c.insert_input(L), c.insert_input(L)
-        tile = np.tile(idx, K)
-        es = linear(1, L, 1, np.zeros(K * N2, np.uint32), tile, ones(K * N2))                    # :97-103
-        k1kis = linear(1, L, 1, np.zeros(K * N2, np.uint32), tile, np.repeat(np.array(P.K0IS, np.uint64), N2))   # :105-115
-        c.connect(e, es)
-        c.connect(k1, k1kis)
-        ais = [c.insert_input(L) for _ in range(K)]
-        r1is = [c.insert_input(L) for _ in range(K)]
-        r1iqis = linear(K, L, 1, np.repeat(np.arange(K, dtype=np.uint32), N2), tile, np.repeat(np.array(P.QIS, np.uint64), N2))  # :130-141
-        for r in r1is:
-            c.connect(r, r1iqis)
-        r2is = c.insert_input(P.N_LOG2, K)                                                       # :147
-        r2_log2 = P.N_LOG2 + (K.bit_length() - 1)
-        chunks = []
-        for start in range(0, 1 << r2_log2, N2):                                                 # :150-161
-            cnt = min(N2, (1 << r2_log2) - start)
-            ng = N2
-            add_ptr = np.minimum(np.arange(ng + 1, dtype=np.uint64), cnt)
-            hc = np.zeros(ng, np.uint8)
-            hc[cnt:] = 1
-            nd = c.insert_vanilla_arrays(1, r2_log2, 1, hc, np.zeros(ng, np.uint64), add_ptr, ones(cnt), np.zeros(cnt, np.uint32),
-                                         np.arange(start, start + cnt, dtype=np.uint64))
-            c.connect(r2is, nd)
-            chunks.append(nd)
-        shifts = list(P.R1_BOUNDS[:K]) + [P.R2_BOUNDS[0]] * len(chunks) + [P.S_BOUND, P.E_BOUND, P.K1_BOUND]   # :163-181 (Q7)
-        na = len(shifts)
-        lasso_in = linear(na, L, 1, np.repeat(np.arange(na, dtype=np.uint32), N2), np.tile(idx, na), ones(na * N2),
-                          consts=np.repeat(np.array(shifts, np.uint64), N2))
-        lasso = c.insert_lasso(self.lasso)                                                       # :205-209
-        for r in r1is:
-            c.connect(r, lasso_in)
-        for ch in chunks:
-            c.connect(ch, lasso_in)
-        for x in (s, e, k1):
-            c.connect(x, lasso_in)
-        c.connect(lasso_in, lasso)
-        s_eval = c.insert_fft(L, False)                                                          # :224
-        c.connect(s, s_eval)
-        s_copy = linear(1, L, 1, np.zeros(N2, np.uint32), idx, ones(N2))                         # :227-235
-        c.connect(s_eval, s_copy)
-        sai_par = linear(K, L, 1, np.repeat(np.arange(K, dtype=np.uint32), N2), tile, ones(K * N2))   # :237-243
-        for ai in ais:                                                                           # :245-260
-            ai_eval = c.insert_fft(L, False)
-            sai_eval = c.insert_vanilla_arrays(2, L, 1, np.zeros(N2, np.uint8), np.zeros(N2, np.uint64), np.zeros(N2 + 1, np.uint64), None, None, None,
-                                               np.arange(N2 + 1, dtype=np.uint64), ones(N2), np.zeros(N2, np.uint32), idx, np.ones(N2, np.uint32), idx)
-            sai = c.insert_fft(L, True)
-            c.connect(ai, ai_eval)
-            c.connect(s_copy, sai_eval)
-            c.connect(ai_eval, sai_eval)
-            c.connect(sai_eval, sai)
-            c.connect(sai, sai_par)
-        n = 1 << P.N_LOG2                                                                        # :262-278
-        w = np.arange(n - 1, dtype=np.uint64)
-        add_ptr = np.concatenate([np.arange(n, dtype=np.uint64), [n - 1], n - 1 + np.arange(1, n, dtype=np.uint64), [2 * n - 2]]).astype(np.uint64)
-        hc = np.zeros(2 * n, np.uint8)
-        hc[n - 1] = hc[2 * n - 1] = 1
-        cyclo = c.insert_vanilla_arrays(1, P.N_LOG2, K, hc, np.zeros(2 * n, np.uint64), add_ptr, ones(2 * n - 2), np.zeros(2 * n - 2, np.uint32),
-                                        np.concatenate([w, w]))
-        summ = c.insert_vanilla_arrays(5, L, K, np.zeros(N2, np.uint8), np.zeros(N2, np.uint64), np.arange(0, 5 * N2 + 1, 5, dtype=np.uint64), ones(5 * N2),
-                                       np.tile(np.arange(5, dtype=np.uint32), N2), np.repeat(idx, 5))   # :280-285
-        c.connect(r2is, cyclo)
-        for x in (sai_par, es, k1kis, r1iqis, cyclo):
-            c.connect(x, summ)
-        self.ids = dict(s=s, e=e, k1=k1, lasso_in=lasso_in, sum=summ)
-        self.ct0is_log2_size = L + (K.bit_length() - 1)                                          # :519-522
+        self.ids = build_bfv_circuit(c, P, lambda: c.insert_lasso(self.lasso))                  # :205-209
+        self.ct0is_log2_size = P.log2_size + (P.K.bit_length() - 1)                             # :519-522
 
     def upload_inputs(self, ins):
         u = lambda v: DeviceBuffer.from_numpy(self.ctx, np.asarray(v, dtype=np.uint64).reshape(-1))

@@ -13,6 +13,7 @@
 #include "gkr_dev.cuh"
 #include "prover.cuh"
 #include "lasso_verify.hpp"
+#include "gkr_verify.hpp"
 
 using namespace hg;
 
@@ -186,6 +187,10 @@ struct ICircuit {
     virtual void prove(size_t n_claims, const size_t* lens, const uint64_t* pts, const uint64_t* vals, ITranscript* t, int mode, const WireOptions& wo) = 0;
     virtual const double* timing() const = 0;
     virtual size_t num_challenges() const = 0;
+    virtual int insert_lasso_host(const LassoPreprocessing&, int) { throw std::runtime_error("hg_circuit_insert_lasso_host needs a host-only circuit (hg_circuit_new_host)"); }
+    virtual void verify(size_t, const size_t*, const uint64_t*, const uint64_t*, ITranscript*, const WireOptions&) {
+        throw std::runtime_error("hg_gkr_verify needs a host-only circuit description (hg_circuit_new_host)");
+    }
     virtual size_t shard_words() = 0;
     virtual size_t prove_shard_dev(size_t n_claims, const size_t* lens, const uint64_t* pts, const uint64_t* vals, ITranscript* t, const WireOptions& wo, int rank, int world,
                                    void* d_out_words, size_t cap_words) = 0;
@@ -294,12 +299,62 @@ template <class FP> struct CircuitT : ICircuit {
 };
 
 // field-dependent free functions of the ABI
+// host-only circuit description: the verifier's side of gkr::verify_gkr (gkr_verify.hpp)
+template <class FP> struct HostCircuitT : ICircuit {
+    typedef typename FP::X X;
+    GkrVerifierHost<FP> v;
+    HostCircuitT() { field_id = FP::FIELD_ID; }
+    [[noreturn]] static void no_device() { throw std::runtime_error("this circuit is a host-only description: it cannot evaluate or prove"); }
+    int insert_input(size_t l, size_t r) override { return v.insert_input(l, r); }
+    int insert_fft(size_t l, bool inv) override { return v.insert_fft(l, inv); }
+    int insert_lasso(ILassoNode*) override { throw std::runtime_error("a host-only circuit takes its Lasso node through hg_circuit_insert_lasso_host"); }
+    int insert_lasso_host(const LassoPreprocessing& pp, int nv) override { return v.insert_lasso(pp, nv); }
+    int insert_vanilla(const VanillaDesc& d) override { return v.insert_vanilla(d); }
+    void connect(int a, int b) override { v.connect(a, b); }
+    void evaluate(const void* const*, size_t) override { no_device(); }
+    void evaluate_host(DeviceCtx*, const void* const*, const size_t*, size_t) override { no_device(); }
+    void node_value(int, const void**, size_t*) override { no_device(); }
+    void prove(size_t, const size_t*, const uint64_t*, const uint64_t*, ITranscript*, int, const WireOptions&) override { no_device(); }
+    const double* timing() const override { static const double z[6] = {0, 0, 0, 0, 0, 0}; return z; }
+    size_t num_challenges() const override { return 0; }
+    size_t shard_words() override { return 0; }
+    size_t prove_shard_dev(size_t, const size_t*, const uint64_t*, const uint64_t*, ITranscript*, const WireOptions&, int, int, void*, size_t) override { no_device(); }
+    void emit_shard_dev(const void*, size_t) override { no_device(); }
+    void verify(size_t n_claims, const size_t* lens, const uint64_t* pts, const uint64_t* vals, ITranscript* t, const WireOptions& wo) override {
+        if (t->field_id != FP::FIELD_ID) throw std::runtime_error("transcript belongs to another field");
+        std::vector<typename GkrVerifierHost<FP>::Claim> oc(n_claims);
+        size_t off = 0;
+        for (size_t i = 0; i < n_claims; i++) {
+            for (size_t k = 0; k < lens[i]; k++) oc[i].point.push_back(FP::x_from_limbs(pts + FP::X_LIMBS * (off + k)));
+            off += lens[i];
+            oc[i].value = FP::x_from_limbs(vals + FP::X_LIMBS * i);
+        }
+        auto res = v.verify(*(Keccak256Transcript<FP>*)t->raw(), wo, oc);
+        input_claims.clear();
+        for (auto& cl : res) {
+            std::vector<InputClaimErased> e;
+            for (auto& ic : cl) {
+                InputClaimErased x;
+                x.nvars = ic.point.size();
+                x.point.resize(ic.point.size() * FP::X_LIMBS);
+                x.value.resize(FP::X_LIMBS);
+                for (size_t q = 0; q < ic.point.size(); q++) FP::x_to_limbs(ic.point[q], x.point.data() + FP::X_LIMBS * q);
+                FP::x_to_limbs(ic.value, x.value.data());
+                e.push_back(x);
+            }
+            input_claims.push_back(e);
+        }
+    }
+};
+
 struct IFieldOps {
     virtual ~IFieldOps() {}
     virtual ITranscript* new_transcript() = 0;
     virtual ILassoNode* new_lasso_node(DeviceCtx* ctx, const LassoPreprocessing& pp, int nv, const std::vector<uint8_t>& rows) = 0;
     virtual ICircuit* new_circuit(DeviceCtx* ctx) = 0;
     virtual void shard_merge_device(DeviceCtx* ctx, const void* d_parts, int world, size_t n_words, void* d_acc) = 0;
+    virtual void mle_eval_host(const uint64_t* table_limbs, size_t n, size_t num_vars, const uint64_t* point_ext, uint64_t* out_ext) = 0;
+    virtual ICircuit* new_host_circuit() = 0;
     virtual void sumcheck_prove(DeviceCtx* ctx, const WireOptions& wo, int arity, size_t n_terms, size_t num_vars, const uint64_t* coeffs, const void* d_tables,
                                 const uint64_t* claim, ITranscript* t, int mode, uint64_t* out_point, uint64_t* out_evals) = 0;
     virtual void mle_eval_batch(DeviceCtx* ctx, const void* d_tables, size_t n_tables, size_t stride, size_t num_vars, const uint64_t* point, uint64_t* out) = 0;
@@ -358,6 +413,14 @@ template <class FP> struct FieldOpsT : IFieldOps {
         HG_CUDA(cudaStreamSynchronize(ctx->stream));
         for (size_t i = 0; i < n; i++) FP::x_to_limbs(ho[i], out_ext + i * FP::X_LIMBS);
     }
+    void mle_eval_host(const uint64_t* table_limbs, size_t n, size_t num_vars, const uint64_t* point_ext, uint64_t* out_ext) override {
+        std::vector<B> t(n);
+        for (size_t i = 0; i < n; i++) t[i] = FP::b_from_limbs(table_limbs + i * FP::B_LIMBS);
+        std::vector<X> pt(num_vars);
+        for (size_t i = 0; i < num_vars; i++) pt[i] = FP::x_from_limbs(point_ext + i * FP::X_LIMBS);
+        FP::x_to_limbs(GkrVerifierHost<FP>::mle_eval_base(t.data(), n, pt), out_ext);
+    }
+    ICircuit* new_host_circuit() override { return new HostCircuitT<FP>(); }
     void shard_merge_device(DeviceCtx* ctx, const void* d_parts, int world, size_t n_words, void* d_acc) override {
         constexpr size_t XW = sizeof(X) / sizeof(uint64_t);
         if (n_words % XW || world < 1) throw std::runtime_error("hg_shard_merge_device: bad arguments");
@@ -468,9 +531,13 @@ struct hg_ctx {
     std::unique_ptr<IFieldOps> ops;
 };
 struct hg_circuit {
-    hg_ctx* ctx;
+    hg_ctx* ctx = nullptr;  // nullptr: a host-only circuit description (hg_circuit_new_host), usable for hg_gkr_verify only
     std::unique_ptr<ICircuit> c;
 };
+static void circuit_use_device(hg_circuit* c) {
+    if (!c->ctx) throw std::runtime_error("this circuit is a host-only description (hg_circuit_new_host): it has no device, only hg_gkr_verify runs on it");
+    circuit_use_device(c);
+}
 struct hg_buf {
     void* p = nullptr;
     size_t bytes = 0;
@@ -790,14 +857,14 @@ size_t hg_gkr_shard_words(hg_circuit* c) {
 int hg_gkr_prove_shard_dev(hg_circuit* c, size_t n_output_claims, const size_t* point_lens, const uint64_t* points_ext, const uint64_t* values_ext, hg_transcript* t,
                            int rank, int world, void* d_out_words, size_t cap_words, size_t* n_words) {
     HG_TRY({
-        HG_CUDA(cudaSetDevice(c->ctx->dev.device));
+        circuit_use_device(c);
         if (!d_out_words || !n_words) throw std::runtime_error("hg_gkr_prove_shard_dev: NULL output");
         *n_words = c->c->prove_shard_dev(n_output_claims, point_lens, points_ext, values_ext, t->t.get(), c->ctx->wire, rank, world, d_out_words, cap_words);
     })
 }
 int hg_gkr_emit_shard_dev(hg_circuit* c, const void* d_merged_words, size_t n_words) {
     HG_TRY({
-        HG_CUDA(cudaSetDevice(c->ctx->dev.device));
+        circuit_use_device(c);
         c->c->emit_shard_dev(d_merged_words, n_words);
     })
 }
@@ -862,14 +929,37 @@ int hg_circuit_new(hg_ctx* ctx, hg_circuit** out) {
         *out = c.release();
     })
 }
+int hg_circuit_new_host(int field_id, hg_circuit** out) {
+    HG_TRY({
+        if (!out) throw std::runtime_error("hg_circuit_new_host: out is NULL");
+        std::unique_ptr<hg_circuit> c(new hg_circuit());
+        c->c.reset(ops_for_field(field_id)->new_host_circuit());
+        *out = c.release();
+    })
+}
+int hg_circuit_insert_lasso_host(hg_circuit* c, const hg_lasso_pp* pp, size_t num_vars, int* out_id) { HG_TRY({ *out_id = c->c->insert_lasso_host(pp->pp, (int)num_vars); }) }
+int hg_gkr_verify(hg_circuit* c, size_t n_output_claims, const size_t* point_lens, const uint64_t* points_ext, const uint64_t* values_ext, hg_transcript* t,
+                  const int* options3) {
+    HG_TRY({
+        WireOptions wo;
+        if (options3) { wo.a3_wire = options3[0]; wo.a3_h1 = options3[1]; wo.a5_ascending = options3[2]; }
+        c->c->verify(n_output_claims, point_lens, points_ext, values_ext, t->t.get(), wo);
+    })
+}
+int hg_mle_eval_host(int field_id, const uint64_t* table_limbs, size_t n, size_t num_vars, const uint64_t* point_ext, uint64_t* out_ext) {
+    HG_TRY({
+        if (n != (size_t)1 << num_vars) throw std::runtime_error("hg_mle_eval_host: the table must have 2^num_vars elements");
+        ops_for_field(field_id)->mle_eval_host(table_limbs, n, num_vars, point_ext, out_ext);
+    })
+}
 void hg_circuit_free(hg_circuit* c) {
     if (!c) return;
-    cudaSetDevice(c->ctx->dev.device);
+    if (c->ctx) cudaSetDevice(c->ctx->dev.device);
     delete c;
 }
 int hg_circuit_insert_input(hg_circuit* c, size_t log2_size, size_t num_reps, int* out_id) { HG_TRY({ *out_id = c->c->insert_input(log2_size, num_reps); }) }
 int hg_circuit_insert_fft(hg_circuit* c, size_t log2_size, int inverse, int* out_id) {
-    HG_TRY({ HG_CUDA(cudaSetDevice(c->ctx->dev.device)); *out_id = c->c->insert_fft(log2_size, inverse != 0); })
+    HG_TRY({ if (c->ctx) circuit_use_device(c); *out_id = c->c->insert_fft(log2_size, inverse != 0); })
 }
 int hg_circuit_insert_lasso(hg_circuit* c, hg_lasso_node* node, int* out_id) { HG_TRY({ *out_id = c->c->insert_lasso(node->n.get()); }) }
 int hg_circuit_insert_vanilla(hg_circuit* c, size_t input_arity, size_t log2_sub_input_size, size_t num_reps, size_t n_gates, const uint8_t* has_const,
@@ -877,7 +967,7 @@ int hg_circuit_insert_vanilla(hg_circuit* c, size_t input_arity, size_t log2_sub
                               const uint64_t* add_wire, const uint64_t* mul_ptr, const uint64_t* mul_coef, const uint32_t* mul_in0, const uint64_t* mul_w0,
                               const uint32_t* mul_in1, const uint64_t* mul_w1, int* out_id) {
     HG_TRY({
-        HG_CUDA(cudaSetDevice(c->ctx->dev.device));
+        if (c->ctx) circuit_use_device(c);
         const size_t L = c->c->field_id == HG_FIELD_BN254 ? 4 : 1;  // limbs per coefficient
         VanillaDesc d;
         d.arity = input_arity; d.log2_sub = log2_sub_input_size; d.num_reps = num_reps; d.n_gates = n_gates;
@@ -903,16 +993,16 @@ int hg_circuit_insert_vanilla(hg_circuit* c, size_t input_arity, size_t log2_sub
 }
 int hg_circuit_connect(hg_circuit* c, int from, int to) { HG_TRY({ c->c->connect(from, to); }) }
 int hg_circuit_evaluate(hg_circuit* c, const void* const* d_inputs, size_t n_inputs) {
-    HG_TRY({ HG_CUDA(cudaSetDevice(c->ctx->dev.device)); c->c->evaluate(d_inputs, n_inputs); })
+    HG_TRY({ circuit_use_device(c); c->c->evaluate(d_inputs, n_inputs); })
 }
 int hg_circuit_evaluate_host(hg_circuit* c, const void* const* host_inputs, const size_t* n_elems, size_t n_inputs) {
-    HG_TRY({ HG_CUDA(cudaSetDevice(c->ctx->dev.device)); c->c->evaluate_host(&c->ctx->dev, host_inputs, n_elems, n_inputs); })
+    HG_TRY({ circuit_use_device(c); c->c->evaluate_host(&c->ctx->dev, host_inputs, n_elems, n_inputs); })
 }
 int hg_circuit_node_value(hg_circuit* c, int id, const void** d_ptr, size_t* len) { HG_TRY({ c->c->node_value(id, d_ptr, len); }) }
 int hg_gkr_prove(hg_circuit* c, size_t n_output_claims, const size_t* point_lens, const uint64_t* points_ext, const uint64_t* values_ext,
                  hg_transcript* t, int mode) {
     HG_TRY({
-        HG_CUDA(cudaSetDevice(c->ctx->dev.device));
+        circuit_use_device(c);
         c->c->prove(n_output_claims, point_lens, points_ext, values_ext, t->t.get(), mode, c->ctx->wire);
     })
 }

@@ -242,6 +242,20 @@ size_t hg_gkr_shard_words(hg_circuit* c);
 int hg_gkr_prove_shard_dev(hg_circuit* c, size_t n_output_claims, const size_t* point_lens, const uint64_t* points_ext, const uint64_t* values_ext, hg_transcript* t,
                            int rank, int world, void* d_out_words, size_t cap_words, size_t* n_words);
 int hg_gkr_emit_shard_dev(hg_circuit* c, const void* d_merged_words, size_t n_words);
+/* ---- verifier: BfvEncrypt::verify (bfv-gkr/src/sk_encryption_circuit.rs:462-517) on the HOST, no GPU and no context.
+ *      hg_circuit_new_host makes a circuit DESCRIPTION: the hg_circuit_insert_input / _fft / _vanilla / _connect calls above build it
+ *      exactly as for a device circuit, the Lasso node is described by its preprocessing and num_vars (hg_circuit_insert_lasso_host);
+ *      evaluate / prove calls on it fail. hg_gkr_verify is gkr::verify_gkr (:509-510): it reads the proof from `t` (made by
+ *      hg_transcript_from_proof, or a caller-owned one with a read callback), checks every node's sumcheck and final evaluation and the
+ *      Lasso node (as hg_lasso_node_verify), and leaves the claims on the input nodes in the hg_gkr_input_claim* getters. The
+ *      caller finishes :512-516 by comparing each claim with the MLE of the corresponding input (hg_mle_eval_host).
+ *      options3 as in hg_lasso_node_verify. Non-zero return = the reference's Err / panic. */
+int hg_circuit_new_host(int field_id, hg_circuit** out);
+int hg_circuit_insert_lasso_host(hg_circuit* c, const hg_lasso_pp* pp, size_t num_vars, int* out_id);
+int hg_gkr_verify(hg_circuit* c, size_t n_output_claims, const size_t* point_lens, const uint64_t* points_ext, const uint64_t* values_ext, hg_transcript* t,
+                  const int* options3);
+/* MultilinearPoly::evaluate on the host: table of 2^num_vars base elements (canonical limbs), point of num_vars extension elements */
+int hg_mle_eval_host(int field_id, const uint64_t* table_limbs, size_t n, size_t num_vars, const uint64_t* point_ext, uint64_t* out_ext);
 /* host phases of the last hg_gkr_prove in microseconds: [witness kernels enqueue, squeeze+upload challenges, protocol walk,
  * batched layer enqueue, wait for the GPU, serialise]; number of extension challenges one proof squeezes */
 void hg_gkr_timing(const hg_circuit* c, double* out_us6);

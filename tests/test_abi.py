@@ -86,6 +86,45 @@ def test_callback_transcript_forwards_every_primitive(api):
         api.CallbackTranscript(Broken()).squeeze_challenge()
 
 
+@pytest.mark.parametrize("field,tag,io_file", [(0, "goldilocks", "circuit_io_{}.npz"), (1, "bn254", "circuit_io_bn254_{}.npz")])
+def test_host_verifier_accepts_golden_bfv_proofs_and_rejects_tampering(api, golden_dir, field, tag, io_file):
+    """hg_gkr_verify + hg_mle_eval_host = BfvEncrypt::verify (sk_encryption_circuit.rs:462-517) in the PRODUCT, on the host: the
+    committed golden proofs of the whole circuit are accepted without a GPU; a flipped bit in the messages of the generic layers,
+    a truncated proof, trailing bytes and a wrong public output are rejected; a flip inside the Lasso node's discarded sumcheck
+    outputs is accepted, as in the reference (lasso.rs:129-133, verifier.rs:218-221 drop them: SURVEY Q12)."""
+    from hyper_greco_b200 import params
+    name = "1024_1x27_65537"
+    P = params.PARAMS[name]
+    io = np.load(os.path.join(golden_dir, io_file.format(name)))
+    flat = [np.ascontiguousarray(v).reshape(-1) for v in [io["s"], io["e"], io["k1"]] + list(io["ais"]) + list(io["r1is"]) + [io["r2is"]]]
+    ct = np.ascontiguousarray(io["ct0is"]).reshape(-1)
+    proof = open(os.path.join(golden_dir, f"proof_{tag}_bfv_encrypt_{name}.bin"), "rb").read()
+    v = api.BfvSkEncryptVerifier(P, field)
+    claims = v.verify(flat, ct, proof)
+    assert len(claims) == len(flat) and all(len(c) >= 1 for c in claims)
+    step = 16 if field == 0 else 32
+    for off in (3, 5 * step + 1, len(proof) - 2, len(proof) - 40 * step):       # first / last node sumchecks of the generic layers
+        bad = bytearray(proof)
+        bad[off] ^= 0x10
+        with pytest.raises(api.HgError):
+            v.verify(flat, ct, bytes(bad))
+    with pytest.raises(api.HgError):
+        v.verify(flat, ct, proof[:-step])
+    with pytest.raises(api.HgError):
+        v.verify(flat, ct, proof + proof[-step:])
+    ct_bad = ct.copy()
+    ct_bad[0] ^= 1
+    with pytest.raises(api.HgError):
+        v.verify(flat, ct_bad, proof)
+    s_bad = [x.copy() for x in flat]
+    s_bad[0][0] ^= 1                                                              # the input-claim check of :512-516
+    with pytest.raises(api.HgError):
+        v.verify(s_bad, ct, proof)
+    # compute entry points of a host-only description fail loudly
+    with pytest.raises(api.HgError):
+        v.circuit.evaluate_host(flat)
+
+
 def test_preprocessing_matches_oracle(api, oracle):
     from hyper_greco_b200 import params, witness
     for name, P in params.PARAMS.items():

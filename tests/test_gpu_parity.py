@@ -430,6 +430,15 @@ def test_full_gkr_prove_full_size_properties(api, ctx, oracle):
     flat = [ins["s"], ins["e"], ins["k1"]] + list(ins["ais"]) + list(ins["r1is"]) + [ins["r2is"]]
     proof3, _ = prover.prove_host([np.array(v, dtype=np.uint64) for v in flat], np.array(ct0is, dtype=np.uint64), 0)
     assert proof3 == proof
+    # the PRODUCT's own host verifier (hg_gkr_verify, no GPU involved) agrees with the oracle's: accepts, same input claims; rejects a flip
+    ver = api.BfvSkEncryptVerifier(P)
+    hflat = [np.array(v, dtype=np.uint64) for v in flat]
+    vclaims = ver.verify(hflat, np.array(ct0is, dtype=np.uint64), proof)
+    assert all((a[0] == b[0]).all() and (a[1] == b[1]).all() for ca, cb in zip(claims, vclaims) for a, b in zip(ca, cb))
+    bad = bytearray(proof)
+    bad[40] ^= 2
+    with pytest.raises(api.HgError):
+        ver.verify(hflat, np.array(ct0is, dtype=np.uint64), bytes(bad))
 
 
 def test_full_gkr_prove_n16384_k8(api, ctx, oracle):
