@@ -31,7 +31,7 @@ SYMBOLS = [
     "hg_lasso_node_log2_input_size", "hg_lasso_node_device_bytes", "hg_lasso_node_prove", "hg_lasso_node_download_polys",
     "hg_lasso_node_num_chunks", "hg_lasso_node_timing", "hg_lasso_node_shard_words", "hg_lasso_node_prove_shard", "hg_lasso_node_emit_shard",
     "hg_shard_merge", "hg_lasso_node_prove_shard_dev", "hg_lasso_node_emit_shard_dev", "hg_shard_merge_device", "hg_gkr_shard_words", "hg_gkr_prove_shard_dev", "hg_gkr_emit_shard_dev",
-    "hg_circuit_new_host", "hg_circuit_insert_lasso_host", "hg_gkr_verify", "hg_mle_eval_host", "hg_lasso_node_verify", "hg_sumcheck_prove", "hg_mle_eval_batch", "hg_ntt", "hg_bfv_evaluate", "hg_field_selftest",
+    "hg_circuit_new_host", "hg_circuit_insert_lasso_host", "hg_gkr_verify", "hg_mle_eval_host", "hg_bfv_witness_generate", "hg_lasso_node_verify", "hg_sumcheck_prove", "hg_mle_eval_batch", "hg_ntt", "hg_bfv_evaluate", "hg_field_selftest",
     "hg_circuit_new", "hg_circuit_free", "hg_circuit_insert_input", "hg_circuit_insert_fft", "hg_circuit_insert_lasso", "hg_circuit_insert_vanilla",
     "hg_circuit_connect", "hg_circuit_evaluate", "hg_circuit_evaluate_host", "hg_circuit_node_value", "hg_gkr_prove", "hg_gkr_timing", "hg_gkr_num_challenges", "hg_gkr_num_inputs", "hg_gkr_num_input_claims",
     "hg_gkr_input_claim_num_vars", "hg_gkr_input_claim",
@@ -130,6 +130,7 @@ def lib():
         L.hg_circuit_insert_lasso_host.argtypes = [vp, vp, sz, C.POINTER(i32)]
         L.hg_gkr_verify.argtypes = [vp, sz, vp, vp, vp, vp, vp]
         L.hg_mle_eval_host.argtypes = [i32, vp, sz, sz, vp, vp]
+        L.hg_bfv_witness_generate.argtypes = [vp, sz, sz] + [vp] * 15
         L.hg_lasso_node_verify.argtypes = [vp, sz, vp, vp, vp, vp]
         L.hg_sumcheck_prove.argtypes = [vp, i32, sz, sz, vp, vp, vp, vp, i32, vp, vp]
         L.hg_mle_eval_batch.argtypes = [vp, vp, sz, sz, sz, vp, vp]
@@ -286,6 +287,28 @@ class DeviceBuffer:
             self.free()
         except Exception:
             pass
+
+
+class DeviceView:
+    """A slice of a DeviceBuffer (no ownership): what Circuit.evaluate needs is .ptr"""
+
+    def __init__(self, base: DeviceBuffer, offset: int, nbytes: int):
+        self.base, self.offset, self.nbytes, self.ctx = base, offset, nbytes, base.ctx
+
+    @property
+    def ptr(self):
+        return self.base.ptr + self.offset
+
+    def download(self, dtype, count):
+        return self.base.download(dtype, count, self.offset)
+
+    def to_field(self, count):
+        k = LIMBS[self.ctx.field]
+        tmp = DeviceBuffer(self.ctx, count * 8 * k)
+        tmp.upload(self.base.download(np.uint64, count * k, self.offset))
+        out = tmp.to_field(count)
+        tmp.free()
+        return out
 
 
 class Keccak256Transcript:

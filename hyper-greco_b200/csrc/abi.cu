@@ -14,6 +14,7 @@
 #include "prover.cuh"
 #include "lasso_verify.hpp"
 #include "gkr_verify.hpp"
+#include "witness_gen.cuh"
 
 using namespace hg;
 
@@ -353,6 +354,9 @@ struct IFieldOps {
     virtual ILassoNode* new_lasso_node(DeviceCtx* ctx, const LassoPreprocessing& pp, int nv, const std::vector<uint8_t>& rows) = 0;
     virtual ICircuit* new_circuit(DeviceCtx* ctx) = 0;
     virtual void shard_merge_device(DeviceCtx* ctx, const void* d_parts, int world, size_t n_words, void* d_acc) = 0;
+    virtual void witness_generate(DeviceCtx* dev, size_t n, size_t K, const uint64_t* qis, const uint64_t* k0is, const uint64_t* r1b, const uint64_t* r2b, const int8_t* s,
+                                  const int8_t* e, const int32_t* k1, const int64_t* a, void* d_s, void* d_e, void* d_k1, void* d_ais, void* d_r1is, void* d_r2is,
+                                  void* d_ct0is) = 0;
     virtual void mle_eval_host(const uint64_t* table_limbs, size_t n, size_t num_vars, const uint64_t* point_ext, uint64_t* out_ext) = 0;
     virtual ICircuit* new_host_circuit() = 0;
     virtual void sumcheck_prove(DeviceCtx* ctx, const WireOptions& wo, int arity, size_t n_terms, size_t num_vars, const uint64_t* coeffs, const void* d_tables,
@@ -412,6 +416,57 @@ template <class FP> struct FieldOpsT : IFieldOps {
         HG_CUDA(cudaMemcpyAsync(ho.data(), o.p, n * sizeof(X), cudaMemcpyDeviceToHost, ctx->stream));
         HG_CUDA(cudaStreamSynchronize(ctx->stream));
         for (size_t i = 0; i < n; i++) FP::x_to_limbs(ho[i], out_ext + i * FP::X_LIMBS);
+    }
+    // scripts/circuit_sk.py:72-140 on the device (witness_gen.cuh). Small host inputs, device outputs in the library's representation.
+    DevBuf<signed char> wg_s_, wg_e_;
+    DevBuf<int> wg_k1_;
+    DevBuf<long long> wg_a_;
+    DevBuf<i128> wg_hat_;
+    DevBuf<WitGenStatus> wg_st_;
+    void witness_generate(DeviceCtx* dev, size_t n, size_t K, const uint64_t* qis, const uint64_t* k0is, const uint64_t* r1b, const uint64_t* r2b, const int8_t* s,
+                          const int8_t* e, const int32_t* k1, const int64_t* a, void* d_s, void* d_e, void* d_k1, void* d_ais, void* d_r1is, void* d_r2is,
+                          void* d_ct0is) override {
+        if (n < 2 || (n & (n - 1)) || K < 1 || K > 64) throw std::runtime_error("hg_bfv_witness_generate: n must be a power of two >= 2 and 1 <= K <= 64");
+        cudaStream_t st = dev->stream;
+        WitGenParams P;
+        memset(&P, 0, sizeof P);
+        P.n = (int)n; P.K = (int)K;
+        for (size_t i = 0; i < K; i++) {
+            if (qis[i] >= ((uint64_t)1 << 62) || qis[i] < 3) throw std::runtime_error("hg_bfv_witness_generate: modulus out of range");
+            P.q[i] = (long long)qis[i]; P.k0[i] = (long long)k0is[i]; P.r1_bound[i] = (long long)r1b[i]; P.r2_bound[i] = (long long)r2b[i];
+        }
+        {   // p as canonical limbs: the limbs of -1 plus one
+            B m1 = FP::b_sub(FP::b_zero(), FP::b_one());
+            u64 l[4] = {0, 0, 0, 0};
+            FP::b_to_limbs(m1, l);
+            u64 c = 1;
+            for (int q = 0; q < 4; q++) { const u64 v = l[q] + c; c = (v < l[q]) ? 1 : 0; P.p[q] = v; }
+        }
+        auto grow = [&](auto& buf, size_t need) { if (buf.n < need) { HG_CUDA(cudaStreamSynchronize(st)); buf.alloc(need); } };
+        grow(wg_s_, n); grow(wg_e_, n); grow(wg_k1_, n); grow(wg_a_, K * n); grow(wg_hat_, K * 2 * n); grow(wg_st_, 1);
+        HG_CUDA(cudaMemcpyAsync(wg_s_.p, s, n, cudaMemcpyHostToDevice, st));
+        HG_CUDA(cudaMemcpyAsync(wg_e_.p, e, n, cudaMemcpyHostToDevice, st));
+        HG_CUDA(cudaMemcpyAsync(wg_k1_.p, k1, n * sizeof(int), cudaMemcpyHostToDevice, st));
+        HG_CUDA(cudaMemcpyAsync(wg_a_.p, a, K * n * sizeof(long long), cudaMemcpyHostToDevice, st));
+        HG_CUDA(cudaMemsetAsync(wg_st_.p, 0, sizeof(WitGenStatus), st));
+        const size_t N2 = 2 * n;
+        HG_K(dev, KC_MISC, K * n * 8 + K * N2 * 16, k_wit_conv<<<dim3((unsigned)((N2 + HG_WIT_KT - 1) / HG_WIT_KT), (unsigned)K), HG_WIT_KT, 0, st>>>(wg_s_.p, wg_a_.p, (int)n, wg_hat_.p));
+        constexpr int L = FP::B_LIMBS;
+        HG_K(dev, KC_MISC, K * N2 * (16 + 3 * 8 * L),
+             k_wit_finish<L><<<dim3((unsigned)((N2 + 255) / 256), (unsigned)K), 256, 0, st>>>(P, wg_e_.p, wg_k1_.p, wg_a_.p, wg_hat_.p, (u64*)d_ais, (u64*)d_r1is, (u64*)d_r2is,
+                                                                                          (u64*)d_ct0is, wg_st_.p));
+        HG_K(dev, KC_MISC, N2 * 3 * 8 * L, k_wit_small<L><<<(unsigned)((N2 + 255) / 256), 256, 0, st>>>(P, wg_s_.p, wg_e_.p, wg_k1_.p, (u64*)d_s, (u64*)d_e, (u64*)d_k1));
+        if (FP::FIELD_ID == 1) {  // canonical limbs -> Montgomery form
+            auto enc = [&](void* p, size_t cnt) { k_field_encode<FP><<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>((B*)p, cnt, 0); HG_LAUNCH_CHECK(); };
+            enc(d_s, N2); enc(d_e, N2); enc(d_k1, N2); enc(d_ais, K * N2); enc(d_r1is, K * N2); enc(d_r2is, K * n); enc(d_ct0is, K * N2);
+        }
+        WitGenStatus hs;
+        HG_CUDA(cudaMemcpyAsync(&hs, wg_st_.p, sizeof hs, cudaMemcpyDeviceToHost, st));
+        HG_CUDA(cudaStreamSynchronize(st));  // also keeps the caller's host arrays alive long enough
+        if (hs.not_multiple_of_cyclo || hs.not_multiple_of_q || hs.r1_out_of_range || hs.r2_out_of_range)
+            throw std::runtime_error("hg_bfv_witness_generate: assertion of circuit_sk.py failed: " + std::to_string(hs.not_multiple_of_cyclo) + " coefficients not a multiple of x^n+1, " +
+                                     std::to_string(hs.not_multiple_of_q) + " not divisible by q_i, " + std::to_string(hs.r1_out_of_range) + " r1 out of range, " +
+                                     std::to_string(hs.r2_out_of_range) + " r2 out of range");
     }
     void mle_eval_host(const uint64_t* table_limbs, size_t n, size_t num_vars, const uint64_t* point_ext, uint64_t* out_ext) override {
         std::vector<B> t(n);
@@ -536,7 +591,7 @@ struct hg_circuit {
 };
 static void circuit_use_device(hg_circuit* c) {
     if (!c->ctx) throw std::runtime_error("this circuit is a host-only description (hg_circuit_new_host): it has no device, only hg_gkr_verify runs on it");
-    circuit_use_device(c);
+    HG_CUDA(cudaSetDevice(c->ctx->dev.device));
 }
 struct hg_buf {
     void* p = nullptr;
@@ -944,6 +999,16 @@ int hg_gkr_verify(hg_circuit* c, size_t n_output_claims, const size_t* point_len
         WireOptions wo;
         if (options3) { wo.a3_wire = options3[0]; wo.a3_h1 = options3[1]; wo.a5_ascending = options3[2]; }
         c->c->verify(n_output_claims, point_lens, points_ext, values_ext, t->t.get(), wo);
+    })
+}
+int hg_bfv_witness_generate(hg_ctx* ctx, size_t n, size_t K, const uint64_t* qis, const uint64_t* k0is, const uint64_t* r1_bounds, const uint64_t* r2_bounds,
+                            const int8_t* s, const int8_t* e, const int32_t* k1, const int64_t* a, void* d_s, void* d_e, void* d_k1, void* d_ais, void* d_r1is,
+                            void* d_r2is, void* d_ct0is) {
+    HG_TRY({
+        HG_CUDA(cudaSetDevice(ctx->dev.device));
+        if (!qis || !k0is || !r1_bounds || !r2_bounds || !s || !e || !k1 || !a || !d_s || !d_e || !d_k1 || !d_ais || !d_r1is || !d_r2is || !d_ct0is)
+            throw std::runtime_error("hg_bfv_witness_generate: NULL argument");
+        ctx->ops->witness_generate(&ctx->dev, n, K, qis, k0is, r1_bounds, r2_bounds, s, e, k1, a, d_s, d_e, d_k1, d_ais, d_r1is, d_r2is, d_ct0is);
     })
 }
 int hg_mle_eval_host(int field_id, const uint64_t* table_limbs, size_t n, size_t num_vars, const uint64_t* point_ext, uint64_t* out_ext) {

@@ -72,6 +72,43 @@ def _center(x, q):
     return x - q if x > (q - 1) // 2 else x
 
 
+def synth_draws(params: BfvSkEncryptConstants, seed: int):
+    """The random part of the synthetic witness (circuit_sk.py:29-70), lowest degree first: s int8, e int8, k1 int32, a [K][n] int64.
+    Same generator and the same order of draws as synth_witness, so both describe the same witness."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n, K = params.N, params.K
+    s = rng.integers(-1, 2, n)
+    e = np.clip(np.rint(rng.normal(0.0, 3.2, n)), -params.E_BOUND, params.E_BOUND).astype(np.int64)
+    k1 = rng.integers(-params.K1_BOUND, params.K1_BOUND + 1, n)
+    a = np.zeros((K, n), np.int64)
+    for i in range(K):
+        half = (params.QIS[i] - 1) // 2
+        a[i] = rng.integers(-half, half + 1, n, dtype=np.int64)
+    return s.astype(np.int8), e.astype(np.int8), k1.astype(np.int32), a
+
+
+def synth_witness_device(ctx, params: BfvSkEncryptConstants, seed: int):
+    """The synthetic witness of synth_witness(params, seed) computed ON THE DEVICE (hg_bfv_witness_generate, csrc/witness_gen.cuh):
+    returns (device input buffers in get_inputs / input-node order [s, e, k1, ais.., r1is.., r2is], device buffer of ct0is), in the
+    library's representation, ready for Circuit.evaluate and mle_eval_batch."""
+    import ctypes as C
+    from . import api
+    s, e, k1, a = synth_draws(params, seed)
+    n, K = params.N, params.K
+    eb = 8 * api.LIMBS[ctx.field]
+    N2 = 2 * n
+    d_s, d_e, d_k1 = (api.DeviceBuffer(ctx, N2 * eb) for _ in range(3))
+    d_a, d_r1, d_ct = (api.DeviceBuffer(ctx, K * N2 * eb) for _ in range(3))
+    d_r2 = api.DeviceBuffer(ctx, K * n * eb)
+    u = lambda v: np.ascontiguousarray(np.array(v[:K], dtype=np.uint64))
+    qis, k0is, r1b, r2b = u(params.QIS), u(params.K0IS), u(params.R1_BOUNDS), u(params.R2_BOUNDS)
+    vp = lambda x: x.ctypes.data_as(C.c_void_p)
+    api._chk(api.lib().hg_bfv_witness_generate(ctx.h, n, K, vp(qis), vp(k0is), vp(r1b), vp(r2b), vp(s), vp(e), vp(k1), vp(np.ascontiguousarray(a)),
+                                               d_s.ptr, d_e.ptr, d_k1.ptr, d_a.ptr, d_r1.ptr, d_r2.ptr, d_ct.ptr))
+    split = lambda b, cnt, per: [api.DeviceView(b, i * per * eb, per * eb) for i in range(cnt)]
+    return [d_s, d_e, d_k1] + split(d_a, K, N2) + split(d_r1, K, N2) + [d_r2], d_ct
+
+
 def synth_witness(params: BfvSkEncryptConstants, seed: int, p: int = GL_P) -> BfvSkEncryptArgs:
     """Synthetic BFV SK-encryption witness with the reference's distribution (circuit_sk.py:29-140):
     s ternary, e ~ N(0, 3.2^2) clipped to +-E_BOUND, k1 uniform in +-K1_BOUND, a_i uniform in +-(q_i-1)/2."""

@@ -242,6 +242,16 @@ size_t hg_gkr_shard_words(hg_circuit* c);
 int hg_gkr_prove_shard_dev(hg_circuit* c, size_t n_output_claims, const size_t* point_lens, const uint64_t* points_ext, const uint64_t* values_ext, hg_transcript* t,
                            int rank, int world, void* d_out_words, size_t cap_words, size_t* n_words);
 int hg_gkr_emit_shard_dev(hg_circuit* c, const void* d_merged_words, size_t n_words);
+/* ---- synthetic witness on the device: the arithmetic of scripts/circuit_sk.py:72-140 (ct0i_hat = a_i s + e + k0_i k1 over Z, exact;
+ *      centred reduction mod (x^n + 1, q_i); r2i, r1i; the bound assertions), written straight into the BfvEncrypt::get_inputs layout
+ *      (sk_encryption_circuit.rs:365-415). The random draws stay with the caller (HOST arrays, lowest degree first): s in {-1,0,1} and e as
+ *      int8, k1 as int32, a as [K][n] int64 with |a_i| <= (q_i - 1) / 2. Outputs are DEVICE pointers in the library's representation,
+ *      ready for hg_circuit_evaluate (input-node order s, e, k1, ais.., r1is.., r2is) and hg_mle_eval_batch (ct0is):
+ *        d_s, d_e, d_k1: 2n elements;  d_ais, d_r1is, d_ct0is: K x 2n;  d_r2is: K x n.
+ *      A failed assertion of the reference script (not a multiple of x^n + 1, not divisible by q_i, r1 / r2 out of range) is an error. */
+int hg_bfv_witness_generate(hg_ctx* ctx, size_t n, size_t K, const uint64_t* qis, const uint64_t* k0is, const uint64_t* r1_bounds, const uint64_t* r2_bounds,
+                            const int8_t* s, const int8_t* e, const int32_t* k1, const int64_t* a, void* d_s, void* d_e, void* d_k1, void* d_ais, void* d_r1is,
+                            void* d_r2is, void* d_ct0is);
 /* ---- verifier: BfvEncrypt::verify (bfv-gkr/src/sk_encryption_circuit.rs:462-517) on the HOST, no GPU and no context.
  *      hg_circuit_new_host makes a circuit DESCRIPTION: the hg_circuit_insert_input / _fft / _vanilla / _connect calls above build it
  *      exactly as for a device circuit, the Lasso node is described by its preprocessing and num_vars (hg_circuit_insert_lasso_host);

@@ -824,3 +824,58 @@ def test_full_gkr_prove_sharded_full_size(api, ctx, golden_dir):
 
     _emulate_ranks_dev(api, ctx, 4, prover.circuit.shard_words, shard, prover.circuit.emit_shard_dev)
     _assert_hash(tr.into_proof(), meta, "sharded BfvEncrypt::prove n=32768, 4 ranks")
+
+
+# ------------------------------------------------------------------------------------------------ witness generator on the device
+@pytest.mark.parametrize("name,seed", [("1024_1x27_65537", 1), ("4096_2x55_65537", 2), ("8192_4x55_65537", 3)])
+def test_device_witness_generator_equals_numpy_restatement(api, ctx, name, seed):
+    """hg_bfv_witness_generate (scripts/circuit_sk.py:72-140 on the device: exact a_i s over Z, centred reductions, r2i, r1i, bound
+    asserts, get_inputs layout) == hyper-greco_b200/witness.py on the same random draws, element for element."""
+    from hyper_greco_b200 import params, witness
+    P = params.PARAMS[name]
+    ins, ct0is = witness.get_inputs(P, witness.synth_witness(P, seed))
+    want = [ins["s"], ins["e"], ins["k1"]] + list(ins["ais"]) + list(ins["r1is"]) + [ins["r2is"]]
+    dev, d_ct = witness.synth_witness_device(ctx, P, seed)
+    assert len(dev) == len(want)
+    for k, (b, w) in enumerate(zip(dev, want)):
+        got = b.download(np.uint64, len(w))
+        assert (got == np.array(w, dtype=np.uint64)).all(), k
+    assert (d_ct.download(np.uint64, len(ct0is)) == np.array(ct0is, dtype=np.uint64)).all()
+
+
+def test_device_witness_generator_full_size_and_bn254(api, ctx, ctx_bn):
+    """n=32768, k=16: the generated witness satisfies the circuit (the `sum` layer of circuit.evaluate equals ct0is,
+    sk_encryption_circuit.rs:280-285) and its proof verifies with the product's host verifier; BN254 output equals the numpy
+    restatement at n=1024; a witness that violates a bound is refused."""
+    from hyper_greco_b200 import params, witness
+    P = params.by_n(32768)
+    dev, d_ct = witness.synth_witness_device(ctx, P, 7)
+    prover = api.BfvSkEncryptProver(ctx, P)
+    prover.circuit.evaluate(dev)
+    ptr, n = prover.circuit.node_value(prover.ids["sum"])
+
+    class NodeValue:  # library-owned device memory, wrapped for mle_eval_batch
+        pass
+    nvw = NodeValue()
+    nvw.ptr = ptr
+    L = prover.ct0is_log2_size
+    assert n == 1 << L
+    pt = api.Keccak256Transcript().squeeze_challenges(L)
+    assert (api.mle_eval_batch(ctx, nvw, 1, L, pt)[0] == api.mle_eval_batch(ctx, d_ct, 1, L, pt)[0]).all()   # sum layer == ct0is (Schwartz-Zippel)
+    proof, _ = prover.prove(dev, d_ct, 0)
+    ins, ct0is = witness.get_inputs(P, witness.synth_witness(P, 7))
+    flat = [np.array(v, dtype=np.uint64) for v in [ins["s"], ins["e"], ins["k1"]] + list(ins["ais"]) + list(ins["r1is"]) + [ins["r2is"]]]
+    api.BfvSkEncryptVerifier(P).verify(flat, np.array(ct0is, dtype=np.uint64), proof)
+    # BN254: canonical limbs after decoding == numpy restatement mod r
+    Pn = params.PARAMS["1024_1x27_65537"]
+    insb, ctb = witness.get_inputs(Pn, witness.synth_witness(Pn, 4, p=witness.BN_R))
+    devb, d_ctb = witness.synth_witness_device(ctx_bn, Pn, 4)
+    wantb = [insb["s"], insb["e"], insb["k1"]] + list(insb["ais"]) + list(insb["r1is"]) + [insb["r2is"]]
+    for b, w in zip(devb, wantb):
+        assert (b.to_field(len(w)) == _bn_limbs(w)).all()
+    assert (d_ctb.to_field(len(ctb)) == _bn_limbs(ctb)).all()
+    # a bound that the witness violates (r1 bound 0) is an error, as the reference script's assert
+    import dataclasses
+    bad = dataclasses.replace(Pn, R1_BOUNDS=(0,))
+    with pytest.raises(api.HgError):
+        witness.synth_witness_device(ctx, bad, 4)
