@@ -30,7 +30,7 @@ METRIC = "gkr_prove_proofs_per_sec"
 UNIT = "proofs/s"
 DEFAULT_CONFIG = "32768_16x59_65537"
 NOMINAL_HBM_GBS = 8000.0   # the ~8 TB/s the north star quotes; the measured copy bandwidth is in MEASURED_PEAKS.json
-WITNESS_POOL = 4           # distinct synthetic witnesses per rank
+WITNESS_POOL = 8           # distinct synthetic witnesses per rank (generated on the device, hg_bfv_witness_generate)
 
 
 def bench_config(args, P, nv, m):
@@ -45,8 +45,8 @@ def bench_config(args, P, nv, m):
         "field": args.field,
         "parallelism": "independent proof instances: `proofs_in_flight_per_gpu` per GPU (one host thread + one context each), no data-path collective",
         "proofs_in_flight_per_gpu": max(1, args.inflight),
-        "witness": f"{WITNESS_POOL} synthetic witnesses per rank (seeds {WITNESS_POOL}*rank ..): slot k proves witness k in the resident region, "
-                   "every slot cycles through all of them in the end-to-end region",
+        "witness": f"{WITNESS_POOL} synthetic witnesses per rank (seeds {WITNESS_POOL}*rank ..), generated on the device (hg_bfv_witness_generate) and kept in pinned "
+                   "host memory: slot k proves witness k in the resident region, every slot cycles through all of them in the end-to-end region",
         "cache": "working set ~4 GB per proof >> 126 MB L2, no explicit flush between steps",
     }
 
@@ -159,9 +159,13 @@ def run_reference(args):
     nv = witness.lasso_num_vars(P)
     hgo.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
     cores = hgo.num_threads()
-    prep = hgo.bfv_prepare(fid, P, ins, ct0is)
+    if fid == 0:
+        prep = hgo.bfv_prepare(fid, P, ins, ct0is)
+        one = lambda: hgo.bfv_prove_prepared(prep)
+    else:   # the prepared-session API of the oracle is Goldilocks only: BfvEncrypt::prove as a whole (circuit.evaluate included, ~3 % of it)
+        one = lambda: hgo.bfv_prove(fid, P, ins, ct0is, cap=1 << 26)
     t0 = time.perf_counter()
-    hgo.bfv_prove_prepared(prep)
+    one()
     t1 = time.perf_counter() - t0
     budget = 270.0
     want_w = max(args.warmup, 1)
@@ -170,10 +174,10 @@ def run_reference(args):
         warm = 1
         steps = max(1, min(args.steps, int(budget / max(t1, 1e-3)) - 1))
     for _ in range(warm - 1):
-        hgo.bfv_prove_prepared(prep)
+        one()
     t0 = time.perf_counter()
     for _ in range(steps):
-        hgo.bfv_prove_prepared(prep)
+        one()
     dt = time.perf_counter() - t0
     v = steps / dt
     capped = steps < args.steps or warm < want_w
@@ -364,8 +368,24 @@ def run_ours(args):
 
     B = max(1, args.inflight)
     pool_n = max(1, min(WITNESS_POOL, args.pool))
-    raw = [make_witness(args.config, WITNESS_POOL * rank + k, args.field) for k in range(pool_n)]
-    pool = [HostWitness(np, torch, *host_vectors(ins, ct, args.field)) for ins, ct in raw]
+    # the witness pool: generated on the device (scripts/circuit_sk.py:72-140 as kernels), downloaded once into pinned host memory
+    # (the end-to-end region starts from HOST vectors, as BfvEncrypt::prove does). Same seeds -> same witnesses as make_witness.
+    pool = []
+    gen_ctx = api.Context(local, fid)
+    t_gen = time.perf_counter()
+    gen_dev_s = 0.0
+    for k in range(pool_n):
+        t_g = time.perf_counter()
+        dev, d_ct = witness.synth_witness_device(gen_ctx, P, WITNESS_POOL * rank + k)
+        gen_dev_s += time.perf_counter() - t_g
+        lens = [2 * P.N] * (3 + 2 * P.K) + [P.K * P.N]
+        host = [b.to_field(n).reshape(-1) for b, n in zip(dev, lens)]
+        pool.append(HostWitness(np, torch, host, d_ct.to_field(P.K * 2 * P.N).reshape(-1)))
+        for b in dev[:3] + [dev[3].base, dev[3 + P.K].base, dev[-1], d_ct]:
+            b.free()
+    witness_gen_ms = {"generate_on_device_ms": 1000.0 * gen_dev_s / pool_n, "with_download_to_pinned_host_ms": 1000.0 * (time.perf_counter() - t_gen) / pool_n,
+                      "note": "per witness; numpy draws + hg_bfv_witness_generate (synchronous), then the copy into the host pool of the end-to-end region"}
+    gen_ctx.close()
     n_in_bytes = pool[0].bytes
     slots = [ProofSlot(api, np, P, pool, k, local, fid) for k in range(B)]
     s0 = slots[0]
@@ -504,10 +524,14 @@ def run_ours(args):
             from oracle import hgo
             hgo.build()
             hgo.set_num_threads(os.cpu_count() or 1)
-            ins0, ct0 = raw[0]
-            sess = hgo.bfv_prepare(fid, P, ins0, ct0)
-            t0 = time.perf_counter()
-            oproof = sess.prove()
+            ins0, ct0 = make_witness(args.config, WITNESS_POOL * rank, args.field)   # numpy restatement of the same witness (seed 0)
+            if fid == 0:
+                sess = hgo.bfv_prepare(fid, P, ins0, ct0)
+                t0 = time.perf_counter()
+                oproof = sess.prove()
+            else:   # BN254: the oracle's one-shot BfvEncrypt::prove (circuit.evaluate included)
+                t0 = time.perf_counter()
+                oproof = hgo.bfv_prove(fid, P, ins0, ct0, cap=1 << 26)
             dt = time.perf_counter() - t0
             same = oproof == s0.e2e(0)
             cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": hgo.num_threads(), "kind": "port",
@@ -527,7 +551,7 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * (n_in_bytes + node_ch + 4096)),
                         "d2h_bytes_per_step": int(B * proof_len * 2), "single_proof_latency_ms": e2e_latency_ms},
                 "gpu_launches": int(launches_per_proof * args.steps * B), "gpu_launches_per_proof": int(launches_per_proof),
-                "single_proof_latency_ms": latency_ms, "wall_ms_per_step": wall_ms / args.steps, "proof_bytes": proof_len, "spin_up_steps": spin_up,
+                "single_proof_latency_ms": latency_ms, "wall_ms_per_step": wall_ms / args.steps, "proof_bytes": proof_len, "spin_up_steps": spin_up, "witness_gen_ms_per_witness": witness_gen_ms,
                 "host_phases_us": host_phases, "roofline": roofline, "cpu_baseline": cpu, "shard": shard}
     barrier()
     for s in slots:

@@ -387,8 +387,9 @@ template <class FP> class GkrCircuitDev {
             use_tail_ = true;
             struct TailOff { bool* f; ~TailOff() { *f = false; } } tail_off{&use_tail_};
             int maxv = 0;
-            for (auto& j : mine) maxv = std::max(maxv, std::min(j.nv, tail_start(j)));
+            for (auto& j : mine) maxv = std::max(maxv, std::min(j.nv, stream_end(j)));
             for (int r = 0; r < maxv; r++) launch_round(ch, mine, r);
+            launch_mid(ch, mine);
             launch_tail(ch, mine);
             launch_finals(ch, mine);
         }
@@ -409,7 +410,7 @@ template <class FP> class GkrCircuitDev {
         const B* value_ptr = nullptr;
         LassoNodeDev<FP>* lasso = nullptr;
         // per-node work buffers of the layer sumcheck
-        DevBuf<X> W, A, wbuf0, wbuf1, tbuf0, tbuf1, capture;
+        DevBuf<X> W, A, wbuf0, wbuf1, tbuf0, tbuf1, capture, midpart;
         DevBuf<B> Xcat;
     };
     struct Job {
@@ -649,9 +650,9 @@ template <class FP> class GkrCircuitDev {
         int blk = 0;
         size_t part_off = 0, bytes = 0;
         size_t round_pairs = 0;  // small rounds get one pair per thread (more CTAs), large ones up to 16 (fewer block-level reductions)
-        for (const Job& j : jobs) if (r < j.nv && r < tail_start(j)) round_pairs += r == 0 ? j.S / 2 : (j.S >> (r - 1)) / 4;
+        for (const Job& j : jobs) if (r < j.nv && r < stream_end(j)) round_pairs += r == 0 ? j.S / 2 : (j.S >> (r - 1)) / 4;
         for (const Job& j : jobs) {
-            if (r >= j.nv || r >= tail_start(j)) continue;
+            if (r >= j.nv || r >= stream_end(j)) continue;
             Node& n = *nodes_[j.node];
             ProdItem<FP> it;
             it.nt = j.nt;
@@ -695,7 +696,7 @@ template <class FP> class GkrCircuitDev {
             Node& n = *nodes_[j.node];
             if (!(n.kind == GKR_VANILLA && n.is_linear)) continue;
             const int m = log2sz(n.n_in);
-            if (m != r || m >= j.nv || r == 0 || m >= tail_start(j)) continue;
+            if (m != r || m >= j.nv || r == 0 || m >= stream_end(j)) continue;
             CopyItem<FP> c; c.src = (m & 1) ? n.tbuf0.p : n.tbuf1.p; c.dst = n.capture.p; c.n = n.arity;
             copies.push_back(c);
         }
@@ -703,7 +704,49 @@ template <class FP> class GkrCircuitDev {
     }
 
     // first round that is NOT streamed: the tail kernel takes over there (prefetch mode only; nv when the job has no tail)
-    int tail_start(const Job& j) const { return (use_tail_ && j.nv >= 3) ? std::max(2, j.nv - HG_PROD_TAIL_LOG) : j.nv; }
+    // Round schedule of a job in prefetch mode (use_tail_): rounds [0, stream_end) are streamed, one launch per round for all jobs;
+    // sumchecks with nv >= 12 then run HG_PROD_MID_K rounds in ONE launch on 1024-entry segments in shared memory (k_prod_mid),
+    // and the rest (tables of <= 2^10 entries) in the one-CTA-per-job tail kernel. Without use_tail_ every round is streamed.
+    static constexpr int HG_PROD_MID_LOG = 15;  // the mid stage starts when the tables are down to 2^(HG_PROD_MID_LOG+1) entries
+    bool has_mid(const Job& j) const { return use_tail_ && use_mid_ && j.nv >= 12; }
+    int stream_end(const Job& j) const {
+        if (!use_tail_ || j.nv < 3) return j.nv;
+        return has_mid(j) ? std::max(2, j.nv - HG_PROD_MID_LOG) : std::max(2, j.nv - HG_PROD_TAIL_LOG);
+    }
+    int tail_start(const Job& j) const { return stream_end(j) + (has_mid(j) ? HG_PROD_MID_K : 0); }
+    // mid stage of every job that has one: input = output of streaming round stream_end - 1, K rounds, output 2 entries per segment
+    void launch_mid(Channel<FP>& ch, const std::vector<Job>& jobs) {
+        cudaStream_t s = ctx_->stream;
+        std::vector<ProdMidItem<FP>> items;
+        int blk = 0, nt_max = 1;
+        size_t bytes = 0;
+        for (const Job& j : jobs) {
+            if (!has_mid(j)) continue;
+            Node& n = *nodes_[j.node];
+            const int se = stream_end(j);
+            ProdMidItem<FP> it;
+            it.n_in = j.S >> (se - 1);
+            if (it.n_in < 2 * (size_t)HG_PROD_MID_SEG || (it.n_in % HG_PROD_MID_SEG)) throw std::runtime_error("gkr: mid stage on a table that is too small");
+            it.nt = j.nt; it.nseg = (int)(it.n_in / HG_PROD_MID_SEG); it.blk_start = blk;
+            it.w_in = ((se - 1) & 1) ? n.wbuf0.p : n.wbuf1.p;  it.tab_in = ((se - 1) & 1) ? n.tbuf0.p : n.tbuf1.p;
+            it.w_out = (se & 1) ? n.wbuf0.p : n.wbuf1.p;       it.tab_out = (se & 1) ? n.tbuf0.p : n.tbuf1.p;
+            it.chal = ch.d_chal(j.r0_idx + se - 1);
+            if (n.midpart.n < (size_t)HG_PROD_MID_K * it.nseg * 4) { HG_CUDA(cudaStreamSynchronize(s)); n.midpart.alloc((size_t)HG_PROD_MID_K * it.nseg * 4); }
+            it.part = n.midpart.p;
+            it.capture = nullptr; it.cap_round = -1; it.arity = n.arity;
+            if (n.kind == GKR_VANILLA && n.is_linear) {
+                const int m = log2sz(n.n_in);
+                if (m >= se && m < se + HG_PROD_MID_K) { it.capture = n.capture.p; it.cap_round = m - se; }
+            }
+            blk += it.nseg;
+            nt_max = std::max(nt_max, j.nt);
+            bytes += (size_t)(j.nt + 1) * it.n_in * sizeof(X);
+            items.push_back(it);
+        }
+        if (items.empty()) return;
+        prod_mid_set_smem<FP>();
+        HG_K(ctx_, KC_GKR_SC, bytes, k_prod_mid<FP><<<blk, 256, prod_mid_smem<FP>(nt_max), s>>>(stage(items), (int)items.size()));
+    }
     // rounds tail_start .. nv-1 and the input evaluations of every job that has a tail, one CTA per job
     void launch_tail(Channel<FP>& ch, const std::vector<Job>& jobs) {
         cudaStream_t s = ctx_->stream;
@@ -717,6 +760,14 @@ template <class FP> class GkrCircuitDev {
             t.n_in = (int)(j.S >> (rt - 1)); t.nt = j.nt; t.rounds = j.nv - rt;
             t.w_in = ((rt - 1) & 1) ? n.wbuf0.p : n.wbuf1.p;
             t.tab_in = ((rt - 1) & 1) ? n.tbuf0.p : n.tbuf1.p;
+            t.mid_part = nullptr; t.mid_msg = nullptr; t.mid_nseg = 0; t.mid_rounds = 0;
+            if (has_mid(j)) {  // the mid stage wrote its pairs where streaming round stream_end would have written
+                const int se = stream_end(j);
+                t.w_in = (se & 1) ? n.wbuf0.p : n.wbuf1.p;
+                t.tab_in = (se & 1) ? n.tbuf0.p : n.tbuf1.p;
+                t.mid_part = n.midpart.p; t.mid_nseg = (int)((j.S >> (se - 1)) / HG_PROD_MID_SEG); t.mid_rounds = HG_PROD_MID_K;
+                t.mid_msg = ch.d_msg(j.msg_off + 4 * (size_t)se);
+            }
             t.chal = ch.d_chal(j.r0_idx + rt - 1);
             t.msg = ch.d_msg(j.msg_off + 4 * (size_t)rt);
             t.evals = ch.d_msg(j.evals_off);
@@ -776,6 +827,10 @@ template <class FP> class GkrCircuitDev {
     std::vector<std::unique_ptr<Node>> nodes_;
     std::vector<int> topo_;
     bool evaluated_ = false, planned_ = false, eval_planned_ = false, use_tail_ = false;
+    // measured on B200 (n = 32768): for the ~70 node sumchecks the mid stage is SLOWER than the streamed rounds it replaces (0.86 vs 0.76 ms
+    // for the class: ~2000 CTAs that each run 9 serial rounds), so it is off here; the Lasso collation sumcheck (one job, 18 us per
+    // streamed round whatever the size) uses it (sumcheck_dev: 0.24 -> 0.19 ms, 13 -> 5 launches)
+    bool use_mid_ = getenv("HG_PROD_MID_LAYERS") ? atoi(getenv("HG_PROD_MID_LAYERS")) != 0 : false;
     size_t tail_smem_ = 0;
     std::vector<EvalLevel> eval_levels_;
     size_t total_chal_ = 0, desc_off_ = 0, eq_off_ = 0;

@@ -259,6 +259,9 @@ template <class FP> struct ProdTailItem {
     typename FP::X* evals;
     const typename FP::X* capture;                               // linear layers whose capture round ran in the streaming part, else nullptr
     int n_in, nt, rounds, linear, arity, cap_round;              // cap_round: index (0-based within the tail) of the round whose folded table holds the input evaluations, -1: none
+    const typename FP::X* mid_part;                              // rounds done by k_prod_mid before this tail: CTA partial sums [mid_rounds][mid_nseg][4] ...
+    typename FP::X* mid_msg;                                     // ... summed into the 4 message slots of each of those rounds (nullptr: no mid stage)
+    int mid_nseg, mid_rounds;
 };
 template <class FP> __device__ __forceinline__ void prod_tail_body(const ProdTailItem<FP>& it, unsigned char* smem_raw) {
     typedef typename FP::X X;
@@ -269,6 +272,13 @@ template <class FP> __device__ __forceinline__ void prod_tail_body(const ProdTai
     X* red = nxt + (size_t)ntab * (it.n_in / 2);        // [32][3]
     for (int e = threadIdx.x; e < len; e += blockDim.x) cur[e] = it.w_in[e];
     for (int e = threadIdx.x; e < nt * len; e += blockDim.x) cur[len + e] = it.tab_in[e];
+    if (it.mid_msg)  // the messages of the rounds k_prod_mid ran: add up its CTA partials (field addition is exact: any order)
+        for (int t = threadIdx.x; t < 4 * it.mid_rounds; t += blockDim.x) {
+            const int rd = t >> 2, p = t & 3;
+            X s = FP::x_zero();
+            if (p < 3) for (int g = 0; g < it.mid_nseg; g++) s = FP::x_add(s, it.mid_part[((size_t)rd * it.mid_nseg + g) * 4 + p]);
+            it.mid_msg[t] = s;
+        }
     __syncthreads();
     for (int rd = 0; rd < it.rounds; rd++) {
         const X r = it.chal[rd];
@@ -309,6 +319,95 @@ template <class FP> __device__ __forceinline__ void prod_tail_body(const ProdTai
         for (int q = threadIdx.x; q < nt; q += blockDim.x) it.evals[q] = FP::fold(cur[(size_t)(q + 1) * len], cur[(size_t)(q + 1) * len + 1], r, aux);
     }
 }
+// ---- the MIDDLE rounds of a product sumcheck in one launch: a CTA owns a segment of 2^(K+1) consecutive entries of every table
+// (folding is local in the index: entries 2b, 2b+1 -> b), keeps it in shared memory, runs K rounds on it (fold by the previous
+// challenge + sample, exactly the tail's loop) and leaves 2 entries per table and segment, plus its partial sums of the K round
+// messages; the tail kernel of the job adds the partials up. Replaces K launches whose data fits the L2 anyway and whose time
+// is launch latency (profiles/: ~11-18 us each) by one.
+constexpr int HG_PROD_MID_K = 9;                        // rounds per launch; segment = 1024 entries
+constexpr int HG_PROD_MID_SEG = 1 << (HG_PROD_MID_K + 1);
+template <class FP> struct ProdMidItem {
+    const typename FP::X* w_in; const typename FP::X* tab_in;   // n_in entries each (nt tables back to back), n_in = nseg * HG_PROD_MID_SEG
+    typename FP::X* w_out; typename FP::X* tab_out;              // 2 * nseg entries each
+    const typename FP::X* chal;                                  // chal[j]: challenge folded in round j of this stage
+    typename FP::X* part;                                        // [K][nseg][4]
+    typename FP::X* capture;                                     // linear layers whose capture round falls into this stage (else nullptr)
+    unsigned long long n_in;
+    int nt, nseg, blk_start, cap_round, arity;
+};
+template <class FP> __device__ __forceinline__ void prod_mid_body(const ProdMidItem<FP>& it, const int seg, unsigned char* smem_raw) {
+    typedef typename FP::X X;
+    constexpr int K = HG_PROD_MID_K, S = HG_PROD_MID_SEG;
+    const int nt = it.nt, ntab = nt + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    X* cur = reinterpret_cast<X*>(smem_raw);            // [ntab][S]: table 0 = weights
+    X* nxt = cur + (size_t)ntab * S;                    // [ntab][S/2]
+    X* wred = nxt + (size_t)ntab * (S / 2);             // [K][nwarps][3]
+    for (int e = threadIdx.x; e < S; e += blockDim.x) cur[e] = it.w_in[(size_t)seg * S + e];
+    for (int q = 0; q < nt; q++)
+        for (int e = threadIdx.x; e < S; e += blockDim.x) cur[(q + 1) * S + e] = it.tab_in[(size_t)q * it.n_in + (size_t)seg * S + e];
+    __syncthreads();
+    int len = S;
+    for (int rd = 0; rd < K; rd++) {
+        const X r = it.chal[rd];
+        const typename FP::FoldAux aux = FP::fold_aux(r);
+        const int npairs = len / 4, half = len / 2;
+        X acc[3] = {FP::x_zero(), FP::x_zero(), FP::x_zero()};
+        for (int b = threadIdx.x; b < npairs; b += blockDim.x) {
+            X lo[3], hi[3];
+            for (int q = 0; q < ntab; q++) {
+                const X* s = cur + (size_t)q * len + 4 * b;
+                lo[q] = FP::fold(s[0], s[1], r, aux); hi[q] = FP::fold(s[2], s[3], r, aux);
+                nxt[(size_t)q * half + 2 * b] = lo[q]; nxt[(size_t)q * half + 2 * b + 1] = hi[q];
+            }
+            if (nt == 1) {
+                acc[0] = FP::x_add(acc[0], FP::fmul(lo[0], lo[1]));
+                acc[1] = FP::x_add(acc[1], FP::fmul(FP::slope(lo[0], hi[0]), FP::slope(lo[1], hi[1])));
+            } else {
+                acc[0] = FP::x_add(acc[0], FP::fmul(lo[0], FP::fmul(lo[1], lo[2])));
+                acc[1] = FP::x_add(acc[1], FP::fmul(FP::slope(lo[0], hi[0]), FP::fmul(FP::slope(lo[1], hi[1]), FP::slope(lo[2], hi[2]))));
+                acc[2] = FP::x_add(acc[2], FP::fmul(FP::at_m1(lo[0], hi[0]), FP::fmul(FP::at_m1(lo[1], hi[1]), FP::at_m1(lo[2], hi[2]))));
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < 3; p++) {  // per-warp sums only: the cross-warp and cross-CTA sums happen once, at the end / in the tail
+            X v = acc[p];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v = FP::x_add(v, FP::x_shfl_down(v, off));
+            if (lane == 0) wred[((size_t)rd * nwarps + warp) * 3 + p] = v;
+        }
+        __syncthreads();  // nxt is complete
+        if (rd == it.cap_round && it.capture)  // linear layer: the table folded over the low variables holds the evaluations of the inputs
+            for (int kk = threadIdx.x; kk < half; kk += blockDim.x) { const size_t g = (size_t)seg * half + kk; if (g < (size_t)it.arity) it.capture[g] = nxt[half + kk]; }
+        X* t = cur; cur = nxt; nxt = t;
+        len = half;
+    }
+    // len == 2: the segment's pair of every table
+    const size_t n_out = it.n_in >> K;
+    for (int e = threadIdx.x; e < 2 * ntab; e += blockDim.x) {
+        const int q = e >> 1, k = e & 1;
+        X* dst = q == 0 ? it.w_out : it.tab_out + (size_t)(q - 1) * n_out;
+        dst[2 * (size_t)seg + k] = cur[(size_t)q * 2 + k];
+    }
+    for (int t = threadIdx.x; t < 4 * K; t += blockDim.x) {
+        const int rd = t >> 2, p = t & 3;
+        X s = FP::x_zero();
+        if (p < 3) for (int w = 0; w < nwarps; w++) s = FP::x_add(s, wred[((size_t)rd * nwarps + w) * 3 + p]);
+        it.part[((size_t)rd * it.nseg + seg) * 4 + p] = s;
+    }
+}
+
+template <class FP> __global__ void __launch_bounds__(256) k_prod_mid(const ProdMidItem<FP>* __restrict__ items, int nitems) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const ProdMidItem<FP> it = items[find_item(items, nitems)];
+    prod_mid_body<FP>(it, blockIdx.x - it.blk_start, smem_raw);
+}
+// a single sumcheck (the Lasso collation sumcheck): descriptor by value
+template <class FP> __global__ void __launch_bounds__(256) k_prod_mid_one(const ProdMidItem<FP> it) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    prod_mid_body<FP>(it, blockIdx.x, smem_raw);
+}
+
 template <class FP> __global__ void __launch_bounds__(256) k_prod_tail(const ProdTailItem<FP>* __restrict__ items) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     prod_tail_body<FP>(items[blockIdx.x], smem_raw);

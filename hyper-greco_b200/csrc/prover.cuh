@@ -354,7 +354,19 @@ struct ScScratch {
     void* partials = nullptr;  // X [max_blocks * max_batch * 4]
     unsigned* counters = nullptr;
     int max_blocks = 0;
+    void* midpart = nullptr;   // X [HG_PROD_MID_K][midpart_segs][4]: CTA partial sums of the mid stage (k_prod_mid); nullptr: no mid stage
+    size_t midpart_segs = 0;
 };
+// shared memory of k_prod_mid for up to two input tables next to the weights (set once, for the largest user)
+template <class FP> inline size_t prod_mid_smem(int nt) { return ((size_t)(nt + 1) * (HG_PROD_MID_SEG + HG_PROD_MID_SEG / 2) + (size_t)HG_PROD_MID_K * 8 * 3) * sizeof(typename FP::X); }
+template <class FP> inline void prod_mid_set_smem() {
+    static bool done = false;  // (per device in a multi-device process: the attribute is per function and device; one device per process here)
+    if (!done) {
+        HG_CUDA(cudaFuncSetAttribute(k_prod_mid<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prod_mid_smem<FP>(2)));
+        HG_CUDA(cudaFuncSetAttribute(k_prod_mid_one<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prod_mid_smem<FP>(2)));
+        done = true;
+    }
+}
 
 // serialisation of one round message + claim bookkeeping (runs on the host when the message has been downloaded).
 // The device sends samples of the TRUE round polynomial h: h(0), h(inf), [h(-1)], and h(1) in round 0. With the running
@@ -474,14 +486,20 @@ void sumcheck_dev(DeviceCtx* ctx, int kclass, Channel<FP>& ch, const WireOptions
     // g = t_0 * t_1 (the collation sumcheck: coefficients {0, 1}) with all challenges known: the last rounds run in one
     // shared-memory launch (k_prod_tail_one), the streamed rounds stop at jt
     const bool tail = product_of_two && ARITY == 1 && nterm == 2 && ch.prefetching() && nv >= 3;
-    const int jt = tail ? std::max(2, nv - HG_PROD_TAIL_LOG) : nv;
+    // with nv >= 12 the HG_PROD_MID_K rounds before the tail run in ONE launch on 1024-entry segments (k_prod_mid): streamed rounds
+    // [0, js), mid rounds [js, jt), tail rounds [jt, nv)
+    static const bool env_mid = getenv("HG_PROD_MID") ? atoi(getenv("HG_PROD_MID")) != 0 : true;
+    const bool mid = tail && env_mid && nv >= 12 && sc.midpart != nullptr;
+    const int js = !tail ? nv : (mid ? std::max(2, nv - 2 * HG_PROD_MID_K) : std::max(2, nv - HG_PROD_TAIL_LOG));
+    const int jt = !tail ? nv : (mid ? js + HG_PROD_MID_K : js);
     const void* cur_in = d_tables;
     bool in_base = true;
     size_t n_in = n;
-    size_t prev_chal = 0, tail_msg = 0, tail_chal = 0;
+    size_t prev_chal = 0, tail_msg = 0, tail_chal = 0, mid_msg = 0, mid_chal = 0;
     for (int j = 0; j < nv; j++) {
-        const bool streamed = j < jt;
-        size_t off = ch.alloc_msg(streamed ? (j == 0 ? D + 1 : D) : 4);  // the tail kernel writes 4 slots per round: [h(0), h(inf), -, 0]
+        const bool streamed = j < js;
+        size_t off = ch.alloc_msg(streamed ? (j == 0 ? D + 1 : D) : 4);  // the mid / tail kernels write 4 slots per round: [h(0), h(inf), -, 0]
+        if (j == js) { mid_msg = off; mid_chal = prev_chal; }
         if (j == jt) { tail_msg = off; tail_chal = prev_chal; }
         if (streamed) {
             X* out = j == 0 ? nullptr : ((j & 1) ? bufA : bufB);
@@ -511,6 +529,25 @@ void sumcheck_dev(DeviceCtx* ctx, int kclass, Channel<FP>& ch, const WireOptions
     if (!launch) return;
     if (tail) {
         ProdTailItem<FP> t;
+        t.mid_part = nullptr; t.mid_msg = nullptr; t.mid_nseg = 0; t.mid_rounds = 0;
+        if (mid) {
+            ProdMidItem<FP> mi;
+            mi.n_in = n_in; mi.nt = 1; mi.nseg = (int)(n_in / HG_PROD_MID_SEG); mi.blk_start = 0;
+            if (n_in < 2 * (size_t)HG_PROD_MID_SEG || (size_t)mi.nseg > sc.midpart_segs) throw std::runtime_error("sumcheck_dev: mid stage does not fit its scratch");
+            X* obuf = (cur_in == (const void*)bufA) ? bufB : bufA;
+            const size_t n_out = n_in >> HG_PROD_MID_K;
+            mi.w_in = (const X*)cur_in; mi.tab_in = (const X*)cur_in + n_in; mi.w_out = obuf; mi.tab_out = obuf + n_out;
+            mi.chal = ch.d_chal(mid_chal); mi.part = (X*)sc.midpart; mi.capture = nullptr; mi.cap_round = -1; mi.arity = 1;
+            prod_mid_set_smem<FP>();
+            {
+                KernelScope ks(ctx, kclass, 2 * n_in * sizeof(X));
+                k_prod_mid_one<FP><<<mi.nseg, 256, prod_mid_smem<FP>(1), ctx->stream>>>(mi);
+                HG_LAUNCH_CHECK();
+            }
+            t.mid_part = (const X*)sc.midpart; t.mid_msg = ch.d_msg(mid_msg); t.mid_nseg = mi.nseg; t.mid_rounds = HG_PROD_MID_K;
+            cur_in = obuf;
+            n_in = n_out;
+        }
         t.w_in = (const X*)cur_in; t.tab_in = (const X*)cur_in + n_in; t.n_in = (int)n_in; t.nt = 1; t.rounds = nv - jt;
         t.chal = ch.d_chal(tail_chal); t.msg = ch.d_msg(tail_msg); t.evals = ch.d_msg(eo) + 1;  // evals[0] (= t_0) is not produced: the caller of the collation sumcheck discards both
         t.capture = nullptr; t.linear = 0; t.arity = 1; t.cap_round = -1;
@@ -751,6 +788,9 @@ template <class FP> class LassoNodeDev {
         d_counters_.alloc(batch + 8);
         HG_CUDA(cudaMemset(d_counters_.p, 0, d_counters_.bytes()));
         sc_.partials = d_partials_.p; sc_.counters = d_counters_.p; sc_.max_blocks = max_blocks_;
+        sc_.midpart_segs = std::max<size_t>(1, R_ / HG_PROD_MID_SEG);
+        d_midpart_.alloc((size_t)HG_PROD_MID_K * sc_.midpart_segs * 4);
+        sc_.midpart = d_midpart_.p;
 
         // challenge / message budget
         size_t v = num_vars_, lm = log2M_;
@@ -1524,7 +1564,7 @@ template <class FP> class LassoNodeDev {
     DevBuf<X> d_eq_, d_gp_coeffs_, d_bufA_, d_bufB_, d_partials_, d_coll_terms_;
     int coll_coeff_state_ = 0;  // 0 not uploaded, 1 ascending, 2 descending
     DevBuf<unsigned> d_counters_, d_gp_counters_;
-    DevBuf<X> d_pool_, d_gp_partials_, d_r0part_;
+    DevBuf<X> d_pool_, d_gp_partials_, d_r0part_, d_midpart_;
     size_t r0_used_ = 0;
     DevBuf<unsigned char> d_desc_, d_cdesc_;
     PinnedBuf<unsigned char> h_desc_, h_cdesc_;
