@@ -207,6 +207,14 @@ void hgo_set_assumption(int which, int value) {
     if (which == 5) assumptions().a5_ascending = value;
 }
 void hgo_keccak256(const uint8_t* in, size_t n, uint8_t* out) { keccak256(in, n, out); }
+// interchange dump: record every base-field squeeze / write of the transcripts used from now on (protocol.hpp EventLog)
+void hgo_events_begin() { event_log().bytes.clear(); event_log().on = true; }
+size_t hgo_events_end(uint8_t* out, size_t cap) {  // stops recording; returns the number of bytes (copied when they fit)
+    event_log().on = false;
+    const size_t n = event_log().bytes.size();
+    if (out && n <= cap) memcpy(out, event_log().bytes.data(), n);
+    return n;
+}
 // base-field challenge chain c_i (transcript.rs:199-203)
 void hgo_challenges(int field, size_t n, uint64_t* out) {
     if (field == 0) { Transcript<Gl> t; for (size_t i = 0; i < n; i++) t.squeeze_base().to_limbs(out + i); }

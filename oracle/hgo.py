@@ -90,6 +90,23 @@ def set_assumption(which, value):
     lib().hgo_set_assumption(which, value)
 
 
+def events_begin():
+    """Interchange dump: start recording every base-field squeeze ('S') / write ('W') of the oracle's transcripts."""
+    lib().hgo_events_begin()
+
+
+def events_end() -> bytes:
+    """Stop recording; returns the event bytes: kind byte + element in proof encoding (big-endian), per event."""
+    lib().hgo_events_end.restype = C.c_size_t
+    lib().hgo_events_end.argtypes = [C.c_void_p, C.c_size_t]
+    cap = 1 << 26
+    buf = np.zeros(cap, np.uint8)
+    n = lib().hgo_events_end(_p(buf), cap)
+    if n > cap:
+        raise OracleError("event log larger than 64 MiB")
+    return buf[:n].tobytes()
+
+
 def set_num_threads(n):
     lib().hgo_set_num_threads(n)
 

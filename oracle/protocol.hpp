@@ -31,8 +31,25 @@ inline Assumptions& assumptions() { static Assumptions a; return a; }
 struct OracleError : std::runtime_error { using std::runtime_error::runtime_error; };
 
 // ---------------------------------------------------------------- transcript (bfv-gkr/src/transcript.rs:117-203)
+// Event recorder for the interchange dump (scripts/hg_dump.py, patches/hyper-greco-dump.diff): when enabled, every base-field
+// squeeze and every base-field write of every Transcript is appended as one kind byte ('S' / 'W') followed by the element in
+// proof encoding (to_repr reversed = big-endian, transcript.rs:183-188). Single-threaded use (the protocol driver is).
+struct EventLog {
+    bool on = false;
+    std::vector<uint8_t> bytes;
+};
+inline EventLog& event_log() { static EventLog e; return e; }
+
 template <class F> struct Transcript {
     typedef typename ExtOf<F>::type E;
+    static void log_event(uint8_t kind, const F& f) {
+        EventLog& e = event_log();
+        if (!e.on) return;
+        uint8_t b[F::REPR_BYTES]; f.to_repr_le(b);
+        std::reverse(b, b + F::REPR_BYTES);
+        e.bytes.push_back(kind);
+        e.bytes.insert(e.bytes.end(), b, b + F::REPR_BYTES);
+    }
     std::vector<uint8_t> pending;  // bytes absorbed into the hasher since the last reset
     std::vector<uint8_t> stream;   // proof bytes (write mode)
     const uint8_t* rd = nullptr; size_t rd_len = 0, rd_pos = 0;  // read mode
@@ -45,7 +62,9 @@ template <class F> struct Transcript {
         keccak256(pending.data(), pending.size(), h);
         pending.assign(h, h + 32);
         n_base_squeezed++;
-        return F::from_le_bytes_mod(h, 32);
+        const F c = F::from_le_bytes_mod(h, 32);
+        log_event('S', c);
+        return c;
     }
     // transcript.rs:149-154
     E squeeze() {
@@ -61,6 +80,7 @@ template <class F> struct Transcript {
         uint8_t b[F::REPR_BYTES]; f.to_repr_le(b);
         std::reverse(b, b + F::REPR_BYTES);
         stream.insert(stream.end(), b, b + F::REPR_BYTES);
+        log_event('W', f);
     }
     void write(const E& e) {
         F b[2]; e.as_bases(b);

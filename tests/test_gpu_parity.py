@@ -879,3 +879,33 @@ def test_device_witness_generator_full_size_and_bn254(api, ctx, ctx_bn):
     bad = dataclasses.replace(Pn, R1_BOUNDS=(0,))
     with pytest.raises(api.HgError):
         witness.synth_witness_device(ctx, bad, 4)
+
+
+def test_product_event_log_equals_interchange_dump(api, ctx, golden_dir):
+    """The order in which the PRODUCT squeezes and writes (interactive schedule, caller-owned transcript) is the order of the committed
+    interchange dump (tests/golden/dumps, scripts/hg_dump.py): same S/W pattern, same challenges, same elements. This is the file a
+    real run of the Rust prover is diffed against (patches/hyper-greco-dump.diff)."""
+    import importlib.util
+    from hyper_greco_b200 import params
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("hg_dump", os.path.join(root, "scripts", "hg_dump.py"))
+    hd = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(hd)
+    name = "1024_1x27_65537"
+    _, events = hd.read_dump(os.path.join(hd.DUMP_DIR, f"bfv_encrypt_goldilocks_{name}_{hd.setting_tag(hd.SETTINGS[0])}.hgdump"))
+    P = params.PARAMS[name]
+    io = np.load(os.path.join(golden_dir, f"circuit_io_{name}.npz"))
+    prover = api.BfvSkEncryptProver(ctx, P)
+    dev = prover.upload_inputs({k: io[k] for k in ("s", "e", "k1", "ais", "r1is", "r2is")})
+    d_ct = api.DeviceBuffer.from_numpy(ctx, io["ct0is"])
+    prover.circuit.evaluate(dev)
+    tr = api.CallbackTranscript(api.Keccak256Transcript())
+    L = prover.ct0is_log2_size
+    point = tr.squeeze_challenges(L)
+    value = api.mle_eval_batch(ctx, d_ct, 1, L, point)[0]
+    prover.circuit.prove_gkr([(np.zeros((0, 2), np.uint64), np.zeros(2, np.uint64)), (point, value)], tr, api.MODE_INTERACTIVE)
+    got = []
+    for kind, limbs in tr.log:            # one extension element = two base-field events of the same kind
+        for b in limbs:
+            got.append(("S" if kind == "squeeze" else "W", int(b).to_bytes(8, "big")))
+    assert got == events

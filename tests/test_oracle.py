@@ -13,6 +13,8 @@ import pytest
 
 from conftest import load_case
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 GL_P = 2**64 - 2**32 + 1
 BN_R = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
 
@@ -303,3 +305,58 @@ def test_oracle_reproduces_committed_golden_proofs(oracle, golden_dir):
     want, _ = _golden_proof(golden_dir, f"proof_goldilocks_bfv_encrypt_{name}.bin")
     assert oracle.bfv_prove(0, P, ins, [int(v) for v in io["ct0is"]]) == want
     oracle.bfv_verify(0, P, ins, [int(v) for v in io["ct0is"]], want)
+
+
+# ------------------------------------------------------------------------------------------------ interchange dumps
+def _dump_tools():
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("hg_dump", os.path.join(ROOT, "scripts", "hg_dump.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_interchange_dumps_are_consistent_with_the_golden_proofs(oracle, golden_dir):
+    """tests/golden/dumps/*.hgdump (ORACLE-GENERATED, one per A3 / A3' / A5 setting): the written elements of the default-setting
+    dump are the committed golden proof, the squeezed elements are the Appendix-E challenge chain, and the oracle reproduces the
+    file today."""
+    import hashlib
+    import os
+    hd = _dump_tools()
+    name = "1024_1x27_65537"
+    default = hd.SETTINGS[0]
+    assert default == dict(A3_wire=0, A3_h1=0, A5_ascending=1)
+    for field, tag in (("goldilocks", "goldilocks"), ("bn254", "bn254")):
+        header, events = hd.read_dump(os.path.join(hd.DUMP_DIR, f"bfv_encrypt_{field}_{name}_{hd.setting_tag(default)}.hgdump"))
+        proof = open(os.path.join(golden_dir, f"proof_{tag}_bfv_encrypt_{name}.bin"), "rb").read()
+        assert hd.proof_of(events) == proof and header["proof_sha256"] == hashlib.sha256(proof).hexdigest()
+        sq = [v for k, v in events if k == "S"]
+        fid = 0 if field == "goldilocks" else 1
+        want = oracle.challenges(fid, len(sq))
+        assert [int.from_bytes(v, "big") for v in sq] == [int(x) for x in want]
+    h, ev = hd.oracle_dump("goldilocks", name, hd.SETTINGS[3])
+    _, committed = hd.read_dump(os.path.join(hd.DUMP_DIR, f"bfv_encrypt_goldilocks_{name}_{hd.setting_tag(hd.SETTINGS[3])}.hgdump"))
+    assert [(ev[i:i + 1].decode(), ev[i + 1:i + 9]) for i in range(0, len(ev), 9)] == committed
+
+
+def test_compare_dump_names_the_matching_setting(golden_dir, tmp_path):
+    """scripts/compare_dump.py: every committed dump is recognised as its own setting; a dump with one flipped written byte matches
+    none and the report points at the element."""
+    import os
+    import subprocess
+    import sys
+    hd = _dump_tools()
+    name = "1024_1x27_65537"
+    tool = os.path.join(ROOT, "scripts", "compare_dump.py")
+    for s in (hd.SETTINGS[0], hd.SETTINGS[1], hd.SETTINGS[5]):
+        path = os.path.join(hd.DUMP_DIR, f"bfv_encrypt_goldilocks_{name}_{hd.setting_tag(s)}.hgdump")
+        r = subprocess.run([sys.executable, tool, path], stdout=subprocess.PIPE, text=True)
+        assert r.returncode == 0 and ("MATCH" in r.stdout) and hd.setting_tag(s) in r.stdout.splitlines()[-1], r.stdout
+    header, events = hd.read_dump(os.path.join(hd.DUMP_DIR, f"bfv_encrypt_goldilocks_{name}_{hd.setting_tag(hd.SETTINGS[0])}.hgdump"))
+    wi = [i for i, (k, _) in enumerate(events) if k == "W"][100]
+    events[wi] = ("W", bytes([events[wi][1][0] ^ 1]) + events[wi][1][1:])
+    bad = tmp_path / "bad.hgdump"
+    hd.write_dump(str(bad), {k: v for k, v in header.items() if k not in ("n_events",)}, b"".join(k.encode() + v for k, v in events))
+    r = subprocess.run([sys.executable, tool, str(bad)], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "NO MATCH" in r.stdout and "#100" in r.stdout, r.stdout
