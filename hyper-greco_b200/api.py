@@ -23,15 +23,15 @@ DEGREE = {GOLDILOCKS: 2, BN254: 1}
 # every symbol include/hg_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "hg_last_error", "hg_version", "hg_ctx_create", "hg_ctx_destroy", "hg_ctx_set_option", "hg_ctx_synchronize", "hg_ctx_launch_count",
-    "hg_ctx_stream", "hg_ctx_profile", "hg_ctx_profile_read", "hg_kernel_class_count", "hg_kernel_class_name", "hg_buf_alloc", "hg_buf_upload", "hg_buf_upload_async", "hg_buf_download", "hg_buf_device_ptr", "hg_buf_size", "hg_buf_free", "hg_field_base_bytes", "hg_field_encode", "hg_field_decode",
+    "hg_ctx_stream", "hg_ctx_profile", "hg_ctx_profile_read", "hg_kernel_class_count", "hg_kernel_class_name", "hg_buf_alloc", "hg_buf_upload", "hg_buf_upload_async", "hg_buf_download", "hg_device_download", "hg_buf_device_ptr", "hg_buf_size", "hg_buf_free", "hg_field_base_bytes", "hg_field_encode", "hg_field_decode",
     "hg_transcript_new", "hg_transcript_from_proof", "hg_transcript_from_callbacks", "hg_transcript_free", "hg_transcript_squeeze_challenge", "hg_transcript_squeeze_challenges", "hg_transcript_write_felt_ext",
     "hg_transcript_read_felt_ext", "hg_transcript_proof_len", "hg_transcript_proof_copy", "hg_transcript_num_squeezed",
-    "hg_lasso_preprocess", "hg_lasso_pp_free", "hg_lasso_pp_num_lookups", "hg_lasso_pp_num_subtables", "hg_lasso_pp_num_memories",
+    "hg_lasso_preprocess", "hg_lasso_preprocess_lookups", "hg_lasso_pp_lookup_index_by_id", "hg_lasso_node_new_ids", "hg_lasso_pp_free", "hg_lasso_pp_num_lookups", "hg_lasso_pp_num_subtables", "hg_lasso_pp_num_memories",
     "hg_lasso_pp_lookup_index", "hg_lasso_pp_memory_maps", "hg_lasso_pp_subtable_id", "hg_lasso_node_new", "hg_lasso_node_free",
     "hg_lasso_node_log2_input_size", "hg_lasso_node_device_bytes", "hg_lasso_node_prove", "hg_lasso_node_download_polys",
     "hg_lasso_node_num_chunks", "hg_lasso_node_timing", "hg_lasso_node_shard_words", "hg_lasso_node_prove_shard", "hg_lasso_node_emit_shard",
     "hg_shard_merge", "hg_lasso_node_prove_shard_dev", "hg_lasso_node_emit_shard_dev", "hg_shard_merge_device", "hg_gkr_shard_words", "hg_gkr_prove_shard_dev", "hg_gkr_emit_shard_dev",
-    "hg_circuit_new_host", "hg_circuit_insert_lasso_host", "hg_gkr_verify", "hg_mle_eval_host", "hg_bfv_witness_generate", "hg_lasso_node_verify", "hg_sumcheck_prove", "hg_mle_eval_batch", "hg_ntt", "hg_bfv_evaluate", "hg_field_selftest",
+    "hg_circuit_new_host", "hg_circuit_insert_lasso_host", "hg_gkr_verify", "hg_mle_eval_host", "hg_bfv_witness_generate", "hg_lasso_node_verify", "hg_sumcheck_prove", "hg_mle_eval_batch", "hg_ntt", "hg_bfv_configure", "hg_field_selftest",
     "hg_circuit_new", "hg_circuit_free", "hg_circuit_insert_input", "hg_circuit_insert_fft", "hg_circuit_insert_lasso", "hg_circuit_insert_vanilla",
     "hg_circuit_connect", "hg_circuit_evaluate", "hg_circuit_evaluate_host", "hg_circuit_node_value", "hg_gkr_prove", "hg_gkr_timing", "hg_gkr_num_challenges", "hg_gkr_num_inputs", "hg_gkr_num_input_claims",
     "hg_gkr_input_claim_num_vars", "hg_gkr_input_claim",
@@ -74,6 +74,7 @@ def lib():
         L.hg_buf_alloc.argtypes = [vp, sz, C.POINTER(vp)]
         L.hg_buf_upload.argtypes = [vp, vp, sz, vp, sz]
         L.hg_buf_download.argtypes = [vp, vp, sz, vp, sz]
+        L.hg_device_download.argtypes = [vp, vp, vp, sz]
         L.hg_buf_upload_async.argtypes = [vp, vp, sz, vp, sz]
         L.hg_buf_device_ptr.argtypes = [vp]
         L.hg_buf_device_ptr.restype = vp
@@ -99,6 +100,9 @@ def lib():
         L.hg_transcript_num_squeezed.restype = sz
         L.hg_lasso_preprocess.argtypes = [vp, sz, sz, sz, C.POINTER(vp)]
         L.hg_lasso_pp_free.argtypes = [vp]
+        L.hg_lasso_preprocess_lookups.argtypes = [vp, sz, sz, sz, C.POINTER(vp)]
+        L.hg_lasso_pp_lookup_index_by_id.argtypes = [vp, C.c_char_p]
+        L.hg_lasso_node_new_ids.argtypes = [vp, vp, sz, vp, vp, sz, C.POINTER(vp)]
         for f in ("hg_lasso_pp_num_lookups", "hg_lasso_pp_num_subtables", "hg_lasso_pp_num_memories"):
             getattr(L, f).argtypes = [vp]
             getattr(L, f).restype = sz
@@ -159,7 +163,7 @@ def lib():
         L.hg_gkr_input_claim_num_vars.argtypes = [vp, sz, sz]
         L.hg_gkr_input_claim_num_vars.restype = sz
         L.hg_gkr_input_claim.argtypes = [vp, sz, sz, vp, vp]
-        L.hg_bfv_evaluate.argtypes = [vp, sz, sz, vp, vp, vp, vp, u64, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.hg_bfv_configure.argtypes = [vp, sz, sz, vp, vp, vp, vp, u64, u64, u64, vp, vp, sz, vp]
         _lib = L
     return _lib
 
@@ -414,18 +418,77 @@ class CallbackTranscript(Keccak256Transcript):
         return self.inner.into_proof()
 
 
-class LassoPreprocessing:
-    """lasso.rs:513-651 for RangeLookup types given by their bounds."""
+class HgLookupDesc(C.Structure):
+    """hg_lookup_desc (include/hg_b200.h)"""
+    _fields_ = [("lookup_id", C.c_char_p), ("n_subtables", C.c_size_t), ("subtable_ids", C.POINTER(C.c_char_p)), ("tables", C.POINTER(C.c_void_p)),
+                ("dimension_masks", C.POINTER(C.c_uint64)), ("n_chunk_bits", C.c_size_t), ("chunk_bits", C.POINTER(C.c_uint32)), ("combine_weight", C.c_uint64)]
 
-    def __init__(self, bounds, C_=4, M=1 << 16):
-        b = np.array([int(x) for x in bounds], np.uint64)
+
+class TableLookup:
+    """A LookupType given by data (table.rs:35-67 through hg_lookup_desc): lookup_id, subtables [(subtable_id, table of M u64, dimensions)],
+    chunk_bits (low chunk first) and the weight w of combine_lookups = sum_t w^t operand_t."""
+
+    def __init__(self, lookup_id, subtables, chunk_bits, combine_weight):
+        self.lookup_id, self.subtables, self.chunk_bits, self.combine_weight = lookup_id, subtables, list(chunk_bits), int(combine_weight)
+
+
+def range_lookup_as_table(bound, M=1 << 16):
+    """RangeLookup::new_boxed(bound) (range.rs:177-274) written out as a TableLookup: the same subtables, indices, chunk bits and weight."""
+    log2M = M.bit_length() - 1
+    bits = bound.bit_length() - 1
+    full = ("full", np.arange(M, dtype=np.uint64))
+    cutoff = (1 << (bits % log2M)) + bound % M                      # range.rs:58-62 (Q5)
+    rem_t = np.arange(M, dtype=np.uint64)
+    rem_t[min(cutoff, M):] = 0
+    rem = (f"bound_{bound}", rem_t)
+    nch = bits // log2M
+    if bound % M == 0:
+        subs, cb = [(full[0], full[1], list(range(nch)))], [log2M] * nch
+    elif bound < M:
+        subs, cb = [(rem[0], rem[1], [0])], [cutoff.bit_length() - 1]
+    else:
+        subs, cb = [(full[0], full[1], list(range(nch))), (rem[0], rem[1], [nch])], [log2M] * nch + [cutoff.bit_length() - 1]
+    return TableLookup(f"range_{bound}", subs, cb, M)
+
+
+class LassoPreprocessing:
+    """lasso.rs:513-651: LassoPreprocessing::preprocess::<C, M>. `bounds`: RangeLookup types given by their bounds; or
+    LassoPreprocessing.preprocess_lookups([TableLookup, ...]) for plug-in lookup types."""
+
+    def __init__(self, bounds, C_=4, M=1 << 16, _lookups=None):
         self.h = C.c_void_p()
-        _chk(lib().hg_lasso_preprocess(_p(b), b.size, C_, M, C.byref(self.h)))
         self.C, self.M = C_, M
+        if _lookups is None:
+            b = np.array([int(x) for x in bounds], np.uint64)
+            _chk(lib().hg_lasso_preprocess(_p(b), b.size, C_, M, C.byref(self.h)))
+            return
+        descs = (HgLookupDesc * len(_lookups))()
+        keep = []
+        for d, lk in zip(descs, _lookups):
+            n = len(lk.subtables)
+            ids = (C.c_char_p * n)(*[sid.encode() for sid, _, _ in lk.subtables])
+            tabs = [np.ascontiguousarray(t, np.uint64) for _, t, _ in lk.subtables]
+            for t in tabs:
+                if t.size != M:
+                    raise HgError(f"subtable of lookup {lk.lookup_id} has {t.size} entries, M = {M}")
+            tp = (C.c_void_p * n)(*[t.ctypes.data for t in tabs])
+            masks = (C.c_uint64 * n)(*[sum(1 << int(x) for x in dims) for _, _, dims in lk.subtables])
+            cb = (C.c_uint32 * len(lk.chunk_bits))(*lk.chunk_bits)
+            d.lookup_id, d.n_subtables, d.subtable_ids, d.tables = lk.lookup_id.encode(), n, ids, tp
+            d.dimension_masks, d.n_chunk_bits, d.chunk_bits, d.combine_weight = masks, len(lk.chunk_bits), cb, lk.combine_weight
+            keep += [ids, tabs, tp, masks, cb]
+        _chk(lib().hg_lasso_preprocess_lookups(descs, len(_lookups), C_, M, C.byref(self.h)))
 
     @classmethod
     def preprocess(cls, bounds, C_=4, M=1 << 16):
         return cls(bounds, C_, M)
+
+    @classmethod
+    def preprocess_lookups(cls, lookups, C_=4, M=1 << 16):
+        return cls(None, C_, M, _lookups=list(lookups))
+
+    def lookup_index_by_id(self, lookup_id: str):
+        return int(lib().hg_lasso_pp_lookup_index_by_id(self.h, lookup_id.encode()))
 
     @property
     def num_lookups(self):
@@ -470,12 +533,16 @@ class LassoNode:
     """LassoNode<F, E, C, M> (lasso.rs:32-154) on one device."""
 
     def __init__(self, ctx: Context, preprocessing: LassoPreprocessing, num_vars: int, lookup_segments):
-        """lookup_segments: [(bound, run_length), ...] = the node's `lookups: Vec<LookupId>` run-length encoded."""
+        """lookup_segments: [(bound | lookup id string, run_length), ...] = the node's `lookups: Vec<LookupId>` run-length encoded."""
         self.ctx, self.pp, self.num_vars = ctx, preprocessing, num_vars
-        sb = np.array([int(b) for b, _ in lookup_segments], np.uint64)
         sl = np.array([int(l) for _, l in lookup_segments], np.uint64)
         self.h = C.c_void_p()
-        _chk(lib().hg_lasso_node_new(ctx.h, preprocessing.h, num_vars, _p(sb), _p(sl), sb.size, C.byref(self.h)))
+        if lookup_segments and isinstance(lookup_segments[0][0], str):
+            ids = (C.c_char_p * len(lookup_segments))(*[b.encode() for b, _ in lookup_segments])
+            _chk(lib().hg_lasso_node_new_ids(ctx.h, preprocessing.h, num_vars, ids, _p(sl), sl.size, C.byref(self.h)))
+        else:
+            sb = np.array([int(b) for b, _ in lookup_segments], np.uint64)
+            _chk(lib().hg_lasso_node_new(ctx.h, preprocessing.h, num_vars, _p(sb), _p(sl), sb.size, C.byref(self.h)))
         self._el = LIMBS[ctx.field] * DEGREE[ctx.field]
 
     def is_input(self):
@@ -500,7 +567,7 @@ class LassoNode:
         Returns the node's single EvalClaim (point limbs [num_vars, el], value limbs [el])."""
         pt = np.zeros((self.num_vars, self._el), np.uint64)
         val = np.zeros(self._el, np.uint64)
-        if isinstance(inputs, DeviceBuffer):
+        if hasattr(inputs, "ptr"):   # DeviceBuffer, DeviceView, NodeValueView: device memory
             n = n_inputs if n_inputs is not None else inputs.nbytes // (8 * LIMBS[self.ctx.field])
             _chk(lib().hg_lasso_node_prove(self.h, inputs.ptr, n, 1, transcript.h, mode, _p(pt), _p(val)))
         else:
@@ -515,7 +582,7 @@ class LassoNode:
         cap = int(lib().hg_lasso_node_shard_words(self.h))
         out = np.zeros(cap, np.uint64)
         nw = C.c_size_t(0)
-        if isinstance(inputs, DeviceBuffer):
+        if hasattr(inputs, "ptr"):   # DeviceBuffer, DeviceView, NodeValueView: device memory
             n = n_inputs if n_inputs is not None else inputs.nbytes // (8 * LIMBS[self.ctx.field])
             _chk(lib().hg_lasso_node_prove_shard(self.h, inputs.ptr, n, 1, transcript.h, rank, world, _p(out), cap, C.byref(nw)))
         else:
@@ -540,7 +607,7 @@ class LassoNode:
         """prove_shard without leaving the device: this rank's partial message buffer is copied to device memory at d_out_ptr
         (stream-ordered on the context's stream). Returns the number of 64-bit words written."""
         nw = C.c_size_t(0)
-        if isinstance(inputs, DeviceBuffer):
+        if hasattr(inputs, "ptr"):   # DeviceBuffer, DeviceView, NodeValueView: device memory
             n = n_inputs if n_inputs is not None else inputs.nbytes // (8 * LIMBS[self.ctx.field])
             _chk(lib().hg_lasso_node_prove_shard_dev(self.h, inputs.ptr, n, 1, transcript.h, rank, world, C.c_void_p(d_out_ptr), cap_words, C.byref(nw)))
         else:
@@ -731,35 +798,37 @@ def ntt(ctx: Context, d_data: DeviceBuffer, log_n, inverse=False, batch=1):
 
 
 class BfvEncrypt:
-    """Driver-level mirror of `BfvEncrypt` (sk_encryption_circuit.rs:300-523) for the part that runs on the device:
-    forward evaluation of the circuit and the Lasso node."""
+    """Driver-level mirror of `BfvEncrypt` (sk_encryption_circuit.rs:300-523) for forward evaluation only: circuit.evaluate (:442)
+    on the device, returning the two layers the tests look at."""
 
     def __init__(self, ctx: Context, params):
-        from . import witness
-        self.ctx, self.P = ctx, params
-        self.pp = LassoPreprocessing.preprocess(witness.lasso_lookup_bounds(params))  # setup(), :319-349
-        self.num_vars = witness.lasso_num_vars(params)
-        self.node = LassoNode(ctx, self.pp, self.num_vars, witness.lasso_lookup_segments(params))  # configure(), :205-209
-        self.n_lasso = sum(l for _, l in witness.lasso_lookup_segments(params))
+        self.prover = BfvSkEncryptProver(ctx, params)
+        self.ctx, self.P, self.pp, self.node = ctx, params, self.prover.pp, self.prover.lasso
 
     def upload_inputs(self, ins):
-        """get_inputs() vectors (python ints or uint64 arrays) -> device buffers."""
-        u = lambda v: DeviceBuffer.from_numpy(self.ctx, np.asarray(v, dtype=np.uint64).reshape(-1))
-        return dict(s=u(ins["s"]), e=u(ins["e"]), k1=u(ins["k1"]), ais=u(np.concatenate([np.asarray(a, dtype=np.uint64) for a in ins["ais"]])),
-                    r1is=u(np.concatenate([np.asarray(a, dtype=np.uint64) for a in ins["r1is"]])), r2is=u(ins["r2is"]))
+        return self.prover.upload_inputs(ins)
 
     def evaluate(self, dev_ins):
-        """circuit.evaluate (:442): returns (lasso inputs DeviceBuffer, sum DeviceBuffer)."""
-        P = self.P
-        N2 = 1 << P.log2_size
-        lasso = DeviceBuffer(self.ctx, self.n_lasso * 8)
-        summ = DeviceBuffer(self.ctx, P.K * N2 * 8)
-        a = lambda v: np.array([int(x) for x in v], np.uint64)
-        q, k0, r1b, r2b = a(P.QIS), a(P.K0IS), a(P.R1_BOUNDS), a(P.R2_BOUNDS)
-        _chk(lib().hg_bfv_evaluate(self.ctx.h, P.log2_size, P.K, _p(q), _p(k0), _p(r1b), _p(r2b), P.S_BOUND, P.E_BOUND, P.K1_BOUND,
-                                   dev_ins["s"].ptr, dev_ins["e"].ptr, dev_ins["k1"].ptr, dev_ins["ais"].ptr, dev_ins["r1is"].ptr, dev_ins["r2is"].ptr,
-                                   lasso.ptr, summ.ptr))
-        return lasso, summ
+        """circuit.evaluate: returns (`lasso_inputs_batched` layer, `sum` layer) as device views (library-owned memory)."""
+        c = self.prover.circuit
+        c.evaluate(dev_ins)
+        out = []
+        for name in ("lasso_in", "sum"):
+            ptr, n = c.node_value(self.prover.ids[name])
+            out.append(NodeValueView(self.ctx, ptr, n))
+        return tuple(out)
+
+
+class NodeValueView:
+    """Value of a circuit node: device memory owned by the circuit (valid until the next evaluate)."""
+
+    def __init__(self, ctx, ptr, n):
+        self.ctx, self.ptr, self.n = ctx, ptr, n
+
+    def download(self, dtype, count):
+        out = np.zeros(count, dtype)
+        _chk(lib().hg_device_download(self.ctx.h, C.c_void_p(self.ptr), _p(out), out.nbytes))
+        return out
 
 
 class VanillaGate:
@@ -930,85 +999,16 @@ class Circuit:
             pass
 
 
-def build_bfv_circuit(c: Circuit, P, insert_lasso):
-    """BfvEncryptBlock::configure (sk_encryption_circuit.rs:86-293): the same node order and connections, for a device circuit
-    (prover) or a host-only description (verifier). insert_lasso() inserts the Lasso node and returns its id. Returns the ids of
-    a few named nodes."""
-    L, K = P.log2_size, P.K
-    N2 = 1 << L
-    idx = np.arange(N2, dtype=np.uint64)
-    ones = lambda n: np.ones(n, np.uint64)
-
-    def linear(arity, log2_sub, reps, in_idx, wires, coefs, consts=None):
-        ng = len(wires)
-        hc = np.zeros(ng, np.uint8) if consts is None else np.ones(ng, np.uint8)
-        cs = np.zeros(ng, np.uint64) if consts is None else np.asarray(consts, np.uint64)
-        return c.insert_vanilla_arrays(arity, log2_sub, reps, hc, cs, np.arange(ng + 1, dtype=np.uint64), coefs, in_idx, wires)
-
-    s, e, k1 = c.insert_input(L), c.insert_input(L), c.insert_input(L)
-    tile = np.tile(idx, K)
-    es = linear(1, L, 1, np.zeros(K * N2, np.uint32), tile, ones(K * N2))                    # :97-103
-    k1kis = linear(1, L, 1, np.zeros(K * N2, np.uint32), tile, np.repeat(np.array(P.K0IS, np.uint64), N2))   # :105-115
-    c.connect(e, es)
-    c.connect(k1, k1kis)
-    ais = [c.insert_input(L) for _ in range(K)]
-    r1is = [c.insert_input(L) for _ in range(K)]
-    r1iqis = linear(K, L, 1, np.repeat(np.arange(K, dtype=np.uint32), N2), tile, np.repeat(np.array(P.QIS, np.uint64), N2))  # :130-141
-    for r in r1is:
-        c.connect(r, r1iqis)
-    r2is = c.insert_input(P.N_LOG2, K)                                                       # :147
-    r2_log2 = P.N_LOG2 + (K.bit_length() - 1)
-    chunks = []
-    for start in range(0, 1 << r2_log2, N2):                                                 # :150-161
-        cnt = min(N2, (1 << r2_log2) - start)
-        ng = N2
-        add_ptr = np.minimum(np.arange(ng + 1, dtype=np.uint64), cnt)
-        hc = np.zeros(ng, np.uint8)
-        hc[cnt:] = 1
-        nd = c.insert_vanilla_arrays(1, r2_log2, 1, hc, np.zeros(ng, np.uint64), add_ptr, ones(cnt), np.zeros(cnt, np.uint32),
-                                     np.arange(start, start + cnt, dtype=np.uint64))
-        c.connect(r2is, nd)
-        chunks.append(nd)
-    shifts = list(P.R1_BOUNDS[:K]) + [P.R2_BOUNDS[0]] * len(chunks) + [P.S_BOUND, P.E_BOUND, P.K1_BOUND]   # :163-181 (Q7)
-    na = len(shifts)
-    lasso_in = linear(na, L, 1, np.repeat(np.arange(na, dtype=np.uint32), N2), np.tile(idx, na), ones(na * N2),
-                      consts=np.repeat(np.array(shifts, np.uint64), N2))
-    lasso = insert_lasso()                                                                   # :205-209
-    for r in r1is:
-        c.connect(r, lasso_in)
-    for ch in chunks:
-        c.connect(ch, lasso_in)
-    for x in (s, e, k1):
-        c.connect(x, lasso_in)
-    c.connect(lasso_in, lasso)
-    s_eval = c.insert_fft(L, False)                                                          # :224
-    c.connect(s, s_eval)
-    s_copy = linear(1, L, 1, np.zeros(N2, np.uint32), idx, ones(N2))                         # :227-235
-    c.connect(s_eval, s_copy)
-    sai_par = linear(K, L, 1, np.repeat(np.arange(K, dtype=np.uint32), N2), tile, ones(K * N2))   # :237-243
-    for ai in ais:                                                                           # :245-260
-        ai_eval = c.insert_fft(L, False)
-        sai_eval = c.insert_vanilla_arrays(2, L, 1, np.zeros(N2, np.uint8), np.zeros(N2, np.uint64), np.zeros(N2 + 1, np.uint64), None, None, None,
-                                           np.arange(N2 + 1, dtype=np.uint64), ones(N2), np.zeros(N2, np.uint32), idx, np.ones(N2, np.uint32), idx)
-        sai = c.insert_fft(L, True)
-        c.connect(ai, ai_eval)
-        c.connect(s_copy, sai_eval)
-        c.connect(ai_eval, sai_eval)
-        c.connect(sai_eval, sai)
-        c.connect(sai, sai_par)
-    n = 1 << P.N_LOG2                                                                        # :262-278
-    w = np.arange(n - 1, dtype=np.uint64)
-    add_ptr = np.concatenate([np.arange(n, dtype=np.uint64), [n - 1], n - 1 + np.arange(1, n, dtype=np.uint64), [2 * n - 2]]).astype(np.uint64)
-    hc = np.zeros(2 * n, np.uint8)
-    hc[n - 1] = hc[2 * n - 1] = 1
-    cyclo = c.insert_vanilla_arrays(1, P.N_LOG2, K, hc, np.zeros(2 * n, np.uint64), add_ptr, ones(2 * n - 2), np.zeros(2 * n - 2, np.uint32),
-                                    np.concatenate([w, w]))
-    summ = c.insert_vanilla_arrays(5, L, K, np.zeros(N2, np.uint8), np.zeros(N2, np.uint64), np.arange(0, 5 * N2 + 1, 5, dtype=np.uint64), ones(5 * N2),
-                                   np.tile(np.arange(5, dtype=np.uint32), N2), np.repeat(idx, 5))   # :280-285
-    c.connect(r2is, cyclo)
-    for x in (sai_par, es, k1kis, r1iqis, cyclo):
-        c.connect(x, summ)
-    return dict(s=s, e=e, k1=k1, lasso_in=lasso_in, sum=summ)
+def build_bfv_circuit(c: Circuit, P, lasso_node=None, lasso_pp=None, lasso_num_vars=0):
+    """BfvEncryptBlock::configure (sk_encryption_circuit.rs:86-293) through hg_bfv_configure: the same node order and connections for a
+    device circuit (prover: lasso_node) or a host-only description (verifier: lasso_pp + num_vars). Returns the ids of a few nodes."""
+    K = P.K
+    u = lambda v: np.ascontiguousarray(np.array(v[:K], dtype=np.uint64))
+    ids = np.zeros(6, np.int32)
+    _chk(lib().hg_bfv_configure(c.h, P.log2_size, K, _p(u(P.QIS)), _p(u(P.K0IS)), _p(u(P.R1_BOUNDS)), _p(u(P.R2_BOUNDS)), P.S_BOUND, P.E_BOUND, P.K1_BOUND,
+                                lasso_node.h if lasso_node is not None else None, lasso_pp.h if lasso_pp is not None else None, lasso_num_vars, _p(ids)))
+    c._keep.extend([x for x in (lasso_node, lasso_pp) if x is not None])
+    return dict(zip(("s", "e", "k1", "lasso_in", "lasso", "sum"), (int(x) for x in ids)))
 
 
 class BfvSkEncryptVerifier:
@@ -1020,7 +1020,7 @@ class BfvSkEncryptVerifier:
         self.pp = LassoPreprocessing.preprocess(witness.lasso_lookup_bounds(params))
         self.circuit = Circuit(None, field)
         nv = witness.lasso_num_vars(params)
-        self.ids = build_bfv_circuit(self.circuit, params, lambda: self.circuit.insert_lasso_host(self.pp, nv))
+        self.ids = build_bfv_circuit(self.circuit, params, lasso_pp=self.pp, lasso_num_vars=nv)
         self.ct0is_log2_size = params.log2_size + (params.K.bit_length() - 1)
 
     def verify(self, host_inputs, host_ct0is, proof: bytes, options=None):
@@ -1054,7 +1054,7 @@ class BfvSkEncryptProver:
         self.pp = LassoPreprocessing.preprocess(witness.lasso_lookup_bounds(P))                 # setup(): :327-341
         self.lasso = LassoNode(ctx, self.pp, witness.lasso_num_vars(P), witness.lasso_lookup_segments(P))
         c = self.circuit = Circuit(ctx)                                                         # configure(): :351-363, :86-293
-        self.ids = build_bfv_circuit(c, P, lambda: c.insert_lasso(self.lasso))                  # :205-209
+        self.ids = build_bfv_circuit(c, P, lasso_node=self.lasso)                               # hg_bfv_configure
         self.ct0is_log2_size = P.log2_size + (P.K.bit_length() - 1)                             # :519-522
 
     def upload_inputs(self, ins):

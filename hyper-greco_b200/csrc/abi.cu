@@ -9,7 +9,7 @@
 
 #include <map>
 
-#include "bfv.cuh"
+#include "bfv_circuit.hpp"
 #include "gkr_dev.cuh"
 #include "prover.cuh"
 #include "lasso_verify.hpp"
@@ -363,9 +363,6 @@ struct IFieldOps {
                                 const uint64_t* claim, ITranscript* t, int mode, uint64_t* out_point, uint64_t* out_evals) = 0;
     virtual void mle_eval_batch(DeviceCtx* ctx, const void* d_tables, size_t n_tables, size_t stride, size_t num_vars, const uint64_t* point, uint64_t* out) = 0;
     virtual void ntt(DeviceCtx* ctx, void* d, int log_n, bool inverse, size_t batch) = 0;
-    virtual void bfv_evaluate(DeviceCtx* ctx, size_t log2_size, size_t K, const uint64_t* qis, const uint64_t* k0is, const uint64_t* r1b, const uint64_t* r2b,
-                              uint64_t sb, uint64_t eb, uint64_t k1b, const void* d_s, const void* d_e, const void* d_k1, const void* d_ais, const void* d_r1is,
-                              const void* d_r2is, void* d_lasso, void* d_sum) = 0;
     virtual void selftest(DeviceCtx* ctx, int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) = 0;
     virtual void encode(DeviceCtx* ctx, void* d, size_t n, bool decode) = 0;
     virtual void shard_merge(uint64_t* acc, const uint64_t* part, size_t n_words) = 0;
@@ -547,36 +544,6 @@ template <class FP> struct FieldOpsT : IFieldOps {
     DevBuf<X> mle_pt_, mle_eq_, mle_partials_, mle_out_;
     DevBuf<unsigned> mle_counters_;
     PinnedBuf<X> mle_hpt_;
-    void bfv_evaluate(DeviceCtx* dev, size_t log2_size, size_t K, const uint64_t* qis, const uint64_t* k0is, const uint64_t* r1_bounds, const uint64_t* r2_bounds,
-                      uint64_t s_bound, uint64_t e_bound, uint64_t k1_bound, const void* d_s, const void* d_e, const void* d_k1, const void* d_ais,
-                      const void* d_r1is, const void* d_r2is, void* d_lasso_inputs, void* d_sum) override {
-        cudaStream_t s = dev->stream;
-        const size_t N2 = (size_t)1 << log2_size, r2_len = K * (N2 / 2);
-        BfvShape sh;
-        sh.log2_size = (int)log2_size; sh.K = (int)K; sh.n_chunks = (int)std::max<size_t>(1, (r2_len + N2 - 1) / N2);
-        std::vector<B> consts(3 * K);
-        for (size_t i = 0; i < K; i++) { consts[i] = FP::b_from_u64(qis[i]); consts[K + i] = FP::b_from_u64(k0is[i]); consts[2 * K + i] = FP::b_from_u64(r1_bounds[i]); }
-        DevBuf<B> d_consts, d_sai, d_seval;
-        d_consts.alloc(3 * K);
-        HG_CUDA(cudaMemcpyAsync(d_consts.p, consts.data(), consts.size() * sizeof(B), cudaMemcpyHostToDevice, s));
-        const size_t total = (K + sh.n_chunks + 3) * N2;
-        HG_K(dev, KC_MISC, total * 2 * sizeof(B),
-             k_bfv_lasso_inputs<FP><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(sh, (const B*)d_s, (const B*)d_e, (const B*)d_k1, (const B*)d_r1is, (const B*)d_r2is,
-                                                                                  r2_len, d_consts.p + 2 * K, FP::b_from_u64(r2_bounds[0]), FP::b_from_u64(s_bound),
-                                                                                  FP::b_from_u64(e_bound), FP::b_from_u64(k1_bound), (B*)d_lasso_inputs));
-        d_seval.alloc(N2);
-        d_sai.alloc(K * N2);
-        HG_CUDA(cudaMemcpyAsync(d_seval.p, d_s, N2 * sizeof(B), cudaMemcpyDeviceToDevice, s));
-        HG_CUDA(cudaMemcpyAsync(d_sai.p, d_ais, K * N2 * sizeof(B), cudaMemcpyDeviceToDevice, s));
-        eng(dev)->run(d_seval.p, (int)log2_size, false, 1);
-        eng(dev)->run(d_sai.p, (int)log2_size, false, K);
-        HG_K(dev, KC_MISC, 3 * K * N2 * sizeof(B), k_pointwise_mul_bcast<FP><<<dim3((unsigned)((N2 + 255) / 256), (unsigned)K), 256, 0, s>>>(d_sai.p, d_seval.p, N2));
-        eng(dev)->run(d_sai.p, (int)log2_size, true, K);
-        HG_K(dev, KC_MISC, 4 * K * N2 * sizeof(B),
-             k_bfv_sum<FP><<<dim3((unsigned)((N2 + 255) / 256), (unsigned)K), 256, 0, s>>>(sh, d_sai.p, (const B*)d_e, (const B*)d_k1, (const B*)d_r1is, (const B*)d_r2is,
-                                                                                         d_consts.p, d_consts.p + K, (B*)d_sum));
-        HG_CUDA(cudaStreamSynchronize(s));
-    }
 };
 
 struct hg_ctx {
@@ -739,6 +706,14 @@ int hg_buf_download(hg_ctx* ctx, const hg_buf* buf, size_t offset, void* host, s
         HG_CUDA(cudaStreamSynchronize(ctx->dev.stream));
     })
 }
+int hg_device_download(hg_ctx* ctx, const void* d_ptr, void* host, size_t bytes) {
+    HG_TRY({
+        if (!d_ptr || !host) throw std::runtime_error("hg_device_download: NULL pointer");
+        HG_CUDA(cudaSetDevice(ctx->dev.device));
+        HG_CUDA(cudaMemcpyAsync(host, d_ptr, bytes, cudaMemcpyDeviceToHost, ctx->dev.stream));
+        HG_CUDA(cudaStreamSynchronize(ctx->dev.stream));
+    })
+}
 void* hg_buf_device_ptr(hg_buf* buf) { return buf->p; }
 size_t hg_buf_size(const hg_buf* buf) { return buf->bytes; }
 void hg_buf_free(hg_buf* buf) {
@@ -811,6 +786,65 @@ int hg_lasso_preprocess(const uint64_t* bounds, size_t n_bounds, size_t C, size_
         h->pp = LassoPreprocessing::preprocess(lk, C, M);
         for (auto& l : h->pp.lookups) h->lookup_bounds.push_back(static_cast<RangeLookup*>(l.get())->bound());
         *out = h.release();
+    })
+}
+int hg_lasso_preprocess_lookups(const hg_lookup_desc* lookups, size_t n_lookups, size_t C, size_t M, hg_lasso_pp** out) {
+    HG_TRY({
+        if (M < 2 || (M & (M - 1))) throw std::runtime_error("M must be a power of two >= 2");
+        if (!lookups || !out || n_lookups < 1) throw std::runtime_error("hg_lasso_preprocess_lookups: NULL argument or no lookups");
+        if (C < 1 || C > (size_t)HG_MAX_C) throw std::runtime_error("hg_lasso_preprocess_lookups: C out of range");
+        const unsigned log2M = ilog2u(M);
+        std::map<std::string, std::shared_ptr<LassoSubtable>> tables;  // one object per subtable id: the same id must mean the same table
+        std::vector<std::shared_ptr<LookupType>> lk;
+        for (size_t i = 0; i < n_lookups; i++) {
+            const hg_lookup_desc& d = lookups[i];
+            if (!d.lookup_id || !d.subtable_ids || !d.tables || !d.dimension_masks || !d.chunk_bits || d.n_subtables < 1 || d.n_chunk_bits < 1 || d.n_chunk_bits > C)
+                throw std::runtime_error("hg_lasso_preprocess_lookups: malformed descriptor " + std::to_string(i));
+            std::vector<std::pair<std::shared_ptr<LassoSubtable>, SubtableIndices>> sts;
+            uint64_t covered = 0;
+            for (size_t q = 0; q < d.n_subtables; q++) {
+                if (!d.subtable_ids[q] || !d.tables[q]) throw std::runtime_error("hg_lasso_preprocess_lookups: NULL subtable in descriptor " + std::to_string(i));
+                if (d.dimension_masks[q] == 0 || (d.dimension_masks[q] >> d.n_chunk_bits)) throw std::runtime_error("hg_lasso_preprocess_lookups: a subtable must serve dimensions below the chunk count");
+                const std::string id = d.subtable_ids[q];
+                std::vector<uint64_t> t(d.tables[q], d.tables[q] + M);
+                auto it = tables.find(id);
+                if (it == tables.end()) it = tables.emplace(id, std::make_shared<TableSubtable>(id, t)).first;
+                else if (it->second->materialize(M) != t) throw std::runtime_error("hg_lasso_preprocess_lookups: subtable id '" + id + "' is used for two different tables");
+                sts.push_back({it->second, SubtableIndices::from_mask(d.dimension_masks[q])});
+                covered |= d.dimension_masks[q];
+            }
+            if (covered != (((uint64_t)1 << d.n_chunk_bits) - 1)) throw std::runtime_error("hg_lasso_preprocess_lookups: every chunk of lookup '" + std::string(d.lookup_id) + "' needs a subtable");
+            std::vector<unsigned> cb(d.chunk_bits, d.chunk_bits + d.n_chunk_bits);
+            for (unsigned b : cb) if (b < 1 || b > log2M) throw std::runtime_error("hg_lasso_preprocess_lookups: chunk_bits must be in 1..=log2(M)");
+            lk.push_back(std::make_shared<TableLookup>(d.lookup_id, sts, cb, d.combine_weight));
+        }
+        std::unique_ptr<hg_lasso_pp> h(new hg_lasso_pp());
+        h->pp = LassoPreprocessing::preprocess(lk, C, M);
+        *out = h.release();
+    })
+}
+int hg_lasso_pp_lookup_index_by_id(const hg_lasso_pp* pp, const char* lookup_id) {
+    if (!pp || !lookup_id) return -1;
+    auto it = pp->pp.lookup_id_to_index.find(lookup_id);
+    return it == pp->pp.lookup_id_to_index.end() ? -1 : (int)it->second;
+}
+int hg_lasso_node_new_ids(hg_ctx* ctx, const hg_lasso_pp* pp, size_t num_vars, const char* const* seg_lookup_ids, const uint64_t* seg_lens, size_t n_segs,
+                          hg_lasso_node** out) {
+    HG_TRY({
+        HG_CUDA(cudaSetDevice(ctx->dev.device));
+        if (num_vars < 1 || num_vars > 30) throw std::runtime_error("num_vars out of range");
+        if (!seg_lookup_ids || !seg_lens || !out) throw std::runtime_error("hg_lasso_node_new_ids: NULL argument");
+        std::vector<uint8_t> rows;
+        for (size_t s = 0; s < n_segs; s++) {
+            const int li = hg_lasso_pp_lookup_index_by_id(pp, seg_lookup_ids[s]);
+            if (li < 0) throw std::runtime_error("lookup id " + std::string(seg_lookup_ids[s] ? seg_lookup_ids[s] : "(null)") + " not in preprocessing");
+            rows.insert(rows.end(), seg_lens[s], (uint8_t)li);
+        }
+        std::unique_ptr<hg_lasso_node> n(new hg_lasso_node());
+        n->ctx = ctx;
+        n->n.reset(ctx->ops->new_lasso_node(&ctx->dev, pp->pp, (int)num_vars, rows));
+        n->n->log2_input_size = std::max<size_t>(num_vars, ilog2u(pp->pp.M));  // lasso.rs:45-47
+        *out = n.release();
     })
 }
 void hg_lasso_pp_free(hg_lasso_pp* pp) { delete pp; }
@@ -964,13 +998,21 @@ int hg_ntt(hg_ctx* ctx, void* d_data, size_t log_n, int inverse, size_t batch) {
         ctx->ops->ntt(&ctx->dev, d_data, (int)log_n, inverse != 0, batch);
     })
 }
-int hg_bfv_evaluate(hg_ctx* ctx, size_t log2_size, size_t K, const uint64_t* qis, const uint64_t* k0is, const uint64_t* r1_bounds,
-                    const uint64_t* r2_bounds, uint64_t s_bound, uint64_t e_bound, uint64_t k1_bound, const void* d_s, const void* d_e,
-                    const void* d_k1, const void* d_ais, const void* d_r1is, const void* d_r2is, void* d_lasso_inputs, void* d_sum) {
+int hg_bfv_configure(hg_circuit* c, size_t log2_size, size_t K, const uint64_t* qis, const uint64_t* k0is, const uint64_t* r1_bounds, const uint64_t* r2_bounds,
+                     uint64_t s_bound, uint64_t e_bound, uint64_t k1_bound, hg_lasso_node* lasso_node, const hg_lasso_pp* lasso_pp, size_t lasso_num_vars,
+                     int* out_ids6) {
     HG_TRY({
-        HG_CUDA(cudaSetDevice(ctx->dev.device));
-        ctx->ops->bfv_evaluate(&ctx->dev, log2_size, K, qis, k0is, r1_bounds, r2_bounds, s_bound, e_bound, k1_bound, d_s, d_e, d_k1, d_ais, d_r1is, d_r2is,
-                               d_lasso_inputs, d_sum);
+        if (!c || !qis || !k0is || !r1_bounds || !r2_bounds || K < 1 || K > 4096) throw std::runtime_error("hg_bfv_configure: bad arguments");
+        if (c->ctx) circuit_use_device(c);
+        if (c->ctx && !lasso_node) throw std::runtime_error("hg_bfv_configure: a device circuit needs the Lasso node (hg_lasso_node_new)");
+        if (!c->ctx && !lasso_pp) throw std::runtime_error("hg_bfv_configure: a host-only circuit needs the Lasso preprocessing and num_vars");
+        BfvCircuitParams P;
+        P.log2_size = log2_size; P.K = K; P.s_bound = s_bound; P.e_bound = e_bound; P.k1_bound = k1_bound;
+        P.qis.assign(qis, qis + K); P.k0is.assign(k0is, k0is + K); P.r1_bounds.assign(r1_bounds, r1_bounds + K); P.r2_bounds.assign(r2_bounds, r2_bounds + K);
+        ICircuit& ic = *c->c;
+        std::function<int()> ins = [&]() { return c->ctx ? ic.insert_lasso(lasso_node->n.get()) : ic.insert_lasso_host(lasso_pp->pp, (int)lasso_num_vars); };
+        const BfvCircuitIds id = ic.field_id == HG_FIELD_BN254 ? bfv_configure<4>(ic, P, ins) : bfv_configure<1>(ic, P, ins);
+        if (out_ids6) { out_ids6[0] = id.s; out_ids6[1] = id.e; out_ids6[2] = id.k1; out_ids6[3] = id.lasso_in; out_ids6[4] = id.lasso; out_ids6[5] = id.sum; }
     })
 }
 

@@ -145,7 +145,7 @@ __global__ void k_polynomialize(const typename FP::B* __restrict__ inputs, size_
         int nm = meta->lookup_nmem[l];
         for (int t = 0; t < nm; t++) {
             int mi = meta->lookup_mem[l][t];
-            FP::bacc_mad(o, wpow[t], subtables[(size_t)meta->mem_sub[mi] * M + d[meta->mem_dim[mi]]]);
+            FP::bacc_mad(o, wpow[l * HG_MAX_C + t], subtables[(size_t)meta->mem_sub[mi] * M + d[meta->mem_dim[mi]]]);  // combine_lookups of the row's own lookup type
         }
     }
     out[j] = FP::bacc_reduce(o);

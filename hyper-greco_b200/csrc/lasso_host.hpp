@@ -29,6 +29,7 @@ class SubtableIndices {
     SubtableIndices() : bits_(0) {}
     static SubtableIndices from_index(unsigned i) { SubtableIndices s; s.bits_ = 1ULL << i; return s; }
     static SubtableIndices from_range(unsigned lo, unsigned hi) { SubtableIndices s; for (unsigned i = lo; i < hi; i++) s.bits_ |= 1ULL << i; return s; }
+    static SubtableIndices from_mask(uint64_t mask) { SubtableIndices s; s.bits_ = mask; return s; }
     void union_with(const SubtableIndices& o) { bits_ |= o.bits_; }
     bool contains(unsigned i) const { return (bits_ >> i) & 1; }
     size_t len() const { return (size_t)__builtin_popcountll(bits_); }
@@ -113,6 +114,39 @@ class RangeLookup : public LookupType {
     uint64_t combine_weight_base(size_t M) const override { return M; }  // range.rs:184-204
   private:
     uint64_t bound_;
+};
+
+// ---- plug-ins: a LassoSubtable / LookupType described by DATA, for callers that bring their own tables through the C ABI
+// (hg_lasso_preprocess_lookups). The traits of table.rs:16-67 carry code (materialize, evaluate_mle, combine_lookups, ...); what the
+// prove / verify path needs from them is: the subtable's M entries (materialize; its MLE is evaluated from them, the MLE being
+// unique), the dimensions it serves (SubtableIndices), the bit widths of the chunks (chunk_bits) and the combination
+// g(operands) = sum_t w^t operand_t (combine_lookups / combine_lookup_expressions of every lookup in the reference, range.rs:184-204).
+// subtable_indices is the uniform split into log2(M)-bit chunks (range.rs:254-256).
+class TableSubtable : public LassoSubtable {
+  public:
+    TableSubtable(SubtableId id, std::vector<uint64_t> table) : id_(std::move(id)), table_(std::move(table)) {}
+    SubtableId subtable_id() const override { return id_; }
+    std::vector<uint64_t> materialize(size_t M) const override {
+        if (table_.size() != M) throw std::invalid_argument("TableSubtable '" + id_ + "': the table has " + std::to_string(table_.size()) + " entries, M = " + std::to_string(M));
+        return table_;
+    }
+  private:
+    SubtableId id_;
+    std::vector<uint64_t> table_;
+};
+class TableLookup : public LookupType {
+  public:
+    TableLookup(LookupId id, std::vector<std::pair<std::shared_ptr<LassoSubtable>, SubtableIndices>> subtables, std::vector<unsigned> chunk_bits, uint64_t weight)
+        : id_(std::move(id)), subtables_(std::move(subtables)), chunk_bits_(std::move(chunk_bits)), weight_(weight) {}
+    LookupId lookup_id() const override { return id_; }
+    std::vector<std::pair<std::shared_ptr<LassoSubtable>, SubtableIndices>> subtables(size_t, size_t) const override { return subtables_; }
+    std::vector<unsigned> chunk_bits(size_t) const override { return chunk_bits_; }
+    uint64_t combine_weight_base(size_t) const override { return weight_; }
+  private:
+    LookupId id_;
+    std::vector<std::pair<std::shared_ptr<LassoSubtable>, SubtableIndices>> subtables_;
+    std::vector<unsigned> chunk_bits_;
+    uint64_t weight_;
 };
 
 // lasso.rs:513-523

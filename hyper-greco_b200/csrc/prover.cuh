@@ -756,7 +756,7 @@ template <class FP> class LassoNodeDev {
         d_cnt_runs_.alloc((size_t)2 * nslots_ * M_);              // start | end of every address run
         d_eq_.alloc(std::max(R_, M_));
         d_coeff_coll_.alloc(m_);
-        d_wpow_.alloc(HG_MAX_C);
+        d_wpow_.alloc((size_t)HG_MAX_LOOKUPS * HG_MAX_C);
         d_gp_coeffs_.alloc(4 * (size_t)m_ * (num_vars_ + log2M_ + 2) + 4);  // [c | c*r_0] per layer of both grand products
         // product trees: sum_k 2m * (N >> k) < 2m * 2N
         d_tree1_.alloc(2 * (size_t)m_ * 2 * R_);
@@ -801,13 +801,16 @@ template <class FP> class LassoNodeDev {
 
         // constant coefficient vectors
         {
-            std::vector<B> cc(m_), wp(HG_MAX_C);
+            std::vector<B> cc(m_), wp((size_t)HG_MAX_LOOKUPS * HG_MAX_C, FP::b_zero());
             B w = FP::b_from_u64(pp.lookups.empty() ? M_ : pp.lookups[0]->combine_weight_base(pp.M));  // mock lookup = first in map order (lasso.rs:65)
             B p = FP::b_one();
             for (int i = 0; i < m_; i++) { cc[i] = p; p = FP::b_mul(p, w); }
             coll_coeff_host_ = cc;
-            p = FP::b_one();
-            for (int t = 0; t < HG_MAX_C; t++) { wp[t] = p; p = FP::b_mul(p, FP::b_from_u64(M_)); }
+            for (size_t l = 0; l < pp.lookups.size(); l++) {  // combine_lookups of lookup type l: operand t weighs w_l^t (range.rs:184-195: w = M)
+                const B wl = FP::b_from_u64(pp.lookups[l]->combine_weight_base(pp.M));
+                p = FP::b_one();
+                for (int t = 0; t < HG_MAX_C; t++) { wp[l * HG_MAX_C + t] = p; p = FP::b_mul(p, wl); }
+            }
             HG_CUDA(cudaMemcpy(d_wpow_.p, wp.data(), wp.size() * sizeof(B), cudaMemcpyHostToDevice));
         }
         HG_CUDA(cudaFuncSetAttribute(k_tree_tail<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HG_TREE_TAIL * sizeof(B))));

@@ -70,6 +70,8 @@ int hg_buf_upload(hg_ctx* ctx, hg_buf* buf, size_t offset, const void* host, siz
 /* the same without waiting: `host` must stay valid (and should be page-locked) until a later call synchronises the context */
 int hg_buf_upload_async(hg_ctx* ctx, hg_buf* buf, size_t offset, const void* host, size_t bytes);
 int hg_buf_download(hg_ctx* ctx, const hg_buf* buf, size_t offset, void* host, size_t bytes);
+/* read `bytes` from any device pointer the library handed out (hg_circuit_node_value), in stream order behind the context's work */
+int hg_device_download(hg_ctx* ctx, const void* d_ptr, void* host, size_t bytes);
 void* hg_buf_device_ptr(hg_buf* buf);
 size_t hg_buf_size(const hg_buf* buf);
 void hg_buf_free(hg_buf* buf);
@@ -113,6 +115,25 @@ size_t hg_transcript_num_squeezed(const hg_transcript* t);                  /* b
 /* ---- Lasso preprocessing: LassoPreprocessing::preprocess::<C, M> over RangeLookup types (lasso/src/lasso.rs:527-627,
  *      lasso/src/table/range.rs:177-274). `bounds[i]` is the argument of RangeLookup::new_boxed. ---------------- */
 int hg_lasso_preprocess(const uint64_t* bounds, size_t n_bounds, size_t C, size_t M, hg_lasso_pp** out);
+/* Plug-in lookup types: LookupType / LassoSubtable (lasso/src/table.rs:16-67) described by DATA, for tables other than the range checks.
+ * What the prove / verify path takes from the traits: the subtable's M entries (materialize; evaluate_mle is computed from them, the
+ * MLE being unique), the dimensions it serves (SubtableIndices as a bit mask over chunk indices), chunk_bits (low chunk first; the
+ * index is truncated to their sum, lasso.rs:388-389, and split into log2(M)-bit chunks, range.rs:254-256) and the combination
+ * g(operands) = sum_t combine_weight^t * operand_t over the lookup's memories (combine_lookups, range.rs:184-204: weight M).
+ * A subtable id must always denote the same table. Lookups are ordered by their id STRING and de-duplicated, as the reference's
+ * BTreeMap does (lasso.rs:530-541). hg_lasso_preprocess(bounds) is the special case lookup_id "range_<bound>". */
+typedef struct hg_lookup_desc {
+    const char* lookup_id;
+    size_t n_subtables;
+    const char* const* subtable_ids;     /* n_subtables NUL-terminated ids */
+    const uint64_t* const* tables;       /* n_subtables tables of M entries (lifted with F::from(u64)) */
+    const uint64_t* dimension_masks;     /* n_subtables masks: bit d = the subtable serves chunk (dimension) d */
+    size_t n_chunk_bits;                 /* number of chunks this lookup type uses (<= C) */
+    const uint32_t* chunk_bits;
+    uint64_t combine_weight;
+} hg_lookup_desc;
+int hg_lasso_preprocess_lookups(const hg_lookup_desc* lookups, size_t n_lookups, size_t C, size_t M, hg_lasso_pp** out);
+int hg_lasso_pp_lookup_index_by_id(const hg_lasso_pp* pp, const char* lookup_id);  /* index in preprocessing (BTreeMap) order, or -1 */
 void hg_lasso_pp_free(hg_lasso_pp* pp);
 size_t hg_lasso_pp_num_lookups(const hg_lasso_pp* pp);
 size_t hg_lasso_pp_num_subtables(const hg_lasso_pp* pp);
@@ -128,6 +149,9 @@ int hg_lasso_pp_subtable_id(const hg_lasso_pp* pp, size_t idx, char* out, size_t
 /* lookups: Vec<LookupId> given as run-length segments (bound of the RangeLookup, run length), in row order. */
 int hg_lasso_node_new(hg_ctx* ctx, const hg_lasso_pp* pp, size_t num_vars, const uint64_t* seg_bounds, const uint64_t* seg_lens, size_t n_segs,
                       hg_lasso_node** out);
+/* the same with the lookups given by their ids (any LookupType, e.g. one made by hg_lasso_preprocess_lookups) */
+int hg_lasso_node_new_ids(hg_ctx* ctx, const hg_lasso_pp* pp, size_t num_vars, const char* const* seg_lookup_ids, const uint64_t* seg_lens, size_t n_segs,
+                          hg_lasso_node** out);
 void hg_lasso_node_free(hg_lasso_node* node);
 size_t hg_lasso_node_log2_input_size(const hg_lasso_node* node);  /* Node::log2_input_size, lasso.rs:45-47 */
 size_t hg_lasso_node_device_bytes(const hg_lasso_node* node);
@@ -191,15 +215,6 @@ int hg_mle_eval_batch(hg_ctx* ctx, const void* d_tables, size_t n_tables, size_t
  *      by 1/n). In place on `batch` consecutive transforms of 2^log_n base elements at the DEVICE pointer d_data. */
 int hg_ntt(hg_ctx* ctx, void* d_data, size_t log_n, int inverse, size_t batch);
 
-/* ---- forward evaluation of the BFV SK-encryption circuit (circuit.evaluate, sk_encryption_circuit.rs:442, topology :86-293)
- *      on the get_inputs() vectors (:365-415), all DEVICE pointers of base elements:
- *        d_s, d_e, d_k1: 2^log2_size; d_ais, d_r1is: K x 2^log2_size; d_r2is: K x 2^(log2_size-1)
- *      outputs: d_lasso_inputs = `lasso_inputs_batched` layer ((K + chunks + 3) x 2^log2_size, the Lasso node's input),
- *               d_sum = `sum` layer (K x 2^log2_size, equals ct0is for a valid witness).
- *      qis/k0is/bounds are the BfvSkEncryptConstans of the parameter set (constants/mod.rs:16-35), host arrays of K. */
-int hg_bfv_evaluate(hg_ctx* ctx, size_t log2_size, size_t K, const uint64_t* qis, const uint64_t* k0is, const uint64_t* r1_bounds,
-                    const uint64_t* r2_bounds, uint64_t s_bound, uint64_t e_bound, uint64_t k1_bound, const void* d_s, const void* d_e,
-                    const void* d_k1, const void* d_ais, const void* d_r1is, const void* d_r2is, void* d_lasso_inputs, void* d_sum);
 
 /* ---- GKR circuit: gkr::circuit::Circuit::{insert, connect, evaluate} and gkr::prove_gkr for the node shapes bfv-gkr builds
  *      (bfv-gkr/src/sk_encryption_circuit.rs:86-293, :442, :455-457). The engine is the un-vendored `gkr` crate; the per-node
@@ -242,6 +257,15 @@ size_t hg_gkr_shard_words(hg_circuit* c);
 int hg_gkr_prove_shard_dev(hg_circuit* c, size_t n_output_claims, const size_t* point_lens, const uint64_t* points_ext, const uint64_t* values_ext, hg_transcript* t,
                            int rank, int world, void* d_out_words, size_t cap_words, size_t* n_words);
 int hg_gkr_emit_shard_dev(hg_circuit* c, const void* d_merged_words, size_t n_words);
+/* ---- BfvEncryptBlock::configure (bfv-gkr/src/sk_encryption_circuit.rs:86-293) in the library: builds the whole circuit of the BFV secret-key
+ *      encryption proof into `c` with the calls above, node for node and connection for connection (a Rust caller that keeps its own
+ *      `configure` binds hg_circuit_insert_* / hg_circuit_connect instead; the result is the same circuit). qis / k0is / r1_bounds /
+ *      r2_bounds: arrays of K (BfvSkEncryptConstans, constants/mod.rs:16-35), K a power of two. The Lasso node: for a device circuit the
+ *      node made by hg_lasso_node_new (lasso_pp may be NULL); for a host-only description (hg_circuit_new_host) its preprocessing and
+ *      num_vars (lasso_node NULL). out_ids6 (may be NULL): node ids of s, e, k1, lasso_inputs_batched, the Lasso node, sum. */
+int hg_bfv_configure(hg_circuit* c, size_t log2_size, size_t K, const uint64_t* qis, const uint64_t* k0is, const uint64_t* r1_bounds, const uint64_t* r2_bounds,
+                     uint64_t s_bound, uint64_t e_bound, uint64_t k1_bound, hg_lasso_node* lasso_node, const hg_lasso_pp* lasso_pp, size_t lasso_num_vars,
+                     int* out_ids6);
 /* ---- synthetic witness on the device: the arithmetic of scripts/circuit_sk.py:72-140 (ct0i_hat = a_i s + e + k0_i k1 over Z, exact;
  *      centred reduction mod (x^n + 1, q_i); r2i, r1i; the bound assertions), written straight into the BfvEncrypt::get_inputs layout
  *      (sk_encryption_circuit.rs:365-415). The random draws stay with the caller (HOST arrays, lowest degree first): s in {-1,0,1} and e as

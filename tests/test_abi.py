@@ -125,6 +125,32 @@ def test_host_verifier_accepts_golden_bfv_proofs_and_rejects_tampering(api, gold
         v.circuit.evaluate_host(flat)
 
 
+def test_plugin_lookup_types_reproduce_range_lookup_preprocessing(api, oracle):
+    """LookupType / LassoSubtable plug-ins through the C ABI (hg_lasso_preprocess_lookups, table.rs:16-67): RangeLookup written out as
+    data gives the same preprocessing as the built-in one (lookup order, subtables, memory numbering) for every parameter set; a
+    custom table is accepted; malformed descriptors are refused."""
+    from hyper_greco_b200 import params, witness
+    for name, P in params.PARAMS.items():
+        bounds = witness.lasso_lookup_bounds(P)
+        a = api.LassoPreprocessing.preprocess(bounds)
+        b = api.LassoPreprocessing.preprocess_lookups([api.range_lookup_as_table(x) for x in bounds])
+        assert (a.num_lookups, a.num_subtables, a.num_memories) == (b.num_lookups, b.num_subtables, b.num_memories)
+        assert a.memory_names() == b.memory_names() and a.memory_maps() == b.memory_maps()
+        for x in bounds:
+            assert a.lookup_index(x) == b.lookup_index_by_id(f"range_{x}") >= 0
+    M = 1 << 16
+    sq = np.array([(i * i) & 0xFFFF for i in range(M)], np.uint64)
+    pp = api.LassoPreprocessing.preprocess_lookups([api.TableLookup("sq16", [("sq", sq, [0, 1])], [16, 16], 3), api.range_lookup_as_table(65537)])
+    assert pp.num_lookups == 2 and pp.num_memories == 4 and pp.lookup_index_by_id("sq16") == 1 and pp.lookup_index_by_id("nope") == -1
+    assert pp.memory_names() == ["full@0", "bound_65537@1", "sq@0", "sq@1"]
+    with pytest.raises(api.HgError):   # a chunk without a subtable
+        api.LassoPreprocessing.preprocess_lookups([api.TableLookup("bad", [("sq", sq, [0])], [16, 16], 3)])
+    with pytest.raises(api.HgError):   # one id, two different tables
+        api.LassoPreprocessing.preprocess_lookups([api.TableLookup("a", [("t", sq, [0])], [16], 2), api.TableLookup("b", [("t", sq + 1, [0])], [16], 2)])
+    with pytest.raises(api.HgError):   # wrong table length
+        api.LassoPreprocessing.preprocess_lookups([api.TableLookup("a", [("t", sq[:100], [0])], [16], 2)])
+
+
 def test_preprocessing_matches_oracle(api, oracle):
     from hyper_greco_b200 import params, witness
     for name, P in params.PARAMS.items():

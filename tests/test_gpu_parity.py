@@ -909,3 +909,49 @@ def test_product_event_log_equals_interchange_dump(api, ctx, golden_dir):
         for b in limbs:
             got.append(("S" if kind == "squeeze" else "W", int(b).to_bytes(8, "big")))
     assert got == events
+
+
+# ------------------------------------------------------------------------------------------------ plug-in lookup types (table.rs:16-67)
+def test_plugin_lookup_types_on_the_device(api, ctx, golden_dir):
+    """hg_lasso_preprocess_lookups + hg_lasso_node_new_ids: (1) RangeLookup written out as table data proves to the committed golden
+    bytes (the plug-in path IS the built-in path); (2) a genuinely different table (16-bit squares, two chunks, weight 3) next to a
+    range check: the product's verifier accepts the proof, the claimed sum is sum_k eq(r, k) * (sq[lo] + 3 sq[hi]) resp. the range
+    output, and a row that reads outside its lookup's chunk bits is truncated as the reference does (lasso.rs:388-389)."""
+    from hyper_greco_b200 import params, witness
+    name = "1024_1x27_65537"
+    P = params.PARAMS[name]
+    golden = open(os.path.join(golden_dir, f"proof_goldilocks_lasso_node_{name}.bin"), "rb").read()
+    inp = np.load(os.path.join(golden_dir, f"lasso_inputs_{name}.npz"))["inputs"]
+    bounds, segs, nv = witness.lasso_lookup_bounds(P), witness.lasso_lookup_segments(P), witness.lasso_num_vars(P)
+    pp = api.LassoPreprocessing.preprocess_lookups([api.range_lookup_as_table(b) for b in bounds])
+    node = api.LassoNode(ctx, pp, nv, [(f"range_{b}", l) for b, l in segs])
+    tr = api.Keccak256Transcript()
+    node.prove_claim_reduction(inp, tr)
+    assert tr.into_proof() == golden
+    node.free()
+    # (2) custom table
+    M = 1 << 16
+    sq = np.array([(i * i) & 0xFFFF for i in range(M)], np.uint64)
+    pp2 = api.LassoPreprocessing.preprocess_lookups([api.TableLookup("sq16", [("sq", sq, [0, 1])], [16, 16], 3), api.range_lookup_as_table(65537)])
+    rng = np.random.default_rng(5)
+    n_sq, n_rg, nv2 = 3000, 1000, 12
+    x_sq = rng.integers(0, 1 << 32, n_sq, dtype=np.uint64)
+    x_sq[0] = (1 << 40) | 0x12345678                                  # bits above the lookup's 32 are dropped
+    x_rg = rng.integers(0, 65537, n_rg, dtype=np.uint64)
+    inputs = np.concatenate([x_sq, x_rg])
+    node2 = api.LassoNode(ctx, pp2, nv2, [("sq16", n_sq), ("range_65537", n_rg)])
+    tr2 = api.Keccak256Transcript()
+    pt, val = node2.prove_claim_reduction(inputs, tr2)
+    proof = tr2.into_proof()
+    vpt, vval = api.lasso_node_verify(pp2, nv2, api.Keccak256Transcript(api.GOLDILOCKS, proof))
+    assert (vpt == pt).all() and (vval == val).all()
+    lo, hi = x_sq & 0xFFFF, (x_sq >> 16) & 0xFFFF
+    out = np.zeros(1 << nv2, np.uint64)
+    out[:n_sq] = sq[lo] + 3 * sq[hi]
+    out[n_sq:n_sq + n_rg] = x_rg                                       # range_65537: full limb + 65536 * remainder limb = the value itself
+    assert (api.mle_eval_host(api.GOLDILOCKS, out, nv2, pt) == val).all()
+    bad = bytearray(proof)
+    bad[-5] ^= 1
+    with pytest.raises(api.HgError):
+        api.lasso_node_verify(pp2, nv2, api.Keccak256Transcript(api.GOLDILOCKS, bytes(bad)))
+    node2.free()
