@@ -153,6 +153,7 @@ template <class FP> class GkrCircuitDev {
     // and direction share one contiguous arena and are transformed by ONE batched NTT (the circuit has 2K+1 forward
     // transforms on one level). Nothing here waits for the device.
     void evaluate(const std::vector<const B*>& inputs) {
+        NvtxSpan span("eval circuit");  // sk_encryption_circuit.rs:442
         cudaStream_t s = ctx_->stream;
         size_t next = 0;
         for (auto& n : nodes_) if (n->kind == GKR_INPUT) { if (next >= inputs.size()) throw std::runtime_error("evaluate: too few inputs"); n->value_ptr = inputs[next++]; }
@@ -242,6 +243,7 @@ template <class FP> class GkrCircuitDev {
     // everything of prove() up to (not including) the download of the messages
     void enqueue(Keccak256Transcript<FP>& tr, ProveMode mode, const WireOptions& wo, const std::vector<InputClaim>& output_claims, int rank, int world) {
         if (!evaluated_) throw std::runtime_error("prove_gkr: evaluate the circuit first");
+        NvtxSpan span("GKR prove");     // sk_encryption_circuit.rs:455
         const bool sharded = world > 1;
         cudaStream_t s = ctx_->stream;
         auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };

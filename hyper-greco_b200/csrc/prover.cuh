@@ -11,6 +11,7 @@
 //   INTERACTIVE  one device->host->device round trip per squeeze; works with any transcript.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <chrono>
 #include <functional>
@@ -28,6 +29,14 @@
 namespace hg {
 
 struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+// NVTX range named after the reference's tracing span (lasso.rs:57,156,253,291; sk_encryption_circuit.rs:442,455): Nsight / ncu --nvtx
+// timelines of this library read like the reference's tracing-forest output. Header-only NVTX3: free when no tool is attached.
+struct NvtxSpan {
+    explicit NvtxSpan(const char* name) { nvtxRangePushA(name); }
+    ~NvtxSpan() { nvtxRangePop(); }
+    NvtxSpan(const NvtxSpan&) = delete;
+    NvtxSpan& operator=(const NvtxSpan&) = delete;
+};
 #define HG_CUDA(expr)                                                                                            \
     do {                                                                                                         \
         cudaError_t _e = (expr);                                                                                 \
@@ -833,6 +842,7 @@ template <class FP> class LassoNodeDev {
     // Output: the claim (r, claimed_sum) for input 0 (lasso.rs:97,113).
     void prove(const B* d_inputs, size_t n_inputs, Keccak256Transcript<FP>& tr, ProveMode mode, const WireOptions& wo, std::vector<X>* out_point,
                X* out_value) {
+        NvtxSpan span("LassoNode::prove_claim_reduction");
         if (!tr.prefetch_legal()) mode = kModeInteractive;  // a transcript that may absorb messages: one round trip per squeeze
         Channel<FP>& ch = *ch_;
         auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -905,6 +915,7 @@ template <class FP> class LassoNodeDev {
 
     // polynomialize (lasso.rs:157-250): everything that needs no challenge
     void enqueue_witness(const B* d_inputs, size_t n_inputs, const WireOptions& wo) {
+        NvtxSpan span("LassoNode::polynomialize");
         cudaStream_t s = ctx_->stream;
         const size_t R = R_, M = M_;
         const int m = m_;
@@ -1013,10 +1024,12 @@ template <class FP> class LassoNodeDev {
         }
         // ---- collation sumcheck (lasso.rs:271-279): t_0 * sum_i c_i t_i == E_0 * S with S = sum_i c_i E_i
         {
+            NvtxSpan span("LassoNode::prove_collation_sum_check");
             // g(E_0, S) = E_0 * (0 * E_0 + 1 * S): nterm = 2, arity 1, tables [E_0 | S]; coefficients {0, 1} live in d_coll_terms_
             sumcheck_dev<FP, 1>(ctx_, KC_SC_COLL, ch, wo, d_coll_.p, R, 2, d_coll_terms_.p, d_bufA_.p, d_bufB_.p, sc_, coll_state, nullptr, nullptr, lead, true);
         }
         // ---- gamma, tau (lasso.rs:99)
+        NvtxSpan span_mc("LassoNode::prove_memory_checking");
         const size_t gt_idx = ch.squeeze(2);
         if (ctx_->join3_pending) {  // the access counters (enqueue_witness) are read from here on
             HG_CUDA(cudaStreamWaitEvent(s, ctx_->ev_join3, 0));
