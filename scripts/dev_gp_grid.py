@@ -24,4 +24,5 @@ for _ in range(3):
     tr = api.Keccak256Transcript(); node.prove_claim_reduction(buf, tr, 0, n_inputs=inp.size)
 prof = ctx.profile_read(); ctx.profile(False)
 gp = prof["sumcheck_grand_product"]
-print(f"MAXBX={os.environ.get('HG_GP_MAXBX')} TARGET={os.environ.get('HG_GP_TARGET')}: {dt*1e3:.3f} ms/proof, GP class {gp[1]/3:.3f} ms, sha={hashlib.sha256(proof).hexdigest()[:12]}")
+tag = " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("HG_"))
+print(f"[{tag}] {dt*1e3:.3f} ms/proof, hash {prof['hash_build'][1]/3:.3f} tree {prof['product_tree'][1]/3:.3f} GP {gp[1]/3:.3f} ms, sha={hashlib.sha256(proof).hexdigest()[:12]}")

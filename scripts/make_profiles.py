@@ -1,10 +1,9 @@
-"""Turns the ncu captures brought back in gpurun_out/ into the tracked summaries under profiles/.
+"""Turns the ncu captures brought back in gpurun_out/ into the tracked summaries under profiles/ (TAG = r2 unless given as argv[1]).
 
-    gpurun_out/r1_launches.csv : ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none
-                                 -c 3000 --csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline
-    gpurun_out/r1_gp.ncu-rep   : ncu --set full --clock-control none --import-source on -k regex:"k_gp_(r0a|r0|fold)_multi" -s 32 -c 4
-                                 python scripts/dev_gp_grid.py
-Writes profiles/r1_launch_list.md, profiles/traffic.json, profiles/r1_ncu_gp_kernels.txt."""
+    gpurun_out/TAG_launches.csv : ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none
+                                  -c 900 --csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --inflight 1 --pool 1
+    gpurun_out/TAG_*.ncu-rep    : ncu --set full --clock-control none --import-source on -k regex:... python scripts/dev_gp_grid.py
+(the exact commands are scripts/gpu_profile.sh). Writes profiles/TAG_launch_list.md, profiles/traffic.json, profiles/TAG_ncu_gp_kernels.txt."""
 import collections
 import csv
 import json
@@ -15,10 +14,10 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CLASSES = [
-    ("sumcheck_grand_product", r"k_gp_r0a_multi|k_gp_r0_multi|k_gp_fold_multi|k_gp_tail"),
+    ("sumcheck_grand_product", r"k_gp_r0a_multi|k_gp_r0_multi|k_gp_fold_multi|k_gp_tail|k_gp_mid"),
     ("misc", r"k_gp_coeffs_multi"),
-    ("sumcheck_collation", r"k_coll_round|k_prod_tail_one|k_sc_round|k_fold_final"),
-    ("gkr_layer_sumcheck", r"k_prod_round_multi|k_prod_tail|k_copy_items|k_fold_items"),
+    ("sumcheck_collation", r"k_coll_round|k_prod_tail_one|k_sc_round|k_fold_final|k_prod_mid_one"),
+    ("gkr_layer_sumcheck", r"k_prod_round_multi|k_prod_tail|k_prod_mid|k_copy_items|k_fold_items"),
     ("gkr_layer_weights", r"k_eq_split_multi|k_eq_accumulate|k_wiring_gather|k_concat_items|k_ext_split|k_ext_merge|k_dot_wconst"),
     ("counters", r"k_cnt_"),
     ("hash_build", r"k_hash_"),
@@ -38,7 +37,8 @@ def classify(name):
 
 
 def main():
-    src = os.path.join(ROOT, "gpurun_out", "r1_launches.csv")
+    TAG = sys.argv[1] if len(sys.argv) > 1 else "r2"
+    src = os.path.join(ROOT, "gpurun_out", f"{TAG}_launches.csv")
     lines = [l for l in open(src) if not l.startswith("==")]
     byid = collections.OrderedDict()
     for x in csv.DictReader(lines):
@@ -62,15 +62,15 @@ def main():
             e[3] += k["dram__bytes_write.sum"]
     bench = None
     try:
-        bench = json.loads(open(os.path.join(ROOT, "profiles", "r1_bench_ours.json")).read().strip().splitlines()[-1])
+        bench = json.loads(open(os.path.join(ROOT, "profiles", f"{TAG}_bench_ours.json")).read().strip().splitlines()[-1])
     except Exception:
         pass
-    out = ["# Launch list of one proof (round 1, final state)", "",
+    out = [f"# Launch list of one proof ({TAG}, final state)", "",
            "Command (on a B200 through gpurun): `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum "
-           "--clock-control none -c 3000 --csv --log-file gpurun_out/r1_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline`.",
+           f"--clock-control none -c 900 --csv --log-file gpurun_out/{TAG}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --inflight 1 --pool 1`.",
            f"Rows below: launches {a}..{b - 1} of that run = the 4th `gkr::prove_gkr` (n=32768, k=16, Goldilocks), {len(step)} launches, "
            f"{total / 1e6:.3f} ms summed kernel time. Under ncu every launch is serialised and runs cold, so only the SHARES are comparable "
-           "with the CUDA-event numbers of `bench.py` (last column, `roofline.per_class` of profiles/r1_bench_ours.json, where the same "
+           f"with the CUDA-event numbers of `bench.py` (last column, `roofline.per_class` of profiles/{TAG}_bench_ours.json, where the same "
            "kernels run back to back on one stream in profiling mode).", "",
            "| class | launches | ncu time (us) | share | DRAM read (MB) | DRAM write (MB) | bench.py events: ms, share |", "|---|---|---|---|---|---|---|"]
     btot = sum(v["ms"] for v in bench["roofline"]["per_class"].values()) if bench else None
@@ -87,26 +87,32 @@ def main():
     for n, k in enumerate(step):
         nm = re.sub(r"\(.*", "", re.sub(r"^void ", "", k["name"]))
         out.append(f"| {n} | `{nm}` | {k['grid']} | {k['block']} | {k['gpu__time_duration.sum'] / 1e3:.1f} | {k['dram__bytes_read.sum'] / 1e6:.2f} | {k['dram__bytes_write.sum'] / 1e6:.2f} |")
-    open(os.path.join(ROOT, "profiles", "r1_launch_list.md"), "w").write("\n".join(out) + "\n")
+    open(os.path.join(ROOT, "profiles", f"{TAG}_launch_list.md"), "w").write("\n".join(out) + "\n")
     traffic = {"_comment": "DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum, ncu) of one proof per kernel class; bench.py reports "
                            "roofline.traffic = bytes per launch of the dominant class (class total / launches), like roofline.achieved is per launch",
-               "_source": "gpurun_out/r1_launches.csv via scripts/make_profiles.py"}
+               "_source": f"gpurun_out/{TAG}_launches.csv via scripts/make_profiles.py"}
     for cls, e in per_cls.items():
         traffic[cls] = {"launches": e[0], "bytes_per_step": e[2] + e[3], "bytes_per_launch": (e[2] + e[3]) / e[0]}
     json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
-    rep = os.path.join(ROOT, "gpurun_out", "r1_gp.ncu-rep")
-    if os.path.exists(rep):
-        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw"], capture_output=True, text=True).stdout
-        keep = re.compile(r"k_gp_|gpu__time_duration.sum|dram__bytes_(read|write).sum |gpu__dram_throughput.avg.pct|sm__throughput.avg.pct|launch__registers_per_thread |"
-                          r"launch__grid_size|launch__occupancy_limit_registers|sm__warps_active.avg.pct|smsp__inst_executed.sum |sm__pipe_(alu|fma)_cycles_active.avg.pct_of_peak_sustained_active|"
-                          r"smsp__issue_active.avg.pct|smsp__average_warps_issue_stalled_(barrier|dispatch_stall|long_scoreboard|math_pipe_throttle|not_selected|wait|short_scoreboard|no_instruction)_per_issue_active")
-        txt = ["ncu --set full --clock-control none --import-source on -k regex:\"k_gp_(r0a|r0|fold)_multi\" -s 32 -c 4 python scripts/dev_gp_grid.py",
-               "(third proof of the run; rounds 0a, 0b, 1, 2 of the batched grand-product sumchecks: 35 layers of both memory-checking trees per launch)", ""]
+    keep = re.compile(r"k_gp_|k_hash_|k_tree_|gpu__time_duration.sum|dram__bytes_(read|write).sum |gpu__dram_throughput.avg.pct|sm__throughput.avg.pct|launch__registers_per_thread |"
+                      r"launch__grid_size|launch__occupancy_limit_registers|sm__warps_active.avg.pct|smsp__inst_executed.sum |sm__pipe_(alu|fma)_cycles_active.avg.pct_of_peak_sustained_active|"
+                      r"smsp__issue_active.avg.pct|smsp__average_warps_issue_stalled_(barrier|dispatch_stall|long_scoreboard|math_pipe_throttle|not_selected|wait|short_scoreboard|no_instruction)_per_issue_active|"
+                      r"sm__inst_executed_pipe_(alu|fma|fmaheavy|lsu).sum |local_(load|store)")
+    txt = []
+    for rep_name in sorted(os.listdir(os.path.join(ROOT, "gpurun_out"))):
+        if rep_name.startswith(TAG + "_") and rep_name.endswith(".ncu-rep"):
+            raw = subprocess.run(["ncu", "-i", os.path.join(ROOT, "gpurun_out", rep_name), "--page", "raw"], capture_output=True, text=True).stdout
+        elif rep_name.startswith(TAG + "_") and rep_name.endswith("_raw.txt"):   # `ncu -i ... --page raw` already run on the box
+            raw = open(os.path.join(ROOT, "gpurun_out", rep_name)).read()
+        else:
+            continue
+        txt += [f"===== {rep_name}: ncu --set full --clock-control none --import-source on (scripts/gpu_profile.sh), python scripts/dev_gp_grid.py", ""]
         for l in raw.splitlines():
             if keep.search(l) and "not_issued" not in l:
-                txt.append("-----" if "k_gp_" in l and "void" in l else "")
+                txt.append("-----" if re.search(r"k_(gp|hash|tree)_", l) and "void" in l else "")
                 txt.append(l.rstrip())
-        open(os.path.join(ROOT, "profiles", "r1_ncu_gp_kernels.txt"), "w").write("\n".join(t for t in txt if t != "") + "\n")
+    if txt:
+        open(os.path.join(ROOT, "profiles", f"{TAG}_ncu_gp_kernels.txt"), "w").write("\n".join(t for t in txt if t != "") + "\n")
     print("profiles written:", {k: (v[0], round(v[1] / 1e3, 1)) for k, v in per_cls.items()})
 
 
