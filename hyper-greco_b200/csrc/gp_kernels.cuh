@@ -484,6 +484,10 @@ template <class FP> __global__ void k_gp_coeffs_multi(const GpCoeffItem<FP>* __r
 }
 
 // ---- tail: one CTA per layer, tables in shared memory, all remaining rounds + the final evaluations
+constexpr int HG_GP_MID_STAGES = 3;   // mid stages per layer (each folds up to HG_GP_MID_MAXK rounds)
+constexpr int HG_GP_MID_SEG = 64;     // entries of a table one mid CTA owns
+constexpr int HG_GP_MID_MAXK = 5;     // 64 -> 2 entries
+constexpr int HG_GP_MID_THREADS = 256;
 template <class FP> struct GpTailItem {
     const void* in;                 // from_base: base tables [nvec][2n]; else extension tables [2*nvec][n] (already scaled)
     const typename FP::X* c;
@@ -495,6 +499,11 @@ template <class FP> struct GpTailItem {
     int i_begin, i_end;             // owned terms (see GpItem)
     const typename FP::X* r0part;   // !from_base: round-0 partial sums of the fused tree builders (gp_fused.cuh), [r0n][4], summed into msg0
     int r0n;
+    // rounds that ran in mid stages (k_gp_mid): stage s left mid_K[s] x mid_n[s] CTA partial sums, [K][n][3]; their sums are the
+    // messages mid_msg[s][3 * q + p]
+    const typename FP::X* mid_part[HG_GP_MID_STAGES];
+    typename FP::X* mid_msg[HG_GP_MID_STAGES];
+    int mid_n[HG_GP_MID_STAGES], mid_K[HG_GP_MID_STAGES];
 };
 
 template <class FP, int NP>
@@ -567,6 +576,15 @@ template <class FP> __global__ void __launch_bounds__(HG_TAIL_THREADS) k_gp_tail
                 for (int p = 0; p < 4; p++) acc[p] = FP::x_add(acc[p], it.r0part[(size_t)b * 4 + p]);
             tail_block_sum<FP, 4>(acc, red, it.msg0);
         }
+        for (int st = 0; st < HG_GP_MID_STAGES; st++)  // rounds that ran in mid stages: add up the CTA partials of every round
+            for (int q = 0; q < it.mid_K[st]; q++) {
+                X acc[3] = {FP::x_zero(), FP::x_zero(), FP::x_zero()};
+                const X* part = it.mid_part[st] + (size_t)q * it.mid_n[st] * 3;
+                for (int b = threadIdx.x; b < it.mid_n[st]; b += blockDim.x)
+#pragma unroll
+                    for (int p = 0; p < 3; p++) acc[p] = FP::x_add(acc[p], part[(size_t)b * 3 + p]);
+                tail_block_sum<FP, 3>(acc, red, it.mid_msg[st] + 3 * q);
+            }
         __syncthreads();
     }
     X* cur = A;
@@ -608,6 +626,91 @@ template <class FP> __global__ void __launch_bounds__(HG_TAIL_THREADS) k_gp_tail
     const X r = it.chal[it.rounds];
     const typename FP::FoldAux aux = FP::fold_aux(r);
     for (int t = 2 * it.i_begin + threadIdx.x; t < 2 * it.i_end; t += blockDim.x) it.evals[t] = FP::fold(cur[2 * t], cur[2 * t + 1], r, aux);
+}
+
+
+// ---- mid stage: K (<= 5) consecutive rounds of a layer in ONE launch, for the rounds whose tables are too short to fill the GPU
+// (profiles/r2_launch_list.md: the streamed rounds 8..14 take 11-26 us each for < 30 MB). Folding pairs (2b, 2b+1) is local to a
+// segment of 2^K consecutive entries, so a CTA that owns HG_GP_MID_SEG = 64 consecutive entries of its tables runs the K rounds in
+// shared memory; only its partial sums per round leave it, and the tables come back 2^K times shorter (64 >> K entries per segment).
+// h is linear in the terms: a segment's terms are split over `groups` CTAs, each with its own copy of t_0. The tail kernel adds the
+// partial sums up (GpTailItem::mid_part). Same arithmetic as k_gp_tail, so the messages are the same field elements.
+template <class FP> struct GpMidItem {
+    const typename FP::X* in;    // [2*nvec][n_in], already scaled (a streamed round >= 1 ran before)
+    typename FP::X* out;         // [2*nvec][n_in >> K]
+    unsigned long long n_in;
+    const typename FP::X* chal;  // chal[q]: the challenge folded in the q-th round of the stage
+    typename FP::X* part;        // [K][nseg * groups][3]
+    int nvec, K, nseg, groups, tpg, blk_start;
+    int i_begin, i_end, write_t0;  // owned terms (see GpItem); table 0 is written by group 0 when term 0 is not owned
+};
+template <class FP> inline size_t gp_mid_smem(int tpg) {
+    return ((size_t)(1 + 2 * tpg) * (HG_GP_MID_SEG + HG_GP_MID_SEG / 2) + 32 * 4) * sizeof(typename FP::X);
+}
+template <class FP> __global__ void __launch_bounds__(HG_GP_MID_THREADS) k_gp_mid(const GpMidItem<FP>* __restrict__ items, int nitems) {
+    typedef typename FP::X X;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int SEG = HG_GP_MID_SEG;
+    const GpMidItem<FP> it = items[find_item(items, nitems)];
+    const int lb = (int)blockIdx.x - it.blk_start;
+    const int seg = lb % it.nseg, grp = lb / it.nseg;
+    const int i0 = it.i_begin + grp * it.tpg, i1 = min(it.i_end, i0 + it.tpg);
+    const int nt = i1 - i0, ntab = 1 + 2 * nt;  // slot 0: t_0 (table 0); slots 1 + 2k, 2 + 2k: l, r of term i0 + k
+    const int cap = 1 + 2 * it.tpg;
+    X* A = reinterpret_cast<X*>(smem_raw);   // [cap][SEG]
+    X* Bf = A + (size_t)cap * SEG;            // [cap][SEG / 2]
+    X* red = Bf + (size_t)cap * (SEG / 2);    // [32][4]
+    const size_t n_in = it.n_in;
+    for (int e = threadIdx.x; e < ntab * SEG; e += blockDim.x) {
+        const int slot = e / SEG, k = e % SEG;
+        const size_t tab = slot ? (size_t)(2 * i0 + slot - 1) : 0;
+        A[e] = it.in[tab * n_in + (size_t)seg * SEG + k];
+    }
+    __syncthreads();
+    X* cur = A;
+    X* nxt = Bf;
+    int len = SEG;
+    const int ncta = it.nseg * it.groups;
+    for (int q = 0; q < it.K; q++) {
+        const X r = it.chal[q];
+        const typename FP::FoldAux aux = FP::fold_aux(r);
+        const int npairs = len / 4, half = len / 2;
+        X acc[3] = {FP::x_zero(), FP::x_zero(), FP::x_zero()};
+        for (int b = threadIdx.x; b < npairs; b += blockDim.x) {  // this CTA's copy of t_0
+            const X* t = cur + 4 * b;
+            nxt[2 * b] = FP::fold(t[0], t[1], r, aux);
+            nxt[2 * b + 1] = FP::fold(t[2], t[3], r, aux);
+        }
+        for (int e = threadIdx.x; e < nt * npairs; e += blockDim.x) {
+            const int k = e / npairs, b = e % npairs;
+            const X* t = cur + 4 * b;
+            const X* l = cur + (1 + 2 * k) * len + 4 * b;
+            const X* g = cur + (2 + 2 * k) * len + 4 * b;
+            const X t_lo = FP::fold(t[0], t[1], r, aux), t_hi = FP::fold(t[2], t[3], r, aux);
+            const X l_lo = FP::fold(l[0], l[1], r, aux), l_hi = FP::fold(l[2], l[3], r, aux);
+            const X r_lo = FP::fold(g[0], g[1], r, aux), r_hi = FP::fold(g[2], g[3], r, aux);
+            nxt[(1 + 2 * k) * half + 2 * b] = l_lo;
+            nxt[(1 + 2 * k) * half + 2 * b + 1] = l_hi;
+            nxt[(2 + 2 * k) * half + 2 * b] = r_lo;
+            nxt[(2 + 2 * k) * half + 2 * b + 1] = r_hi;
+            const X p0 = FP::fmul(l_lo, r_lo), p1 = FP::fmul(FP::slope(l_lo, l_hi), FP::slope(r_lo, r_hi)),
+                    p2 = FP::fmul(FP::at_m1(l_lo, l_hi), FP::at_m1(r_lo, r_hi));
+            acc[0] = FP::x_add(acc[0], FP::fmul(t_lo, p0));
+            acc[1] = FP::x_add(acc[1], FP::fmul(FP::slope(t_lo, t_hi), p1));
+            acc[2] = FP::x_add(acc[2], FP::fmul(FP::at_m1(t_lo, t_hi), p2));
+        }
+        tail_block_sum<FP, 3>(acc, red, it.part + ((size_t)q * ncta + lb) * 3);  // ends with __syncthreads: nxt is complete
+        X* tmp = cur; cur = nxt; nxt = tmp;
+        len = half;
+    }
+    // len = SEG >> K entries per table go back to memory
+    const size_t n_out = n_in >> it.K;
+    for (int e = threadIdx.x; e < ntab * len; e += blockDim.x) {
+        const int slot = e / len, k = e % len;
+        if (slot == 0 && !(it.write_t0 && grp == 0)) continue;  // t_0 is table 0 = l_0: written by the CTA that owns term 0, or by group 0 when no term 0 here
+        const size_t tab = slot ? (size_t)(2 * i0 + slot - 1) : 0;
+        it.out[tab * n_out + (size_t)seg * len + k] = cur[slot * len + k];
+    }
 }
 
 }  // namespace hg

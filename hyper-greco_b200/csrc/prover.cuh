@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>
 
+#include <array>
 #include <chrono>
 #include <functional>
 #include <memory>
@@ -1388,8 +1389,27 @@ template <class FP> class LassoNodeDev {
             }
         }
         if (pool_off > d_pool_.n) throw std::runtime_error("run_gp_batch: pool too small");
+        // Rounds of layer k: streamed launches r = 1..S_k (r = 0 only without the fused tree builders), then up to HG_GP_MID_STAGES mid
+        // stages of <= 5 rounds each in shared-memory segments (k_gp_mid) once the tables are at most 2^HG_GP_MID_LOG long, then the tail
+        // kernel from 2^GP_TAIL_LOG entries on. Round 1 is always streamed: it scales the tables by c_i.
+        static const int env_mid_log = getenv("HG_GP_MID_LOG") ? atoi(getenv("HG_GP_MID_LOG")) : FP::GP_MID_LOG;
+        static const int env_mid_tpg = getenv("HG_GP_MID_TPG") ? std::max(1, atoi(getenv("HG_GP_MID_TPG"))) : 7;
+        std::vector<int> S(nl, 0);
+        std::vector<std::vector<int>> midK(nl);
         int maxJ = -1;
-        for (auto& j : jobs) if (j.n > ((size_t)1 << FP::GP_TAIL_LOG)) maxJ = std::max(maxJ, j.nv - FP::GP_TAIL_LOG);
+        for (int k = 0; k < nl; k++) {
+            const auto& j = jobs[k];
+            if (j.n <= ((size_t)1 << FP::GP_TAIL_LOG)) continue;
+            const int J = j.nv - FP::GP_TAIL_LOG;  // rounds before the tail
+            S[k] = J;
+            if (env_mid_log > FP::GP_TAIL_LOG && J >= 2) {
+                S[k] = std::max(1, j.nv - env_mid_log);
+                int left = J - S[k];
+                if (left > HG_GP_MID_STAGES * HG_GP_MID_MAXK) { S[k] += left - HG_GP_MID_STAGES * HG_GP_MID_MAXK; left = HG_GP_MID_STAGES * HG_GP_MID_MAXK; }
+                while (left > 0) { const int K = std::min(left, HG_GP_MID_MAXK); midK[k].push_back(K); left -= K; }
+            }
+            maxJ = std::max(maxJ, S[k]);
+        }
         std::vector<std::vector<GpItem<FP>>> rounds(maxJ + 1);
         std::vector<GpItem<FP>> round0a;  // first half of round 0 (k_gp_r0a_multi): own geometry, partials and counters
         size_t round0a_bytes = 0, part0a_off = 0;
@@ -1404,13 +1424,34 @@ template <class FP> class LassoNodeDev {
         static const double env_target = getenv("HG_GP_TARGET") ? atof(getenv("HG_GP_TARGET")) : FP::GP_TARGET;
         const int target_blocks = std::max(1, (int)(ctx_->sm_count * env_target * (HG_BLOCK / FP::GP_BLOCK)));
         const size_t gp_max_bx = (size_t)ctx_->sm_count * env_maxbx * (HG_BLOCK / FP::GP_BLOCK);
+        // Work-balanced shape (HG_GP_BALANCE, default on for fields with GP_BALANCE): a round finishes with its slowest CTA, and a
+        // CTA's time is (terms it loops over) x (positions per thread). With one term group per large layer the late rounds ran
+        // ~1000 CTAs of which the largest layer's looped over all 2m terms while the SMs were half empty (profiles/r2_launch_list.md:
+        // round 5 93 us for 0.3 GB). Here every item gets term groups of about total thread-terms / resident threads, so that the
+        // whole round is one wave of equal CTAs, and the items are placed in the grid heaviest CTA first.
+        static const int env_balance = getenv("HG_GP_BALANCE") ? atoi(getenv("HG_GP_BALANCE")) : FP::GP_BALANCE;
+        static const int env_min_tpg = getenv("HG_GP_MIN_TPG") ? std::max(1, atoi(getenv("HG_GP_MIN_TPG"))) : 4;
+        const size_t resident_threads = (size_t)ctx_->sm_count * FP::GP_MIN_BLOCKS * HG_BLOCK;
         for (int r = 0; r <= maxJ; r++) {
             int blk = 0;
             size_t part_off = 0;
+            // layers that take part in this round, their thread count along the table, and the round's total thread-terms
+            std::vector<int> order;
+            std::vector<size_t> tx(nl, 0);
+            size_t total_tt = 0;
             for (int k = 0; k < nl; k++) {
                 const auto& j = jobs[k];
-                if (j.n <= ((size_t)1 << FP::GP_TAIL_LOG) || r > j.nv - FP::GP_TAIL_LOG) continue;
+                if (j.n <= ((size_t)1 << FP::GP_TAIL_LOG) || r > S[k]) continue;
                 if (r == 0 && j.r0n > 0) continue;  // sampled by the fused tree builders
+                tx[k] = r == 0 ? (j.n / 2 + FP::GP_R0_U - 1) / FP::GP_R0_U : (j.n >> (r - 1)) / 4;
+                total_tt += std::min(tx[k], gp_max_bx * FP::GP_BLOCK) * (size_t)(own_end(j.nvec) - own_begin(j.nvec));
+                order.push_back(k);
+            }
+            const size_t tpg_bal = std::max<size_t>((size_t)env_min_tpg, (total_tt + resident_threads - 1) / resident_threads);
+            if (env_balance && r >= 1)  // heaviest CTAs first: longer table (more positions per thread, the same term count) first
+                std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return tx[a] > tx[b]; });
+            for (int k : order) {
+                const auto& j = jobs[k];
                 GpItem<FP> it;
                 const int ntab = 2 * j.nvec;
                 it.nvec = j.nvec;
@@ -1438,6 +1479,8 @@ template <class FP> class LassoNodeDev {
                 if (b < 1) b = 1;
                 if (b > gp_max_bx) b = gp_max_bx;
                 int g = (int)std::min<size_t>((size_t)nown, std::max<size_t>(1, ((size_t)target_blocks + b - 1) / b));
+                if (env_balance && r >= 1 && tpg_bal * 5 < (size_t)nown * 4)  // (a split that saves less than a fifth of the loop is not worth re-folding t_0)
+                    g = std::max(g, (int)std::max<size_t>(1, (size_t)nown / tpg_bal));  // rounded down: rather one wave of slightly longer CTAs than a second wave
                 it.tpg = (nown + g - 1) / g;
                 it.groups = (nown + it.tpg - 1) / it.tpg;
                 it.bx = (int)b;
@@ -1477,9 +1520,15 @@ template <class FP> class LassoNodeDev {
         if (round0a.size() + 64 > d_gp_counters_.n) throw std::runtime_error("run_gp_batch: too many layers");
         std::vector<GpTailItem<FP>> titems(nl);
         size_t tail_bytes = 0;
+        std::vector<GpMidItem<FP>> mitems[HG_GP_MID_STAGES];
+        std::vector<int> mitem_layer[HG_GP_MID_STAGES];
+        std::vector<std::array<size_t, HG_GP_MID_STAGES>> mid_part_off(nl);
+        int mid_blk[HG_GP_MID_STAGES] = {0, 0, 0}, mid_tpg_max = 1;
+        size_t mid_bytes[HG_GP_MID_STAGES] = {0, 0, 0}, mid_part_need = 0;
         for (int k = 0; k < nl; k++) {
             const auto& j = jobs[k];
             GpTailItem<FP>& t = titems[k];
+            for (int st = 0; st < HG_GP_MID_STAGES; st++) { t.mid_part[st] = nullptr; t.mid_msg[st] = nullptr; t.mid_n[st] = 0; t.mid_K[st] = 0; }
             t.c = coef[k]; t.nvec = j.nvec; t.evals = ch.d_msg(j.evals_off);
             t.i_begin = own_begin(j.nvec); t.i_end = own_end(j.nvec);
             t.r0part = j.r0part; t.r0n = j.r0n;
@@ -1489,14 +1538,46 @@ template <class FP> class LassoNodeDev {
                 tail_bytes += 2 * (size_t)j.nvec * j.n * sizeof(B);
             } else {
                 const int J = j.nv - FP::GP_TAIL_LOG;
-                t.from_base = 0; t.in = (J & 1) ? bufA[k] : bufB[k]; t.n = 1 << FP::GP_TAIL_LOG; t.rounds = FP::GP_TAIL_LOG - 1;
+                // mid stages: in = what the last streamed round (or the previous stage) wrote, out = the other buffer of the layer
+                const X* cur = (S[k] & 1) ? bufA[k] : bufB[k];
+                int rnd = S[k];  // rounds done so far
+                const int nown = t.i_end - t.i_begin;
+                for (size_t st = 0; st < midK[k].size(); st++) {
+                    GpMidItem<FP> mi;
+                    mi.in = cur; mi.out = (cur == bufA[k]) ? bufB[k] : bufA[k];
+                    mi.n_in = j.n >> rnd; mi.K = midK[k][st];
+                    mi.chal = ch.d_chal(j.r0_idx + rnd);
+                    mi.nvec = j.nvec; mi.nseg = (int)(mi.n_in / HG_GP_MID_SEG);
+                    mi.tpg = std::min(nown, env_mid_tpg); mi.groups = (nown + mi.tpg - 1) / mi.tpg;
+                    mi.i_begin = t.i_begin; mi.i_end = t.i_end; mi.write_t0 = t.i_begin > 0;
+                    const int ncta = mi.nseg * mi.groups;
+                    mi.blk_start = mid_blk[st]; mid_blk[st] += ncta;
+                    mi.part = nullptr;  // assigned below
+                    mid_part_off[k][st] = mid_part_need; mid_part_need += (size_t)mi.K * ncta * 3;
+                    t.mid_n[st] = ncta; t.mid_K[st] = mi.K; t.mid_msg[st] = ch.d_msg(j.msg_off + 4 + 3 * (size_t)rnd);
+                    mid_bytes[st] += (size_t)(2 * nown + mi.write_t0) * (mi.n_in + (mi.n_in >> mi.K)) * sizeof(X);
+                    mid_tpg_max = std::max(mid_tpg_max, mi.tpg);
+                    mitems[st].push_back(mi);
+                    mitem_layer[st].push_back(k);
+                    cur = mi.out; rnd += mi.K;
+                }
+                if (rnd != J) throw std::runtime_error("run_gp_batch: round plan does not reach the tail");
+                t.from_base = 0; t.in = cur; t.n = 1 << FP::GP_TAIL_LOG; t.rounds = FP::GP_TAIL_LOG - 1;
                 t.chal = ch.d_chal(j.r0_idx + J); t.msg0 = ch.d_msg(j.msg_off); t.msg = ch.d_msg(j.msg_off + 4 + 3 * (size_t)J);
                 tail_bytes += 2 * (size_t)j.nvec * ((size_t)1 << FP::GP_TAIL_LOG) * sizeof(X);
             }
         }
+        if (mid_part_need > d_gp_midpart_.n) { HG_CUDA(cudaStreamSynchronize(s)); d_gp_midpart_.alloc(mid_part_need * 2); }
+        for (int st = 0; st < HG_GP_MID_STAGES; st++)
+            for (size_t q = 0; q < mitems[st].size(); q++) {
+                const int k = mitem_layer[st][q];
+                mitems[st][q].part = d_gp_midpart_.p + mid_part_off[k][st];
+                titems[k].mid_part[st] = mitems[st][q].part;
+            }
         // upload descriptors
         size_t bytes = titems.size() * sizeof(GpTailItem<FP>);
         for (auto& rv : rounds) bytes += rv.size() * sizeof(GpItem<FP>) + 16;
+        for (auto& mv : mitems) bytes += mv.size() * sizeof(GpMidItem<FP>) + 16;
         bytes += round0a.size() * sizeof(GpItem<FP>) + 64;
         if (h_desc_.n < bytes) { h_desc_.alloc(bytes * 2); d_desc_.alloc(bytes * 2); }
         unsigned char* hp = h_desc_.p;
@@ -1506,6 +1587,8 @@ template <class FP> class LassoNodeDev {
         for (size_t r = 0; r < rounds.size(); r++) r_off[r] = put(rounds[r].data(), rounds[r].size() * sizeof(GpItem<FP>));
         size_t t_off = put(titems.data(), titems.size() * sizeof(GpTailItem<FP>));
         size_t a_off = put(round0a.data(), round0a.size() * sizeof(GpItem<FP>));
+        size_t m_off[HG_GP_MID_STAGES];
+        for (int st = 0; st < HG_GP_MID_STAGES; st++) m_off[st] = put(mitems[st].data(), mitems[st].size() * sizeof(GpMidItem<FP>));
         if (off > h_desc_.n) throw std::runtime_error("run_gp_batch: descriptor staging overflow");
         HG_CUDA(cudaMemcpyAsync(d_desc_.p, h_desc_.p, off, cudaMemcpyHostToDevice, s));
         // launches
@@ -1523,6 +1606,17 @@ template <class FP> class LassoNodeDev {
             if (r == 0) k_gp_r0_multi<FP, FP::GP_R0_U><<<grid, FP::GP_BLOCK, 0, s>>>(di, ni);
             else if (r == 1) k_gp_fold_multi<FP, B, true><<<grid, FP::GP_BLOCK, 0, s>>>(di, ni);
             else k_gp_fold_multi<FP, X, false><<<grid, FP::GP_BLOCK, 0, s>>>(di, ni);
+            HG_LAUNCH_CHECK();
+        }
+        for (int st = 0; st < HG_GP_MID_STAGES; st++) {
+            if (mitems[st].empty()) continue;
+            const size_t smem = gp_mid_smem<FP>(mid_tpg_max);
+            if (smem > gp_mid_smem_set_) {
+                HG_CUDA(cudaFuncSetAttribute(k_gp_mid<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                gp_mid_smem_set_ = smem;
+            }
+            KernelScope ks(ctx_, KC_SC_GP, mid_bytes[st]);
+            k_gp_mid<FP><<<mid_blk[st], HG_GP_MID_THREADS, smem, s>>>((const GpMidItem<FP>*)(d_desc_.p + m_off[st]), (int)mitems[st].size());
             HG_LAUNCH_CHECK();
         }
         {
@@ -1580,7 +1674,8 @@ template <class FP> class LassoNodeDev {
     DevBuf<X> d_eq_, d_gp_coeffs_, d_bufA_, d_bufB_, d_partials_, d_coll_terms_;
     int coll_coeff_state_ = 0;  // 0 not uploaded, 1 ascending, 2 descending
     DevBuf<unsigned> d_counters_, d_gp_counters_;
-    DevBuf<X> d_pool_, d_gp_partials_, d_r0part_, d_midpart_;
+    DevBuf<X> d_pool_, d_gp_partials_, d_r0part_, d_midpart_, d_gp_midpart_;
+    size_t gp_mid_smem_set_ = 48 * 1024;  // largest dynamic shared memory k_gp_mid has been allowed so far
     size_t r0_used_ = 0;
     DevBuf<unsigned char> d_desc_, d_cdesc_;
     PinnedBuf<unsigned char> h_desc_, h_cdesc_;
