@@ -531,6 +531,7 @@ struct FrField {
     static constexpr int GP_TAIL_LOG = 5, GP_MIN_BLOCKS = 1, GP_R0_U = 2, GP_R0A_QPT = 1, GP_BLOCK = 256;
     static constexpr int FUSED_MIN_BLOCKS = 2;
     static constexpr int GP_MID_LOG = 0;
+    static constexpr int GP_TAIL_GROUPS = 4;
     static constexpr int GP_BALANCE = 0;
     static constexpr double GP_TARGET = 2.0;
     HG_HD static B b_zero() { return fr_zero(); }

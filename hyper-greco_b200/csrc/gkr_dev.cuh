@@ -117,6 +117,26 @@ template <class FP> class GkrCircuitDev {
                         ro[fill[x]] = (uint32_t)(r * ng + g); rc[fill[x]] = addc[e]; fill[x]++;
                     }
             up(n.rev_ptr, rp); up(n.rev_out, ro); up(n.rev_coef, rc);
+            // piecewise-identity wiring (k_wiring_runs): maximal runs of elements with one reader each, consecutive outputs, one coefficient
+            static const bool env_runs = getenv("HG_WIRE_RUNS") ? atoi(getenv("HG_WIRE_RUNS")) != 0 : true;
+            bool compressible = env_runs;
+            typedef typename Node::WireRun WireRun;
+            for (size_t x = 0; compressible && x < S; x++) {
+                const uint64_t deg = rp[x + 1] - rp[x];
+                if (deg > 1) { compressible = false; break; }
+                WireRun* last = n.wire_runs.empty() ? nullptr : &n.wire_runs.back();
+                if (deg == 0) {
+                    if (last && last->kind == 0) last->len++;
+                    else n.wire_runs.push_back(WireRun{x, 1, 0, 0, FP::b_zero()});
+                } else {
+                    const uint32_t o = ro[rp[x]];
+                    const B c = rc[rp[x]];
+                    if (last && last->kind != 0 && (uint64_t)last->out0 + last->len == o && FP::b_eq(last->coef, c)) last->len++;
+                    else n.wire_runs.push_back(WireRun{x, 1, o, FP::b_eq(c, FP::b_one()) ? 1 : 2, c});
+                }
+                if (n.wire_runs.size() > 4096) compressible = false;  // not worth a descriptor per run
+            }
+            if (!compressible) n.wire_runs.clear();
             if (n.has_consts) {
                 std::vector<B> cf(n.out_len, FP::b_zero());
                 for (size_t r = 0; r < d.num_reps; r++) for (size_t g = 0; g < ng; g++) cf[r * ng + g] = cg[g];
@@ -404,6 +424,8 @@ template <class FP> class GkrCircuitDev {
         bool fft_inverse = false, is_linear = false, is_elemmul = false, has_consts = false;
         size_t ng = 0, out_len = 0, n_in = 0, a_pad = 1;
         std::vector<int> preds, succs;
+        struct WireRun { uint64_t x0, len; uint32_t out0; int kind; B coef; };
+        std::vector<WireRun> wire_runs;  // non-empty: the reverse wiring is piecewise the identity (k_wiring_runs)
         DevBuf<u64> add_ptr, add_wire, mul_ptr, mul_w0, mul_w1, rev_ptr;
         DevBuf<u32> add_in, mul_in0, mul_in1, rev_out;
         DevBuf<B> add_coef, mul_coef, consts, consts_full, rev_coef, value;
@@ -592,6 +614,9 @@ template <class FP> class GkrCircuitDev {
         std::vector<X*> fft_fwd, fft_inv;  // W tables whose transform is needed, grouped by size via a map below
         std::map<std::pair<int, int>, std::vector<int>> fft_groups;  // (log2 size, inverse) -> node ids
         std::vector<WiringItem<FP>> wires;
+        std::vector<WireRunItem<FP>> runs;
+        int run_blk = 0;
+        size_t run_bytes = 0;
         std::vector<ConcatItem<FP>> cats;
         int wire_blk = 0, cat_blk = 0;
         size_t wire_bytes = 0, cat_bytes = 0;
@@ -611,18 +636,29 @@ template <class FP> class GkrCircuitDev {
                 continue;
             }
             const size_t S = n.a_pad * n.n_in;
+            if (!n.wire_runs.empty()) {
+                for (const typename Node::WireRun& r : n.wire_runs) {
+                    WireRunItem<FP> ri; ri.w = n.W.p + r.out0; ri.A = n.A.p + r.x0; ri.n = r.len; ri.coef = r.coef; ri.kind = r.kind; ri.blk_start = run_blk;
+                    run_blk += (int)((r.len + HG_BLOCK * HG_WIRERUN_PER_THREAD - 1) / (HG_BLOCK * HG_WIRERUN_PER_THREAD));
+                    runs.push_back(ri);
+                }
+                run_bytes += S * sizeof(X) * 2;
+            } else {
             WiringItem<FP> wi; wi.rev_ptr = n.rev_ptr.p; wi.rev_out = n.rev_out.p; wi.rev_coef = n.rev_coef.p; wi.w = n.W.p; wi.A = n.A.p; wi.n = S; wi.blk_start = wire_blk;
             wire_blk += (int)((S + HG_BLOCK * HG_WIRING_PER_THREAD - 1) / (HG_BLOCK * HG_WIRING_PER_THREAD));
             wire_bytes += S * sizeof(X) * 2;
             wires.push_back(wi);
+            }
             if (n.a_pad != (size_t)n.arity) cat(nullptr, n.Xcat.p + (size_t)n.arity * n.n_in, (n.a_pad - n.arity) * n.n_in);
-            for (int k = 0; k < n.arity; k++) cat(nodes_[n.preds.at(k)]->value_ptr, n.Xcat.p + (size_t)k * n.n_in, n.n_in);
+            if (n.arity > 1)  // a single input IS the concatenation: the sumcheck reads it in place (tables())
+                for (int k = 0; k < n.arity; k++) cat(nodes_[n.preds.at(k)]->value_ptr, n.Xcat.p + (size_t)k * n.n_in, n.n_in);
             if (n.has_consts) {
                 int blocks = (int)std::min<size_t>((n.out_len + HG_BLOCK - 1) / HG_BLOCK, (size_t)ctx_->sm_count * 2);
                 HG_K(ctx_, KC_GKR_PREP, n.out_len * (sizeof(X) + sizeof(B)),
                      k_dot_wconst<FP><<<blocks, HG_BLOCK, 0, s>>>(n.W.p, n.consts_full.p, n.out_len, d_partials_.p, d_counters_.p, ch.d_msg(j.const_off)));
             }
         }
+        if (!runs.empty()) HG_K(ctx_, KC_GKR_PREP, run_bytes, k_wiring_runs<FP><<<run_blk, HG_BLOCK, 0, s>>>(stage(runs), (int)runs.size()));
         if (!wires.empty()) HG_K(ctx_, KC_GKR_PREP, wire_bytes, k_wiring_gather<FP><<<wire_blk, HG_BLOCK, 0, s>>>(stage(wires), (int)wires.size()));
         if (!cats.empty()) HG_K(ctx_, KC_GKR_PREP, cat_bytes, k_concat_items<FP><<<cat_blk, HG_BLOCK, 0, s>>>(stage(cats), (int)cats.size()));
         // FFT-matrix weights: A = transform(W) plane by plane, batched over all FFT nodes of the same size and direction
@@ -643,7 +679,10 @@ template <class FP> class GkrCircuitDev {
     }
 
     const X* weights(const Node& n) const { return n.kind == GKR_VANILLA && n.is_elemmul ? n.W.p : n.A.p; }
-    const B* tables(const Node& n) const { return n.kind == GKR_FFT ? nodes_[n.preds.at(0)]->value_ptr : n.Xcat.p; }
+    const B* tables(const Node& n) const {
+        if (n.kind == GKR_FFT || (n.kind == GKR_VANILLA && n.is_linear && n.arity == 1)) return nodes_[n.preds.at(0)]->value_ptr;
+        return n.Xcat.p;
+    }
 
     // round r of every job that still has one
     void launch_round(Channel<FP>& ch, const std::vector<Job>& jobs, int r) {

@@ -127,6 +127,42 @@ template <class FP> __global__ void k_wiring_gather(const WiringItem<FP>* __rest
         it.A[x] = FP::xacc_reduce_(acc);
     }
 }
+// Linear layers whose reverse wiring is piecewise the identity: every input element feeds at most one output and consecutive elements
+// feed consecutive outputs with the same coefficient (the relay / scale / shift / sum layers of sk_encryption_circuit.rs:97-285). Then
+// A = coef * W run by run, streamed, instead of chasing rev_ptr -> rev_out -> W per element (k_wiring_gather: 228 us, 0.44 GB of
+// index reads per proof, profiles/r2_launch_list.md). Same products, same reduction: identical field elements.
+template <class FP> struct WireRunItem {
+    const typename FP::X* w;  // W + first output of the run
+    typename FP::X* A;        // A + first input element of the run
+    u64 n;
+    typename FP::B coef;
+    int kind;                 // 0: elements that feed nothing (zeros), 1: coefficient one (copy), 2: scaled
+    int blk_start;
+};
+constexpr int HG_WIRERUN_PER_THREAD = 4;
+template <class FP> __global__ void k_wiring_runs(const WireRunItem<FP>* __restrict__ items, int nitems) {
+    typedef typename FP::X X;
+    const WireRunItem<FP> it = items[find_item(items, nitems)];
+    const size_t base = (size_t)(blockIdx.x - it.blk_start) * blockDim.x * HG_WIRERUN_PER_THREAD + threadIdx.x;
+    X v[HG_WIRERUN_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < HG_WIRERUN_PER_THREAD; k++) {
+        const size_t i = base + (size_t)k * blockDim.x;
+        v[k] = FP::x_zero();
+        if (it.kind != 0 && i < it.n) v[k] = it.w[i];
+    }
+#pragma unroll
+    for (int k = 0; k < HG_WIRERUN_PER_THREAD; k++) {
+        const size_t i = base + (size_t)k * blockDim.x;
+        if (i >= it.n) continue;
+        if (it.kind == 2) {
+            typename FP::XAcc acc = FP::xacc_zero_();
+            FP::xacc_mad_b(acc, v[k], it.coef);
+            v[k] = FP::xacc_reduce_(acc);
+        }
+        it.A[i] = v[k];
+    }
+}
 // concatenated input tables of the layer sumchecks: dst[0..n) = src[0..n) (src = nullptr: zeros), every node's pieces in one launch
 template <class FP> struct ConcatItem { const typename FP::B* src; typename FP::B* dst; u64 n; int blk_start; };
 constexpr int HG_CONCAT_PER_THREAD = 8;

@@ -194,7 +194,8 @@ namespace hg {
 
 // table length at which a layer moves to the shared-memory tail kernel: FP::GP_TAIL_LOG (64 elements of 16 B for
 // Goldilocks, 32 elements of 32 B for BN254: 2*m tables * 1.5 * that must fit 227 KB)
-constexpr int HG_TAIL_THREADS = 512;
+constexpr int HG_TAIL_THREADS = 256;
+constexpr int HG_GP_TAIL_MAXR = 10;  // most rounds the tail kernel runs (tables of up to 2^11 entries)
 // threads per CTA of the batched streaming kernels: FP::GP_BLOCK (128 for Goldilocks: same registers per thread, twice the CTAs
 // per SM, 3 % faster; 256 for BN254)
 #ifndef HG_GP_PREFETCH
@@ -504,6 +505,10 @@ template <class FP> struct GpTailItem {
     const typename FP::X* mid_part[HG_GP_MID_STAGES];
     typename FP::X* mid_msg[HG_GP_MID_STAGES];
     int mid_n[HG_GP_MID_STAGES], mid_K[HG_GP_MID_STAGES];
+    // the layer's terms are split over `groups` CTAs of tpg terms; gpart: [groups][1 + HG_GP_TAIL_MAXR][4] partial sums
+    int tpg, groups;
+    typename FP::X* gpart;
+    unsigned* counter;
 };
 
 template <class FP, int NP>
@@ -530,61 +535,79 @@ __device__ __forceinline__ void tail_block_sum(typename FP::X (&acc)[NP], typena
     __syncthreads();
 }
 
-template <class FP> __global__ void __launch_bounds__(HG_TAIL_THREADS) k_gp_tail(const GpTailItem<FP>* __restrict__ items) {
+// One layer is split over `groups` CTAs by terms (h is linear in them): CTA g keeps its own copy of t_0 (slot 0) and the tables of
+// its terms (slots 1 + 2k, 2 + 2k = l, r of term i0 + k) in shared memory, writes its partial sums per round to gpart, and the last
+// CTA of the layer to finish (counter) adds the groups up into the message slots. One CTA per layer took 60 us for 35 layers
+// (profiles/r2_launch_list.md): a serial chain of rounds with 2 (term, pair) items per thread in its first round.
+template <class FP> __global__ void __launch_bounds__(HG_TAIL_THREADS) k_gp_tail(const GpTailItem<FP>* __restrict__ items, int max_groups) {
     typedef typename FP::B B;
     typedef typename FP::X X;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const GpTailItem<FP> it = items[blockIdx.x];
-    const int ntab = 2 * it.nvec;
-    constexpr int TAIL = 1 << FP::GP_TAIL_LOG;
-    X* A = reinterpret_cast<X*>(smem_raw);          // [ntab][TAIL]
-    X* Bf = A + (size_t)ntab * TAIL;                // [ntab][TAIL/2]
-    X* red = Bf + (size_t)ntab * (TAIL / 2);        // [32][4]
+    __shared__ bool is_last;
+    const GpTailItem<FP> it = items[blockIdx.x / max_groups];
+    const int g = blockIdx.x % max_groups;
+    if (g >= it.groups) return;
+    const int i0 = it.i_begin + g * it.tpg, i1 = min(it.i_end, i0 + it.tpg);
+    const int nt = i1 - i0, ntab = 1 + 2 * nt, cap = 1 + 2 * it.tpg;
     int len = it.n;
+    X* A = reinterpret_cast<X*>(smem_raw);        // [cap][n]
+    X* Bf = A + (size_t)cap * len;                 // [cap][n / 2]
+    X* red = Bf + (size_t)cap * (len / 2);         // [32][4]
+    X* gpart = it.gpart + (size_t)g * (HG_GP_TAIL_MAXR + 1) * 4;  // [1 + rounds][4]: slot 0 = round 0 (from_base), slot 1 + rd = tail round rd
     if (it.from_base) {
         const B* base = (const B*)it.in;  // vector i = [l_i (n) | r_i (n)] -> tables 2i, 2i+1 are consecutive runs of n
-        for (int e = threadIdx.x; e < ntab * len; e += blockDim.x) A[e] = FP::lift(base[e]);
+        for (int e = threadIdx.x; e < ntab * len; e += blockDim.x) {
+            const int slot = e / len, k = e % len;
+            const size_t tab = slot ? (size_t)(2 * i0 + slot - 1) : 0;
+            A[e] = FP::lift(base[tab * len + k]);
+        }
         __syncthreads();
         // round 0 on the unscaled tables: h(0), h(inf), h(-1), h(1)
         X acc[4] = {FP::x_zero(), FP::x_zero(), FP::x_zero(), FP::x_zero()};
         const int npairs = len / 2;
-        for (int e = threadIdx.x; e < (it.i_end - it.i_begin) * npairs; e += blockDim.x) {
-            const int i = it.i_begin + e / npairs, b = e % npairs;
+        for (int e = threadIdx.x; e < nt * npairs; e += blockDim.x) {
+            const int k = e / npairs, b = e % npairs;
             const X t_lo = A[2 * b], t_hi = A[2 * b + 1];
-            const X l_lo = A[(2 * i) * len + 2 * b], l_hi = A[(2 * i) * len + 2 * b + 1];
-            const X r_lo = A[(2 * i + 1) * len + 2 * b], r_hi = A[(2 * i + 1) * len + 2 * b + 1];
-            const X ci = it.c[i];
+            const X l_lo = A[(1 + 2 * k) * len + 2 * b], l_hi = A[(1 + 2 * k) * len + 2 * b + 1];
+            const X r_lo = A[(2 + 2 * k) * len + 2 * b], r_hi = A[(2 + 2 * k) * len + 2 * b + 1];
+            const X ci = it.c[i0 + k];
             acc[0] = FP::x_add(acc[0], FP::fmul(FP::fmul(ci, t_lo), FP::fmul(l_lo, r_lo)));
             acc[1] = FP::x_add(acc[1], FP::fmul(FP::fmul(ci, FP::slope(t_lo, t_hi)), FP::fmul(FP::slope(l_lo, l_hi), FP::slope(r_lo, r_hi))));
             acc[2] = FP::x_add(acc[2], FP::fmul(FP::fmul(ci, FP::at_m1(t_lo, t_hi)), FP::fmul(FP::at_m1(l_lo, l_hi), FP::at_m1(r_lo, r_hi))));
             acc[3] = FP::x_add(acc[3], FP::fmul(FP::fmul(ci, t_hi), FP::fmul(l_hi, r_hi)));
         }
-        tail_block_sum<FP, 4>(acc, red, it.msg0);
-        // pre-scale l_i by c_i (i > 0) and r_0 by c_0, as round 1 of the streaming kernels does
-        for (int e = threadIdx.x; e < it.nvec * len; e += blockDim.x) {
-            const int i = e / len, k = e % len, tab = i ? 2 * i : 1;
-            A[tab * len + k] = FP::fmul(A[tab * len + k], it.c[i]);
+        tail_block_sum<FP, 4>(acc, red, gpart);
+        // pre-scale l_i by c_i (i > 0) and r_0 by c_0, as round 1 of the streaming kernels does (slot 0, the copy of t_0, stays)
+        for (int e = threadIdx.x; e < nt * len; e += blockDim.x) {
+            const int k = e / len, q = e % len, i = i0 + k, slot = i ? 1 + 2 * k : 2 + 2 * k;
+            A[slot * len + q] = FP::fmul(A[slot * len + q], it.c[i]);
         }
         __syncthreads();
     } else {
         const X* src = (const X*)it.in;
-        for (int e = threadIdx.x; e < ntab * len; e += blockDim.x) A[e] = src[e];
-        if (it.r0n > 0) {  // round 0 was sampled while the tree was built: add up the CTA partials
-            X acc[4] = {FP::x_zero(), FP::x_zero(), FP::x_zero(), FP::x_zero()};
-            for (int b = threadIdx.x; b < it.r0n; b += blockDim.x)
-#pragma unroll
-                for (int p = 0; p < 4; p++) acc[p] = FP::x_add(acc[p], it.r0part[(size_t)b * 4 + p]);
-            tail_block_sum<FP, 4>(acc, red, it.msg0);
+        for (int e = threadIdx.x; e < ntab * len; e += blockDim.x) {
+            const int slot = e / len, k = e % len;
+            const size_t tab = slot ? (size_t)(2 * i0 + slot - 1) : 0;
+            A[e] = src[tab * len + k];
         }
-        for (int st = 0; st < HG_GP_MID_STAGES; st++)  // rounds that ran in mid stages: add up the CTA partials of every round
-            for (int q = 0; q < it.mid_K[st]; q++) {
-                X acc[3] = {FP::x_zero(), FP::x_zero(), FP::x_zero()};
-                const X* part = it.mid_part[st] + (size_t)q * it.mid_n[st] * 3;
-                for (int b = threadIdx.x; b < it.mid_n[st]; b += blockDim.x)
+        if (g == 0) {
+            if (it.r0n > 0) {  // round 0 was sampled while the tree was built: add up the CTA partials
+                X acc[4] = {FP::x_zero(), FP::x_zero(), FP::x_zero(), FP::x_zero()};
+                for (int b = threadIdx.x; b < it.r0n; b += blockDim.x)
 #pragma unroll
-                    for (int p = 0; p < 3; p++) acc[p] = FP::x_add(acc[p], part[(size_t)b * 3 + p]);
-                tail_block_sum<FP, 3>(acc, red, it.mid_msg[st] + 3 * q);
+                    for (int p = 0; p < 4; p++) acc[p] = FP::x_add(acc[p], it.r0part[(size_t)b * 4 + p]);
+                tail_block_sum<FP, 4>(acc, red, it.msg0);
             }
+            for (int st = 0; st < HG_GP_MID_STAGES; st++)  // rounds that ran in mid stages: add up the CTA partials of every round
+                for (int q = 0; q < it.mid_K[st]; q++) {
+                    X acc[3] = {FP::x_zero(), FP::x_zero(), FP::x_zero()};
+                    const X* part = it.mid_part[st] + (size_t)q * it.mid_n[st] * 3;
+                    for (int b = threadIdx.x; b < it.mid_n[st]; b += blockDim.x)
+#pragma unroll
+                        for (int p = 0; p < 3; p++) acc[p] = FP::x_add(acc[p], part[(size_t)b * 3 + p]);
+                    tail_block_sum<FP, 3>(acc, red, it.mid_msg[st] + 3 * q);
+                }
+        }
         __syncthreads();
     }
     X* cur = A;
@@ -594,41 +617,61 @@ template <class FP> __global__ void __launch_bounds__(HG_TAIL_THREADS) k_gp_tail
         const typename FP::FoldAux aux = FP::fold_aux(r);
         const int npairs = len / 4, half = len / 2;
         X acc[3] = {FP::x_zero(), FP::x_zero(), FP::x_zero()};
-        if (it.i_begin > 0)  // t_0's table is folded on every device
-            for (int b = threadIdx.x; b < npairs; b += blockDim.x) {
-                const X* t = cur + 4 * b;
-                nxt[2 * b] = FP::fold(t[0], t[1], r, aux);
-                nxt[2 * b + 1] = FP::fold(t[2], t[3], r, aux);
-            }
-        for (int e = threadIdx.x; e < (it.i_end - it.i_begin) * npairs; e += blockDim.x) {
-            const int i = it.i_begin + e / npairs, b = e % npairs;
+        for (int b = threadIdx.x; b < npairs; b += blockDim.x) {  // this CTA's copy of t_0
             const X* t = cur + 4 * b;
-            const X* l = cur + (2 * i) * len + 4 * b;
-            const X* q = cur + (2 * i + 1) * len + 4 * b;
+            nxt[2 * b] = FP::fold(t[0], t[1], r, aux);
+            nxt[2 * b + 1] = FP::fold(t[2], t[3], r, aux);
+        }
+        for (int e = threadIdx.x; e < nt * npairs; e += blockDim.x) {
+            const int k = e / npairs, b = e % npairs;
+            const X* t = cur + 4 * b;
+            const X* l = cur + (1 + 2 * k) * len + 4 * b;
+            const X* q = cur + (2 + 2 * k) * len + 4 * b;
             const X t_lo = FP::fold(t[0], t[1], r, aux), t_hi = FP::fold(t[2], t[3], r, aux);
             const X l_lo = FP::fold(l[0], l[1], r, aux), l_hi = FP::fold(l[2], l[3], r, aux);
             const X r_lo = FP::fold(q[0], q[1], r, aux), r_hi = FP::fold(q[2], q[3], r, aux);
-            nxt[(2 * i) * half + 2 * b] = l_lo;
-            nxt[(2 * i) * half + 2 * b + 1] = l_hi;
-            nxt[(2 * i + 1) * half + 2 * b] = r_lo;
-            nxt[(2 * i + 1) * half + 2 * b + 1] = r_hi;
+            nxt[(1 + 2 * k) * half + 2 * b] = l_lo;
+            nxt[(1 + 2 * k) * half + 2 * b + 1] = l_hi;
+            nxt[(2 + 2 * k) * half + 2 * b] = r_lo;
+            nxt[(2 + 2 * k) * half + 2 * b + 1] = r_hi;
             const X p0 = FP::fmul(l_lo, r_lo), p1 = FP::fmul(FP::slope(l_lo, l_hi), FP::slope(r_lo, r_hi)),
                     p2 = FP::fmul(FP::at_m1(l_lo, l_hi), FP::at_m1(r_lo, r_hi));
             acc[0] = FP::x_add(acc[0], FP::fmul(t_lo, p0));
             acc[1] = FP::x_add(acc[1], FP::fmul(FP::slope(t_lo, t_hi), p1));
             acc[2] = FP::x_add(acc[2], FP::fmul(FP::at_m1(t_lo, t_hi), p2));
         }
-        tail_block_sum<FP, 3>(acc, red, it.msg + 3 * rd);  // ends with __syncthreads: nxt is complete
+        tail_block_sum<FP, 3>(acc, red, gpart + (size_t)(1 + rd) * 4);  // ends with __syncthreads: nxt is complete
         X* tmp = cur; cur = nxt; nxt = tmp;
         len = half;
     }
-    // len == 2: final evaluations
-    const X r = it.chal[it.rounds];
-    const typename FP::FoldAux aux = FP::fold_aux(r);
-    for (int t = 2 * it.i_begin + threadIdx.x; t < 2 * it.i_end; t += blockDim.x) it.evals[t] = FP::fold(cur[2 * t], cur[2 * t + 1], r, aux);
+    // len == 2: final evaluations of this CTA's tables
+    {
+        const X r = it.chal[it.rounds];
+        const typename FP::FoldAux aux = FP::fold_aux(r);
+        for (int s = 1 + threadIdx.x; s < ntab; s += blockDim.x) it.evals[2 * i0 + s - 1] = FP::fold(cur[2 * s], cur[2 * s + 1], r, aux);
+    }
+    // the last CTA of the layer adds the groups up
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned t = atomicAdd(it.counter, 1u);
+        is_last = (t == (unsigned)it.groups - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int e = threadIdx.x; e < (1 + it.rounds) * 4; e += blockDim.x) {
+        const int slot = e / 4, p = e % 4;
+        if (slot == 0 ? !it.from_base : p == 3) continue;
+        X v = FP::x_zero();
+        for (int q = 0; q < it.groups; q++) v = FP::x_add(v, FP::x_ldcg(it.gpart + ((size_t)q * (HG_GP_TAIL_MAXR + 1) + slot) * 4 + p));
+        if (slot == 0) it.msg0[p] = v; else it.msg[3 * (slot - 1) + p] = v;
+    }
+    if (threadIdx.x == 0) *it.counter = 0;
 }
 
+}  // namespace hg
 
+namespace hg {
 // ---- mid stage: K (<= 5) consecutive rounds of a layer in ONE launch, for the rounds whose tables are too short to fill the GPU
 // (profiles/r2_launch_list.md: the streamed rounds 8..14 take 11-26 us each for < 30 MB). Folding pairs (2b, 2b+1) is local to a
 // segment of 2^K consecutive entries, so a CTA that owns HG_GP_MID_SEG = 64 consecutive entries of its tables runs the K rounds in

@@ -784,13 +784,21 @@ template <class FP> class LassoNodeDev {
         h_desc_.alloc(1 << 16);
         d_desc_.alloc(1 << 16);
         {
-            const size_t tail_smem = (size_t)2 * (2 * m_) * ((1 << FP::GP_TAIL_LOG) + (1 << FP::GP_TAIL_LOG) / 2) * sizeof(X) + 32 * 4 * sizeof(X);
+            // grand-product tail kernel: tables of at most 2^tail_log_ entries, every layer split over tail_groups_ CTAs by terms
+            tail_log_ = getenv("HG_GP_TAIL_LOG") ? atoi(getenv("HG_GP_TAIL_LOG")) : FP::GP_TAIL_LOG;
+            tail_groups_ = getenv("HG_GP_TAIL_GROUPS") ? atoi(getenv("HG_GP_TAIL_GROUPS")) : FP::GP_TAIL_GROUPS;
+            if (tail_log_ < 2 || tail_log_ > HG_GP_TAIL_MAXR + 1) throw std::runtime_error("LassoNode: HG_GP_TAIL_LOG out of range");
+            tail_groups_ = std::max(1, std::min(tail_groups_, 2 * m_));
             int smem_max = 0;
             HG_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-            if (tail_smem > (size_t)smem_max)
-                throw std::runtime_error("LassoNode: " + std::to_string(m_) + " memories need " + std::to_string(tail_smem) + " bytes of shared memory in the grand-product tail kernel, the device offers " +
-                                         std::to_string(smem_max) + " (at most " + std::to_string((smem_max - 32 * 4 * sizeof(X)) / (6 * ((size_t)1 << FP::GP_TAIL_LOG) * sizeof(X))) + " memories for this field)");
-            HG_CUDA(cudaFuncSetAttribute(k_gp_tail<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
+            while (gp_tail_smem(tail_groups_) > (size_t)smem_max && tail_groups_ < 2 * m_) tail_groups_++;  // more groups = fewer tables per CTA
+            if (gp_tail_smem(tail_groups_) > (size_t)smem_max)
+                throw std::runtime_error("LassoNode: the grand-product tail kernel needs " + std::to_string(gp_tail_smem(tail_groups_)) + " bytes of shared memory, the device offers " +
+                                         std::to_string(smem_max) + " (lower HG_GP_TAIL_LOG)");
+            HG_CUDA(cudaFuncSetAttribute(k_gp_tail<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gp_tail_smem(tail_groups_)));
+            d_gp_tailpart_.alloc((size_t)(num_vars_ + log2M_ + 2) * tail_groups_ * (HG_GP_TAIL_MAXR + 1) * 4);
+            d_gp_tailcnt_.alloc((size_t)(num_vars_ + log2M_ + 2));
+            HG_CUDA(cudaMemset(d_gp_tailcnt_.p, 0, d_gp_tailcnt_.bytes()));
         }
         max_blocks_ = ctx->sm_count * 8;
         size_t batch = std::max<size_t>((size_t)m_, pp.C);
@@ -1184,7 +1192,12 @@ template <class FP> class LassoNodeDev {
     // a grand product whose launches were deferred (prefetch mode): what build_tree needs
     struct GpPlan { B* tree = nullptr; size_t N = 0; int nvars = 0; size_t roots_off = 0, ev0_off = 0, job_begin = 0; bool level1_done = false; };
     // does layer k of a tree over vectors of length N get its round 0 from a streaming kernel (tables longer than the tail kernel takes)?
-    static bool gp_needs_r0(size_t N, int k, int nvars) { return k <= nvars - 2 && ((N >> k) / 2) > ((size_t)1 << FP::GP_TAIL_LOG); }
+    bool gp_needs_r0(size_t N, int k, int nvars) const { return k <= nvars - 2 && ((N >> k) / 2) > ((size_t)1 << tail_log_); }
+    // shared memory of k_gp_tail when a layer's 2m terms are split over `groups` CTAs: (1 + 2 tpg) tables of 2^tail_log_ entries + half as many folded
+    size_t gp_tail_smem(int groups) const {
+        const int tpg = (2 * m_ + groups - 1) / groups;
+        return ((size_t)(1 + 2 * tpg) * (((size_t)1 << tail_log_) + ((size_t)1 << tail_log_) / 2) + 32 * 4) * sizeof(X);
+    }
     // position blocks per vector of the fused builders: every CTA ends with a block-level reduction that costs about as much as
     // one pass over its data, so CTAs are long (~16 per SM over the whole launch, at least 8 positions per thread)
     int fused_nxb(size_t work, int nvec) const {
@@ -1382,7 +1395,7 @@ template <class FP> class LassoNodeDev {
         for (int k = 0; k < nl; k++) {
             const auto& j = jobs[k];
             coef[k] = j.coef;
-            if (j.n > ((size_t)1 << FP::GP_TAIL_LOG)) {
+            if (j.n > ((size_t)1 << tail_log_)) {
                 size_t a = 2 * (size_t)j.nvec * (j.n / 2), b = 2 * (size_t)j.nvec * (j.n / 4);
                 bufA[k] = d_pool_.p + pool_off; pool_off += a;
                 bufB[k] = d_pool_.p + pool_off; pool_off += b;
@@ -1399,10 +1412,10 @@ template <class FP> class LassoNodeDev {
         int maxJ = -1;
         for (int k = 0; k < nl; k++) {
             const auto& j = jobs[k];
-            if (j.n <= ((size_t)1 << FP::GP_TAIL_LOG)) continue;
-            const int J = j.nv - FP::GP_TAIL_LOG;  // rounds before the tail
+            if (j.n <= ((size_t)1 << tail_log_)) continue;
+            const int J = j.nv - tail_log_;  // rounds before the tail
             S[k] = J;
-            if (env_mid_log > FP::GP_TAIL_LOG && J >= 2) {
+            if (env_mid_log > tail_log_ && J >= 2) {
                 S[k] = std::max(1, j.nv - env_mid_log);
                 int left = J - S[k];
                 if (left > HG_GP_MID_STAGES * HG_GP_MID_MAXK) { S[k] += left - HG_GP_MID_STAGES * HG_GP_MID_MAXK; left = HG_GP_MID_STAGES * HG_GP_MID_MAXK; }
@@ -1441,7 +1454,7 @@ template <class FP> class LassoNodeDev {
             size_t total_tt = 0;
             for (int k = 0; k < nl; k++) {
                 const auto& j = jobs[k];
-                if (j.n <= ((size_t)1 << FP::GP_TAIL_LOG) || r > S[k]) continue;
+                if (j.n <= ((size_t)1 << tail_log_) || r > S[k]) continue;
                 if (r == 0 && j.r0n > 0) continue;  // sampled by the fused tree builders
                 tx[k] = r == 0 ? (j.n / 2 + FP::GP_R0_U - 1) / FP::GP_R0_U : (j.n >> (r - 1)) / 4;
                 total_tt += std::min(tx[k], gp_max_bx * FP::GP_BLOCK) * (size_t)(own_end(j.nvec) - own_begin(j.nvec));
@@ -1529,15 +1542,23 @@ template <class FP> class LassoNodeDev {
             const auto& j = jobs[k];
             GpTailItem<FP>& t = titems[k];
             for (int st = 0; st < HG_GP_MID_STAGES; st++) { t.mid_part[st] = nullptr; t.mid_msg[st] = nullptr; t.mid_n[st] = 0; t.mid_K[st] = 0; }
+            {
+                const int nown = own_end(j.nvec) - own_begin(j.nvec);
+                t.tpg = std::max(1, (j.nvec + tail_groups_ - 1) / tail_groups_);  // sized for all 2m terms: the shared-memory budget was checked for that
+                t.groups = std::max(1, (nown + t.tpg - 1) / t.tpg);
+                if ((size_t)k >= d_gp_tailcnt_.n) throw std::runtime_error("run_gp_batch: too many layers for the tail scratch");
+                t.gpart = d_gp_tailpart_.p + (size_t)k * tail_groups_ * (HG_GP_TAIL_MAXR + 1) * 4;
+                t.counter = d_gp_tailcnt_.p + k;
+            }
             t.c = coef[k]; t.nvec = j.nvec; t.evals = ch.d_msg(j.evals_off);
             t.i_begin = own_begin(j.nvec); t.i_end = own_end(j.nvec);
             t.r0part = j.r0part; t.r0n = j.r0n;
-            if (j.n <= ((size_t)1 << FP::GP_TAIL_LOG)) {
+            if (j.n <= ((size_t)1 << tail_log_)) {
                 t.from_base = 1; t.in = j.tables; t.n = (int)j.n; t.rounds = j.nv - 1;
                 t.chal = ch.d_chal(j.r0_idx); t.msg0 = ch.d_msg(j.msg_off); t.msg = ch.d_msg(j.msg_off + 4);
                 tail_bytes += 2 * (size_t)j.nvec * j.n * sizeof(B);
             } else {
-                const int J = j.nv - FP::GP_TAIL_LOG;
+                const int J = j.nv - tail_log_;
                 // mid stages: in = what the last streamed round (or the previous stage) wrote, out = the other buffer of the layer
                 const X* cur = (S[k] & 1) ? bufA[k] : bufB[k];
                 int rnd = S[k];  // rounds done so far
@@ -1562,9 +1583,9 @@ template <class FP> class LassoNodeDev {
                     cur = mi.out; rnd += mi.K;
                 }
                 if (rnd != J) throw std::runtime_error("run_gp_batch: round plan does not reach the tail");
-                t.from_base = 0; t.in = cur; t.n = 1 << FP::GP_TAIL_LOG; t.rounds = FP::GP_TAIL_LOG - 1;
+                t.from_base = 0; t.in = cur; t.n = 1 << tail_log_; t.rounds = tail_log_ - 1;
                 t.chal = ch.d_chal(j.r0_idx + J); t.msg0 = ch.d_msg(j.msg_off); t.msg = ch.d_msg(j.msg_off + 4 + 3 * (size_t)J);
-                tail_bytes += 2 * (size_t)j.nvec * ((size_t)1 << FP::GP_TAIL_LOG) * sizeof(X);
+                tail_bytes += 2 * (size_t)j.nvec * ((size_t)1 << tail_log_) * sizeof(X);
             }
         }
         if (mid_part_need > d_gp_midpart_.n) { HG_CUDA(cudaStreamSynchronize(s)); d_gp_midpart_.alloc(mid_part_need * 2); }
@@ -1620,9 +1641,9 @@ template <class FP> class LassoNodeDev {
             HG_LAUNCH_CHECK();
         }
         {
-            const size_t smem = (size_t)2 * (2 * m_) * ((1 << FP::GP_TAIL_LOG) + (1 << FP::GP_TAIL_LOG) / 2) * sizeof(X) + 32 * 4 * sizeof(X);
+            const size_t smem = gp_tail_smem(tail_groups_);
             KernelScope ks(ctx_, KC_SC_GP, tail_bytes);
-            k_gp_tail<FP><<<nl, HG_TAIL_THREADS, smem, s>>>((const GpTailItem<FP>*)(d_desc_.p + t_off));
+            k_gp_tail<FP><<<nl * tail_groups_, HG_TAIL_THREADS, smem, s>>>((const GpTailItem<FP>*)(d_desc_.p + t_off), tail_groups_);
             HG_LAUNCH_CHECK();
         }
     }
@@ -1674,7 +1695,9 @@ template <class FP> class LassoNodeDev {
     DevBuf<X> d_eq_, d_gp_coeffs_, d_bufA_, d_bufB_, d_partials_, d_coll_terms_;
     int coll_coeff_state_ = 0;  // 0 not uploaded, 1 ascending, 2 descending
     DevBuf<unsigned> d_counters_, d_gp_counters_;
-    DevBuf<X> d_pool_, d_gp_partials_, d_r0part_, d_midpart_, d_gp_midpart_;
+    DevBuf<X> d_pool_, d_gp_partials_, d_r0part_, d_midpart_, d_gp_midpart_, d_gp_tailpart_;
+    DevBuf<unsigned> d_gp_tailcnt_;
+    int tail_log_ = FP::GP_TAIL_LOG, tail_groups_ = 1;
     size_t gp_mid_smem_set_ = 48 * 1024;  // largest dynamic shared memory k_gp_mid has been allowed so far
     size_t r0_used_ = 0;
     DevBuf<unsigned char> d_desc_, d_cdesc_;
