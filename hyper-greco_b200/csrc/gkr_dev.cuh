@@ -393,6 +393,7 @@ template <class FP> class GkrCircuitDev {
             jobs.push_back(job);
         }
         const double t3 = now();
+        bool early = false;
         if (mode == kModePrefetch) {
             struct StreamSwap {  // every helper reads ctx->stream when it launches
                 DeviceCtx* c; cudaStream_t main; bool on;
@@ -414,7 +415,10 @@ template <class FP> class GkrCircuitDev {
             launch_mid(ch, mine);
             launch_tail(ch, mine);
             launch_finals(ch, mine);
+            early = fork && !sharded;
         }
+        static const bool env_early = getenv("HG_EARLY_FLUSH") ? atoi(getenv("HG_EARLY_FLUSH")) != 0 : true;
+        if (early && env_early) ch.arm_early(ctx_->ev_join);  // after the StreamSwap scope: ev_join marks the end of every node sumcheck
         const double t4 = now();
         timing_[0] = t1 - t0; timing_[1] = t2 - t1; timing_[2] = t3 - t2; timing_[3] = t4 - t3;
     }
@@ -539,7 +543,7 @@ template <class FP> class GkrCircuitDev {
         msg_budget_ = msg + 64;
         ch_.reset(new Channel<FP>(ctx_, chal + 8, msg + 64));
         d_eq_.alloc(eq_elems + 64);
-        d_partials_.alloc(((size_t)ctx_->sm_count * 16 + 8) * 4 * (items + 4));
+        d_partials_.alloc(((size_t)ctx_->sm_count * 16 + 8) * 8 * (items + 4));  // 8 sums per CTA when round 0 rides on round 1
         d_counters_.alloc(items + 64);
         HG_CUDA(cudaMemset(d_counters_.p, 0, d_counters_.bytes()));
         h_desc_.alloc(1 << 20);
@@ -691,9 +695,16 @@ template <class FP> class GkrCircuitDev {
         int blk = 0;
         size_t part_off = 0, bytes = 0;
         size_t round_pairs = 0;  // small rounds get one pair per thread (more CTAs), large ones up to 16 (fewer block-level reductions)
-        for (const Job& j : jobs) if (r < j.nv && r < stream_end(j)) round_pairs += r == 0 ? j.S / 2 : (j.S >> (r - 1)) / 4;
+        // prefetch mode: round 0 of every job with a streamed round 1 is sampled by that round's launch (k_prod_round_multi FUSE0)
+        static const bool env_fuse0 = getenv("HG_PROD_FUSE0") ? atoi(getenv("HG_PROD_FUSE0")) != 0 : true;
+        auto fused0 = [&](const Job& j) { return env_fuse0 && use_tail_ && j.nv >= 2 && stream_end(j) >= 2; };
+        for (const Job& j : jobs) if (r < j.nv && r < stream_end(j) && !(r == 0 && fused0(j))) round_pairs += r == 0 ? j.S / 2 : (j.S >> (r - 1)) / 4;
+        bool any_fused = false;
         for (const Job& j : jobs) {
             if (r >= j.nv || r >= stream_end(j)) continue;
+            if (r == 0 && fused0(j)) continue;
+            const bool fuse = r == 1 && fused0(j);
+            any_fused = any_fused || fuse;
             Node& n = *nodes_[j.node];
             ProdItem<FP> it;
             it.nt = j.nt;
@@ -707,7 +718,7 @@ template <class FP> class GkrCircuitDev {
                 it.tab_out = (r & 1) ? n.tbuf0.p : n.tbuf1.p;
                 it.r_prev = ch.d_chal(j.r0_idx + r - 1);
             }
-            it.msg = ch.d_msg(j.msg_off + 4 * (size_t)r);
+            it.msg = ch.d_msg(j.msg_off + 4 * (size_t)(fuse ? 0 : r));
             const size_t npairs = r == 0 ? it.n_in / 2 : it.n_in / 4;
             // several pairs per thread: the block-level reduction that ends every block costs about as much as eight pairs (measured optimum 8-16)
             static const size_t ppt_max = getenv("HG_PROD_PPT") ? (size_t)atoi(getenv("HG_PROD_PPT")) : 16;
@@ -716,7 +727,7 @@ template <class FP> class GkrCircuitDev {
             it.nblk = (int)b; it.bx = (int)b; it.blk_start = blk;
             blk += it.nblk;
             it.partials = d_partials_.p + part_off;
-            part_off += b * 4;
+            part_off += b * (fuse ? 8 : 4);
             it.counter = d_counters_.p + 8 + items.size();
             bytes += it.n_in * ((r <= 1 ? sizeof(B) : sizeof(X)) * j.nt + sizeof(X)) + (r ? (it.n_in / 2) * sizeof(X) * (j.nt + 1) : 0);
             items.push_back(it);
@@ -727,6 +738,7 @@ template <class FP> class GkrCircuitDev {
         const ProdItem<FP>* di = stage(items);
         KernelScope ks(ctx_, KC_GKR_SC, bytes);
         if (r == 0) k_prod_round_multi<FP, B, false><<<blk, HG_PROD_BLOCK, 0, s>>>(di, (int)items.size());
+        else if (r == 1 && any_fused) k_prod_round_multi<FP, B, true, true><<<blk, HG_PROD_BLOCK, 0, s>>>(di, (int)items.size());
         else if (r == 1) k_prod_round_multi<FP, B, true><<<blk, HG_PROD_BLOCK, 0, s>>>(di, (int)items.size());
         else k_prod_round_multi<FP, X, true><<<blk, HG_PROD_BLOCK, 0, s>>>(di, (int)items.size());
         HG_LAUNCH_CHECK();

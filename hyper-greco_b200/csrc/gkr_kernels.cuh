@@ -207,8 +207,11 @@ template <class FP> struct ProdItem {
 };
 // one item, NT tables. Threads run few iterations here, so sums are kept reduced (4 registers each): unreduced accumulators
 // (24 registers each) cost more in occupancy than they save in reductions (measured: 2.5 ms vs 1.8 ms per proof)
-template <class FP, class TIN, bool FOLD, int NT>
-__device__ __forceinline__ void prod_round_item(const ProdItem<FP>& it, unsigned lb, typename FP::X (&acc)[4]) {
+// FUSE0 (round 1 in prefetch mode, TIN = base): r_0 is known before round 0 is computed, so the pass that folds the raw tables by
+// r_0 also samples round 0 on them (a quad of raw entries = two round-0 pairs) and the launch of round 0, one more read of the
+// largest tables of the class, is gone. acc[0..3] = round 0 [h(0), h(inf), h(-1), h(1)], acc[4..7] = round 1.
+template <class FP, class TIN, bool FOLD, int NT, bool FUSE0 = false>
+__device__ __forceinline__ void prod_round_item(const ProdItem<FP>& it, unsigned lb, typename FP::X (&acc)[FUSE0 ? 8 : 4]) {
     typedef typename FP::X X;
     typedef typename std::conditional<FOLD, X, TIN>::type EL;
     constexpr int NS = NT + 1;  // samples 0, inf (and -1 for the degree-3 case); slot 3 = h(1), round 0 only
@@ -235,11 +238,17 @@ __device__ __forceinline__ void prod_round_item(const ProdItem<FP>& it, unsigned
         acc[0] = FP::xacc_reduce_(P0); acc[1] = FP::xacc_reduce_(P1); acc[3] = FP::xacc_reduce_(P3);
         return;
     }
+    constexpr int O = FUSE0 ? 4 : 0;  // where this round's samples go
+    typename FP::XAcc Q0, Q1, Q3;     // FUSE0, NT == 1: round 0 = extension weight times BASE entry, accumulated unreduced as in the unfused round 0
+    if constexpr (FUSE0 && NT == 1) { Q0 = FP::xacc_zero_(); Q1 = FP::xacc_zero_(); Q3 = FP::xacc_zero_(); }
     for (size_t b = (size_t)lb * blockDim.x + threadIdx.x; b < npairs; b += (size_t)it.nblk * blockDim.x) {
         X wlo, whi;
+        X wraw[4];
+        (void)wraw;
         if constexpr (FOLD) {
             X s[4];
             load4(it.w_in + 4 * b, s);
+            if constexpr (FUSE0) { wraw[0] = s[0]; wraw[1] = s[1]; wraw[2] = s[2]; wraw[3] = s[3]; }
             wlo = FP::fold(s[0], s[1], r, aux); whi = FP::fold(s[2], s[3], r, aux);
             store2(it.w_out + 2 * b, wlo, whi);
         } else {
@@ -248,11 +257,14 @@ __device__ __forceinline__ void prod_round_item(const ProdItem<FP>& it, unsigned
             wlo = s[0]; whi = s[1];
         }
         EL lo[NT], hi[NT];
+        TIN traw[NT][4];
+        (void)traw;
 #pragma unroll
         for (int q = 0; q < NT; q++) {
             if constexpr (FOLD) {
                 TIN s[4];
                 load4(tab + (size_t)q * n_in + 4 * b, s);
+                if constexpr (FUSE0) { traw[q][0] = s[0]; traw[q][1] = s[1]; traw[q][2] = s[2]; traw[q][3] = s[3]; }
                 lo[q] = FP::fold(s[0], s[1], r, aux); hi[q] = FP::fold(s[2], s[3], r, aux);
                 store2(it.tab_out + (size_t)q * n_out + 2 * b, lo[q], hi[q]);
             } else {
@@ -261,28 +273,47 @@ __device__ __forceinline__ void prod_round_item(const ProdItem<FP>& it, unsigned
                 lo[q] = s[0]; hi[q] = s[1];
             }
         }
+        if constexpr (FUSE0) {  // round 0 on the two raw pairs (0, 1) and (2, 3) of this quad
+#pragma unroll
+            for (int h = 0; h < 4; h += 2) {
+                if constexpr (NT == 1) {
+                    FP::xacc_mad_b(Q0, wraw[h], traw[0][h]);
+                    FP::xacc_mad_b(Q1, FP::slope(wraw[h], wraw[h + 1]), FP::slope(traw[0][h], traw[0][h + 1]));
+                    FP::xacc_mad_b(Q3, wraw[h + 1], traw[0][h + 1]);
+                } else {
+                    acc[0] = FP::x_add(acc[0], FP::fmul_any(wraw[h], FP::fmul(traw[0][h], traw[1][h])));
+                    acc[1] = FP::x_add(acc[1], FP::fmul_any(FP::slope(wraw[h], wraw[h + 1]), FP::fmul(FP::slope(traw[0][h], traw[0][h + 1]), FP::slope(traw[1][h], traw[1][h + 1]))));
+                    acc[2] = FP::x_add(acc[2], FP::fmul_any(FP::at_m1(wraw[h], wraw[h + 1]), FP::fmul(FP::at_m1(traw[0][h], traw[0][h + 1]), FP::at_m1(traw[1][h], traw[1][h + 1]))));
+                    acc[3] = FP::x_add(acc[3], FP::fmul_any(wraw[h + 1], FP::fmul(traw[0][h + 1], traw[1][h + 1])));
+                }
+            }
+        }
         if constexpr (NT == 1) {
-            acc[0] = FP::x_add(acc[0], FP::fmul_any(wlo, lo[0]));
-            acc[1] = FP::x_add(acc[1], FP::fmul_any(FP::slope(wlo, whi), FP::slope(lo[0], hi[0])));
+            acc[O + 0] = FP::x_add(acc[O + 0], FP::fmul_any(wlo, lo[0]));
+            acc[O + 1] = FP::x_add(acc[O + 1], FP::fmul_any(FP::slope(wlo, whi), FP::slope(lo[0], hi[0])));
             if (!FOLD) acc[3] = FP::x_add(acc[3], FP::fmul_any(whi, hi[0]));
         } else {
-            acc[0] = FP::x_add(acc[0], FP::fmul_any(wlo, FP::fmul(lo[0], lo[1])));
-            acc[1] = FP::x_add(acc[1], FP::fmul_any(FP::slope(wlo, whi), FP::fmul(FP::slope(lo[0], hi[0]), FP::slope(lo[1], hi[1]))));
-            acc[2] = FP::x_add(acc[2], FP::fmul_any(FP::at_m1(wlo, whi), FP::fmul(FP::at_m1(lo[0], hi[0]), FP::at_m1(lo[1], hi[1]))));
+            acc[O + 0] = FP::x_add(acc[O + 0], FP::fmul_any(wlo, FP::fmul(lo[0], lo[1])));
+            acc[O + 1] = FP::x_add(acc[O + 1], FP::fmul_any(FP::slope(wlo, whi), FP::fmul(FP::slope(lo[0], hi[0]), FP::slope(lo[1], hi[1]))));
+            acc[O + 2] = FP::x_add(acc[O + 2], FP::fmul_any(FP::at_m1(wlo, whi), FP::fmul(FP::at_m1(lo[0], hi[0]), FP::at_m1(lo[1], hi[1]))));
             if (!FOLD) acc[3] = FP::x_add(acc[3], FP::fmul_any(whi, FP::fmul(hi[0], hi[1])));
         }
     }
+    if constexpr (FUSE0 && NT == 1) { acc[0] = FP::xacc_reduce_(Q0); acc[1] = FP::xacc_reduce_(Q1); acc[3] = FP::xacc_reduce_(Q3); }
 }
 constexpr int HG_PROD_BLOCK = 128;  // threads per CTA of the streamed layer-sumcheck rounds
-template <class FP, class TIN, bool FOLD>
+template <class FP, class TIN, bool FOLD, bool FUSE0 = false>
 __global__ void __launch_bounds__(HG_PROD_BLOCK, ((FOLD || sizeof(typename FP::B) > 8) ? 1 : 3) * (HG_BLOCK / HG_PROD_BLOCK)) k_prod_round_multi(const ProdItem<FP>* __restrict__ items, int nitems) {
     typedef typename FP::X X;
+    constexpr int NP = FUSE0 ? 8 : 4;  // FUSE0: it.msg is the slot of round 0, the slot of round 1 follows it
     const ProdItem<FP> it = items[find_item(items, nitems)];
     const unsigned lb = blockIdx.x - it.blk_start;
-    X acc[4] = {FP::x_zero(), FP::x_zero(), FP::x_zero(), FP::x_zero()};
-    if (it.nt == 1) prod_round_item<FP, TIN, FOLD, 1>(it, lb, acc);
-    else prod_round_item<FP, TIN, FOLD, 2>(it, lb, acc);
-    block_reduce_finalize_ex<FP, 4>(acc, it.partials, it.counter, it.msg, it.nblk, lb);
+    X acc[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) acc[p] = FP::x_zero();
+    if (it.nt == 1) prod_round_item<FP, TIN, FOLD, 1, FUSE0>(it, lb, acc);
+    else prod_round_item<FP, TIN, FOLD, 2, FUSE0>(it, lb, acc);
+    block_reduce_finalize_ex<FP, NP>(acc, it.partials, it.counter, it.msg, it.nblk, lb);
 }
 
 // ---- the last rounds of every node sumcheck in ONE launch: one CTA per node, weights and tables (extension elements, at most

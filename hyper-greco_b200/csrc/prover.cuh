@@ -150,12 +150,14 @@ template <class FP> class Channel {
         d_chal_.alloc(chal_cap); h_chal_.alloc(chal_cap);
         d_msg_.alloc(msg_cap); h_msg_.alloc(msg_cap);
         HG_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+        HG_CUDA(cudaStreamCreateWithFlags(&copy_stream2_, cudaStreamNonBlocking));
         HG_CUDA(cudaEventCreateWithFlags(&ev_side_done_, cudaEventDisableTiming));
         HG_CUDA(cudaEventCreateWithFlags(&ev_side_copied_, cudaEventDisableTiming));
+        HG_CUDA(cudaEventCreateWithFlags(&ev_early_copied_, cudaEventDisableTiming));
     }
     ~Channel() {
-        cudaEventDestroy(ev_side_done_); cudaEventDestroy(ev_side_copied_);
-        cudaStreamDestroy(copy_stream_);
+        cudaEventDestroy(ev_side_done_); cudaEventDestroy(ev_side_copied_); cudaEventDestroy(ev_early_copied_);
+        cudaStreamDestroy(copy_stream_); cudaStreamDestroy(copy_stream2_);
     }
     Channel(const Channel&) = delete;
     Channel& operator=(const Channel&) = delete;
@@ -163,7 +165,7 @@ template <class FP> class Channel {
         tr_ = tr; active_tr_ = tr; mode_ = mode;
         chal_cursor_ = chal_ready_ = msg_cursor_ = msg_ready_ = 0;
         deferred_.clear(); deferred_done_ = 0;
-        side_state_ = 0;
+        side_state_ = 0; early_armed_ = false;
         if (total_chal > d_chal_.n) throw std::runtime_error("Channel: challenge capacity exceeded");
         if (mode_ == kModePrefetch) {
             for (size_t i = 0; i < total_chal; i++) h_chal_.p[i] = tr_->squeeze_challenge();
@@ -211,12 +213,31 @@ template <class FP> class Channel {
                                     cudaMemcpyDeviceToHost, copy_stream_));
         HG_CUDA(cudaEventRecord(ev_side_copied_, copy_stream_));
     }
+    // ---- early head (prefetch mode, with a closed side segment): everything emitted BEFORE the side segment whose kernels are done
+    // when `after` fires (the node sumchecks that precede the Lasso node in protocol order run on the second stream and finish long
+    // before the grand products). Their messages are copied then, and flush() serialises them straight into the transcript while
+    // the device still works on the side segment: about two thirds of the serialisation leaves the critical path.
+    void arm_early(cudaEvent_t after) {
+        if (side_state_ != 2 || side_msg_begin_ == 0 || side_def_begin_ == 0) return;
+        HG_CUDA(cudaStreamWaitEvent(copy_stream2_, after, 0));
+        HG_CUDA(cudaMemcpyAsync(h_msg_.p, d_msg_.p, side_msg_begin_ * sizeof(X), cudaMemcpyDeviceToHost, copy_stream2_));
+        HG_CUDA(cudaEventRecord(ev_early_copied_, copy_stream2_));
+        early_armed_ = true;
+    }
     // bring finished messages to the host and serialise everything emitted so far, in order
     void flush(double* wait_us = nullptr, double* emit_us = nullptr) {
         auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         const double t0 = now();
         double side_us = 0;
         if (side_state_ == 1) side_state_ = 0;  // never closed: plain in-order flush
+        if (early_armed_ && side_state_ == 2 && deferred_done_ == 0 && msg_ready_ == 0) {
+            HG_CUDA(cudaEventSynchronize(ev_early_copied_));
+            const double e0 = now();
+            msg_ready_ = side_msg_begin_;
+            while (deferred_done_ < side_def_begin_) deferred_[deferred_done_++]();
+            side_us += now() - e0;
+        }
+        early_armed_ = false;
         auto copy_range = [&](size_t a, size_t b) {
             if (b > a) HG_CUDA(cudaMemcpyAsync(h_msg_.p + a, d_msg_.p + a, (b - a) * sizeof(X), cudaMemcpyDeviceToHost, ctx_->stream));
         };
@@ -232,7 +253,7 @@ template <class FP> class Channel {
             active_tr_ = tr_;
             side_bytes_ = side.proof();
             side_state_ = 3;
-            side_us = now() - s0;
+            side_us += now() - s0;
         } else {
             copy_range(msg_ready_, msg_cursor_);
         }
@@ -298,8 +319,9 @@ template <class FP> class Channel {
     DeviceCtx* ctx_;
     Keccak256Transcript<FP>* tr_ = nullptr;
     Keccak256Transcript<FP>* active_tr_ = nullptr;  // where serialisers write: tr_, or the side buffer
-    cudaStream_t copy_stream_ = nullptr;
-    cudaEvent_t ev_side_done_ = nullptr, ev_side_copied_ = nullptr;
+    cudaStream_t copy_stream_ = nullptr, copy_stream2_ = nullptr;
+    cudaEvent_t ev_side_done_ = nullptr, ev_side_copied_ = nullptr, ev_early_copied_ = nullptr;
+    bool early_armed_ = false;
     int side_state_ = 0;  // 0 none, 1 open, 2 closed (copy in flight), 3 serialised
     size_t side_def_begin_ = 0, side_def_end_ = 0, side_msg_begin_ = 0, side_msg_end_ = 0;
     std::vector<uint8_t> side_bytes_;
