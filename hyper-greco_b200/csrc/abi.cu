@@ -621,6 +621,7 @@ int hg_ctx_create(int device, int field_id, hg_ctx** out) {
             HG_CUDA(cudaStreamCreateWithFlags(&c->dev.stream3, cudaStreamNonBlocking));
             HG_CUDA(cudaEventCreateWithFlags(&c->dev.ev_fork3, cudaEventDisableTiming));
             HG_CUDA(cudaEventCreateWithFlags(&c->dev.ev_join3, cudaEventDisableTiming));
+            HG_CUDA(cudaEventCreateWithFlags(&c->dev.ev_coll, cudaEventDisableTiming));
         }
         HG_CUDA(cudaDeviceGetAttribute(&c->dev.sm_count, cudaDevAttrMultiProcessorCount, device));
         *out = c.release();
@@ -634,6 +635,7 @@ void hg_ctx_destroy(hg_ctx* ctx) {
     if (ctx->dev.ev_join) cudaEventDestroy(ctx->dev.ev_join);
     if (ctx->dev.ev_fork3) cudaEventDestroy(ctx->dev.ev_fork3);
     if (ctx->dev.ev_join3) cudaEventDestroy(ctx->dev.ev_join3);
+    if (ctx->dev.ev_coll) cudaEventDestroy(ctx->dev.ev_coll);
     if (ctx->dev.stream3) cudaStreamDestroy(ctx->dev.stream3);
     if (ctx->dev.stream2) cudaStreamDestroy(ctx->dev.stream2);
     if (ctx->dev.stream) cudaStreamDestroy(ctx->dev.stream);
