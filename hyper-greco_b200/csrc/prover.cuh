@@ -1045,8 +1045,9 @@ template <class FP> class LassoNodeDev {
         const bool lead = shard_rank_ == 0;  // the claim and the collation sumcheck belong to rank 0 (the openings are distributed, see below)
         // With every challenge known up front nothing below waits for the claim or the collation sumcheck (gamma, tau are challenges), so
         // they run on the side stream behind the access counters, next to the hash / tree / grand-product kernels, and are joined before
-        // the openings (which reuse the eq tables and the partial-sum scratch). 0.25 ms off the critical path of one proof.
-        static const bool env_coll_side = getenv("HG_COLL_SIDE") ? atoi(getenv("HG_COLL_SIDE")) != 0 : true;
+        // the openings (which reuse the eq tables and the partial-sum scratch). Measured: no change of the single-proof latency (5.07 vs
+        // 5.08 ms, profiles/r2_experiments.md) because the three streams already keep the SMs busy; off by default.
+        static const bool env_coll_side = getenv("HG_COLL_SIDE") ? atoi(getenv("HG_COLL_SIDE")) != 0 : false;
         const bool coll_side = env_coll_side && lead && mode == kModePrefetch && ctx_->two_streams && !ctx_->profile && ctx_->stream3 != nullptr && ctx_->ev_coll != nullptr;
         struct CollStream {  // launches go to stream3 while this lives (RAII: an exception must not leave the context there)
             DeviceCtx* c; cudaStream_t main; bool on;
