@@ -99,6 +99,32 @@ template <class FP> class GkrCircuitDev {
         up(n.add_ptr, d.add_ptr); up(n.add_in, d.add_in); up(n.add_wire, d.add_wire); up(n.add_coef, addc);
         up(n.mul_ptr, d.mul_ptr); up(n.mul_in0, d.mul_in0); up(n.mul_w0, d.mul_w0); up(n.mul_in1, d.mul_in1); up(n.mul_w1, d.mul_w1); up(n.mul_coef, mulc);
         up(n.consts, cg);
+        {   // forward runs (k_vanilla_runs): maximal stretches of gates with the same number of edge slots, every slot walking one input
+            // wire by wire with one coefficient, and the same constant
+            static const bool env_fwd = getenv("HG_FWD_RUNS") ? atoi(getenv("HG_FWD_RUNS")) != 0 : true;
+            typedef typename Node::FwdRun FwdRun;
+            bool ok = env_fwd;
+            if (ok && n.is_elemmul) {
+                FwdRun r; r.g0 = 0; r.len = ng; r.ne = -2; r.cst = FP::b_zero();
+                r.in[0] = 0; r.in[1] = 1; r.w0[0] = r.w0[1] = 0; r.coef[0] = r.coef[1] = FP::b_one();
+                n.fwd_runs.push_back(r);
+            } else if (ok && n.is_linear) {
+                for (size_t g = 0; ok && g < ng; g++) {
+                    const uint64_t e0 = d.add_ptr[g], ne = d.add_ptr[g + 1] - e0;
+                    if (ne > (uint64_t)HG_FWD_MAXE) { ok = false; break; }
+                    FwdRun* last = n.fwd_runs.empty() ? nullptr : &n.fwd_runs.back();
+                    bool ext = last && (uint64_t)last->ne == ne && FP::b_eq(last->cst, cg[g]);
+                    for (uint64_t e = 0; ext && e < ne; e++)
+                        ext = last->in[e] == d.add_in[e0 + e] && last->w0[e] + (g - last->g0) == d.add_wire[e0 + e] && FP::b_eq(last->coef[e], addc[e0 + e]);
+                    if (ext) { last->len++; continue; }
+                    FwdRun r; r.g0 = g; r.len = 1; r.ne = (int)ne; r.cst = cg[g];
+                    for (uint64_t e = 0; e < ne; e++) { r.in[e] = d.add_in[e0 + e]; r.w0[e] = d.add_wire[e0 + e]; r.coef[e] = addc[e0 + e]; }
+                    n.fwd_runs.push_back(r);
+                    if (n.fwd_runs.size() * d.num_reps > 4096) ok = false;
+                }
+            }
+            if (!ok) n.fwd_runs.clear();
+        }
         if (n.is_linear) {
             // reverse wiring: for every element x of the concatenated inputs, the (output, coefficient) pairs that read it
             const size_t S = n.a_pad * n.n_in;
@@ -191,8 +217,51 @@ template <class FP> class GkrCircuitDev {
                 }
                 ntt_->run(grp.arena->p, first.log2_size, first.fft_inverse, grp.nodes.size());
             }
+            std::vector<FwdRunItem<FP>> fitems;  // every layer of this level whose gates come in runs: one launch
+            int fblk = 0;
+            size_t fbytes = 0;
             for (int id : lvl.vanilla) {
                 Node& n = *nodes_[id];
+                if (n.fwd_runs.empty()) continue;
+                const size_t sub = (size_t)1 << n.log2_sub;
+                auto push = [&](FwdRunItem<FP>& it) {
+                    it.blk_start = fblk;
+                    fblk += (int)((it.n + (size_t)HG_BLOCK * HG_FWD_PER_THREAD - 1) / ((size_t)HG_BLOCK * HG_FWD_PER_THREAD));
+                    fitems.push_back(it);
+                };
+                for (int r = 0; r < n.num_reps; r++)
+                    for (const typename Node::FwdRun& fr : n.fwd_runs) {
+                        FwdRunItem<FP> it;
+                        it.out = n.value.p + (size_t)r * n.ng + fr.g0; it.n = fr.len; it.ne = fr.ne; it.cst = fr.cst;
+                        for (int e = 0; e < HG_FWD_MAXE; e++) { it.in[e] = nullptr; it.coef[e] = FP::b_zero(); }
+                        for (int e = 0; e < (fr.ne == -2 ? 2 : fr.ne); e++) { it.in[e] = nodes_[n.preds.at(fr.in[e])]->value_ptr + (size_t)r * sub + fr.w0[e]; it.coef[e] = fr.coef[e]; }
+                        push(it);
+                    }
+                if (n.out_len > n.ng * (size_t)n.num_reps) {  // padding up to the power of two
+                    FwdRunItem<FP> it;
+                    it.out = n.value.p + n.ng * (size_t)n.num_reps; it.n = n.out_len - n.ng * (size_t)n.num_reps; it.ne = 0; it.cst = FP::b_zero();
+                    for (int e = 0; e < HG_FWD_MAXE; e++) { it.in[e] = nullptr; it.coef[e] = FP::b_zero(); }
+                    push(it);
+                }
+                fbytes += n.out_len * sizeof(B) * 2;
+                n.value_ptr = n.value.p;
+            }
+            if (!fitems.empty()) {
+                // own staging buffers (the prover resets its descriptor ring per proof); re-uploaded only when a pointer changed
+                const size_t bytes = fitems.size() * sizeof(FwdRunItem<FP>);
+                if (!lvl.h_items) { lvl.h_items.reset(new PinnedBuf<unsigned char>()); lvl.d_items.reset(new DevBuf<unsigned char>()); }
+                if (lvl.h_items->n < bytes) { HG_CUDA(cudaStreamSynchronize(s)); lvl.h_items->alloc(bytes); lvl.d_items->alloc(bytes); lvl.items_bytes = 0; }
+                if (lvl.items_bytes != bytes || memcmp(lvl.h_items->p, fitems.data(), bytes) != 0) {
+                    if (lvl.items_bytes) HG_CUDA(cudaStreamSynchronize(s));  // an earlier upload from this buffer may still be pending
+                    memcpy(lvl.h_items->p, fitems.data(), bytes);
+                    HG_CUDA(cudaMemcpyAsync(lvl.d_items->p, lvl.h_items->p, bytes, cudaMemcpyHostToDevice, s));
+                    lvl.items_bytes = bytes;
+                }
+                HG_K(ctx_, KC_MISC, fbytes, k_vanilla_runs<FP><<<fblk, HG_BLOCK, 0, s>>>((const FwdRunItem<FP>*)lvl.d_items->p, (int)fitems.size()));
+            }
+            for (int id : lvl.vanilla) {
+                Node& n = *nodes_[id];
+                if (!n.fwd_runs.empty()) continue;
                 bool changed = false;
                 for (size_t k = 0; k < n.preds.size(); k++) {
                     const B* p = nodes_[n.preds[k]]->value_ptr;
@@ -428,6 +497,8 @@ template <class FP> class GkrCircuitDev {
         bool fft_inverse = false, is_linear = false, is_elemmul = false, has_consts = false;
         size_t ng = 0, out_len = 0, n_in = 0, a_pad = 1;
         std::vector<int> preds, succs;
+        struct FwdRun { uint64_t g0, len; int ne; uint32_t in[HG_FWD_MAXE]; uint64_t w0[HG_FWD_MAXE]; B coef[HG_FWD_MAXE]; B cst; };
+        std::vector<FwdRun> fwd_runs;    // non-empty: the gates come in runs (k_vanilla_runs evaluates the layer)
         struct WireRun { uint64_t x0, len; uint32_t out0; int kind; B coef; };
         std::vector<WireRun> wire_runs;  // non-empty: the reverse wiring is piecewise the identity (k_wiring_runs)
         DevBuf<u64> add_ptr, add_wire, mul_ptr, mul_w0, mul_w1, rev_ptr;
@@ -448,7 +519,10 @@ template <class FP> class GkrCircuitDev {
     };
 
     struct FftGroup { std::vector<int> nodes; std::unique_ptr<DevBuf<B>> arena; };
-    struct EvalLevel { std::vector<FftGroup> fft_groups; std::vector<int> vanilla; };
+    struct EvalLevel {
+        std::vector<FftGroup> fft_groups; std::vector<int> vanilla;
+        std::unique_ptr<PinnedBuf<unsigned char>> h_items; std::unique_ptr<DevBuf<unsigned char>> d_items; size_t items_bytes = 0;  // k_vanilla_runs descriptors
+    };
     // static schedule of evaluate(): levels, FFT batches, pointer tables
     void plan_evaluate() {
         if (eval_planned_) return;

@@ -34,6 +34,36 @@ __global__ void k_vanilla_eval(VanillaFwd w, const typename FP::B* __restrict__ 
     out[t] = FP::b_add(consts[g], FP::bacc_reduce(acc));
 }
 
+// Forward evaluation of the layers whose gates come in runs: gates g0..g0+n-1 each read wire w0_e + (g - g0) of input in_e with one
+// coefficient per edge slot e (relay / scale / shift / sum layers: one to five slots, sk_encryption_circuit.rs:97-285), or multiply two
+// inputs element-wise (ne = -2, :245-260). One streamed launch per circuit level for all such layers instead of one index-chasing
+// launch per layer (k_vanilla_eval: 28 bytes of gate description per edge). Same products, one reduction per gate: identical values.
+constexpr int HG_FWD_MAXE = 5;
+constexpr int HG_FWD_PER_THREAD = 4;
+template <class FP> struct FwdRunItem {
+    typename FP::B* out;
+    u64 n;
+    const typename FP::B* in[HG_FWD_MAXE];
+    typename FP::B coef[HG_FWD_MAXE];
+    typename FP::B cst;
+    int ne;  // additive edge slots (0: constant gates), -2: out = in[0] * in[1]
+    int blk_start;
+};
+template <class FP> __global__ void k_vanilla_runs(const FwdRunItem<FP>* __restrict__ items, int nitems) {
+    typedef typename FP::B B;
+    const FwdRunItem<FP> it = items[find_item(items, nitems)];
+    const size_t base = (size_t)(blockIdx.x - it.blk_start) * blockDim.x * HG_FWD_PER_THREAD + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < HG_FWD_PER_THREAD; k++) {
+        const size_t i = base + (size_t)k * blockDim.x;
+        if (i >= it.n) continue;
+        typename FP::BAcc acc = FP::bacc_zero();
+        if (it.ne == -2) FP::bacc_mad(acc, FP::b_one(), FP::fmul(it.in[0][i], it.in[1][i]));
+        else for (int e = 0; e < it.ne; e++) FP::bacc_mad(acc, it.coef[e], it.in[e][i]);
+        it.out[i] = FP::b_add(it.cst, FP::bacc_reduce(acc));
+    }
+}
+
 // ---- eq factor tables of every (node, claim) pair in one launch
 // eq_lo of claim t carries the factor alpha^t (alpha = nullptr: single claim), so W = sum_t eq_lo_t (x) eq_hi_t needs no scaling pass
 template <class FP> struct EqSplitItem {

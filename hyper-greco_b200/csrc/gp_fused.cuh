@@ -11,7 +11,7 @@
 //   * q_i(b; X) = l_i r_i is quadratic in X: q(inf) costs one product of slopes, q(-1) = 2 q(0) - q(1) + 2 q(inf) none;
 //   * per vector i the base-field sums D_i(p) = sum_b t_0(b; p) q_i(b; p) are accumulated unreduced and multiplied by the
 //     extension coefficient c_i once per thread;
-//   * every CTA writes its four partial sums; the tail kernel of the layer (one CTA per layer, gp_kernels.cuh) adds them
+//   * every CTA writes its four partial sums; the tail kernel of the layer (its first CTA, gp_kernels.cuh) adds them
 //     up. Field addition is exact, so the order of summation does not change a bit of the message.
 // Blocks are numbered vector-fastest: the CTAs of one position range run back to back and share the t_0 segment (vector 0)
 // and, in the hash kernel, the address / counter columns of a chunk through L2.
