@@ -12,7 +12,7 @@ cap() {  # name, kernel regex, skip, count
     rm -f gpurun_out/r2_$1.ncu-rep
 }
 cap fused "k_hash_rw_up_r0|k_tree_up_r0" 26 2
-cap fold "k_gp_fold_multi" 28 3
+cap fold "k_gp_fold_multi" 26 3
 timeout 400 compute-sanitizer --tool racecheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -5 gpurun_out/r2_racecheck.log
 timeout 400 compute-sanitizer --tool memcheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/r2_memcheck.log
 du -sh gpurun_out
