@@ -286,7 +286,7 @@ def _golden_proof(golden_dir, fname):
     return data, meta["files"][fname]
 
 
-def test_oracle_reproduces_committed_golden_proofs(oracle, golden_dir):
+def test_oracle_reproduces_its_committed_golden_proofs(oracle, golden_dir):
     """The committed proof bytes (tests/golden/make_golden_proofs.py) are what the oracle produces today: any change of the
     restatement shows up here, and the same files are what the GPU tests and an off-box Rust run compare against."""
     name = "1024_1x27_65537"
