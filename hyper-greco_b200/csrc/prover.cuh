@@ -146,6 +146,7 @@ enum ProveMode { kModePrefetch = 0, kModeInteractive = 1 };
 template <class FP> class Channel {
   public:
     typedef typename FP::X X;
+    struct RoundOp { void* st; size_t off, next_idx; WireOptions w; int slot_h1; bool round0; };  // arguments of one emit_round
     Channel(DeviceCtx* ctx, size_t chal_cap, size_t msg_cap) : ctx_(ctx) {
         d_chal_.alloc(chal_cap); h_chal_.alloc(chal_cap);
         d_msg_.alloc(msg_cap); h_msg_.alloc(msg_cap);
@@ -194,7 +195,10 @@ template <class FP> class Channel {
         if (msg_cursor_ > d_msg_.n) throw std::runtime_error("Channel: message capacity exceeded");
         return off;
     }
-    void emit(std::function<void()> fn) { deferred_.push_back(std::move(fn)); }
+    void emit(std::function<void()> fn) { deferred_.emplace_back(); deferred_.back().fn = std::move(fn); }
+    // a round message (emit_round): by far the most frequent serialiser (~1 500 per proof), kept as plain data instead of a
+    // heap-allocated closure. `st` stays alive through the closures of its sumcheck that hold the shared_ptr.
+    void emit_round_op(void (*exec)(Channel&, const RoundOp&), const RoundOp& op) { deferred_.emplace_back(); deferred_.back().exec = exec; deferred_.back().op = op; }
     // ---- side segment (prefetch mode): a run of messages whose serialisers depend on nothing emitted before them (the Lasso
     // node: it ignores its incoming claim, lasso.rs:60). Its messages are copied to the host as soon as its kernels finish and
     // serialised into a side buffer while the device works on what was enqueued after it; flush() splices the bytes in place.
@@ -234,7 +238,7 @@ template <class FP> class Channel {
             HG_CUDA(cudaEventSynchronize(ev_early_copied_));
             const double e0 = now();
             msg_ready_ = side_msg_begin_;
-            while (deferred_done_ < side_def_begin_) deferred_[deferred_done_++]();
+            while (deferred_done_ < side_def_begin_) deferred_[deferred_done_++](*this);
             side_us += now() - e0;
         }
         early_armed_ = false;
@@ -249,7 +253,7 @@ template <class FP> class Channel {
             Keccak256Transcript<FP> side;
             active_tr_ = &side;
             msg_ready_ = side_msg_end_;  // side serialisers read their own range only
-            for (size_t i = side_def_begin_; i < side_def_end_; i++) deferred_[i]();
+            for (size_t i = side_def_begin_; i < side_def_end_; i++) deferred_[i](*this);
             active_tr_ = tr_;
             side_bytes_ = side.proof();
             side_state_ = 3;
@@ -268,7 +272,7 @@ template <class FP> class Channel {
                 side_state_ = 0;
                 continue;
             }
-            deferred_[deferred_done_++]();
+            deferred_[deferred_done_++](*this);
         }
         if (wait_us) *wait_us = (t1 - t0 - side_us) + (t2 - t1);
         if (emit_us) *emit_us = side_us + (now() - t2);
@@ -296,14 +300,14 @@ template <class FP> class Channel {
         HG_CUDA(cudaMemcpyAsync(h_msg_.p, d_merged, count * sizeof(X), cudaMemcpyDeviceToHost, ctx_->stream));
         HG_CUDA(cudaStreamSynchronize(ctx_->stream));
         msg_ready_ = msg_cursor_;
-        for (; deferred_done_ < deferred_.size(); deferred_done_++) deferred_[deferred_done_]();
+        for (; deferred_done_ < deferred_.size(); deferred_done_++) deferred_[deferred_done_](*this);
     }
     // replace the host copy of the messages by the merged one and serialise
     void emit_merged(const X* merged, size_t count) {
         if (count != msg_cursor_) throw std::runtime_error("Channel: merged message count does not match this proof");
         memcpy(h_msg_.p, merged, count * sizeof(X));
         msg_ready_ = msg_cursor_;
-        for (; deferred_done_ < deferred_.size(); deferred_done_++) deferred_[deferred_done_]();
+        for (; deferred_done_ < deferred_.size(); deferred_done_++) deferred_[deferred_done_](*this);
     }
     size_t msg_used() const { return msg_cursor_; }
     const X* d_chal(size_t i) const { return d_chal_.p + i; }
@@ -329,7 +333,13 @@ template <class FP> class Channel {
     DevBuf<X> d_chal_, d_msg_;
     PinnedBuf<X> h_chal_, h_msg_;
     size_t chal_cursor_ = 0, chal_ready_ = 0, msg_cursor_ = 0, msg_ready_ = 0;
-    std::vector<std::function<void()>> deferred_;
+    struct Deferred {
+        std::function<void()> fn;
+        void (*exec)(Channel&, const RoundOp&) = nullptr;
+        RoundOp op;
+        void operator()(Channel& ch) const { if (exec) exec(ch, op); else fn(); }
+    };
+    std::vector<Deferred> deferred_;
     size_t deferred_done_ = 0;
 };
 
@@ -408,9 +418,15 @@ template <class FP, int D>
 void emit_round(Channel<FP>& ch, std::shared_ptr<ScHostState<FP>> st, size_t off, const WireOptions& wo, bool round0, size_t next_idx,
                 int slot_h1 = D) {
     typedef typename FP::X X;
-    Channel<FP>* chp = &ch;
-    WireOptions w = wo;
-    ch.emit([chp, st, off, w, round0, next_idx, slot_h1]() {
+    typename Channel<FP>::RoundOp rop;
+    rop.st = st.get(); rop.off = off; rop.next_idx = next_idx; rop.w = wo; rop.slot_h1 = slot_h1; rop.round0 = round0;
+    ch.emit_round_op([](Channel<FP>& chr, const typename Channel<FP>::RoundOp& o) {
+        Channel<FP>* chp = &chr;
+        ScHostState<FP>* st = (ScHostState<FP>*)o.st;
+        const size_t off = o.off, next_idx = o.next_idx;
+        const WireOptions w = o.w;
+        const bool round0 = o.round0;
+        const int slot_h1 = o.slot_h1;
         typedef RoundPoly<FP> RP;
         auto horner = [](const X* c, int deg, X x) { X r = c[deg]; for (int i = deg; i-- > 0;) r = FP::x_add(FP::x_mul(r, x), c[i]); return r; };
         X s;
@@ -471,7 +487,7 @@ void emit_round(Channel<FP>& ch, std::shared_ptr<ScHostState<FP>> st, size_t off
         st->pending_deg = D;
         st->pending_chal = next_idx;
         st->has_pending = true;
-    });
+    }, rop);
 }
 
 // same for the fixed 4-slot layout [h(0), h(inf), h(-1), h(1)] of the generic GKR layer kernels (gkr_kernels.cuh)
