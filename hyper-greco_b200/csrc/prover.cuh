@@ -1064,7 +1064,8 @@ template <class FP> class LassoNodeDev {
         // the openings (which reuse the eq tables and the partial-sum scratch). Measured: no change of the single-proof latency (5.07 vs
         // 5.08 ms, profiles/r2_experiments.md) because the three streams already keep the SMs busy; off by default.
         static const bool env_coll_side = getenv("HG_COLL_SIDE") ? atoi(getenv("HG_COLL_SIDE")) != 0 : false;
-        const bool coll_side = env_coll_side && lead && mode == kModePrefetch && ctx_->two_streams && !ctx_->profile && ctx_->stream3 != nullptr && ctx_->ev_coll != nullptr;
+        // (a sharded proof is latency-bound on every rank and rank 0 alone runs these two: there the side stream is always used)
+        const bool coll_side = (env_coll_side || shard_world_ > 1) && lead && mode == kModePrefetch && ctx_->two_streams && !ctx_->profile && ctx_->stream3 != nullptr && ctx_->ev_coll != nullptr;
         struct CollStream {  // launches go to stream3 while this lives (RAII: an exception must not leave the context there)
             DeviceCtx* c; cudaStream_t main; bool on;
             CollStream(DeviceCtx* ctx, bool enable) : c(ctx), main(ctx->stream), on(enable) {
