@@ -13,6 +13,7 @@ circuit (sk_encryption_circuit.rs:455-457) on a synthetic witness of the n=32768
 metric config). `value` = proofs/s over all GPUs; the latency of one proof alone is reported next to it. ONE JSON line on rank 0.
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -48,6 +49,7 @@ def bench_config(args, P, nv, m):
         "witness": f"{WITNESS_POOL} synthetic witnesses per rank (seeds {WITNESS_POOL}*rank ..), generated on the device (hg_bfv_witness_generate) and kept in pinned "
                    "host memory: slot k proves witness k in the resident region, every slot cycles through all of them in the end-to-end region",
         "cache": "working set ~4 GB per proof >> 126 MB L2, no explicit flush between steps",
+        "harness": "python gc paused inside the timed regions (the caller in production is Rust)",
     }
 
 
@@ -309,11 +311,14 @@ def measure_sharded(api, np, torch, dist, slot, host_w, steps, warmup, rank, wor
 
     for _ in range(max(warmup, 3) + 10):
         step()
+    gc.collect()
+    gc.disable()   # a generation-2 collection of the harness's Python heap inside the loop cost 25 ms once per measurement (profiles/r2_experiments.md)
     barrier()
     w0 = time.perf_counter()
     for _ in range(steps):
         step()
     barrier()
+    gc.enable()
     t = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_sharded = 1000.0 * float(t[0]) / steps
@@ -430,6 +435,8 @@ def run_ours(args):
     # k). Every slot ends each proof with a stream synchronise, so the device is idle at both events; events on torch's current
     # stream between two device-wide synchronisations measure the device time of the whole region. Max over ranks.
     sampler = ClockSampler(local)
+    gc.collect()
+    gc.disable()   # re-enabled after the end-to-end region: the harness's garbage collector is not part of the product
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -464,6 +471,7 @@ def run_ours(args):
     for _ in range(n_lat):
         s0.e2e()
     e2e_latency_ms = 1000.0 * (time.perf_counter() - w0) / n_lat
+    gc.enable()
     s0.restore_resident()
 
     line = None
@@ -539,8 +547,8 @@ def run_ours(args):
     # ---- one proof over all GPUs (BASELINE.json config 4), reported inside the same line
     shard = None
     if world > 1 and not args.no_shard:
-        shared = make_witness(args.config, 10_000, args.field)         # the same witness on every rank
-        shard = measure_sharded(api, np, torch, dist, s0, HostWitness(np, torch, *host_vectors(*shared, args.field)), max(10, args.steps), warm, rank, world, barrier)
+        shared_w = HostWitness(np, torch, *host_vectors(*make_witness(args.config, 10_000, args.field), args.field))   # the same witness on every rank
+        shard = measure_sharded(api, np, torch, dist, s0, shared_w, max(10, args.steps), warm, rank, world, barrier)
     if rank == 0:
         node_ch = node_chal_bytes(nv) * (1 if fid == 0 else 1)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
