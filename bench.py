@@ -431,6 +431,22 @@ def run_ours(args):
     barrier()
     latency_ms = e0.elapsed_time(e1) / n_lat
 
+    # ---- the same proof in INTERACTIVE mode (one device->host->device round trip per squeeze: what a caller-owned transcript that
+    # absorbs its messages gets); single GPU only, a few proofs, outside every timed region
+    interactive_ms = None
+    if world == 1:
+        def interactive():
+            tr_i = api.Keccak256Transcript(fid)
+            tr_i.squeeze_challenges(prover.ct0is_log2_size)
+            prover.circuit.prove_gkr(s0.out_claims, tr_i, api.MODE_INTERACTIVE)
+            return tr_i
+        same_bytes = interactive().into_proof() == tr.into_proof()
+        w0 = time.perf_counter()
+        for _ in range(3):
+            interactive()
+        interactive_ms = {"single_proof_latency_ms": 1000.0 * (time.perf_counter() - w0) / 3, "bytes_equal_prefetch": same_bytes,
+                          "note": "HG_MODE_INTERACTIVE: one round trip per challenge (1 534 per proof), sequential per-layer launches"}
+
     # ---- timed region: exactly K steps; a step = one batch of B independent proofs, one per in-flight slot (slot k proves witness
     # k). Every slot ends each proof with a stream synchronise, so the device is idle at both events; events on torch's current
     # stream between two device-wide synchronisations measure the device time of the whole region. Max over ranks.
@@ -559,7 +575,7 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * (n_in_bytes + node_ch + 4096)),
                         "d2h_bytes_per_step": int(B * proof_len * 2), "single_proof_latency_ms": e2e_latency_ms},
                 "gpu_launches": int(launches_per_proof * args.steps * B), "gpu_launches_per_proof": int(launches_per_proof),
-                "single_proof_latency_ms": latency_ms, "wall_ms_per_step": wall_ms / args.steps, "proof_bytes": proof_len, "spin_up_steps": spin_up, "witness_gen_ms_per_witness": witness_gen_ms,
+                "single_proof_latency_ms": latency_ms, "interactive_mode": interactive_ms, "wall_ms_per_step": wall_ms / args.steps, "proof_bytes": proof_len, "spin_up_steps": spin_up, "witness_gen_ms_per_witness": witness_gen_ms,
                 "host_phases_us": host_phases, "roofline": roofline, "cpu_baseline": cpu, "shard": shard}
     barrier()
     for s in slots:
