@@ -188,14 +188,20 @@ template <class FP> struct TreeR0Args {
     int nvec, nxb;
     VecRange own;
 };
+// The two product trees of a node (read / write sets over R rows, init / final sets over M entries) are independent: step k of both
+// goes into ONE launch (blocks [0, nblk_a) work for tree a, the rest for tree b), so the short launches of the small tree disappear
+// into those of the large one (nblk_a = gridDim.x: a single tree).
 template <class FP, bool TWO>
-__global__ void __launch_bounds__(HG_FUSED_BLOCK, FP::FUSED_MIN_BLOCKS) k_tree_up_r0(const TreeR0Args<FP> a) {
+__global__ void __launch_bounds__(HG_FUSED_BLOCK, FP::FUSED_MIN_BLOCKS) k_tree_up_r0(const TreeR0Args<FP> a_first, const TreeR0Args<FP> a_second, unsigned nblk_a) {
     typedef typename FP::B B;
     typedef typename FP::X X;
-    const int i = blockIdx.x % a.nvec, xb = blockIdx.x / a.nvec;
+    const bool second = blockIdx.x >= nblk_a;
+    const TreeR0Args<FP>& a = second ? a_second : a_first;
+    const unsigned bid = blockIdx.x - (second ? nblk_a : 0u);
+    const int i = bid % a.nvec, xb = bid / a.nvec;
     const size_t q = a.q;
-    X* myA = a.partA + (size_t)blockIdx.x * 4;
-    X* myB = TWO ? a.partB + (size_t)blockIdx.x * 4 : nullptr;
+    X* myA = a.partA + (size_t)bid * 4;
+    X* myB = TWO ? a.partB + (size_t)bid * 4 : nullptr;
     if (!vec_needed(a.own, i)) {
         if (threadIdx.x < 4) { myA[threadIdx.x] = FP::x_zero(); if (TWO) myB[threadIdx.x] = FP::x_zero(); }
         return;

@@ -1139,8 +1139,7 @@ template <class FP> class LassoNodeDev {
             HG_K(ctx_, KC_HASH, (size_t)m * M * (4 + 3 * sizeof(B)),
                  k_hash_if<FP><<<dim3((unsigned)((M + HG_BLOCK - 1) / HG_BLOCK), m), HG_BLOCK, 0, s>>>(d_subtables_.p, d_final_cts_.p, d_pos_sub_.p, d_pos_slot_.p,
                                                                                                        ch.d_chal(gt_idx), M, m, d_tree2_.p, own_range(2 * m)));
-            build_tree(ch, plan1, jobs, fuse);
-            build_tree(ch, plan2, jobs, fuse);
+            build_trees(ch, plan1, plan2, jobs, fuse);
             run_gp_batch(ch, wo, jobs);
         } else {
         if (fused_up)
@@ -1273,8 +1272,10 @@ template <class FP> class LassoNodeDev {
     }
     // product tree of one grand product (prover.rs:191-195, Layer::up :332-354); with `fuse` the builders also sample round 0 of
     // every layer that is streamed (gp_fused.cuh) and the layer jobs get the partial-sum regions
-    void build_tree(Channel<FP>& ch, const GpPlan& pl, std::vector<GpLayerJob<FP>>& jobs, bool fuse) {
-        cudaStream_t s = ctx_->stream;
+    // one fused builder step of a tree (k_tree_up_r0): its arguments, whether it builds two levels, its grid and algorithmic bytes
+    struct TreeStep { TreeR0Args<FP> a; bool two; unsigned nblk; size_t bytes; };
+    // the fused steps of one tree (layers whose round 0 is streamed); *cur_out = last complete layer afterwards
+    std::vector<TreeStep> plan_tree_fused(const GpPlan& pl, std::vector<GpLayerJob<FP>>& jobs, bool fuse, int* cur_out) {
         const int nvec = 2 * m_, nvars = pl.nvars;
         const size_t N = pl.N;
         std::vector<B*> layer(nvars);
@@ -1282,32 +1283,65 @@ template <class FP> class LassoNodeDev {
         for (int k = 1; k < nvars; k++) layer[k] = layer[k - 1] + (size_t)nvec * (N >> (k - 1));
         auto job_of = [&](int k) -> GpLayerJob<FP>& { return jobs[pl.job_begin + (size_t)(nvars - 2 - k)]; };  // sumcheck nv = nvars-1-k is job nv-1
         int cur = pl.level1_done ? 1 : 0;  // last layer that is complete
-        if (fuse) {
-            while (cur < nvars - 1 && gp_needs_r0(N, cur, nvars)) {
-                const bool two = cur + 2 <= nvars - 1 && gp_needs_r0(N, cur + 1, nvars);
-                const size_t len = N >> cur, q = two ? len / 4 : len / 2;
-                TreeR0Args<FP> a;
-                a.in = layer[cur]; a.out1 = layer[cur + 1]; a.out2 = two ? layer[cur + 2] : nullptr;
-                a.q = q; a.nvec = nvec; a.own = own_range(nvec);
-                a.nxb = fused_nxb(q / 2, nvec);
-                const size_t nblk = (size_t)a.nxb * nvec;
-                GpLayerJob<FP>& ja = job_of(cur);
-                a.cA = ja.coef; a.partA = r0_alloc(nblk);
-                ja.r0part = a.partA; ja.r0n = (int)nblk;
-                a.cB = nullptr; a.partB = nullptr;
-                if (two) {
-                    GpLayerJob<FP>& jb = job_of(cur + 1);
-                    a.cB = jb.coef; a.partB = r0_alloc(nblk);
-                    jb.r0part = a.partB; jb.r0n = (int)nblk;
-                }
-                // bytes: the layer read once, the layer(s) above written once
-                KernelScope ks(ctx_, KC_TREE, (size_t)nvec * (len + len / 2 + (two ? len / 4 : 0)) * sizeof(B));
-                if (two) k_tree_up_r0<FP, true><<<(unsigned)nblk, HG_FUSED_BLOCK, 0, s>>>(a);
-                else k_tree_up_r0<FP, false><<<(unsigned)nblk, HG_FUSED_BLOCK, 0, s>>>(a);
-                HG_LAUNCH_CHECK();
-                cur += two ? 2 : 1;
+        std::vector<TreeStep> steps;
+        while (fuse && cur < nvars - 1 && gp_needs_r0(N, cur, nvars)) {
+            const bool two = cur + 2 <= nvars - 1 && gp_needs_r0(N, cur + 1, nvars);
+            const size_t len = N >> cur, q = two ? len / 4 : len / 2;
+            TreeStep st;
+            TreeR0Args<FP>& a = st.a;
+            a.in = layer[cur]; a.out1 = layer[cur + 1]; a.out2 = two ? layer[cur + 2] : nullptr;
+            a.q = q; a.nvec = nvec; a.own = own_range(nvec);
+            a.nxb = fused_nxb(q / 2, nvec);
+            const size_t nblk = (size_t)a.nxb * nvec;
+            GpLayerJob<FP>& ja = job_of(cur);
+            a.cA = ja.coef; a.partA = r0_alloc(nblk);
+            ja.r0part = a.partA; ja.r0n = (int)nblk;
+            a.cB = nullptr; a.partB = nullptr;
+            if (two) {
+                GpLayerJob<FP>& jb = job_of(cur + 1);
+                a.cB = jb.coef; a.partB = r0_alloc(nblk);
+                jb.r0part = a.partB; jb.r0n = (int)nblk;
             }
+            st.two = two; st.nblk = (unsigned)nblk;
+            st.bytes = (size_t)nvec * (len + len / 2 + (two ? len / 4 : 0)) * sizeof(B);  // the layer read once, the layer(s) above written once
+            steps.push_back(st);
+            cur += two ? 2 : 1;
         }
+        *cur_out = cur;
+        return steps;
+    }
+    void launch_tree_step(const TreeStep& x, const TreeStep* y) {  // y: the step of the other tree that shares the launch (same `two`), or nullptr
+        cudaStream_t s = ctx_->stream;
+        KernelScope ks(ctx_, KC_TREE, x.bytes + (y ? y->bytes : 0));
+        const unsigned grid = x.nblk + (y ? y->nblk : 0);
+        if (x.two) k_tree_up_r0<FP, true><<<grid, HG_FUSED_BLOCK, 0, s>>>(x.a, y ? y->a : x.a, x.nblk);
+        else k_tree_up_r0<FP, false><<<grid, HG_FUSED_BLOCK, 0, s>>>(x.a, y ? y->a : x.a, x.nblk);
+        HG_LAUNCH_CHECK();
+    }
+    // both product trees of the node (prover.rs:191-195, Layer::up :332-354). With `fuse` the builders also sample round 0 of every
+    // layer that is streamed (gp_fused.cuh) and the layer jobs get the partial-sum regions; step k of both trees shares a launch.
+    void build_trees(Channel<FP>& ch, const GpPlan& pl1, const GpPlan& pl2, std::vector<GpLayerJob<FP>>& jobs, bool fuse) {
+        static const bool env_pair = getenv("HG_TREE_PAIR") ? atoi(getenv("HG_TREE_PAIR")) != 0 : true;
+        int cur1 = 0, cur2 = 0;
+        const std::vector<TreeStep> s1 = plan_tree_fused(pl1, jobs, fuse, &cur1), s2 = plan_tree_fused(pl2, jobs, fuse, &cur2);
+        size_t k2 = 0;
+        for (size_t k1 = 0; k1 < s1.size(); k1++) {
+            const TreeStep* mate = (env_pair && k2 < s2.size() && s2[k2].two == s1[k1].two) ? &s2[k2] : nullptr;
+            launch_tree_step(s1[k1], mate);
+            if (mate) k2++;
+        }
+        for (; k2 < s2.size(); k2++) launch_tree_step(s2[k2], nullptr);
+        build_tree_rest(ch, pl1, cur1);
+        build_tree_rest(ch, pl2, cur2);
+    }
+    // the levels above the fused part of one tree and its top
+    void build_tree_rest(Channel<FP>& ch, const GpPlan& pl, int cur) {
+        cudaStream_t s = ctx_->stream;
+        const int nvec = 2 * m_, nvars = pl.nvars;
+        const size_t N = pl.N;
+        std::vector<B*> layer(nvars);
+        layer[0] = pl.tree;
+        for (int k = 1; k < nvars; k++) layer[k] = layer[k - 1] + (size_t)nvec * (N >> (k - 1));
         for (int k = cur + 1; k < nvars;) {
             const size_t len_prev = N >> (k - 1);  // vector length of the layer this step reads
             if (len_prev <= (size_t)HG_TREE_TAIL && len_prev > 2) {  // the rest of the tree in one launch (shared memory)
