@@ -302,11 +302,16 @@ def measure_sharded(api, np, torch, dist, slot, host_w, steps, warmup, rank, wor
     claims = [(np.zeros((0, el), np.uint64), np.zeros(el, np.uint64)), (point, value)]
     ex = api.ShardExchange(ctx, prover.circuit.shard_words)
     last = {}
+    split_emit = os.environ.get("HG_SHARD_SPLIT_EMIT", "1") != "0" and world > 1
 
     def step():
         tr = api.Keccak256Transcript(slot.field_id)
         tr.squeeze_challenges(L)
-        ex.run(lambda r, w, ptr, cap: prover.circuit.prove_gkr_shard_dev(claims, tr, r, w, ptr, cap), prover.circuit.emit_shard_dev)
+        if split_emit:   # every rank serialises one range of the proof, rank 0 appends the gathered ranges
+            ex.run(lambda r, w, ptr, cap: prover.circuit.prove_gkr_shard_dev(claims, tr, r, w, ptr, cap), None,
+                   emit_part=prover.circuit.emit_shard_part_dev, transcript=tr)
+        else:
+            ex.run(lambda r, w, ptr, cap: prover.circuit.prove_gkr_shard_dev(claims, tr, r, w, ptr, cap), prover.circuit.emit_shard_dev)
         last["tr"] = tr
 
     for _ in range(max(warmup, 3) + 10):
@@ -344,7 +349,8 @@ def measure_sharded(api, np, torch, dist, slot, host_w, steps, warmup, rank, wor
                "bytes_equal": tr1.into_proof() == proof, "steps": steps,
                "partition": "generic node sumchecks by node (q % gpus), Lasso node by grand-product vectors, openings and counter slots; polynomialize replicated",
                "collective": f"one NCCL all_gather of {8 * prover.circuit.shard_words} bytes per rank per proof (message buffers only) + one merge kernel; "
-                             "rank 0 serialises (one D2H of the same size)",
+                             + ("every rank serialises one range of the proof (hg_gkr_emit_shard_part_dev), one all_gather of the byte ranges, rank 0 appends them"
+                                if split_emit else "rank 0 serialises (one D2H of the same size)"),
                "timing": "wall clock between barriers, max over ranks (the step ends with host-side serialisation on rank 0)"}
     barrier()
     d_ct.free()

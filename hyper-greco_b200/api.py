@@ -30,7 +30,7 @@ SYMBOLS = [
     "hg_lasso_pp_lookup_index", "hg_lasso_pp_memory_maps", "hg_lasso_pp_subtable_id", "hg_lasso_node_new", "hg_lasso_node_free",
     "hg_lasso_node_log2_input_size", "hg_lasso_node_device_bytes", "hg_lasso_node_prove", "hg_lasso_node_download_polys",
     "hg_lasso_node_num_chunks", "hg_lasso_node_timing", "hg_lasso_node_shard_words", "hg_lasso_node_prove_shard", "hg_lasso_node_emit_shard",
-    "hg_shard_merge", "hg_lasso_node_prove_shard_dev", "hg_lasso_node_emit_shard_dev", "hg_shard_merge_device", "hg_gkr_shard_words", "hg_gkr_prove_shard_dev", "hg_gkr_emit_shard_dev",
+    "hg_shard_merge", "hg_lasso_node_prove_shard_dev", "hg_lasso_node_emit_shard_dev", "hg_shard_merge_device", "hg_gkr_shard_words", "hg_gkr_prove_shard_dev", "hg_gkr_emit_shard_dev", "hg_gkr_emit_shard_part_dev", "hg_transcript_append_bytes",
     "hg_circuit_new_host", "hg_circuit_insert_lasso_host", "hg_gkr_verify", "hg_mle_eval_host", "hg_bfv_witness_generate", "hg_lasso_node_verify", "hg_sumcheck_prove", "hg_mle_eval_batch", "hg_ntt", "hg_bfv_configure", "hg_field_selftest",
     "hg_circuit_new", "hg_circuit_free", "hg_circuit_insert_input", "hg_circuit_insert_fft", "hg_circuit_insert_lasso", "hg_circuit_insert_vanilla",
     "hg_circuit_connect", "hg_circuit_evaluate", "hg_circuit_evaluate_host", "hg_circuit_node_value", "hg_gkr_prove", "hg_gkr_timing", "hg_gkr_num_challenges", "hg_gkr_num_inputs", "hg_gkr_num_input_claims",
@@ -130,6 +130,8 @@ def lib():
         L.hg_gkr_shard_words.restype = sz
         L.hg_gkr_prove_shard_dev.argtypes = [vp, sz, vp, vp, vp, vp, i32, i32, vp, sz, C.POINTER(sz)]
         L.hg_gkr_emit_shard_dev.argtypes = [vp, vp, sz]
+        L.hg_gkr_emit_shard_part_dev.argtypes = [vp, vp, sz, i32, i32, vp, sz, vp]
+        L.hg_transcript_append_bytes.argtypes = [vp, vp, sz]
         L.hg_circuit_new_host.argtypes = [i32, C.POINTER(vp)]
         L.hg_circuit_insert_lasso_host.argtypes = [vp, vp, sz, C.POINTER(i32)]
         L.hg_gkr_verify.argtypes = [vp, sz, vp, vp, vp, vp, vp]
@@ -350,6 +352,12 @@ class Keccak256Transcript:
         out = np.zeros(self._el, np.uint64)
         _chk(lib().hg_transcript_read_felt_ext(self.h, _p(out)))
         return out
+
+    def append_bytes(self, data: bytes):
+        """bytes serialised elsewhere (the per-rank parts of a sharded proof)"""
+        buf = np.frombuffer(data, np.uint8)
+        if buf.size:
+            _chk(lib().hg_transcript_append_bytes(self.h, _p(np.ascontiguousarray(buf)), buf.size))
 
     def into_proof(self) -> bytes:
         n = lib().hg_transcript_proof_len(self.h)
@@ -707,9 +715,15 @@ class ShardExchange:
         self.gathered = torch.zeros(self.world * cap_words, dtype=torch.int64, device=dev)
         self.merged = torch.zeros(cap_words, dtype=torch.int64, device=dev)
         self.stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+        self.PART_CAP = max(1 << 14, ((768 * 1024) // max(1, self.world) + 255) & ~255)
 
-    def run(self, prove_shard_dev, emit_shard_dev):
-        """prove_shard_dev(rank, world, d_out_ptr, cap) -> n_words;  emit_shard_dev(d_merged_ptr, n_words) -> result (rank 0 only)."""
+    PART_CAP = 1 << 18   # bytes one rank's part of the proof may take in the byte exchange (set per instance: ~768 KB / world; the whole proof is 119 KB for Goldilocks, 238 KB for BN254)
+
+    def run(self, prove_shard_dev, emit_shard_dev, emit_part=None, transcript=None):
+        """prove_shard_dev(rank, world, d_out_ptr, cap) -> n_words;  emit_shard_dev(d_merged_ptr, n_words) -> result (rank 0 only).
+        With emit_part(d_merged_ptr, n_words, part, nparts) -> bytes and rank 0's transcript, the serialisation is split over the
+        ranks as well: every rank serialises one range of the proof, the ranges are all-gathered (fixed-size byte buffers with a
+        length header) and rank 0 appends them in order."""
         import time
         timing = os.environ.get("HG_SHARD_TIMING") == "1"   # phase timing costs two extra synchronisations per proof
         t0 = time.perf_counter()
@@ -729,7 +743,32 @@ class ShardExchange:
             self.ctx.synchronize()
         t3 = time.perf_counter()
         res = None
-        if self.rank != 0:
+        if emit_part is not None and self.world > 1:
+            part = emit_part(self.merged.data_ptr(), n, self.rank, self.world)   # waits for the merge, serialises this rank's range
+            if len(part) + 8 > self.PART_CAP:
+                raise HgError("ShardExchange: a part of the proof exceeds the byte-exchange buffer")
+            if not hasattr(self, "bytes_host"):
+                self.bytes_host = self.torch.zeros(self.PART_CAP, dtype=self.torch.uint8).pin_memory()
+                self.bytes_dev = self.torch.zeros(self.PART_CAP, dtype=self.torch.uint8, device=self.part.device)
+                self.bytes_all = self.torch.zeros(self.world * self.PART_CAP, dtype=self.torch.uint8, device=self.part.device)
+                self.bytes_all_host = self.torch.zeros(self.world * self.PART_CAP, dtype=self.torch.uint8).pin_memory()
+            hb = self.bytes_host.numpy()
+            hb[:8] = np.frombuffer(np.uint64(len(part)).tobytes(), np.uint8)
+            hb[8:8 + len(part)] = np.frombuffer(part, np.uint8)
+            used = (8 + len(part) + 255) & ~255
+            with self.torch.cuda.stream(self.stream):
+                self.bytes_dev[:used].copy_(self.bytes_host[:used], non_blocking=True)
+                self.dist.all_gather_into_tensor(self.bytes_all, self.bytes_dev, group=self.group)
+                if self.rank == 0:
+                    self.bytes_all_host.copy_(self.bytes_all, non_blocking=True)
+            self.ctx.synchronize()
+            if self.rank == 0:
+                ab = self.bytes_all_host.numpy()
+                for r in range(self.world):
+                    ln = int(np.frombuffer(ab[r * self.PART_CAP: r * self.PART_CAP + 8].tobytes(), np.uint64)[0])
+                    transcript.append_bytes(ab[r * self.PART_CAP + 8: r * self.PART_CAP + 8 + ln].tobytes())
+                res = True
+        elif self.rank != 0:
             self.ctx.synchronize()
         else:
             res = emit_shard_dev(self.merged.data_ptr(), n)
@@ -986,6 +1025,15 @@ class Circuit:
         """Rank 0: serialise the merged buffer into the transcript given to prove_gkr_shard_dev; returns the input claims."""
         _chk(lib().hg_gkr_emit_shard_dev(self.h, C.c_void_p(d_merged_ptr), n_words))
         return self._read_input_claims()
+
+    def emit_shard_part_dev(self, d_merged_ptr: int, n_words: int, part: int, nparts: int) -> bytes:
+        """Every rank: the bytes of range `part` of `nparts` of the proof (hg_gkr_emit_shard_part_dev). Concatenated in order they are the
+        proof bytes that emit_shard_dev would have written; append them to rank 0's transcript (Keccak256Transcript.append_bytes)."""
+        cap = 1 << 19
+        buf = (C.c_uint8 * cap)()
+        n = C.c_size_t(0)
+        _chk(lib().hg_gkr_emit_shard_part_dev(self.h, C.c_void_p(d_merged_ptr), n_words, part, nparts, buf, cap, C.byref(n)))
+        return bytes(memoryview(buf)[: n.value])
 
     def free(self):
         if self.h:

@@ -46,6 +46,7 @@ struct ITranscript {
     virtual void write(const uint64_t* in) = 0;
     virtual void read(uint64_t* out) = 0;
     virtual const std::vector<uint8_t>& proof() const = 0;
+    virtual void append_raw(const uint8_t* b, size_t n) = 0;
     virtual size_t num_squeezed() const = 0;
     virtual void* raw() = 0;
 };
@@ -58,6 +59,7 @@ template <class FP> struct TranscriptT : ITranscript {
     void write(const uint64_t* in) override { t.write_felt_ext(FP::x_from_limbs(in)); }
     void read(uint64_t* out) override { FP::x_to_limbs(t.read_felt_ext(), out); }
     const std::vector<uint8_t>& proof() const override { return t.proof(); }
+    void append_raw(const uint8_t* b, size_t n) override { t.append_raw(b, n); }
     size_t num_squeezed() const override { return t.num_base_squeezed(); }
     void* raw() override { return &t; }
 };
@@ -196,6 +198,7 @@ struct ICircuit {
     virtual size_t prove_shard_dev(size_t n_claims, const size_t* lens, const uint64_t* pts, const uint64_t* vals, ITranscript* t, const WireOptions& wo, int rank, int world,
                                    void* d_out_words, size_t cap_words) = 0;
     virtual void emit_shard_dev(const void* d_merged, size_t n_words) = 0;
+    virtual void emit_shard_part_dev(const void* d_merged, size_t n_words, int part, int nparts, std::vector<uint8_t>& bytes) = 0;
 };
 template <class FP> struct CircuitT : ICircuit {
     typedef typename FP::B B;
@@ -275,6 +278,10 @@ template <class FP> struct CircuitT : ICircuit {
         if (n_words % XW) throw std::runtime_error("emit_shard: truncated message buffer");
         set_input_claims(c.emit_shard_dev((const X*)d_merged, n_words / XW));
     }
+    void emit_shard_part_dev(const void* d_merged, size_t n_words, int part, int nparts, std::vector<uint8_t>& bytes) override {
+        if (n_words % XW) throw std::runtime_error("emit_shard: truncated message buffer");
+        set_input_claims(c.emit_shard_part_dev((const X*)d_merged, n_words / XW, part, nparts, bytes));
+    }
     void prove(size_t n_claims, const size_t* lens, const uint64_t* pts, const uint64_t* vals, ITranscript* t, int mode, const WireOptions& wo) override {
         if (t->field_id != FP::FIELD_ID) throw std::runtime_error("transcript belongs to another field");
         set_input_claims(c.prove(*(Keccak256Transcript<FP>*)t->raw(), mode == HG_MODE_INTERACTIVE ? kModeInteractive : kModePrefetch, wo, output_claims(n_claims, lens, pts, vals)));
@@ -321,6 +328,7 @@ template <class FP> struct HostCircuitT : ICircuit {
     size_t shard_words() override { return 0; }
     size_t prove_shard_dev(size_t, const size_t*, const uint64_t*, const uint64_t*, ITranscript*, const WireOptions&, int, int, void*, size_t) override { no_device(); }
     void emit_shard_dev(const void*, size_t) override { no_device(); }
+    void emit_shard_part_dev(const void*, size_t, int, int, std::vector<uint8_t>&) override { no_device(); }
     void verify(size_t n_claims, const size_t* lens, const uint64_t* pts, const uint64_t* vals, ITranscript* t, const WireOptions& wo) override {
         if (t->field_id != FP::FIELD_ID) throw std::runtime_error("transcript belongs to another field");
         std::vector<typename GkrVerifierHost<FP>::Claim> oc(n_claims);
@@ -776,6 +784,9 @@ int hg_transcript_proof_copy(const hg_transcript* t, uint8_t* out, size_t cap) {
         memcpy(out, p.data(), p.size());
     })
 }
+int hg_transcript_append_bytes(hg_transcript* t, const uint8_t* bytes, size_t n) {
+    HG_TRY({ t->t->append_raw(bytes, n); })
+}
 size_t hg_transcript_num_squeezed(const hg_transcript* t) { return t->t->num_squeezed(); }
 
 // ---- preprocessing
@@ -957,6 +968,17 @@ int hg_gkr_emit_shard_dev(hg_circuit* c, const void* d_merged_words, size_t n_wo
     HG_TRY({
         circuit_use_device(c);
         c->c->emit_shard_dev(d_merged_words, n_words);
+    })
+}
+int hg_gkr_emit_shard_part_dev(hg_circuit* c, const void* d_merged_words, size_t n_words, int part, int nparts, uint8_t* out_bytes, size_t cap, size_t* out_len) {
+    HG_TRY({
+        circuit_use_device(c);
+        if (!out_bytes || !out_len) throw std::runtime_error("hg_gkr_emit_shard_part_dev: NULL output");
+        std::vector<uint8_t> bytes;
+        c->c->emit_shard_part_dev(d_merged_words, n_words, part, nparts, bytes);
+        if (bytes.size() > cap) throw std::runtime_error("hg_gkr_emit_shard_part_dev: output buffer too small");
+        if (!bytes.empty()) memcpy(out_bytes, bytes.data(), bytes.size());
+        *out_len = bytes.size();
     })
 }
 int hg_lasso_node_emit_shard(hg_lasso_node* node, const uint64_t* merged_words, size_t n_words, uint64_t* out_point, uint64_t* out_value) {

@@ -304,6 +304,12 @@ template <class FP> class GkrCircuitDev {
         ch_->emit_merged_device(d_merged, count);
         return collect();
     }
+    // the same with the serialisation split over the devices: device `part` returns the bytes of its range of the proof (the caller
+    // concatenates the ranges in order and appends them to rank 0's transcript); the input claims are valid on every device
+    std::vector<std::vector<InputClaim>> emit_shard_part_dev(const X* d_merged, size_t count, int part, int nparts, std::vector<uint8_t>& bytes) {
+        ch_->emit_merged_device_part(d_merged, count, part, nparts, bytes);
+        return collect();
+    }
     size_t shard_message_count() { plan(); return msg_budget_; }
 
   private:

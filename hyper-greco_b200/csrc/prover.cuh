@@ -302,6 +302,48 @@ template <class FP> class Channel {
         msg_ready_ = msg_cursor_;
         for (; deferred_done_ < deferred_.size(); deferred_done_++) deferred_[deferred_done_](*this);
     }
+    // ---- the serialisation of a sharded proof split over the devices too. The proof is the concatenation of what the serialisers
+    // write, in order, and every device walked the whole protocol, so device `part` of `nparts` serialises one contiguous range of
+    // serialisers into `out` and the ranges are concatenated by the caller. A range starts at the serialiser that initialises the
+    // claim of a sumcheck (the round records behind it carry state from one to the next). Outside its range a device still runs the
+    // plain serialisers (they move claim values between nodes) with their output discarded, and skips the round records, which are
+    // ~95 % of the arithmetic: afterwards the input claims are valid on every device.
+    void emit_merged_device_part(const X* d_merged, size_t count, int part, int nparts, std::vector<uint8_t>& out) {
+        if (count != msg_cursor_) throw std::runtime_error("Channel: merged message count does not match this proof");
+        if (nparts < 1 || part < 0 || part >= nparts) throw std::runtime_error("Channel: bad part index");
+        if (tr_->hooked()) throw std::runtime_error("Channel: a sharded proof is serialised into the library's own transcript");
+        HG_CUDA(cudaMemcpyAsync(h_msg_.p, d_merged, count * sizeof(X), cudaMemcpyDeviceToHost, ctx_->stream));
+        // cut points: serialiser i may start a range if it is a plain one directly followed by a round record; weights = round records
+        const size_t nd = deferred_.size();
+        std::vector<size_t> cuts{0};
+        std::vector<size_t> rounds_before(nd + 1, 0);
+        for (size_t i = 0; i < nd; i++) rounds_before[i + 1] = rounds_before[i] + (deferred_[i].exec ? 1 : 0);
+        for (size_t i = 1; i + 1 < nd; i++) if (!deferred_[i].exec && deferred_[i + 1].exec) cuts.push_back(i);
+        cuts.push_back(nd);
+        auto bound = [&](int q) -> size_t {  // first cut with at least q / nparts of the round records before it
+            if (q <= 0) return 0;
+            if (q >= nparts) return nd;
+            const size_t want = rounds_before[nd] * (size_t)q / (size_t)nparts;
+            for (size_t c : cuts) if (rounds_before[c] >= want) return c;
+            return nd;
+        };
+        const size_t a = bound(part), b = bound(part + 1);
+        HG_CUDA(cudaStreamSynchronize(ctx_->stream));
+        msg_ready_ = msg_cursor_;
+        Keccak256Transcript<FP> local, sink;
+        sink.set_discard(true);
+        for (size_t i = 0; i < nd; i++) {
+            const bool mine = i >= a && i < b;
+            active_tr_ = mine ? &local : &sink;
+            dry_ = !mine;
+            deferred_[i](*this);
+        }
+        dry_ = false;
+        active_tr_ = tr_;
+        deferred_done_ = nd;
+        out = local.proof();
+    }
+    bool dry() const { return dry_; }
     // replace the host copy of the messages by the merged one and serialise
     void emit_merged(const X* merged, size_t count) {
         if (count != msg_cursor_) throw std::runtime_error("Channel: merged message count does not match this proof");
@@ -325,7 +367,7 @@ template <class FP> class Channel {
     Keccak256Transcript<FP>* active_tr_ = nullptr;  // where serialisers write: tr_, or the side buffer
     cudaStream_t copy_stream_ = nullptr, copy_stream2_ = nullptr;
     cudaEvent_t ev_side_done_ = nullptr, ev_side_copied_ = nullptr, ev_early_copied_ = nullptr;
-    bool early_armed_ = false;
+    bool early_armed_ = false, dry_ = false;
     int side_state_ = 0;  // 0 none, 1 open, 2 closed (copy in flight), 3 serialised
     size_t side_def_begin_ = 0, side_def_end_ = 0, side_msg_begin_ = 0, side_msg_end_ = 0;
     std::vector<uint8_t> side_bytes_;
@@ -337,7 +379,7 @@ template <class FP> class Channel {
         std::function<void()> fn;
         void (*exec)(Channel&, const RoundOp&) = nullptr;
         RoundOp op;
-        void operator()(Channel& ch) const { if (exec) exec(ch, op); else fn(); }
+        void operator()(Channel& ch) const { if (exec) { if (!ch.dry()) exec(ch, op); } else fn(); }
     };
     std::vector<Deferred> deferred_;
     size_t deferred_done_ = 0;

@@ -167,6 +167,7 @@ template <class HF> class Keccak256Transcript {
     }
     void common_felt(const Base&) {}
     void write_felt(const Base& f) {
+        if (discard_) return;
         uint8_t b[HF::REPR_BYTES];
         HF::base_to_repr_le(f, b);
         const size_t o = stream_.size();
@@ -174,7 +175,14 @@ template <class HF> class Keccak256Transcript {
         uint8_t* dst = stream_.data() + o;
         for (int i = 0; i < HF::REPR_BYTES; i++) dst[i] = b[HF::REPR_BYTES - 1 - i];
     }
+    // a transcript that swallows what is written to it (Channel: closures replayed for their bookkeeping only)
+    void set_discard(bool d) { discard_ = d; }
+    void append_raw(const uint8_t* b, size_t n) {  // bytes serialised elsewhere (a sharded proof assembled from per-rank parts)
+        if (hooked_) throw TranscriptError("append_raw on a callback transcript");
+        stream_.insert(stream_.end(), b, b + n);
+    }
     void write_felt_ext(const Ext& e) {
+        if (discard_) return;
         if (hooked_) {
             uint64_t limbs[8] = {0};
             HF::x_to_limbs(e, limbs);
@@ -215,7 +223,7 @@ template <class HF> class Keccak256Transcript {
   private:
     std::vector<uint8_t> stream_, rd_;
     size_t pos_ = 0, n_squeezed_ = 0;
-    bool reading_ = false;
+    bool reading_ = false, discard_ = false;
     TranscriptHooks hooks_;
     bool hooked_ = false;
 };

@@ -110,6 +110,8 @@ int hg_transcript_write_felt_ext(hg_transcript* t, const uint64_t* ext);    /* t
 int hg_transcript_read_felt_ext(hg_transcript* t, uint64_t* out_ext);       /* transcript.rs:172-177 */
 size_t hg_transcript_proof_len(const hg_transcript* t);                     /* into_proof, transcript.rs:126-128 */
 int hg_transcript_proof_copy(const hg_transcript* t, uint8_t* out, size_t cap);
+/* append bytes that were serialised elsewhere (the per-rank parts of a sharded proof, hg_gkr_emit_shard_part_dev); not for callback transcripts */
+int hg_transcript_append_bytes(hg_transcript* t, const uint8_t* bytes, size_t n);
 size_t hg_transcript_num_squeezed(const hg_transcript* t);                  /* base-field squeezes so far */
 
 /* ---- Lasso preprocessing: LassoPreprocessing::preprocess::<C, M> over RangeLookup types (lasso/src/lasso.rs:527-627,
@@ -257,6 +259,11 @@ size_t hg_gkr_shard_words(hg_circuit* c);
 int hg_gkr_prove_shard_dev(hg_circuit* c, size_t n_output_claims, const size_t* point_lens, const uint64_t* points_ext, const uint64_t* values_ext, hg_transcript* t,
                            int rank, int world, void* d_out_words, size_t cap_words, size_t* n_words);
 int hg_gkr_emit_shard_dev(hg_circuit* c, const void* d_merged_words, size_t n_words);
+/* The serialisation split over the ranks as well (rank 0's host work is what bounds a sharded proof): after the merge EVERY rank calls
+ * this with part = its rank, nparts = world, and gets the bytes of one contiguous range of the proof; the ranges, concatenated in rank
+ * order (any exchange of < 256 KB), are appended to rank 0's transcript with hg_transcript_append_bytes. The input claims are valid
+ * on every rank afterwards. Bytes equal those of hg_gkr_emit_shard_dev. */
+int hg_gkr_emit_shard_part_dev(hg_circuit* c, const void* d_merged_words, size_t n_words, int part, int nparts, uint8_t* out_bytes, size_t cap, size_t* out_len);
 /* ---- BfvEncryptBlock::configure (bfv-gkr/src/sk_encryption_circuit.rs:86-293) in the library: builds the whole circuit of the BFV secret-key
  *      encryption proof into `c` with the calls above, node for node and connection for connection (a Rust caller that keeps its own
  *      `configure` binds hg_circuit_insert_* / hg_circuit_connect instead; the result is the same circuit). qis / k0is / r1_bounds /

@@ -803,6 +803,48 @@ def test_full_gkr_prove_sharded_equals_single_device(api, ctx, golden_dir, name,
     assert again == want
 
 
+@pytest.mark.parametrize("name,world", [("1024_1x27_65537", 2), ("4096_2x55_65537", 3), ("4096_2x55_65537", 8)])
+def test_full_gkr_prove_sharded_parts_concatenate_to_the_proof(api, ctx, golden_dir, name, world):
+    """hg_gkr_emit_shard_part_dev: the serialisation of a sharded proof split over the ranks. Every part is emitted from the merged
+    message buffer (here by the one emulated circuit, whose serialisers are those every rank holds); the parts, concatenated in
+    order and appended to rank 0's transcript, are the single-device proof, and the input claims are the same after every part."""
+    import torch
+    from hyper_greco_b200 import params
+    P = params.PARAMS[name]
+    io = np.load(os.path.join(golden_dir, f"circuit_io_{name}.npz"))
+    prover = api.BfvSkEncryptProver(ctx, P)
+    dev = prover.upload_inputs({k: io[k] for k in ("s", "e", "k1", "ais", "r1is", "r2is")})
+    d_ct = api.DeviceBuffer.from_numpy(ctx, io["ct0is"])
+    want, claims0 = prover.prove(dev, d_ct, 0)
+    L = prover.ct0is_log2_size
+    tr = api.Keccak256Transcript()
+    head = len(tr.into_proof())
+
+    def shard(r, w, ptr, cap):
+        t = tr if r == 0 else api.Keccak256Transcript()
+        point = t.squeeze_challenges(L)
+        value = api.mle_eval_batch(ctx, d_ct, 1, L, point)[0]
+        return prover.circuit.prove_gkr_shard_dev([(np.zeros((0, point.shape[1]), np.uint64), np.zeros(point.shape[1], np.uint64)), (point, value)], t, r, w, ptr, cap)
+
+    parts, claims = [], []
+
+    def emit_parts(d_merged, n):
+        for p in range(world):
+            parts.append(prover.circuit.emit_shard_part_dev(d_merged, n, p, world))
+            claims.append(prover.circuit._read_input_claims())
+        return None
+
+    _emulate_ranks_dev(api, ctx, world, prover.circuit.shard_words, shard, emit_parts)
+    assert head == 0 and all(len(x) > 0 for x in parts)
+    for x in parts:
+        tr.append_bytes(x)
+    assert tr.into_proof() == want
+    for cl in claims:
+        assert all((a[0] == b[0]).all() and (a[1] == b[1]).all() for ca, cb in zip(claims0, cl) for a, b in zip(ca, cb))
+    again, _ = prover.prove(dev, d_ct, 0)   # the unsharded path still works on the same circuit afterwards
+    assert again == want
+
+
 def test_full_gkr_prove_sharded_full_size(api, ctx, golden_dir):
     """BASELINE.json config 4 (n=32768 k=16 Goldilocks, one proof over 2/4/8 GPUs): 4 emulated ranks give the committed sha256."""
     from hyper_greco_b200 import params, witness
