@@ -86,6 +86,26 @@ def test_callback_transcript_forwards_every_primitive(api):
         api.CallbackTranscript(Broken()).squeeze_challenge()
 
 
+def test_transcript_append_bytes_assembles_a_proof_from_parts(api, golden_dir):
+    """hg_transcript_append_bytes: the parts of a sharded proof (hg_gkr_emit_shard_part_dev) are concatenated into rank 0's transcript.
+    Written elements and appended bytes share one stream, a proof cut anywhere and re-assembled reads back identically (the host
+    verifier accepts the golden proof rebuilt from three parts), and a callback transcript refuses (its bytes live with the caller)."""
+    import os
+    name = "1024_1x27_65537"
+    data = open(os.path.join(golden_dir, f"proof_goldilocks_lasso_node_{name}.bin"), "rb").read()
+    t = api.Keccak256Transcript(api.GOLDILOCKS)
+    c = t.squeeze_challenge()
+    t.write_felt_ext(c)
+    head = t.into_proof()
+    for part in (data[:1000], b"", data[1000:20000], data[20000:]):
+        t.append_bytes(part)
+    assert t.into_proof() == head + data
+    rd = api.Keccak256Transcript.from_proof(t.into_proof(), api.GOLDILOCKS)
+    assert (rd.read_felt_ext() == c).all()
+    with pytest.raises(api.HgError):
+        api.CallbackTranscript(api.Keccak256Transcript(api.GOLDILOCKS), api.GOLDILOCKS).append_bytes(b"\x00" * 16)
+
+
 @pytest.mark.parametrize("field,tag,io_file", [(0, "goldilocks", "circuit_io_{}.npz"), (1, "bn254", "circuit_io_bn254_{}.npz")])
 def test_host_verifier_accepts_golden_bfv_proofs_and_rejects_tampering(api, golden_dir, field, tag, io_file):
     """hg_gkr_verify + hg_mle_eval_host = BfvEncrypt::verify (sk_encryption_circuit.rs:462-517) in the PRODUCT, on the host: the
