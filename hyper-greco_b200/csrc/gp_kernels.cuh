@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(FP::GP_BLOCK, FP::GP_MIN_BLOCKS * (HG_BLOCK / 
 }
 
 template <class FP, class TIN, bool SCALE>
-__global__ void __launch_bounds__(FP::GP_BLOCK, FP::GP_MIN_BLOCKS * (HG_BLOCK / FP::GP_BLOCK)) k_gp_fold_multi(const GpItem<FP>* __restrict__ items, int nitems) {
+__global__ void __launch_bounds__(FP::GP_BLOCK, FP::GP_FOLD_CTAS) k_gp_fold_multi(const GpItem<FP>* __restrict__ items, int nitems) {
     typedef typename FP::X X;
     constexpr int NP = 3;
     const GpItem<FP> it = items[gp_find_item<FP>(items, nitems)];
